@@ -1,0 +1,160 @@
+/*
+ * mdeggs.h — C ABI of the B200 engine for the multiDEGGs differential-correlation hot path.
+ *
+ * One call (`mdeggs_run_omic`) replaces, for one omic layer, everything the reference does between
+ * "edges and node rows selected" (R/core_functions.R:319-336) and "best percentile chosen"
+ * (R/core_functions.R:471-495):
+ *
+ *   reference (all citations relative to the reference repo)            this ABI
+ *   ------------------------------------------------------------------  ------------------------------
+ *   assayData[rownames %in% nodes, ]            core_functions.R:336     node-row gather (kernel K1)
+ *   apply(category_vec, 1, median, na.rm=TRUE)  core_functions.R:353-365 out.median      (kernel K2)
+ *   quantile(as.matrix(assayData), p)           core_functions.R:718     out.cutoff      (kernel K3)
+ *   fit_lm_interaction()                        core_functions.R:1058-1074  out.p_edge/stat/coef (K4)
+ *   aov(B ~ A * metadata), row 3                core_functions.R:963-968    out.p_edge/stat/coef (K5)
+ *   MASS::rlm + sfsmisc::f.robftest(var = 3)    core_functions.R:914-925    out.p_edge/stat/iters (K6)
+ *   calc_pvalues_percentile() set logic         core_functions.R:723-779    out.cat/tot_edges   (K7)
+ *   p.adjust(bonferroni|BH) + count < 0.05      core_functions.R:1027-1035, 796-808  out.padj/sig_count (K8)
+ *   which.max(sig_pvalues)                      core_functions.R:475-495    out.best
+ *
+ * The R host keeps strings, factors, data.frames, message()/stop() texts; it calls
+ * this ABI through the `.Call` shim in multideggs_b200/r/src/rcall.c.  All functions are `extern "C"`,
+ * take plain pointers and sizes, never throw, and return 0 or a negative MDEGGS_E* code.
+ */
+#ifndef MDEGGS_H
+#define MDEGGS_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MDEGGS_ABI_VERSION 1
+#define MDEGGS_MAX_K 8 /* categories per run (the reference has no limit; >8 is rejected) */
+
+/* regression_method (core_functions.R:143) */
+#define MDEGGS_METHOD_LM 0
+#define MDEGGS_METHOD_RLM 1
+/* padj_method (core_functions.R:58-62, 1012, 1027) */
+#define MDEGGS_PADJ_NONE 0       /* "none": count raw p < 0.05 */
+#define MDEGGS_PADJ_BONFERRONI 1 /* "bonferroni" */
+#define MDEGGS_PADJ_BH 2         /* "BH" / "fdr" */
+#define MDEGGS_PADJ_HOST 3       /* "q.value", holm, hochberg, hommel, BY: raw p + masks returned, host adjusts */
+/* rlm covariance used by the Wald test (MASS::summary.rlm `method`) */
+#define MDEGGS_RLM_COV_XTWX 0
+#define MDEGGS_RLM_COV_XTX 1
+/* assay memory layout */
+#define MDEGGS_LAYOUT_COLMAJOR 0 /* R matrix genes x samples: element (g,s) at assay[g + s*ld]          */
+#define MDEGGS_LAYOUT_ROWMAJOR 1 /* genes x samples, sample fastest: element (g,s) at assay[g*ld + s]
+                                    (= the samples x genes column-major `x` of multiDEGGs_filter, fs:81) */
+/* where the caller's buffers live */
+#define MDEGGS_MEM_HOST 0
+#define MDEGGS_MEM_DEVICE 1 /* all problem/result pointers are device pointers on the context's first GPU */
+
+/* per-edge status (never an error of the call; the host decides what R would have done) */
+#define MDEGGS_EDGE_OK 0
+#define MDEGGS_EDGE_SINGULAR 1    /* solve(XtX) would throw (core_functions.R:1068) / rank-deficient design */
+#define MDEGGS_EDGE_NONFINITE 2   /* NA/NaN/Inf in either gene row (.lm.fit would error)              */
+#define MDEGGS_EDGE_NOT_CONVERGED 3 /* rlm: 20 IRLS iterations without convergence (R: warning only)  */
+#define MDEGGS_EDGE_ZERO_SCALE 4  /* rlm: MAD scale == 0                                              */
+
+/* error codes */
+#define MDEGGS_OK 0
+#define MDEGGS_EINVAL (-1)
+#define MDEGGS_ECUDA (-2)
+#define MDEGGS_ENCCL (-3)
+#define MDEGGS_ENOMEM (-4)
+#define MDEGGS_EUNSUPPORTED (-5)
+
+typedef struct mdeggs_ctx mdeggs_ctx;
+
+typedef struct mdeggs_problem {
+  const double* assay; /* G x n doubles, borrowed, never written                                        */
+  int64_t ld;          /* leading dimension (>= G col-major, >= n row-major)                            */
+  int32_t G, n;        /* rows (genes/features) and columns (samples) AFTER sample alignment            */
+  int32_t layout;      /* MDEGGS_LAYOUT_*                                                               */
+  int32_t mem;         /* MDEGGS_MEM_*                                                                  */
+  const int32_t* from; /* [E] 1-based row index of gene A (predictor), network order, already de-duplicated */
+  const int32_t* to;   /* [E] 1-based row index of gene B (response)                                    */
+  int64_t E;
+  const int32_t* group; /* [n] category code 1..K of each sample (as.integer(factor)); always HOST memory */
+  int32_t K;
+  const double* pct; /* [P] percentile_vector as the doubles R computed (seq(from,to,by)); always HOST memory */
+  int32_t P;
+  int32_t method;       /* MDEGGS_METHOD_*; ignored when K >= 3 (core_functions.R:963)                  */
+  int32_t padj;         /* MDEGGS_PADJ_*                                                                */
+  int32_t tested_coef;  /* rlm only: 1-based coefficient index of the Wald test; reference uses 3        */
+  int32_t rlm_cov_mode; /* MDEGGS_RLM_COV_*                                                             */
+} mdeggs_problem;
+
+/* Caller-allocated outputs; any pointer may be NULL (= not wanted, not computed/copied).
+ * Arrays indexed [P x E] have E fastest: x[p*E + e]. */
+typedef struct mdeggs_result {
+  double* cutoff;     /* [P]     type-7 quantile of the node-filtered matrix                            */
+  double* median;     /* [K x G] median[k*G + g]; NaN for rows that are not network nodes               */
+  double* p_edge;     /* [E]     raw p-value of the edge (independent of percentile/category)           */
+  double* stat;       /* [E]     t (K==2 lm), Wald F (rlm), interaction F (K>=3)                        */
+  double* coef;       /* [2K x E] coef[e*2K + j], R order: (Intercept), A, metadata2..K, A:metadata2..K  */
+  double* df;         /* [2]     numerator, denominator degrees of freedom                              */
+  int32_t* status;    /* [E]     MDEGGS_EDGE_*                                                          */
+  int32_t* iters;     /* [E]     rlm IRLS iterations (0 otherwise)                                      */
+  int8_t* cat;        /* [P x E] 0 = not tested at this percentile, c = specific to category c (1..K)   */
+  double* padj;       /* [P x E] adjusted p (NaN where cat == 0); not filled for PADJ_NONE/PADJ_HOST    */
+  int64_t* tot_edges; /* [P]     edges left at this percentile (core_functions.R:773-779)               */
+  int64_t* sig_count; /* [P]     sig_pvalues_count (core_functions.R:796-808); -1 where tot_edges == 0  */
+  int64_t* fail_count; /* [P]    tested edges whose fit failed hard (status SINGULAR/NONFINITE): in R such a
+                                 percentile is lost (cores > 1) or the whole omic errors (cores == 1), quirk q7 */
+  int32_t* best;      /* [1]     1-based index of the first maximum of sig_count over percentiles with
+                                 tot_edges > 0 and fail_count == 0 (core_functions.R:475-495); 0 if none   */
+  int8_t* cat_best;   /* [E]     cat row of the best percentile                                         */
+  double* padj_best;  /* [E]     padj row of the best percentile                                        */
+} mdeggs_result;
+
+typedef struct mdeggs_stats {
+  int64_t n_nodes;        /* rows kept by the node filter                                               */
+  int64_t unique_fits;    /* pair fits executed (== E)                                                  */
+  int64_t ref_equiv_tests; /* sum over percentiles of tot_edges: fits the reference would have run      */
+  int64_t kernel_launches; /* CUDA kernels launched by the last call (this library's + CUB's)           */
+  int64_t h2d_bytes, d2h_bytes;
+  int32_t fit_path;       /* 0 warp-per-edge streaming, 1 dense tile cross-moments, 2 rlm IRLS          */
+  int32_t n_ranks;
+  float ms_total;         /* device time of the whole pipeline (CUDA events on the engine stream)       */
+  float ms_h2d, ms_gather, ms_stats, ms_quantile, ms_fit, ms_tail, ms_collective, ms_percolate, ms_adjust, ms_d2h;
+  int64_t fit_bytes;      /* algorithmic bytes of the fit kernel: E * (16 n + 16)                        */
+} mdeggs_stats;
+
+/* Single process, n_dev >= 1 GPUs of this host (edges sharded, NCCL all-gather when n_dev > 1). */
+int mdeggs_create(mdeggs_ctx** out, const int* device_ids, int n_dev);
+/* One process per GPU (torchrun): `unique_id` = 128 bytes from mdeggs_nccl_unique_id() on rank 0,
+ * distributed to all ranks by the caller (torch.distributed broadcast). world == 1 ignores it. */
+int mdeggs_create_rank(mdeggs_ctx** out, int device_id, int rank, int world, const void* unique_id);
+int mdeggs_nccl_unique_id(void* out128);
+int mdeggs_destroy(mdeggs_ctx* ctx);
+
+/* Runs the whole path for one omic layer and waits for completion. With MDEGGS_MEM_DEVICE nothing
+ * crosses PCIe except `group`, `pct` (tiny) and one 8-byte count. */
+int mdeggs_run_omic(mdeggs_ctx* ctx, const mdeggs_problem* in, mdeggs_result* out);
+
+/* Feature construction of predict.multiDEGGs_filter (feature_selection_for_ML.R:406-445):
+ * out[s + j*n] = x[s + a[j]*ldx] / x[s + b[j]*ldx]  (or product), non-finite -> 0; x is n x G col-major,
+ * a/b are 0-based column indices. mem as above. */
+int mdeggs_pair_features(mdeggs_ctx* ctx, const double* x, int64_t ldx, int32_t n, const int32_t* a,
+                         const int32_t* b, int32_t n_pairs, int32_t ratio, int32_t mem, double* out);
+
+int mdeggs_last_stats(const mdeggs_ctx* ctx, mdeggs_stats* out);
+const char* mdeggs_last_error(const mdeggs_ctx* ctx);
+const char* mdeggs_strerror(int code);
+int mdeggs_abi_version(void);
+
+/* Scalar device-math twins exported for tests (host wrappers that launch a 1-thread kernel):
+ * Student-t lower tail as R's pt(), F upper tail as pf(lower.tail=FALSE), and the reference's
+ * 2*(1-pt(|t|,df)) expression. n values each. */
+int mdeggs_dev_pt(mdeggs_ctx* ctx, const double* x, const double* df, int64_t n, double* out);
+int mdeggs_dev_pf_upper(mdeggs_ctx* ctx, const double* f, const double* df1, const double* df2, int64_t n, double* out);
+int mdeggs_dev_p_two_sided_ref(mdeggs_ctx* ctx, const double* t, const double* df, int64_t n, double* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MDEGGS_H */

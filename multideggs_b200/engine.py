@@ -1,0 +1,177 @@
+"""ctypes binding of libmdeggs.so (the CUDA engine behind include/mdeggs.h).
+
+There is deliberately NO fallback: if the shared library is missing, cannot be loaded, or no CUDA
+device is usable, `Engine()` raises.  The library is built in-tree by `__graft_entry__.build()` /
+`python -m multideggs_b200.build` into multideggs_b200/csrc/libmdeggs.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Sequence
+
+import numpy as np
+
+from . import _abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libmdeggs.so")
+_LIB: C.CDLL | None = None
+
+# every symbol include/mdeggs.h declares (tests check the library exports all of them)
+ABI_SYMBOLS = (
+    "mdeggs_create", "mdeggs_create_rank", "mdeggs_nccl_unique_id", "mdeggs_destroy", "mdeggs_run_omic",
+    "mdeggs_pair_features", "mdeggs_last_stats", "mdeggs_last_error", "mdeggs_strerror", "mdeggs_abi_version",
+    "mdeggs_dev_pt", "mdeggs_dev_pf_upper", "mdeggs_dev_p_two_sided_ref",
+)
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+def load_library() -> C.CDLL:
+    """dlopen libmdeggs.so and declare prototypes. Raises EngineError if it is not built."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise EngineError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    vp, i, i64 = C.c_void_p, C.c_int, C.c_int64
+    L.mdeggs_create.argtypes = [C.POINTER(vp), C.POINTER(C.c_int), i]
+    L.mdeggs_create_rank.argtypes = [C.POINTER(vp), i, i, i, vp]
+    L.mdeggs_nccl_unique_id.argtypes = [vp]
+    L.mdeggs_destroy.argtypes = [vp]
+    L.mdeggs_run_omic.argtypes = [vp, C.POINTER(_abi.CProblem), C.POINTER(_abi.CResult)]
+    L.mdeggs_pair_features.argtypes = [vp, vp, i64, C.c_int32, vp, vp, C.c_int32, C.c_int32, C.c_int32, vp]
+    L.mdeggs_last_stats.argtypes = [vp, C.POINTER(_abi.CStats)]
+    L.mdeggs_last_error.argtypes = [vp]
+    L.mdeggs_last_error.restype = C.c_char_p
+    L.mdeggs_strerror.argtypes = [i]
+    L.mdeggs_strerror.restype = C.c_char_p
+    L.mdeggs_abi_version.restype = i
+    L.mdeggs_dev_pt.argtypes = [vp, vp, vp, i64, vp]
+    L.mdeggs_dev_pf_upper.argtypes = [vp, vp, vp, vp, i64, vp]
+    L.mdeggs_dev_p_two_sided_ref.argtypes = [vp, vp, vp, i64, vp]
+    for nm in ABI_SYMBOLS:
+        if getattr(L, nm).restype is C.c_int or getattr(L, nm).restype is None:
+            getattr(L, nm).restype = i
+    if L.mdeggs_abi_version() != _abi.ABI_VERSION:
+        raise EngineError("libmdeggs.so ABI version mismatch; rebuild")
+    _LIB = L
+    return L
+
+
+class Engine:
+    """Owns one `mdeggs_ctx` (device memory, streams, NCCL communicators). Not re-entrant.
+
+    Engine(devices=[0])                     single process, one or several GPUs of this host
+    Engine.for_rank(device, rank, world, unique_id)   one process per GPU (torchrun)
+    """
+
+    def __init__(self, devices: Sequence[int] = (0,), _handle: C.c_void_p | None = None):
+        self._lib = load_library()
+        self._ctx = C.c_void_p()
+        if _handle is not None:
+            self._ctx = _handle
+            return
+        arr = (C.c_int * len(devices))(*devices)
+        rc = self._lib.mdeggs_create(C.byref(self._ctx), arr, len(devices))
+        if rc != 0:
+            raise EngineError(f"mdeggs_create failed: {self._lib.mdeggs_strerror(rc).decode()}")
+
+    @classmethod
+    def for_rank(cls, device: int, rank: int, world: int, unique_id: bytes | None) -> "Engine":
+        lib = load_library()
+        h = C.c_void_p()
+        buf = C.create_string_buffer(unique_id, 128) if unique_id is not None else None
+        rc = lib.mdeggs_create_rank(C.byref(h), device, rank, world, buf)
+        if rc != 0:
+            raise EngineError(f"mdeggs_create_rank failed: {lib.mdeggs_strerror(rc).decode()}")
+        return cls(_handle=h)
+
+    @staticmethod
+    def nccl_unique_id() -> bytes:
+        lib = load_library()
+        buf = C.create_string_buffer(128)
+        rc = lib.mdeggs_nccl_unique_id(buf)
+        if rc != 0:
+            raise EngineError(f"mdeggs_nccl_unique_id failed: {lib.mdeggs_strerror(rc).decode()}")
+        return buf.raw
+
+    def close(self) -> None:
+        if self._ctx:
+            self._lib.mdeggs_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int, what: str) -> None:
+        if rc != 0:
+            msg = self._lib.mdeggs_last_error(self._ctx)
+            raise EngineError(f"{what}: {self._lib.mdeggs_strerror(rc).decode()}: {msg.decode() if msg else ''}")
+
+    # -- the hot path ---------------------------------------------------------------------------
+    def run_omic(self, problem: _abi.Problem, want: Sequence[str] = _abi.DEFAULT_WANT) -> dict[str, np.ndarray]:
+        """Host buffers in, host buffers out (numpy). One call = one omic layer."""
+        cprob = problem.to_c()
+        cres, arrays = _abi.alloc_result(problem.dims, tuple(want))
+        self._check(self._lib.mdeggs_run_omic(self._ctx, C.byref(cprob), C.byref(cres)), "mdeggs_run_omic")
+        return arrays
+
+    def run_omic_raw(self, cprob: _abi.CProblem, cres: _abi.CResult) -> None:
+        """Pre-marshalled structs (device or pinned-host pointers); used by bench.py."""
+        self._check(self._lib.mdeggs_run_omic(self._ctx, C.byref(cprob), C.byref(cres)), "mdeggs_run_omic")
+
+    def stats(self) -> dict:
+        st = _abi.CStats()
+        self._check(self._lib.mdeggs_last_stats(self._ctx, C.byref(st)), "mdeggs_last_stats")
+        return st.asdict()
+
+    def pair_features(self, x: np.ndarray, a: np.ndarray, b: np.ndarray, ratio: bool = True) -> np.ndarray:
+        """predict.multiDEGGs_filter feature construction (feature_selection_for_ML.R:423-431)."""
+        x = np.asfortranarray(x, dtype=np.float64)
+        a = np.ascontiguousarray(a, dtype=np.int32)
+        b = np.ascontiguousarray(b, dtype=np.int32)
+        n = x.shape[0]
+        out = np.empty((n, a.shape[0]), dtype=np.float64, order="F")
+        self._check(self._lib.mdeggs_pair_features(self._ctx, x.ctypes.data, max(n, 1), n, a.ctypes.data,
+                                                   b.ctypes.data, a.shape[0], int(ratio), _abi.MEM_HOST,
+                                                   out.ctypes.data), "mdeggs_pair_features")
+        return out
+
+    # -- device math twins (tests) --------------------------------------------------------------
+    def _vec(self, fn, *cols) -> np.ndarray:
+        cols = [np.ascontiguousarray(np.broadcast_to(np.asarray(c, dtype=np.float64), np.broadcast(*cols).shape)).ravel()
+                for c in cols]
+        out = np.empty_like(cols[0])
+        self._check(fn(self._ctx, *[c.ctypes.data for c in cols], cols[0].shape[0], out.ctypes.data), "dev math")
+        return out
+
+    def dev_pt(self, x, df) -> np.ndarray:
+        return self._vec(self._lib.mdeggs_dev_pt, x, df)
+
+    def dev_pf_upper(self, f, df1, df2) -> np.ndarray:
+        return self._vec(self._lib.mdeggs_dev_pf_upper, f, df1, df2)
+
+    def dev_p_two_sided_ref(self, t, df) -> np.ndarray:
+        return self._vec(self._lib.mdeggs_dev_p_two_sided_ref, t, df)
+
+
+_DEFAULT: Engine | None = None
+
+
+def default_engine() -> Engine:
+    """Lazily created process-wide engine (never before a fork: created on first use)."""
+    global _DEFAULT
+    if _DEFAULT is None:
+        env = os.environ.get("MDEGGS_GPUS")
+        devices = [int(t) for t in env.split(",")] if env else [0]
+        _DEFAULT = Engine(devices)
+    return _DEFAULT
