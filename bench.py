@@ -1,0 +1,409 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the multiDEGGs differential-correlation hot path on B200.
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA engine
+  python bench.py --impl reference --gpus N --steps K ...  # the CPU restatement of the reference (rank 0 only)
+
+A "step" is one whole-job pass of the hot path over one omic layer (node filter -> gather -> gene stats ->
+quantiles -> pair fits -> tails -> percolation -> BH -> best percentile) on synthetic data of BASELINE.json's
+config 3 (20,000 genes x 1,000 samples, 3 categories, built-in 53,035-edge network, BH).
+  value  : unique network edges tested per second, inputs already resident in HBM (device pointers).
+  e2e    : the same through the C-ABI call with HOST buffers (pinned), H2D + D2H inside the timed region.
+At N > 1 the main line is weak scaling over independent omic layers (one layer per GPU, the reference's
+`lapply` over omics, core_functions.R:214; no data-path collective); the edge-sharded + NCCL all-gather path
+of config 5 (4,000 x 2,000, all 7,998,000 pairs) is reported beside it under "also".
+One JSON line is printed by rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "gene-pair interaction tests/sec"
+UNIT = "unique pair tests/s"
+
+
+# ----------------------------------------------------------------------------------------------
+def _peaks() -> dict:
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            d = json.load(fh)
+        return {"hbm_gbs": float(d["hbm_gbs"]), "source": "MEASURED_PEAKS.json (of measured)"}
+    return {"hbm_gbs": 6650.0, "source": "B200_PROFILING.md fallback (of fallback)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def _workload(name: str, seed_offset: int = 0):
+    from multideggs_b200 import synth
+    if name == "cfg3":
+        return synth.cfg3(seed=20261019 + seed_offset)
+    if name == "cfg3-small":
+        return synth.cfg3(n_genes=4000, n_samples=200, max_edges=6000, seed=20261019 + seed_offset)
+    if name == "cfg5":
+        return synth.cfg5()
+    if name == "cfg5-small":
+        return synth.cfg5(n_features=600, n_samples=400)
+    raise SystemExit(f"unknown workload {name}")
+
+
+WANT = ("cutoff", "p_edge", "status", "tot_edges", "sig_count", "fail_count", "best", "cat_best", "padj_best")
+
+
+# ----------------------------------------------------------------------------------------------
+# reference arm: CPU restatement of the reference algorithm on the host cores
+# ----------------------------------------------------------------------------------------------
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pyoracle
+    name = args.workload or "cfg3"
+    wl = _workload(name)
+    prob = wl.problem()
+    E = prob.dims[2]
+    want = ("tot_edges", "sig_count", "best")  # no per-edge outputs => pure reference mode (refit per percentile)
+    cores = pyoracle.lib().mdeggs_oracle_threads()
+    for _ in range(max(args.warmup, 0)):
+        pyoracle.run_omic(prob, want, pyoracle.MODE_REFERENCE, 0)
+    t0 = time.perf_counter()
+    tests = 0
+    for _ in range(args.steps):
+        r = pyoracle.run_omic(prob, want, pyoracle.MODE_REFERENCE, 0)
+        tests += int(r["tot_edges"].sum())
+    dt = time.perf_counter() - t0
+    value = E * args.steps / dt
+    used = min(cores, len(prob.pct))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": name, "genes": int(prob.assay.shape[0]), "samples": int(prob.assay.shape[1]),
+                   "edges": int(E), "categories": int(prob.K), "percentiles": int(len(prob.pct)), "padj": "BH",
+                   "note": "R is not installed here: CPU restatement of the reference algorithm (oracle/), "
+                           "reference mode = every (percentile, category, edge) refitted, parallel over "
+                           "percentiles only like mclapply"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": "port",
+                         "sample": f"full {name} workload per step, {args.steps} steps, host threads available {cores}"},
+        "ref_equiv_tests_per_s": tests / dt,
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# CUDA arm
+# ----------------------------------------------------------------------------------------------
+def _device_problem(torch, prob, dev):
+    """Inputs resident in HBM: torch tensors own the memory, the C struct carries their pointers."""
+    from multideggs_b200 import _abi
+    a = prob.assay
+    assert a.flags.f_contiguous
+    t_assay = torch.from_numpy(np.ascontiguousarray(a.T)).to(dev)  # memory == column-major G x n
+    t_from = torch.from_numpy(np.ascontiguousarray(prob.from_idx, dtype=np.int32)).to(dev)
+    t_to = torch.from_numpy(np.ascontiguousarray(prob.to_idx, dtype=np.int32)).to(dev)
+    G, n, E, K, P = prob.dims
+    group = np.ascontiguousarray(prob.group, dtype=np.int32)
+    pct = np.ascontiguousarray(prob.pct, dtype=np.float64)
+    cprob = _abi.CProblem(t_assay.data_ptr(), G, G, n, _abi.LAYOUT_COLMAJOR, _abi.MEM_DEVICE, t_from.data_ptr(),
+                          t_to.data_ptr(), E, group.ctypes.data, K, pct.ctypes.data, P, prob.method, prob.padj,
+                          prob.tested_coef, prob.rlm_cov_mode)
+    outs = {}
+    cres = _abi.CResult()
+    for nm in WANT:
+        dt, shp = _abi.RESULT_FIELDS[nm]
+        tdt = {np.float64: torch.float64, np.int32: torch.int32, np.int8: torch.int8, np.int64: torch.int64}[dt]
+        t = torch.zeros(shp(G, n, E, K, P), dtype=tdt, device=dev)
+        outs[nm] = t
+        setattr(cres, nm, t.data_ptr())
+    keep = (t_assay, t_from, t_to, group, pct, outs)
+    return cprob, cres, keep
+
+
+def _host_problem(torch, prob):
+    """Pinned host buffers for the e2e leg."""
+    from multideggs_b200 import _abi
+    G, n, E, K, P = prob.dims
+    pin = lambda arr: torch.from_numpy(np.ascontiguousarray(arr)).pin_memory()
+    t_assay = pin(prob.assay.T)
+    t_from = pin(np.asarray(prob.from_idx, dtype=np.int32))
+    t_to = pin(np.asarray(prob.to_idx, dtype=np.int32))
+    group = np.ascontiguousarray(prob.group, dtype=np.int32)
+    pct = np.ascontiguousarray(prob.pct, dtype=np.float64)
+    cprob = _abi.CProblem(t_assay.data_ptr(), G, G, n, _abi.LAYOUT_COLMAJOR, _abi.MEM_HOST, t_from.data_ptr(),
+                          t_to.data_ptr(), E, group.ctypes.data, K, pct.ctypes.data, P, prob.method, prob.padj,
+                          prob.tested_coef, prob.rlm_cov_mode)
+    outs = {}
+    cres = _abi.CResult()
+    d2h = 0
+    for nm in WANT:
+        dt, shp = _abi.RESULT_FIELDS[nm]
+        tdt = {np.float64: torch.float64, np.int32: torch.int32, np.int8: torch.int8, np.int64: torch.int64}[dt]
+        t = torch.zeros(shp(G, n, E, K, P), dtype=tdt).pin_memory()
+        outs[nm] = t
+        d2h += t.numel() * t.element_size()
+        setattr(cres, nm, t.data_ptr())
+    h2d = t_assay.numel() * 8 + 2 * E * 4
+    return cprob, cres, (t_assay, t_from, t_to, group, pct, outs), h2d, d2h
+
+
+def _timed_steps(torch, eng, cprob, cres, steps, warmup, flush, dist_sync):
+    """W warm-up steps, then K steps; device time per step by CUDA events on the (legacy) default stream, which
+    orders against the engine's blocking streams; L2 flushed (untimed) between steps."""
+    for _ in range(warmup):
+        eng.run_omic_raw(cprob, cres)
+    dist_sync()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    stage = {}
+    t_wall0 = time.perf_counter()
+    for i in range(steps):
+        if flush is not None:
+            flush.add_(1.0)  # touches 2 x 256 MiB > 126 MB L2
+        ev[i][0].record()
+        eng.run_omic_raw(cprob, cres)
+        ev[i][1].record()
+        st = eng.stats()
+        for k, v in st.items():
+            if k.startswith("ms_"):
+                stage[k] = stage.get(k, 0.0) + v
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t_wall0
+    dist_sync()
+    ms = sum(a.elapsed_time(b) for a, b in ev)
+    return ms, wall, {k: v / steps for k, v in stage.items()}, st
+
+
+def run_cuda(args) -> None:
+    import torch
+    import multideggs_b200 as md
+    from multideggs_b200 import _abi
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus must equal WORLD_SIZE under torchrun")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=dev)
+
+    def dist_sync():
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(x: float) -> float:
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    name = args.workload or "cfg3"
+    wl = _workload(name, seed_offset=rank)  # N > 1: one independent omic layer per GPU (weak scaling)
+    prob = wl.problem()
+    G, n, E, K, P = prob.dims
+    eng = md.Engine([local])
+    flush = torch.zeros(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+
+    # ---- value: inputs resident in HBM ----
+    cprob, cres, keep = _device_problem(torch, prob, dev)
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms, wall, stage, st = _timed_steps(torch, eng, cprob, cres, args.steps, args.warmup, flush, dist_sync)
+    clocks = sampler.stop()
+    ms = max_over_ranks(ms)
+    value = world * E * args.steps / (ms * 1e-3)
+    tot_edges = keep[5]["tot_edges"].cpu().numpy()
+    ref_equiv = int(tot_edges.sum())
+    best = int(keep[5]["best"].cpu().numpy()[0])
+    sig = keep[5]["sig_count"].cpu().numpy()
+
+    # ---- e2e: host buffers through the C ABI ----
+    hprob, hres, hkeep, h2d, d2h = _host_problem(torch, prob)
+    for _ in range(args.warmup):
+        eng.run_omic_raw(hprob, hres)
+    dist_sync()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        eng.run_omic_raw(hprob, hres)
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    dist_sync()
+    e2e_value = world * E * args.steps / e2e_s
+    e2e_stage = {k: v for k, v in eng.stats().items() if k.startswith("ms_")}
+    assert int(hkeep[5]["best"].numpy()[0]) == best, "host and device legs disagree"
+
+    # ---- roofline of the dominant kernel (pair fit): algorithmic bytes E*(16n+16) / its CUDA-event time ----
+    peaks = _peaks()
+    fit_ms = stage["ms_fit"]
+    fit_bytes = E * (16 * n + 16)
+    achieved = fit_bytes / (fit_ms * 1e-3) / 1e9 if fit_ms > 0 else None
+    roofline = {"bound": "hbm", "kernel": "k_fit_stream", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": (achieved / peaks["hbm_gbs"]) if achieved else None, "traffic": None,
+                "peak_source": peaks["source"], "algorithmic_bytes_per_launch": fit_bytes,
+                "kernel_ms": fit_ms, "stage_ms": stage}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": name, "genes": G, "samples": n, "edges": E, "categories": K, "percentiles": P,
+                   "padj": "BH", "network_nodes": int(st["n_nodes"]),
+                   "parallelism": "1 GPU" if world == 1 else f"{world} independent omic layers, one per GPU (no collective)",
+                   "l2": "inputs (160 MB) exceed L2; plus a 256 MiB read-modify-write flush between steps (untimed)",
+                   "timing": "CUDA events per step on the default stream, max over ranks"},
+        "ref_equiv_tests_per_s": world * ref_equiv * args.steps / (ms * 1e-3),
+        "result_check": {"best_percentile_index": best, "sig_pairs": int(sig[best - 1]) if best > 0 else 0,
+                         "tests_the_reference_would_run": ref_equiv},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": 1e3 * e2e_s / args.steps, "stage_ms_last_step": e2e_stage,
+                "api": "mdeggs_run_omic (C ABI) with pinned host buffers"},
+        "gpu_launches": int(st["kernel_launches"]) * args.steps,
+        "clocks": clocks,
+        "roofline": roofline,
+    }
+
+    # ---- CPU baseline beside it (rank 0, N = 1): the oracle on the box's host cores ----
+    if rank == 0 and world == 1 and not args.no_cpu:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import pyoracle
+        cores = pyoracle.lib().mdeggs_oracle_threads()
+        t0 = time.perf_counter()
+        pyoracle.run_omic(prob, ("tot_edges", "sig_count", "best"), pyoracle.MODE_REFERENCE, 0)
+        dt_ref = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        r_u = pyoracle.run_omic(prob, ("p_edge", "tot_edges", "sig_count", "best"), pyoracle.MODE_UNIQUE, 0)
+        dt_uni = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": E / dt_ref, "unit": UNIT, "cores": min(cores, P), "kind": "port",
+                                "sample": f"one full {name} job, reference mode (refit per percentile, "
+                                          f"percentile-parallel like mclapply), {dt_ref:.2f} s; host threads {cores}",
+                                "unique_mode": {"value": E / dt_uni, "cores": cores, "seconds": dt_uni}}
+        line["result_check"]["oracle_best"] = int(r_u["best"][0])
+        line["result_check"]["oracle_sig_pairs"] = int(r_u["sig_count"][int(r_u["best"][0]) - 1]) if r_u["best"][0] > 0 else 0
+
+    # ---- also: config 5, edges sharded over the ranks + NCCL all-gather of p-values (strong scaling) ----
+    if not args.no_cfg5:
+        del cprob, cres, keep, hprob, hres, hkeep
+        torch.cuda.empty_cache()
+        name5 = "cfg5-small" if name.endswith("small") else "cfg5"
+        wl5 = _workload(name5)
+        prob5 = wl5.problem()
+        if world > 1:
+            uid = torch.zeros(128, dtype=torch.uint8, device=dev)
+            if rank == 0:
+                uid = torch.frombuffer(bytearray(md.Engine.nccl_unique_id()), dtype=torch.uint8).to(dev)
+            dist.broadcast(uid, 0)
+            eng5 = md.Engine.for_rank(local, rank, world, bytes(uid.cpu().numpy().tobytes()))
+        else:
+            eng5 = eng
+        c5, r5, keep5 = _device_problem(torch, prob5, dev)
+        ms5, _, stage5, st5 = _timed_steps(torch, eng5, c5, r5, max(2, args.steps // 4), 2, flush, dist_sync)
+        ms5 = max_over_ranks(ms5)
+        steps5 = max(2, args.steps // 4)
+        E5, n5 = prob5.dims[2], prob5.dims[1]
+        line["also"] = {"cfg5": {
+            "workload": name5, "edges": E5, "samples": n5, "features": prob5.dims[0], "scaling": "strong",
+            "parallelism": f"edges sharded over {world} GPU(s)" + ("; NCCL all-gather of p-values + status" if world > 1 else ""),
+            "value": E5 * steps5 / (ms5 * 1e-3), "unit": UNIT, "ms_per_step": ms5 / steps5, "steps": steps5,
+            "stage_ms": stage5, "fit_path": int(st5["fit_path"]),
+            "fit_GBps_algorithmic": (E5 / world) * (16 * n5 + 16) / (stage5["ms_fit"] * 1e-3) / 1e9 if stage5["ms_fit"] > 0 else None,
+            "best": int(keep5[5]["best"].cpu().numpy()[0])}}
+        if world > 1:
+            eng5.close()
+
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--workload", default=None, help="cfg3 (default) | cfg3-small | cfg5 | cfg5-small")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-cfg5", action="store_true", help="skip the config-5 'also' leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        if args.steps > 5:
+            args.steps = 5  # each step is a whole job of several seconds on the host cores
+        args.warmup = min(args.warmup, 1)
+        run_reference(args)
+    else:
+        run_cuda(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -58,6 +58,9 @@ extern "C" {
 #define MDEGGS_EDGE_NONFINITE 2   /* NA/NaN/Inf in either gene row (.lm.fit would error)              */
 #define MDEGGS_EDGE_NOT_CONVERGED 3 /* rlm: 20 IRLS iterations without convergence (R: warning only)  */
 #define MDEGGS_EDGE_ZERO_SCALE 4  /* rlm: MAD scale == 0                                              */
+#define MDEGGS_EDGE_SELFLOOP 5    /* exact fit: from == to (the built-in network has one self-loop) or a response
+                                     that is constant inside every category; R returns rounding noise / noise,
+                                     the engine returns p = 1, stat = 0 (documented deviation)              */
 
 /* error codes */
 #define MDEGGS_OK 0

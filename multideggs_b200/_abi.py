@@ -19,7 +19,7 @@ PADJ_NONE, PADJ_BONFERRONI, PADJ_BH, PADJ_HOST = 0, 1, 2, 3
 RLM_COV_XTWX, RLM_COV_XTX = 0, 1
 LAYOUT_COLMAJOR, LAYOUT_ROWMAJOR = 0, 1
 MEM_HOST, MEM_DEVICE = 0, 1
-EDGE_OK, EDGE_SINGULAR, EDGE_NONFINITE, EDGE_NOT_CONVERGED, EDGE_ZERO_SCALE = 0, 1, 2, 3, 4
+EDGE_OK, EDGE_SINGULAR, EDGE_NONFINITE, EDGE_NOT_CONVERGED, EDGE_ZERO_SCALE, EDGE_SELFLOOP = 0, 1, 2, 3, 4, 5
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)

@@ -1,0 +1,942 @@
+// mdeggs_engine.cu — context, pipeline orchestration and the extern "C" ABI of include/mdeggs.h.
+//
+// One `mdeggs_run_omic` call = one omic layer of get_diffNetworks_singleOmic (R/core_functions.R:258-529)
+// from "edges selected" to "best percentile chosen".  Pipeline per GPU (stream s_main unless noted):
+//   H2D -> K0 node filter -> K1 gather/transposition -> { K3 radix sort + quantiles on s_sort }
+//        -> K2 gene stats -> K4/K5/K6 pair fits on this rank's edge block -> tail probabilities
+//        -> [NCCL all-gather of p/status over NVLink when world > 1] -> K7 percolation masks
+//        -> K8 sort-once + per-(percentile,category) Bonferroni/BH + counts -> best percentile -> D2H
+// Every unique edge is fitted ONCE (its p-value does not depend on the percentile); the
+// reference refits it for each of the 13-15 percentiles.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+#include <string>
+#include <vector>
+
+#include "mdeggs.h"
+#include "mdeggs_kernels.cuh"
+#include "mdeggs_rlm.cuh"
+#include "nccl_dl.h"
+
+using namespace mdeggs;
+
+namespace {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p && cap) cudaFree(p);  // cap == 0 marks a borrowed caller pointer
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p && cap) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T>
+  T* as() const {
+    return reinterpret_cast<T*>(p);
+  }
+};
+
+enum Ev { EV_START, EV_H2D, EV_GATHER, EV_STATS, EV_FIT, EV_TAIL, EV_COLL, EV_PERC, EV_ADJ, EV_END, EV_Q0, EV_Q1, EV_COUNT };
+
+// scalar slots in the `scal` buffer (8-byte each)
+enum Scal { SC_NNODES = 0, SC_ERR = 1, SC_BEST = 2, SC_NVALID = 3, SC_COUNT = 8 };
+
+struct Shard {
+  int device = 0, rank = 0, world = 1;
+  cudaStream_t s_main = nullptr, s_sort = nullptr;
+  cudaEvent_t ev[EV_COUNT] = {};
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  nccl_comm_t comm = nullptr;
+  DevBuf assay, from, to, flags, excl, node_of_row, rowlist, scal, src_of_pos, pct, cutoff, D, keys, keys_sorted,
+      cub_tmp, cub_tmp2, mean, sxx, med, bad, stat, status, p_edge, coef, iters, act, counters, sortk, sortk2, idx,
+      idx2, ps, sa, sb, tile_cnt, tile_base, seg_n, tile_min, tile_carry, padj_best, cat_best, cat, padj, med_out,
+      small_out, rlm_ws;
+  void release_all() {
+    DevBuf* all[] = {&assay, &from, &to, &flags, &excl, &node_of_row, &rowlist, &scal, &src_of_pos, &pct, &cutoff,
+                     &D, &keys, &keys_sorted, &cub_tmp, &cub_tmp2, &mean, &sxx, &med, &bad, &stat, &status, &p_edge,
+                     &coef, &iters, &act, &counters, &sortk, &sortk2, &idx, &idx2, &ps, &sa, &sb, &tile_cnt,
+                     &tile_base, &seg_n, &tile_min, &tile_carry, &padj_best, &cat_best, &cat, &padj, &med_out,
+                     &small_out, &rlm_ws};
+    for (DevBuf* b : all) b->release();
+  }
+};
+
+}  // namespace
+
+struct mdeggs_ctx {
+  std::vector<Shard> shards;
+  std::string err;
+  mdeggs_stats stats;
+  int64_t launches = 0;
+  bool smem_attr_set = false;
+};
+
+namespace {
+
+void set_err(mdeggs_ctx* c, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  c->err = buf;
+}
+
+#define CU(call)                                                                               \
+  do {                                                                                         \
+    cudaError_t e_ = (call);                                                                   \
+    if (e_ != cudaSuccess) {                                                                   \
+      set_err(ctx, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));         \
+      return e_ == cudaErrorMemoryAllocation ? MDEGGS_ENOMEM : MDEGGS_ECUDA;                   \
+    }                                                                                          \
+  } while (0)
+
+#define NC(call)                                                                               \
+  do {                                                                                         \
+    int r_ = (call);                                                                           \
+    if (r_ != 0) {                                                                             \
+      NcclApi& api_ = nccl_api();                                                              \
+      set_err(ctx, "%s:%d %s: %s", __FILE__, __LINE__, #call,                                  \
+              api_.GetErrorString ? api_.GetErrorString(r_) : "nccl error");                  \
+      return MDEGGS_ENCCL;                                                                     \
+    }                                                                                          \
+  } while (0)
+
+#define LAUNCH(kernel, grid, block, smem, stream, ...)                                         \
+  do {                                                                                         \
+    kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                                \
+    ++ctx->launches;                                                                           \
+  } while (0)
+
+inline unsigned blocks_for(int64_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+
+int init_shard(mdeggs_ctx* ctx, Shard& s) {
+  CU(cudaSetDevice(s.device));
+  CU(cudaStreamCreate(&s.s_main));
+  CU(cudaStreamCreate(&s.s_sort));
+  for (int i = 0; i < EV_COUNT; ++i) CU(cudaEventCreate(&s.ev[i]));
+  CU(cudaEventCreateWithFlags(&s.ev_fork, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&s.ev_join, cudaEventDisableTiming));
+  CU(s.scal.ensure(SC_COUNT * 8));
+  return MDEGGS_OK;
+}
+
+struct HostLayout {
+  SegLayout L;
+  std::vector<int32_t> src_of_pos;
+};
+
+int build_layout(mdeggs_ctx* ctx, const mdeggs_problem* in, HostLayout& H) {
+  SegLayout& L = H.L;
+  memset(&L, 0, sizeof L);
+  L.K = in->K;
+  L.n = in->n;
+  for (int s = 0; s < in->n; ++s) {
+    int g = in->group[s];
+    if (g < 1 || g > in->K) {
+      set_err(ctx, "group[%d] = %d outside 1..K", s, g);
+      return MDEGGS_EINVAL;
+    }
+    L.cnt[g - 1]++;
+  }
+  int off = 0;
+  for (int k = 0; k < in->K; ++k) {
+    L.off[k] = off;
+    off += (L.cnt[k] + 3) & ~3;
+  }
+  L.off[in->K] = off;
+  L.npad = off;
+  H.src_of_pos.assign((size_t)(off > 0 ? off : 1), -1);
+  int fill[MDEGGS_MAX_K] = {0};
+  for (int s = 0; s < in->n; ++s) {  // stable: samples keep their order inside a category
+    int k = in->group[s] - 1;
+    H.src_of_pos[(size_t)L.off[k] + fill[k]++] = s;
+  }
+  return MDEGGS_OK;
+}
+
+template <int K>
+void launch_fit_stream(mdeggs_ctx* ctx, Shard& s, const SegLayout& L, int64_t e_lo, int64_t e_hi, double* coef) {
+  int64_t ne = e_hi - e_lo;
+  if (ne <= 0) return;
+  int64_t want_blocks = (ne + 7) / 8;  // 8 warps per CTA, one edge per warp per trip
+  int64_t cap = 148 * 8 * 16;          // persistent-ish: at most 16 waves of 8 CTAs/SM, warps loop
+  unsigned grid = (unsigned)(want_blocks < cap ? want_blocks : cap);
+  LAUNCH(k_fit_stream<K>, grid, 256, 0, s.s_main, s.D.as<double>(), L, s.from.as<int32_t>(), s.to.as<int32_t>(),
+         s.node_of_row.as<int32_t>(), s.mean.as<double>(), s.sxx.as<double>(), s.bad.as<uint8_t>(), e_lo, e_hi,
+         s.stat.as<double>(), s.status.as<int32_t>(), coef);
+}
+
+int copy_out(mdeggs_ctx* ctx, Shard& s, void* dst, const void* src, size_t bytes, int mem) {
+  if (!dst || bytes == 0) return MDEGGS_OK;
+  CU(cudaMemcpyAsync(dst, src, bytes, mem == MDEGGS_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
+                     s.s_main));
+  if (mem == MDEGGS_MEM_HOST) ctx->stats.d2h_bytes += (int64_t)bytes;
+  return MDEGGS_OK;
+}
+
+// ---- BH / Bonferroni over a block of percentiles (or the device-chosen best one) -----------------
+int run_adjust(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, int n_segments, int p0, const int32_t* best_dev,
+               unsigned long long* sig_dev, double* padj_out, int64_t padj_stride, int act_stride) {
+  const int64_t E = in->E;
+  const int ntiles = (int)((E + BH_TILE - 1) / BH_TILE);
+  BhArgs A;
+  A.ps = s.ps.as<double>();
+  A.sa = s.sa.as<int32_t>();
+  A.sb = s.sb.as<int32_t>();
+  A.sidx = s.idx2.as<int32_t>();
+  A.act = s.act.as<uint8_t>();
+  A.act_stride = act_stride;
+  A.E = E;
+  A.n_valid = s.scal.as<unsigned long long>() + SC_NVALID;
+  A.K = in->K;
+  A.P = in->P;
+  A.ntiles = ntiles;
+  A.p0 = p0;
+  A.best = best_dev;
+  dim3 grid((unsigned)ntiles, (unsigned)n_segments);
+  LAUNCH(k_bh_count, grid, BH_THREADS, 0, s.s_main, A, s.tile_cnt.as<int32_t>());
+  LAUNCH(k_bh_scan_tiles, n_segments, 256, 0, s.s_main, s.tile_cnt.as<int32_t>(), ntiles, s.tile_base.as<long long>(),
+         s.seg_n.as<long long>());
+  if (in->padj == MDEGGS_PADJ_BH) {
+    LAUNCH(k_bh_tilemin, grid, BH_THREADS, 0, s.s_main, A, s.tile_base.as<long long>(), s.seg_n.as<long long>(),
+           s.tile_min.as<double>());
+    LAUNCH(k_bh_suffix_min, n_segments, 256, 0, s.s_main, s.tile_min.as<double>(), ntiles, s.tile_carry.as<double>());
+  }
+  LAUNCH(k_bh_final, grid, BH_THREADS, 0, s.s_main, A, in->padj, s.tile_base.as<long long>(), s.seg_n.as<long long>(),
+         s.tile_carry.as<double>(), sig_dev, padj_out, padj_stride);
+  return MDEGGS_OK;
+}
+
+int run_shard_front(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const HostLayout& H, const void* assay_src,
+                    int src_device, int32_t* n_nodes_host) {
+  const SegLayout& L = H.L;
+  const int G = in->G, n = in->n;
+  const int64_t E = in->E;
+  CU(cudaSetDevice(s.device));
+  CU(cudaEventRecord(s.ev[EV_START], s.s_main));
+  // ---- inputs ----
+  const size_t assay_elems = (in->layout == MDEGGS_LAYOUT_COLMAJOR) ? (size_t)in->ld * (size_t)(n - 1) + (size_t)G
+                                                                   : (size_t)in->ld * (size_t)(G - 1) + (size_t)n;
+  const double* d_assay;
+  const int32_t *d_from, *d_to;
+  if (in->mem == MDEGGS_MEM_HOST) {
+    CU(s.assay.ensure(assay_elems * 8));
+    CU(s.from.ensure((size_t)E * 4 + 4));
+    CU(s.to.ensure((size_t)E * 4 + 4));
+    CU(cudaMemcpyAsync(s.assay.p, in->assay, assay_elems * 8, cudaMemcpyHostToDevice, s.s_main));
+    if (E > 0) {
+      CU(cudaMemcpyAsync(s.from.p, in->from, (size_t)E * 4, cudaMemcpyHostToDevice, s.s_main));
+      CU(cudaMemcpyAsync(s.to.p, in->to, (size_t)E * 4, cudaMemcpyHostToDevice, s.s_main));
+    }
+    ctx->stats.h2d_bytes += (int64_t)(assay_elems * 8 + (size_t)E * 8);
+    d_assay = s.assay.as<double>();
+    d_from = s.from.as<int32_t>();
+    d_to = s.to.as<int32_t>();
+  } else if (s.device == src_device) {
+    d_assay = in->assay;
+    d_from = in->from;
+    d_to = in->to;
+  } else {
+    CU(s.assay.ensure(assay_elems * 8));
+    CU(s.from.ensure((size_t)E * 4 + 4));
+    CU(s.to.ensure((size_t)E * 4 + 4));
+    CU(cudaMemcpyPeerAsync(s.assay.p, s.device, in->assay, src_device, assay_elems * 8, s.s_main));
+    if (E > 0) {
+      CU(cudaMemcpyPeerAsync(s.from.p, s.device, in->from, src_device, (size_t)E * 4, s.s_main));
+      CU(cudaMemcpyPeerAsync(s.to.p, s.device, in->to, src_device, (size_t)E * 4, s.s_main));
+    }
+    d_assay = s.assay.as<double>();
+    d_from = s.from.as<int32_t>();
+    d_to = s.to.as<int32_t>();
+  }
+  (void)assay_src;
+  // borrowed device pointers are stashed in the DevBuf slots without ownership for later stages
+  if (in->mem == MDEGGS_MEM_DEVICE && s.device == src_device) {
+    s.assay.release();
+    s.from.release();
+    s.to.release();
+    s.assay.p = (void*)d_assay;
+    s.from.p = (void*)d_from;
+    s.to.p = (void*)d_to;  // cap stays 0 => never freed by us
+  }
+  CU(s.src_of_pos.ensure(H.src_of_pos.size() * 4));
+  CU(cudaMemcpyAsync(s.src_of_pos.p, H.src_of_pos.data(), H.src_of_pos.size() * 4, cudaMemcpyHostToDevice, s.s_main));
+  CU(s.pct.ensure((size_t)(in->P > 0 ? in->P : 1) * 8));
+  if (in->P > 0) CU(cudaMemcpyAsync(s.pct.p, in->pct, (size_t)in->P * 8, cudaMemcpyHostToDevice, s.s_main));
+  CU(cudaEventRecord(s.ev[EV_H2D], s.s_main));
+  // ---- K0 node filter ----
+  CU(s.flags.ensure((size_t)G * 4));
+  CU(s.excl.ensure((size_t)G * 4));
+  CU(s.node_of_row.ensure((size_t)G * 4));
+  CU(s.rowlist.ensure((size_t)G * 4));
+  CU(cudaMemsetAsync(s.flags.p, 0, (size_t)G * 4, s.s_main));
+  CU(cudaMemsetAsync(s.scal.p, 0, SC_COUNT * 8, s.s_main));
+  if (E > 0) {
+    int64_t nb = (E + 255) / 256;
+    unsigned grid = (unsigned)(nb < 148 * 32 ? nb : 148 * 32);
+    LAUNCH(k_mark_nodes, grid, 256, 0, s.s_main, d_from, d_to, E, G, s.flags.as<int32_t>(),
+           s.scal.as<int32_t>() + 2 * SC_ERR);
+  }
+  size_t tmp_bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, s.flags.as<int32_t>(), s.excl.as<int32_t>(), G, s.s_main);
+  CU(s.cub_tmp.ensure(tmp_bytes));
+  CU(cub::DeviceScan::ExclusiveSum(s.cub_tmp.p, tmp_bytes, s.flags.as<int32_t>(), s.excl.as<int32_t>(), G, s.s_main));
+  ctx->launches += 2;
+  LAUNCH(k_build_rowlist, blocks_for(G, 256), 256, 0, s.s_main, s.flags.as<int32_t>(), s.excl.as<int32_t>(), G,
+         s.node_of_row.as<int32_t>(), s.rowlist.as<int32_t>(), s.scal.as<int32_t>() + 2 * SC_NNODES);
+  // the only mid-pipeline host read: node count (sizes D / the sort) and the index-range error flag
+  long long host_scal[2];
+  CU(cudaMemcpyAsync(host_scal, s.scal.p, 16, cudaMemcpyDeviceToHost, s.s_main));
+  CU(cudaStreamSynchronize(s.s_main));
+  if ((int32_t)host_scal[SC_ERR] != 0) {
+    set_err(ctx, "from/to contain an index outside 1..G");
+    return MDEGGS_EINVAL;
+  }
+  *n_nodes_host = (int32_t)host_scal[SC_NNODES];
+  return MDEGGS_OK;
+}
+
+int run_shard_main(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const mdeggs_result* out, const HostLayout& H,
+                   int32_t n_nodes) {
+  const SegLayout& L = H.L;
+  const int G = in->G, n = in->n, K = in->K, P = in->P;
+  const int64_t E = in->E;
+  CU(cudaSetDevice(s.device));
+  const int32_t* d_nn = s.scal.as<int32_t>() + 2 * SC_NNODES;
+  const size_t nn = (size_t)(n_nodes > 0 ? n_nodes : 1);
+  // ---- K1 gather ----
+  CU(s.D.ensure(nn * (size_t)L.npad * 8));
+  CU(s.keys.ensure(nn * (size_t)n * 8));
+  CU(s.keys_sorted.ensure(nn * (size_t)n * 8));
+  CU(s.mean.ensure(nn * K * 8));
+  CU(s.sxx.ensure(nn * K * 8));
+  CU(s.med.ensure(nn * K * 8));
+  CU(s.bad.ensure(nn));
+  CU(s.cutoff.ensure((size_t)(P > 0 ? P : 1) * 8));
+  if (n_nodes > 0) {
+    if (in->layout == MDEGGS_LAYOUT_COLMAJOR) {
+      dim3 grid((unsigned)((L.npad + 31) / 32), (unsigned)((n_nodes + 31) / 32));
+      LAUNCH(k_gather_colmajor, grid, 256, 0, s.s_main, s.assay.as<double>(), in->ld, s.rowlist.as<int32_t>(), d_nn,
+             s.src_of_pos.as<int32_t>(), L.npad, n, s.D.as<double>(), s.keys.as<unsigned long long>());
+    } else {
+      dim3 grid((unsigned)((L.npad + 255) / 256), (unsigned)n_nodes);
+      LAUNCH(k_gather_rowmajor, grid, 256, 0, s.s_main, s.assay.as<double>(), in->ld, s.rowlist.as<int32_t>(), d_nn,
+             s.src_of_pos.as<int32_t>(), L.npad, n, s.D.as<double>(), s.keys.as<unsigned long long>());
+    }
+  }
+  CU(cudaEventRecord(s.ev[EV_GATHER], s.s_main));
+  // ---- K3 on the side stream: sort all values once, read every percentile's cut-off ----
+  CU(cudaEventRecord(s.ev_fork, s.s_main));
+  CU(cudaStreamWaitEvent(s.s_sort, s.ev_fork, 0));
+  CU(cudaEventRecord(s.ev[EV_Q0], s.s_sort));
+  if (n_nodes > 0 && P > 0) {
+    size_t tb = 0;
+    int64_t items = (int64_t)n_nodes * n;
+    cub::DeviceRadixSort::SortKeys(nullptr, tb, s.keys.as<unsigned long long>(), s.keys_sorted.as<unsigned long long>(),
+                                   items, 0, 64, s.s_sort);
+    CU(s.cub_tmp2.ensure(tb));
+    CU(cub::DeviceRadixSort::SortKeys(s.cub_tmp2.p, tb, s.keys.as<unsigned long long>(),
+                                      s.keys_sorted.as<unsigned long long>(), items, 0, 64, s.s_sort));
+    ctx->launches += 10;
+    LAUNCH(k_quantiles, 1, 64, 0, s.s_sort, s.keys_sorted.as<unsigned long long>(), d_nn, n, s.pct.as<double>(), P,
+           s.cutoff.as<double>());
+  } else if (P > 0) {
+    LAUNCH(k_fill_f64, 1, 64, 0, s.s_sort, s.cutoff.as<double>(), (int64_t)P, nan(""));
+  }
+  CU(cudaEventRecord(s.ev[EV_Q1], s.s_sort));
+  CU(cudaEventRecord(s.ev_join, s.s_sort));
+  // ---- K2 gene stats ----
+  if (n_nodes > 0) {
+    size_t smem = (size_t)L.npad * 8;
+    int use_smem = smem <= 200 * 1024;
+    if (use_smem && smem > 48 * 1024 && !ctx->smem_attr_set) {
+      CU(cudaFuncSetAttribute(k_gene_stats<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      ctx->smem_attr_set = true;
+    }
+    LAUNCH(k_gene_stats<128>, (unsigned)n_nodes, 128, use_smem ? smem : 0, s.s_main, s.D.as<double>(), L, d_nn,
+           s.mean.as<double>(), s.sxx.as<double>(), s.med.as<double>(), s.bad.as<uint8_t>(), use_smem);
+  }
+  CU(cudaEventRecord(s.ev[EV_STATS], s.s_main));
+  // ---- pair fits on this rank's contiguous edge block ----
+  const int64_t chunk = (E + s.world - 1) / s.world;
+  const int64_t e_lo = (int64_t)s.rank * chunk < E ? (int64_t)s.rank * chunk : E;
+  const int64_t e_hi = e_lo + chunk < E ? e_lo + chunk : E;
+  const size_t epad = (size_t)(chunk * s.world > 0 ? chunk * s.world : 1);
+  const bool want_coef = out->coef != nullptr;
+  const bool is_rlm = (K == 2 && in->method == MDEGGS_METHOD_RLM);
+  CU(s.stat.ensure(epad * 8));
+  CU(s.status.ensure(epad * 4));
+  CU(s.p_edge.ensure(epad * 8));
+  if (want_coef) CU(s.coef.ensure(epad * 2 * K * 8));
+  if (is_rlm) CU(s.iters.ensure(epad * 4));
+  double* d_coef = want_coef ? s.coef.as<double>() : nullptr;
+  ctx->stats.fit_path = is_rlm ? 2 : 0;
+  if (e_hi > e_lo) {
+    if (is_rlm) {
+      int rc = launch_fit_rlm(ctx->launches, s.s_main, s.D.as<double>(), L, s.from.as<int32_t>(), s.to.as<int32_t>(),
+                              s.node_of_row.as<int32_t>(), s.mean.as<double>(), s.sxx.as<double>(),
+                              s.bad.as<uint8_t>(), e_lo, e_hi, in->tested_coef, in->rlm_cov_mode,
+                              s.stat.as<double>(), s.status.as<int32_t>(), d_coef, s.iters.as<int32_t>());
+      if (rc != 0) {
+        set_err(ctx, "rlm kernel configuration failed (n too large for shared memory?)");
+        return MDEGGS_EUNSUPPORTED;
+      }
+    } else {
+      switch (K) {
+        case 2: launch_fit_stream<2>(ctx, s, L, e_lo, e_hi, d_coef); break;
+        case 3: launch_fit_stream<3>(ctx, s, L, e_lo, e_hi, d_coef); break;
+        case 4: launch_fit_stream<4>(ctx, s, L, e_lo, e_hi, d_coef); break;
+        case 5: launch_fit_stream<5>(ctx, s, L, e_lo, e_hi, d_coef); break;
+        case 6: launch_fit_stream<6>(ctx, s, L, e_lo, e_hi, d_coef); break;
+        case 7: launch_fit_stream<7>(ctx, s, L, e_lo, e_hi, d_coef); break;
+        default: launch_fit_stream<8>(ctx, s, L, e_lo, e_hi, d_coef); break;
+      }
+    }
+  }
+  CU(cudaEventRecord(s.ev[EV_FIT], s.s_main));
+  double df1, df2;
+  int tail_mode;
+  if (K == 2) {
+    df1 = 1.0;
+    df2 = (double)(n - 4);
+    tail_mode = is_rlm ? 1 : 0;
+  } else {
+    int Ke = 0;
+    for (int k = 0; k < K; ++k) Ke += L.cnt[k] > 0;
+    df1 = (double)(Ke - 1);
+    df2 = (double)(n - 2 * Ke);
+    tail_mode = 1;
+  }
+  if (e_hi > e_lo)
+    LAUNCH(k_tail, blocks_for(e_hi - e_lo, 128), 128, 0, s.s_main, s.stat.as<double>(), s.status.as<int32_t>(), e_lo,
+           e_hi, tail_mode, df1, df2, s.p_edge.as<double>());
+  CU(cudaEventRecord(s.ev[EV_TAIL], s.s_main));
+  return MDEGGS_OK;
+}
+
+// NCCL all-gather of the per-rank edge blocks (p-values, status and whatever per-edge output was requested)
+int run_collective(mdeggs_ctx* ctx, const mdeggs_problem* in, const mdeggs_result* out) {
+  const int64_t E = in->E;
+  Shard& s0 = ctx->shards[0];
+  if (s0.world > 1 && E > 0) {
+    NcclApi& api = nccl_api();
+    const int64_t chunk = (E + s0.world - 1) / s0.world;
+    const bool is_rlm = (in->K == 2 && in->method == MDEGGS_METHOD_RLM);
+    NC(api.GroupStart());
+    for (Shard& s : ctx->shards) {
+      CU(cudaSetDevice(s.device));
+      char* pe = (char*)s.p_edge.p;
+      char* st = (char*)s.status.p;
+      NC(api.AllGather(pe + (size_t)s.rank * chunk * 8, pe, (size_t)chunk, NCCL_FLOAT64, s.comm, s.s_main));
+      NC(api.AllGather(st + (size_t)s.rank * chunk * 4, st, (size_t)chunk, NCCL_INT32, s.comm, s.s_main));
+      if (out->stat) {
+        char* x = (char*)s.stat.p;
+        NC(api.AllGather(x + (size_t)s.rank * chunk * 8, x, (size_t)chunk, NCCL_FLOAT64, s.comm, s.s_main));
+      }
+      if (out->coef) {
+        char* x = (char*)s.coef.p;
+        size_t per = (size_t)chunk * 2 * in->K;
+        NC(api.AllGather(x + (size_t)s.rank * per * 8, x, per, NCCL_FLOAT64, s.comm, s.s_main));
+      }
+      if (out->iters && is_rlm) {
+        char* x = (char*)s.iters.p;
+        NC(api.AllGather(x + (size_t)s.rank * chunk * 4, x, (size_t)chunk, NCCL_INT32, s.comm, s.s_main));
+      }
+    }
+    NC(api.GroupEnd());
+  }
+  for (Shard& s : ctx->shards) {
+    CU(cudaSetDevice(s.device));
+    CU(cudaEventRecord(s.ev[EV_COLL], s.s_main));
+  }
+  return MDEGGS_OK;
+}
+
+int run_shard_back(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const mdeggs_result* out, const HostLayout& H,
+                   int32_t n_nodes, bool emit) {
+  const int G = in->G, n = in->n, K = in->K, P = in->P;
+  const int64_t E = in->E;
+  (void)n;
+  CU(cudaSetDevice(s.device));
+  const int32_t* d_nn = s.scal.as<int32_t>() + 2 * SC_NNODES;
+  int32_t* d_best = s.scal.as<int32_t>() + 2 * SC_BEST;
+  const int act_stride = n_nodes > 0 ? n_nodes : 1;
+  const int Pn = P > 0 ? P : 1;
+  CU(cudaStreamWaitEvent(s.s_main, s.ev_join, 0));  // cut-offs ready
+  // counters: tot[P] fail[P] sig[P] sig_raw[P] (u64), then out: tot_out[P] sig_out[P] fail_out[P] (i64)
+  CU(s.counters.ensure((size_t)Pn * 8 * 7));
+  CU(cudaMemsetAsync(s.counters.p, 0, (size_t)Pn * 8 * 7, s.s_main));
+  unsigned long long* c_tot = s.counters.as<unsigned long long>();
+  unsigned long long* c_fail = c_tot + Pn;
+  unsigned long long* c_sig = c_tot + 2 * Pn;
+  unsigned long long* c_raw = c_tot + 3 * Pn;
+  long long* o_tot = (long long*)(c_tot + 4 * Pn);
+  long long* o_sig = o_tot + Pn;
+  long long* o_fail = o_tot + 2 * Pn;
+  CU(s.act.ensure((size_t)Pn * act_stride));
+  const bool dev_out = in->mem == MDEGGS_MEM_DEVICE;
+  int8_t* d_cat = nullptr;
+  if (out->cat && E > 0 && P > 0) {
+    if (dev_out && emit) d_cat = out->cat;
+    else {
+      CU(s.cat.ensure((size_t)P * E));
+      d_cat = s.cat.as<int8_t>();
+    }
+  }
+  if (n_nodes > 0 && P > 0) {
+    LAUNCH(k_actmask, blocks_for((int64_t)P * n_nodes, 256), 256, 0, s.s_main, s.med.as<double>(),
+           s.cutoff.as<double>(), d_nn, P, K, act_stride, s.act.as<uint8_t>());
+    if (E > 0)
+      LAUNCH(k_percolate, blocks_for(E, 256), 256, (size_t)3 * P * sizeof(unsigned), s.s_main, s.from.as<int32_t>(),
+             s.to.as<int32_t>(), s.node_of_row.as<int32_t>(), s.status.as<int32_t>(), s.p_edge.as<double>(),
+             s.act.as<uint8_t>(), act_stride, E, P, c_tot, c_fail, c_raw, d_cat);
+  }
+  CU(cudaEventRecord(s.ev[EV_PERC], s.s_main));
+  // ---- K8 ----
+  const bool dev_adjust = (in->padj == MDEGGS_PADJ_BONFERRONI || in->padj == MDEGGS_PADJ_BH);
+  double* d_padj = nullptr;
+  if (dev_adjust && E > 0 && P > 0 && n_nodes > 0) {
+    const int ntiles = (int)((E + BH_TILE - 1) / BH_TILE);
+    CU(s.sortk.ensure((size_t)E * 8));
+    CU(s.sortk2.ensure((size_t)E * 8));
+    CU(s.idx.ensure((size_t)E * 4));
+    CU(s.idx2.ensure((size_t)E * 4));
+    CU(s.ps.ensure((size_t)E * 8));
+    CU(s.sa.ensure((size_t)E * 4));
+    CU(s.sb.ensure((size_t)E * 4));
+    const size_t nseg = (size_t)P * K;
+    CU(s.tile_cnt.ensure(nseg * ntiles * 4));
+    CU(s.tile_base.ensure(nseg * ntiles * 8));
+    CU(s.tile_min.ensure(nseg * ntiles * 8));
+    CU(s.tile_carry.ensure(nseg * ntiles * 8));
+    CU(s.seg_n.ensure(nseg * 8));
+    LAUNCH(k_sort_keys, blocks_for(E, 256), 256, 0, s.s_main, s.p_edge.as<double>(), E,
+           s.sortk.as<unsigned long long>(), s.idx.as<int32_t>());
+    size_t tb = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, s.sortk.as<unsigned long long>(), s.sortk2.as<unsigned long long>(),
+                                    s.idx.as<int32_t>(), s.idx2.as<int32_t>(), E, 0, 64, s.s_main);
+    CU(s.cub_tmp.ensure(tb));
+    CU(cub::DeviceRadixSort::SortPairs(s.cub_tmp.p, tb, s.sortk.as<unsigned long long>(),
+                                       s.sortk2.as<unsigned long long>(), s.idx.as<int32_t>(), s.idx2.as<int32_t>(), E,
+                                       0, 64, s.s_main));
+    ctx->launches += 10;
+    LAUNCH(k_gather_sorted, blocks_for(E, 256), 256, 0, s.s_main, s.sortk2.as<unsigned long long>(),
+           s.idx2.as<int32_t>(), s.from.as<int32_t>(), s.to.as<int32_t>(), s.node_of_row.as<int32_t>(), E,
+           s.ps.as<double>(), s.sa.as<int32_t>(), s.sb.as<int32_t>(), s.scal.as<unsigned long long>() + SC_NVALID);
+    if (out->padj) {
+      if (dev_out && emit) d_padj = out->padj;
+      else {
+        CU(s.padj.ensure((size_t)P * E * 8));
+        d_padj = s.padj.as<double>();
+      }
+      int64_t tot = (int64_t)P * E;
+      LAUNCH(k_fill_f64, (unsigned)(blocks_for(tot, 256) < 148u * 16 ? blocks_for(tot, 256) : 148u * 16), 256, 0,
+             s.s_main, d_padj, tot, nan(""));
+    }
+    int rc = run_adjust(ctx, s, in, P * K, 0, nullptr, c_sig, d_padj, E, act_stride);
+    if (rc) return rc;
+  }
+  const unsigned long long* sig_src = dev_adjust ? c_sig : c_raw;
+  LAUNCH(k_select_best, 1, 32, 0, s.s_main, c_tot, c_fail, sig_src, P, in->padj == MDEGGS_PADJ_HOST ? 1 : 0, o_tot,
+         o_sig, o_fail, d_best);
+  // rows of the chosen percentile
+  const bool want_cat_best = out->cat_best && E > 0 && in->padj != MDEGGS_PADJ_HOST;
+  const bool want_padj_best = out->padj_best && E > 0 && dev_adjust && n_nodes > 0 && P > 0;
+  if (want_cat_best) {
+    CU(s.cat_best.ensure((size_t)E));
+    LAUNCH(k_cat_row, blocks_for(E, 256), 256, 0, s.s_main, s.from.as<int32_t>(), s.to.as<int32_t>(),
+           s.node_of_row.as<int32_t>(), s.act.as<uint8_t>(), act_stride, E, d_best, s.cat_best.as<int8_t>());
+  }
+  if (want_padj_best) {
+    CU(s.padj_best.ensure((size_t)E * 8));
+    LAUNCH(k_fill_f64, (unsigned)(blocks_for(E, 256) < 148u * 16 ? blocks_for(E, 256) : 148u * 16), 256, 0, s.s_main,
+           s.padj_best.as<double>(), E, nan(""));
+    int rc = run_adjust(ctx, s, in, K, 0, d_best, nullptr, s.padj_best.as<double>(), E, act_stride);
+    if (rc) return rc;
+  }
+  CU(cudaEventRecord(s.ev[EV_ADJ], s.s_main));
+  if (!emit) {
+    CU(cudaEventRecord(s.ev[EV_END], s.s_main));
+    return MDEGGS_OK;
+  }
+  // ---- outputs ----
+  const int mem = in->mem;
+  int rc;
+  if ((rc = copy_out(ctx, s, out->cutoff, s.cutoff.p, (size_t)P * 8, mem))) return rc;
+  if (out->median) {
+    CU(s.med_out.ensure((size_t)G * K * 8));
+    LAUNCH(k_scatter_median, blocks_for((int64_t)G * K, 256), 256, 0, s.s_main, s.med.as<double>(),
+           s.node_of_row.as<int32_t>(), G, K, s.med_out.as<double>());
+    if ((rc = copy_out(ctx, s, out->median, s.med_out.p, (size_t)G * K * 8, mem))) return rc;
+  }
+  if ((rc = copy_out(ctx, s, out->p_edge, s.p_edge.p, (size_t)E * 8, mem))) return rc;
+  if ((rc = copy_out(ctx, s, out->stat, s.stat.p, (size_t)E * 8, mem))) return rc;
+  if ((rc = copy_out(ctx, s, out->coef, s.coef.p, (size_t)E * 2 * K * 8, mem))) return rc;
+  if ((rc = copy_out(ctx, s, out->status, s.status.p, (size_t)E * 4, mem))) return rc;
+  if (out->iters) {
+    if (K == 2 && in->method == MDEGGS_METHOD_RLM) {
+      if ((rc = copy_out(ctx, s, out->iters, s.iters.p, (size_t)E * 4, mem))) return rc;
+    } else if (mem == MDEGGS_MEM_HOST) {
+      memset(out->iters, 0, (size_t)E * 4);
+    } else {
+      CU(cudaMemsetAsync(out->iters, 0, (size_t)E * 4, s.s_main));
+    }
+  }
+  if (out->cat && d_cat && d_cat != out->cat)
+    if ((rc = copy_out(ctx, s, out->cat, d_cat, (size_t)P * E, mem))) return rc;
+  if (out->padj && d_padj && d_padj != out->padj)
+    if ((rc = copy_out(ctx, s, out->padj, d_padj, (size_t)P * E * 8, mem))) return rc;
+  if ((rc = copy_out(ctx, s, out->tot_edges, o_tot, (size_t)P * 8, mem))) return rc;
+  if ((rc = copy_out(ctx, s, out->sig_count, o_sig, (size_t)P * 8, mem))) return rc;
+  if ((rc = copy_out(ctx, s, out->fail_count, o_fail, (size_t)P * 8, mem))) return rc;
+  if ((rc = copy_out(ctx, s, out->best, d_best, 4, mem))) return rc;
+  if (want_cat_best)
+    if ((rc = copy_out(ctx, s, out->cat_best, s.cat_best.p, (size_t)E, mem))) return rc;
+  if (want_padj_best)
+    if ((rc = copy_out(ctx, s, out->padj_best, s.padj_best.p, (size_t)E * 8, mem))) return rc;
+  if (out->df) {
+    double dfh[2];
+    if (K == 2) {
+      dfh[0] = 1.0;
+      dfh[1] = (double)(in->n - 4);
+    } else {
+      int Ke = 0;
+      for (int k = 0; k < K; ++k) Ke += H.L.cnt[k] > 0;
+      dfh[0] = (double)(Ke - 1);
+      dfh[1] = (double)(in->n - 2 * Ke);
+    }
+    if (mem == MDEGGS_MEM_HOST) {
+      out->df[0] = dfh[0];
+      out->df[1] = dfh[1];
+    } else {
+      CU(s.small_out.ensure(16));
+      CU(cudaMemcpyAsync(s.small_out.p, dfh, 16, cudaMemcpyHostToDevice, s.s_main));
+      CU(cudaStreamSynchronize(s.s_main));
+      CU(cudaMemcpyAsync(out->df, s.small_out.p, 16, cudaMemcpyDeviceToDevice, s.s_main));
+    }
+  }
+  CU(cudaEventRecord(s.ev[EV_END], s.s_main));
+  return MDEGGS_OK;
+}
+
+float ev_ms(cudaEvent_t a, cudaEvent_t b) {
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, a, b) != cudaSuccess) return 0.f;
+  return ms;
+}
+
+}  // namespace
+
+// =================================================================================================
+// extern "C" ABI
+// =================================================================================================
+extern "C" {
+
+int mdeggs_abi_version(void) { return MDEGGS_ABI_VERSION; }
+
+const char* mdeggs_strerror(int code) {
+  switch (code) {
+    case MDEGGS_OK: return "ok";
+    case MDEGGS_EINVAL: return "invalid argument";
+    case MDEGGS_ECUDA: return "CUDA error";
+    case MDEGGS_ENCCL: return "NCCL error";
+    case MDEGGS_ENOMEM: return "out of device memory";
+    case MDEGGS_EUNSUPPORTED: return "unsupported configuration";
+    default: return "unknown error";
+  }
+}
+
+const char* mdeggs_last_error(const mdeggs_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int mdeggs_create(mdeggs_ctx** out, const int* device_ids, int n_dev) {
+  if (!out || n_dev < 1 || !device_ids) return MDEGGS_EINVAL;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count < 1) return MDEGGS_ECUDA;
+  for (int i = 0; i < n_dev; ++i)
+    if (device_ids[i] < 0 || device_ids[i] >= count) return MDEGGS_EINVAL;
+  mdeggs_ctx* ctx = new mdeggs_ctx();
+  memset(&ctx->stats, 0, sizeof ctx->stats);
+  ctx->shards.resize((size_t)n_dev);
+  for (int i = 0; i < n_dev; ++i) {
+    ctx->shards[(size_t)i].device = device_ids[i];
+    ctx->shards[(size_t)i].rank = i;
+    ctx->shards[(size_t)i].world = n_dev;
+    int rc = init_shard(ctx, ctx->shards[(size_t)i]);
+    if (rc) {
+      delete ctx;
+      return rc;
+    }
+  }
+  if (n_dev > 1) {
+    NcclApi& api = nccl_api();
+    if (!api.load()) {
+      delete ctx;
+      return MDEGGS_ENCCL;
+    }
+    std::vector<nccl_comm_t> comms((size_t)n_dev);
+    if (api.CommInitAll(comms.data(), n_dev, device_ids) != 0) {
+      delete ctx;
+      return MDEGGS_ENCCL;
+    }
+    for (int i = 0; i < n_dev; ++i) ctx->shards[(size_t)i].comm = comms[(size_t)i];
+  }
+  *out = ctx;
+  return MDEGGS_OK;
+}
+
+int mdeggs_nccl_unique_id(void* out128) {
+  NcclApi& api = nccl_api();
+  if (!out128 || !api.load()) return MDEGGS_ENCCL;
+  nccl_unique_id id;
+  if (api.GetUniqueId(&id) != 0) return MDEGGS_ENCCL;
+  memcpy(out128, &id, 128);
+  return MDEGGS_OK;
+}
+
+int mdeggs_create_rank(mdeggs_ctx** out, int device_id, int rank, int world, const void* unique_id) {
+  if (!out || world < 1 || rank < 0 || rank >= world) return MDEGGS_EINVAL;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count < 1) return MDEGGS_ECUDA;
+  if (device_id < 0 || device_id >= count) return MDEGGS_EINVAL;
+  mdeggs_ctx* ctx = new mdeggs_ctx();
+  memset(&ctx->stats, 0, sizeof ctx->stats);
+  ctx->shards.resize(1);
+  Shard& s = ctx->shards[0];
+  s.device = device_id;
+  s.rank = rank;
+  s.world = world;
+  int rc = init_shard(ctx, s);
+  if (rc) {
+    delete ctx;
+    return rc;
+  }
+  if (world > 1) {
+    NcclApi& api = nccl_api();
+    if (!unique_id || !api.load()) {
+      delete ctx;
+      return MDEGGS_ENCCL;
+    }
+    nccl_unique_id id;
+    memcpy(&id, unique_id, 128);
+    if (api.CommInitRank(&s.comm, world, id, rank) != 0) {
+      delete ctx;
+      return MDEGGS_ENCCL;
+    }
+  }
+  *out = ctx;
+  return MDEGGS_OK;
+}
+
+int mdeggs_destroy(mdeggs_ctx* ctx) {
+  if (!ctx) return MDEGGS_OK;
+  for (Shard& s : ctx->shards) {
+    cudaSetDevice(s.device);
+    cudaDeviceSynchronize();
+    if (s.comm) nccl_api().CommDestroy(s.comm);
+    s.release_all();
+    for (int i = 0; i < EV_COUNT; ++i)
+      if (s.ev[i]) cudaEventDestroy(s.ev[i]);
+    if (s.ev_fork) cudaEventDestroy(s.ev_fork);
+    if (s.ev_join) cudaEventDestroy(s.ev_join);
+    if (s.s_main) cudaStreamDestroy(s.s_main);
+    if (s.s_sort) cudaStreamDestroy(s.s_sort);
+  }
+  delete ctx;
+  return MDEGGS_OK;
+}
+
+int mdeggs_run_omic(mdeggs_ctx* ctx, const mdeggs_problem* in, mdeggs_result* out) {
+  if (!ctx || !in || !out) return MDEGGS_EINVAL;
+  ctx->err.clear();
+  if (in->K < 2 || in->K > MDEGGS_MAX_K) {
+    set_err(ctx, "K = %d outside 2..%d", in->K, MDEGGS_MAX_K);
+    return MDEGGS_EINVAL;
+  }
+  if (in->G < 1 || in->n < 1 || in->E < 0 || in->P < 0 || !in->assay || !in->group || (in->P > 0 && !in->pct) ||
+      (in->E > 0 && (!in->from || !in->to)) || in->E > 2147483647LL) {
+    set_err(ctx, "bad problem dimensions or null pointer");
+    return MDEGGS_EINVAL;
+  }
+  if ((in->layout == MDEGGS_LAYOUT_COLMAJOR && in->ld < in->G) || (in->layout == MDEGGS_LAYOUT_ROWMAJOR && in->ld < in->n) ||
+      (in->layout != MDEGGS_LAYOUT_COLMAJOR && in->layout != MDEGGS_LAYOUT_ROWMAJOR)) {
+    set_err(ctx, "bad layout / leading dimension");
+    return MDEGGS_EINVAL;
+  }
+  if (in->K == 2 && in->method == MDEGGS_METHOD_RLM && (in->tested_coef < 1 || in->tested_coef > 4)) {
+    set_err(ctx, "tested_coef must be 1..4");
+    return MDEGGS_EINVAL;
+  }
+  if (in->n <= 2 * in->K) {
+    set_err(ctx, "n = %d leaves no residual degrees of freedom for K = %d", in->n, in->K);
+    return MDEGGS_EINVAL;
+  }
+  HostLayout H;
+  int rc = build_layout(ctx, in, H);
+  if (rc) return rc;
+  ctx->launches = 0;
+  memset(&ctx->stats, 0, sizeof ctx->stats);
+  const int src_device = ctx->shards[0].device;
+  int32_t n_nodes = 0;
+  for (Shard& s : ctx->shards) {
+    int32_t nn = 0;
+    rc = run_shard_front(ctx, s, in, H, in->assay, src_device, &nn);
+    if (rc) return rc;
+    n_nodes = nn;
+  }
+  for (Shard& s : ctx->shards) {
+    rc = run_shard_main(ctx, s, in, out, H, n_nodes);
+    if (rc) return rc;
+  }
+  rc = run_collective(ctx, in, out);
+  if (rc) return rc;
+  for (size_t i = 0; i < ctx->shards.size(); ++i) {
+    rc = run_shard_back(ctx, ctx->shards[i], in, out, H, n_nodes, i == 0);
+    if (rc) return rc;
+  }
+  for (Shard& s : ctx->shards) {
+    CU(cudaSetDevice(s.device));
+    CU(cudaStreamSynchronize(s.s_sort));
+    CU(cudaStreamSynchronize(s.s_main));
+  }
+  CU(cudaSetDevice(src_device));
+  // ---- stats ----
+  Shard& s0 = ctx->shards[0];
+  mdeggs_stats& st = ctx->stats;
+  st.n_nodes = n_nodes;
+  st.unique_fits = in->E;
+  st.kernel_launches = ctx->launches;
+  st.n_ranks = s0.world;
+  st.fit_bytes = in->E * (16LL * in->n + 16);
+  st.ms_total = ev_ms(s0.ev[EV_START], s0.ev[EV_END]);
+  st.ms_h2d = ev_ms(s0.ev[EV_START], s0.ev[EV_H2D]);
+  st.ms_gather = ev_ms(s0.ev[EV_H2D], s0.ev[EV_GATHER]);
+  st.ms_stats = ev_ms(s0.ev[EV_GATHER], s0.ev[EV_STATS]);
+  st.ms_quantile = ev_ms(s0.ev[EV_Q0], s0.ev[EV_Q1]);
+  st.ms_fit = ev_ms(s0.ev[EV_STATS], s0.ev[EV_FIT]);
+  st.ms_tail = ev_ms(s0.ev[EV_FIT], s0.ev[EV_TAIL]);
+  st.ms_collective = ev_ms(s0.ev[EV_TAIL], s0.ev[EV_COLL]);
+  st.ms_percolate = ev_ms(s0.ev[EV_COLL], s0.ev[EV_PERC]);
+  st.ms_adjust = ev_ms(s0.ev[EV_PERC], s0.ev[EV_ADJ]);
+  st.ms_d2h = ev_ms(s0.ev[EV_ADJ], s0.ev[EV_END]);
+  if (out->tot_edges && in->mem == MDEGGS_MEM_HOST)
+    for (int p = 0; p < in->P; ++p) st.ref_equiv_tests += out->tot_edges[p];
+  return MDEGGS_OK;
+}
+
+int mdeggs_last_stats(const mdeggs_ctx* ctx, mdeggs_stats* out) {
+  if (!ctx || !out) return MDEGGS_EINVAL;
+  *out = ctx->stats;
+  return MDEGGS_OK;
+}
+
+int mdeggs_pair_features(mdeggs_ctx* ctx, const double* x, int64_t ldx, int32_t n, const int32_t* a, const int32_t* b,
+                         int32_t n_pairs, int32_t ratio, int32_t mem, double* out) {
+  if (!ctx || !x || !out || n < 0 || n_pairs < 0 || ldx < n) return MDEGGS_EINVAL;
+  if (n == 0 || n_pairs == 0) return MDEGGS_OK;
+  Shard& s = ctx->shards[0];
+  CU(cudaSetDevice(s.device));
+  const size_t total = (size_t)n * n_pairs;
+  if (mem == MDEGGS_MEM_DEVICE) {
+    LAUNCH(k_pair_features, blocks_for((int64_t)total, 256), 256, 0, s.s_main, x, ldx, n, a, b, n_pairs, ratio, out);
+    CU(cudaStreamSynchronize(s.s_main));
+    return MDEGGS_OK;
+  }
+  // host: only the referenced columns cross PCIe
+  std::vector<int32_t> cols;
+  std::vector<int32_t> ra((size_t)n_pairs), rb((size_t)n_pairs);
+  {
+    std::vector<std::pair<int32_t, int32_t>> seen;
+    auto remap = [&](int32_t c) {
+      for (auto& pr : seen)
+        if (pr.first == c) return pr.second;
+      int32_t id = (int32_t)cols.size();
+      cols.push_back(c);
+      seen.push_back({c, id});
+      return id;
+    };
+    for (int j = 0; j < n_pairs; ++j) {
+      if (a[j] < 0 || b[j] < 0) return MDEGGS_EINVAL;
+      ra[(size_t)j] = remap(a[j]);
+      rb[(size_t)j] = remap(b[j]);
+    }
+  }
+  DevBuf dx, da, db, dout;
+  int rc = MDEGGS_OK;
+  do {
+    if (dx.ensure(cols.size() * (size_t)n * 8) != cudaSuccess || da.ensure((size_t)n_pairs * 4) != cudaSuccess ||
+        db.ensure((size_t)n_pairs * 4) != cudaSuccess || dout.ensure(total * 8) != cudaSuccess) {
+      rc = MDEGGS_ENOMEM;
+      break;
+    }
+    for (size_t c = 0; c < cols.size(); ++c)
+      cudaMemcpyAsync(dx.as<double>() + c * (size_t)n, x + (size_t)cols[c] * ldx, (size_t)n * 8, cudaMemcpyHostToDevice,
+                      s.s_main);
+    cudaMemcpyAsync(da.p, ra.data(), (size_t)n_pairs * 4, cudaMemcpyHostToDevice, s.s_main);
+    cudaMemcpyAsync(db.p, rb.data(), (size_t)n_pairs * 4, cudaMemcpyHostToDevice, s.s_main);
+    LAUNCH(k_pair_features, blocks_for((int64_t)total, 256), 256, 0, s.s_main, dx.as<double>(), (int64_t)n, n,
+           da.as<int32_t>(), db.as<int32_t>(), n_pairs, ratio, dout.as<double>());
+    cudaMemcpyAsync(out, dout.p, total * 8, cudaMemcpyDeviceToHost, s.s_main);
+    if (cudaStreamSynchronize(s.s_main) != cudaSuccess) rc = MDEGGS_ECUDA;
+  } while (0);
+  dx.release();
+  da.release();
+  db.release();
+  dout.release();
+  return rc;
+}
+
+static int dev_math(mdeggs_ctx* ctx, int which, const double* x, const double* a, const double* b, int64_t n,
+                    double* out) {
+  if (!ctx || !x || !a || !out || n < 0) return MDEGGS_EINVAL;
+  if (n == 0) return MDEGGS_OK;
+  Shard& s = ctx->shards[0];
+  CU(cudaSetDevice(s.device));
+  DevBuf dx, da, db, dout;
+  int rc = MDEGGS_OK;
+  if (dx.ensure((size_t)n * 8) != cudaSuccess || da.ensure((size_t)n * 8) != cudaSuccess ||
+      db.ensure((size_t)n * 8) != cudaSuccess || dout.ensure((size_t)n * 8) != cudaSuccess) {
+    rc = MDEGGS_ENOMEM;
+  } else {
+    cudaMemcpyAsync(dx.p, x, (size_t)n * 8, cudaMemcpyHostToDevice, s.s_main);
+    cudaMemcpyAsync(da.p, a, (size_t)n * 8, cudaMemcpyHostToDevice, s.s_main);
+    cudaMemcpyAsync(db.p, b ? b : a, (size_t)n * 8, cudaMemcpyHostToDevice, s.s_main);
+    LAUNCH(k_dev_math, blocks_for(n, 128), 128, 0, s.s_main, which, dx.as<double>(), da.as<double>(), db.as<double>(), n,
+           dout.as<double>());
+    cudaMemcpyAsync(out, dout.p, (size_t)n * 8, cudaMemcpyDeviceToHost, s.s_main);
+    if (cudaStreamSynchronize(s.s_main) != cudaSuccess) rc = MDEGGS_ECUDA;
+  }
+  dx.release();
+  da.release();
+  db.release();
+  dout.release();
+  return rc;
+}
+
+int mdeggs_dev_pt(mdeggs_ctx* ctx, const double* x, const double* df, int64_t n, double* out) {
+  return dev_math(ctx, 0, x, df, nullptr, n, out);
+}
+int mdeggs_dev_pf_upper(mdeggs_ctx* ctx, const double* f, const double* df1, const double* df2, int64_t n, double* out) {
+  return dev_math(ctx, 1, f, df1, df2, n, out);
+}
+int mdeggs_dev_p_two_sided_ref(mdeggs_ctx* ctx, const double* t, const double* df, int64_t n, double* out) {
+  return dev_math(ctx, 2, t, df, nullptr, n, out);
+}
+
+}  // extern "C"

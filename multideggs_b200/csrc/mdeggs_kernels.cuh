@@ -1,0 +1,813 @@
+// mdeggs_kernels.cuh — hand-written sm_100a kernels of the multiDEGGs hot path (see include/mdeggs.h).
+//
+// Data layout in HBM (all FP64):
+//   D[node][npad]   gene-major rows of the network-node genes; the samples of each category form one
+//                   contiguous segment, every segment padded to a multiple of 4 doubles (32 B) so that a
+//                   warp reads rows as coalesced 16-byte vectors; padding slots hold the segment mean, so
+//                   they contribute exactly 0 to every centred sum and no kernel needs a tail predicate.
+//   mean/sxx/med[node][K]   per gene, per category: mean, centred sum of squares, exact median.
+// Each kernel cites the reference lines it replaces.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cub/block/block_reduce.cuh>
+#include <cub/block/block_scan.cuh>
+
+#include "mdeggs.h"
+#include "mdeggs_math.cuh"
+
+namespace mdeggs {
+
+struct SegLayout {
+  int K, n, npad;
+  int off[MDEGGS_MAX_K + 1];  // padded segment offsets (doubles); off[K] == npad
+  int cnt[MDEGGS_MAX_K];      // samples per category
+};
+
+// order-preserving map double -> uint64; every NaN maps to the maximum key
+__device__ __forceinline__ unsigned long long dkey(double v) {
+  if (isnan(v)) return ~0ull;
+  unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double dkey_inv(unsigned long long k) {
+  unsigned long long b = (k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k;
+  return __longlong_as_double((long long)b);
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K0: node filter   (core_functions.R:333-336: nodes <- unique(c(from,to)); assayData[rownames %in% nodes,])
+// ------------------------------------------------------------------------------------------------
+__global__ void k_mark_nodes(const int32_t* __restrict__ from, const int32_t* __restrict__ to, int64_t E, int G,
+                             int32_t* __restrict__ flags, int32_t* __restrict__ err) {
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += stride) {
+    int a = from[e], b = to[e];
+    if (a < 1 || a > G || b < 1 || b > G) {
+      *err = 1;
+      continue;
+    }
+    if (!flags[a - 1]) flags[a - 1] = 1;
+    if (!flags[b - 1]) flags[b - 1] = 1;
+  }
+}
+
+__global__ void k_build_rowlist(const int32_t* __restrict__ flags, const int32_t* __restrict__ excl, int G,
+                                int32_t* __restrict__ node_of_row, int32_t* __restrict__ rowlist,
+                                int32_t* __restrict__ n_nodes) {
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= G) return;
+  int f = flags[g], pos = excl[g];
+  node_of_row[g] = f ? pos : -1;
+  if (f) rowlist[pos] = g;
+  if (g == G - 1) *n_nodes = pos + f;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1: gather + transposition  (replaces the per-pair `assayData[gene, ]` row look-ups, core_functions.R:880-881)
+//   in : R column-major G x n (gene fastest)  or row-major (sample fastest)
+//   out: D[node][pos] with category-contiguous samples; keys[node*n + s] sortable keys for the quantile sort
+// 32x32 smem tile, coalesced on both sides. Padding positions (src < 0) are written by k_gene_stats.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_gather_colmajor(const double* __restrict__ assay, int64_t ld,
+                                                         const int32_t* __restrict__ rowlist,
+                                                         const int32_t* __restrict__ n_nodes_p,
+                                                         const int32_t* __restrict__ src_of_pos, int npad, int n,
+                                                         double* __restrict__ D,
+                                                         unsigned long long* __restrict__ keys) {
+  __shared__ double tile[32][33];
+  const int n_nodes = *n_nodes_p;
+  const int node0 = blockIdx.y * 32, pos0 = blockIdx.x * 32;
+  if (node0 >= n_nodes) return;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const int node_r = node0 + tx;
+  const int64_t row = node_r < n_nodes ? rowlist[node_r] : -1;
+#pragma unroll
+  for (int j = ty; j < 32; j += 8) {
+    int pos = pos0 + j;
+    int s = pos < npad ? src_of_pos[pos] : -1;
+    double v = 0.0;
+    if (s >= 0 && row >= 0) v = __ldg(assay + row + (int64_t)s * ld);
+    tile[j][tx] = v;
+  }
+  __syncthreads();
+  const int pos_w = pos0 + tx;
+  const int s_w = pos_w < npad ? src_of_pos[pos_w] : -1;
+#pragma unroll
+  for (int i = ty; i < 32; i += 8) {
+    int node = node0 + i;
+    if (node < n_nodes && s_w >= 0) {
+      double v = tile[tx][i];
+      D[(size_t)node * npad + pos_w] = v;
+      keys[(size_t)node * n + s_w] = dkey(v);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_gather_rowmajor(const double* __restrict__ assay, int64_t ld,
+                                                         const int32_t* __restrict__ rowlist,
+                                                         const int32_t* __restrict__ n_nodes_p,
+                                                         const int32_t* __restrict__ src_of_pos, int npad, int n,
+                                                         double* __restrict__ D,
+                                                         unsigned long long* __restrict__ keys) {
+  const int n_nodes = *n_nodes_p;
+  const int node = blockIdx.y;
+  if (node >= n_nodes) return;
+  const int64_t row = rowlist[node];
+  for (int pos = blockIdx.x * blockDim.x + threadIdx.x; pos < npad; pos += gridDim.x * blockDim.x) {
+    int s = src_of_pos[pos];
+    if (s >= 0) {
+      double v = __ldg(assay + row * ld + s);
+      D[(size_t)node * npad + pos] = v;
+      keys[(size_t)node * n + s] = dkey(v);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: per-gene, per-category statistics
+//   median  — apply(category_vec, 1, stats::median, na.rm = TRUE)   core_functions.R:353-365
+//   mean, centred Sxx — the sufficient statistics of fit_lm_interaction / aov shared by every edge that
+//   touches the gene (core_functions.R:1058-1074, 966-968)
+// One CTA per gene, the row staged in shared memory; one warp per category. The exact median is an order
+// statistic found by 64-step bisection on the sortable key (no sort, no scratch).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long warp_select_key(const double* seg, int m, int kth, int lane) {
+  unsigned long long prefix = 0;
+  for (int bit = 63; bit >= 0; --bit) {
+    unsigned long long cand = prefix | (1ull << bit);
+    int c = 0;
+    for (int i = lane; i < m; i += 32) c += (dkey(seg[i]) < cand);
+    c = __reduce_add_sync(0xffffffffu, c);
+    if (c <= kth) prefix = cand;
+  }
+  return prefix;
+}
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) k_gene_stats(double* __restrict__ D, SegLayout L,
+                                                       const int32_t* __restrict__ n_nodes_p,
+                                                       double* __restrict__ mean, double* __restrict__ sxx,
+                                                       double* __restrict__ med, uint8_t* __restrict__ bad,
+                                                       int use_smem) {
+  extern __shared__ double srow[];
+  __shared__ int s_bad;
+  const int node = blockIdx.x;
+  if (node >= *n_nodes_p) return;
+  double* grow = D + (size_t)node * L.npad;
+  const double* r = grow;
+  if (threadIdx.x == 0) s_bad = 0;
+  if (use_smem) {
+    for (int k = 0; k < L.K; ++k)
+      for (int i = threadIdx.x; i < L.cnt[k]; i += THREADS) srow[L.off[k] + i] = grow[L.off[k] + i];
+    r = srow;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int k = warp; k < L.K; k += THREADS / 32) {
+    const double* seg = r + L.off[k];
+    const int m = L.cnt[k];
+    double s = 0.0, vmin = INFINITY, vmax = -INFINITY;
+    int nn = 0, nf = 0;
+    for (int i = lane; i < m; i += 32) {
+      double v = seg[i];
+      s += v;
+      vmin = fmin(vmin, v);
+      vmax = fmax(vmax, v);
+      nn += !isnan(v);
+      nf |= !isfinite(v);
+    }
+    s = warp_sum(s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      vmin = fmin(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+      vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+    }
+    nn = __reduce_add_sync(0xffffffffu, nn);
+    nf = __reduce_or_sync(0xffffffffu, nf);
+    double mu = m > 0 ? s / (double)m : nan("");
+    double d1 = 0.0, d2 = 0.0;
+    for (int i = lane; i < m; i += 32) {
+      double d = seg[i] - mu;
+      d1 += d;
+      d2 = fma(d, d, d2);
+    }
+    d1 = warp_sum(d1);
+    d2 = warp_sum(d2);
+    if (m > 0) {
+      double c = d1 / (double)m;  // first-order correction of the mean
+      mu += c;
+      d2 -= d1 * c;
+    }
+    if (m > 0 && vmin == vmax) {  // constant inside the category: exact zero spread (aliased column in R)
+      mu = vmin;
+      d2 = 0.0;
+    }
+    // exact median of the non-NaN values
+    double median = nan("");
+    if (nn > 0) {
+      if (nn & 1) {
+        median = dkey_inv(warp_select_key(seg, m, nn / 2, lane));
+      } else {
+        unsigned long long k1 = warp_select_key(seg, m, nn / 2 - 1, lane);
+        int c_le = 0;
+        unsigned long long nxt = ~0ull;
+        for (int i = lane; i < m; i += 32) {
+          unsigned long long kk = dkey(seg[i]);
+          c_le += (kk <= k1);
+          if (kk > k1 && kk < nxt) nxt = kk;
+        }
+        c_le = __reduce_add_sync(0xffffffffu, c_le);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          unsigned long long other = __shfl_xor_sync(0xffffffffu, nxt, o);
+          nxt = other < nxt ? other : nxt;
+        }
+        unsigned long long k2 = (c_le > nn / 2) ? k1 : nxt;
+        double a = dkey_inv(k1), b = dkey_inv(k2);
+        median = __ddiv_rn(__dadd_rn(a, b), 2.0);
+      }
+    }
+    if (lane == 0) {
+      mean[(size_t)node * L.K + k] = mu;
+      sxx[(size_t)node * L.K + k] = d2;
+      med[(size_t)node * L.K + k] = median;
+      if (nf) atomicOr(&s_bad, 1);
+    }
+    for (int i = L.off[k] + m + lane; i < L.off[k + 1]; i += 32) grow[i] = mu;  // padding := segment mean
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) bad[node] = (uint8_t)s_bad;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: type-7 quantiles of the whole node-filtered matrix from its sorted keys
+//   cut_off <- stats::quantile(as.matrix(assayData), prob = percentile, na.rm = TRUE)  core_functions.R:718
+// ------------------------------------------------------------------------------------------------
+__global__ void k_quantiles(const unsigned long long* __restrict__ sorted, const int32_t* __restrict__ n_nodes_p,
+                            int n, const double* __restrict__ pct, int P, double* __restrict__ cutoff) {
+  __shared__ long long sN;
+  if (threadIdx.x == 0) {
+    long long total = (long long)(*n_nodes_p) * n, lo = 0, hi = total;  // first index holding a NaN key
+    while (lo < hi) {
+      long long mid = (lo + hi) >> 1;
+      if (sorted[mid] == ~0ull) hi = mid;
+      else lo = mid + 1;
+    }
+    sN = lo;
+  }
+  __syncthreads();
+  const long long N = sN;
+  for (int p = threadIdx.x; p < P; p += blockDim.x) {
+    if (N <= 0) {
+      cutoff[p] = nan("");
+      continue;
+    }
+    double idx = __dadd_rn(1.0, __dmul_rn((double)(N - 1), pct[p]));
+    double lo = floor(idx), hi = ceil(idx);
+    long long ilo = (long long)lo, ihi = (long long)hi;
+    ilo = ilo < 1 ? 1 : ilo;
+    ihi = ihi > N ? N : ihi;
+    double q = dkey_inv(sorted[ilo - 1]);
+    double xh = dkey_inv(sorted[ihi - 1]);
+    if (idx > lo && xh != q) {
+      double h = __dsub_rn(idx, lo);
+      q = __dadd_rn(__dmul_rn(__dsub_rn(1.0, h), q), __dmul_rn(h, xh));
+    }
+    cutoff[p] = q;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4 / K5: streaming pair fit, one warp per edge
+//   K == 2 : fit_lm_interaction  (core_functions.R:1058-1074)  -> t statistic of the A:category coefficient
+//   K >= 3 : aov(B ~ A * metadata), row "A:metadata" (core_functions.R:966-968) -> interaction F statistic
+// With the per-gene statistics of K2 a pair needs only the K centred cross moments
+//   Sxy_k = sum_{i in k} (a_i - mean_a,k)(b_i - mean_b,k)
+// i.e. one pass over two rows (16 n bytes), two subtractions and one FMA per sample; the 4x4 (2K x 2K)
+// normal equations collapse to closed forms in (Sxx_k, Syy_k, Sxy_k):
+//   slope_k = Sxy_k / Sxx_k;  RSS_full = sum_k (Syy_k - Sxy_k slope_k)
+//   K == 2: t = (slope_2 - slope_1) / sqrt(RSS_full/(n-4) * (1/Sxx_1 + 1/Sxx_2))
+//   K >= 3: RSS_add = sum Syy - (sum Sxy)^2 / sum Sxx;  F = ((RSS_add-RSS_full)/(K-1)) / (RSS_full/(n-2K))
+// ------------------------------------------------------------------------------------------------
+template <int K>
+struct PairMoments {
+  double sxy[K];
+};
+
+template <int K>
+__device__ __forceinline__ void finish_pair(const SegLayout& L, const double* __restrict__ mean,
+                                            const double* __restrict__ sxx, int a, int b,
+                                            const PairMoments<K>& pm, double* __restrict__ stat_out,
+                                            int32_t* __restrict__ status_out, double* __restrict__ coef_out) {
+  double slope[K], icpt[K];
+  double rss = 0.0, s_xy = 0.0, s_xx = 0.0, s_yy = 0.0, inv_sum = 0.0;
+  bool singular = false;
+  int Ke = 0;  // categories that have samples in this omic (an empty level is an aliased column in R, quirk q2)
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    slope[k] = icpt[k] = nan("");
+    if (L.cnt[k] == 0) continue;
+    ++Ke;
+    double ma = mean[(size_t)a * K + k], mb = mean[(size_t)b * K + k];
+    double sa = sxx[(size_t)a * K + k], sb = sxx[(size_t)b * K + k];
+    double c = pm.sxy[k];
+    // LINPACK dqrdc2 declares a column aliased when its residual norm drops below 1e-7 x its norm
+    if (L.cnt[k] < 2 || !(sa > 1e-14 * (sa + (double)L.cnt[k] * ma * ma))) singular = true;
+    slope[k] = c / sa;
+    icpt[k] = mb - slope[k] * ma;
+    rss += sb - c * slope[k];
+    s_xy += c;
+    s_xx += sa;
+    s_yy += sb;
+    inv_sum += 1.0 / sa;
+  }
+  if (Ke < 2) singular = true;
+  const bool exact_fit = !singular && s_yy == 0.0;  // response constant in every category: R returns noise/noise
+  double stat;
+  if (K == 2) {
+    double dof = (double)(L.n - 4);
+    double se = sqrt(rss / dof * inv_sum);
+    stat = (slope[1] - slope[0]) / se;
+  } else {
+    double rss_add = s_yy - s_xy * s_xy / s_xx;
+    double d1 = (double)(Ke - 1), d2 = (double)(L.n - 2 * Ke);
+    stat = ((rss_add - rss) / d1) / (rss / d2);
+  }
+  if (singular) stat = nan("");
+  if (exact_fit) stat = 0.0;
+  *stat_out = stat;
+  *status_out = singular ? MDEGGS_EDGE_SINGULAR : (exact_fit ? MDEGGS_EDGE_SELFLOOP : MDEGGS_EDGE_OK);
+  if (coef_out) {  // R order: (Intercept), A, metadata2..K, A:metadata2..K; NA when the reference level is empty
+    const bool ok = !singular && L.cnt[0] > 0;
+    coef_out[0] = ok ? icpt[0] : nan("");
+    coef_out[1] = ok ? slope[0] : nan("");
+#pragma unroll
+    for (int k = 1; k < K; ++k) {
+      coef_out[1 + k] = ok ? icpt[k] - icpt[0] : nan("");
+      coef_out[K + k] = ok ? slope[k] - slope[0] : nan("");
+    }
+  }
+}
+
+template <int K>
+__global__ void __launch_bounds__(256) k_fit_stream(const double* __restrict__ D, SegLayout L,
+                                                    const int32_t* __restrict__ from,
+                                                    const int32_t* __restrict__ to,
+                                                    const int32_t* __restrict__ node_of_row,
+                                                    const double* __restrict__ mean,
+                                                    const double* __restrict__ sxx,
+                                                    const uint8_t* __restrict__ bad, int64_t e_lo, int64_t e_hi,
+                                                    double* __restrict__ stat, int32_t* __restrict__ status,
+                                                    double* __restrict__ coef) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t e = e_lo + warp0; e < e_hi; e += nwarps) {
+    const int ra = from[e] - 1, rb = to[e] - 1;
+    const int a = node_of_row[ra], b = node_of_row[rb];
+    if (ra == rb || bad[a] || bad[b]) {
+      if (lane == 0) {
+        bool self = (ra == rb) && !bad[a];
+        stat[e] = self ? 0.0 : nan("");
+        status[e] = self ? MDEGGS_EDGE_SELFLOOP : MDEGGS_EDGE_NONFINITE;
+        if (coef)
+          for (int j = 0; j < 2 * K; ++j) coef[(size_t)e * 2 * K + j] = nan("");
+      }
+      continue;
+    }
+    const double2* __restrict__ pa = reinterpret_cast<const double2*>(D + (size_t)a * L.npad);
+    const double2* __restrict__ pb = reinterpret_cast<const double2*>(D + (size_t)b * L.npad);
+    PairMoments<K> pm;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const double ma = mean[(size_t)a * K + k], mb = mean[(size_t)b * K + k];
+      const int beg = L.off[k] >> 1, end = L.off[k + 1] >> 1;
+      double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll 4
+      for (int i = beg + lane; i < end; i += 32) {
+        double2 x = __ldg(pa + i), y = __ldg(pb + i);
+        acc0 = fma(x.x - ma, y.x - mb, acc0);
+        acc1 = fma(x.y - ma, y.y - mb, acc1);
+      }
+      pm.sxy[k] = warp_sum(acc0 + acc1);
+    }
+    if (lane == 0)
+      finish_pair<K>(L, mean, sxx, a, b, pm, stat + e, status + e, coef ? coef + (size_t)e * 2 * K : nullptr);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// tail probabilities, one thread per edge
+//   mode 0: 2 * (1 - pt(|t|, df2))            core_functions.R:1072
+//   mode 1: pf(F, df1, df2, lower.tail=FALSE)  core_functions.R:968 (aov) / 920 (f.robftest)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_tail(const double* __restrict__ stat, const int32_t* __restrict__ status, int64_t e_lo,
+                       int64_t e_hi, int mode, double df1, double df2, double* __restrict__ p_out) {
+  int64_t e = e_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= e_hi) return;
+  int st = status[e];
+  double p;
+  if (st == MDEGGS_EDGE_SINGULAR || st == MDEGGS_EDGE_NONFINITE || st == MDEGGS_EDGE_ZERO_SCALE) p = nan("");
+  else if (st == MDEGGS_EDGE_SELFLOOP) p = 1.0;
+  else p = (mode == 0) ? p_two_sided_ref_dev(stat[e], df2) : pf_upper_dev(stat[e], df1, df2);
+  p_out[e] = p;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K7: percolation masks   (calc_pvalues_percentile, core_functions.R:723-779)
+//   act[p][node] bit k  <=>  median_k(node) > cut_off_p           (core_functions.R:724, strict >)
+//   an edge is tested at percentile p iff both ends are active in EXACTLY one category (745-770)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_actmask(const double* __restrict__ med, const double* __restrict__ cutoff,
+                          const int32_t* __restrict__ n_nodes_p, int P, int K, int act_stride,
+                          uint8_t* __restrict__ act) {
+  const int n_nodes = *n_nodes_p;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)P * n_nodes) return;
+  int p = (int)(i / n_nodes), node = (int)(i % n_nodes);
+  double c = cutoff[p];
+  unsigned m = 0;
+  for (int k = 0; k < K; ++k) m |= (unsigned)(med[(size_t)node * K + k] > c) << k;  // NaN median: never active
+  act[(size_t)p * act_stride + node] = (uint8_t)m;
+}
+
+__device__ __forceinline__ int edge_category(unsigned ma, unsigned mb) {
+  unsigned m = ma & mb;
+  return (m != 0 && (m & (m - 1)) == 0) ? __ffs(m) : 0;  // 1-based category, 0 = none or shared
+}
+
+// counts per percentile: tot_edges (773-779), hard failures, and for padj "none" the raw p < 0.05 count (796-808)
+__global__ void __launch_bounds__(256) k_percolate(const int32_t* __restrict__ from, const int32_t* __restrict__ to,
+                                                   const int32_t* __restrict__ node_of_row,
+                                                   const int32_t* __restrict__ status,
+                                                   const double* __restrict__ p_edge,
+                                                   const uint8_t* __restrict__ act, int act_stride, int64_t E, int P,
+                                                   unsigned long long* __restrict__ tot,
+                                                   unsigned long long* __restrict__ fail,
+                                                   unsigned long long* __restrict__ sig_raw,
+                                                   int8_t* __restrict__ cat_out) {
+  extern __shared__ unsigned int s_cnt[];  // [3][P]
+  for (int i = threadIdx.x; i < 3 * P; i += blockDim.x) s_cnt[i] = 0;
+  __syncthreads();
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = e < E;
+  int a = 0, b = 0, st = 0;
+  double pv = 1.0;
+  if (live) {
+    a = node_of_row[from[e] - 1];
+    b = node_of_row[to[e] - 1];
+    st = status[e];
+    pv = p_edge[e];
+  }
+  const bool hard = (st == MDEGGS_EDGE_SINGULAR || st == MDEGGS_EDGE_NONFINITE);
+  const int lane = threadIdx.x & 31;
+  for (int p = 0; p < P; ++p) {
+    int c = 0;
+    if (live) c = edge_category(act[(size_t)p * act_stride + a], act[(size_t)p * act_stride + b]);
+    if (cat_out && live) cat_out[(size_t)p * E + e] = (int8_t)c;
+    unsigned m_t = __ballot_sync(0xffffffffu, c != 0);
+    unsigned m_f = __ballot_sync(0xffffffffu, c != 0 && hard);
+    unsigned m_s = __ballot_sync(0xffffffffu, c != 0 && pv < 0.05);
+    if (lane == 0) {
+      if (m_t) atomicAdd(&s_cnt[p], __popc(m_t));
+      if (m_f) atomicAdd(&s_cnt[P + p], __popc(m_f));
+      if (m_s) atomicAdd(&s_cnt[2 * P + p], __popc(m_s));
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < P; i += blockDim.x) {
+    if (s_cnt[i]) atomicAdd(&tot[i], (unsigned long long)s_cnt[i]);
+    if (s_cnt[P + i]) atomicAdd(&fail[i], (unsigned long long)s_cnt[P + i]);
+    if (s_cnt[2 * P + i]) atomicAdd(&sig_raw[i], (unsigned long long)s_cnt[2 * P + i]);
+  }
+}
+
+// cat row of one percentile chosen on the device (best)
+__global__ void k_cat_row(const int32_t* __restrict__ from, const int32_t* __restrict__ to,
+                          const int32_t* __restrict__ node_of_row, const uint8_t* __restrict__ act, int act_stride,
+                          int64_t E, const int32_t* __restrict__ best, int8_t* __restrict__ cat_out) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  int p = *best - 1;
+  int c = 0;
+  if (p >= 0) {
+    int a = node_of_row[from[e] - 1], b = node_of_row[to[e] - 1];
+    c = edge_category(act[(size_t)p * act_stride + a], act[(size_t)p * act_stride + b]);
+  }
+  cat_out[e] = (int8_t)c;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K8: multiple-testing adjustment per (percentile, category) segment + significant-pair count
+//   stats::p.adjust(p, "bonferroni" | "BH")  core_functions.R:1027-1035;  count < 0.05  796-808
+// The raw p-value of an edge does not depend on the percentile, so ALL edges are sorted once by p
+// (CUB radix sort on sortable keys, NaN last); a (percentile, category) segment is a sub-sequence of that
+// order. For each segment: rank i by a prefix count of its members, BH value (n/i)*p in R's operation
+// order, cummin from the largest p (a suffix min), pmin(1, .), scatter back to network order.
+// Three passes over 1024-element tiles with tile-level partials (count -> ranks -> suffix-min).
+// ------------------------------------------------------------------------------------------------
+constexpr int BH_THREADS = 256;
+constexpr int BH_ITEMS = 4;
+constexpr int BH_TILE = BH_THREADS * BH_ITEMS;
+
+__global__ void k_sort_keys(const double* __restrict__ p_edge, int64_t E, unsigned long long* __restrict__ keys,
+                            int32_t* __restrict__ idx) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  keys[e] = dkey(p_edge[e]);
+  idx[e] = (int32_t)e;
+}
+
+__global__ void k_gather_sorted(const unsigned long long* __restrict__ keys_sorted,
+                                const int32_t* __restrict__ idx_sorted, const int32_t* __restrict__ from,
+                                const int32_t* __restrict__ to, const int32_t* __restrict__ node_of_row, int64_t E,
+                                double* __restrict__ ps, int32_t* __restrict__ sa, int32_t* __restrict__ sb,
+                                unsigned long long* __restrict__ n_valid) {
+  int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool valid = false;
+  if (j < E) {
+    unsigned long long k = keys_sorted[j];
+    int32_t e = idx_sorted[j];
+    valid = (k != ~0ull);
+    ps[j] = valid ? dkey_inv(k) : nan("");
+    sa[j] = node_of_row[from[e] - 1];
+    sb[j] = node_of_row[to[e] - 1];
+  }
+  unsigned m = __ballot_sync(0xffffffffu, valid);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_valid, (unsigned long long)__popc(m));
+}
+
+struct BhArgs {
+  const double* ps;
+  const int32_t *sa, *sb, *sidx;
+  const uint8_t* act;
+  int act_stride;
+  int64_t E;
+  const unsigned long long* n_valid;
+  int K, P, ntiles;
+  int p0;               // first percentile handled by blockIdx.y == 0 (segments y -> p = p0 + y / K, c = y % K + 1)
+  const int32_t* best;  // when non-null: p0 := *best - 1 (device-chosen percentile), grid.y == K
+};
+
+__device__ __forceinline__ bool bh_segment(const BhArgs& A, int& p, int& c) {
+  int base = A.p0;
+  if (A.best) {
+    base = *A.best - 1;
+    if (base < 0) return false;
+  }
+  p = base + (int)blockIdx.y / A.K;
+  c = (int)blockIdx.y % A.K + 1;
+  return true;
+}
+
+__device__ __forceinline__ void bh_load(const BhArgs& A, int p, int c, int64_t tile0, int (&flag)[BH_ITEMS],
+                                        double (&pv)[BH_ITEMS]) {
+  const int64_t nv = (int64_t)*A.n_valid;
+#pragma unroll
+  for (int it = 0; it < BH_ITEMS; ++it) {
+    int64_t j = tile0 + (int64_t)threadIdx.x * BH_ITEMS + it;
+    flag[it] = 0;
+    pv[it] = 0.0;
+    if (j < nv) {
+      int cc = edge_category(A.act[(size_t)p * A.act_stride + A.sa[j]], A.act[(size_t)p * A.act_stride + A.sb[j]]);
+      flag[it] = (cc == c);
+      pv[it] = A.ps[j];
+    }
+  }
+}
+
+// pass A: members per tile
+__global__ void __launch_bounds__(BH_THREADS) k_bh_count(BhArgs A, int32_t* __restrict__ tile_cnt) {
+  int p, c;
+  if (!bh_segment(A, p, c)) return;
+  typedef cub::BlockReduce<int, BH_THREADS> Reduce;
+  __shared__ typename Reduce::TempStorage tmp;
+  int flag[BH_ITEMS];
+  double pv[BH_ITEMS];
+  bh_load(A, p, c, (int64_t)blockIdx.x * BH_TILE, flag, pv);
+  int s = 0;
+#pragma unroll
+  for (int it = 0; it < BH_ITEMS; ++it) s += flag[it];
+  int tot = Reduce(tmp).Sum(s);
+  if (threadIdx.x == 0) tile_cnt[(size_t)blockIdx.y * A.ntiles + blockIdx.x] = tot;
+}
+
+// exclusive scan of the tile counts of each segment (one CTA per segment); seg_n = members of the segment
+__global__ void __launch_bounds__(256) k_bh_scan_tiles(const int32_t* __restrict__ tile_cnt, int ntiles,
+                                                       long long* __restrict__ tile_base,
+                                                       long long* __restrict__ seg_n) {
+  typedef cub::BlockScan<long long, 256> Scan;
+  __shared__ typename Scan::TempStorage tmp;
+  __shared__ long long carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const size_t base = (size_t)blockIdx.x * ntiles;
+  for (int t0 = 0; t0 < ntiles; t0 += 256) {
+    int t = t0 + threadIdx.x;
+    long long v = t < ntiles ? (long long)tile_cnt[base + t] : 0, ex, agg;
+    Scan(tmp).ExclusiveSum(v, ex, agg);
+    if (t < ntiles) tile_base[base + t] = carry + ex;
+    __syncthreads();
+    if (threadIdx.x == 0) carry += agg;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) seg_n[blockIdx.x] = carry;
+}
+
+__device__ __forceinline__ double bh_value(double n, long long i, double p) {
+  return __dmul_rn(__ddiv_rn(n, (double)i), p);  // (n / i) * p[o]  (stats::p.adjust, "BH")
+}
+
+struct MinOp {
+  __device__ __forceinline__ double operator()(double a, double b) const { return a < b ? a : b; }
+};
+
+// pass B: BH values with global ranks -> minimum of each tile
+__global__ void __launch_bounds__(BH_THREADS) k_bh_tilemin(BhArgs A, const long long* __restrict__ tile_base,
+                                                          const long long* __restrict__ seg_n,
+                                                          double* __restrict__ tile_min) {
+  int p, c;
+  if (!bh_segment(A, p, c)) return;
+  typedef cub::BlockScan<int, BH_THREADS> Scan;
+  typedef cub::BlockReduce<double, BH_THREADS> Reduce;
+  __shared__ union {
+    typename Scan::TempStorage scan;
+    typename Reduce::TempStorage red;
+  } tmp;
+  int flag[BH_ITEMS], rank[BH_ITEMS];
+  double pv[BH_ITEMS];
+  bh_load(A, p, c, (int64_t)blockIdx.x * BH_TILE, flag, pv);
+  Scan(tmp.scan).InclusiveSum(flag, rank);
+  __syncthreads();
+  const size_t seg = blockIdx.y;
+  const long long base = tile_base[seg * A.ntiles + blockIdx.x];
+  const double n = (double)seg_n[seg];
+  double mn = INFINITY;
+#pragma unroll
+  for (int it = 0; it < BH_ITEMS; ++it)
+    if (flag[it]) mn = fmin(mn, bh_value(n, base + rank[it], pv[it]));
+  double tmn = Reduce(tmp.red).Reduce(mn, MinOp());
+  if (threadIdx.x == 0) tile_min[seg * A.ntiles + blockIdx.x] = tmn;
+}
+
+// exclusive suffix-min over the tiles of each segment (one CTA per segment, walks tiles from the end)
+__global__ void __launch_bounds__(256) k_bh_suffix_min(const double* __restrict__ tile_min, int ntiles,
+                                                       double* __restrict__ tile_carry) {
+  typedef cub::BlockScan<double, 256> Scan;
+  __shared__ typename Scan::TempStorage tmp;
+  __shared__ double carry;
+  if (threadIdx.x == 0) carry = INFINITY;
+  __syncthreads();
+  const size_t base = (size_t)blockIdx.x * ntiles;
+  for (int t0 = 0; t0 < ntiles; t0 += 256) {
+    int r = t0 + threadIdx.x;  // reversed tile index
+    int t = ntiles - 1 - r;
+    double v = r < ntiles ? tile_min[base + t] : INFINITY, ex, agg;
+    Scan(tmp).ExclusiveScan(v, ex, INFINITY, MinOp(), agg);
+    if (r < ntiles) tile_carry[base + t] = fmin(carry, ex);
+    __syncthreads();
+    if (threadIdx.x == 0) carry = fmin(carry, agg);
+    __syncthreads();
+  }
+}
+
+// pass C: adjusted values, count < 0.05, optional scatter to network order
+//   mode 1 bonferroni: pmin(1, n * p);  mode 2 BH: pmin(1, cummin((n/i) * p[o]))[ro]
+__global__ void __launch_bounds__(BH_THREADS) k_bh_final(BhArgs A, int mode, const long long* __restrict__ tile_base,
+                                                        const long long* __restrict__ seg_n,
+                                                        const double* __restrict__ tile_carry,
+                                                        unsigned long long* __restrict__ sig,
+                                                        double* __restrict__ padj_out, int64_t padj_stride) {
+  int p, c;
+  if (!bh_segment(A, p, c)) return;
+  typedef cub::BlockScan<int, BH_THREADS> ScanI;
+  typedef cub::BlockScan<double, BH_THREADS> ScanD;
+  typedef cub::BlockReduce<int, BH_THREADS> Reduce;
+  __shared__ union {
+    typename ScanI::TempStorage si;
+    typename ScanD::TempStorage sd;
+    typename Reduce::TempStorage red;
+  } tmp;
+  int flag[BH_ITEMS], rank[BH_ITEMS];
+  double pv[BH_ITEMS], q[BH_ITEMS];
+  const int64_t tile0 = (int64_t)blockIdx.x * BH_TILE;
+  bh_load(A, p, c, tile0, flag, pv);
+  const size_t seg = blockIdx.y;
+  const double n = (double)seg_n[seg];
+  if (mode == 2) {
+    ScanI(tmp.si).InclusiveSum(flag, rank);
+    __syncthreads();
+    const long long base = tile_base[seg * A.ntiles + blockIdx.x];
+    // suffix min inside the tile: scan the reversed sequence (thread T-1-t, item order reversed)
+    double v[BH_ITEMS], sfx[BH_ITEMS];
+#pragma unroll
+    for (int it = 0; it < BH_ITEMS; ++it) v[it] = flag[it] ? bh_value(n, base + rank[it], pv[it]) : INFINITY;
+    // own items: local suffix (items after me in this thread)
+    double run = INFINITY;
+#pragma unroll
+    for (int it = BH_ITEMS - 1; it >= 0; --it) {
+      run = fmin(run, v[it]);
+      sfx[it] = run;
+    }
+    // threads after me: exclusive scan over reversed thread ids
+    __shared__ double tmin_s[BH_THREADS];
+    tmin_s[BH_THREADS - 1 - threadIdx.x] = run;
+    __syncthreads();
+    double mine = tmin_s[threadIdx.x], ex;
+    ScanD(tmp.sd).ExclusiveScan(mine, ex, INFINITY, MinOp());
+    __syncthreads();
+    tmin_s[threadIdx.x] = ex;  // ex of reversed position r = min over reversed positions < r
+    __syncthreads();
+    double after = tmin_s[BH_THREADS - 1 - threadIdx.x];
+    const double carry = tile_carry[seg * A.ntiles + blockIdx.x];
+#pragma unroll
+    for (int it = 0; it < BH_ITEMS; ++it) q[it] = fmin(1.0, fmin(sfx[it], fmin(after, carry)));
+    __syncthreads();
+  } else {
+#pragma unroll
+    for (int it = 0; it < BH_ITEMS; ++it) q[it] = fmin(1.0, __dmul_rn(n, pv[it]));
+  }
+  int cnt = 0;
+#pragma unroll
+  for (int it = 0; it < BH_ITEMS; ++it) {
+    if (!flag[it]) continue;
+    cnt += (q[it] < 0.05);
+    if (padj_out) {
+      int64_t j = tile0 + (int64_t)threadIdx.x * BH_ITEMS + it;
+      int64_t row = A.best ? 0 : (p - A.p0);
+      padj_out[row * padj_stride + A.sidx[j]] = q[it];
+    }
+  }
+  if (sig) {
+    int tot = Reduce(tmp.red).Sum(cnt);
+    if (threadIdx.x == 0 && tot) atomicAdd(&sig[p], (unsigned long long)tot);
+  }
+}
+
+// which.max(sig_pvalues) over non-NULL percentiles (core_functions.R:475-495): first maximum
+__global__ void k_select_best(const unsigned long long* __restrict__ tot, const unsigned long long* __restrict__ fail,
+                              const unsigned long long* __restrict__ sig, int P, int host_adjust,
+                              long long* __restrict__ tot_out, long long* __restrict__ sig_out,
+                              long long* __restrict__ fail_out, int32_t* __restrict__ best) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  int b = 0;
+  long long bv = -1;
+  for (int p = 0; p < P; ++p) {
+    long long t = (long long)tot[p], s = t > 0 ? (long long)sig[p] : -1;
+    if (host_adjust) s = -1;
+    tot_out[p] = t;
+    sig_out[p] = s;
+    fail_out[p] = (long long)fail[p];
+    if (!host_adjust && t > 0 && fail[p] == 0 && s > bv) {
+      bv = s;
+      b = p + 1;
+    }
+  }
+  *best = b;
+}
+
+__global__ void k_fill_f64(double* __restrict__ x, int64_t n, double v) {
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) x[i] = v;
+}
+
+// median[k*G + g] for the caller (NaN for rows that are not nodes)
+__global__ void k_scatter_median(const double* __restrict__ med, const int32_t* __restrict__ node_of_row, int G,
+                                 int K, double* __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)G * K) return;
+  int k = (int)(i / G), g = (int)(i % G);
+  int node = node_of_row[g];
+  out[i] = node >= 0 ? med[(size_t)node * K + k] : nan("");
+}
+
+// predict.multiDEGGs_filter feature construction (feature_selection_for_ML.R:423-431)
+__global__ void k_pair_features(const double* __restrict__ x, int64_t ldx, int n, const int32_t* __restrict__ a,
+                                const int32_t* __restrict__ b, int n_pairs, int ratio, double* __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)n * n_pairs) return;
+  int j = (int)(i / n), s = (int)(i % n);
+  double va = x[s + (int64_t)a[j] * ldx], vb = x[s + (int64_t)b[j] * ldx];
+  double r = ratio ? __ddiv_rn(va, vb) : __dmul_rn(va, vb);
+  out[i] = isfinite(r) ? r : 0.0;
+}
+
+// scalar math twins for tests
+__global__ void k_dev_math(int which, const double* __restrict__ x, const double* __restrict__ a,
+                           const double* __restrict__ b, int64_t n, double* __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (which == 0) out[i] = pt_dev(x[i], a[i]);
+  else if (which == 1) out[i] = pf_upper_dev(x[i], a[i], b[i]);
+  else out[i] = p_two_sided_ref_dev(x[i], a[i]);
+}
+
+}  // namespace mdeggs

@@ -1,0 +1,296 @@
+// mdeggs_rlm.cuh — K6: batched Huber IRLS for regression_method = "rlm", two categories.
+//
+// Replaces, per edge,  MASS::rlm(B ~ A * metadata)  followed by  sfsmisc::f.robftest(fit, var = 3)
+// (R/core_functions.R:914-925).  MASS defaults: psi.huber k = 1.345, init = "ls", scale.est = "MAD"
+// (median|r| / 0.6745 re-estimated every iteration), maxit = 20, acc = 1e-4 on irls.delta(resid).
+//
+// One warp per edge.  The 4-parameter weighted fit of  B ~ A * g  decomposes into two independent weighted
+// simple regressions (one per category); only the MAD scale couples them.  Rows A and B are staged once in
+// shared memory, residuals live in shared memory, so HBM/L2 bytes are paid once per edge and each IRLS
+// iteration is: one pass for the Huber weights + 5 weighted moments per category, one pass for the new
+// residuals + convergence norm, and one exact order statistic (median of |r|, 63-step key bisection).
+// The Wald test needs only closed-form diagonal entries of (X'X)^-1 / (X'WX)^-1 in the same decomposition.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "mdeggs.h"
+#include "mdeggs_kernels.cuh"
+
+namespace mdeggs {
+
+struct GroupFit {
+  double W, ma, mb, sxx, sxy, slope, icpt;
+};
+
+// median of |r| over the real (non-padding) samples: exact order statistic by bisection on the IEEE bits
+// (|r| >= 0, so the raw bit pattern is already order preserving)
+__device__ __forceinline__ double warp_median_abs(const double* r, const SegLayout& L, int lane) {
+  const int n = L.n;
+  auto count_less = [&](unsigned long long cand) {
+    int c = 0;
+    for (int k = 0; k < 2; ++k)
+      for (int i = L.off[k] + lane; i < L.off[k] + L.cnt[k]; i += 32)
+        c += ((unsigned long long)__double_as_longlong(fabs(r[i])) < cand);
+    return __reduce_add_sync(0xffffffffu, c);
+  };
+  auto select = [&](int kth) {
+    unsigned long long prefix = 0;
+    for (int bit = 62; bit >= 0; --bit) {
+      unsigned long long cand = prefix | (1ull << bit);
+      if (count_less(cand) <= kth) prefix = cand;
+    }
+    return prefix;
+  };
+  if (n & 1) return __longlong_as_double((long long)select(n / 2));
+  unsigned long long k1 = select(n / 2 - 1);
+  int c_le = 0;
+  unsigned long long nxt = ~0ull;
+  for (int k = 0; k < 2; ++k)
+    for (int i = L.off[k] + lane; i < L.off[k] + L.cnt[k]; i += 32) {
+      unsigned long long kk = (unsigned long long)__double_as_longlong(fabs(r[i]));
+      c_le += (kk <= k1);
+      if (kk > k1 && kk < nxt) nxt = kk;
+    }
+  c_le = __reduce_add_sync(0xffffffffu, c_le);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    unsigned long long other = __shfl_xor_sync(0xffffffffu, nxt, o);
+    nxt = other < nxt ? other : nxt;
+  }
+  unsigned long long k2 = (c_le > n / 2) ? k1 : nxt;
+  return __ddiv_rn(__dadd_rn(__longlong_as_double((long long)k1), __longlong_as_double((long long)k2)), 2.0);
+}
+
+template <bool CACHE_AB>
+__global__ void __launch_bounds__(256) k_fit_rlm(const double* __restrict__ D, SegLayout L,
+                                                 const int32_t* __restrict__ from, const int32_t* __restrict__ to,
+                                                 const int32_t* __restrict__ node_of_row,
+                                                 const double* __restrict__ mean, const double* __restrict__ sxx,
+                                                 const uint8_t* __restrict__ bad, int64_t e_lo, int64_t e_hi,
+                                                 int tested_coef, int cov_mode, double* __restrict__ stat,
+                                                 int32_t* __restrict__ status, double* __restrict__ coef,
+                                                 int32_t* __restrict__ iters) {
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const int per_warp = CACHE_AB ? 3 * L.npad : L.npad;
+  double* r = smem + (size_t)wib * per_warp;
+  double* sa = CACHE_AB ? r + L.npad : nullptr;
+  double* sb = CACHE_AB ? r + 2 * L.npad : nullptr;
+  const double kh = 1.345;
+  const int n = L.n;
+  for (int64_t e = e_lo + (int64_t)blockIdx.x * wpb + wib; e < e_hi; e += (int64_t)gridDim.x * wpb) {
+    const int ra = from[e] - 1, rb = to[e] - 1;
+    const int a = node_of_row[ra], b = node_of_row[rb];
+    auto put = [&](double st_v, int code, int it) {
+      if (lane == 0) {
+        stat[e] = st_v;
+        status[e] = code;
+        iters[e] = it;
+        if (coef)
+          for (int j = 0; j < 4; ++j) coef[(size_t)e * 4 + j] = nan("");
+      }
+    };
+    if (ra == rb || bad[a] || bad[b]) {
+      bool self = (ra == rb) && !bad[a];
+      put(self ? 0.0 : nan(""), self ? MDEGGS_EDGE_SELFLOOP : MDEGGS_EDGE_NONFINITE, 0);
+      continue;
+    }
+    const double* ga = D + (size_t)a * L.npad;
+    const double* gb = D + (size_t)b * L.npad;
+    if (CACHE_AB) {
+      for (int i = lane; i < L.npad; i += 32) {
+        sa[i] = __ldg(ga + i);
+        sb[i] = __ldg(gb + i);
+      }
+      __syncwarp();
+    }
+    const double* pa = CACHE_AB ? sa : ga;
+    const double* pb = CACHE_AB ? sb : gb;
+    // unweighted centring constants (from K2) keep every weighted moment well conditioned
+    double ca[2], cb[2];
+    bool singular = false;
+    for (int k = 0; k < 2; ++k) {
+      ca[k] = mean[(size_t)a * 2 + k];
+      cb[k] = mean[(size_t)b * 2 + k];
+      double s = sxx[(size_t)a * 2 + k];
+      if (L.cnt[k] < 2 || !(s > 1e-14 * (s + (double)L.cnt[k] * ca[k] * ca[k]))) singular = true;
+    }
+    if (singular) {  // rlm(): "'x' is singular: singular fits are not implemented in 'rlm'"
+      put(nan(""), MDEGGS_EDGE_SINGULAR, 0);
+      continue;
+    }
+    if (sxx[(size_t)b * 2] == 0.0 && sxx[(size_t)b * 2 + 1] == 0.0) {  // constant response: exact fit
+      put(0.0, MDEGGS_EDGE_SELFLOOP, 0);
+      continue;
+    }
+    GroupFit gf[2];
+    // ---- init = "ls": ordinary least squares residuals ----
+    for (int k = 0; k < 2; ++k) {
+      double acc = 0.0;
+      for (int i = L.off[k] + lane; i < L.off[k] + L.cnt[k]; i += 32) acc = fma(pa[i] - ca[k], pb[i] - cb[k], acc);
+      acc = warp_sum(acc);
+      gf[k].W = (double)L.cnt[k];
+      gf[k].ma = ca[k];
+      gf[k].mb = cb[k];
+      gf[k].sxx = sxx[(size_t)a * 2 + k];
+      gf[k].sxy = acc;
+      gf[k].slope = acc / gf[k].sxx;
+      gf[k].icpt = cb[k] - gf[k].slope * ca[k];
+      for (int i = L.off[k] + lane; i < L.off[k] + L.cnt[k]; i += 32) r[i] = pb[i] - gf[k].icpt - gf[k].slope * pa[i];
+    }
+    __syncwarp();
+    double scale = 0.0;
+    bool done = false, zero_scale = false;
+    int it = 0;
+    for (it = 1; it <= 20; ++it) {
+      scale = warp_median_abs(r, L, lane) / 0.6745;
+      if (scale == 0.0) {
+        zero_scale = true;
+        done = true;
+        break;
+      }
+      double diff = 0.0, old_ss = 0.0;
+      for (int k = 0; k < 2; ++k) {
+        double sw = 0.0, swa = 0.0, swb = 0.0, swaa = 0.0, swab = 0.0;
+        for (int i = L.off[k] + lane; i < L.off[k] + L.cnt[k]; i += 32) {
+          double u = fabs(r[i] / scale);
+          double w = (u <= kh) ? 1.0 : kh / u;  // psi.huber weight pmin(1, k/|u|)
+          double da = pa[i] - ca[k], db = pb[i] - cb[k];
+          sw += w;
+          swa = fma(w, da, swa);
+          swb = fma(w, db, swb);
+          swaa = fma(w * da, da, swaa);
+          swab = fma(w * da, db, swab);
+        }
+        sw = warp_sum(sw);
+        swa = warp_sum(swa);
+        swb = warp_sum(swb);
+        swaa = warp_sum(swaa);
+        swab = warp_sum(swab);
+        GroupFit& g = gf[k];
+        g.W = sw;
+        double dma = swa / sw, dmb = swb / sw;
+        g.ma = ca[k] + dma;
+        g.mb = cb[k] + dmb;
+        g.sxx = swaa - swa * dma;
+        g.sxy = swab - swa * dmb;
+        g.slope = g.sxy / g.sxx;
+        g.icpt = g.mb - g.slope * g.ma;
+        for (int i = L.off[k] + lane; i < L.off[k] + L.cnt[k]; i += 32) {
+          double ro = r[i];
+          double rn = pb[i] - g.icpt - g.slope * pa[i];
+          double d = ro - rn;
+          diff = fma(d, d, diff);
+          old_ss = fma(ro, ro, old_ss);
+          r[i] = rn;
+        }
+      }
+      __syncwarp();
+      diff = warp_sum(diff);
+      old_ss = warp_sum(old_ss);
+      double conv = sqrt(diff / fmax(old_ss, 1e-20));  // irls.delta
+      if (conv <= 1e-4) {
+        done = true;
+        break;
+      }
+    }
+    if (it > 20) it = 20;
+    if (zero_scale) {
+      put(nan(""), MDEGGS_EDGE_ZERO_SCALE, it);
+      continue;
+    }
+    // ---- summary.rlm + Wald F of coefficient `tested_coef` (f.robftest) ----
+    double S = 0.0, npp = 0.0, sumw = 0.0;
+    double W2[2] = {0, 0}, wa2[2] = {0, 0}, waa2[2] = {0, 0};
+    for (int k = 0; k < 2; ++k) {
+      double sw = 0.0, swa = 0.0, swaa = 0.0;
+      for (int i = L.off[k] + lane; i < L.off[k] + L.cnt[k]; i += 32) {
+        double u = fabs(r[i] / scale);
+        double w = (u <= kh) ? 1.0 : kh / u;
+        double rw = r[i] * w;
+        S = fma(rw, rw, S);
+        npp += (u <= kh) ? 1.0 : 0.0;
+        double da = pa[i] - ca[k];
+        sw += w;
+        swa = fma(w, da, swa);
+        swaa = fma(w * da, da, swaa);
+      }
+      W2[k] = warp_sum(sw);
+      wa2[k] = warp_sum(swa);
+      waa2[k] = warp_sum(swaa);
+      sumw += W2[k];
+    }
+    S = warp_sum(S);
+    npp = warp_sum(npp);
+    const double rdf = (double)(n - 4);
+    S /= rdf;
+    const double mn = npp / (double)n;
+    const double var_pp = (double)n * mn * (1.0 - mn) / (double)(n - 1);
+    const double kappa = 1.0 + 4.0 * var_pp / ((double)n * mn * mn);
+    const double stddev = sqrt(S) * (kappa / mn);
+    double v_icpt[2], v_slope[2];
+    double cov_scale = 1.0;
+    if (cov_mode == MDEGGS_RLM_COV_XTWX) {
+      cov_scale = sumw / (double)n;  // X~ = X sqrt(w / mean(w))  =>  cov.unscaled = mean(w) (X'WX)^-1
+      for (int k = 0; k < 2; ++k) {
+        double dm = wa2[k] / W2[k];
+        double mk = ca[k] + dm, sx = waa2[k] - wa2[k] * dm;
+        v_icpt[k] = 1.0 / W2[k] + mk * mk / sx;
+        v_slope[k] = 1.0 / sx;
+      }
+    } else {
+      for (int k = 0; k < 2; ++k) {
+        double sx = sxx[(size_t)a * 2 + k];
+        v_icpt[k] = 1.0 / (double)L.cnt[k] + ca[k] * ca[k] / sx;
+        v_slope[k] = 1.0 / sx;
+      }
+    }
+    double beta[4] = {gf[0].icpt, gf[0].slope, gf[1].icpt - gf[0].icpt, gf[1].slope - gf[0].slope};
+    double cov[4] = {v_icpt[0], v_slope[0], v_icpt[0] + v_icpt[1], v_slope[0] + v_slope[1]};
+    const int v = tested_coef - 1;
+    const double var_v = stddev * stddev * cov_scale * cov[v];
+    const double F = beta[v] * beta[v] / var_v;
+    if (lane == 0) {
+      stat[e] = F;
+      status[e] = done ? MDEGGS_EDGE_OK : MDEGGS_EDGE_NOT_CONVERGED;
+      iters[e] = it;
+      if (coef)
+        for (int j = 0; j < 4; ++j) coef[(size_t)e * 4 + j] = beta[j];
+    }
+    __syncwarp();
+  }
+}
+
+// returns 0 on success, non-zero if even the residual-only variant does not fit in shared memory
+inline int launch_fit_rlm(int64_t& launches, cudaStream_t stream, const double* D, const SegLayout& L,
+                          const int32_t* from, const int32_t* to, const int32_t* node_of_row, const double* mean,
+                          const double* sxx, const uint8_t* bad, int64_t e_lo, int64_t e_hi, int tested_coef,
+                          int cov_mode, double* stat, int32_t* status, double* coef, int32_t* iters) {
+  const size_t budget = 200 * 1024;
+  const size_t row = (size_t)L.npad * 8;
+  bool cache = 3 * row * 2 <= budget;  // at least two warps per CTA with A, B, r resident
+  size_t per_warp = cache ? 3 * row : row;
+  if (per_warp > budget) return 1;
+  int wpb = (int)(budget / per_warp);
+  if (wpb > 8) wpb = 8;
+  size_t smem = per_warp * (size_t)wpb;
+  int64_t ne = e_hi - e_lo;
+  int64_t want = (ne + wpb - 1) / wpb;
+  unsigned grid = (unsigned)(want < 148 * 16 ? want : 148 * 16);
+  if (cache) {
+    if (smem > 48 * 1024)
+      cudaFuncSetAttribute(k_fit_rlm<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
+    k_fit_rlm<true><<<grid, wpb * 32, smem, stream>>>(D, L, from, to, node_of_row, mean, sxx, bad, e_lo, e_hi,
+                                                     tested_coef, cov_mode, stat, status, coef, iters);
+  } else {
+    if (smem > 48 * 1024)
+      cudaFuncSetAttribute(k_fit_rlm<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
+    k_fit_rlm<false><<<grid, wpb * 32, smem, stream>>>(D, L, from, to, node_of_row, mean, sxx, bad, e_lo, e_hi,
+                                                      tested_coef, cov_mode, stat, status, coef, iters);
+  }
+  ++launches;
+  return 0;
+}
+
+}  // namespace mdeggs

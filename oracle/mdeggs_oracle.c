@@ -450,30 +450,46 @@ int orc_fit_lm_interaction(const double* a, const double* b, const double* g01, 
  * [1, A, 1{g=2}..1{g=K}, A*1{g=2}..A*1{g=K}]. ws: (2K+2) n doubles. */
 int orc_fit_aov(const double* a, const double* b, const int32_t* grp, int n, int K, double* ws, double* coef,
                 double* f_out, double* p_out) {
-  int p = 2 * K;
   *f_out = NAN;
   *p_out = NAN;
-  for (int j = 0; j < p; ++j) coef[j] = NAN;
+  for (int j = 0; j < 2 * K; ++j) coef[j] = NAN;
   if (any_nonfinite(a, b, n)) return MDEGGS_EDGE_NONFINITE; /* documented deviation: model.frame would drop rows */
+  /* levels without samples in this omic (quirk q2) give all-zero, aliased columns that lm() pivots out:
+   * the test is the one of the Ke non-empty levels, df (Ke-1, n-2Ke) */
+  int lev[MDEGGS_MAX_K], Ke = 0, cnt[MDEGGS_MAX_K] = {0};
+  for (int i = 0; i < n; ++i) cnt[grp[i]]++;
+  for (int k = 0; k < K; ++k)
+    if (cnt[k] > 0) lev[Ke++] = k;
+  if (Ke < 2) return MDEGGS_EDGE_SINGULAR;
+  int p = 2 * Ke;
   double* X = ws;
   double* resid = ws + (size_t)p * n;
   double* eff = ws + (size_t)(p + 1) * n;
   for (int i = 0; i < n; ++i) {
     X[i] = 1.0;
     X[n + i] = a[i];
-    for (int k = 1; k < K; ++k) {
-      double ind = (grp[i] == k) ? 1.0 : 0.0;
+    for (int k = 1; k < Ke; ++k) {
+      double ind = (grp[i] == lev[k]) ? 1.0 : 0.0;
       X[(size_t)(1 + k) * n + i] = ind;
-      X[(size_t)(K + k) * n + i] = a[i] * ind;
+      X[(size_t)(Ke + k) * n + i] = a[i] * ind;
     }
   }
   orc_qr qr;
-  dqrls(X, n, p, b, 1e-7, &qr, coef, resid, eff);
+  double cf[2 * MDEGGS_MAX_K];
+  dqrls(X, n, p, b, 1e-7, &qr, cf, resid, eff);
   if (qr.rank < p) return MDEGGS_EDGE_SINGULAR; /* aliased interaction column: Df/SS rows change in R */
+  if (lev[0] == 0) { /* R order: (Intercept), A, metadata<L2..LK> at 1 + level, A:metadata<L> at K + level */
+    coef[0] = cf[0];
+    coef[1] = cf[1];
+    for (int k = 1; k < Ke; ++k) {
+      coef[1 + lev[k]] = cf[1 + k];
+      coef[K + lev[k]] = cf[Ke + k];
+    }
+  } /* else: the reference level itself is empty; coefficients are left NA (the F test is unaffected) */
   double ss_int = 0.0, rss = 0.0;
-  for (int j = K + 1; j < p; ++j) ss_int += eff[j] * eff[j];
+  for (int j = Ke + 1; j < p; ++j) ss_int += eff[j] * eff[j];
   for (int i = p; i < n; ++i) rss += eff[i] * eff[i];
-  double d1 = (double)(K - 1), d2 = (double)(n - p);
+  double d1 = (double)(Ke - 1), d2 = (double)(n - p);
   double f = (ss_int / d1) / (rss / d2);
   *f_out = f;
   *p_out = orc_pf_upper(f, d1, d2);
@@ -696,6 +712,19 @@ int mdeggs_oracle_fit_edge(const mdeggs_problem* in, const double* rowA, const d
   return orc_fit_aov(rowA, rowB, grp0, in->n, in->K, ws, coef, stat, p);
 }
 
+static int response_is_constant(const double* y, const int32_t* grp0, int n, int K) {
+  double first[MDEGGS_MAX_K];
+  int seen[MDEGGS_MAX_K] = {0};
+  for (int i = 0; i < n; ++i) {
+    int k = grp0[i];
+    if (!isfinite(y[i])) return 0;
+    if (!seen[k]) seen[k] = 1, first[k] = y[i];
+    else if (y[i] != first[k]) return 0;
+  }
+  (void)K;
+  return 1;
+}
+
 int mdeggs_oracle_run_omic(const mdeggs_problem* in, mdeggs_result* out, int mode, int nthreads) {
   const int G = in->G, n = in->n, K = in->K, P = in->P;
   const int64_t E = in->E;
@@ -771,8 +800,11 @@ int mdeggs_oracle_run_omic(const mdeggs_problem* in, mdeggs_result* out, int mod
       out->df[0] = 1.0;
       out->df[1] = (double)(n - 4);
     } else {
-      out->df[0] = (double)(K - 1);
-      out->df[1] = (double)(n - 2 * K);
+      int Ke = 0, cnt[MDEGGS_MAX_K] = {0};
+      for (int s = 0; s < n; ++s) cnt[in->group[s] - 1]++;
+      for (int k = 0; k < K; ++k) Ke += cnt[k] > 0;
+      out->df[0] = (double)(Ke - 1);
+      out->df[1] = (double)(n - 2 * Ke);
     }
   }
 
@@ -791,7 +823,18 @@ int mdeggs_oracle_run_omic(const mdeggs_problem* in, mdeggs_result* out, int mod
       const double* rb = rows + (int64_t)node_of[in->to[e] - 1] * n;
       double stat, p;
       int iters;
-      int st = mdeggs_oracle_fit_edge(in, ra, rb, g01, grp0, ws, coef, &stat, &p, &iters);
+      int st;
+      if (in->from[e] == in->to[e] || response_is_constant(rb, grp0, n, K)) {
+        /* exact fit (self-loop / constant response): R's t is rounding noise; documented deviation shared
+         * with the engine: p = 1, stat = 0 */
+        st = MDEGGS_EDGE_SELFLOOP;
+        stat = 0.0;
+        p = 1.0;
+        iters = 0;
+        for (int j = 0; j < ncoef; ++j) coef[j] = NAN;
+      } else {
+        st = mdeggs_oracle_fit_edge(in, ra, rb, g01, grp0, ws, coef, &stat, &p, &iters);
+      }
       p_edge[e] = p;
       st_edge[e] = st;
       if (out->p_edge) out->p_edge[e] = p;
@@ -855,7 +898,10 @@ int mdeggs_oracle_run_omic(const mdeggs_problem* in, mdeggs_result* out, int mod
           const double* rb = rows + (int64_t)node_of[in->to[e] - 1] * n;
           double coef[2 * MDEGGS_MAX_K], stat, p;
           int iters;
-          int st = mdeggs_oracle_fit_edge(in, ra, rb, g01, grp0, ws, coef, &stat, &p, &iters);
+          int st = MDEGGS_EDGE_SELFLOOP;
+          p = 1.0;
+          if (in->from[e] != in->to[e] && !response_is_constant(rb, grp0, n, K))
+            st = mdeggs_oracle_fit_edge(in, ra, rb, g01, grp0, ws, coef, &stat, &p, &iters);
           if (!need_unique && (st == MDEGGS_EDGE_SINGULAR || st == MDEGGS_EDGE_NONFINITE)) ++fail[pi];
           pv[j++] = p;
         } else {

@@ -1,0 +1,192 @@
+"""-m gpu: the CUDA path (through the C ABI) against the CPU oracle on the same inputs."""
+import numpy as np
+import pandas as pd
+import pytest
+
+import multideggs_b200 as md
+from multideggs_b200 import _abi, host, synth
+from helpers import ALL_FIELDS, assert_parity
+
+pytestmark = pytest.mark.gpu
+
+
+def _both(engine, oracle, prob, want=ALL_FIELDS):
+    gpu = engine.run_omic(prob, want)
+    ref = oracle.run_omic(prob, want)
+    return gpu, ref
+
+
+@pytest.mark.parametrize("omic", ["RNAseq", "Proteomics", "Olink"])
+@pytest.mark.parametrize("method,padj", [("lm", "bonferroni"), ("lm", "BH"), ("lm", "none"), ("lm", "q.value"),
+                                         ("rlm", "BH"), ("rlm", "bonferroni")])
+def test_bundled_engine_vs_oracle(engine, oracle, bundled, omic, method, padj):
+    fac = host.tidy_metadata(metadata=bundled["metadata"], category_variable="response")
+    pct = md.FILTER_PERCENTILES if padj == "q.value" else md.DEFAULT_PERCENTILES
+    prep = host.prepare_omic(bundled[omic], omic, fac, method, None, pct, padj)
+    gpu, ref = _both(engine, oracle, prep.problem)
+    assert_parity(gpu, ref, prep.problem, what=f"{omic}/{method}/{padj}: ")
+
+
+@pytest.mark.parametrize("G,n,E,K,seed", [
+    (40, 10, 60, 2, 1), (64, 22, 200, 2, 2), (100, 100, 500, 2, 3), (300, 1000, 800, 2, 4), (50, 2000, 300, 2, 5),
+    (80, 37, 300, 3, 6), (120, 333, 900, 3, 7), (60, 1000, 400, 3, 8), (90, 64, 500, 4, 9), (70, 120, 300, 5, 10),
+    (33, 17, 40, 2, 11), (257, 129, 1025, 3, 12),
+])
+@pytest.mark.parametrize("padj", [_abi.PADJ_BH, _abi.PADJ_BONFERRONI])
+def test_random_lm_aov(engine, oracle, G, n, E, K, seed, padj):
+    prob = synth.random_problem(G, n, E, K, seed, _abi.METHOD_LM, padj)
+    gpu, ref = _both(engine, oracle, prob)
+    assert_parity(gpu, ref, prob, what=f"G{G} n{n} E{E} K{K}: ")
+    assert ref["tot_edges"].sum() > 0
+
+
+@pytest.mark.parametrize("G,n,E,seed", [(40, 30, 80, 21), (60, 100, 200, 22), (50, 501, 150, 23), (30, 1200, 60, 24)])
+@pytest.mark.parametrize("coef,cov", [(3, _abi.RLM_COV_XTWX), (4, _abi.RLM_COV_XTWX), (3, _abi.RLM_COV_XTX)])
+def test_random_rlm(engine, oracle, G, n, E, seed, coef, cov):
+    prob = synth.random_problem(G, n, E, 2, seed, _abi.METHOD_RLM, _abi.PADJ_BH)
+    prob.tested_coef, prob.rlm_cov_mode = coef, cov
+    gpu, ref = _both(engine, oracle, prob)
+    assert_parity(gpu, ref, prob, rtol=1e-8, what=f"rlm G{G} n{n}: ")
+
+
+def test_row_major_layout_matches_col_major(engine):
+    a = synth.random_problem(50, 40, 120, 2, 31)
+    b = synth.random_problem(50, 40, 120, 2, 31, row_major=True)
+    ra, rb = engine.run_omic(a, ALL_FIELDS), engine.run_omic(b, ALL_FIELDS)
+    for k in ra:
+        assert np.array_equal(ra[k], rb[k], equal_nan=True), k
+
+
+def test_edge_cases_status(engine, oracle):
+    prob = synth.random_problem(30, 40, 50, 2, 41)
+    v = prob.assay.copy()
+    v[3, :] = 7.0                                  # constant gene -> singular when it is the predictor
+    v[5, prob.group == 1] = 2.5                    # constant inside one category
+    v[8, 4] = np.nan                               # NA
+    v[9, 2] = np.inf
+    prob.assay = np.asfortranarray(v)
+    fr = np.concatenate([prob.from_idx, [4, 6, 9, 10, 12, 12]]).astype(np.int32)
+    to = np.concatenate([prob.to_idx, [1, 2, 3, 11, 12, 13]]).astype(np.int32)   # includes a self-loop 12->12
+    prob.from_idx, prob.to_idx = fr, to
+    gpu, ref = _both(engine, oracle, prob)
+    assert set(np.unique(gpu["status"])) >= {0, 1, 2, 5}
+    assert_parity(gpu, ref, prob, what="edge cases: ")
+
+
+def test_ties_and_clamped_values(engine, oracle):
+    prob = synth.random_problem(60, 50, 200, 3, 51)
+    v = np.round(prob.assay, 1)                    # heavy ties: medians / quantiles hit equal values
+    v[v < 4.0] = 0.0                               # clamp floor as in data-raw/synthetic_data.R:254-255
+    prob.assay = np.asfortranarray(v)
+    gpu, ref = _both(engine, oracle, prob)
+    assert_parity(gpu, ref, prob, what="ties: ")
+
+
+def test_zero_sample_category_and_empty_percentiles(engine, oracle):
+    prob = synth.random_problem(40, 30, 100, 2, 61)
+    prob.K = 3                                     # level 3 exists but has no sample (quirk q2)
+    prob.pct = np.array([0.0, 0.5, 0.999999, 1.0])
+    gpu, ref = _both(engine, oracle, prob)
+    assert_parity(gpu, ref, prob, what="empty category: ")
+
+
+def test_device_tails_match_oracle(engine, oracle):
+    rng = np.random.default_rng(7)
+    t = np.concatenate([rng.standard_normal(2000) * 3, [0.0, 1e-8, 40.0, -40.0, 9.9, 10.1, 28.8]])
+    for df in (1.0, 2.0, 5.0, 18.0, 96.0, 996.0, 1996.0, 4e5):
+        got = engine.dev_pt(t, df)
+        ref = np.array([oracle.lib().orc_pt(float(x), df) for x in t])
+        assert np.all(np.abs(got - ref) <= 1e-13), df
+        got2 = engine.dev_p_two_sided_ref(t, df)
+        ref2 = np.array([oracle.lib().orc_p_two_sided_ref(float(x), df) for x in t])
+        assert np.all(np.abs(got2 - ref2) <= 1e-9 * ref2 + 4.5e-16), df
+    f = np.abs(rng.standard_normal(2000)) * 10
+    f = np.concatenate([f, [0.0, 1e-12, 1e3, 1e6]])
+    for d1, d2 in ((1.0, 96.0), (2.0, 994.0), (3.0, 20.0), (7.0, 1992.0), (1.0, 1e5)):
+        got = engine.dev_pf_upper(f, d1, d2)
+        ref = np.array([oracle.lib().orc_pf_upper(float(x), d1, d2) for x in f])
+        assert np.all(np.abs(got - ref) <= 1e-10 * ref + 1e-300), (d1, d2)
+
+
+# ---- the reference's own test expectations, through the public API on the GPU ------------------------
+def test_get_diffNetworks_multi_omics(engine, bundled):
+    """tests/testthat/test-core_functions.R:2-51"""
+    assays = {k: bundled[k] for k in ("RNAseq", "Proteomics", "Olink")}
+    deggs = md.get_diffNetworks(assayData=assays, metadata=bundled["metadata"], category_variable="response",
+                                regression_method="lm", padj_method="bonferroni", verbose=False,
+                                show_progressBar=False, cores=1, engine=engine)
+    assert isinstance(deggs, md.Deggs) and tuple(deggs.keys()) == md.Deggs.FIELDS
+    assert deggs["diffNetworks"]["RNAseq"]["sig_pvalues_count"] == 7
+    assert deggs["diffNetworks"]["RNAseq"]["Responder"].shape[0] == 3
+    assert deggs["diffNetworks"]["Proteomics"]["Responder"] == md.NO_LINKS
+    assert deggs["diffNetworks"]["Olink"]["Non_responder"].shape[1] == 4
+    assert deggs["diffNetworks"]["Olink"]["Responder"] == md.NO_LINKS
+    nr = deggs["diffNetworks"]["RNAseq"]["Non_responder"]
+    assert "TNF" in set(nr["from"]) and "TNFRSF1A" in set(nr["to"])
+
+
+def test_get_multiOmics_diffNetworks_rlm_BH(engine, bundled):
+    """tests/testthat/test-core_functions.R:55-91"""
+    assays = {k: bundled[k] for k in ("RNAseq", "Olink")}
+    deggs = md.get_diffNetworks(assayData=assays, metadata=bundled["metadata"], category_variable="response",
+                                regression_method="rlm", padj_method="BH", verbose=False, show_progressBar=False,
+                                cores=1, engine=engine)
+    res = md.get_multiOmics_diffNetworks(deggs)
+    assert len(res) == 2
+    assert res["Non_responder"].shape[1] == 5
+    assert list(res["Responder"].columns) == ["from", "to", "p.value", "p.adj", "layer"]
+    assert res["Responder"].shape[0] == 3
+    assert "AKT2" in set(res["Non_responder"]["from"]) and "MTOR" in set(res["Non_responder"]["to"])
+    assert "FANCD2" in set(res["Responder"]["from"]) and "FAN1" in set(res["Responder"]["to"])
+
+
+def test_get_sig_deggs_single_omic(engine, bundled):
+    """tests/testthat/test-core_functions.R:95-127"""
+    deggs = md.get_diffNetworks(assayData=bundled["RNAseq"], metadata=bundled["metadata"],
+                                category_variable="response", regression_method="lm", padj_method="bonferroni",
+                                verbose=False, show_progressBar=False, cores=1, engine=engine)
+    res = md.get_sig_deggs(deggs)
+    assert res.shape == (7, 4)
+    for a, b in (("TNF", "TNFRSF1A"), ("TGFB3", "TGFBR1"), ("IL1B", "IL1R2")):
+        assert a in set(res["from"]) and b in set(res["to"])
+
+
+def test_multiDEGGs_filter_and_predict(engine, bundled):
+    """tests/testthat/test-ML_functions.R:2-17, 57-69 (the nestedcv-free parts)"""
+    x = bundled["RNAseq"].T
+    y = bundled["metadata"]["response"].cat.codes.to_numpy() + 1.0
+    res = md.multiDEGGs_filter(y=y, x=x, engine=engine)
+    assert res["pairs"].shape == (7, 4)
+    assert "IL1B" in set(res["pairs"]["from"]) and "IL1R2" in set(res["pairs"]["to"])
+    assert "FASLG" in set(res["pairs"]["from"]) and "FAS" in set(res["pairs"]["to"])
+    res5 = md.multiDEGGs_filter(y=y, x=x, nfilter=5, engine=engine)
+    assert res5["pairs"].shape[0] == 5          # first-N rows in network order (fs:148-150)
+    assert "FANCD2" in set(res5["pairs"]["from"]) and "FAN1" in set(res5["pairs"]["to"])
+    feats = md.predict(res, x, engine=engine)
+    assert feats.shape == (100, 7) and "TNF:TNFRSF1A" in feats.columns
+    a, b = x["TNF"].to_numpy(), x["TNFRSF1A"].to_numpy()
+    expect = np.where(np.isfinite(a / b), a / b, 0.0)
+    assert np.array_equal(feats["TNF:TNFRSF1A"].to_numpy(), expect)
+
+
+def test_cfg3_scaled_down(engine, oracle):
+    wl = synth.cfg3(n_genes=3000, n_samples=120, max_edges=4000)
+    prob = wl.problem()
+    gpu, ref = _both(engine, oracle, prob, ("cutoff", "p_edge", "stat", "status", "tot_edges", "sig_count",
+                                           "fail_count", "best", "cat_best", "padj_best", "median"))
+    assert_parity(gpu, ref, prob, what="cfg3-small: ")
+
+
+def test_cfg5_scaled_down(engine, oracle):
+    wl = synth.cfg5(n_features=120, n_samples=200, planted=0.01)
+    prob = wl.problem()
+    gpu, ref = _both(engine, oracle, prob)
+    assert_parity(gpu, ref, prob, what="cfg5-small: ")
+
+
+def test_stats_and_launch_count(engine):
+    prob = synth.random_problem(50, 40, 120, 2, 71)
+    engine.run_omic(prob)
+    st = engine.stats()
+    assert st["kernel_launches"] > 5 and st["unique_fits"] == 120 and st["n_nodes"] > 0
+    assert st["fit_bytes"] == 120 * (16 * 40 + 16)
