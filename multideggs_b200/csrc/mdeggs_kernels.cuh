@@ -346,7 +346,7 @@ __device__ __forceinline__ void finish_pair(const SegLayout& L, const double* __
   *stat_out = stat;
   *status_out = singular ? MDEGGS_EDGE_SINGULAR : (exact_fit ? MDEGGS_EDGE_SELFLOOP : MDEGGS_EDGE_OK);
   if (coef_out) {  // R order: (Intercept), A, metadata2..K, A:metadata2..K; NA when the reference level is empty
-    const bool ok = !singular && L.cnt[0] > 0;
+    const bool ok = !singular && !exact_fit && L.cnt[0] > 0;
     coef_out[0] = ok ? icpt[0] : nan("");
     coef_out[1] = ok ? slope[0] : nan("");
 #pragma unroll
