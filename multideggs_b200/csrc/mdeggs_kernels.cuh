@@ -28,7 +28,7 @@ struct SegLayout {
 // order-preserving map double -> uint64; every NaN maps to the maximum key
 __device__ __forceinline__ unsigned long long dkey(double v) {
   if (isnan(v)) return ~0ull;
-  unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  unsigned long long b = (unsigned long long)__double_as_longlong(__dadd_rn(v, 0.0));  // -0.0 -> +0.0
   return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
 }
 __device__ __forceinline__ double dkey_inv(unsigned long long k) {
@@ -139,16 +139,58 @@ __global__ void __launch_bounds__(256) k_gather_rowmajor(const double* __restric
 // One CTA per gene, the row staged in shared memory; one warp per category. The exact median is an order
 // statistic found by 64-step bisection on the sortable key (no sort, no scratch).
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned long long warp_select_key(const double* seg, int m, int kth, int lane) {
-  unsigned long long prefix = 0;
-  for (int bit = 63; bit >= 0; --bit) {
-    unsigned long long cand = prefix | (1ull << bit);
+// Exact k-th smallest (0-based) of m keys held behind `key_at(i)`, one warp.  Keys are known to lie in
+// [kmin, kmax] except NaN keys (== ~0), which sit above every valid key and are never selected (kth < n_valid).
+// Bisection on the key bits starts below the common prefix of kmin/kmax and stops as soon as the candidate
+// interval holds <= 32 keys; those are spread one per lane and ranked with 32 shuffles.  Typical cost for a
+// few hundred values: ~6 counting passes instead of 64.
+template <class KeyAt>
+__device__ __forceinline__ unsigned long long warp_select(KeyAt key_at, int m, int kth, unsigned long long kmin,
+                                                          unsigned long long kmax, int n_valid,
+                                                          unsigned long long* scratch32, int lane) {
+  if (kmin == kmax) return kmin;
+  const int top = 63 - __clzll((long long)(kmin ^ kmax));
+  unsigned long long prefix = (top == 63) ? 0ull : (kmin >> (top + 1)) << (top + 1);
+  int cnt_lo = 0, cnt_hi = n_valid;  // keys < prefix, keys < prefix + 2^(bit+1)
+  int bit = top;
+  for (; bit >= 0 && cnt_hi - cnt_lo > 32; --bit) {
+    const unsigned long long cand = prefix | (1ull << bit);
     int c = 0;
-    for (int i = lane; i < m; i += 32) c += (dkey(seg[i]) < cand);
+    for (int i = lane; i < m; i += 32) c += (key_at(i) < cand);
     c = __reduce_add_sync(0xffffffffu, c);
-    if (c <= kth) prefix = cand;
+    if (c <= kth) {
+      prefix = cand;
+      cnt_lo = c;
+    } else {
+      cnt_hi = c;
+    }
   }
-  return prefix;
+  if (bit < 0) return prefix;  // > 32 identical keys: the prefix is the key itself
+  // candidates: prefix <= key < prefix + 2^(bit+1)   (bit+1 == 64 cannot happen here: top < 64 and bit <= top)
+  const unsigned long long span = (bit == 63) ? ~0ull : ((1ull << (bit + 1)) - 1ull);
+  const unsigned long long hi_incl = prefix | span;
+  int base = 0;
+  for (int i0 = 0; i0 < m; i0 += 32) {
+    int i = i0 + lane;
+    unsigned long long k = i < m ? key_at(i) : ~0ull;
+    bool in = i < m && k >= prefix && k <= hi_incl && k != ~0ull;
+    unsigned mask = __ballot_sync(0xffffffffu, in);
+    if (in) scratch32[base + __popc(mask & ((1u << lane) - 1u))] = k;
+    base += __popc(mask);
+  }
+  __syncwarp();
+  const int ncand = cnt_hi - cnt_lo;
+  unsigned long long mine = lane < ncand ? scratch32[lane] : ~0ull;
+  int r = 0;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    unsigned long long other = __shfl_sync(0xffffffffu, mine, j);
+    r += (other < mine) || (other == mine && j < lane);
+  }
+  unsigned hit = __ballot_sync(0xffffffffu, lane < ncand && r == kth - cnt_lo);
+  unsigned long long res = __shfl_sync(0xffffffffu, mine, __ffs(hit) - 1);
+  __syncwarp();
+  return res;
 }
 
 template <int THREADS>
@@ -159,6 +201,7 @@ __global__ void __launch_bounds__(THREADS) k_gene_stats(double* __restrict__ D, 
                                                        int use_smem) {
   extern __shared__ double srow[];
   __shared__ int s_bad;
+  __shared__ unsigned long long s_cand[THREADS / 32][32];
   const int node = blockIdx.x;
   if (node >= *n_nodes_p) return;
   double* grow = D + (size_t)node * L.npad;
@@ -210,17 +253,19 @@ __global__ void __launch_bounds__(THREADS) k_gene_stats(double* __restrict__ D, 
       mu = vmin;
       d2 = 0.0;
     }
-    // exact median of the non-NaN values
+    // exact median of the non-NaN values (fmin/fmax ignore NaN, so vmin/vmax bound every valid key)
     double median = nan("");
     if (nn > 0) {
+      auto key_at = [&](int i) { return dkey(seg[i]); };
+      const unsigned long long kmin = dkey(vmin), kmax = dkey(vmax);
       if (nn & 1) {
-        median = dkey_inv(warp_select_key(seg, m, nn / 2, lane));
+        median = dkey_inv(warp_select(key_at, m, nn / 2, kmin, kmax, nn, s_cand[warp], lane));
       } else {
-        unsigned long long k1 = warp_select_key(seg, m, nn / 2 - 1, lane);
+        unsigned long long k1 = warp_select(key_at, m, nn / 2 - 1, kmin, kmax, nn, s_cand[warp], lane);
         int c_le = 0;
         unsigned long long nxt = ~0ull;
         for (int i = lane; i < m; i += 32) {
-          unsigned long long kk = dkey(seg[i]);
+          unsigned long long kk = key_at(i);
           c_le += (kk <= k1);
           if (kk > k1 && kk < nxt) nxt = kk;
         }

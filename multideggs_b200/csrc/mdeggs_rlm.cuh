@@ -23,35 +23,36 @@ struct GroupFit {
   double W, ma, mb, sxx, sxy, slope, icpt;
 };
 
-// median of |r| over the real (non-padding) samples: exact order statistic by bisection on the IEEE bits
-// (|r| >= 0, so the raw bit pattern is already order preserving)
-__device__ __forceinline__ double warp_median_abs(const double* r, const SegLayout& L, int lane) {
-  const int n = L.n;
-  auto count_less = [&](unsigned long long cand) {
-    int c = 0;
-    for (int k = 0; k < 2; ++k)
-      for (int i = L.off[k] + lane; i < L.off[k] + L.cnt[k]; i += 32)
-        c += ((unsigned long long)__double_as_longlong(fabs(r[i])) < cand);
-    return __reduce_add_sync(0xffffffffu, c);
+// median of |r| over the real (non-padding) samples: exact order statistic (|r| >= 0, so the raw IEEE bit
+// pattern is already order preserving); narrowing bisection + in-warp ranking (warp_select)
+__device__ __forceinline__ double warp_median_abs(const double* r, const SegLayout& L, int lane,
+                                                  unsigned long long* scratch32) {
+  const int n = L.n, c0 = L.cnt[0], o0 = L.off[0], o1 = L.off[1];
+  auto key_at = [&](int i) {
+    int idx = i < c0 ? o0 + i : o1 + (i - c0);
+    return (unsigned long long)__double_as_longlong(fabs(r[idx]));
   };
-  auto select = [&](int kth) {
-    unsigned long long prefix = 0;
-    for (int bit = 62; bit >= 0; --bit) {
-      unsigned long long cand = prefix | (1ull << bit);
-      if (count_less(cand) <= kth) prefix = cand;
-    }
-    return prefix;
-  };
-  if (n & 1) return __longlong_as_double((long long)select(n / 2));
-  unsigned long long k1 = select(n / 2 - 1);
+  unsigned long long kmin = ~0ull, kmax = 0ull;
+  for (int i = lane; i < n; i += 32) {
+    unsigned long long k = key_at(i);
+    kmin = k < kmin ? k : kmin;
+    kmax = k > kmax ? k : kmax;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    unsigned long long a = __shfl_xor_sync(0xffffffffu, kmin, o), b = __shfl_xor_sync(0xffffffffu, kmax, o);
+    kmin = a < kmin ? a : kmin;
+    kmax = b > kmax ? b : kmax;
+  }
+  if (n & 1) return __longlong_as_double((long long)warp_select(key_at, n, n / 2, kmin, kmax, n, scratch32, lane));
+  unsigned long long k1 = warp_select(key_at, n, n / 2 - 1, kmin, kmax, n, scratch32, lane);
   int c_le = 0;
   unsigned long long nxt = ~0ull;
-  for (int k = 0; k < 2; ++k)
-    for (int i = L.off[k] + lane; i < L.off[k] + L.cnt[k]; i += 32) {
-      unsigned long long kk = (unsigned long long)__double_as_longlong(fabs(r[i]));
-      c_le += (kk <= k1);
-      if (kk > k1 && kk < nxt) nxt = kk;
-    }
+  for (int i = lane; i < n; i += 32) {
+    unsigned long long kk = key_at(i);
+    c_le += (kk <= k1);
+    if (kk > k1 && kk < nxt) nxt = kk;
+  }
   c_le = __reduce_add_sync(0xffffffffu, c_le);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -72,6 +73,7 @@ __global__ void __launch_bounds__(256) k_fit_rlm(const double* __restrict__ D, S
                                                  int32_t* __restrict__ status, double* __restrict__ coef,
                                                  int32_t* __restrict__ iters) {
   extern __shared__ double smem[];
+  __shared__ unsigned long long s_cand[8][32];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   const int per_warp = CACHE_AB ? 3 * L.npad : L.npad;
   double* r = smem + (size_t)wib * per_warp;
@@ -144,7 +146,7 @@ __global__ void __launch_bounds__(256) k_fit_rlm(const double* __restrict__ D, S
     bool done = false, zero_scale = false;
     int it = 0;
     for (it = 1; it <= 20; ++it) {
-      scale = warp_median_abs(r, L, lane) / 0.6745;
+      scale = warp_median_abs(r, L, lane, s_cand[wib]) / 0.6745;
       if (scale == 0.0) {
         zero_scale = true;
         done = true;

@@ -437,7 +437,10 @@ int orc_fit_lm_interaction(const double* a, const double* b, const double* g01, 
   for (int i = 0; i < n; ++i) rss += resid[i] * resid[i];
   double sigma2 = rss / dof;
   double inv[16];
-  if (small_inverse(xtx, 4, inv)) return MDEGGS_EDGE_SINGULAR; /* solve() throws */
+  if (small_inverse(xtx, 4, inv)) { /* solve() throws: no coefficients reach the caller */
+    for (int j = 0; j < 4; ++j) coef4[j] = NAN;
+    return MDEGGS_EDGE_SINGULAR;
+  }
   double se4 = sqrt(sigma2 * inv[15]);
   double t = coef4[3] / se4;
   *t_out = t;
