@@ -1,0 +1,162 @@
+// mdeggs_dense.cuh — K4D: pair fits for DENSE networks (e.g. the user-supplied all-pairs network of
+// BASELINE config 5: 4,000 features, 7,998,000 edges).
+//
+// Same arithmetic as k_fit_stream (fit_lm_interaction, R/core_functions.R:1058-1074; aov row 3, 966-968):
+// every edge needs the K within-category centred cross moments Sxy_k(a,b).  When the edge list covers a
+// large fraction of all node pairs, streaming two 16n-byte rows per edge re-reads each gene row thousands of
+// times (config 5: 256 GB of L1/L2 traffic).  Here a CTA stages a 128-gene x 8-sample tile of two row blocks
+// in shared memory (centred on the fly) and accumulates the 128x128 block of cross moments in registers
+// (8x8 per thread, plain FP64 FMAs — no tensor cores), so each row is read nn/128 times instead of ~nn times.
+// Only tile pairs with ti <= tj are computed (Sxy is symmetric); k_fit_dense_edges then finishes each edge
+// from Sxy[min(a,b)][max(a,b)] with the same closed forms as the streaming kernel (finish_pair).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "mdeggs_kernels.cuh"
+
+namespace mdeggs {
+
+constexpr int DT = 128;   // tile edge (genes)
+constexpr int DKC = 8;    // samples per shared-memory stage (2 stages x 2 tiles = 33 KB static smem)
+constexpr int DLD = DT + 2;  // padded leading dimension of the transposed stage [DKC][DLD]
+
+// S[k][i][j] (row-major nn x nn per category), written for tile pairs ti <= tj
+__global__ void __launch_bounds__(256, 1) k_dense_moments(const double* __restrict__ D, SegLayout L,
+                                                          const double* __restrict__ mean, int nn, int ntiles,
+                                                          double* __restrict__ S) {
+  __shared__ __align__(16) double As[2][DKC][DLD];
+  __shared__ __align__(16) double Bs[2][DKC][DLD];
+  // blockIdx.x -> (ti, tj) with ti <= tj  (row-wise enumeration of the upper triangle)
+  int ti = 0, rem = blockIdx.x;
+  while (rem >= ntiles - ti) {
+    rem -= ntiles - ti;
+    ++ti;
+  }
+  const int tj = ti + rem;
+  const int k = blockIdx.y;
+  const int seg_beg = L.off[k], seg_len = L.off[k + 1] - L.off[k];
+  if (L.cnt[k] == 0) return;
+  const int i0 = ti * DT, j0 = tj * DT;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  // loader mapping: 128 rows x 8 samples = 512 double2; thread handles rows lr + 64 q (q = 0,1), sample pair lc
+  const int lc = tid & 3, lr = tid >> 2;
+  double ma[2], mb[2];
+  const double* pa[2];
+  const double* pb[2];
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    int ra = i0 + lr + 64 * q, rb = j0 + lr + 64 * q;
+    bool va = ra < nn, vb = rb < nn;
+    ma[q] = va ? mean[(size_t)ra * L.K + k] : 0.0;
+    mb[q] = vb ? mean[(size_t)rb * L.K + k] : 0.0;
+    pa[q] = va ? D + (size_t)ra * L.npad + seg_beg + 2 * lc : nullptr;
+    pb[q] = vb ? D + (size_t)rb * L.npad + seg_beg + 2 * lc : nullptr;
+  }
+  double acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
+
+  double2 ra_reg[2], rb_reg[2];
+  auto gload = [&](int kk) {  // segment length is a multiple of 4, DKC = 8: guard the tail per double2
+    const bool in = kk + 2 * lc < seg_len;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      ra_reg[q] = (in && pa[q]) ? __ldg(reinterpret_cast<const double2*>(pa[q] + kk)) : make_double2(ma[q], ma[q]);
+      rb_reg[q] = (in && pb[q]) ? __ldg(reinterpret_cast<const double2*>(pb[q] + kk)) : make_double2(mb[q], mb[q]);
+    }
+  };
+  auto sstore = [&](int buf) {  // transposed + centred
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      As[buf][2 * lc][lr + 64 * q] = ra_reg[q].x - ma[q];
+      As[buf][2 * lc + 1][lr + 64 * q] = ra_reg[q].y - ma[q];
+      Bs[buf][2 * lc][lr + 64 * q] = rb_reg[q].x - mb[q];
+      Bs[buf][2 * lc + 1][lr + 64 * q] = rb_reg[q].y - mb[q];
+    }
+  };
+  gload(0);
+  sstore(0);
+  __syncthreads();
+  int buf = 0;
+  for (int kk = 0; kk < seg_len; kk += DKC) {
+    const bool more = kk + DKC < seg_len;
+    if (more) gload(kk + DKC);
+#pragma unroll
+    for (int s = 0; s < DKC; ++s) {
+      double a[8], b[8];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        double2 va = *reinterpret_cast<const double2*>(&As[buf][s][ty * 2 + 32 * g]);
+        double2 vb = *reinterpret_cast<const double2*>(&Bs[buf][s][tx * 2 + 32 * g]);
+        a[2 * g] = va.x;
+        a[2 * g + 1] = va.y;
+        b[2 * g] = vb.x;
+        b[2 * g + 1] = vb.y;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+    }
+    if (more) {
+      sstore(buf ^ 1);
+      __syncthreads();
+      buf ^= 1;
+    }
+  }
+  double* Sk = S + (size_t)k * nn * nn;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = i0 + ty * 2 + 32 * (i >> 1) + (i & 1);
+    if (r >= nn) continue;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const int c = j0 + tx * 2 + 32 * g;
+      if (c + 1 < nn && !(nn & 1)) {  // 16-byte aligned only when the row pitch is even
+        *reinterpret_cast<double2*>(Sk + (size_t)r * nn + c) = make_double2(acc[i][2 * g], acc[i][2 * g + 1]);
+      } else {
+        if (c < nn) Sk[(size_t)r * nn + c] = acc[i][2 * g];
+        if (c + 1 < nn) Sk[(size_t)r * nn + c + 1] = acc[i][2 * g + 1];
+      }
+    }
+  }
+}
+
+// one thread per edge: gather the K cross moments of the pair and finish with the shared closed forms
+template <int K>
+__global__ void __launch_bounds__(256) k_fit_dense_edges(const double* __restrict__ S, SegLayout L, int nn,
+                                                         const int32_t* __restrict__ from,
+                                                         const int32_t* __restrict__ to,
+                                                         const int32_t* __restrict__ node_of_row,
+                                                         const double* __restrict__ mean,
+                                                         const double* __restrict__ sxx,
+                                                         const uint8_t* __restrict__ bad, int64_t e_lo, int64_t e_hi,
+                                                         double* __restrict__ stat, int32_t* __restrict__ status,
+                                                         double* __restrict__ coef) {
+  const int64_t e = e_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= e_hi) return;
+  const int ra = from[e] - 1, rb = to[e] - 1;
+  const int a = node_of_row[ra], b = node_of_row[rb];
+  if (ra == rb || bad[a] || bad[b]) {
+    bool self = (ra == rb) && !bad[a];
+    stat[e] = self ? 0.0 : nan("");
+    status[e] = self ? MDEGGS_EDGE_SELFLOOP : MDEGGS_EDGE_NONFINITE;
+    if (coef)
+      for (int j = 0; j < 2 * K; ++j) coef[(size_t)e * 2 * K + j] = nan("");
+    return;
+  }
+  const int i = a < b ? a : b, j = a < b ? b : a;
+  PairMoments<K> pm;
+#pragma unroll
+  for (int k = 0; k < K; ++k) pm.sxy[k] = L.cnt[k] ? __ldg(S + ((size_t)k * nn + i) * nn + j) : 0.0;
+  finish_pair<K>(L, mean, sxx, a, b, pm, stat + e, status + e, coef ? coef + (size_t)e * 2 * K : nullptr);
+}
+
+// dense path pays off when the edge list is a sizeable fraction of all node pairs:
+// streaming moves 16 n E bytes through L1/L2, the tiles do ~nn^2 n FP64 FMAs; at comparable rates 16 E > nn^2
+inline bool dense_path_candidate(int64_t E, int64_t nn) { return nn >= 256 && 16 * E >= nn * nn; }
+
+}  // namespace mdeggs

@@ -12,6 +12,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <cub/device/device_radix_sort.cuh>
@@ -20,8 +21,10 @@
 #include <vector>
 
 #include "mdeggs.h"
+#include "mdeggs_dense.cuh"
 #include "mdeggs_kernels.cuh"
 #include "mdeggs_rlm.cuh"
+#include "mdeggs_select.cuh"
 #include "nccl_dl.h"
 
 using namespace mdeggs;
@@ -66,13 +69,13 @@ struct Shard {
   DevBuf assay, from, to, flags, excl, node_of_row, rowlist, scal, src_of_pos, pct, cutoff, D, keys, keys_sorted,
       cub_tmp, cub_tmp2, mean, sxx, med, bad, stat, status, p_edge, coef, iters, act, counters, sortk, sortk2, idx,
       idx2, ps, sa, sb, tile_cnt, tile_base, seg_n, tile_min, tile_carry, padj_best, cat_best, cat, padj, med_out,
-      small_out, rlm_ws;
+      small_out, rlm_ws, rsel_hist, rsel_state, dense_S, cf_tab;
   void release_all() {
     DevBuf* all[] = {&assay, &from, &to, &flags, &excl, &node_of_row, &rowlist, &scal, &src_of_pos, &pct, &cutoff,
                      &D, &keys, &keys_sorted, &cub_tmp, &cub_tmp2, &mean, &sxx, &med, &bad, &stat, &status, &p_edge,
                      &coef, &iters, &act, &counters, &sortk, &sortk2, &idx, &idx2, &ps, &sa, &sb, &tile_cnt,
                      &tile_base, &seg_n, &tile_min, &tile_carry, &padj_best, &cat_best, &cat, &padj, &med_out,
-                     &small_out, &rlm_ws};
+                     &small_out, &rlm_ws, &rsel_hist, &rsel_state, &dense_S, &cf_tab};
     for (DevBuf* b : all) b->release();
   }
 };
@@ -85,6 +88,8 @@ struct mdeggs_ctx {
   mdeggs_stats stats;
   int64_t launches = 0;
   bool smem_attr_set = false;
+  bool rsel_attr_set = false;
+  int fit_path_override = -1;  // -1 auto, 0 force streaming, 1 force dense (MDEGGS_FIT_PATH, tests)
 };
 
 namespace {
@@ -172,6 +177,14 @@ int build_layout(mdeggs_ctx* ctx, const mdeggs_problem* in, HostLayout& H) {
 }
 
 template <int K>
+void launch_fit_dense_edges(mdeggs_ctx* ctx, Shard& s, const SegLayout& L, int nn, int64_t e_lo, int64_t e_hi,
+                            double* coef) {
+  LAUNCH(k_fit_dense_edges<K>, blocks_for(e_hi - e_lo, 256), 256, 0, s.s_main, s.dense_S.as<double>(), L, nn,
+         s.from.as<int32_t>(), s.to.as<int32_t>(), s.node_of_row.as<int32_t>(), s.mean.as<double>(),
+         s.sxx.as<double>(), s.bad.as<uint8_t>(), e_lo, e_hi, s.stat.as<double>(), s.status.as<int32_t>(), coef);
+}
+
+template <int K>
 void launch_fit_stream(mdeggs_ctx* ctx, Shard& s, const SegLayout& L, int64_t e_lo, int64_t e_hi, double* coef) {
   int64_t ne = e_hi - e_lo;
   if (ne <= 0) return;
@@ -215,11 +228,13 @@ int run_adjust(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, int n_segmen
   LAUNCH(k_bh_scan_tiles, n_segments, 256, 0, s.s_main, s.tile_cnt.as<int32_t>(), ntiles, s.tile_base.as<long long>(),
          s.seg_n.as<long long>());
   if (in->padj == MDEGGS_PADJ_BH) {
-    LAUNCH(k_bh_tilemin, grid, BH_THREADS, 0, s.s_main, A, s.tile_base.as<long long>(), s.seg_n.as<long long>(),
+    LAUNCH(k_bh_tilemin, grid, BH_THREADS, 0, s.s_main, A, s.tile_cnt.as<int32_t>(), s.tile_base.as<long long>(),
+           s.seg_n.as<long long>(),
            s.tile_min.as<double>());
     LAUNCH(k_bh_suffix_min, n_segments, 256, 0, s.s_main, s.tile_min.as<double>(), ntiles, s.tile_carry.as<double>());
   }
-  LAUNCH(k_bh_final, grid, BH_THREADS, 0, s.s_main, A, in->padj, s.tile_base.as<long long>(), s.seg_n.as<long long>(),
+  LAUNCH(k_bh_final, grid, BH_THREADS, 0, s.s_main, A, in->padj, s.tile_cnt.as<int32_t>(), s.tile_base.as<long long>(),
+         s.seg_n.as<long long>(),
          s.tile_carry.as<double>(), sig_dev, padj_out, padj_stride);
   return MDEGGS_OK;
 }
@@ -323,8 +338,6 @@ int run_shard_main(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
   const size_t nn = (size_t)(n_nodes > 0 ? n_nodes : 1);
   // ---- K1 gather ----
   CU(s.D.ensure(nn * (size_t)L.npad * 8));
-  CU(s.keys.ensure(nn * (size_t)n * 8));
-  CU(s.keys_sorted.ensure(nn * (size_t)n * 8));
   CU(s.mean.ensure(nn * K * 8));
   CU(s.sxx.ensure(nn * K * 8));
   CU(s.med.ensure(nn * K * 8));
@@ -334,29 +347,37 @@ int run_shard_main(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
     if (in->layout == MDEGGS_LAYOUT_COLMAJOR) {
       dim3 grid((unsigned)((L.npad + 31) / 32), (unsigned)((n_nodes + 31) / 32));
       LAUNCH(k_gather_colmajor, grid, 256, 0, s.s_main, s.assay.as<double>(), in->ld, s.rowlist.as<int32_t>(), d_nn,
-             s.src_of_pos.as<int32_t>(), L.npad, n, s.D.as<double>(), s.keys.as<unsigned long long>());
+             s.src_of_pos.as<int32_t>(), L.npad, n, s.D.as<double>());
     } else {
       dim3 grid((unsigned)((L.npad + 255) / 256), (unsigned)n_nodes);
       LAUNCH(k_gather_rowmajor, grid, 256, 0, s.s_main, s.assay.as<double>(), in->ld, s.rowlist.as<int32_t>(), d_nn,
-             s.src_of_pos.as<int32_t>(), L.npad, n, s.D.as<double>(), s.keys.as<unsigned long long>());
+             s.src_of_pos.as<int32_t>(), L.npad, n, s.D.as<double>());
     }
   }
   CU(cudaEventRecord(s.ev[EV_GATHER], s.s_main));
-  // ---- K3 on the side stream: sort all values once, read every percentile's cut-off ----
+  // ---- K3 on the side stream: radix-select every percentile's two order statistics (no sort) ----
   CU(cudaEventRecord(s.ev_fork, s.s_main));
   CU(cudaStreamWaitEvent(s.s_sort, s.ev_fork, 0));
   CU(cudaEventRecord(s.ev[EV_Q0], s.s_sort));
   if (n_nodes > 0 && P > 0) {
-    size_t tb = 0;
-    int64_t items = (int64_t)n_nodes * n;
-    cub::DeviceRadixSort::SortKeys(nullptr, tb, s.keys.as<unsigned long long>(), s.keys_sorted.as<unsigned long long>(),
-                                   items, 0, 64, s.s_sort);
-    CU(s.cub_tmp2.ensure(tb));
-    CU(cub::DeviceRadixSort::SortKeys(s.cub_tmp2.p, tb, s.keys.as<unsigned long long>(),
-                                      s.keys_sorted.as<unsigned long long>(), items, 0, 64, s.s_sort));
-    ctx->launches += 10;
-    LAUNCH(k_quantiles, 1, 64, 0, s.s_sort, s.keys_sorted.as<unsigned long long>(), d_nn, n, s.pct.as<double>(), P,
-           s.cutoff.as<double>());
+    const size_t hist_bytes = (size_t)2 * P * RSEL_BINS * sizeof(unsigned int);
+    CU(s.rsel_hist.ensure(hist_bytes));
+    CU(s.rsel_state.ensure(sizeof(RselState) + 16));
+    CU(cudaMemsetAsync(s.rsel_hist.p, 0, hist_bytes, s.s_sort));
+    CU(cudaMemsetAsync(s.rsel_state.p, 0, sizeof(RselState) + 16, s.s_sort));
+    RselState* d_st = s.rsel_state.as<RselState>();
+    unsigned long long* d_nan = reinterpret_cast<unsigned long long*>(s.rsel_state.as<char>() + sizeof(RselState));
+    const size_t hsmem = (size_t)RSEL_SMEM_SLOTS * RSEL_BINS * sizeof(unsigned int);
+    if (!ctx->rsel_attr_set) {
+      CU(cudaFuncSetAttribute(k_rsel_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsmem));
+      ctx->rsel_attr_set = true;
+    }
+    for (int pass = 0; pass < RSEL_PASSES; ++pass) {
+      LAUNCH(k_rsel_hist, 148 * 2, 512, hsmem, s.s_sort, s.D.as<double>(), s.src_of_pos.as<int32_t>(), L.npad, d_nn,
+             pass, d_st, s.rsel_hist.as<unsigned int>(), d_nan);
+      LAUNCH(k_rsel_scan, (unsigned)(pass == 0 ? 1 : 2 * P), 256, 0, s.s_sort, pass, d_st, s.rsel_hist.as<unsigned int>(), d_nan, d_nn, n,
+             s.pct.as<double>(), P, s.cutoff.as<double>());
+    }
   } else if (P > 0) {
     LAUNCH(k_fill_f64, 1, 64, 0, s.s_sort, s.cutoff.as<double>(), (int64_t)P, nan(""));
   }
@@ -387,7 +408,21 @@ int run_shard_main(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
   if (want_coef) CU(s.coef.ensure(epad * 2 * K * 8));
   if (is_rlm) CU(s.iters.ensure(epad * 4));
   double* d_coef = want_coef ? s.coef.as<double>() : nullptr;
-  ctx->stats.fit_path = is_rlm ? 2 : 0;
+  bool use_dense = false;
+  if (!is_rlm && ctx->fit_path_override != 0) {
+    use_dense = ctx->fit_path_override == 1;
+    const size_t need = (size_t)K * (size_t)n_nodes * (size_t)n_nodes * 8;
+    if (ctx->fit_path_override < 0 && dense_path_candidate(E, n_nodes)) {
+      use_dense = need <= s.dense_S.cap;
+      if (!use_dense) {  // cudaMemGetInfo costs ~1 ms: only asked when the moment matrices must be (re)allocated
+        size_t free_b = 0, total_b = 0;
+        CU(cudaMemGetInfo(&free_b, &total_b));
+        use_dense = need < (free_b + s.dense_S.cap) / 2;
+      }
+    }
+    if (use_dense) CU(s.dense_S.ensure(need));
+  }
+  ctx->stats.fit_path = is_rlm ? 2 : (use_dense ? 1 : 0);
   if (e_hi > e_lo) {
     if (is_rlm) {
       int rc = launch_fit_rlm(ctx->launches, s.s_main, s.D.as<double>(), L, s.from.as<int32_t>(), s.to.as<int32_t>(),
@@ -397,6 +432,21 @@ int run_shard_main(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
       if (rc != 0) {
         set_err(ctx, "rlm kernel configuration failed (n too large for shared memory?)");
         return MDEGGS_EUNSUPPORTED;
+      }
+    } else if (use_dense) {
+      // all ranks compute the (replicated) moment matrices; only the edge finishing is sharded
+      const int ntl = (n_nodes + DT - 1) / DT;
+      dim3 grid((unsigned)(ntl * (ntl + 1) / 2), (unsigned)K);
+      LAUNCH(k_dense_moments, grid, 256, 0, s.s_main, s.D.as<double>(), L, s.mean.as<double>(), (int)n_nodes, ntl,
+             s.dense_S.as<double>());
+      switch (K) {
+        case 2: launch_fit_dense_edges<2>(ctx, s, L, n_nodes, e_lo, e_hi, d_coef); break;
+        case 3: launch_fit_dense_edges<3>(ctx, s, L, n_nodes, e_lo, e_hi, d_coef); break;
+        case 4: launch_fit_dense_edges<4>(ctx, s, L, n_nodes, e_lo, e_hi, d_coef); break;
+        case 5: launch_fit_dense_edges<5>(ctx, s, L, n_nodes, e_lo, e_hi, d_coef); break;
+        case 6: launch_fit_dense_edges<6>(ctx, s, L, n_nodes, e_lo, e_hi, d_coef); break;
+        case 7: launch_fit_dense_edges<7>(ctx, s, L, n_nodes, e_lo, e_hi, d_coef); break;
+        default: launch_fit_dense_edges<8>(ctx, s, L, n_nodes, e_lo, e_hi, d_coef); break;
       }
     } else {
       switch (K) {
@@ -424,9 +474,20 @@ int run_shard_main(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
     df2 = (double)(n - 2 * Ke);
     tail_mode = 1;
   }
-  if (e_hi > e_lo)
+  if (e_hi > e_lo) {
+    CU(s.cf_tab.ensure((size_t)(2 * CF_TABLE_LEN + 1) * 8));
+    TailConsts tc;
+    tc.a = tail_mode == 0 ? 0.5 : df1 / 2.0;
+    tc.b = df2 / 2.0;
+    tc.lbeta_ab = 0.0;
+    tc.e_ab = s.cf_tab.as<double>();
+    tc.e_ba = s.cf_tab.as<double>() + CF_TABLE_LEN;
+    const double* d_lbeta = s.cf_tab.as<double>() + 2 * CF_TABLE_LEN;
+    LAUNCH(k_cf_tables, 1, 256, 0, s.s_main, tc.a, tc.b, s.cf_tab.as<double>(), s.cf_tab.as<double>() + CF_TABLE_LEN,
+           s.cf_tab.as<double>() + 2 * CF_TABLE_LEN);
     LAUNCH(k_tail, blocks_for(e_hi - e_lo, 128), 128, 0, s.s_main, s.stat.as<double>(), s.status.as<int32_t>(), e_lo,
-           e_hi, tail_mode, df1, df2, s.p_edge.as<double>());
+           e_hi, tail_mode, df1, df2, tc, d_lbeta, s.p_edge.as<double>());
+  }
   CU(cudaEventRecord(s.ev[EV_TAIL], s.s_main));
   return MDEGGS_OK;
 }
@@ -673,6 +734,7 @@ int mdeggs_create(mdeggs_ctx** out, const int* device_ids, int n_dev) {
     if (device_ids[i] < 0 || device_ids[i] >= count) return MDEGGS_EINVAL;
   mdeggs_ctx* ctx = new mdeggs_ctx();
   memset(&ctx->stats, 0, sizeof ctx->stats);
+  if (const char* fp = getenv("MDEGGS_FIT_PATH")) ctx->fit_path_override = atoi(fp);
   ctx->shards.resize((size_t)n_dev);
   for (int i = 0; i < n_dev; ++i) {
     ctx->shards[(size_t)i].device = device_ids[i];
@@ -717,6 +779,7 @@ int mdeggs_create_rank(mdeggs_ctx** out, int device_id, int rank, int world, con
   if (device_id < 0 || device_id >= count) return MDEGGS_EINVAL;
   mdeggs_ctx* ctx = new mdeggs_ctx();
   memset(&ctx->stats, 0, sizeof ctx->stats);
+  if (const char* fp = getenv("MDEGGS_FIT_PATH")) ctx->fit_path_override = atoi(fp);
   ctx->shards.resize(1);
   Shard& s = ctx->shards[0];
   s.device = device_id;
@@ -782,6 +845,10 @@ int mdeggs_run_omic(mdeggs_ctx* ctx, const mdeggs_problem* in, mdeggs_result* ou
   if (in->K == 2 && in->method == MDEGGS_METHOD_RLM && (in->tested_coef < 1 || in->tested_coef > 4)) {
     set_err(ctx, "tested_coef must be 1..4");
     return MDEGGS_EINVAL;
+  }
+  if (2 * in->P > RSEL_MAX_T) {
+    set_err(ctx, "more than %d percentiles are not supported", RSEL_MAX_T / 2);
+    return MDEGGS_EUNSUPPORTED;
   }
   if (in->n <= 2 * in->K) {
     set_err(ctx, "n = %d leaves no residual degrees of freedom for K = %d", in->n, in->K);

@@ -73,15 +73,14 @@ __global__ void k_build_rowlist(const int32_t* __restrict__ flags, const int32_t
 // ------------------------------------------------------------------------------------------------
 // K1: gather + transposition  (replaces the per-pair `assayData[gene, ]` row look-ups, core_functions.R:880-881)
 //   in : R column-major G x n (gene fastest)  or row-major (sample fastest)
-//   out: D[node][pos] with category-contiguous samples; keys[node*n + s] sortable keys for the quantile sort
+//   out: D[node][pos] with category-contiguous samples
 // 32x32 smem tile, coalesced on both sides. Padding positions (src < 0) are written by k_gene_stats.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_gather_colmajor(const double* __restrict__ assay, int64_t ld,
                                                          const int32_t* __restrict__ rowlist,
                                                          const int32_t* __restrict__ n_nodes_p,
                                                          const int32_t* __restrict__ src_of_pos, int npad, int n,
-                                                         double* __restrict__ D,
-                                                         unsigned long long* __restrict__ keys) {
+                                                         double* __restrict__ D) {
   __shared__ double tile[32][33];
   const int n_nodes = *n_nodes_p;
   const int node0 = blockIdx.y * 32, pos0 = blockIdx.x * 32;
@@ -104,9 +103,7 @@ __global__ void __launch_bounds__(256) k_gather_colmajor(const double* __restric
   for (int i = ty; i < 32; i += 8) {
     int node = node0 + i;
     if (node < n_nodes && s_w >= 0) {
-      double v = tile[tx][i];
-      D[(size_t)node * npad + pos_w] = v;
-      keys[(size_t)node * n + s_w] = dkey(v);
+      D[(size_t)node * npad + pos_w] = tile[tx][i];
     }
   }
 }
@@ -115,8 +112,7 @@ __global__ void __launch_bounds__(256) k_gather_rowmajor(const double* __restric
                                                          const int32_t* __restrict__ rowlist,
                                                          const int32_t* __restrict__ n_nodes_p,
                                                          const int32_t* __restrict__ src_of_pos, int npad, int n,
-                                                         double* __restrict__ D,
-                                                         unsigned long long* __restrict__ keys) {
+                                                         double* __restrict__ D) {
   const int n_nodes = *n_nodes_p;
   const int node = blockIdx.y;
   if (node >= n_nodes) return;
@@ -124,9 +120,7 @@ __global__ void __launch_bounds__(256) k_gather_rowmajor(const double* __restric
   for (int pos = blockIdx.x * blockDim.x + threadIdx.x; pos < npad; pos += gridDim.x * blockDim.x) {
     int s = src_of_pos[pos];
     if (s >= 0) {
-      double v = __ldg(assay + row * ld + s);
-      D[(size_t)node * npad + pos] = v;
-      keys[(size_t)node * n + s] = dkey(v);
+      D[(size_t)node * npad + pos] = __ldg(assay + row * ld + s);
     }
   }
 }
@@ -293,44 +287,6 @@ __global__ void __launch_bounds__(THREADS) k_gene_stats(double* __restrict__ D, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// K3: type-7 quantiles of the whole node-filtered matrix from its sorted keys
-//   cut_off <- stats::quantile(as.matrix(assayData), prob = percentile, na.rm = TRUE)  core_functions.R:718
-// ------------------------------------------------------------------------------------------------
-__global__ void k_quantiles(const unsigned long long* __restrict__ sorted, const int32_t* __restrict__ n_nodes_p,
-                            int n, const double* __restrict__ pct, int P, double* __restrict__ cutoff) {
-  __shared__ long long sN;
-  if (threadIdx.x == 0) {
-    long long total = (long long)(*n_nodes_p) * n, lo = 0, hi = total;  // first index holding a NaN key
-    while (lo < hi) {
-      long long mid = (lo + hi) >> 1;
-      if (sorted[mid] == ~0ull) hi = mid;
-      else lo = mid + 1;
-    }
-    sN = lo;
-  }
-  __syncthreads();
-  const long long N = sN;
-  for (int p = threadIdx.x; p < P; p += blockDim.x) {
-    if (N <= 0) {
-      cutoff[p] = nan("");
-      continue;
-    }
-    double idx = __dadd_rn(1.0, __dmul_rn((double)(N - 1), pct[p]));
-    double lo = floor(idx), hi = ceil(idx);
-    long long ilo = (long long)lo, ihi = (long long)hi;
-    ilo = ilo < 1 ? 1 : ilo;
-    ihi = ihi > N ? N : ihi;
-    double q = dkey_inv(sorted[ilo - 1]);
-    double xh = dkey_inv(sorted[ihi - 1]);
-    if (idx > lo && xh != q) {
-      double h = __dsub_rn(idx, lo);
-      q = __dadd_rn(__dmul_rn(__dsub_rn(1.0, h), q), __dmul_rn(h, xh));
-    }
-    cutoff[p] = q;
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
 // K4 / K5: streaming pair fit, one warp per edge
 //   K == 2 : fit_lm_interaction  (core_functions.R:1058-1074)  -> t statistic of the A:category coefficient
 //   K >= 3 : aov(B ~ A * metadata), row "A:metadata" (core_functions.R:966-968) -> interaction F statistic
@@ -454,15 +410,18 @@ __global__ void __launch_bounds__(256) k_fit_stream(const double* __restrict__ D
 //   mode 0: 2 * (1 - pt(|t|, df2))            core_functions.R:1072
 //   mode 1: pf(F, df1, df2, lower.tail=FALSE)  core_functions.R:968 (aov) / 920 (f.robftest)
 // ------------------------------------------------------------------------------------------------
-__global__ void k_tail(const double* __restrict__ stat, const int32_t* __restrict__ status, int64_t e_lo,
-                       int64_t e_hi, int mode, double df1, double df2, double* __restrict__ p_out) {
+__global__ void __launch_bounds__(128) k_tail(const double* __restrict__ stat, const int32_t* __restrict__ status,
+                                              int64_t e_lo, int64_t e_hi, int mode, double df1, double df2,
+                                              TailConsts tc, const double* __restrict__ lbeta_p,
+                                              double* __restrict__ p_out) {
   int64_t e = e_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= e_hi) return;
+  tc.lbeta_ab = *lbeta_p;
   int st = status[e];
   double p;
   if (st == MDEGGS_EDGE_SINGULAR || st == MDEGGS_EDGE_NONFINITE || st == MDEGGS_EDGE_ZERO_SCALE) p = nan("");
   else if (st == MDEGGS_EDGE_SELFLOOP) p = 1.0;
-  else p = (mode == 0) ? p_two_sided_ref_dev(stat[e], df2) : pf_upper_dev(stat[e], df1, df2);
+  else p = (mode == 0) ? p_two_sided_ref_tab(tc, stat[e], df2) : pf_upper_tab(tc, stat[e], df1, df2);
   p_out[e] = p;
 }
 
@@ -676,11 +635,16 @@ struct MinOp {
 };
 
 // pass B: BH values with global ranks -> minimum of each tile
-__global__ void __launch_bounds__(BH_THREADS) k_bh_tilemin(BhArgs A, const long long* __restrict__ tile_base,
+__global__ void __launch_bounds__(BH_THREADS) k_bh_tilemin(BhArgs A, const int32_t* __restrict__ tile_cnt,
+                                                          const long long* __restrict__ tile_base,
                                                           const long long* __restrict__ seg_n,
                                                           double* __restrict__ tile_min) {
   int p, c;
   if (!bh_segment(A, p, c)) return;
+  if (tile_cnt[(size_t)blockIdx.y * A.ntiles + blockIdx.x] == 0) {  // no member of this segment in the tile
+    if (threadIdx.x == 0) tile_min[(size_t)blockIdx.y * A.ntiles + blockIdx.x] = INFINITY;
+    return;
+  }
   typedef cub::BlockScan<int, BH_THREADS> Scan;
   typedef cub::BlockReduce<double, BH_THREADS> Reduce;
   __shared__ union {
@@ -726,13 +690,15 @@ __global__ void __launch_bounds__(256) k_bh_suffix_min(const double* __restrict_
 
 // pass C: adjusted values, count < 0.05, optional scatter to network order
 //   mode 1 bonferroni: pmin(1, n * p);  mode 2 BH: pmin(1, cummin((n/i) * p[o]))[ro]
-__global__ void __launch_bounds__(BH_THREADS) k_bh_final(BhArgs A, int mode, const long long* __restrict__ tile_base,
+__global__ void __launch_bounds__(BH_THREADS) k_bh_final(BhArgs A, int mode, const int32_t* __restrict__ tile_cnt,
+                                                        const long long* __restrict__ tile_base,
                                                         const long long* __restrict__ seg_n,
                                                         const double* __restrict__ tile_carry,
                                                         unsigned long long* __restrict__ sig,
                                                         double* __restrict__ padj_out, int64_t padj_stride) {
   int p, c;
   if (!bh_segment(A, p, c)) return;
+  if (tile_cnt[(size_t)blockIdx.y * A.ntiles + blockIdx.x] == 0) return;
   typedef cub::BlockScan<int, BH_THREADS> ScanI;
   typedef cub::BlockScan<double, BH_THREADS> ScanD;
   typedef cub::BlockReduce<int, BH_THREADS> Reduce;

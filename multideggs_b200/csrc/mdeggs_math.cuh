@@ -5,9 +5,9 @@
 //   stats::pf(lower.tail = FALSE) inside summary(aov)[["Pr(>F)"]]  R/core_functions.R:966-968
 //   stats::pf(lower.tail = FALSE) inside sfsmisc::f.robftest      R/core_functions.R:919-922
 // R implements both on top of pbeta (TOMS 708 bratio, not vendored in the reference).  Here the
-// regularised incomplete beta is evaluated with (i) a division-free power series when x*(a+b) is small
-// and (ii) a modified-Lentz continued fraction otherwise, always on the side that yields the wanted
-// tail without cancellation; log Beta uses Stirling-corrected differences so that df up to ~1e6 keeps
+// regularised incomplete beta is evaluated by its continued fraction, always on the side that yields the
+// wanted tail without cancellation (generic modified-Lentz version for the scalar twins; table-driven
+// forward recurrence for the per-run batched kernel, see TailConsts below); log Beta uses Stirling-corrected differences so that df up to ~1e6 keeps
 // ~1e-13 relative accuracy.  pt()/pf() reproduce R's argument switching (nmath pt.c / pf.c), and the
 // two-sided lm p-value reproduces the reference's operation order bit for bit given `val`.
 #pragma once
@@ -123,6 +123,110 @@ __device__ inline double pf_upper_dev(double f, double d1, double d2) {
   double den = d2 + d1 * f;
   if (d1 * f > d2) return pbeta_xy_dev(d2 / den, d1 * f / den, d2 / 2.0, d1 / 2.0, true);
   return pbeta_xy_dev(d1 * f / den, d2 / den, d1 / 2.0, d2 / 2.0, false);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Table-driven tails for a whole run.  Within one omic every edge uses the SAME degrees of freedom, so the
+// continued-fraction coefficients of I_x(a,b) depend on the edge only through x:  d_j = x * e_j(a,b).
+// k_cf_tables precomputes e_j for both argument orders and log Beta once; per edge the fraction is then
+// evaluated by the forward three-term recurrence (2 FMAs per term, one division + convergence test every
+// 4 terms) instead of modified Lentz (6 divisions per iteration): ~7x fewer dependent FP64 divisions.
+// ---------------------------------------------------------------------------------------------------
+constexpr int CF_TABLE_LEN = 1024;
+
+struct TailConsts {
+  double a, b;        // (0.5, df/2) for pt, (df1/2, df2/2) for pf
+  double lbeta_ab;    // log Beta(a, b)
+  const double* e_ab;  // e_j for I_x(a, b),  j = 1..CF_TABLE_LEN
+  const double* e_ba;  // e_j for I_x(b, a)
+};
+
+// e_1 = -(a+b)/(a+1); e_{2m} = m(b-m)/((a+2m-1)(a+2m)); e_{2m+1} = -(a+m)(a+b+m)/((a+2m)(a+2m+1))
+__global__ void k_cf_tables(double a, double b, double* __restrict__ e_ab, double* __restrict__ e_ba,
+                            double* __restrict__ lbeta_out) {
+  for (int j = threadIdx.x + 1; j <= CF_TABLE_LEN; j += blockDim.x) {
+    for (int o = 0; o < 2; ++o) {
+      double p = o ? b : a, q = o ? a : b;
+      double m = (double)(j >> 1), e;
+      if (j & 1) e = -(p + m) * (p + q + m) / ((p + 2.0 * m) * (p + 2.0 * m + 1.0));
+      else e = m * (q - m) / ((p + 2.0 * m - 1.0) * (p + 2.0 * m));
+      (o ? e_ba : e_ab)[j - 1] = e;
+    }
+  }
+  if (threadIdx.x == 0) *lbeta_out = lbeta_dev(a, b);
+}
+
+// continued fraction value h(x) = 1/(1 + d_1/(1 + d_2/(1 + ...))), d_j = x e_j
+__device__ inline double beta_cf_tab(const double* __restrict__ e, double a, double b, double x) {
+  double Am = 0.0, A = 1.0, Bm = 1.0, B = 1.0;  // (A_0, A_1), (B_0, B_1)
+  double f_old = 1.0;
+  for (int j = 0; j < CF_TABLE_LEN; j += 4) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      double d = x * __ldg(e + j + u);
+      double An = fma(d, Am, A), Bn = fma(d, Bm, B);
+      Am = A;
+      Bm = B;
+      A = An;
+      B = Bn;
+    }
+    double r = 1.0 / B;
+    A *= r;
+    Am *= r;
+    Bm *= r;
+    B = 1.0;
+    if (fabs(A - f_old) <= 4e-16 * fabs(A)) return A;
+    f_old = A;
+  }
+  return beta_cf_dev(a, b, x);  // table exhausted (never seen for |t| < 40, df < 1e6): generic Lentz
+}
+
+// pbeta_xy for the run's (a, b) pair; `swapped` = the caller's first parameter is tc.b
+__device__ inline double pbeta_xy_tab(const TailConsts& tc, bool swapped, double x, double y, bool lower) {
+  const double a = swapped ? tc.b : tc.a, b = swapped ? tc.a : tc.b;
+  if (isnan(x) || isnan(y)) return nan("");
+  if (x <= 0.0) return lower ? 0.0 : 1.0;
+  if (y <= 0.0) return lower ? 1.0 : 0.0;
+  double lx = (x < 0.5) ? log(x) : log1p(-y);
+  double ly = (y < 0.5) ? log(y) : log1p(-x);
+  double front = exp(a * lx + b * ly - tc.lbeta_ab);
+  if (x < (a + 1.0) / (a + b + 2.0)) {
+    double w = front * beta_cf_tab(swapped ? tc.e_ba : tc.e_ab, a, b, x) / a;
+    return lower ? w : 1.0 - w;
+  }
+  double w1 = front * beta_cf_tab(swapped ? tc.e_ab : tc.e_ba, b, a, y) / b;
+  return lower ? 1.0 - w1 : w1;
+}
+
+// 2 * (1 - pt(|t|, n)) with tc = {0.5, n/2}: same composition as p_two_sided_ref_dev
+__device__ inline double p_two_sided_ref_tab(const TailConsts& tc, double t, double n) {
+  if (isnan(t)) return nan("");
+  double x = fabs(t), u;
+  if (isinf(x)) {
+    u = 1.0;
+  } else {
+    double val;
+    if (n > x * x) {
+      double den = n + x * x;
+      val = pbeta_xy_tab(tc, false, x * x / den, n / den, false);
+    } else {
+      double nx = 1.0 + (x / n) * x;
+      val = pbeta_xy_tab(tc, true, 1.0 / nx, (x / n) * x / nx, true);
+    }
+    val *= 0.5;
+    u = (x <= 0.0) ? val : __dadd_rn(__dsub_rn(0.5, val), 0.5);
+  }
+  return __dmul_rn(2.0, __dsub_rn(1.0, u));
+}
+
+// pf(f, d1, d2, lower.tail = FALSE) with tc = {d1/2, d2/2}
+__device__ inline double pf_upper_tab(const TailConsts& tc, double f, double d1, double d2) {
+  if (isnan(f)) return nan("");
+  if (f <= 0.0) return 1.0;
+  if (isinf(f)) return 0.0;
+  double den = d2 + d1 * f;
+  if (d1 * f > d2) return pbeta_xy_tab(tc, true, d2 / den, d1 * f / den, true);
+  return pbeta_xy_tab(tc, false, d1 * f / den, d2 / den, false);
 }
 
 }  // namespace mdeggs

@@ -1,0 +1,241 @@
+// mdeggs_select.cuh — K3: exact multi-quantile selection over the whole node-filtered matrix, no sort.
+//
+// Replaces  cut_off <- stats::quantile(as.matrix(assayData), prob = percentile, na.rm = TRUE)
+// (R/core_functions.R:718), which the reference recomputes for each of the 13-15 percentiles.  Type 7 needs
+// two order statistics per percentile (floor/ceil of 1 + (N-1)p): T = 2P target ranks out of N ~ 8.4e6
+// values.  A most-significant-digit radix SELECT finds all T at once: six passes over D (12,12,12,12,12,4
+// key bits), each histogramming only the elements whose already-fixed key prefix equals the prefix of some
+// target (the first two passes see most of the data, the rest almost nothing), followed by a one-CTA kernel
+// that walks the histograms and narrows every target.  Bytes per pass = the matrix once (it is L2-resident
+// right after the gather); versus a full 64-bit radix sort: ~1/8 of the passes and no key/scratch arrays.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cub/block/block_scan.cuh>
+
+#include "mdeggs_kernels.cuh"
+
+namespace mdeggs {
+
+constexpr int RSEL_MAX_T = 256;       // 2 * P
+constexpr int RSEL_BINS = 4096;
+constexpr int RSEL_SMEM_SLOTS = 4;    // slots whose histogram is privatised in shared memory
+constexpr int RSEL_PASSES = 6;
+
+struct RselState {
+  long long N;                               // non-NaN values
+  int T;                                     // targets
+  int U[2];                                  // distinct active prefixes; pass d reads U[d & 1], writes U[(d+1) & 1]
+  unsigned int done;                         // CTAs of the current narrowing step that have finished
+  unsigned long long prefix[RSEL_MAX_T];     // per target: key bits fixed so far (right aligned)
+  long long rank[RSEL_MAX_T];                // per target: rank inside its prefix group (0-based)
+  int slot[2][RSEL_MAX_T];                   // per target: index into slot_prefix (double buffered like U)
+  unsigned long long slot_prefix[2][RSEL_MAX_T];  // sorted, unique
+};
+
+__host__ __device__ __forceinline__ int rsel_width(int pass) { return pass < 5 ? 12 : 4; }
+__host__ __device__ __forceinline__ int rsel_consumed(int pass) { return 12 * pass; }
+
+__global__ void __launch_bounds__(512) k_rsel_hist(const double* __restrict__ D, const int32_t* __restrict__ src_of_pos,
+                                                   int npad, const int32_t* __restrict__ n_nodes_p, int pass,
+                                                   const RselState* __restrict__ st, unsigned int* __restrict__ hist,
+                                                   unsigned long long* __restrict__ nan_count) {
+  extern __shared__ unsigned int sh[];  // [RSEL_SMEM_SLOTS][RSEL_BINS]
+  __shared__ unsigned long long s_pref[RSEL_MAX_T];
+  __shared__ int s_U;
+  const int width = rsel_width(pass), consumed = rsel_consumed(pass);
+  const int nbins = 1 << width;
+  if (threadIdx.x == 0) s_U = pass == 0 ? 1 : st->U[pass & 1];
+  __syncthreads();
+  const int U = s_U;
+  const int usm = U < RSEL_SMEM_SLOTS ? U : RSEL_SMEM_SLOTS;
+  for (int i = threadIdx.x; i < usm * nbins; i += blockDim.x) sh[i] = 0;
+  for (int i = threadIdx.x; i < U; i += blockDim.x) s_pref[i] = pass == 0 ? 0ull : st->slot_prefix[pass & 1][i];
+  __syncthreads();
+  const int n_nodes = *n_nodes_p;
+  const int half = npad >> 1;  // double2 units per row (npad is a multiple of 4)
+  const int shift = 64 - consumed - width;
+  const unsigned long long dmask = (unsigned long long)(nbins - 1);
+  const unsigned long long pmin = s_pref[0], pmax = s_pref[U - 1];
+  unsigned long long nans = 0;
+  for (int row = blockIdx.x; row < n_nodes; row += gridDim.x) {
+    const double2* __restrict__ R2 = reinterpret_cast<const double2*>(D + (size_t)row * npad);
+    for (int c = threadIdx.x; c < half; c += blockDim.x) {
+      const double2 v = __ldg(R2 + c);
+      const int pos = 2 * c;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (src_of_pos[pos + h] < 0) continue;  // padding slot
+        const unsigned long long key = dkey(h ? v.y : v.x);
+        if (pass == 0 && key == ~0ull) ++nans;
+        int slot = 0;
+        if (pass > 0) {
+          const unsigned long long pre = key >> (64 - consumed);
+          if (pre < pmin || pre > pmax) continue;  // outside every active prefix: the common case after pass 1
+          int lo = 0, hi = U - 1;
+          slot = -1;
+          while (lo <= hi) {
+            int mid = (lo + hi) >> 1;
+            unsigned long long q = s_pref[mid];
+            if (q == pre) {
+              slot = mid;
+              break;
+            }
+            if (q < pre) lo = mid + 1;
+            else hi = mid - 1;
+          }
+          if (slot < 0) continue;
+        }
+        const unsigned int digit = (unsigned int)((key >> shift) & dmask);
+        if (slot < RSEL_SMEM_SLOTS) atomicAdd(&sh[slot * nbins + digit], 1u);
+        else atomicAdd(&hist[(size_t)slot * RSEL_BINS + digit], 1u);
+      }
+    }
+  }
+  if (pass == 0) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nans += __shfl_xor_sync(0xffffffffu, nans, o);
+    if ((threadIdx.x & 31) == 0 && nans) atomicAdd(nan_count, nans);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < usm * nbins; i += blockDim.x) {
+    unsigned int c = sh[i];
+    if (c) atomicAdd(&hist[(size_t)(i / nbins) * RSEL_BINS + (i % nbins)], c);
+  }
+}
+
+// one CTA per active prefix slot: narrow the targets of that slot by one digit; the last CTA to finish rebuilds
+// the (sorted, unique) slot table for the next pass and, after the final pass, turns the selected keys into
+// type-7 cut-offs  q = (1-h) x[lo] + h x[hi]  in R's operation order.
+__global__ void __launch_bounds__(256) k_rsel_scan(int pass, RselState* __restrict__ st, unsigned int* __restrict__ hist,
+                                                   const unsigned long long* __restrict__ nan_count,
+                                                   const int32_t* __restrict__ n_nodes_p, int n,
+                                                   const double* __restrict__ pct, int P,
+                                                   double* __restrict__ cutoff) {
+  typedef cub::BlockScan<long long, 256> Scan;
+  __shared__ typename Scan::TempStorage tmp;
+  __shared__ long long cum[RSEL_BINS + 1];
+  __shared__ int s_last;
+  const int width = rsel_width(pass);
+  const int nbins = 1 << width;
+  const int tid = threadIdx.x, s = blockIdx.x;
+  const int cur = pass & 1, nxt = cur ^ 1;
+  if (pass == 0) {
+    if (s != 0) return;
+    __shared__ long long sN;
+    if (tid == 0) {
+      sN = (long long)(*n_nodes_p) * n - (long long)(*nan_count);
+      st->N = sN;
+      st->T = 2 * P;
+      st->U[0] = 1;
+      st->slot_prefix[0][0] = 0;
+    }
+    __syncthreads();
+    const long long N = sN;
+    for (int p = tid; p < P; p += blockDim.x) {
+      long long ilo = 1, ihi = 1;
+      if (N > 0) {
+        double idx = __dadd_rn(1.0, __dmul_rn((double)(N - 1), pct[p]));
+        ilo = (long long)floor(idx);
+        ihi = (long long)ceil(idx);
+        ilo = ilo < 1 ? 1 : (ilo > N ? N : ilo);
+        ihi = ihi < 1 ? 1 : (ihi > N ? N : ihi);
+      }
+      st->prefix[2 * p] = 0;
+      st->prefix[2 * p + 1] = 0;
+      st->rank[2 * p] = ilo - 1;
+      st->rank[2 * p + 1] = ihi - 1;
+      st->slot[0][2 * p] = 0;
+      st->slot[0][2 * p + 1] = 0;
+    }
+    __threadfence();
+    __syncthreads();
+  }
+  const int T = 2 * P;
+  const int U = pass == 0 ? 1 : st->U[cur];
+  if (s >= U) return;
+  // exclusive scan of hist[s][0..nbins): 256 threads x 16 bins
+  unsigned int* h = hist + (size_t)s * RSEL_BINS;
+  constexpr int PER = RSEL_BINS / 256;
+  long long v[PER], ex[PER];
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    int b = tid * PER + j;
+    v[j] = b < nbins ? (long long)h[b] : 0;
+  }
+  long long agg;
+  Scan(tmp).ExclusiveSum(v, ex, agg);
+#pragma unroll
+  for (int j = 0; j < PER; ++j) cum[tid * PER + j] = ex[j];
+  if (tid == 0) cum[RSEL_BINS] = agg;
+  __syncthreads();
+  for (int t = tid; t < T; t += blockDim.x) {
+    if (st->slot[cur][t] != s) continue;
+    long long r = st->rank[t];
+    int lo = 0, hi = nbins - 1;  // largest b with cum[b] <= r  (then hist[b] > 0 and r < cum[b+1])
+    while (lo < hi) {
+      int mid = (lo + hi + 1) >> 1;
+      if (cum[mid] <= r) lo = mid;
+      else hi = mid - 1;
+    }
+    st->prefix[t] = (st->prefix[t] << width) | (unsigned long long)lo;
+    st->rank[t] = r - cum[lo];
+  }
+#pragma unroll
+  for (int j = 0; j < PER; ++j) h[tid * PER + j] = 0;  // clean slate for the next pass
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(&st->done, 1u) == (unsigned)(U - 1));
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // rebuild the sorted, unique slot table in shared memory (T <= 256 == blockDim.x), O(T^2) in parallel
+  __shared__ unsigned long long s_p[RSEL_MAX_T];
+  __shared__ int s_first[RSEL_MAX_T];
+  {
+    volatile unsigned long long* pref = st->prefix;
+    if (tid < T) s_p[tid] = pref[tid];
+    __syncthreads();
+    if (tid < T) {
+      int first = 1;
+      for (int v = 0; v < tid; ++v) first &= (s_p[v] != s_p[tid]);
+      s_first[tid] = first;
+    }
+    __syncthreads();
+    if (tid < T) {
+      int sl = 0;
+      for (int u = 0; u < T; ++u) sl += (s_first[u] && s_p[u] < s_p[tid]);
+      st->slot[nxt][tid] = sl;
+      if (s_first[tid]) st->slot_prefix[nxt][sl] = s_p[tid];
+    }
+    if (tid == 0) {
+      int Un = 0;
+      for (int u = 0; u < T; ++u) Un += s_first[u];
+      st->U[nxt] = Un;
+      st->done = 0;
+    }
+  }
+  __syncthreads();
+  if (pass == RSEL_PASSES - 1) {
+    const long long N = st->N;
+    const unsigned long long* pref = s_p;
+    for (int p = tid; p < P; p += blockDim.x) {
+      if (N <= 0) {
+        cutoff[p] = nan("");
+        continue;
+      }
+      double idx = __dadd_rn(1.0, __dmul_rn((double)(N - 1), pct[p]));
+      double lo = floor(idx);
+      double q = dkey_inv(pref[2 * p]);
+      double xh = dkey_inv(pref[2 * p + 1]);
+      if (idx > lo && xh != q) {
+        double hfrac = __dsub_rn(idx, lo);
+        q = __dadd_rn(__dmul_rn(__dsub_rn(1.0, hfrac), q), __dmul_rn(hfrac, xh));
+      }
+      cutoff[p] = q;
+    }
+  }
+}
+
+}  // namespace mdeggs

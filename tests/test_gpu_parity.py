@@ -190,3 +190,33 @@ def test_stats_and_launch_count(engine):
     st = engine.stats()
     assert st["kernel_launches"] > 5 and st["unique_fits"] == 120 and st["n_nodes"] > 0
     assert st["fit_bytes"] == 120 * (16 * 40 + 16)
+
+
+@pytest.mark.parametrize("nf,n,K", [(300, 64, 2), (257, 100, 3), (130, 37, 2), (385, 520, 2)])
+def test_dense_tile_path_matches_oracle(oracle, nf, n, K, monkeypatch):
+    """All-pairs network through the dense cross-moment kernel (forced), same parity bar as the streaming kernel."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    monkeypatch.setenv("MDEGGS_FIT_PATH", "1")
+    eng = md.Engine([0])
+    rng = np.random.default_rng(nf)
+    prob = synth.random_problem(nf, n, 10, K, 900 + nf)
+    iu, ju = np.triu_indices(nf, k=1)
+    sel = rng.permutation(iu.shape[0])[: min(iu.shape[0], 20000)]
+    flip = rng.random(sel.shape[0]) < 0.3                       # some edges reversed: B ~ A vs A ~ B
+    fr = np.where(flip, ju[sel], iu[sel]) + 1
+    to = np.where(flip, iu[sel], ju[sel]) + 1
+    prob.from_idx, prob.to_idx = fr.astype(np.int32), to.astype(np.int32)
+    gpu = eng.run_omic(prob, ALL_FIELDS)
+    assert eng.stats()["fit_path"] == 1
+    ref = oracle.run_omic(prob, ALL_FIELDS)
+    assert_parity(gpu, ref, prob, what=f"dense nf{nf} n{n} K{K}: ")
+    monkeypatch.setenv("MDEGGS_FIT_PATH", "0")
+    eng0 = md.Engine([0])
+    gpu0 = eng0.run_omic(prob, ALL_FIELDS)
+    assert eng0.stats()["fit_path"] == 0
+    assert np.array_equal(gpu0["status"], gpu["status"]) and np.array_equal(gpu0["cat_best"], gpu["cat_best"])
+    assert np.allclose(gpu0["stat"], gpu["stat"], rtol=1e-10, atol=0, equal_nan=True)
+    eng.close()
+    eng0.close()
