@@ -298,7 +298,9 @@ def run_cuda(args) -> None:
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     dist_sync()
     e2e_value = world * E * args.steps / e2e_s
-    e2e_stage = {k: v for k, v in eng.stats().items() if k.startswith("ms_")}
+    e2e_stats = eng.stats()
+    e2e_stage = {k: v for k, v in e2e_stats.items() if k.startswith("ms_")}
+    h2d, d2h = int(e2e_stats["h2d_bytes"]), int(e2e_stats["d2h_bytes"])  # bytes the engine actually moved per step
     assert int(hkeep[5]["best"].numpy()[0]) == best, "host and device legs disagree"
 
     # ---- roofline of the dominant kernel (pair fit): algorithmic bytes E*(16n+16) / its CUDA-event time ----
@@ -325,7 +327,9 @@ def run_cuda(args) -> None:
                          "tests_the_reference_would_run": ref_equiv},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": 1e3 * e2e_s / args.steps, "stage_ms_last_step": e2e_stage,
-                "api": "mdeggs_run_omic (C ABI) with pinned host buffers"},
+                "host_input_bytes": int(prob.assay.nbytes + 8 * E),
+                "api": "mdeggs_run_omic (C ABI) with pinned host buffers; only the band of network-node rows of the "
+                       "assay crosses PCIe"},
         "gpu_launches": int(st["kernel_launches"]) * args.steps,
         "clocks": clocks,
         "roofline": roofline,

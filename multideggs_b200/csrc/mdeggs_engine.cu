@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdarg.h>
+#include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -66,16 +67,17 @@ struct Shard {
   cudaEvent_t ev[EV_COUNT] = {};
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   nccl_comm_t comm = nullptr;
+  int64_t row_off = 0, ld_eff = 0;  // the device copy of the assay starts at host row `row_off`
   DevBuf assay, from, to, flags, excl, node_of_row, rowlist, scal, src_of_pos, pct, cutoff, D, keys, keys_sorted,
       cub_tmp, cub_tmp2, mean, sxx, med, bad, stat, status, p_edge, coef, iters, act, counters, sortk, sortk2, idx,
       idx2, ps, sa, sb, tile_cnt, tile_base, seg_n, tile_min, tile_carry, padj_best, cat_best, cat, padj, med_out,
-      small_out, rlm_ws, rsel_hist, rsel_state, dense_S, cf_tab;
+      small_out, rlm_ws, rsel_hist, rsel_state, rsel_cand, dense_S, cf_tab;
   void release_all() {
     DevBuf* all[] = {&assay, &from, &to, &flags, &excl, &node_of_row, &rowlist, &scal, &src_of_pos, &pct, &cutoff,
                      &D, &keys, &keys_sorted, &cub_tmp, &cub_tmp2, &mean, &sxx, &med, &bad, &stat, &status, &p_edge,
                      &coef, &iters, &act, &counters, &sortk, &sortk2, &idx, &idx2, &ps, &sa, &sb, &tile_cnt,
                      &tile_base, &seg_n, &tile_min, &tile_carry, &padj_best, &cat_best, &cat, &padj, &med_out,
-                     &small_out, &rlm_ws, &rsel_hist, &rsel_state, &dense_S, &cf_tab};
+                     &small_out, &rlm_ws, &rsel_hist, &rsel_state, &rsel_cand, &dense_S, &cf_tab};
     for (DevBuf* b : all) b->release();
   }
 };
@@ -252,23 +254,62 @@ int run_shard_front(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const H
   const double* d_assay;
   const int32_t *d_from, *d_to;
   if (in->mem == MDEGGS_MEM_HOST) {
-    CU(s.assay.ensure(assay_elems * 8));
+    // Only rows that are network nodes are ever read (core_functions.R:336). For small edge lists the host finds
+    // the node-row RANGE [r_lo, r_hi] in one pass over from/to and only that band crosses PCIe (config 3: the
+    // 8,405 node genes are the first rows of 20,000 -> 67 MB instead of 160 MB).
+    int64_t r_lo = 0, r_hi = G - 1;
+    if (E > 0 && E <= (int64_t)1 << 20) {
+      int32_t lo = INT32_MAX, hi = 0;
+      for (int64_t e = 0; e < E; ++e) {
+        int32_t a = in->from[e], b = in->to[e];
+        lo = a < lo ? a : lo;
+        lo = b < lo ? b : lo;
+        hi = a > hi ? a : hi;
+        hi = b > hi ? b : hi;
+      }
+      if (lo >= 1 && hi <= G) {  // out-of-range indices are reported by the device check below
+        r_lo = lo - 1;
+        r_hi = hi - 1;
+      }
+    }
+    const int64_t band = r_hi - r_lo + 1;
+    s.row_off = r_lo;
     CU(s.from.ensure((size_t)E * 4 + 4));
     CU(s.to.ensure((size_t)E * 4 + 4));
-    CU(cudaMemcpyAsync(s.assay.p, in->assay, assay_elems * 8, cudaMemcpyHostToDevice, s.s_main));
+    size_t copied;
+    if (in->layout == MDEGGS_LAYOUT_COLMAJOR) {
+      CU(s.assay.ensure((size_t)band * (size_t)n * 8));
+      s.ld_eff = band;
+      if (band == G && in->ld == G) {
+        CU(cudaMemcpyAsync(s.assay.p, in->assay, (size_t)G * n * 8, cudaMemcpyHostToDevice, s.s_main));
+      } else {
+        CU(cudaMemcpy2DAsync(s.assay.p, (size_t)band * 8, in->assay + r_lo, (size_t)in->ld * 8, (size_t)band * 8,
+                             (size_t)n, cudaMemcpyHostToDevice, s.s_main));
+      }
+      copied = (size_t)band * n * 8;
+    } else {
+      s.ld_eff = in->ld;
+      copied = ((size_t)in->ld * (size_t)(band - 1) + (size_t)n) * 8;
+      CU(s.assay.ensure(copied));
+      CU(cudaMemcpyAsync(s.assay.p, in->assay + (size_t)r_lo * in->ld, copied, cudaMemcpyHostToDevice, s.s_main));
+    }
     if (E > 0) {
       CU(cudaMemcpyAsync(s.from.p, in->from, (size_t)E * 4, cudaMemcpyHostToDevice, s.s_main));
       CU(cudaMemcpyAsync(s.to.p, in->to, (size_t)E * 4, cudaMemcpyHostToDevice, s.s_main));
     }
-    ctx->stats.h2d_bytes += (int64_t)(assay_elems * 8 + (size_t)E * 8);
+    ctx->stats.h2d_bytes += (int64_t)(copied + (size_t)E * 8);
     d_assay = s.assay.as<double>();
     d_from = s.from.as<int32_t>();
     d_to = s.to.as<int32_t>();
   } else if (s.device == src_device) {
+    s.row_off = 0;
+    s.ld_eff = in->ld;
     d_assay = in->assay;
     d_from = in->from;
     d_to = in->to;
   } else {
+    s.row_off = 0;
+    s.ld_eff = in->ld;
     CU(s.assay.ensure(assay_elems * 8));
     CU(s.from.ensure((size_t)E * 4 + 4));
     CU(s.to.ensure((size_t)E * 4 + 4));
@@ -346,11 +387,11 @@ int run_shard_main(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
   if (n_nodes > 0) {
     if (in->layout == MDEGGS_LAYOUT_COLMAJOR) {
       dim3 grid((unsigned)((L.npad + 31) / 32), (unsigned)((n_nodes + 31) / 32));
-      LAUNCH(k_gather_colmajor, grid, 256, 0, s.s_main, s.assay.as<double>(), in->ld, s.rowlist.as<int32_t>(), d_nn,
+      LAUNCH(k_gather_colmajor, grid, 256, 0, s.s_main, s.assay.as<double>(), s.ld_eff, s.row_off, s.rowlist.as<int32_t>(), d_nn,
              s.src_of_pos.as<int32_t>(), L.npad, n, s.D.as<double>());
     } else {
       dim3 grid((unsigned)((L.npad + 255) / 256), (unsigned)n_nodes);
-      LAUNCH(k_gather_rowmajor, grid, 256, 0, s.s_main, s.assay.as<double>(), in->ld, s.rowlist.as<int32_t>(), d_nn,
+      LAUNCH(k_gather_rowmajor, grid, 256, 0, s.s_main, s.assay.as<double>(), s.ld_eff, s.row_off, s.rowlist.as<int32_t>(), d_nn,
              s.src_of_pos.as<int32_t>(), L.npad, n, s.D.as<double>());
     }
   }
@@ -368,15 +409,28 @@ int run_shard_main(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
     RselState* d_st = s.rsel_state.as<RselState>();
     unsigned long long* d_nan = reinterpret_cast<unsigned long long*>(s.rsel_state.as<char>() + sizeof(RselState));
     const size_t hsmem = (size_t)RSEL_SMEM_SLOTS * RSEL_BINS * sizeof(unsigned int);
-    if (!ctx->rsel_attr_set) {
-      CU(cudaFuncSetAttribute(k_rsel_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsmem));
-      ctx->rsel_attr_set = true;
+    RselCand cand;
+    {
+      size_t total = (size_t)n_nodes * (size_t)n;
+      cand.capacity = (unsigned int)(total < (size_t)(4u << 20) ? total : (size_t)(4u << 20));
+      CU(s.rsel_cand.ensure((size_t)cand.capacity * 8));
+      cand.keys = s.rsel_cand.as<unsigned long long>();
+      cand.count = reinterpret_cast<unsigned int*>(s.rsel_state.as<char>() + sizeof(RselState) + 8);
     }
+    const unsigned big_grid = 148 * 6, small_grid = 148;
     for (int pass = 0; pass < RSEL_PASSES; ++pass) {
-      LAUNCH(k_rsel_hist, 148 * 2, 512, hsmem, s.s_sort, s.D.as<double>(), s.src_of_pos.as<int32_t>(), L.npad, d_nn,
-             pass, d_st, s.rsel_hist.as<unsigned int>(), d_nan);
-      LAUNCH(k_rsel_scan, (unsigned)(pass == 0 ? 1 : 2 * P), 256, 0, s.s_sort, pass, d_st, s.rsel_hist.as<unsigned int>(), d_nan, d_nn, n,
-             s.pct.as<double>(), P, s.cutoff.as<double>());
+      if (pass < 2) {
+        LAUNCH(k_rsel_pass<0>, big_grid, 256, hsmem, s.s_sort, s.D.as<double>(), s.src_of_pos.as<int32_t>(), L.npad,
+               d_nn, pass, d_st, s.rsel_hist.as<unsigned int>(), d_nan, cand);
+      } else {
+        if (pass == 2)  // 24 key bits fixed: compact the survivors once, the last read of D
+          LAUNCH(k_rsel_pass<1>, big_grid, 256, 0, s.s_sort, s.D.as<double>(), s.src_of_pos.as<int32_t>(), L.npad,
+                 d_nn, pass, d_st, s.rsel_hist.as<unsigned int>(), d_nan, cand);
+        LAUNCH(k_rsel_pass<2>, small_grid, 256, hsmem, s.s_sort, s.D.as<double>(), s.src_of_pos.as<int32_t>(), L.npad,
+               d_nn, pass, d_st, s.rsel_hist.as<unsigned int>(), d_nan, cand);
+      }
+      LAUNCH(k_rsel_scan, (unsigned)(pass == 0 ? 1 : 2 * P), 256, 0, s.s_sort, pass, d_st,
+             s.rsel_hist.as<unsigned int>(), d_nan, d_nn, n, s.pct.as<double>(), P, s.cutoff.as<double>());
     }
   } else if (P > 0) {
     LAUNCH(k_fill_f64, 1, 64, 0, s.s_sort, s.cutoff.as<double>(), (int64_t)P, nan(""));

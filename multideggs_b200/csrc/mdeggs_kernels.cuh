@@ -77,7 +77,7 @@ __global__ void k_build_rowlist(const int32_t* __restrict__ flags, const int32_t
 // 32x32 smem tile, coalesced on both sides. Padding positions (src < 0) are written by k_gene_stats.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_gather_colmajor(const double* __restrict__ assay, int64_t ld,
-                                                         const int32_t* __restrict__ rowlist,
+                                                         int64_t row_off, const int32_t* __restrict__ rowlist,
                                                          const int32_t* __restrict__ n_nodes_p,
                                                          const int32_t* __restrict__ src_of_pos, int npad, int n,
                                                          double* __restrict__ D) {
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(256) k_gather_colmajor(const double* __restric
   if (node0 >= n_nodes) return;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
   const int node_r = node0 + tx;
-  const int64_t row = node_r < n_nodes ? rowlist[node_r] : -1;
+  const int64_t row = node_r < n_nodes ? rowlist[node_r] - row_off : -1;  // device copy starts at host row row_off
 #pragma unroll
   for (int j = ty; j < 32; j += 8) {
     int pos = pos0 + j;
@@ -109,14 +109,14 @@ __global__ void __launch_bounds__(256) k_gather_colmajor(const double* __restric
 }
 
 __global__ void __launch_bounds__(256) k_gather_rowmajor(const double* __restrict__ assay, int64_t ld,
-                                                         const int32_t* __restrict__ rowlist,
+                                                         int64_t row_off, const int32_t* __restrict__ rowlist,
                                                          const int32_t* __restrict__ n_nodes_p,
                                                          const int32_t* __restrict__ src_of_pos, int npad, int n,
                                                          double* __restrict__ D) {
   const int n_nodes = *n_nodes_p;
   const int node = blockIdx.y;
   if (node >= n_nodes) return;
-  const int64_t row = rowlist[node];
+  const int64_t row = rowlist[node] - row_off;
   for (int pos = blockIdx.x * blockDim.x + threadIdx.x; pos < npad; pos += gridDim.x * blockDim.x) {
     int s = src_of_pos[pos];
     if (s >= 0) {

@@ -3,11 +3,14 @@
 // Replaces  cut_off <- stats::quantile(as.matrix(assayData), prob = percentile, na.rm = TRUE)
 // (R/core_functions.R:718), which the reference recomputes for each of the 13-15 percentiles.  Type 7 needs
 // two order statistics per percentile (floor/ceil of 1 + (N-1)p): T = 2P target ranks out of N ~ 8.4e6
-// values.  A most-significant-digit radix SELECT finds all T at once: six passes over D (12,12,12,12,12,4
-// key bits), each histogramming only the elements whose already-fixed key prefix equals the prefix of some
-// target (the first two passes see most of the data, the rest almost nothing), followed by a one-CTA kernel
-// that walks the histograms and narrows every target.  Bytes per pass = the matrix once (it is L2-resident
-// right after the gather); versus a full 64-bit radix sort: ~1/8 of the passes and no key/scratch arrays.
+// values.  A most-significant-digit radix SELECT finds all T at once: six digit passes (12,12,12,12,12,4 key
+// bits), each histogramming only the elements whose already-fixed key prefix equals the prefix of some
+// target, each followed by a small kernel (one CTA per active prefix) that walks the histograms and narrows
+// every target.  Only the first two passes read the matrix D; after 24 bits are fixed the surviving
+// candidates (a few thousand per target) are compacted once (third and last read of D) and the remaining
+// four passes run on that list.  Versus a full 64-bit radix sort of the matrix: 3 reads of D instead of ~16
+// read+write sweeps, and no key/scratch arrays.  If the candidate list overflows (huge tie groups) the
+// remaining passes fall back to scanning D.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -20,7 +23,7 @@ namespace mdeggs {
 
 constexpr int RSEL_MAX_T = 256;       // 2 * P
 constexpr int RSEL_BINS = 4096;
-constexpr int RSEL_SMEM_SLOTS = 4;    // slots whose histogram is privatised in shared memory
+constexpr int RSEL_SMEM_SLOTS = 2;    // slots whose histogram is privatised in shared memory (32 KB)
 constexpr int RSEL_PASSES = 6;
 
 struct RselState {
@@ -37,10 +40,31 @@ struct RselState {
 __host__ __device__ __forceinline__ int rsel_width(int pass) { return pass < 5 ? 12 : 4; }
 __host__ __device__ __forceinline__ int rsel_consumed(int pass) { return 12 * pass; }
 
-__global__ void __launch_bounds__(512) k_rsel_hist(const double* __restrict__ D, const int32_t* __restrict__ src_of_pos,
+struct RselCand {
+  unsigned long long* keys;   // compacted candidate keys (24-bit prefix matches an active slot)
+  unsigned int* count;        // number of candidates appended
+  unsigned int capacity;
+};
+
+__device__ __forceinline__ int rsel_find_slot(const unsigned long long* s_pref, int U, unsigned long long pre) {
+  int lo = 0, hi = U - 1;
+  while (lo <= hi) {
+    int mid = (lo + hi) >> 1;
+    unsigned long long q = s_pref[mid];
+    if (q == pre) return mid;
+    if (q < pre) lo = mid + 1;
+    else hi = mid - 1;
+  }
+  return -1;
+}
+
+// MODE 0: histogram pass over D;  MODE 1: compaction of D into cand (after pass 1);  MODE 2: histogram pass over
+// the compacted candidates (falls back to D when the compaction overflowed)
+template <int MODE>
+__global__ void __launch_bounds__(256) k_rsel_pass(const double* __restrict__ D, const int32_t* __restrict__ src_of_pos,
                                                    int npad, const int32_t* __restrict__ n_nodes_p, int pass,
                                                    const RselState* __restrict__ st, unsigned int* __restrict__ hist,
-                                                   unsigned long long* __restrict__ nan_count) {
+                                                   unsigned long long* __restrict__ nan_count, RselCand cand) {
   extern __shared__ unsigned int sh[];  // [RSEL_SMEM_SLOTS][RSEL_BINS]
   __shared__ unsigned long long s_pref[RSEL_MAX_T];
   __shared__ int s_U;
@@ -49,55 +73,88 @@ __global__ void __launch_bounds__(512) k_rsel_hist(const double* __restrict__ D,
   if (threadIdx.x == 0) s_U = pass == 0 ? 1 : st->U[pass & 1];
   __syncthreads();
   const int U = s_U;
-  const int usm = U < RSEL_SMEM_SLOTS ? U : RSEL_SMEM_SLOTS;
+  const int usm = (MODE == 1) ? 0 : (U < RSEL_SMEM_SLOTS ? U : RSEL_SMEM_SLOTS);
   for (int i = threadIdx.x; i < usm * nbins; i += blockDim.x) sh[i] = 0;
   for (int i = threadIdx.x; i < U; i += blockDim.x) s_pref[i] = pass == 0 ? 0ull : st->slot_prefix[pass & 1][i];
   __syncthreads();
-  const int n_nodes = *n_nodes_p;
-  const int half = npad >> 1;  // double2 units per row (npad is a multiple of 4)
   const int shift = 64 - consumed - width;
   const unsigned long long dmask = (unsigned long long)(nbins - 1);
   const unsigned long long pmin = s_pref[0], pmax = s_pref[U - 1];
-  unsigned long long nans = 0;
-  for (int row = blockIdx.x; row < n_nodes; row += gridDim.x) {
-    const double2* __restrict__ R2 = reinterpret_cast<const double2*>(D + (size_t)row * npad);
-    for (int c = threadIdx.x; c < half; c += blockDim.x) {
-      const double2 v = __ldg(R2 + c);
-      const int pos = 2 * c;
+
+  auto visit = [&](unsigned long long key) {  // histogram one key (MODE 0 / 2)
+    int slot = 0;
+    if (pass > 0) {
+      const unsigned long long pre = key >> (64 - consumed);
+      if (pre < pmin || pre > pmax) return;  // outside every active prefix: the common case after pass 1
+      slot = rsel_find_slot(s_pref, U, pre);
+      if (slot < 0) return;
+    }
+    const unsigned int digit = (unsigned int)((key >> shift) & dmask);
+    if (slot < RSEL_SMEM_SLOTS) atomicAdd(&sh[slot * nbins + digit], 1u);
+    else atomicAdd(&hist[(size_t)slot * RSEL_BINS + digit], 1u);
+  };
+
+  const bool overflow = (MODE == 2) && (*cand.count > cand.capacity);
+  if (MODE == 2 && !overflow) {
+    const unsigned int nc = *cand.count;
+    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < nc; i += gridDim.x * blockDim.x)
+      visit(cand.keys[i]);
+  } else {
+    const int n_nodes = *n_nodes_p;
+    const int half = npad >> 1;  // double2 units per row (npad is a multiple of 4)
+    const int lane = threadIdx.x & 31;
+    unsigned long long nans = 0;
+    // each CTA takes 4 rows at a time so that every thread has 4 independent 16-byte loads in flight
+    for (int row0 = blockIdx.x * 4; row0 < n_nodes; row0 += gridDim.x * 4) {
+      for (int c = threadIdx.x; c < half; c += blockDim.x) {
+        double2 v[4];
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        if (src_of_pos[pos + h] < 0) continue;  // padding slot
-        const unsigned long long key = dkey(h ? v.y : v.x);
-        if (pass == 0 && key == ~0ull) ++nans;
-        int slot = 0;
-        if (pass > 0) {
-          const unsigned long long pre = key >> (64 - consumed);
-          if (pre < pmin || pre > pmax) continue;  // outside every active prefix: the common case after pass 1
-          int lo = 0, hi = U - 1;
-          slot = -1;
-          while (lo <= hi) {
-            int mid = (lo + hi) >> 1;
-            unsigned long long q = s_pref[mid];
-            if (q == pre) {
-              slot = mid;
-              break;
+        for (int r = 0; r < 4; ++r)
+          v[r] = (row0 + r < n_nodes) ? __ldg(reinterpret_cast<const double2*>(D + (size_t)(row0 + r) * npad) + c)
+                                      : make_double2(0.0, 0.0);
+        const bool ok0 = src_of_pos[2 * c] >= 0, ok1 = src_of_pos[2 * c + 1] >= 0;  // padding slots are skipped
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          if (row0 + r >= n_nodes) break;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const bool ok = h ? ok1 : ok0;
+            const unsigned long long key = dkey(h ? v[r].y : v[r].x);
+            if (MODE == 1) {
+              // compaction: keep keys whose fixed prefix matches an active slot (warp-aggregated append)
+              bool keep = false;
+              if (ok) {
+                const unsigned long long pre = key >> (64 - consumed);
+                keep = pre >= pmin && pre <= pmax && rsel_find_slot(s_pref, U, pre) >= 0;
+              }
+              const unsigned am = __activemask();
+              const unsigned m = __ballot_sync(am, keep);
+              if (m) {
+                const int leader = __ffs(m) - 1;
+                unsigned int base = 0;
+                if (lane == leader) base = atomicAdd(cand.count, (unsigned int)__popc(m));
+                base = __shfl_sync(am, base, leader);
+                if (keep) {
+                  unsigned int idx = base + __popc(m & ((1u << lane) - 1u));
+                  if (idx < cand.capacity) cand.keys[idx] = key;
+                }
+              }
+            } else {
+              if (!ok) continue;
+              if (pass == 0 && key == ~0ull) ++nans;
+              visit(key);
             }
-            if (q < pre) lo = mid + 1;
-            else hi = mid - 1;
           }
-          if (slot < 0) continue;
         }
-        const unsigned int digit = (unsigned int)((key >> shift) & dmask);
-        if (slot < RSEL_SMEM_SLOTS) atomicAdd(&sh[slot * nbins + digit], 1u);
-        else atomicAdd(&hist[(size_t)slot * RSEL_BINS + digit], 1u);
       }
     }
-  }
-  if (pass == 0) {
+    if (MODE == 0 && pass == 0) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) nans += __shfl_xor_sync(0xffffffffu, nans, o);
-    if ((threadIdx.x & 31) == 0 && nans) atomicAdd(nan_count, nans);
+      for (int o = 16; o > 0; o >>= 1) nans += __shfl_xor_sync(0xffffffffu, nans, o);
+      if (lane == 0 && nans) atomicAdd(nan_count, nans);
+    }
   }
+  if (MODE == 1) return;
   __syncthreads();
   for (int i = threadIdx.x; i < usm * nbins; i += blockDim.x) {
     unsigned int c = sh[i];

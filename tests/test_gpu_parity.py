@@ -220,3 +220,48 @@ def test_dense_tile_path_matches_oracle(oracle, nf, n, K, monkeypatch):
     assert np.allclose(gpu0["stat"], gpu["stat"], rtol=1e-10, atol=0, equal_nan=True)
     eng.close()
     eng0.close()
+
+
+def test_single_process_multi_gpu_matches_one_gpu(engine):
+    """Edges sharded over the GPUs of one process (ncclCommInitAll + all-gather): identical to one GPU."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    eng2 = md.Engine(list(range(min(4, torch.cuda.device_count()))))
+    for K, method in ((2, _abi.METHOD_LM), (3, _abi.METHOD_LM), (2, _abi.METHOD_RLM)):
+        prob = synth.random_problem(80, 60, 333, K, 500 + K, method, _abi.PADJ_BH)
+        a = engine.run_omic(prob, ALL_FIELDS)
+        b = eng2.run_omic(prob, ALL_FIELDS)
+        for k in a:
+            assert np.array_equal(a[k], b[k], equal_nan=True), (K, method, k)
+    assert eng2.stats()["n_ranks"] >= 2
+    eng2.close()
+
+
+def test_node_band_copy_and_leading_dimension(engine, oracle):
+    """Only the band of node rows crosses PCIe; ld > G (a sub-matrix of a bigger R matrix) is honoured."""
+    import ctypes as C
+    base = synth.random_problem(200, 40, 10, 2, 81)
+    rng = np.random.default_rng(81)
+    pairs = set()
+    while len(pairs) < 150:
+        a, b = (int(v) for v in rng.integers(51, 121, size=2))      # nodes only in rows 51..120
+        if a != b:
+            pairs.add((a, b))
+    fr = np.array([p[0] for p in pairs], dtype=np.int32)
+    to = np.array([p[1] for p in pairs], dtype=np.int32)
+    base.from_idx, base.to_idx = fr, to
+    ref = oracle.run_omic(base, ALL_FIELDS)
+    gpu = engine.run_omic(base, ALL_FIELDS)
+    assert engine.stats()["h2d_bytes"] < 0.5 * base.assay.nbytes
+    assert_parity(gpu, ref, base, what="band: ")
+    # same data embedded in a taller column-major buffer: ld = G + 9
+    G, n = base.assay.shape
+    big = np.asfortranarray(np.full((G + 9, n), 777.0))
+    big[:G, :] = base.assay
+    cprob = base.to_c()
+    cprob.assay, cprob.ld = big.ctypes.data, G + 9
+    cres, arrays = _abi.alloc_result(base.dims, ALL_FIELDS)
+    engine.run_omic_raw(cprob, cres)
+    for k in gpu:
+        assert np.array_equal(gpu[k], arrays[k], equal_nan=True), k
