@@ -120,7 +120,8 @@ typedef struct mdeggs_stats {
   int64_t ref_equiv_tests; /* sum over percentiles of tot_edges: fits the reference would have run      */
   int64_t kernel_launches; /* CUDA kernels launched by the last call (this library's + CUB's)           */
   int64_t h2d_bytes, d2h_bytes;
-  int32_t fit_path;       /* 0 warp-per-edge streaming, 1 dense tile cross-moments, 2 rlm IRLS          */
+  int32_t fit_path;       /* bits 0-7: 0 warp-per-edge streaming, 1 dense tile cross-moments, 2 rlm IRLS;
+                             bit 8: the compute phase was replayed from a CUDA graph                       */
   int32_t n_ranks;
   float ms_total;         /* device time of the whole pipeline (CUDA events on the engine stream)       */
   float ms_h2d, ms_gather, ms_stats, ms_quantile, ms_fit, ms_tail, ms_collective, ms_percolate, ms_adjust, ms_d2h;
@@ -146,6 +147,10 @@ int mdeggs_pair_features(mdeggs_ctx* ctx, const double* x, int64_t ldx, int32_t 
                          const int32_t* b, int32_t n_pairs, int32_t ratio, int32_t mem, double* out);
 
 int mdeggs_last_stats(const mdeggs_ctx* ctx, mdeggs_stats* out);
+/* Engine options: "graph" (1 = replay the compute phase from a CUDA graph when a call repeats with identical
+ * shapes and buffers [default], 0 = always launch eagerly, which also keeps the per-stage timings);
+ * "fit_path" (-1 = choose streaming vs dense-tile pair fits automatically [default], 0 = streaming, 1 = dense). */
+int mdeggs_set_option(mdeggs_ctx* ctx, const char* name, int64_t value);
 const char* mdeggs_last_error(const mdeggs_ctx* ctx);
 const char* mdeggs_strerror(int code);
 int mdeggs_abi_version(void);

@@ -135,9 +135,9 @@ __global__ void __launch_bounds__(256) k_fit_dense_edges(const double* __restric
                                                          const double* __restrict__ sxx,
                                                          const uint8_t* __restrict__ bad, int64_t e_lo, int64_t e_hi,
                                                          double* __restrict__ stat, int32_t* __restrict__ status,
-                                                         double* __restrict__ coef) {
+                                                         double* __restrict__ coef, const int32_t* __restrict__ err) {
   const int64_t e = e_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= e_hi) return;
+  if (e >= e_hi || *err) return;
   const int ra = from[e] - 1, rb = to[e] - 1;
   const int a = node_of_row[ra], b = node_of_row[rb];
   if (ra == rb || bad[a] || bad[b]) {

@@ -68,6 +68,17 @@ struct Shard {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   nccl_comm_t comm = nullptr;
   int64_t row_off = 0, ld_eff = 0;  // the device copy of the assay starts at host row `row_off`
+  void* h_stage = nullptr;          // pinned host staging for the tiny per-call inputs (src_of_pos, pct, df)
+  size_t h_stage_cap = 0;
+  cudaError_t ensure_stage(size_t bytes) {
+    if (bytes <= h_stage_cap) return cudaSuccess;
+    if (h_stage) cudaFreeHost(h_stage);
+    h_stage = nullptr;
+    h_stage_cap = 0;
+    cudaError_t e = cudaMallocHost(&h_stage, bytes + 256);
+    if (e == cudaSuccess) h_stage_cap = bytes + 256;
+    return e;
+  }
   DevBuf assay, from, to, flags, excl, node_of_row, rowlist, scal, src_of_pos, pct, cutoff, D, keys, keys_sorted,
       cub_tmp, cub_tmp2, mean, sxx, med, bad, stat, status, p_edge, coef, iters, act, counters, sortk, sortk2, idx,
       idx2, ps, sa, sb, tile_cnt, tile_base, seg_n, tile_min, tile_carry, padj_best, cat_best, cat, padj, med_out,
@@ -84,11 +95,29 @@ struct Shard {
 
 }  // namespace
 
+// Everything that is baked into a captured compute graph: if any of it changes the graph is rebuilt.
+struct GraphKey {
+  mdeggs_problem in;  // group / pct pointers zeroed (their content reaches the device through staging)
+  mdeggs_result out;
+  SegLayout L;
+  const void *d_assay, *d_from, *d_to;
+  int64_t row_off, ld_eff;
+  size_t dense_cap;
+};
+
 struct mdeggs_ctx {
   std::vector<Shard> shards;
   std::string err;
   mdeggs_stats stats;
   int64_t launches = 0;
+  // CUDA-graph replay of the compute phase (K0..K8) for repeated calls with identical shapes and buffers
+  int use_graph = 1;         // option "graph" / MDEGGS_GRAPH
+  bool capturing = false;
+  bool key_valid = false;
+  GraphKey key;
+  int key_hits = 0;
+  cudaGraphExec_t graph_exec = nullptr;
+  int64_t graph_launches = 0;
   bool smem_attr_set = false;
   bool rsel_attr_set = false;
   int fit_path_override = -1;  // -1 auto, 0 force streaming, 1 force dense (MDEGGS_FIT_PATH, tests)
@@ -123,6 +152,12 @@ void set_err(mdeggs_ctx* c, const char* fmt, ...) {
               api_.GetErrorString ? api_.GetErrorString(r_) : "nccl error");                  \
       return MDEGGS_ENCCL;                                                                     \
     }                                                                                          \
+  } while (0)
+
+// stage-boundary timing events are not recorded while the compute phase is being captured into a graph
+#define EVREC(ev, stream)                                  \
+  do {                                                     \
+    if (!ctx->capturing) CU(cudaEventRecord((ev), (stream))); \
   } while (0)
 
 #define LAUNCH(kernel, grid, block, smem, stream, ...)                                         \
@@ -183,7 +218,8 @@ void launch_fit_dense_edges(mdeggs_ctx* ctx, Shard& s, const SegLayout& L, int n
                             double* coef) {
   LAUNCH(k_fit_dense_edges<K>, blocks_for(e_hi - e_lo, 256), 256, 0, s.s_main, s.dense_S.as<double>(), L, nn,
          s.from.as<int32_t>(), s.to.as<int32_t>(), s.node_of_row.as<int32_t>(), s.mean.as<double>(),
-         s.sxx.as<double>(), s.bad.as<uint8_t>(), e_lo, e_hi, s.stat.as<double>(), s.status.as<int32_t>(), coef);
+         s.sxx.as<double>(), s.bad.as<uint8_t>(), e_lo, e_hi, s.stat.as<double>(), s.status.as<int32_t>(), coef,
+         s.scal.as<int32_t>() + 2 * SC_ERR);
 }
 
 template <int K>
@@ -195,7 +231,7 @@ void launch_fit_stream(mdeggs_ctx* ctx, Shard& s, const SegLayout& L, int64_t e_
   unsigned grid = (unsigned)(want_blocks < cap ? want_blocks : cap);
   LAUNCH(k_fit_stream<K>, grid, 256, 0, s.s_main, s.D.as<double>(), L, s.from.as<int32_t>(), s.to.as<int32_t>(),
          s.node_of_row.as<int32_t>(), s.mean.as<double>(), s.sxx.as<double>(), s.bad.as<uint8_t>(), e_lo, e_hi,
-         s.stat.as<double>(), s.status.as<int32_t>(), coef);
+         s.stat.as<double>(), s.status.as<int32_t>(), coef, s.scal.as<int32_t>() + 2 * SC_ERR);
 }
 
 int copy_out(mdeggs_ctx* ctx, Shard& s, void* dst, const void* src, size_t bytes, int mem) {
@@ -241,9 +277,8 @@ int run_adjust(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, int n_segmen
   return MDEGGS_OK;
 }
 
-int run_shard_front(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const HostLayout& H, const void* assay_src,
-                    int src_device, int32_t* n_nodes_host) {
-  const SegLayout& L = H.L;
+// Phase A (always eager): caller inputs -> device, tiny per-call tables through pinned staging.
+int stage_inputs(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const HostLayout& H, int src_device) {
   const int G = in->G, n = in->n;
   const int64_t E = in->E;
   CU(cudaSetDevice(s.device));
@@ -322,7 +357,6 @@ int run_shard_front(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const H
     d_from = s.from.as<int32_t>();
     d_to = s.to.as<int32_t>();
   }
-  (void)assay_src;
   // borrowed device pointers are stashed in the DevBuf slots without ownership for later stages
   if (in->mem == MDEGGS_MEM_DEVICE && s.device == src_device) {
     s.assay.release();
@@ -332,11 +366,26 @@ int run_shard_front(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const H
     s.from.p = (void*)d_from;
     s.to.p = (void*)d_to;  // cap stays 0 => never freed by us
   }
-  CU(s.src_of_pos.ensure(H.src_of_pos.size() * 4));
-  CU(cudaMemcpyAsync(s.src_of_pos.p, H.src_of_pos.data(), H.src_of_pos.size() * 4, cudaMemcpyHostToDevice, s.s_main));
+  const size_t sop_bytes = H.src_of_pos.size() * 4, pct_bytes = (size_t)(in->P > 0 ? in->P : 0) * 8;
+  const size_t pct_off = (sop_bytes + 15) & ~(size_t)15;
+  CU(s.ensure_stage(pct_off + pct_bytes + 32));
+  memcpy(s.h_stage, H.src_of_pos.data(), sop_bytes);
+  if (pct_bytes) memcpy((char*)s.h_stage + pct_off, in->pct, pct_bytes);
+  CU(s.src_of_pos.ensure(sop_bytes));
+  CU(cudaMemcpyAsync(s.src_of_pos.p, s.h_stage, sop_bytes, cudaMemcpyHostToDevice, s.s_main));
   CU(s.pct.ensure((size_t)(in->P > 0 ? in->P : 1) * 8));
-  if (in->P > 0) CU(cudaMemcpyAsync(s.pct.p, in->pct, (size_t)in->P * 8, cudaMemcpyHostToDevice, s.s_main));
+  if (pct_bytes) CU(cudaMemcpyAsync(s.pct.p, (char*)s.h_stage + pct_off, pct_bytes, cudaMemcpyHostToDevice, s.s_main));
   CU(cudaEventRecord(s.ev[EV_H2D], s.s_main));
+  return MDEGGS_OK;
+}
+
+// Phase B starts here (capturable): K0 node filter
+int run_shard_front(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, int32_t* n_nodes_host) {
+  const int G = in->G;
+  const int64_t E = in->E;
+  CU(cudaSetDevice(s.device));
+  const int32_t* d_from = s.from.as<int32_t>();
+  const int32_t* d_to = s.to.as<int32_t>();
   // ---- K0 node filter ----
   CU(s.flags.ensure((size_t)G * 4));
   CU(s.excl.ensure((size_t)G * 4));
@@ -357,15 +406,11 @@ int run_shard_front(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const H
   ctx->launches += 2;
   LAUNCH(k_build_rowlist, blocks_for(G, 256), 256, 0, s.s_main, s.flags.as<int32_t>(), s.excl.as<int32_t>(), G,
          s.node_of_row.as<int32_t>(), s.rowlist.as<int32_t>(), s.scal.as<int32_t>() + 2 * SC_NNODES);
-  // the only mid-pipeline host read: node count (sizes D / the sort) and the index-range error flag
-  long long host_scal[2];
-  CU(cudaMemcpyAsync(host_scal, s.scal.p, 16, cudaMemcpyDeviceToHost, s.s_main));
-  CU(cudaStreamSynchronize(s.s_main));
-  if ((int32_t)host_scal[SC_ERR] != 0) {
-    set_err(ctx, "from/to contain an index outside 1..G");
-    return MDEGGS_EINVAL;
-  }
-  *n_nodes_host = (int32_t)host_scal[SC_NNODES];
+  // No mid-pipeline host read: buffers and grids are sized for the upper bound min(G, 2E) of the node count,
+  // kernels read the real count from device memory, and an out-of-range edge index raises a device flag that
+  // makes every later edge kernel exit at once; the flag and the count are read after the final sync.
+  int64_t cap = 2 * E < (int64_t)G ? 2 * E : (int64_t)G;
+  *n_nodes_host = (int32_t)cap;
   return MDEGGS_OK;
 }
 
@@ -395,11 +440,11 @@ int run_shard_main(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
              s.src_of_pos.as<int32_t>(), L.npad, n, s.D.as<double>());
     }
   }
-  CU(cudaEventRecord(s.ev[EV_GATHER], s.s_main));
+  EVREC(s.ev[EV_GATHER], s.s_main);
   // ---- K3 on the side stream: radix-select every percentile's two order statistics (no sort) ----
   CU(cudaEventRecord(s.ev_fork, s.s_main));
   CU(cudaStreamWaitEvent(s.s_sort, s.ev_fork, 0));
-  CU(cudaEventRecord(s.ev[EV_Q0], s.s_sort));
+  EVREC(s.ev[EV_Q0], s.s_sort);
   if (n_nodes > 0 && P > 0) {
     const size_t hist_bytes = (size_t)2 * P * RSEL_BINS * sizeof(unsigned int);
     CU(s.rsel_hist.ensure(hist_bytes));
@@ -435,20 +480,35 @@ int run_shard_main(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
   } else if (P > 0) {
     LAUNCH(k_fill_f64, 1, 64, 0, s.s_sort, s.cutoff.as<double>(), (int64_t)P, nan(""));
   }
-  CU(cudaEventRecord(s.ev[EV_Q1], s.s_sort));
+  EVREC(s.ev[EV_Q1], s.s_sort);
   CU(cudaEventRecord(s.ev_join, s.s_sort));
   // ---- K2 gene stats ----
   if (n_nodes > 0) {
-    size_t smem = (size_t)L.npad * 8;
-    int use_smem = smem <= 200 * 1024;
-    if (use_smem && smem > 48 * 1024 && !ctx->smem_attr_set) {
-      CU(cudaFuncSetAttribute(k_gene_stats<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      ctx->smem_attr_set = true;
+    int max_cnt = 0;
+    for (int k = 0; k < K; ++k) max_cnt = L.cnt[k] > max_cnt ? L.cnt[k] : max_cnt;
+    if (max_cnt <= 32 * 32) {  // segments fit in registers: one warp per (gene, category)
+      CU(cudaMemsetAsync(s.bad.p, 0, nn, s.s_main));
+      const unsigned grid = (unsigned)(((long long)n_nodes * K + 7) / 8);
+#define MDEGGS_GS(IT)                                                                                          \
+  LAUNCH(k_gene_stats_reg<IT>, grid, 256, 0, s.s_main, s.D.as<double>(), L, d_nn, s.mean.as<double>(),        \
+         s.sxx.as<double>(), s.med.as<double>(), s.bad.as<uint8_t>())
+      if (max_cnt <= 32 * 4) MDEGGS_GS(4);
+      else if (max_cnt <= 32 * 8) MDEGGS_GS(8);
+      else if (max_cnt <= 32 * 16) MDEGGS_GS(16);
+      else MDEGGS_GS(32);
+#undef MDEGGS_GS
+    } else {
+      size_t smem = (size_t)L.npad * 8;
+      int use_smem = smem <= 200 * 1024;
+      if (use_smem && smem > 48 * 1024 && !ctx->smem_attr_set) {
+        CU(cudaFuncSetAttribute(k_gene_stats<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        ctx->smem_attr_set = true;
+      }
+      LAUNCH(k_gene_stats<128>, (unsigned)n_nodes, 128, use_smem ? smem : 0, s.s_main, s.D.as<double>(), L, d_nn,
+             s.mean.as<double>(), s.sxx.as<double>(), s.med.as<double>(), s.bad.as<uint8_t>(), use_smem);
     }
-    LAUNCH(k_gene_stats<128>, (unsigned)n_nodes, 128, use_smem ? smem : 0, s.s_main, s.D.as<double>(), L, d_nn,
-           s.mean.as<double>(), s.sxx.as<double>(), s.med.as<double>(), s.bad.as<uint8_t>(), use_smem);
   }
-  CU(cudaEventRecord(s.ev[EV_STATS], s.s_main));
+  EVREC(s.ev[EV_STATS], s.s_main);
   // ---- pair fits on this rank's contiguous edge block ----
   const int64_t chunk = (E + s.world - 1) / s.world;
   const int64_t e_lo = (int64_t)s.rank * chunk < E ? (int64_t)s.rank * chunk : E;
@@ -482,7 +542,8 @@ int run_shard_main(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
       int rc = launch_fit_rlm(ctx->launches, s.s_main, s.D.as<double>(), L, s.from.as<int32_t>(), s.to.as<int32_t>(),
                               s.node_of_row.as<int32_t>(), s.mean.as<double>(), s.sxx.as<double>(),
                               s.bad.as<uint8_t>(), e_lo, e_hi, in->tested_coef, in->rlm_cov_mode,
-                              s.stat.as<double>(), s.status.as<int32_t>(), d_coef, s.iters.as<int32_t>());
+                              s.stat.as<double>(), s.status.as<int32_t>(), d_coef, s.iters.as<int32_t>(),
+                              s.scal.as<int32_t>() + 2 * SC_ERR);
       if (rc != 0) {
         set_err(ctx, "rlm kernel configuration failed (n too large for shared memory?)");
         return MDEGGS_EUNSUPPORTED;
@@ -514,7 +575,7 @@ int run_shard_main(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
       }
     }
   }
-  CU(cudaEventRecord(s.ev[EV_FIT], s.s_main));
+  EVREC(s.ev[EV_FIT], s.s_main);
   double df1, df2;
   int tail_mode;
   if (K == 2) {
@@ -542,7 +603,7 @@ int run_shard_main(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
     LAUNCH(k_tail, blocks_for(e_hi - e_lo, 128), 128, 0, s.s_main, s.stat.as<double>(), s.status.as<int32_t>(), e_lo,
            e_hi, tail_mode, df1, df2, tc, d_lbeta, s.p_edge.as<double>());
   }
-  CU(cudaEventRecord(s.ev[EV_TAIL], s.s_main));
+  EVREC(s.ev[EV_TAIL], s.s_main);
   return MDEGGS_OK;
 }
 
@@ -579,7 +640,7 @@ int run_collective(mdeggs_ctx* ctx, const mdeggs_problem* in, const mdeggs_resul
   }
   for (Shard& s : ctx->shards) {
     CU(cudaSetDevice(s.device));
-    CU(cudaEventRecord(s.ev[EV_COLL], s.s_main));
+    EVREC(s.ev[EV_COLL], s.s_main);
   }
   return MDEGGS_OK;
 }
@@ -594,6 +655,33 @@ int run_shard_back(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
   int32_t* d_best = s.scal.as<int32_t>() + 2 * SC_BEST;
   const int act_stride = n_nodes > 0 ? n_nodes : 1;
   const int Pn = P > 0 ? P : 1;
+  const bool dev_adjust = (in->padj == MDEGGS_PADJ_BONFERRONI || in->padj == MDEGGS_PADJ_BH);
+  const bool do_adjust = dev_adjust && E > 0 && P > 0 && n_nodes > 0;
+  if (do_adjust) {
+    // The raw p-value of an edge does not depend on the percentile: sort ALL edges by p once. This needs no
+    // cut-off, so it is enqueued BEFORE joining the quantile stream and overlaps the tail of the radix select.
+    CU(s.sortk.ensure((size_t)E * 8));
+    CU(s.sortk2.ensure((size_t)E * 8));
+    CU(s.idx.ensure((size_t)E * 4));
+    CU(s.idx2.ensure((size_t)E * 4));
+    CU(s.ps.ensure((size_t)E * 8));
+    CU(s.sa.ensure((size_t)E * 4));
+    CU(s.sb.ensure((size_t)E * 4));
+    LAUNCH(k_sort_keys, blocks_for(E, 256), 256, 0, s.s_main, s.p_edge.as<double>(), E,
+           s.sortk.as<unsigned long long>(), s.idx.as<int32_t>());
+    size_t tb = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, s.sortk.as<unsigned long long>(), s.sortk2.as<unsigned long long>(),
+                                    s.idx.as<int32_t>(), s.idx2.as<int32_t>(), E, 0, 64, s.s_main);
+    CU(s.cub_tmp.ensure(tb));
+    CU(cub::DeviceRadixSort::SortPairs(s.cub_tmp.p, tb, s.sortk.as<unsigned long long>(),
+                                       s.sortk2.as<unsigned long long>(), s.idx.as<int32_t>(), s.idx2.as<int32_t>(), E,
+                                       0, 64, s.s_main));
+    ctx->launches += 10;
+    LAUNCH(k_gather_sorted, blocks_for(E, 256), 256, 0, s.s_main, s.sortk2.as<unsigned long long>(),
+           s.idx2.as<int32_t>(), s.from.as<int32_t>(), s.to.as<int32_t>(), s.node_of_row.as<int32_t>(), E,
+           s.ps.as<double>(), s.sa.as<int32_t>(), s.sb.as<int32_t>(), s.scal.as<unsigned long long>() + SC_NVALID,
+           s.scal.as<int32_t>() + 2 * SC_ERR);
+  }
   CU(cudaStreamWaitEvent(s.s_main, s.ev_join, 0));  // cut-offs ready
   // counters: tot[P] fail[P] sig[P] sig_raw[P] (u64), then out: tot_out[P] sig_out[P] fail_out[P] (i64)
   CU(s.counters.ensure((size_t)Pn * 8 * 7));
@@ -621,42 +709,24 @@ int run_shard_back(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
     if (E > 0)
       LAUNCH(k_percolate, blocks_for(E, 256), 256, (size_t)3 * P * sizeof(unsigned), s.s_main, s.from.as<int32_t>(),
              s.to.as<int32_t>(), s.node_of_row.as<int32_t>(), s.status.as<int32_t>(), s.p_edge.as<double>(),
-             s.act.as<uint8_t>(), act_stride, E, P, c_tot, c_fail, c_raw, d_cat);
+             s.act.as<uint8_t>(), act_stride, E, P, c_tot, c_fail, c_raw, d_cat, s.scal.as<int32_t>() + 2 * SC_ERR);
   }
-  CU(cudaEventRecord(s.ev[EV_PERC], s.s_main));
+  EVREC(s.ev[EV_PERC], s.s_main);
   // ---- K8 ----
-  const bool dev_adjust = (in->padj == MDEGGS_PADJ_BONFERRONI || in->padj == MDEGGS_PADJ_BH);
   double* d_padj = nullptr;
-  if (dev_adjust && E > 0 && P > 0 && n_nodes > 0) {
+  const bool want_padj_best = out->padj_best && do_adjust;
+  // adjusted values of every percentile are kept when they fit a modest scratch matrix, so the best row is a copy
+  const bool keep_all_padj = do_adjust && (out->padj || (want_padj_best && (size_t)P * (size_t)E * 8 <= ((size_t)256 << 20)));
+  if (do_adjust) {
     const int ntiles = (int)((E + BH_TILE - 1) / BH_TILE);
-    CU(s.sortk.ensure((size_t)E * 8));
-    CU(s.sortk2.ensure((size_t)E * 8));
-    CU(s.idx.ensure((size_t)E * 4));
-    CU(s.idx2.ensure((size_t)E * 4));
-    CU(s.ps.ensure((size_t)E * 8));
-    CU(s.sa.ensure((size_t)E * 4));
-    CU(s.sb.ensure((size_t)E * 4));
     const size_t nseg = (size_t)P * K;
     CU(s.tile_cnt.ensure(nseg * ntiles * 4));
     CU(s.tile_base.ensure(nseg * ntiles * 8));
     CU(s.tile_min.ensure(nseg * ntiles * 8));
     CU(s.tile_carry.ensure(nseg * ntiles * 8));
     CU(s.seg_n.ensure(nseg * 8));
-    LAUNCH(k_sort_keys, blocks_for(E, 256), 256, 0, s.s_main, s.p_edge.as<double>(), E,
-           s.sortk.as<unsigned long long>(), s.idx.as<int32_t>());
-    size_t tb = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, tb, s.sortk.as<unsigned long long>(), s.sortk2.as<unsigned long long>(),
-                                    s.idx.as<int32_t>(), s.idx2.as<int32_t>(), E, 0, 64, s.s_main);
-    CU(s.cub_tmp.ensure(tb));
-    CU(cub::DeviceRadixSort::SortPairs(s.cub_tmp.p, tb, s.sortk.as<unsigned long long>(),
-                                       s.sortk2.as<unsigned long long>(), s.idx.as<int32_t>(), s.idx2.as<int32_t>(), E,
-                                       0, 64, s.s_main));
-    ctx->launches += 10;
-    LAUNCH(k_gather_sorted, blocks_for(E, 256), 256, 0, s.s_main, s.sortk2.as<unsigned long long>(),
-           s.idx2.as<int32_t>(), s.from.as<int32_t>(), s.to.as<int32_t>(), s.node_of_row.as<int32_t>(), E,
-           s.ps.as<double>(), s.sa.as<int32_t>(), s.sb.as<int32_t>(), s.scal.as<unsigned long long>() + SC_NVALID);
-    if (out->padj) {
-      if (dev_out && emit) d_padj = out->padj;
+    if (keep_all_padj) {
+      if (out->padj && dev_out && emit) d_padj = out->padj;
       else {
         CU(s.padj.ensure((size_t)P * E * 8));
         d_padj = s.padj.as<double>();
@@ -673,34 +743,54 @@ int run_shard_back(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
          o_sig, o_fail, d_best);
   // rows of the chosen percentile
   const bool want_cat_best = out->cat_best && E > 0 && in->padj != MDEGGS_PADJ_HOST;
-  const bool want_padj_best = out->padj_best && E > 0 && dev_adjust && n_nodes > 0 && P > 0;
-  if (want_cat_best) {
-    CU(s.cat_best.ensure((size_t)E));
-    LAUNCH(k_cat_row, blocks_for(E, 256), 256, 0, s.s_main, s.from.as<int32_t>(), s.to.as<int32_t>(),
-           s.node_of_row.as<int32_t>(), s.act.as<uint8_t>(), act_stride, E, d_best, s.cat_best.as<int8_t>());
-  }
-  if (want_padj_best) {
-    CU(s.padj_best.ensure((size_t)E * 8));
+  if (want_cat_best) CU(s.cat_best.ensure((size_t)E));
+  if (want_padj_best) CU(s.padj_best.ensure((size_t)E * 8));
+  const bool row_copy = want_padj_best && keep_all_padj;
+  if (want_padj_best && !row_copy) {  // P x E too large to keep: rerun the adjustment for the best percentile only
     LAUNCH(k_fill_f64, (unsigned)(blocks_for(E, 256) < 148u * 16 ? blocks_for(E, 256) : 148u * 16), 256, 0, s.s_main,
            s.padj_best.as<double>(), E, nan(""));
     int rc = run_adjust(ctx, s, in, K, 0, d_best, nullptr, s.padj_best.as<double>(), E, act_stride);
     if (rc) return rc;
   }
-  CU(cudaEventRecord(s.ev[EV_ADJ], s.s_main));
-  if (!emit) {
-    CU(cudaEventRecord(s.ev[EV_END], s.s_main));
-    return MDEGGS_OK;
-  }
-  // ---- outputs ----
-  const int mem = in->mem;
-  int rc;
-  if ((rc = copy_out(ctx, s, out->cutoff, s.cutoff.p, (size_t)P * 8, mem))) return rc;
-  if (out->median) {
+  if (want_cat_best || row_copy)
+    LAUNCH(k_best_rows, blocks_for(E, 256), 256, 0, s.s_main, s.from.as<int32_t>(), s.to.as<int32_t>(),
+           s.node_of_row.as<int32_t>(), s.act.as<uint8_t>(), act_stride, E, d_best,
+           want_cat_best ? s.cat_best.as<int8_t>() : nullptr, row_copy ? d_padj : nullptr,
+           row_copy ? s.padj_best.as<double>() : nullptr, s.scal.as<int32_t>() + 2 * SC_ERR);
+  if (emit && out->median) {
     CU(s.med_out.ensure((size_t)G * K * 8));
     LAUNCH(k_scatter_median, blocks_for((int64_t)G * K, 256), 256, 0, s.s_main, s.med.as<double>(),
            s.node_of_row.as<int32_t>(), G, K, s.med_out.as<double>());
-    if ((rc = copy_out(ctx, s, out->median, s.med_out.p, (size_t)G * K * 8, mem))) return rc;
   }
+  EVREC(s.ev[EV_ADJ], s.s_main);
+  return MDEGGS_OK;
+}
+
+// Phase C (always eager): results -> caller buffers
+int emit_outputs(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const mdeggs_result* out, const HostLayout& H,
+                 int32_t n_nodes) {
+  const int G = in->G, K = in->K, P = in->P;
+  const int64_t E = in->E;
+  CU(cudaSetDevice(s.device));
+  const int Pn = P > 0 ? P : 1;
+  int32_t* d_best = s.scal.as<int32_t>() + 2 * SC_BEST;
+  unsigned long long* c_tot = s.counters.as<unsigned long long>();
+  long long* o_tot = (long long*)(c_tot + 4 * Pn);
+  long long* o_sig = o_tot + Pn;
+  long long* o_fail = o_tot + 2 * Pn;
+  const bool dev_out = in->mem == MDEGGS_MEM_DEVICE;
+  const bool dev_adjust = (in->padj == MDEGGS_PADJ_BONFERRONI || in->padj == MDEGGS_PADJ_BH);
+  const int8_t* d_cat = (out->cat && E > 0 && P > 0) ? (dev_out ? out->cat : s.cat.as<int8_t>()) : nullptr;
+  const double* d_padj = (dev_adjust && E > 0 && P > 0 && n_nodes > 0 && out->padj)
+                             ? (dev_out ? out->padj : s.padj.as<double>())
+                             : nullptr;  // (an internal scratch copy used only for the best row is never emitted)
+  const bool want_cat_best = out->cat_best && E > 0 && in->padj != MDEGGS_PADJ_HOST;
+  const bool want_padj_best = out->padj_best && E > 0 && dev_adjust && n_nodes > 0 && P > 0;
+  const int mem = in->mem;
+  int rc;
+  if ((rc = copy_out(ctx, s, out->cutoff, s.cutoff.p, (size_t)P * 8, mem))) return rc;
+  if (out->median)
+    if ((rc = copy_out(ctx, s, out->median, s.med_out.p, (size_t)G * K * 8, mem))) return rc;
   if ((rc = copy_out(ctx, s, out->p_edge, s.p_edge.p, (size_t)E * 8, mem))) return rc;
   if ((rc = copy_out(ctx, s, out->stat, s.stat.p, (size_t)E * 8, mem))) return rc;
   if ((rc = copy_out(ctx, s, out->coef, s.coef.p, (size_t)E * 2 * K * 8, mem))) return rc;
@@ -740,11 +830,11 @@ int run_shard_back(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
     if (mem == MDEGGS_MEM_HOST) {
       out->df[0] = dfh[0];
       out->df[1] = dfh[1];
-    } else {
-      CU(s.small_out.ensure(16));
-      CU(cudaMemcpyAsync(s.small_out.p, dfh, 16, cudaMemcpyHostToDevice, s.s_main));
-      CU(cudaStreamSynchronize(s.s_main));
-      CU(cudaMemcpyAsync(out->df, s.small_out.p, 16, cudaMemcpyDeviceToDevice, s.s_main));
+    } else {  // the tail of the pinned staging block carries the two doubles
+      double* st = reinterpret_cast<double*>((char*)s.h_stage + s.h_stage_cap - 16);
+      st[0] = dfh[0];
+      st[1] = dfh[1];
+      CU(cudaMemcpyAsync(out->df, st, 16, cudaMemcpyHostToDevice, s.s_main));
     }
   }
   CU(cudaEventRecord(s.ev[EV_END], s.s_main));
@@ -789,6 +879,7 @@ int mdeggs_create(mdeggs_ctx** out, const int* device_ids, int n_dev) {
   mdeggs_ctx* ctx = new mdeggs_ctx();
   memset(&ctx->stats, 0, sizeof ctx->stats);
   if (const char* fp = getenv("MDEGGS_FIT_PATH")) ctx->fit_path_override = atoi(fp);
+  if (const char* g = getenv("MDEGGS_GRAPH")) ctx->use_graph = atoi(g);
   ctx->shards.resize((size_t)n_dev);
   for (int i = 0; i < n_dev; ++i) {
     ctx->shards[(size_t)i].device = device_ids[i];
@@ -834,6 +925,7 @@ int mdeggs_create_rank(mdeggs_ctx** out, int device_id, int rank, int world, con
   mdeggs_ctx* ctx = new mdeggs_ctx();
   memset(&ctx->stats, 0, sizeof ctx->stats);
   if (const char* fp = getenv("MDEGGS_FIT_PATH")) ctx->fit_path_override = atoi(fp);
+  if (const char* g = getenv("MDEGGS_GRAPH")) ctx->use_graph = atoi(g);
   ctx->shards.resize(1);
   Shard& s = ctx->shards[0];
   s.device = device_id;
@@ -863,9 +955,11 @@ int mdeggs_create_rank(mdeggs_ctx** out, int device_id, int rank, int world, con
 
 int mdeggs_destroy(mdeggs_ctx* ctx) {
   if (!ctx) return MDEGGS_OK;
+  if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
   for (Shard& s : ctx->shards) {
     cudaSetDevice(s.device);
     cudaDeviceSynchronize();
+    if (s.h_stage) cudaFreeHost(s.h_stage);
     if (s.comm) nccl_api().CommDestroy(s.comm);
     s.release_all();
     for (int i = 0; i < EV_COUNT; ++i)
@@ -914,22 +1008,106 @@ int mdeggs_run_omic(mdeggs_ctx* ctx, const mdeggs_problem* in, mdeggs_result* ou
   ctx->launches = 0;
   memset(&ctx->stats, 0, sizeof ctx->stats);
   const int src_device = ctx->shards[0].device;
-  int32_t n_nodes = 0;
+  Shard& sh0 = ctx->shards[0];
+  // ---- phase A: inputs (eager) ----
   for (Shard& s : ctx->shards) {
-    int32_t nn = 0;
-    rc = run_shard_front(ctx, s, in, H, in->assay, src_device, &nn);
-    if (rc) return rc;
-    n_nodes = nn;
-  }
-  for (Shard& s : ctx->shards) {
-    rc = run_shard_main(ctx, s, in, out, H, n_nodes);
+    rc = stage_inputs(ctx, s, in, H, src_device);
     if (rc) return rc;
   }
-  rc = run_collective(ctx, in, out);
+  // ---- phase B: compute, replayed from a CUDA graph when this exact call shape repeats ----
+  auto enqueue_compute = [&](int32_t* n_cap) -> int {
+    int r = MDEGGS_OK;
+    for (Shard& s : ctx->shards)
+      if ((r = run_shard_front(ctx, s, in, n_cap))) return r;
+    for (Shard& s : ctx->shards)
+      if ((r = run_shard_main(ctx, s, in, out, H, *n_cap))) return r;
+    if ((r = run_collective(ctx, in, out))) return r;
+    for (size_t i = 0; i < ctx->shards.size(); ++i)
+      if ((r = run_shard_back(ctx, ctx->shards[i], in, out, H, *n_cap, i == 0))) return r;
+    return r;
+  };
+  int32_t n_nodes = (int32_t)(2 * in->E < (int64_t)in->G ? 2 * in->E : (int64_t)in->G);
+  bool graph_ok = ctx->use_graph && ctx->shards.size() == 1 && sh0.world == 1;
+  bool replayed = false;
+  if (graph_ok) {
+    GraphKey key;
+    memset(&key, 0, sizeof key);
+    key.in = *in;
+    key.in.group = nullptr;
+    key.in.pct = nullptr;
+    key.out = *out;
+    key.L = H.L;
+    key.d_assay = sh0.assay.p;
+    key.d_from = sh0.from.p;
+    key.d_to = sh0.to.p;
+    key.row_off = sh0.row_off;
+    key.ld_eff = sh0.ld_eff;
+    key.dense_cap = sh0.dense_S.cap;
+    if (in->mem == MDEGGS_MEM_HOST) {  // host buffers are only touched by the eager phases A and C
+      key.in.assay = nullptr;
+      key.in.from = key.in.to = nullptr;
+      memset(&key.out, 0, sizeof key.out);
+      const void* const* op = reinterpret_cast<const void* const*>(out);
+      void** kp = reinterpret_cast<void**>(&key.out);
+      for (size_t i = 0; i < sizeof(mdeggs_result) / sizeof(void*); ++i) kp[i] = op[i] ? (void*)1 : nullptr;
+    }
+    if (ctx->key_valid && memcmp(&key, &ctx->key, sizeof key) == 0) {
+      ++ctx->key_hits;
+    } else {
+      if (ctx->graph_exec) {
+        cudaGraphExecDestroy(ctx->graph_exec);
+        ctx->graph_exec = nullptr;
+      }
+      ctx->key = key;
+      ctx->key_valid = true;
+      ctx->key_hits = 0;
+    }
+    if (ctx->key_hits >= 1 && !ctx->graph_exec) {  // second identical call: every buffer already has its size
+      cudaGraph_t graph = nullptr;
+      CU(cudaSetDevice(sh0.device));
+      CU(cudaStreamBeginCapture(sh0.s_main, cudaStreamCaptureModeRelaxed));
+      ctx->capturing = true;
+      ctx->launches = 0;
+      int32_t cap = 0;
+      int r = enqueue_compute(&cap);
+      ctx->capturing = false;
+      cudaError_t ce = cudaStreamEndCapture(sh0.s_main, &graph);
+      if (r != MDEGGS_OK || ce != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        ctx->use_graph = 0;  // capture not possible in this configuration: stay eager from now on
+        graph_ok = false;
+      } else {
+        ce = cudaGraphInstantiate(&ctx->graph_exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ce != cudaSuccess) {
+          ctx->graph_exec = nullptr;
+          cudaGetLastError();
+          ctx->use_graph = 0;
+          graph_ok = false;
+        } else {
+          ctx->graph_launches = ctx->launches;
+        }
+      }
+    }
+    if (graph_ok && ctx->graph_exec) {
+      CU(cudaGraphLaunch(ctx->graph_exec, sh0.s_main));
+      CU(cudaEventRecord(sh0.ev[EV_ADJ], sh0.s_main));
+      ctx->launches = ctx->graph_launches;
+      replayed = true;
+    }
+  }
+  if (!replayed) {
+    ctx->launches = 0;
+    rc = enqueue_compute(&n_nodes);
+    if (rc) return rc;
+  }
+  // ---- phase C: outputs (eager) ----
+  rc = emit_outputs(ctx, sh0, in, out, H, n_nodes);
   if (rc) return rc;
-  for (size_t i = 0; i < ctx->shards.size(); ++i) {
-    rc = run_shard_back(ctx, ctx->shards[i], in, out, H, n_nodes, i == 0);
-    if (rc) return rc;
+  for (size_t i = 1; i < ctx->shards.size(); ++i) {
+    CU(cudaSetDevice(ctx->shards[i].device));
+    CU(cudaEventRecord(ctx->shards[i].ev[EV_END], ctx->shards[i].s_main));
   }
   for (Shard& s : ctx->shards) {
     CU(cudaSetDevice(s.device));
@@ -937,8 +1115,18 @@ int mdeggs_run_omic(mdeggs_ctx* ctx, const mdeggs_problem* in, mdeggs_result* ou
     CU(cudaStreamSynchronize(s.s_main));
   }
   CU(cudaSetDevice(src_device));
-  // ---- stats ----
   Shard& s0 = ctx->shards[0];
+  {
+    long long host_scal[2] = {0, 0};
+    CU(cudaMemcpy(host_scal, s0.scal.p, 16, cudaMemcpyDeviceToHost));
+    if ((int32_t)host_scal[SC_ERR] != 0) {
+      set_err(ctx, "from/to contain an index outside 1..G");
+      return MDEGGS_EINVAL;
+    }
+    n_nodes = (int32_t)host_scal[SC_NNODES];
+  }
+  // ---- stats ----
+  (void)replayed;
   mdeggs_stats& st = ctx->stats;
   st.n_nodes = n_nodes;
   st.unique_fits = in->E;
@@ -956,9 +1144,33 @@ int mdeggs_run_omic(mdeggs_ctx* ctx, const mdeggs_problem* in, mdeggs_result* ou
   st.ms_percolate = ev_ms(s0.ev[EV_COLL], s0.ev[EV_PERC]);
   st.ms_adjust = ev_ms(s0.ev[EV_PERC], s0.ev[EV_ADJ]);
   st.ms_d2h = ev_ms(s0.ev[EV_ADJ], s0.ev[EV_END]);
+  if (replayed) {  // graph replay: no stage boundaries inside the graph; everything between H2D and D2H is compute
+    st.ms_gather = st.ms_stats = st.ms_quantile = st.ms_fit = st.ms_tail = st.ms_collective = st.ms_percolate = 0.f;
+    st.ms_adjust = 0.f;
+    st.fit_path |= 0x100;  // bit 8 flags "replayed from a CUDA graph"
+  }
   if (out->tot_edges && in->mem == MDEGGS_MEM_HOST)
     for (int p = 0; p < in->P; ++p) st.ref_equiv_tests += out->tot_edges[p];
   return MDEGGS_OK;
+}
+
+int mdeggs_set_option(mdeggs_ctx* ctx, const char* name, int64_t value) {
+  if (!ctx || !name) return MDEGGS_EINVAL;
+  if (!strcmp(name, "graph")) {
+    ctx->use_graph = (int)value;
+    if (!value && ctx->graph_exec) {
+      cudaGraphExecDestroy(ctx->graph_exec);
+      ctx->graph_exec = nullptr;
+    }
+    ctx->key_valid = false;
+    return MDEGGS_OK;
+  }
+  if (!strcmp(name, "fit_path")) {
+    ctx->fit_path_override = (int)value;
+    ctx->key_valid = false;
+    return MDEGGS_OK;
+  }
+  return MDEGGS_EINVAL;
 }
 
 int mdeggs_last_stats(const mdeggs_ctx* ctx, mdeggs_stats* out) {

@@ -286,6 +286,150 @@ __global__ void __launch_bounds__(THREADS) k_gene_stats(double* __restrict__ D, 
   if (threadIdx.x == 0) bad[node] = (uint8_t)s_bad;
 }
 
+// Register-resident variant of K2 for segments of up to 32*ITEMS samples: one warp per (gene, category), the
+// segment lives in registers as sortable keys, so every counting pass of the selection is ITEMS compares per lane
+// with no shared-memory traffic.  `bad` must be zero-initialised by the caller.
+template <int ITEMS>
+__device__ __forceinline__ unsigned long long warp_select_reg(const unsigned long long (&keys)[ITEMS], int kth,
+                                                              unsigned long long kmin, unsigned long long kmax,
+                                                              int n_valid, unsigned long long* scratch32, int lane) {
+  if (kmin == kmax) return kmin;
+  const int top = 63 - __clzll((long long)(kmin ^ kmax));
+  unsigned long long prefix = (top == 63) ? 0ull : (kmin >> (top + 1)) << (top + 1);
+  int cnt_lo = 0, cnt_hi = n_valid;
+  int bit = top;
+  for (; bit >= 0 && cnt_hi - cnt_lo > 32; --bit) {
+    const unsigned long long cand = prefix | (1ull << bit);
+    int c = 0;
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) c += (keys[j] < cand);
+    c = __reduce_add_sync(0xffffffffu, c);
+    if (c <= kth) {
+      prefix = cand;
+      cnt_lo = c;
+    } else {
+      cnt_hi = c;
+    }
+  }
+  if (bit < 0) return prefix;
+  const unsigned long long span = (bit == 63) ? ~0ull : ((1ull << (bit + 1)) - 1ull);
+  const unsigned long long hi_incl = prefix | span;
+  int base = 0;
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j) {
+    const unsigned long long k = keys[j];
+    const bool in = k >= prefix && k <= hi_incl && k != ~0ull;
+    const unsigned mask = __ballot_sync(0xffffffffu, in);
+    if (in) scratch32[base + __popc(mask & ((1u << lane) - 1u))] = k;
+    base += __popc(mask);
+  }
+  __syncwarp();
+  const int ncand = cnt_hi - cnt_lo;
+  unsigned long long mine = lane < ncand ? scratch32[lane] : ~0ull;
+  int r = 0;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    unsigned long long other = __shfl_sync(0xffffffffu, mine, j);
+    r += (other < mine) || (other == mine && j < lane);
+  }
+  unsigned hit = __ballot_sync(0xffffffffu, lane < ncand && r == kth - cnt_lo);
+  unsigned long long res = __shfl_sync(0xffffffffu, mine, __ffs(hit) - 1);
+  __syncwarp();
+  return res;
+}
+
+template <int ITEMS>
+__global__ void __launch_bounds__(256) k_gene_stats_reg(double* __restrict__ D, SegLayout L,
+                                                        const int32_t* __restrict__ n_nodes_p,
+                                                        double* __restrict__ mean, double* __restrict__ sxx,
+                                                        double* __restrict__ med, uint8_t* __restrict__ bad) {
+  __shared__ unsigned long long s_cand[8][32];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const long long w = (long long)blockIdx.x * 8 + wib;
+  const int node = (int)(w / L.K), k = (int)(w % L.K);
+  if (node >= *n_nodes_p) return;
+  double* grow = D + (size_t)node * L.npad;
+  const double* seg = grow + L.off[k];
+  const int m = L.cnt[k];
+  unsigned long long keys[ITEMS];
+  double s = 0.0, vmin = INFINITY, vmax = -INFINITY;
+  int nn = 0, nf = 0;
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j) {
+    const int i = lane + 32 * j;
+    const bool valid = i < m;
+    const double v = valid ? seg[i] : nan("");
+    keys[j] = dkey(v);  // out-of-range slots carry the NaN key: never counted, never selected
+    if (valid) {
+      s += v;
+      vmin = fmin(vmin, v);
+      vmax = fmax(vmax, v);
+      nn += !isnan(v);
+      nf |= !isfinite(v);
+    }
+  }
+  s = warp_sum(s);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    vmin = fmin(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+    vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+  }
+  nn = __reduce_add_sync(0xffffffffu, nn);
+  nf = __reduce_or_sync(0xffffffffu, nf);
+  double mu = m > 0 ? s / (double)m : nan("");
+  double d1 = 0.0, d2 = 0.0;
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j) {
+    if (lane + 32 * j < m) {
+      double d = dkey_inv(keys[j]) - mu;  // (-0.0 was canonicalised to +0.0 by dkey: same value)
+      d1 += d;
+      d2 = fma(d, d, d2);
+    }
+  }
+  d1 = warp_sum(d1);
+  d2 = warp_sum(d2);
+  if (m > 0) {
+    double c = d1 / (double)m;
+    mu += c;
+    d2 -= d1 * c;
+  }
+  if (m > 0 && vmin == vmax) {
+    mu = vmin;
+    d2 = 0.0;
+  }
+  double median = nan("");
+  if (nn > 0) {
+    const unsigned long long kmin = dkey(vmin), kmax = dkey(vmax);
+    if (nn & 1) {
+      median = dkey_inv(warp_select_reg<ITEMS>(keys, nn / 2, kmin, kmax, nn, s_cand[wib], lane));
+    } else {
+      unsigned long long k1 = warp_select_reg<ITEMS>(keys, nn / 2 - 1, kmin, kmax, nn, s_cand[wib], lane);
+      int c_le = 0;
+      unsigned long long nxt = ~0ull;
+#pragma unroll
+      for (int j = 0; j < ITEMS; ++j) {
+        c_le += (keys[j] <= k1);
+        if (keys[j] > k1 && keys[j] < nxt) nxt = keys[j];
+      }
+      c_le = __reduce_add_sync(0xffffffffu, c_le);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long other = __shfl_xor_sync(0xffffffffu, nxt, o);
+        nxt = other < nxt ? other : nxt;
+      }
+      unsigned long long k2 = (c_le > nn / 2) ? k1 : nxt;
+      median = __ddiv_rn(__dadd_rn(dkey_inv(k1), dkey_inv(k2)), 2.0);
+    }
+  }
+  if (lane == 0) {
+    mean[(size_t)node * L.K + k] = mu;
+    sxx[(size_t)node * L.K + k] = d2;
+    med[(size_t)node * L.K + k] = median;
+    if (nf) bad[node] = 1;
+  }
+  for (int i = L.off[k] + m + lane; i < L.off[k + 1]; i += 32) grow[i] = mu;  // padding := segment mean
+}
+
 // ------------------------------------------------------------------------------------------------
 // K4 / K5: streaming pair fit, one warp per edge
 //   K == 2 : fit_lm_interaction  (core_functions.R:1058-1074)  -> t statistic of the A:category coefficient
@@ -367,7 +511,8 @@ __global__ void __launch_bounds__(256) k_fit_stream(const double* __restrict__ D
                                                     const double* __restrict__ sxx,
                                                     const uint8_t* __restrict__ bad, int64_t e_lo, int64_t e_hi,
                                                     double* __restrict__ stat, int32_t* __restrict__ status,
-                                                    double* __restrict__ coef) {
+                                                    double* __restrict__ coef, const int32_t* __restrict__ err) {
+  if (*err) return;  // an edge index was out of range: nothing below may touch from/to
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -457,8 +602,9 @@ __global__ void __launch_bounds__(256) k_percolate(const int32_t* __restrict__ f
                                                    unsigned long long* __restrict__ tot,
                                                    unsigned long long* __restrict__ fail,
                                                    unsigned long long* __restrict__ sig_raw,
-                                                   int8_t* __restrict__ cat_out) {
+                                                   int8_t* __restrict__ cat_out, const int32_t* __restrict__ err) {
   extern __shared__ unsigned int s_cnt[];  // [3][P]
+  if (*err) return;
   for (int i = threadIdx.x; i < 3 * P; i += blockDim.x) s_cnt[i] = 0;
   __syncthreads();
   int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -497,9 +643,10 @@ __global__ void __launch_bounds__(256) k_percolate(const int32_t* __restrict__ f
 // cat row of one percentile chosen on the device (best)
 __global__ void k_cat_row(const int32_t* __restrict__ from, const int32_t* __restrict__ to,
                           const int32_t* __restrict__ node_of_row, const uint8_t* __restrict__ act, int act_stride,
-                          int64_t E, const int32_t* __restrict__ best, int8_t* __restrict__ cat_out) {
+                          int64_t E, const int32_t* __restrict__ best, int8_t* __restrict__ cat_out,
+                          const int32_t* __restrict__ err) {
   int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= E) return;
+  if (e >= E || *err) return;
   int p = *best - 1;
   int c = 0;
   if (p >= 0) {
@@ -507,6 +654,27 @@ __global__ void k_cat_row(const int32_t* __restrict__ from, const int32_t* __res
     c = edge_category(act[(size_t)p * act_stride + a], act[(size_t)p * act_stride + b]);
   }
   cat_out[e] = (int8_t)c;
+}
+
+// rows of the device-chosen best percentile: category row (recomputed from the masks) and, when the adjusted
+// values of every percentile are still in the scratch matrix, its p.adj row (else a BH pass is rerun for it)
+__global__ void k_best_rows(const int32_t* __restrict__ from, const int32_t* __restrict__ to,
+                            const int32_t* __restrict__ node_of_row, const uint8_t* __restrict__ act, int act_stride,
+                            int64_t E, const int32_t* __restrict__ best, int8_t* __restrict__ cat_out,
+                            const double* __restrict__ padj_all, double* __restrict__ padj_best,
+                            const int32_t* __restrict__ err) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E || *err) return;
+  const int p = *best - 1;
+  if (cat_out) {
+    int c = 0;
+    if (p >= 0) {
+      int a = node_of_row[from[e] - 1], b = node_of_row[to[e] - 1];
+      c = edge_category(act[(size_t)p * act_stride + a], act[(size_t)p * act_stride + b]);
+    }
+    cat_out[e] = (int8_t)c;
+  }
+  if (padj_best) padj_best[e] = (p >= 0 && padj_all) ? padj_all[(size_t)p * E + e] : nan("");
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -534,10 +702,10 @@ __global__ void k_gather_sorted(const unsigned long long* __restrict__ keys_sort
                                 const int32_t* __restrict__ idx_sorted, const int32_t* __restrict__ from,
                                 const int32_t* __restrict__ to, const int32_t* __restrict__ node_of_row, int64_t E,
                                 double* __restrict__ ps, int32_t* __restrict__ sa, int32_t* __restrict__ sb,
-                                unsigned long long* __restrict__ n_valid) {
+                                unsigned long long* __restrict__ n_valid, const int32_t* __restrict__ err) {
   int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   bool valid = false;
-  if (j < E) {
+  if (j < E && !*err) {
     unsigned long long k = keys_sorted[j];
     int32_t e = idx_sorted[j];
     valid = (k != ~0ull);

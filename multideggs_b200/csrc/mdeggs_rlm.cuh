@@ -71,8 +71,9 @@ __global__ void __launch_bounds__(256) k_fit_rlm(const double* __restrict__ D, S
                                                  const uint8_t* __restrict__ bad, int64_t e_lo, int64_t e_hi,
                                                  int tested_coef, int cov_mode, double* __restrict__ stat,
                                                  int32_t* __restrict__ status, double* __restrict__ coef,
-                                                 int32_t* __restrict__ iters) {
+                                                 int32_t* __restrict__ iters, const int32_t* __restrict__ err) {
   extern __shared__ double smem[];
+  if (*err) return;
   __shared__ unsigned long long s_cand[8][32];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   const int per_warp = CACHE_AB ? 3 * L.npad : L.npad;
@@ -268,7 +269,7 @@ __global__ void __launch_bounds__(256) k_fit_rlm(const double* __restrict__ D, S
 inline int launch_fit_rlm(int64_t& launches, cudaStream_t stream, const double* D, const SegLayout& L,
                           const int32_t* from, const int32_t* to, const int32_t* node_of_row, const double* mean,
                           const double* sxx, const uint8_t* bad, int64_t e_lo, int64_t e_hi, int tested_coef,
-                          int cov_mode, double* stat, int32_t* status, double* coef, int32_t* iters) {
+                          int cov_mode, double* stat, int32_t* status, double* coef, int32_t* iters, const int32_t* err) {
   const size_t budget = 200 * 1024;
   const size_t row = (size_t)L.npad * 8;
   bool cache = 3 * row * 2 <= budget;  // at least two warps per CTA with A, B, r resident
@@ -284,12 +285,12 @@ inline int launch_fit_rlm(int64_t& launches, cudaStream_t stream, const double* 
     if (smem > 48 * 1024)
       cudaFuncSetAttribute(k_fit_rlm<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
     k_fit_rlm<true><<<grid, wpb * 32, smem, stream>>>(D, L, from, to, node_of_row, mean, sxx, bad, e_lo, e_hi,
-                                                     tested_coef, cov_mode, stat, status, coef, iters);
+                                                     tested_coef, cov_mode, stat, status, coef, iters, err);
   } else {
     if (smem > 48 * 1024)
       cudaFuncSetAttribute(k_fit_rlm<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
     k_fit_rlm<false><<<grid, wpb * 32, smem, stream>>>(D, L, from, to, node_of_row, mean, sxx, bad, e_lo, e_hi,
-                                                      tested_coef, cov_mode, stat, status, coef, iters);
+                                                      tested_coef, cov_mode, stat, status, coef, iters, err);
   }
   ++launches;
   return 0;

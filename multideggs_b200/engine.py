@@ -21,7 +21,7 @@ _LIB: C.CDLL | None = None
 # every symbol include/mdeggs.h declares (tests check the library exports all of them)
 ABI_SYMBOLS = (
     "mdeggs_create", "mdeggs_create_rank", "mdeggs_nccl_unique_id", "mdeggs_destroy", "mdeggs_run_omic",
-    "mdeggs_pair_features", "mdeggs_last_stats", "mdeggs_last_error", "mdeggs_strerror", "mdeggs_abi_version",
+    "mdeggs_pair_features", "mdeggs_last_stats", "mdeggs_set_option", "mdeggs_last_error", "mdeggs_strerror", "mdeggs_abi_version",
     "mdeggs_dev_pt", "mdeggs_dev_pf_upper", "mdeggs_dev_p_two_sided_ref",
 )
 
@@ -47,6 +47,7 @@ def load_library() -> C.CDLL:
     L.mdeggs_run_omic.argtypes = [vp, C.POINTER(_abi.CProblem), C.POINTER(_abi.CResult)]
     L.mdeggs_pair_features.argtypes = [vp, vp, i64, C.c_int32, vp, vp, C.c_int32, C.c_int32, C.c_int32, vp]
     L.mdeggs_last_stats.argtypes = [vp, C.POINTER(_abi.CStats)]
+    L.mdeggs_set_option.argtypes = [vp, C.c_char_p, i64]
     L.mdeggs_last_error.argtypes = [vp]
     L.mdeggs_last_error.restype = C.c_char_p
     L.mdeggs_strerror.argtypes = [i]
@@ -128,6 +129,10 @@ class Engine:
     def run_omic_raw(self, cprob: _abi.CProblem, cres: _abi.CResult) -> None:
         """Pre-marshalled structs (device or pinned-host pointers); used by bench.py."""
         self._check(self._lib.mdeggs_run_omic(self._ctx, C.byref(cprob), C.byref(cres)), "mdeggs_run_omic")
+
+    def set_option(self, name: str, value: int) -> None:
+        """"graph": 1/0 CUDA-graph replay of repeated identical calls; "fit_path": -1 auto, 0 streaming, 1 dense."""
+        self._check(self._lib.mdeggs_set_option(self._ctx, name.encode(), int(value)), "mdeggs_set_option")
 
     def stats(self) -> dict:
         st = _abi.CStats()

@@ -265,3 +265,35 @@ def test_node_band_copy_and_leading_dimension(engine, oracle):
     engine.run_omic_raw(cprob, cres)
     for k in gpu:
         assert np.array_equal(gpu[k], arrays[k], equal_nan=True), k
+
+
+def test_graph_replay_is_bit_identical(oracle):
+    """Third identical raw call is replayed from the captured CUDA graph: same bytes out, new inputs honoured."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    eng = md.Engine([0])
+    prob = synth.random_problem(90, 70, 400, 3, 601)
+    cprob = prob.to_c()
+    cres, arr = _abi.alloc_result(prob.dims, ALL_FIELDS)
+    eng.run_omic_raw(cprob, cres)
+    first = {k: v.copy() for k, v in arr.items()}
+    assert not (eng.stats()["fit_path"] & 0x100)
+    for _ in range(3):
+        eng.run_omic_raw(cprob, cres)
+    assert eng.stats()["fit_path"] & 0x100, "graph replay did not engage"
+    for k in first:
+        assert np.array_equal(first[k], arr[k], equal_nan=True), k
+    # same buffers, new CONTENT (values and percentiles): the replay must see it
+    prob.assay[...] = np.asfortranarray(synth.random_problem(90, 70, 400, 3, 602).assay)
+    prob._keep[4][...] = _abi.r_seq(0.25, 0.98, 0.06)[: len(prob.pct)]
+    prob2 = _abi.Problem(assay=prob.assay.copy(order="F"), from_idx=prob.from_idx, to_idx=prob.to_idx, group=prob.group,
+                         K=3, pct=prob._keep[4].copy(), padj=prob.padj)
+    eng.run_omic_raw(cprob, cres)
+    assert eng.stats()["fit_path"] & 0x100
+    ref = oracle.run_omic(prob2, ALL_FIELDS)
+    assert_parity(arr, ref, prob2, what="graph replay, new content: ")
+    eng.set_option("graph", 0)
+    eng.run_omic_raw(cprob, cres)
+    assert not (eng.stats()["fit_path"] & 0x100)
+    eng.close()
