@@ -7,8 +7,8 @@
 // times (config 5: 256 GB of L1/L2 traffic).  Here a CTA stages a 128-gene x 8-sample tile of two row blocks
 // in shared memory (centred on the fly) and accumulates the 128x128 block of cross moments in registers
 // (8x8 per thread, plain FP64 FMAs — no tensor cores), so each row is read nn/128 times instead of ~nn times.
-// Only tile pairs with ti <= tj are computed (Sxy is symmetric); k_fit_dense_edges then finishes each edge
-// from Sxy[min(a,b)][max(a,b)] with the same closed forms as the streaming kernel (finish_pair).
+// Only tile pairs with ti <= tj are computed (Sxy is symmetric); k_finish (src 1) then finishes each edge
+// from Sxy[min(a,b)][max(a,b)] with the same closed forms as the streaming path (finish_pair).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -123,36 +123,6 @@ __global__ void __launch_bounds__(256, 1) k_dense_moments(const double* __restri
       }
     }
   }
-}
-
-// one thread per edge: gather the K cross moments of the pair and finish with the shared closed forms
-template <int K>
-__global__ void __launch_bounds__(256) k_fit_dense_edges(const double* __restrict__ S, SegLayout L, int nn,
-                                                         const int32_t* __restrict__ from,
-                                                         const int32_t* __restrict__ to,
-                                                         const int32_t* __restrict__ node_of_row,
-                                                         const double* __restrict__ mean,
-                                                         const double* __restrict__ sxx,
-                                                         const uint8_t* __restrict__ bad, int64_t e_lo, int64_t e_hi,
-                                                         double* __restrict__ stat, int32_t* __restrict__ status,
-                                                         double* __restrict__ coef, const int32_t* __restrict__ err) {
-  const int64_t e = e_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= e_hi || *err) return;
-  const int ra = from[e] - 1, rb = to[e] - 1;
-  const int a = node_of_row[ra], b = node_of_row[rb];
-  if (ra == rb || bad[a] || bad[b]) {
-    bool self = (ra == rb) && !bad[a];
-    stat[e] = self ? 0.0 : nan("");
-    status[e] = self ? MDEGGS_EDGE_SELFLOOP : MDEGGS_EDGE_NONFINITE;
-    if (coef)
-      for (int j = 0; j < 2 * K; ++j) coef[(size_t)e * 2 * K + j] = nan("");
-    return;
-  }
-  const int i = a < b ? a : b, j = a < b ? b : a;
-  PairMoments<K> pm;
-#pragma unroll
-  for (int k = 0; k < K; ++k) pm.sxy[k] = L.cnt[k] ? __ldg(S + ((size_t)k * nn + i) * nn + j) : 0.0;
-  finish_pair<K>(L, mean, sxx, a, b, pm, stat + e, status + e, coef ? coef + (size_t)e * 2 * K : nullptr);
 }
 
 // dense path pays off when the edge list is a sizeable fraction of all node pairs:

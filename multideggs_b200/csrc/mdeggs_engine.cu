@@ -82,13 +82,13 @@ struct Shard {
   DevBuf assay, from, to, flags, excl, node_of_row, rowlist, scal, src_of_pos, pct, cutoff, D, keys, keys_sorted,
       cub_tmp, cub_tmp2, mean, sxx, med, bad, stat, status, p_edge, coef, iters, act, counters, sortk, sortk2, idx,
       idx2, ps, sa, sb, tile_cnt, tile_base, seg_n, tile_min, tile_carry, padj_best, cat_best, cat, padj, med_out,
-      small_out, rlm_ws, rsel_hist, rsel_state, rsel_cand, dense_S, cf_tab;
+      small_out, rlm_ws, rsel_hist, rsel_state, rsel_cand, dense_S, cf_tab, sxy;
   void release_all() {
     DevBuf* all[] = {&assay, &from, &to, &flags, &excl, &node_of_row, &rowlist, &scal, &src_of_pos, &pct, &cutoff,
                      &D, &keys, &keys_sorted, &cub_tmp, &cub_tmp2, &mean, &sxx, &med, &bad, &stat, &status, &p_edge,
                      &coef, &iters, &act, &counters, &sortk, &sortk2, &idx, &idx2, &ps, &sa, &sb, &tile_cnt,
                      &tile_base, &seg_n, &tile_min, &tile_carry, &padj_best, &cat_best, &cat, &padj, &med_out,
-                     &small_out, &rlm_ws, &rsel_hist, &rsel_state, &rsel_cand, &dense_S, &cf_tab};
+                     &small_out, &rlm_ws, &rsel_hist, &rsel_state, &rsel_cand, &dense_S, &cf_tab, &sxy};
     for (DevBuf* b : all) b->release();
   }
 };
@@ -214,24 +214,24 @@ int build_layout(mdeggs_ctx* ctx, const mdeggs_problem* in, HostLayout& H) {
 }
 
 template <int K>
-void launch_fit_dense_edges(mdeggs_ctx* ctx, Shard& s, const SegLayout& L, int nn, int64_t e_lo, int64_t e_hi,
-                            double* coef) {
-  LAUNCH(k_fit_dense_edges<K>, blocks_for(e_hi - e_lo, 256), 256, 0, s.s_main, s.dense_S.as<double>(), L, nn,
-         s.from.as<int32_t>(), s.to.as<int32_t>(), s.node_of_row.as<int32_t>(), s.mean.as<double>(),
-         s.sxx.as<double>(), s.bad.as<uint8_t>(), e_lo, e_hi, s.stat.as<double>(), s.status.as<int32_t>(), coef,
+void launch_fit_stream(mdeggs_ctx* ctx, Shard& s, const SegLayout& L, int64_t e_lo, int64_t e_hi) {
+  int64_t ne = e_hi - e_lo;
+  if (ne <= 0) return;
+  int64_t want_blocks = (ne + 7) / 8;  // 8 warps per CTA, one edge per warp per trip
+  int64_t cap = 148 * 8 * 16;          // at most 16 waves of 8 CTAs/SM; warps loop beyond that
+  unsigned grid = (unsigned)(want_blocks < cap ? want_blocks : cap);
+  LAUNCH(k_fit_stream<K>, grid, 256, 0, s.s_main, s.D.as<double>(), L, s.from.as<int32_t>(), s.to.as<int32_t>(),
+         s.node_of_row.as<int32_t>(), s.mean.as<double>(), s.bad.as<uint8_t>(), e_lo, e_hi, s.sxy.as<double>(),
          s.scal.as<int32_t>() + 2 * SC_ERR);
 }
 
 template <int K>
-void launch_fit_stream(mdeggs_ctx* ctx, Shard& s, const SegLayout& L, int64_t e_lo, int64_t e_hi, double* coef) {
-  int64_t ne = e_hi - e_lo;
-  if (ne <= 0) return;
-  int64_t want_blocks = (ne + 7) / 8;  // 8 warps per CTA, one edge per warp per trip
-  int64_t cap = 148 * 8 * 16;          // persistent-ish: at most 16 waves of 8 CTAs/SM, warps loop
-  unsigned grid = (unsigned)(want_blocks < cap ? want_blocks : cap);
-  LAUNCH(k_fit_stream<K>, grid, 256, 0, s.s_main, s.D.as<double>(), L, s.from.as<int32_t>(), s.to.as<int32_t>(),
-         s.node_of_row.as<int32_t>(), s.mean.as<double>(), s.sxx.as<double>(), s.bad.as<uint8_t>(), e_lo, e_hi,
-         s.stat.as<double>(), s.status.as<int32_t>(), coef, s.scal.as<int32_t>() + 2 * SC_ERR);
+void launch_finish(mdeggs_ctx* ctx, Shard& s, const SegLayout& L, int src, int nn, int64_t e_lo, int64_t e_hi, int mode,
+                   double df1, double df2, const TailConsts& tc, const double* d_lbeta, double* coef) {
+  LAUNCH(k_finish<K>, blocks_for(e_hi - e_lo, 128), 128, 0, s.s_main, src, s.sxy.as<double>(), s.dense_S.as<double>(),
+         nn, L, s.from.as<int32_t>(), s.to.as<int32_t>(), s.node_of_row.as<int32_t>(), s.mean.as<double>(),
+         s.sxx.as<double>(), s.bad.as<uint8_t>(), e_lo, e_hi, mode, df1, df2, tc, d_lbeta, s.stat.as<double>(),
+         s.status.as<int32_t>(), coef, s.p_edge.as<double>(), s.scal.as<int32_t>() + 2 * SC_ERR);
 }
 
 int copy_out(mdeggs_ctx* ctx, Shard& s, void* dst, const void* src, size_t bytes, int mem) {
@@ -482,6 +482,17 @@ int run_shard_main(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
   }
   EVREC(s.ev[EV_Q1], s.s_sort);
   CU(cudaEventRecord(s.ev_join, s.s_sort));
+  // ---- per-run tail tables (depend only on the degrees of freedom) ----
+  {
+    const bool rlm2 = (K == 2 && in->method == MDEGGS_METHOD_RLM);
+    int Ke = 0;
+    for (int k = 0; k < K; ++k) Ke += L.cnt[k] > 0;
+    const double tdf1 = K == 2 ? 1.0 : (double)(Ke - 1), tdf2 = K == 2 ? (double)(n - 4) : (double)(n - 2 * Ke);
+    const double ta = (K == 2 && !rlm2) ? 0.5 : tdf1 / 2.0;
+    CU(s.cf_tab.ensure((size_t)(2 * CF_TABLE_LEN + 1) * 8));
+    LAUNCH(k_cf_tables, 1, 256, 0, s.s_main, ta, tdf2 / 2.0, s.cf_tab.as<double>(), s.cf_tab.as<double>() + CF_TABLE_LEN,
+           s.cf_tab.as<double>() + 2 * CF_TABLE_LEN);
+  }
   // ---- K2 gene stats ----
   if (n_nodes > 0) {
     int max_cnt = 0;
@@ -521,6 +532,7 @@ int run_shard_main(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
   CU(s.p_edge.ensure(epad * 8));
   if (want_coef) CU(s.coef.ensure(epad * 2 * K * 8));
   if (is_rlm) CU(s.iters.ensure(epad * 4));
+  if (!is_rlm) CU(s.sxy.ensure(epad * K * 8));
   double* d_coef = want_coef ? s.coef.as<double>() : nullptr;
   bool use_dense = false;
   if (!is_rlm && ctx->fit_path_override != 0) {
@@ -554,24 +566,15 @@ int run_shard_main(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
       dim3 grid((unsigned)(ntl * (ntl + 1) / 2), (unsigned)K);
       LAUNCH(k_dense_moments, grid, 256, 0, s.s_main, s.D.as<double>(), L, s.mean.as<double>(), (int)n_nodes, ntl,
              s.dense_S.as<double>());
-      switch (K) {
-        case 2: launch_fit_dense_edges<2>(ctx, s, L, n_nodes, e_lo, e_hi, d_coef); break;
-        case 3: launch_fit_dense_edges<3>(ctx, s, L, n_nodes, e_lo, e_hi, d_coef); break;
-        case 4: launch_fit_dense_edges<4>(ctx, s, L, n_nodes, e_lo, e_hi, d_coef); break;
-        case 5: launch_fit_dense_edges<5>(ctx, s, L, n_nodes, e_lo, e_hi, d_coef); break;
-        case 6: launch_fit_dense_edges<6>(ctx, s, L, n_nodes, e_lo, e_hi, d_coef); break;
-        case 7: launch_fit_dense_edges<7>(ctx, s, L, n_nodes, e_lo, e_hi, d_coef); break;
-        default: launch_fit_dense_edges<8>(ctx, s, L, n_nodes, e_lo, e_hi, d_coef); break;
-      }
     } else {
       switch (K) {
-        case 2: launch_fit_stream<2>(ctx, s, L, e_lo, e_hi, d_coef); break;
-        case 3: launch_fit_stream<3>(ctx, s, L, e_lo, e_hi, d_coef); break;
-        case 4: launch_fit_stream<4>(ctx, s, L, e_lo, e_hi, d_coef); break;
-        case 5: launch_fit_stream<5>(ctx, s, L, e_lo, e_hi, d_coef); break;
-        case 6: launch_fit_stream<6>(ctx, s, L, e_lo, e_hi, d_coef); break;
-        case 7: launch_fit_stream<7>(ctx, s, L, e_lo, e_hi, d_coef); break;
-        default: launch_fit_stream<8>(ctx, s, L, e_lo, e_hi, d_coef); break;
+        case 2: launch_fit_stream<2>(ctx, s, L, e_lo, e_hi); break;
+        case 3: launch_fit_stream<3>(ctx, s, L, e_lo, e_hi); break;
+        case 4: launch_fit_stream<4>(ctx, s, L, e_lo, e_hi); break;
+        case 5: launch_fit_stream<5>(ctx, s, L, e_lo, e_hi); break;
+        case 6: launch_fit_stream<6>(ctx, s, L, e_lo, e_hi); break;
+        case 7: launch_fit_stream<7>(ctx, s, L, e_lo, e_hi); break;
+        default: launch_fit_stream<8>(ctx, s, L, e_lo, e_hi); break;
       }
     }
   }
@@ -598,10 +601,16 @@ int run_shard_main(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
     tc.e_ab = s.cf_tab.as<double>();
     tc.e_ba = s.cf_tab.as<double>() + CF_TABLE_LEN;
     const double* d_lbeta = s.cf_tab.as<double>() + 2 * CF_TABLE_LEN;
-    LAUNCH(k_cf_tables, 1, 256, 0, s.s_main, tc.a, tc.b, s.cf_tab.as<double>(), s.cf_tab.as<double>() + CF_TABLE_LEN,
-           s.cf_tab.as<double>() + 2 * CF_TABLE_LEN);
-    LAUNCH(k_tail, blocks_for(e_hi - e_lo, 128), 128, 0, s.s_main, s.stat.as<double>(), s.status.as<int32_t>(), e_lo,
-           e_hi, tail_mode, df1, df2, tc, d_lbeta, s.p_edge.as<double>());
+    const int src = is_rlm ? 2 : (use_dense ? 1 : 0);
+    switch (K) {
+      case 2: launch_finish<2>(ctx, s, L, src, n_nodes, e_lo, e_hi, tail_mode, df1, df2, tc, d_lbeta, d_coef); break;
+      case 3: launch_finish<3>(ctx, s, L, src, n_nodes, e_lo, e_hi, tail_mode, df1, df2, tc, d_lbeta, d_coef); break;
+      case 4: launch_finish<4>(ctx, s, L, src, n_nodes, e_lo, e_hi, tail_mode, df1, df2, tc, d_lbeta, d_coef); break;
+      case 5: launch_finish<5>(ctx, s, L, src, n_nodes, e_lo, e_hi, tail_mode, df1, df2, tc, d_lbeta, d_coef); break;
+      case 6: launch_finish<6>(ctx, s, L, src, n_nodes, e_lo, e_hi, tail_mode, df1, df2, tc, d_lbeta, d_coef); break;
+      case 7: launch_finish<7>(ctx, s, L, src, n_nodes, e_lo, e_hi, tail_mode, df1, df2, tc, d_lbeta, d_coef); break;
+      default: launch_finish<8>(ctx, s, L, src, n_nodes, e_lo, e_hi, tail_mode, df1, df2, tc, d_lbeta, d_coef); break;
+    }
   }
   EVREC(s.ev[EV_TAIL], s.s_main);
   return MDEGGS_OK;

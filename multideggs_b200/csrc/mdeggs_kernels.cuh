@@ -502,16 +502,17 @@ __device__ __forceinline__ void finish_pair(const SegLayout& L, const double* __
   }
 }
 
+// The streaming kernel only produces the K centred cross moments of each edge (sxy[e*K + k]); the closed forms
+// (divisions, sqrt) and the tail probability are done one THREAD per edge by k_finish, so no warp ever idles 31
+// lanes behind a scalar epilogue.
 template <int K>
-__global__ void __launch_bounds__(256) k_fit_stream(const double* __restrict__ D, SegLayout L,
-                                                    const int32_t* __restrict__ from,
-                                                    const int32_t* __restrict__ to,
-                                                    const int32_t* __restrict__ node_of_row,
-                                                    const double* __restrict__ mean,
-                                                    const double* __restrict__ sxx,
-                                                    const uint8_t* __restrict__ bad, int64_t e_lo, int64_t e_hi,
-                                                    double* __restrict__ stat, int32_t* __restrict__ status,
-                                                    double* __restrict__ coef, const int32_t* __restrict__ err) {
+__global__ void __launch_bounds__(256, 4) k_fit_stream(const double* __restrict__ D, SegLayout L,
+                                                       const int32_t* __restrict__ from,
+                                                       const int32_t* __restrict__ to,
+                                                       const int32_t* __restrict__ node_of_row,
+                                                       const double* __restrict__ mean,
+                                                       const uint8_t* __restrict__ bad, int64_t e_lo, int64_t e_hi,
+                                                       double* __restrict__ sxy, const int32_t* __restrict__ err) {
   if (*err) return;  // an edge index was out of range: nothing below may touch from/to
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -519,19 +520,10 @@ __global__ void __launch_bounds__(256) k_fit_stream(const double* __restrict__ D
   for (int64_t e = e_lo + warp0; e < e_hi; e += nwarps) {
     const int ra = from[e] - 1, rb = to[e] - 1;
     const int a = node_of_row[ra], b = node_of_row[rb];
-    if (ra == rb || bad[a] || bad[b]) {
-      if (lane == 0) {
-        bool self = (ra == rb) && !bad[a];
-        stat[e] = self ? 0.0 : nan("");
-        status[e] = self ? MDEGGS_EDGE_SELFLOOP : MDEGGS_EDGE_NONFINITE;
-        if (coef)
-          for (int j = 0; j < 2 * K; ++j) coef[(size_t)e * 2 * K + j] = nan("");
-      }
-      continue;
-    }
+    if (ra == rb || bad[a] || bad[b]) continue;  // k_finish classifies these edges; their moments are not read
     const double2* __restrict__ pa = reinterpret_cast<const double2*>(D + (size_t)a * L.npad);
     const double2* __restrict__ pb = reinterpret_cast<const double2*>(D + (size_t)b * L.npad);
-    PairMoments<K> pm;
+    double mine = 0.0;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
       const double ma = mean[(size_t)a * K + k], mb = mean[(size_t)b * K + k];
@@ -543,26 +535,57 @@ __global__ void __launch_bounds__(256) k_fit_stream(const double* __restrict__ D
         acc0 = fma(x.x - ma, y.x - mb, acc0);
         acc1 = fma(x.y - ma, y.y - mb, acc1);
       }
-      pm.sxy[k] = warp_sum(acc0 + acc1);
+      double tot = warp_sum(acc0 + acc1);
+      if (lane == k) mine = tot;
     }
-    if (lane == 0)
-      finish_pair<K>(L, mean, sxx, a, b, pm, stat + e, status + e, coef ? coef + (size_t)e * 2 * K : nullptr);
+    if (lane < K) sxy[(size_t)e * K + lane] = mine;
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// tail probabilities, one thread per edge
+// finish, one thread per edge: closed-form statistic from the cross moments, then the tail probability
+//   src 0: moments from k_fit_stream (sxy[e][K]);  src 1: moments from the dense matrices S[k][i][j];
+//   src 2: statistic and status already written by k_fit_rlm
 //   mode 0: 2 * (1 - pt(|t|, df2))            core_functions.R:1072
 //   mode 1: pf(F, df1, df2, lower.tail=FALSE)  core_functions.R:968 (aov) / 920 (f.robftest)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_tail(const double* __restrict__ stat, const int32_t* __restrict__ status,
-                                              int64_t e_lo, int64_t e_hi, int mode, double df1, double df2,
-                                              TailConsts tc, const double* __restrict__ lbeta_p,
-                                              double* __restrict__ p_out) {
-  int64_t e = e_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= e_hi) return;
+template <int K>
+__global__ void __launch_bounds__(128) k_finish(int src, const double* __restrict__ sxy, const double* __restrict__ S,
+                                                int nn, SegLayout L, const int32_t* __restrict__ from,
+                                                const int32_t* __restrict__ to,
+                                                const int32_t* __restrict__ node_of_row,
+                                                const double* __restrict__ mean, const double* __restrict__ sxx,
+                                                const uint8_t* __restrict__ bad, int64_t e_lo, int64_t e_hi, int mode,
+                                                double df1, double df2, TailConsts tc,
+                                                const double* __restrict__ lbeta_p, double* __restrict__ stat,
+                                                int32_t* __restrict__ status, double* __restrict__ coef,
+                                                double* __restrict__ p_out, const int32_t* __restrict__ err) {
+  const int64_t e = e_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= e_hi || *err) return;
   tc.lbeta_ab = *lbeta_p;
-  int st = status[e];
+  if (src != 2) {
+    const int ra = from[e] - 1, rb = to[e] - 1;
+    const int a = node_of_row[ra], b = node_of_row[rb];
+    if (ra == rb || bad[a] || bad[b]) {
+      const bool self = (ra == rb) && !bad[a];
+      stat[e] = self ? 0.0 : nan("");
+      status[e] = self ? MDEGGS_EDGE_SELFLOOP : MDEGGS_EDGE_NONFINITE;
+      if (coef)
+        for (int j = 0; j < 2 * K; ++j) coef[(size_t)e * 2 * K + j] = nan("");
+    } else {
+      PairMoments<K> pm;
+      if (src == 0) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) pm.sxy[k] = sxy[(size_t)e * K + k];
+      } else {
+        const int i = a < b ? a : b, j = a < b ? b : a;
+#pragma unroll
+        for (int k = 0; k < K; ++k) pm.sxy[k] = L.cnt[k] ? __ldg(S + ((size_t)k * nn + i) * nn + j) : 0.0;
+      }
+      finish_pair<K>(L, mean, sxx, a, b, pm, stat + e, status + e, coef ? coef + (size_t)e * 2 * K : nullptr);
+    }
+  }
+  const int st = status[e];
   double p;
   if (st == MDEGGS_EDGE_SINGULAR || st == MDEGGS_EDGE_NONFINITE || st == MDEGGS_EDGE_ZERO_SCALE) p = nan("");
   else if (st == MDEGGS_EDGE_SELFLOOP) p = 1.0;
