@@ -149,7 +149,8 @@ int mdeggs_pair_features(mdeggs_ctx* ctx, const double* x, int64_t ldx, int32_t 
 int mdeggs_last_stats(const mdeggs_ctx* ctx, mdeggs_stats* out);
 /* Engine options: "graph" (1 = replay the compute phase from a CUDA graph when a call repeats with identical
  * shapes and buffers [default], 0 = always launch eagerly, which also keeps the per-stage timings);
- * "fit_path" (-1 = choose streaming vs dense-tile pair fits automatically [default], 0 = streaming, 1 = dense). */
+ * "fit_path" (-1 = choose streaming vs dense-tile pair fits automatically [default], 0 = streaming, 1 = dense);
+ * "rsel_cap" (tests: cap the quantile candidate list so that the overflow path is exercised; 0 = default). */
 int mdeggs_set_option(mdeggs_ctx* ctx, const char* name, int64_t value);
 const char* mdeggs_last_error(const mdeggs_ctx* ctx);
 const char* mdeggs_strerror(int code);

@@ -120,6 +120,7 @@ struct mdeggs_ctx {
   int64_t graph_launches = 0;
   bool smem_attr_set = false;
   bool rsel_attr_set = false;
+  int64_t rsel_cap_override = 0;  // option "rsel_cap": shrink the candidate list to exercise the overflow path (tests)
   int fit_path_override = -1;  // -1 auto, 0 force streaming, 1 force dense (MDEGGS_FIT_PATH, tests)
 };
 
@@ -458,25 +459,28 @@ int run_shard_main(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
     {
       size_t total = (size_t)n_nodes * (size_t)n;
       cand.capacity = (unsigned int)(total < (size_t)(4u << 20) ? total : (size_t)(4u << 20));
+      if (ctx->rsel_cap_override > 0 && (size_t)ctx->rsel_cap_override < cand.capacity) cand.capacity = (unsigned int)ctx->rsel_cap_override;
       CU(s.rsel_cand.ensure((size_t)cand.capacity * 8));
       cand.keys = s.rsel_cand.as<unsigned long long>();
       cand.count = reinterpret_cast<unsigned int*>(s.rsel_state.as<char>() + sizeof(RselState) + 8);
     }
     const unsigned big_grid = 148 * 6, small_grid = 148;
-    for (int pass = 0; pass < RSEL_PASSES; ++pass) {
-      if (pass < 2) {
-        LAUNCH(k_rsel_pass<0>, big_grid, 256, hsmem, s.s_sort, s.D.as<double>(), s.src_of_pos.as<int32_t>(), L.npad,
-               d_nn, pass, d_st, s.rsel_hist.as<unsigned int>(), d_nan, cand);
-      } else {
-        if (pass == 2)  // 24 key bits fixed: compact the survivors once, the last read of D
-          LAUNCH(k_rsel_pass<1>, big_grid, 256, 0, s.s_sort, s.D.as<double>(), s.src_of_pos.as<int32_t>(), L.npad,
-                 d_nn, pass, d_st, s.rsel_hist.as<unsigned int>(), d_nan, cand);
-        LAUNCH(k_rsel_pass<2>, small_grid, 256, hsmem, s.s_sort, s.D.as<double>(), s.src_of_pos.as<int32_t>(), L.npad,
-               d_nn, pass, d_st, s.rsel_hist.as<unsigned int>(), d_nan, cand);
-      }
+    // two digit passes over D (24 key bits), one compaction pass, one finishing kernel
+    for (int pass = 0; pass < 2; ++pass) {
+      LAUNCH(k_rsel_pass<0>, big_grid, 256, hsmem, s.s_sort, s.D.as<double>(), s.src_of_pos.as<int32_t>(), L.npad,
+             d_nn, pass, d_st, s.rsel_hist.as<unsigned int>(), d_nan, cand);
       LAUNCH(k_rsel_scan, (unsigned)(pass == 0 ? 1 : 2 * P), 256, 0, s.s_sort, pass, d_st,
              s.rsel_hist.as<unsigned int>(), d_nan, d_nn, n, s.pct.as<double>(), P, s.cutoff.as<double>());
     }
+    LAUNCH(k_rsel_pass<1>, big_grid, 256, 0, s.s_sort, s.D.as<double>(), s.src_of_pos.as<int32_t>(), L.npad, d_nn, 2,
+           d_st, s.rsel_hist.as<unsigned int>(), d_nan, cand);
+    if (!ctx->rsel_attr_set) {
+      CU(cudaFuncSetAttribute(k_rsel_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, RSEL_FIN_CAP * 8));
+      ctx->rsel_attr_set = true;
+    }
+    LAUNCH(k_rsel_finish, (unsigned)(2 * P), RSEL_FIN_THREADS, (size_t)RSEL_FIN_CAP * 8, s.s_sort, s.D.as<double>(),
+           s.src_of_pos.as<int32_t>(), L.npad, d_nn, d_st, cand, s.pct.as<double>(), P, s.cutoff.as<double>());
+    (void)small_grid;
   } else if (P > 0) {
     LAUNCH(k_fill_f64, 1, 64, 0, s.s_sort, s.cutoff.as<double>(), (int64_t)P, nan(""));
   }
@@ -503,9 +507,12 @@ int run_shard_main(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
 #define MDEGGS_GS(IT)                                                                                          \
   LAUNCH(k_gene_stats_reg<IT>, grid, 256, 0, s.s_main, s.D.as<double>(), L, d_nn, s.mean.as<double>(),        \
          s.sxx.as<double>(), s.med.as<double>(), s.bad.as<uint8_t>())
-      if (max_cnt <= 32 * 4) MDEGGS_GS(4);
+      if (max_cnt <= 32 * 2) MDEGGS_GS(2);
+      else if (max_cnt <= 32 * 4) MDEGGS_GS(4);
       else if (max_cnt <= 32 * 8) MDEGGS_GS(8);
+      else if (max_cnt <= 32 * 12) MDEGGS_GS(12);
       else if (max_cnt <= 32 * 16) MDEGGS_GS(16);
+      else if (max_cnt <= 32 * 24) MDEGGS_GS(24);
       else MDEGGS_GS(32);
 #undef MDEGGS_GS
     } else {
@@ -1171,6 +1178,11 @@ int mdeggs_set_option(mdeggs_ctx* ctx, const char* name, int64_t value) {
       cudaGraphExecDestroy(ctx->graph_exec);
       ctx->graph_exec = nullptr;
     }
+    ctx->key_valid = false;
+    return MDEGGS_OK;
+  }
+  if (!strcmp(name, "rsel_cap")) {
+    ctx->rsel_cap_override = value;
     ctx->key_valid = false;
     return MDEGGS_OK;
   }

@@ -301,8 +301,14 @@ __device__ __forceinline__ unsigned long long warp_select_reg(const unsigned lon
   for (; bit >= 0 && cnt_hi - cnt_lo > 32; --bit) {
     const unsigned long long cand = prefix | (1ull << bit);
     int c = 0;
+    if (bit >= 32) {  // low word of cand is zero: key < cand  <=>  hi(key) < hi(cand), one 32-bit compare
+      const unsigned int ch = (unsigned int)(cand >> 32);
 #pragma unroll
-    for (int j = 0; j < ITEMS; ++j) c += (keys[j] < cand);
+      for (int j = 0; j < ITEMS; ++j) c += ((unsigned int)(keys[j] >> 32) < ch);
+    } else {
+#pragma unroll
+      for (int j = 0; j < ITEMS; ++j) c += (keys[j] < cand);
+    }
     c = __reduce_add_sync(0xffffffffu, c);
     if (c <= kth) {
       prefix = cand;

@@ -113,37 +113,53 @@ __global__ void __launch_bounds__(256) k_rsel_pass(const double* __restrict__ D,
           v[r] = (row0 + r < n_nodes) ? __ldg(reinterpret_cast<const double2*>(D + (size_t)(row0 + r) * npad) + c)
                                       : make_double2(0.0, 0.0);
         const bool ok0 = src_of_pos[2 * c] >= 0, ok1 = src_of_pos[2 * c + 1] >= 0;  // padding slots are skipped
+        if (MODE == 1) {
+          // compaction: keep keys whose fixed prefix matches an active slot; one warp-aggregated append per
+          // 8 elements (exclusive warp scan of the per-thread counts + a single atomicAdd by the last lane)
+          unsigned int mask = 0;  // bit (2r + h) set: element kept
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            if (row0 + r >= n_nodes) break;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              if (!(h ? ok1 : ok0)) continue;
+              const unsigned long long pre = dkey(h ? v[r].y : v[r].x) >> (64 - consumed);
+              if (pre >= pmin && pre <= pmax && rsel_find_slot(s_pref, U, pre) >= 0) mask |= 1u << (2 * r + h);
+            }
+          }
+          const int nk = __popc(mask);
+          const unsigned am = __activemask();
+          if (__any_sync(am, nk > 0)) {
+            int incl = nk;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+              int t = __shfl_up_sync(am, incl, o);
+              if (lane >= o) incl += t;
+            }
+            const int last = 31 - __clz(am);
+            unsigned int base = 0;
+            if (lane == last) base = atomicAdd(cand.count, (unsigned int)incl);
+            base = __shfl_sync(am, base, last);
+            const unsigned int idx = base + (unsigned int)(incl - nk);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              if (mask & (1u << q)) {
+                const unsigned int at = idx + __popc(mask & ((1u << q) - 1u));
+                if (at < cand.capacity) cand.keys[at] = dkey((q & 1) ? v[q >> 1].y : v[q >> 1].x);
+              }
+            }
+          }
+          continue;
+        }
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
           if (row0 + r >= n_nodes) break;
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
-            const bool ok = h ? ok1 : ok0;
+            if (!(h ? ok1 : ok0)) continue;
             const unsigned long long key = dkey(h ? v[r].y : v[r].x);
-            if (MODE == 1) {
-              // compaction: keep keys whose fixed prefix matches an active slot (warp-aggregated append)
-              bool keep = false;
-              if (ok) {
-                const unsigned long long pre = key >> (64 - consumed);
-                keep = pre >= pmin && pre <= pmax && rsel_find_slot(s_pref, U, pre) >= 0;
-              }
-              const unsigned am = __activemask();
-              const unsigned m = __ballot_sync(am, keep);
-              if (m) {
-                const int leader = __ffs(m) - 1;
-                unsigned int base = 0;
-                if (lane == leader) base = atomicAdd(cand.count, (unsigned int)__popc(m));
-                base = __shfl_sync(am, base, leader);
-                if (keep) {
-                  unsigned int idx = base + __popc(m & ((1u << lane) - 1u));
-                  if (idx < cand.capacity) cand.keys[idx] = key;
-                }
-              }
-            } else {
-              if (!ok) continue;
-              if (pass == 0 && key == ~0ull) ++nans;
-              visit(key);
-            }
+            if (pass == 0 && key == ~0ull) ++nans;
+            visit(key);
           }
         }
       }
@@ -292,6 +308,182 @@ __global__ void __launch_bounds__(256) k_rsel_scan(int pass, RselState* __restri
       }
       cutoff[p] = q;
     }
+  }
+}
+
+// After two digit passes (24 key bits fixed) and the compaction, ONE kernel finishes every target: a CTA per active
+// prefix pulls that prefix's candidates (typically a few thousand) into shared memory, sorts them (bitonic) and reads
+// each target at its rank; the last CTA to finish evaluates the type-7 cut-offs.  Groups that do not fit in shared
+// memory (massive ties) or a compaction overflow take a slower in-CTA digit-by-digit path over the same source.
+constexpr int RSEL_FIN_CAP = 8192;  // keys per CTA in shared memory (64 KB)
+constexpr int RSEL_FIN_THREADS = 512;
+
+__global__ void __launch_bounds__(RSEL_FIN_THREADS) k_rsel_finish(const double* __restrict__ D, const int32_t* __restrict__ src_of_pos,
+                                                     int npad, const int32_t* __restrict__ n_nodes_p,
+                                                     RselState* __restrict__ st, RselCand cand,
+                                                     const double* __restrict__ pct, int P, double* __restrict__ cutoff) {
+  extern __shared__ unsigned long long fk[];  // RSEL_FIN_CAP keys; reused as a 4096-bin histogram on the slow path
+  __shared__ unsigned int s_cnt;
+  __shared__ int s_last;
+  __shared__ long long s_scan[RSEL_FIN_THREADS];
+  __shared__ unsigned long long s_pfx;
+  __shared__ long long s_rank;
+  const int tid = threadIdx.x, s = blockIdx.x;
+  const int T = 2 * P;
+  const int U = st->U[0];
+  if (s >= U) return;
+  const unsigned long long prefix = st->slot_prefix[0][s];  // 24 bits
+  const bool overflow = *cand.count > cand.capacity;
+  const unsigned int nc = overflow ? 0u : *cand.count;
+  const int n_nodes = *n_nodes_p;
+  const int half = npad >> 1;
+
+  // visit every source key whose top `bits` bits equal `pfx`
+  auto for_each_match = [&](unsigned long long pfx, int bits, auto&& fn) {
+    if (!overflow) {
+      // 8 independent loads in flight per thread: the candidate list is read by every CTA
+      for (unsigned int i0 = tid; i0 < nc; i0 += RSEL_FIN_THREADS * 8) {
+        unsigned long long k[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          unsigned int i = i0 + u * RSEL_FIN_THREADS;
+          k[u] = i < nc ? __ldg(cand.keys + i) : 0ull;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (i0 + u * RSEL_FIN_THREADS < nc && (k[u] >> (64 - bits)) == pfx) fn(k[u]);
+      }
+    } else {
+      for (int row = 0; row < n_nodes; ++row) {
+        const double2* R2 = reinterpret_cast<const double2*>(D + (size_t)row * npad);
+        for (int c = tid; c < half; c += RSEL_FIN_THREADS) {
+          double2 v = __ldg(R2 + c);
+          if (src_of_pos[2 * c] >= 0) {
+            unsigned long long k = dkey(v.x);
+            if ((k >> (64 - bits)) == pfx) fn(k);
+          }
+          if (src_of_pos[2 * c + 1] >= 0) {
+            unsigned long long k = dkey(v.y);
+            if ((k >> (64 - bits)) == pfx) fn(k);
+          }
+        }
+      }
+    }
+  };
+
+  if (tid == 0) s_cnt = 0;
+  __syncthreads();
+  for_each_match(prefix, 24, [&](unsigned long long k) {
+    unsigned int pos = atomicAdd(&s_cnt, 1u);
+    if (pos < (unsigned)RSEL_FIN_CAP) fk[pos] = k;
+  });
+  __syncthreads();
+  const unsigned int c = s_cnt;
+  if (c <= (unsigned)RSEL_FIN_CAP) {
+    unsigned int n2 = 1;
+    while (n2 < c) n2 <<= 1;
+    for (unsigned int i = c + tid; i < n2; i += RSEL_FIN_THREADS) fk[i] = ~0ull;
+    __syncthreads();
+    for (unsigned int k = 2; k <= n2; k <<= 1) {
+      for (unsigned int j = k >> 1; j > 0; j >>= 1) {
+        for (unsigned int i = tid; i < n2; i += RSEL_FIN_THREADS) {
+          unsigned int ixj = i ^ j;
+          if (ixj > i) {
+            unsigned long long a = fk[i], b = fk[ixj];
+            bool up = (i & k) == 0;
+            if ((a > b) == up) {
+              fk[i] = b;
+              fk[ixj] = a;
+            }
+          }
+        }
+        __syncthreads();
+      }
+    }
+    for (int t = tid; t < T; t += RSEL_FIN_THREADS)
+      if (st->slot[0][t] == s) st->prefix[t] = fk[st->rank[t]];
+  } else {
+    // slow path: one target at a time, digit by digit, histogram in shared memory
+    unsigned int* hist = reinterpret_cast<unsigned int*>(fk);
+    for (int t = 0; t < T; ++t) {
+      if (st->slot[0][t] != s) continue;  // uniform across the CTA
+      if (tid == 0) {
+        s_pfx = prefix;
+        s_rank = st->rank[t];
+      }
+      __syncthreads();
+      for (int pass = 2; pass < RSEL_PASSES; ++pass) {
+        const int width = rsel_width(pass), consumed = rsel_consumed(pass);
+        const int nbins = 1 << width;
+        const int shift = 64 - consumed - width;
+        for (int i = tid; i < RSEL_BINS; i += RSEL_FIN_THREADS) hist[i] = 0;
+        __syncthreads();
+        const unsigned long long pfx = s_pfx;
+        for_each_match(pfx, consumed, [&](unsigned long long k) {
+          atomicAdd(&hist[(unsigned int)((k >> shift) & (unsigned long long)(nbins - 1))], 1u);
+        });
+        __syncthreads();
+        // exclusive scan of the bins (16 per thread), then locate the bin holding the rank
+        long long loc = 0;
+        for (int j = 0; j < RSEL_BINS / RSEL_FIN_THREADS; ++j) loc += hist[tid * (RSEL_BINS / RSEL_FIN_THREADS) + j];
+        s_scan[tid] = loc;
+        __syncthreads();
+        if (tid == 0) {
+          long long run = 0;
+          for (int i = 0; i < RSEL_FIN_THREADS; ++i) {
+            long long v = s_scan[i];
+            s_scan[i] = run;
+            run += v;
+          }
+        }
+        __syncthreads();
+        const long long r = s_rank;
+        long long run = s_scan[tid];
+        int found = -1;
+        long long found_base = 0;
+        for (int j = 0; j < RSEL_BINS / RSEL_FIN_THREADS; ++j) {
+          int b = tid * (RSEL_BINS / RSEL_FIN_THREADS) + j;
+          long long h = hist[b];
+          if (b < nbins && r >= run && r < run + h) {
+            found = b;
+            found_base = run;
+          }
+          run += h;
+        }
+        __syncthreads();
+        if (found >= 0) {  // exactly one thread
+          s_pfx = (pfx << width) | (unsigned long long)found;
+          s_rank = r - found_base;
+        }
+        __syncthreads();
+      }
+      if (tid == 0) st->prefix[t] = s_pfx;
+      __syncthreads();
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(&st->done, 1u) == (unsigned)(U - 1));
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (tid == 0) st->done = 0;
+  const long long N = st->N;
+  volatile unsigned long long* pref = st->prefix;
+  for (int p = tid; p < P; p += RSEL_FIN_THREADS) {
+    if (N <= 0) {
+      cutoff[p] = nan("");
+      continue;
+    }
+    double idx = __dadd_rn(1.0, __dmul_rn((double)(N - 1), pct[p]));
+    double lo = floor(idx);
+    double q = dkey_inv(pref[2 * p]);
+    double xh = dkey_inv(pref[2 * p + 1]);
+    if (idx > lo && xh != q) {
+      double hfrac = __dsub_rn(idx, lo);
+      q = __dadd_rn(__dmul_rn(__dsub_rn(1.0, hfrac), q), __dmul_rn(hfrac, xh));
+    }
+    cutoff[p] = q;
   }
 }
 

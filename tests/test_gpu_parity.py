@@ -297,3 +297,30 @@ def test_graph_replay_is_bit_identical(oracle):
     eng.run_omic_raw(cprob, cres)
     assert not (eng.stats()["fit_path"] & 0x100)
     eng.close()
+
+
+def test_quantile_select_tie_groups_and_overflow(oracle):
+    """Radix-select corner paths: a tie group larger than the per-CTA shared-memory sort (slow in-CTA digit path) and
+    a candidate list that overflows (falls back to scanning the matrix). Cut-offs stay bit-exact."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    eng = md.Engine([0])
+    prob = synth.random_problem(500, 100, 600, 2, 701)
+    v = np.round(prob.assay, 1)
+    v[v < 4.9] = 0.0                      # ~45% exact zeros: one 64-bit-identical group of > 8192 values
+    prob.assay = np.asfortranarray(v)
+    prob.pct = np.array([0.05, 0.2, 0.35, 0.45, 0.5, 0.6, 0.75, 0.9, 0.99, 1.0])
+    ref = oracle.run_omic(prob, ALL_FIELDS)
+    gpu = eng.run_omic(prob, ALL_FIELDS)
+    assert (v == 0.0).sum() > 8192 and ref["cutoff"][0] == 0.0
+    assert_parity(gpu, ref, prob, what="tie group: ")
+    eng.set_option("rsel_cap", 1000)       # force the compaction to overflow
+    gpu2 = eng.run_omic(prob, ALL_FIELDS)
+    assert np.array_equal(gpu2["cutoff"], ref["cutoff"])
+    smooth = synth.random_problem(300, 80, 400, 3, 702)
+    ref3 = oracle.run_omic(smooth, ("cutoff", "tot_edges", "best"))
+    gpu3 = eng.run_omic(smooth, ("cutoff", "tot_edges", "best"))
+    for k in ref3:
+        assert np.array_equal(gpu3[k], ref3[k]), k
+    eng.close()
