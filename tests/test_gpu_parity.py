@@ -324,3 +324,60 @@ def test_quantile_select_tie_groups_and_overflow(oracle):
     for k in ref3:
         assert np.array_equal(gpu3[k], ref3[k]), k
     eng.close()
+
+
+def test_cfg4_filter_flow_scaled_down(engine, oracle):
+    """Config 4 (multiDEGGs_filter inside nestedcv folds): q.value path = raw p + masks from the device, host adjusts.
+    The public API on the GPU must select exactly the pairs the same host flow selects from the oracle's numbers."""
+    import pandas as pd
+    from helpers import oracle_single_omic
+    wl = synth.cfg4(n_features=1500, n_samples=24, planted=0.15)
+    x = pd.DataFrame(wl.assay.values.T, index=wl.assay.samples, columns=wl.assay.genes)
+    y = wl.group.astype(float)
+    rng = np.random.default_rng(4)
+    folds = np.array_split(rng.permutation(24), 3)
+    for hold in [None] + folds:
+        keep = np.ones(24, dtype=bool)
+        if hold is not None:
+            keep[hold] = False
+        xs, ys = x.iloc[keep], y[keep]
+        try:
+            got = md.multiDEGGs_filter(ys, xs, engine=engine)
+            got_pairs = list(got["pairs"].index) if got["pairs"].shape[0] else []
+        except ValueError as e:
+            got_pairs = str(e)
+        fac = host.tidy_metadata(metadata=pd.Series(ys, index=xs.index))
+        counts = md.Assay(np.ascontiguousarray(xs.to_numpy().T), wl.assay.genes, np.asarray(xs.index).astype(str))
+        try:
+            nets = oracle_single_omic(counts, "assayData1", fac, "lm", None, md.FILTER_PERCENTILES, "q.value")
+            frames = [v for v in nets.values() if isinstance(v, pd.DataFrame)]
+            sig = [f[(f["p.adj"] < 0.05).to_numpy()] for f in frames]
+            exp_pairs = [i for f in sig for i in f.index]
+            if len(exp_pairs) <= 1:
+                exp_pairs = []          # t-test fallback branch (fs:157-162): no pairs
+        except ValueError as e:
+            exp_pairs = str(e)
+        if isinstance(exp_pairs, str):
+            # get_diffNetworks swallows the per-omic error (message + NULL layer); get_sig_deggs then finds nothing
+            assert got_pairs == [] or isinstance(got_pairs, str)
+        else:
+            assert got_pairs == exp_pairs
+
+
+@pytest.mark.parametrize("padj", ["none", "holm", "hochberg", "BY", "hommel", "q.value"])
+def test_host_adjusted_methods_through_api(engine, oracle, bundled, padj):
+    """padj methods the device leaves to the host (or 'none'): same networks from engine and oracle numbers."""
+    import pandas as pd
+    from helpers import oracle_single_omic
+    fac = host.tidy_metadata(metadata=bundled["metadata"], category_variable="response")
+    got = md.get_diffNetworks_singleOmic(bundled["RNAseq"], "RNAseq", fac, "lm", network=None,
+                                         percentile_vector=md.DEFAULT_PERCENTILES, padj_method=padj, engine=engine)
+    exp = oracle_single_omic(bundled["RNAseq"], "RNAseq", fac, "lm", None, md.DEFAULT_PERCENTILES, padj)
+    assert got.keys() == exp.keys() and got["sig_pvalues_count"] == exp["sig_pvalues_count"]
+    for k in got:
+        if isinstance(got[k], pd.DataFrame):
+            assert list(got[k].index) == list(exp[k].index) and list(got[k].columns) == list(exp[k].columns)
+            for col in got[k].columns[2:]:
+                assert np.allclose(got[k][col].to_numpy(), exp[k][col].to_numpy(), rtol=1e-9, atol=4.5e-16, equal_nan=True)
+        else:
+            assert got[k] == exp[k]
