@@ -266,11 +266,11 @@ int run_adjust(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, int n_segmen
   LAUNCH(k_bh_count, grid, BH_THREADS, 0, s.s_main, A, s.tile_cnt.as<int32_t>());
   LAUNCH(k_bh_scan_tiles, n_segments, 256, 0, s.s_main, s.tile_cnt.as<int32_t>(), ntiles, s.tile_base.as<long long>(),
          s.seg_n.as<long long>());
-  if (in->padj == MDEGGS_PADJ_BH) {
-    LAUNCH(k_bh_tilemin, grid, BH_THREADS, 0, s.s_main, A, s.tile_cnt.as<int32_t>(), s.tile_base.as<long long>(),
-           s.seg_n.as<long long>(),
-           s.tile_min.as<double>());
-    LAUNCH(k_bh_suffix_min, n_segments, 256, 0, s.s_main, s.tile_min.as<double>(), ntiles, s.tile_carry.as<double>());
+  if (in->padj != MDEGGS_PADJ_BONFERRONI) {
+    LAUNCH(k_bh_tilemin, grid, BH_THREADS, 0, s.s_main, A, in->padj, s.tile_cnt.as<int32_t>(),
+           s.tile_base.as<long long>(), s.seg_n.as<long long>(), s.tile_min.as<double>());
+    LAUNCH(k_bh_suffix_min, n_segments, 256, 0, s.s_main, s.tile_min.as<double>(), ntiles, in->padj,
+           s.tile_carry.as<double>());
   }
   LAUNCH(k_bh_final, grid, BH_THREADS, 0, s.s_main, A, in->padj, s.tile_cnt.as<int32_t>(), s.tile_base.as<long long>(),
          s.seg_n.as<long long>(),
@@ -671,7 +671,8 @@ int run_shard_back(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
   int32_t* d_best = s.scal.as<int32_t>() + 2 * SC_BEST;
   const int act_stride = n_nodes > 0 ? n_nodes : 1;
   const int Pn = P > 0 ? P : 1;
-  const bool dev_adjust = (in->padj == MDEGGS_PADJ_BONFERRONI || in->padj == MDEGGS_PADJ_BH);
+  const bool dev_adjust = (in->padj == MDEGGS_PADJ_BONFERRONI || in->padj == MDEGGS_PADJ_BH || in->padj == MDEGGS_PADJ_HOLM ||
+                           in->padj == MDEGGS_PADJ_HOCHBERG || in->padj == MDEGGS_PADJ_BY);
   const bool do_adjust = dev_adjust && E > 0 && P > 0 && n_nodes > 0;
   if (do_adjust) {
     // The raw p-value of an edge does not depend on the percentile: sort ALL edges by p once. This needs no
@@ -795,7 +796,8 @@ int emit_outputs(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const mdeg
   long long* o_sig = o_tot + Pn;
   long long* o_fail = o_tot + 2 * Pn;
   const bool dev_out = in->mem == MDEGGS_MEM_DEVICE;
-  const bool dev_adjust = (in->padj == MDEGGS_PADJ_BONFERRONI || in->padj == MDEGGS_PADJ_BH);
+  const bool dev_adjust = (in->padj == MDEGGS_PADJ_BONFERRONI || in->padj == MDEGGS_PADJ_BH || in->padj == MDEGGS_PADJ_HOLM ||
+                           in->padj == MDEGGS_PADJ_HOCHBERG || in->padj == MDEGGS_PADJ_BY);
   const int8_t* d_cat = (out->cat && E > 0 && P > 0) ? (dev_out ? out->cat : s.cat.as<int8_t>()) : nullptr;
   const double* d_padj = (dev_adjust && E > 0 && P > 0 && n_nodes > 0 && out->padj)
                              ? (dev_out ? out->padj : s.padj.as<double>())

@@ -823,23 +823,44 @@ __global__ void __launch_bounds__(256) k_bh_scan_tiles(const int32_t* __restrict
   if (threadIdx.x == 0) seg_n[blockIdx.x] = carry;
 }
 
-__device__ __forceinline__ double bh_value(double n, long long i, double p) {
-  return __dmul_rn(__ddiv_rn(n, (double)i), p);  // (n / i) * p[o]  (stats::p.adjust, "BH")
+// q = sum(1 / (1:n)) of stats::p.adjust(method = "BY"): summed left to right for small n, asymptotic beyond
+__device__ __forceinline__ double harmonic_number(long long n) {
+  if (n < 128) {
+    double s = 0.0;
+    for (long long j = 1; j <= n; ++j) s += 1.0 / (double)j;
+    return s;
+  }
+  const double x = (double)n, r = 1.0 / (x * x);
+  return log(x) + 0.57721566490153286061 + 0.5 / x - r * (1.0 / 12.0 - r * (1.0 / 120.0 - r / 252.0));
+}
+
+// value that enters the cumulative min/max of stats::p.adjust, i = ascending rank inside the segment
+// `num` = n for BH, q * n for BY (q = sum(1/(1:n)), hoisted out of the per-element path by adj_numerator)
+__device__ __forceinline__ double adj_numerator(int mode, double n) {
+  return mode == MDEGGS_PADJ_BY ? __dmul_rn(harmonic_number((long long)n), n) : n;
+}
+__device__ __forceinline__ double adj_value(int mode, double n, double num, long long i, double p) {
+  if (mode == MDEGGS_PADJ_BH || mode == MDEGGS_PADJ_BY) return __dmul_rn(__ddiv_rn(num, (double)i), p);  // (n/i) p[o]
+  return __dmul_rn(__dsub_rn(__dadd_rn(n, 1.0), (double)i), p);  // holm / hochberg: (n + 1 - i) * p[o]
 }
 
 struct MinOp {
   __device__ __forceinline__ double operator()(double a, double b) const { return a < b ? a : b; }
 };
+struct MaxOp {
+  __device__ __forceinline__ double operator()(double a, double b) const { return a > b ? a : b; }
+};
 
 // pass B: BH values with global ranks -> minimum of each tile
-__global__ void __launch_bounds__(BH_THREADS) k_bh_tilemin(BhArgs A, const int32_t* __restrict__ tile_cnt,
+__global__ void __launch_bounds__(BH_THREADS) k_bh_tilemin(BhArgs A, int mode, const int32_t* __restrict__ tile_cnt,
                                                           const long long* __restrict__ tile_base,
                                                           const long long* __restrict__ seg_n,
                                                           double* __restrict__ tile_min) {
   int p, c;
   if (!bh_segment(A, p, c)) return;
   if (tile_cnt[(size_t)blockIdx.y * A.ntiles + blockIdx.x] == 0) {  // no member of this segment in the tile
-    if (threadIdx.x == 0) tile_min[(size_t)blockIdx.y * A.ntiles + blockIdx.x] = INFINITY;
+    if (threadIdx.x == 0)
+      tile_min[(size_t)blockIdx.y * A.ntiles + blockIdx.x] = mode == MDEGGS_PADJ_HOLM ? -INFINITY : INFINITY;
     return;
   }
   typedef cub::BlockScan<int, BH_THREADS> Scan;
@@ -856,31 +877,40 @@ __global__ void __launch_bounds__(BH_THREADS) k_bh_tilemin(BhArgs A, const int32
   const size_t seg = blockIdx.y;
   const long long base = tile_base[seg * A.ntiles + blockIdx.x];
   const double n = (double)seg_n[seg];
-  double mn = INFINITY;
+  const bool fwd_max = mode == MDEGGS_PADJ_HOLM;  // holm: cummax over ascending p; others: cummin from the largest p
+  double mn = fwd_max ? -INFINITY : INFINITY;
+  const double num = adj_numerator(mode, n);
 #pragma unroll
   for (int it = 0; it < BH_ITEMS; ++it)
-    if (flag[it]) mn = fmin(mn, bh_value(n, base + rank[it], pv[it]));
-  double tmn = Reduce(tmp.red).Reduce(mn, MinOp());
+    if (flag[it]) {
+      double v = adj_value(mode, n, num, base + rank[it], pv[it]);
+      mn = fwd_max ? fmax(mn, v) : fmin(mn, v);
+    }
+  double tmn = fwd_max ? Reduce(tmp.red).Reduce(mn, MaxOp()) : Reduce(tmp.red).Reduce(mn, MinOp());
   if (threadIdx.x == 0) tile_min[seg * A.ntiles + blockIdx.x] = tmn;
 }
 
-// exclusive suffix-min over the tiles of each segment (one CTA per segment, walks tiles from the end)
-__global__ void __launch_bounds__(256) k_bh_suffix_min(const double* __restrict__ tile_min, int ntiles,
+// carry over the tiles of each segment (one CTA per segment): exclusive suffix-min walking the tiles from the end
+// (BH, hochberg, BY) or exclusive prefix-max walking them from the start (holm)
+__global__ void __launch_bounds__(256) k_bh_suffix_min(const double* __restrict__ tile_min, int ntiles, int mode,
                                                        double* __restrict__ tile_carry) {
   typedef cub::BlockScan<double, 256> Scan;
   __shared__ typename Scan::TempStorage tmp;
   __shared__ double carry;
-  if (threadIdx.x == 0) carry = INFINITY;
+  const bool fwd_max = mode == MDEGGS_PADJ_HOLM;
+  const double ident = fwd_max ? -INFINITY : INFINITY;
+  if (threadIdx.x == 0) carry = ident;
   __syncthreads();
   const size_t base = (size_t)blockIdx.x * ntiles;
   for (int t0 = 0; t0 < ntiles; t0 += 256) {
-    int r = t0 + threadIdx.x;  // reversed tile index
-    int t = ntiles - 1 - r;
-    double v = r < ntiles ? tile_min[base + t] : INFINITY, ex, agg;
-    Scan(tmp).ExclusiveScan(v, ex, INFINITY, MinOp(), agg);
-    if (r < ntiles) tile_carry[base + t] = fmin(carry, ex);
+    int r = t0 + threadIdx.x;                    // position in walking order
+    int t = fwd_max ? r : ntiles - 1 - r;        // tile index
+    double v = r < ntiles ? tile_min[base + t] : ident, ex, agg;
+    if (fwd_max) Scan(tmp).ExclusiveScan(v, ex, ident, MaxOp(), agg);
+    else Scan(tmp).ExclusiveScan(v, ex, ident, MinOp(), agg);
+    if (r < ntiles) tile_carry[base + t] = fwd_max ? fmax(carry, ex) : fmin(carry, ex);
     __syncthreads();
-    if (threadIdx.x == 0) carry = fmin(carry, agg);
+    if (threadIdx.x == 0) carry = fwd_max ? fmax(carry, agg) : fmin(carry, agg);
     __syncthreads();
   }
 }
@@ -910,34 +940,47 @@ __global__ void __launch_bounds__(BH_THREADS) k_bh_final(BhArgs A, int mode, con
   bh_load(A, p, c, tile0, flag, pv);
   const size_t seg = blockIdx.y;
   const double n = (double)seg_n[seg];
-  if (mode == 2) {
+  if (mode != MDEGGS_PADJ_BONFERRONI) {
+    const bool fwd_max = mode == MDEGGS_PADJ_HOLM;
+    const double ident = fwd_max ? -INFINITY : INFINITY;
     ScanI(tmp.si).InclusiveSum(flag, rank);
     __syncthreads();
     const long long base = tile_base[seg * A.ntiles + blockIdx.x];
-    // suffix min inside the tile: scan the reversed sequence (thread T-1-t, item order reversed)
-    double v[BH_ITEMS], sfx[BH_ITEMS];
+    double v[BH_ITEMS], run_it[BH_ITEMS];
+    const double num = adj_numerator(mode, n);
 #pragma unroll
-    for (int it = 0; it < BH_ITEMS; ++it) v[it] = flag[it] ? bh_value(n, base + rank[it], pv[it]) : INFINITY;
-    // own items: local suffix (items after me in this thread)
-    double run = INFINITY;
+    for (int it = 0; it < BH_ITEMS; ++it) v[it] = flag[it] ? adj_value(mode, n, num, base + rank[it], pv[it]) : ident;
+    // running min (from the thread's last item backwards) or max (forwards) over the thread's own items
+    double run = ident;
+    if (fwd_max) {
 #pragma unroll
-    for (int it = BH_ITEMS - 1; it >= 0; --it) {
-      run = fmin(run, v[it]);
-      sfx[it] = run;
+      for (int it = 0; it < BH_ITEMS; ++it) {
+        run = fmax(run, v[it]);
+        run_it[it] = run;
+      }
+    } else {
+#pragma unroll
+      for (int it = BH_ITEMS - 1; it >= 0; --it) {
+        run = fmin(run, v[it]);
+        run_it[it] = run;
+      }
     }
-    // threads after me: exclusive scan over reversed thread ids
-    __shared__ double tmin_s[BH_THREADS];
-    tmin_s[BH_THREADS - 1 - threadIdx.x] = run;
+    // aggregate of the threads before (holm) / after (others) this one: exclusive scan in walking order
+    __shared__ double tagg_s[BH_THREADS];
+    const int wpos = fwd_max ? threadIdx.x : BH_THREADS - 1 - threadIdx.x;
+    tagg_s[wpos] = run;
     __syncthreads();
-    double mine = tmin_s[threadIdx.x], ex;
-    ScanD(tmp.sd).ExclusiveScan(mine, ex, INFINITY, MinOp());
+    double mine = tagg_s[threadIdx.x], ex;
+    if (fwd_max) ScanD(tmp.sd).ExclusiveScan(mine, ex, ident, MaxOp());
+    else ScanD(tmp.sd).ExclusiveScan(mine, ex, ident, MinOp());
     __syncthreads();
-    tmin_s[threadIdx.x] = ex;  // ex of reversed position r = min over reversed positions < r
+    tagg_s[threadIdx.x] = ex;
     __syncthreads();
-    double after = tmin_s[BH_THREADS - 1 - threadIdx.x];
+    const double others = tagg_s[wpos];
     const double carry = tile_carry[seg * A.ntiles + blockIdx.x];
 #pragma unroll
-    for (int it = 0; it < BH_ITEMS; ++it) q[it] = fmin(1.0, fmin(sfx[it], fmin(after, carry)));
+    for (int it = 0; it < BH_ITEMS; ++it)
+      q[it] = fwd_max ? fmin(1.0, fmax(run_it[it], fmax(others, carry))) : fmin(1.0, fmin(run_it[it], fmin(others, carry)));
     __syncthreads();
   } else {
 #pragma unroll

@@ -221,7 +221,13 @@ def _padj_code(padj_method: str) -> int:
         return _abi.PADJ_BONFERRONI
     if padj_method in ("BH", "fdr"):
         return _abi.PADJ_BH
-    if padj_method == "q.value" or padj_method in P_ADJUST_METHODS:
+    if padj_method == "holm":
+        return _abi.PADJ_HOLM
+    if padj_method == "hochberg":
+        return _abi.PADJ_HOCHBERG
+    if padj_method == "BY":
+        return _abi.PADJ_BY
+    if padj_method in ("q.value", "hommel"):
         return _abi.PADJ_HOST
     raise ValueError(f"padj_method must be one of {P_ADJUST_METHODS + ('q.value',)}")
 
@@ -292,7 +298,7 @@ def prepare_omic(assayData, assayDataName: str, metadata: Factor, regression_met
 def want_fields(prep: OmicPrep, extra: Sequence[str] = ()) -> tuple[str, ...]:
     base = ["cutoff", "p_edge", "status", "tot_edges", "sig_count", "fail_count", "best", "cat_best"]
     code = prep.problem.padj
-    if code in (_abi.PADJ_BONFERRONI, _abi.PADJ_BH):
+    if code in _abi.DEVICE_PADJ:
         base.append("padj_best")
     if code == _abi.PADJ_HOST:
         base.append("cat")

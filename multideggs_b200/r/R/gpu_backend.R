@@ -16,7 +16,10 @@
   if (padj_method == "none") return(0L)
   if (padj_method == "bonferroni") return(1L)
   if (padj_method %in% c("BH", "fdr")) return(2L)
-  3L  # q.value, holm, hochberg, hommel, BY: raw p + masks come back, R adjusts each segment
+  if (padj_method == "holm") return(4L)
+  if (padj_method == "hochberg") return(5L)
+  if (padj_method == "BY") return(6L)
+  3L  # q.value, hommel: raw p + masks come back, R adjusts each segment
 }
 
 get_diffNetworks_singleOmic <- function(assayData, assayDataName, metadata, regression_method,

@@ -857,6 +857,11 @@ int mdeggs_oracle_run_omic(const mdeggs_problem* in, mdeggs_result* out, int mod
   int8_t* cat_all = (int8_t*)malloc((size_t)(P > 0 ? P : 1) * (size_t)(E > 0 ? E : 1));
   double* padj_all = (double*)malloc(sizeof(double) * (size_t)(P > 0 ? P : 1) * (size_t)(E > 0 ? E : 1));
   int padj_method = in->padj;
+  /* ABI code -> orc_p_adjust method (0 none, 1 bonferroni, 2 BH, 3 holm, 4 hochberg, 5 BY) */
+  const int orc_method = padj_method == MDEGGS_PADJ_BONFERRONI ? 1 : padj_method == MDEGGS_PADJ_BH ? 2
+                         : padj_method == MDEGGS_PADJ_HOLM ? 3 : padj_method == MDEGGS_PADJ_HOCHBERG ? 4
+                         : padj_method == MDEGGS_PADJ_BY ? 5 : 0;
+  const int dev_adjust = orc_method != 0;
   int pthreads = (mode == MDEGGS_ORACLE_MODE_REFERENCE) ? (nthreads < P ? nthreads : P) : nthreads;
   if (pthreads < 1) pthreads = 1;
 #pragma omp parallel for schedule(dynamic, 1) num_threads(pthreads)
@@ -911,15 +916,15 @@ int mdeggs_oracle_run_omic(const mdeggs_problem* in, mdeggs_result* out, int mod
           pv[j++] = p_edge[e];
         }
       }
-      if (padj_method == MDEGGS_PADJ_BONFERRONI || padj_method == MDEGGS_PADJ_BH) {
-        orc_p_adjust(pv, m, padj_method, pa);
+      if (dev_adjust) {
+        orc_p_adjust(pv, m, orc_method, pa);
       } else {
         memcpy(pa, pv, sizeof(double) * (size_t)m);
       }
       j = 0;
       for (int64_t e = 0; e < E; ++e) {
         if (cat[e] != k) continue;
-        if (padj_method == MDEGGS_PADJ_BONFERRONI || padj_method == MDEGGS_PADJ_BH) padj[e] = pa[j];
+        if (dev_adjust) padj[e] = pa[j];
         if (pa[j] < 0.05) ++nsig; /* NaN compares false == na.rm = TRUE */
         ++j;
       }
@@ -943,7 +948,7 @@ int mdeggs_oracle_run_omic(const mdeggs_problem* in, mdeggs_result* out, int mod
   }
   if (out->best) *out->best = host_adjust ? 0 : best;
   if (out->cat) memcpy(out->cat, cat_all, (size_t)P * (size_t)E);
-  int fills_padj = (padj_method == MDEGGS_PADJ_BONFERRONI || padj_method == MDEGGS_PADJ_BH);
+  int fills_padj = dev_adjust;
   if (out->padj && fills_padj) memcpy(out->padj, padj_all, sizeof(double) * (size_t)P * (size_t)E);
   if (best > 0 && !host_adjust) {
     if (out->cat_best) memcpy(out->cat_best, cat_all + (int64_t)(best - 1) * E, (size_t)E);

@@ -32,7 +32,7 @@ def test_bundled_engine_vs_oracle(engine, oracle, bundled, omic, method, padj):
     (80, 37, 300, 3, 6), (120, 333, 900, 3, 7), (60, 1000, 400, 3, 8), (90, 64, 500, 4, 9), (70, 120, 300, 5, 10),
     (33, 17, 40, 2, 11), (257, 129, 1025, 3, 12),
 ])
-@pytest.mark.parametrize("padj", [_abi.PADJ_BH, _abi.PADJ_BONFERRONI])
+@pytest.mark.parametrize("padj", [_abi.PADJ_BH, _abi.PADJ_BONFERRONI, _abi.PADJ_HOLM, _abi.PADJ_HOCHBERG, _abi.PADJ_BY])
 def test_random_lm_aov(engine, oracle, G, n, E, K, seed, padj):
     prob = synth.random_problem(G, n, E, K, seed, _abi.METHOD_LM, padj)
     gpu, ref = _both(engine, oracle, prob)
