@@ -29,6 +29,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ["NCCL_DEBUG"] = os.environ.get("MDEGGS_NCCL_DEBUG", "WARN")  # NCCL's version banner goes to stdout otherwise
 
 METRIC = "gene-pair interaction tests/sec"
 UNIT = "unique pair tests/s"

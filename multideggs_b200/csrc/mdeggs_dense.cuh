@@ -24,6 +24,7 @@ constexpr int DLD = DT + 2;  // padded leading dimension of the transposed stage
 // S[k][i][j] (row-major nn x nn per category), written for tile pairs ti <= tj
 __global__ void __launch_bounds__(256, 1) k_dense_moments(const double* __restrict__ D, SegLayout L,
                                                           const double* __restrict__ mean, int nn, int ntiles,
+                                                          const int32_t* __restrict__ row_range,
                                                           double* __restrict__ S) {
   __shared__ __align__(16) double As[2][DKC][DLD];
   __shared__ __align__(16) double Bs[2][DKC][DLD];
@@ -34,6 +35,8 @@ __global__ void __launch_bounds__(256, 1) k_dense_moments(const double* __restri
     ++ti;
   }
   const int tj = ti + rem;
+  // multi-GPU: this rank only needs the tile rows that its edge block touches (row = min(a, b) of an edge)
+  if (row_range && (ti < row_range[0] / DT || ti > row_range[1] / DT)) return;
   const int k = blockIdx.y;
   const int seg_beg = L.off[k], seg_len = L.off[k + 1] - L.off[k];
   if (L.cnt[k] == 0) return;
@@ -122,6 +125,29 @@ __global__ void __launch_bounds__(256, 1) k_dense_moments(const double* __restri
         if (c + 1 < nn) Sk[(size_t)r * nn + c + 1] = acc[i][2 * g + 1];
       }
     }
+  }
+}
+
+// [min, max] over this rank's edges of the smaller node index of the edge: the rows of S it will read
+__global__ void k_edge_row_range(const int32_t* __restrict__ from, const int32_t* __restrict__ to,
+                                 const int32_t* __restrict__ node_of_row, int64_t e_lo, int64_t e_hi,
+                                 int32_t* __restrict__ row_range, const int32_t* __restrict__ err) {
+  if (*err) return;
+  int lo = 0x7fffffff, hi = -1;
+  for (int64_t e = e_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < e_hi; e += (int64_t)gridDim.x * blockDim.x) {
+    int a = node_of_row[from[e] - 1], b = node_of_row[to[e] - 1];
+    int i = a < b ? a : b;
+    lo = i < lo ? i : lo;
+    hi = i > hi ? i : hi;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (lo != 0x7fffffff) atomicMin(&row_range[0], lo);
+    if (hi >= 0) atomicMax(&row_range[1], hi);
   }
 }
 

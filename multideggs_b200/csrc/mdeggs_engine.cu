@@ -59,7 +59,7 @@ struct DevBuf {
 enum Ev { EV_START, EV_H2D, EV_GATHER, EV_STATS, EV_FIT, EV_TAIL, EV_COLL, EV_PERC, EV_ADJ, EV_END, EV_Q0, EV_Q1, EV_COUNT };
 
 // scalar slots in the `scal` buffer (8-byte each)
-enum Scal { SC_NNODES = 0, SC_ERR = 1, SC_BEST = 2, SC_NVALID = 3, SC_COUNT = 8 };
+enum Scal { SC_NNODES = 0, SC_ERR = 1, SC_BEST = 2, SC_NVALID = 3, SC_ROWLO = 4, SC_ROWHI = 5, SC_COUNT = 8 };
 
 struct Shard {
   int device = 0, rank = 0, world = 1;
@@ -67,6 +67,7 @@ struct Shard {
   cudaEvent_t ev[EV_COUNT] = {};
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   nccl_comm_t comm = nullptr;
+  bool smem_attr_set = false, rsel_attr_set = false;  // cudaFuncSetAttribute is per device
   int64_t row_off = 0, ld_eff = 0;  // the device copy of the assay starts at host row `row_off`
   void* h_stage = nullptr;          // pinned host staging for the tiny per-call inputs (src_of_pos, pct, df)
   size_t h_stage_cap = 0;
@@ -111,6 +112,7 @@ struct mdeggs_ctx {
   mdeggs_stats stats;
   int64_t launches = 0;
   // CUDA-graph replay of the compute phase (K0..K8) for repeated calls with identical shapes and buffers
+  int debug_sync = 0;        // MDEGGS_DEBUG_SYNC=1
   int use_graph = 1;         // option "graph" / MDEGGS_GRAPH
   bool capturing = false;
   bool key_valid = false;
@@ -118,8 +120,6 @@ struct mdeggs_ctx {
   int key_hits = 0;
   cudaGraphExec_t graph_exec = nullptr;
   int64_t graph_launches = 0;
-  bool smem_attr_set = false;
-  bool rsel_attr_set = false;
   int64_t rsel_cap_override = 0;  // option "rsel_cap": shrink the candidate list to exercise the overflow path (tests)
   int fit_path_override = -1;  // -1 auto, 0 force streaming, 1 force dense (MDEGGS_FIT_PATH, tests)
 };
@@ -165,6 +165,13 @@ void set_err(mdeggs_ctx* c, const char* fmt, ...) {
   do {                                                                                         \
     kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                                \
     ++ctx->launches;                                                                           \
+    if (ctx->debug_sync && !ctx->capturing) { /* MDEGGS_DEBUG_SYNC=1: pinpoint a failing launch */ \
+      cudaError_t le_ = cudaGetLastError();                                                    \
+      if (le_ == cudaSuccess) le_ = cudaStreamSynchronize(stream);                             \
+      if (le_ != cudaSuccess)                                                                  \
+        fprintf(stderr, "[mdeggs] %s:%d launch of %s failed: %s\n", __FILE__, __LINE__, #kernel, \
+                cudaGetErrorString(le_));                                                      \
+    }                                                                                          \
   } while (0)
 
 inline unsigned blocks_for(int64_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
@@ -244,8 +251,10 @@ int copy_out(mdeggs_ctx* ctx, Shard& s, void* dst, const void* src, size_t bytes
 }
 
 // ---- BH / Bonferroni over a block of percentiles (or the device-chosen best one) -----------------
-int run_adjust(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, int n_segments, int p0, const int32_t* best_dev,
-               unsigned long long* sig_dev, double* padj_out, int64_t padj_stride, int act_stride) {
+int run_adjust(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, int n_segments, int p0, int p_stride,
+               const int32_t* best_dev, unsigned long long* sig_dev, double* padj_out, int64_t padj_stride,
+               int act_stride) {
+  if (n_segments <= 0) return MDEGGS_OK;
   const int64_t E = in->E;
   const int ntiles = (int)((E + BH_TILE - 1) / BH_TILE);
   BhArgs A;
@@ -261,6 +270,7 @@ int run_adjust(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, int n_segmen
   A.P = in->P;
   A.ntiles = ntiles;
   A.p0 = p0;
+  A.p_stride = p_stride;
   A.best = best_dev;
   dim3 grid((unsigned)ntiles, (unsigned)n_segments);
   LAUNCH(k_bh_count, grid, BH_THREADS, 0, s.s_main, A, s.tile_cnt.as<int32_t>());
@@ -474,9 +484,9 @@ int run_shard_main(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
     }
     LAUNCH(k_rsel_pass<1>, big_grid, 256, 0, s.s_sort, s.D.as<double>(), s.src_of_pos.as<int32_t>(), L.npad, d_nn, 2,
            d_st, s.rsel_hist.as<unsigned int>(), d_nan, cand);
-    if (!ctx->rsel_attr_set) {
+    if (!s.rsel_attr_set) {
       CU(cudaFuncSetAttribute(k_rsel_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, RSEL_FIN_CAP * 8));
-      ctx->rsel_attr_set = true;
+      s.rsel_attr_set = true;
     }
     LAUNCH(k_rsel_finish, (unsigned)(2 * P), RSEL_FIN_THREADS, (size_t)RSEL_FIN_CAP * 8, s.s_sort, s.D.as<double>(),
            s.src_of_pos.as<int32_t>(), L.npad, d_nn, d_st, cand, s.pct.as<double>(), P, s.cutoff.as<double>());
@@ -518,9 +528,9 @@ int run_shard_main(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
     } else {
       size_t smem = (size_t)L.npad * 8;
       int use_smem = smem <= 200 * 1024;
-      if (use_smem && smem > 48 * 1024 && !ctx->smem_attr_set) {
+      if (use_smem && smem > 48 * 1024 && !s.smem_attr_set) {
         CU(cudaFuncSetAttribute(k_gene_stats<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        ctx->smem_attr_set = true;
+        s.smem_attr_set = true;
       }
       LAUNCH(k_gene_stats<128>, (unsigned)n_nodes, 128, use_smem ? smem : 0, s.s_main, s.D.as<double>(), L, d_nn,
              s.mean.as<double>(), s.sxx.as<double>(), s.med.as<double>(), s.bad.as<uint8_t>(), use_smem);
@@ -571,8 +581,18 @@ int run_shard_main(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
       // all ranks compute the (replicated) moment matrices; only the edge finishing is sharded
       const int ntl = (n_nodes + DT - 1) / DT;
       dim3 grid((unsigned)(ntl * (ntl + 1) / 2), (unsigned)K);
+      const int32_t* d_range = nullptr;
+      if (s.world > 1) {  // this rank only computes the tile rows its contiguous edge block reads
+        int32_t* rr = s.scal.as<int32_t>() + 2 * SC_ROWLO;
+        CU(cudaMemsetAsync(rr, 0x7f, 4, s.s_main));                     // row_range[0] = huge
+        CU(cudaMemsetAsync(rr + 1, 0xff, 4, s.s_main));                 // row_range[1] = -1
+        int64_t nb = (e_hi - e_lo + 255) / 256;
+        LAUNCH(k_edge_row_range, (unsigned)(nb < 148 * 8 ? nb : 148 * 8), 256, 0, s.s_main, s.from.as<int32_t>(),
+               s.to.as<int32_t>(), s.node_of_row.as<int32_t>(), e_lo, e_hi, rr, s.scal.as<int32_t>() + 2 * SC_ERR);
+        d_range = rr;
+      }
       LAUNCH(k_dense_moments, grid, 256, 0, s.s_main, s.D.as<double>(), L, s.mean.as<double>(), (int)n_nodes, ntl,
-             s.dense_S.as<double>());
+             d_range, s.dense_S.as<double>());
     } else {
       switch (K) {
         case 2: launch_fit_stream<2>(ctx, s, L, e_lo, e_hi); break;
@@ -733,7 +753,11 @@ int run_shard_back(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
   double* d_padj = nullptr;
   const bool want_padj_best = out->padj_best && do_adjust;
   // adjusted values of every percentile are kept when they fit a modest scratch matrix, so the best row is a copy
-  const bool keep_all_padj = do_adjust && (out->padj || (want_padj_best && (size_t)P * (size_t)E * 8 <= ((size_t)256 << 20)));
+  // multi-GPU: the (percentile, category) segments are independent, so rank r adjusts percentiles r, r+world, ...
+  // and only the per-percentile significant counts are all-reduced; a full P x E p.adj output keeps it replicated
+  const bool shard_p = do_adjust && s.world > 1 && !out->padj;
+  const bool keep_all_padj = do_adjust && !shard_p &&
+                             (out->padj || (want_padj_best && (size_t)P * (size_t)E * 8 <= ((size_t)256 << 20)));
   if (do_adjust) {
     const int ntiles = (int)((E + BH_TILE - 1) / BH_TILE);
     const size_t nseg = (size_t)P * K;
@@ -752,9 +776,58 @@ int run_shard_back(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
       LAUNCH(k_fill_f64, (unsigned)(blocks_for(tot, 256) < 148u * 16 ? blocks_for(tot, 256) : 148u * 16), 256, 0,
              s.s_main, d_padj, tot, nan(""));
     }
-    int rc = run_adjust(ctx, s, in, P * K, 0, nullptr, c_sig, d_padj, E, act_stride);
+    const int p0 = shard_p ? s.rank : 0, stride = shard_p ? s.world : 1;
+    const int n_loc = p0 < P ? (P - p0 + stride - 1) / stride : 0;
+    int rc = run_adjust(ctx, s, in, n_loc * K, p0, stride, nullptr, c_sig, d_padj, E, act_stride);
     if (rc) return rc;
   }
+  return MDEGGS_OK;
+}
+
+// all-reduce of the per-percentile significant counts when the adjustment was sharded over the ranks
+int run_sig_allreduce(mdeggs_ctx* ctx, const mdeggs_problem* in, const mdeggs_result* out) {
+  Shard& s0 = ctx->shards[0];
+  const bool dev_adjust = (in->padj == MDEGGS_PADJ_BONFERRONI || in->padj == MDEGGS_PADJ_BH || in->padj == MDEGGS_PADJ_HOLM ||
+                           in->padj == MDEGGS_PADJ_HOCHBERG || in->padj == MDEGGS_PADJ_BY);
+  if (!(dev_adjust && s0.world > 1 && !out->padj && in->E > 0 && in->P > 0)) return MDEGGS_OK;
+  NcclApi& api = nccl_api();
+  const int Pn = in->P;
+  NC(api.GroupStart());
+  for (Shard& s : ctx->shards) {
+    CU(cudaSetDevice(s.device));
+    unsigned long long* c_sig = s.counters.as<unsigned long long>() + 2 * Pn;
+    NC(api.AllReduce(c_sig, c_sig, (size_t)Pn, NCCL_UINT64, NCCL_SUM, s.comm, s.s_main));
+  }
+  NC(api.GroupEnd());
+  return MDEGGS_OK;
+}
+
+int run_shard_back2(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const mdeggs_result* out, const HostLayout& H,
+                    int32_t n_nodes, bool emit) {
+  const int G = in->G, K = in->K, P = in->P;
+  const int64_t E = in->E;
+  (void)H;
+  CU(cudaSetDevice(s.device));
+  int32_t* d_best = s.scal.as<int32_t>() + 2 * SC_BEST;
+  const int act_stride = n_nodes > 0 ? n_nodes : 1;
+  const int Pn = P > 0 ? P : 1;
+  unsigned long long* c_tot = s.counters.as<unsigned long long>();
+  unsigned long long* c_fail = c_tot + Pn;
+  unsigned long long* c_sig = c_tot + 2 * Pn;
+  unsigned long long* c_raw = c_tot + 3 * Pn;
+  long long* o_tot = (long long*)(c_tot + 4 * Pn);
+  long long* o_sig = o_tot + Pn;
+  long long* o_fail = o_tot + 2 * Pn;
+  const bool dev_out = in->mem == MDEGGS_MEM_DEVICE;
+  const bool dev_adjust = (in->padj == MDEGGS_PADJ_BONFERRONI || in->padj == MDEGGS_PADJ_BH || in->padj == MDEGGS_PADJ_HOLM ||
+                           in->padj == MDEGGS_PADJ_HOCHBERG || in->padj == MDEGGS_PADJ_BY);
+  const bool do_adjust = dev_adjust && E > 0 && P > 0 && n_nodes > 0;
+  const bool want_padj_best = out->padj_best && do_adjust;
+  const bool shard_p = do_adjust && s.world > 1 && !out->padj;
+  const bool keep_all_padj = do_adjust && !shard_p &&
+                             (out->padj || (want_padj_best && (size_t)P * (size_t)E * 8 <= ((size_t)256 << 20)));
+  double* d_padj = nullptr;
+  if (keep_all_padj) d_padj = (out->padj && dev_out && emit) ? out->padj : s.padj.as<double>();
   const unsigned long long* sig_src = dev_adjust ? c_sig : c_raw;
   LAUNCH(k_select_best, 1, 32, 0, s.s_main, c_tot, c_fail, sig_src, P, in->padj == MDEGGS_PADJ_HOST ? 1 : 0, o_tot,
          o_sig, o_fail, d_best);
@@ -766,7 +839,7 @@ int run_shard_back(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
   if (want_padj_best && !row_copy) {  // P x E too large to keep: rerun the adjustment for the best percentile only
     LAUNCH(k_fill_f64, (unsigned)(blocks_for(E, 256) < 148u * 16 ? blocks_for(E, 256) : 148u * 16), 256, 0, s.s_main,
            s.padj_best.as<double>(), E, nan(""));
-    int rc = run_adjust(ctx, s, in, K, 0, d_best, nullptr, s.padj_best.as<double>(), E, act_stride);
+    int rc = run_adjust(ctx, s, in, K, 0, 1, d_best, nullptr, s.padj_best.as<double>(), E, act_stride);
     if (rc) return rc;
   }
   if (want_cat_best || row_copy)
@@ -898,6 +971,7 @@ int mdeggs_create(mdeggs_ctx** out, const int* device_ids, int n_dev) {
   memset(&ctx->stats, 0, sizeof ctx->stats);
   if (const char* fp = getenv("MDEGGS_FIT_PATH")) ctx->fit_path_override = atoi(fp);
   if (const char* g = getenv("MDEGGS_GRAPH")) ctx->use_graph = atoi(g);
+  if (const char* g = getenv("MDEGGS_DEBUG_SYNC")) ctx->debug_sync = atoi(g);
   ctx->shards.resize((size_t)n_dev);
   for (int i = 0; i < n_dev; ++i) {
     ctx->shards[(size_t)i].device = device_ids[i];
@@ -944,6 +1018,7 @@ int mdeggs_create_rank(mdeggs_ctx** out, int device_id, int rank, int world, con
   memset(&ctx->stats, 0, sizeof ctx->stats);
   if (const char* fp = getenv("MDEGGS_FIT_PATH")) ctx->fit_path_override = atoi(fp);
   if (const char* g = getenv("MDEGGS_GRAPH")) ctx->use_graph = atoi(g);
+  if (const char* g = getenv("MDEGGS_DEBUG_SYNC")) ctx->debug_sync = atoi(g);
   ctx->shards.resize(1);
   Shard& s = ctx->shards[0];
   s.device = device_id;
@@ -1042,6 +1117,9 @@ int mdeggs_run_omic(mdeggs_ctx* ctx, const mdeggs_problem* in, mdeggs_result* ou
     if ((r = run_collective(ctx, in, out))) return r;
     for (size_t i = 0; i < ctx->shards.size(); ++i)
       if ((r = run_shard_back(ctx, ctx->shards[i], in, out, H, *n_cap, i == 0))) return r;
+    if ((r = run_sig_allreduce(ctx, in, out))) return r;
+    for (size_t i = 0; i < ctx->shards.size(); ++i)
+      if ((r = run_shard_back2(ctx, ctx->shards[i], in, out, H, *n_cap, i == 0))) return r;
     return r;
   };
   int32_t n_nodes = (int32_t)(2 * in->E < (int64_t)in->G ? 2 * in->E : (int64_t)in->G);
@@ -1133,6 +1211,7 @@ int mdeggs_run_omic(mdeggs_ctx* ctx, const mdeggs_problem* in, mdeggs_result* ou
     CU(cudaStreamSynchronize(s.s_main));
   }
   CU(cudaSetDevice(src_device));
+  CU(cudaGetLastError());  // kernel launches are not checked one by one: surface any launch failure here
   Shard& s0 = ctx->shards[0];
   {
     long long host_scal[2] = {0, 0};

@@ -754,8 +754,9 @@ struct BhArgs {
   int64_t E;
   const unsigned long long* n_valid;
   int K, P, ntiles;
-  int p0;               // first percentile handled by blockIdx.y == 0 (segments y -> p = p0 + y / K, c = y % K + 1)
-  const int32_t* best;  // when non-null: p0 := *best - 1 (device-chosen percentile), grid.y == K
+  int p0, p_stride;     // segment y -> percentile p = p0 + (y / K) * p_stride, category c = y % K + 1
+                        // (multi-GPU: rank r adjusts percentiles r, r + world, ...)
+  const int32_t* best;  // when non-null: p := *best - 1 (device-chosen percentile), grid.y == K
 };
 
 __device__ __forceinline__ bool bh_segment(const BhArgs& A, int& p, int& c) {
@@ -764,7 +765,7 @@ __device__ __forceinline__ bool bh_segment(const BhArgs& A, int& p, int& c) {
     base = *A.best - 1;
     if (base < 0) return false;
   }
-  p = base + (int)blockIdx.y / A.K;
+  p = base + ((int)blockIdx.y / A.K) * (A.best ? 1 : A.p_stride);
   c = (int)blockIdx.y % A.K + 1;
   return true;
 }
@@ -993,7 +994,7 @@ __global__ void __launch_bounds__(BH_THREADS) k_bh_final(BhArgs A, int mode, con
     cnt += (q[it] < 0.05);
     if (padj_out) {
       int64_t j = tile0 + (int64_t)threadIdx.x * BH_ITEMS + it;
-      int64_t row = A.best ? 0 : (p - A.p0);
+      int64_t row = A.best ? 0 : p;  // full matrix rows are indexed by the absolute percentile
       padj_out[row * padj_stride + A.sidx[j]] = q[it];
     }
   }

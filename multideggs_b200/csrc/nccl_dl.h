@@ -14,7 +14,8 @@ typedef struct ncclComm* nccl_comm_t;
 typedef struct {
   char internal[128];
 } nccl_unique_id;
-enum { NCCL_INT8 = 0, NCCL_INT32 = 2, NCCL_FLOAT64 = 8 };
+enum { NCCL_INT8 = 0, NCCL_INT32 = 2, NCCL_UINT64 = 5, NCCL_FLOAT64 = 8 };
+enum { NCCL_SUM = 0 };
 
 struct NcclApi {
   void* handle = nullptr;
@@ -23,6 +24,7 @@ struct NcclApi {
   int (*CommInitAll)(nccl_comm_t*, int, const int*) = nullptr;
   int (*CommDestroy)(nccl_comm_t) = nullptr;
   int (*AllGather)(const void*, void*, size_t, int, nccl_comm_t, cudaStream_t) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
   int (*GroupStart)() = nullptr;
   int (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
@@ -43,11 +45,12 @@ struct NcclApi {
     MDEGGS_SYM(CommInitAll, "ncclCommInitAll");
     MDEGGS_SYM(CommDestroy, "ncclCommDestroy");
     MDEGGS_SYM(AllGather, "ncclAllGather");
+    MDEGGS_SYM(AllReduce, "ncclAllReduce");
     MDEGGS_SYM(GroupStart, "ncclGroupStart");
     MDEGGS_SYM(GroupEnd, "ncclGroupEnd");
     MDEGGS_SYM(GetErrorString, "ncclGetErrorString");
 #undef MDEGGS_SYM
-    return GetUniqueId && CommInitRank && CommInitAll && CommDestroy && AllGather && GroupStart && GroupEnd;
+    return GetUniqueId && CommInitRank && CommInitAll && CommDestroy && AllGather && AllReduce && GroupStart && GroupEnd;
   }
 };
 

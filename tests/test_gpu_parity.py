@@ -235,6 +235,19 @@ def test_single_process_multi_gpu_matches_one_gpu(engine):
         for k in a:
             assert np.array_equal(a[k], b[k], equal_nan=True), (K, method, k)
     assert eng2.stats()["n_ranks"] >= 2
+    # best-percentile outputs only: the BH segments are sharded over the ranks and the counts all-reduced;
+    # dense-tile path: every rank computes only the tile rows of its edge block
+    want = _abi.DEFAULT_WANT
+    for fit_path in (0, 1):
+        engine.set_option("fit_path", fit_path)
+        eng2.set_option("fit_path", fit_path)
+        for padj in (_abi.PADJ_BH, _abi.PADJ_HOLM, _abi.PADJ_BONFERRONI):
+            prob = synth.random_problem(300, 50, 2500, 2, 900 + padj, _abi.METHOD_LM, padj)
+            a = engine.run_omic(prob, want)
+            b = eng2.run_omic(prob, want)
+            for k in a:
+                assert np.array_equal(a[k], b[k], equal_nan=True), (fit_path, padj, k)
+    engine.set_option("fit_path", -1)
     eng2.close()
 
 
