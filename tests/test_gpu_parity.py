@@ -30,7 +30,7 @@ def test_bundled_engine_vs_oracle(engine, oracle, bundled, omic, method, padj):
 @pytest.mark.parametrize("G,n,E,K,seed", [
     (40, 10, 60, 2, 1), (64, 22, 200, 2, 2), (100, 100, 500, 2, 3), (300, 1000, 800, 2, 4), (50, 2000, 300, 2, 5),
     (80, 37, 300, 3, 6), (120, 333, 900, 3, 7), (60, 1000, 400, 3, 8), (90, 64, 500, 4, 9), (70, 120, 300, 5, 10),
-    (33, 17, 40, 2, 11), (257, 129, 1025, 3, 12),
+    (33, 17, 40, 2, 11), (257, 129, 1025, 3, 12), (60, 400, 200, 8, 13), (45, 90, 150, 7, 14), (40, 66, 90, 6, 15),
 ])
 @pytest.mark.parametrize("padj", [_abi.PADJ_BH, _abi.PADJ_BONFERRONI, _abi.PADJ_HOLM, _abi.PADJ_HOCHBERG, _abi.PADJ_BY])
 def test_random_lm_aov(engine, oracle, G, n, E, K, seed, padj):
@@ -394,3 +394,29 @@ def test_host_adjusted_methods_through_api(engine, oracle, bundled, padj):
                 assert np.allclose(got[k][col].to_numpy(), exp[k][col].to_numpy(), rtol=1e-9, atol=4.5e-16, equal_nan=True)
         else:
             assert got[k] == exp[k]
+
+
+@pytest.mark.parametrize("n,K,method", [(2600, 2, _abi.METHOD_LM), (2600, 2, _abi.METHOD_RLM), (3300, 3, _abi.METHOD_LM),
+                                        (9000, 2, _abi.METHOD_RLM), (30000, 2, _abi.METHOD_LM)])
+def test_large_sample_counts(engine, oracle, n, K, method):
+    """Segments beyond the register-resident K2 kernel (> 1,024 samples per category: row staged in shared memory),
+    beyond shared memory (30,000 samples: global-memory path), and rlm with the residual-only staging."""
+    prob = synth.random_problem(24, n, 40, K, 1000 + n, method, _abi.PADJ_BH)
+    gpu, ref = _both(engine, oracle, prob)
+    assert_parity(gpu, ref, prob, rtol=1e-8 if method == _abi.METHOD_RLM else 1e-9, what=f"n={n}: ")
+
+
+def test_rlm_too_many_samples_is_reported(engine):
+    prob = synth.random_problem(8, 40000, 6, 2, 77, _abi.METHOD_RLM, _abi.PADJ_BH)
+    with pytest.raises(md.EngineError, match="unsupported"):
+        engine.run_omic(prob)
+
+
+def test_invalid_edge_index_is_reported(engine):
+    prob = synth.random_problem(30, 20, 40, 2, 78)
+    prob.to_idx = prob.to_idx.copy()
+    prob.to_idx[7] = 31                       # > G
+    with pytest.raises(md.EngineError, match="outside 1..G"):
+        engine.run_omic(prob)
+    big = synth.random_problem(30, 20, 40, 2, 79)   # the context stays usable afterwards
+    assert engine.run_omic(big)["best"].shape == (1,)
