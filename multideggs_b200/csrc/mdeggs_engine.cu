@@ -253,7 +253,7 @@ int copy_out(mdeggs_ctx* ctx, Shard& s, void* dst, const void* src, size_t bytes
 // ---- BH / Bonferroni over a block of percentiles (or the device-chosen best one) -----------------
 int run_adjust(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, int n_segments, int p0, int p_stride,
                const int32_t* best_dev, unsigned long long* sig_dev, double* padj_out, int64_t padj_stride,
-               int act_stride) {
+               int act_stride, bool reuse_tiles = false) {
   if (n_segments <= 0) return MDEGGS_OK;
   const int64_t E = in->E;
   const int ntiles = (int)((E + BH_TILE - 1) / BH_TILE);
@@ -272,11 +272,15 @@ int run_adjust(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, int n_segmen
   A.p0 = p0;
   A.p_stride = p_stride;
   A.best = best_dev;
+  A.tot = s.counters.as<unsigned long long>();  // c_tot[P], filled by k_percolate
+  A.reuse_tiles = reuse_tiles ? 1 : 0;
   dim3 grid((unsigned)ntiles, (unsigned)n_segments);
-  LAUNCH(k_bh_count, grid, BH_THREADS, 0, s.s_main, A, s.tile_cnt.as<int32_t>());
-  LAUNCH(k_bh_scan_tiles, n_segments, 256, 0, s.s_main, s.tile_cnt.as<int32_t>(), ntiles, s.tile_base.as<long long>(),
-         s.seg_n.as<long long>());
-  if (in->padj != MDEGGS_PADJ_BONFERRONI) {
+  if (!reuse_tiles) {
+    LAUNCH(k_bh_count, grid, BH_THREADS, 0, s.s_main, A, s.tile_cnt.as<int32_t>());
+    LAUNCH(k_bh_scan_tiles, n_segments, 256, 0, s.s_main, s.tile_cnt.as<int32_t>(), ntiles,
+           s.tile_base.as<long long>(), s.seg_n.as<long long>());
+  }
+  if (in->padj != MDEGGS_PADJ_BONFERRONI && !reuse_tiles) {
     LAUNCH(k_bh_tilemin, grid, BH_THREADS, 0, s.s_main, A, in->padj, s.tile_cnt.as<int32_t>(),
            s.tile_base.as<long long>(), s.seg_n.as<long long>(), s.tile_min.as<double>());
     LAUNCH(k_bh_suffix_min, n_segments, 256, 0, s.s_main, s.tile_min.as<double>(), ntiles, in->padj,
@@ -839,7 +843,10 @@ int run_shard_back2(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const m
   if (want_padj_best && !row_copy) {  // P x E too large to keep: rerun the adjustment for the best percentile only
     LAUNCH(k_fill_f64, (unsigned)(blocks_for(E, 256) < 148u * 16 ? blocks_for(E, 256) : 148u * 16), 256, 0, s.s_main,
            s.padj_best.as<double>(), E, nan(""));
-    int rc = run_adjust(ctx, s, in, K, 0, 1, d_best, nullptr, s.padj_best.as<double>(), E, act_stride);
+    // single rank: the tile partials of every percentile are still there, only the final pass is repeated;
+    // sharded K8: this rank may not own the best percentile, so the whole adjustment is rerun for it
+    int rc = shard_p ? run_adjust(ctx, s, in, K, 0, 1, d_best, nullptr, s.padj_best.as<double>(), E, act_stride)
+                     : run_adjust(ctx, s, in, K, 0, 1, d_best, nullptr, s.padj_best.as<double>(), E, act_stride, true);
     if (rc) return rc;
   }
   if (want_cat_best || row_copy)

@@ -757,16 +757,22 @@ struct BhArgs {
   int p0, p_stride;     // segment y -> percentile p = p0 + (y / K) * p_stride, category c = y % K + 1
                         // (multi-GPU: rank r adjusts percentiles r, r + world, ...)
   const int32_t* best;  // when non-null: p := *best - 1 (device-chosen percentile), grid.y == K
+  const unsigned long long* tot;  // tot_edges[P] from k_percolate: percentiles without tested edges are skipped
+  int reuse_tiles;      // best-percentile pass: reuse the tile partials of the all-percentile pass (segment index
+                        // of percentile p is ((p - p0) / p_stride) * K + c - 1 there)
 };
 
-__device__ __forceinline__ bool bh_segment(const BhArgs& A, int& p, int& c) {
-  int base = A.p0;
-  if (A.best) {
-    base = *A.best - 1;
-    if (base < 0) return false;
-  }
-  p = base + ((int)blockIdx.y / A.K) * (A.best ? 1 : A.p_stride);
+// maps blockIdx.y to (percentile p, category c, segment index `seg` into the tile-partial arrays)
+__device__ __forceinline__ bool bh_segment(const BhArgs& A, int& p, int& c, size_t& seg) {
   c = (int)blockIdx.y % A.K + 1;
+  if (A.best) {
+    p = *A.best - 1;
+    if (p < 0) return false;
+    seg = A.reuse_tiles ? (size_t)((p - A.p0) / A.p_stride) * A.K + (c - 1) : (size_t)blockIdx.y;
+  } else {
+    p = A.p0 + ((int)blockIdx.y / A.K) * A.p_stride;
+    seg = blockIdx.y;
+  }
   return true;
 }
 
@@ -789,7 +795,12 @@ __device__ __forceinline__ void bh_load(const BhArgs& A, int p, int c, int64_t t
 // pass A: members per tile
 __global__ void __launch_bounds__(BH_THREADS) k_bh_count(BhArgs A, int32_t* __restrict__ tile_cnt) {
   int p, c;
-  if (!bh_segment(A, p, c)) return;
+  size_t seg;
+  if (!bh_segment(A, p, c, seg)) return;
+  if (A.tot && A.tot[p] == 0) {  // nothing is tested at this percentile
+    if (threadIdx.x == 0) tile_cnt[seg * A.ntiles + blockIdx.x] = 0;
+    return;
+  }
   typedef cub::BlockReduce<int, BH_THREADS> Reduce;
   __shared__ typename Reduce::TempStorage tmp;
   int flag[BH_ITEMS];
@@ -799,7 +810,7 @@ __global__ void __launch_bounds__(BH_THREADS) k_bh_count(BhArgs A, int32_t* __re
 #pragma unroll
   for (int it = 0; it < BH_ITEMS; ++it) s += flag[it];
   int tot = Reduce(tmp).Sum(s);
-  if (threadIdx.x == 0) tile_cnt[(size_t)blockIdx.y * A.ntiles + blockIdx.x] = tot;
+  if (threadIdx.x == 0) tile_cnt[seg * A.ntiles + blockIdx.x] = tot;
 }
 
 // exclusive scan of the tile counts of each segment (one CTA per segment); seg_n = members of the segment
@@ -858,10 +869,10 @@ __global__ void __launch_bounds__(BH_THREADS) k_bh_tilemin(BhArgs A, int mode, c
                                                           const long long* __restrict__ seg_n,
                                                           double* __restrict__ tile_min) {
   int p, c;
-  if (!bh_segment(A, p, c)) return;
-  if (tile_cnt[(size_t)blockIdx.y * A.ntiles + blockIdx.x] == 0) {  // no member of this segment in the tile
-    if (threadIdx.x == 0)
-      tile_min[(size_t)blockIdx.y * A.ntiles + blockIdx.x] = mode == MDEGGS_PADJ_HOLM ? -INFINITY : INFINITY;
+  size_t seg;
+  if (!bh_segment(A, p, c, seg)) return;
+  if (tile_cnt[seg * A.ntiles + blockIdx.x] == 0) {  // no member of this segment in the tile
+    if (threadIdx.x == 0) tile_min[seg * A.ntiles + blockIdx.x] = mode == MDEGGS_PADJ_HOLM ? -INFINITY : INFINITY;
     return;
   }
   typedef cub::BlockScan<int, BH_THREADS> Scan;
@@ -875,7 +886,6 @@ __global__ void __launch_bounds__(BH_THREADS) k_bh_tilemin(BhArgs A, int mode, c
   bh_load(A, p, c, (int64_t)blockIdx.x * BH_TILE, flag, pv);
   Scan(tmp.scan).InclusiveSum(flag, rank);
   __syncthreads();
-  const size_t seg = blockIdx.y;
   const long long base = tile_base[seg * A.ntiles + blockIdx.x];
   const double n = (double)seg_n[seg];
   const bool fwd_max = mode == MDEGGS_PADJ_HOLM;  // holm: cummax over ascending p; others: cummin from the largest p
@@ -925,8 +935,9 @@ __global__ void __launch_bounds__(BH_THREADS) k_bh_final(BhArgs A, int mode, con
                                                         unsigned long long* __restrict__ sig,
                                                         double* __restrict__ padj_out, int64_t padj_stride) {
   int p, c;
-  if (!bh_segment(A, p, c)) return;
-  if (tile_cnt[(size_t)blockIdx.y * A.ntiles + blockIdx.x] == 0) return;
+  size_t seg;
+  if (!bh_segment(A, p, c, seg)) return;
+  if (tile_cnt[seg * A.ntiles + blockIdx.x] == 0) return;
   typedef cub::BlockScan<int, BH_THREADS> ScanI;
   typedef cub::BlockScan<double, BH_THREADS> ScanD;
   typedef cub::BlockReduce<int, BH_THREADS> Reduce;
@@ -939,7 +950,6 @@ __global__ void __launch_bounds__(BH_THREADS) k_bh_final(BhArgs A, int mode, con
   double pv[BH_ITEMS], q[BH_ITEMS];
   const int64_t tile0 = (int64_t)blockIdx.x * BH_TILE;
   bh_load(A, p, c, tile0, flag, pv);
-  const size_t seg = blockIdx.y;
   const double n = (double)seg_n[seg];
   if (mode != MDEGGS_PADJ_BONFERRONI) {
     const bool fwd_max = mode == MDEGGS_PADJ_HOLM;
