@@ -392,6 +392,35 @@ def run_cuda(args) -> None:
         if world > 1:
             eng5.close()
 
+    # ---- also: rlm stress (K6 batched IRLS), FP64-pipe roofline against this GPU's own DFMA peak (rank 0) ----
+    if rank == 0 and not args.no_rlm:
+        from multideggs_b200 import _abi as A
+        rng = np.random.default_rng(7)
+        grp2 = (np.arange(n) % 2 + 1).astype(np.int32)
+        rng.shuffle(grp2)
+        rprob = A.Problem(assay=prob.assay, from_idx=prob.from_idx, to_idx=prob.to_idx, group=grp2, K=2, pct=prob.pct,
+                          method=A.METHOD_RLM, padj=A.PADJ_BH)
+        eng.set_option("graph", 0)
+        want_r = ("iters", "status", "best", "tot_edges")
+        res_r = eng.run_omic(rprob, want_r)                       # warm-up + iteration counts
+        fit_ms_r = []
+        for _ in range(3):
+            eng.run_omic(rprob, want_r)
+            fit_ms_r.append(eng.stats()["ms_fit"])
+        eng.set_option("graph", 1)
+        it = res_r["iters"][res_r["status"] != A.EDGE_SELFLOOP].astype(np.float64)
+        flops_r = float(np.sum(n * (18.0 + 20.0 * it)))          # SURVEY section 8 d: n (18 + 20 iters) per pair fit
+        peak64 = eng.fp64_peak_tflops()
+        ms_r = float(np.median(fit_ms_r))
+        line.setdefault("also", {})["rlm_stress"] = {
+            "workload": f"{name} matrix and network, 2 shuffled categories, regression_method='rlm'", "edges": int(E),
+            "samples": int(n), "kernel": "k_fit_rlm", "kernel_ms": ms_r, "pair_fits_per_s": E / (ms_r * 1e-3),
+            "mean_irls_iterations": float(it.mean()),
+            "roofline": {"bound": "fp64", "achieved": flops_r / (ms_r * 1e-3) / 1e12, "peak": peak64, "unit": "TFLOP/s",
+                         "frac": flops_r / (ms_r * 1e-3) / 1e12 / peak64,
+                         "peak_source": "own DFMA-chain microbenchmark in this run (mdeggs_measure_fp64_peak)",
+                         "flops_model": "n (18 + 20 iters) per pair fit, FMA = 2 flops; the exact MAD selection is not credited"}}
+
     if rank == 0:
         print(json.dumps(line), flush=True)
     if dist is not None:
@@ -408,6 +437,7 @@ def main() -> None:
     ap.add_argument("--workload", default=None, help="cfg3 (default) | cfg3-small | cfg5 | cfg5-small")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-cfg5", action="store_true", help="skip the config-5 'also' leg")
+    ap.add_argument("--no-rlm", action="store_true", help="skip the rlm stress 'also' leg")
     args = ap.parse_args()
     if args.impl == "reference":
         if args.steps > 5:

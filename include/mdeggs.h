@@ -149,6 +149,9 @@ int mdeggs_run_omic(mdeggs_ctx* ctx, const mdeggs_problem* in, mdeggs_result* ou
 int mdeggs_pair_features(mdeggs_ctx* ctx, const double* x, int64_t ldx, int32_t n, const int32_t* a,
                          const int32_t* b, int32_t n_pairs, int32_t ratio, int32_t mem, double* out);
 
+/* Measures this GPU's FP64 FMA peak with a register-only DFMA-chain kernel (TFLOP/s): the denominator of the
+ * rlm (K6) roofline, which is FP64-pipe bound (SURVEY section 8 d). */
+int mdeggs_measure_fp64_peak(mdeggs_ctx* ctx, double* tflops_out);
 int mdeggs_last_stats(const mdeggs_ctx* ctx, mdeggs_stats* out);
 /* Engine options: "graph" (1 = replay the compute phase from a CUDA graph when a call repeats with identical
  * shapes and buffers [default], 0 = always launch eagerly, which also keeps the per-stage timings);

@@ -1371,6 +1371,26 @@ static int dev_math(mdeggs_ctx* ctx, int which, const double* x, const double* a
   return rc;
 }
 
+int mdeggs_measure_fp64_peak(mdeggs_ctx* ctx, double* tflops_out) {
+  if (!ctx || !tflops_out) return MDEGGS_EINVAL;
+  Shard& s = ctx->shards[0];
+  CU(cudaSetDevice(s.device));
+  CU(s.small_out.ensure(64));
+  const int iters = 8192, blocks = 148 * 8, threads = 256;
+  float best_ms = 1e30f;
+  for (int rep = 0; rep < 4; ++rep) {  // first repetition warms up
+    CU(cudaEventRecord(s.ev[EV_Q0], s.s_main));
+    LAUNCH(k_dfma_peak, blocks, threads, 0, s.s_main, iters, 1.0 + rep, s.small_out.as<double>());
+    CU(cudaEventRecord(s.ev[EV_Q1], s.s_main));
+    CU(cudaStreamSynchronize(s.s_main));
+    float ms = ev_ms(s.ev[EV_Q0], s.ev[EV_Q1]);
+    if (rep > 0 && ms < best_ms) best_ms = ms;
+  }
+  const double flops = 2.0 * 16.0 * (double)iters * (double)blocks * (double)threads;
+  *tflops_out = flops / ((double)best_ms * 1e-3) / 1e12;
+  return MDEGGS_OK;
+}
+
 int mdeggs_dev_pt(mdeggs_ctx* ctx, const double* x, const double* df, int64_t n, double* out) {
   return dev_math(ctx, 0, x, df, nullptr, n, out);
 }

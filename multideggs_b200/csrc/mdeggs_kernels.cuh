@@ -1062,6 +1062,22 @@ __global__ void k_pair_features(const double* __restrict__ x, int64_t ldx, int n
   out[i] = isfinite(r) ? r : 0.0;
 }
 
+// FP64 FMA peak of this GPU (denominator of the rlm roofline, SURVEY §8 d): 16 independent DFMA chains per thread
+__global__ void __launch_bounds__(256) k_dfma_peak(int iters, double seed, double* __restrict__ sink) {
+  double a[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) a[j] = seed + (double)(threadIdx.x + j);
+  const double m = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) a[j] = fma(a[j], m, c);
+  }
+  double t = 0.0;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) t += a[j];
+  if (t == 12345.678) sink[0] = t;  // never true: keeps the chains alive
+}
+
 // scalar math twins for tests
 __global__ void k_dev_math(int which, const double* __restrict__ x, const double* __restrict__ a,
                            const double* __restrict__ b, int64_t n, double* __restrict__ out) {

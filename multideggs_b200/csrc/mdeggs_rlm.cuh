@@ -265,11 +265,328 @@ __global__ void __launch_bounds__(256) k_fit_rlm(const double* __restrict__ D, S
   }
 }
 
+// Register-resident variant for npad <= 32 * ITEMS (n up to ~1,000): rows A and B are staged once in shared memory,
+// |residual| keys live in registers, the MAD median is a register-only narrowing selection (warp_select_reg), and the
+// irls.delta convergence norm needs NO pass: with r_old - r_new = (i_new - i_old) + (s_new - s_old) a inside a category,
+//   sum (r_old - r_new)^2 = n di^2 + 2 di ds sum(a) + ds^2 sum(a^2),   sum r_old^2 = Syy - 2 s Sxy + s^2 Sxx + n (mb - i - s ma)^2
+// are closed forms in the unweighted per-gene moments of K2.  Per IRLS iteration: one pass for the residual keys, the
+// selection, one pass for the Huber weights + 5 weighted moments per category.
+template <int ITEMS>
+__global__ void __launch_bounds__(256) k_fit_rlm_reg(const double* __restrict__ D, SegLayout L,
+                                                     const int32_t* __restrict__ from, const int32_t* __restrict__ to,
+                                                     const int32_t* __restrict__ node_of_row,
+                                                     const double* __restrict__ mean, const double* __restrict__ sxx,
+                                                     const uint8_t* __restrict__ bad, int64_t e_lo, int64_t e_hi,
+                                                     int tested_coef, int cov_mode, double* __restrict__ stat,
+                                                     int32_t* __restrict__ status, double* __restrict__ coef,
+                                                     int32_t* __restrict__ iters, const int32_t* __restrict__ err) {
+  extern __shared__ double smem[];  // per warp: A row, B row (npad doubles each)
+  __shared__ unsigned long long s_cand[8][32];
+  if (*err) return;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  double* sa = smem + (size_t)wib * 2 * L.npad;
+  double* sb = sa + L.npad;
+  const double kh = 1.345;
+  const int n = L.n, c0 = L.cnt[0], c1 = L.cnt[1], o1 = L.off[1];
+  // per-lane validity / category of the positions lane + 32 j (same for every edge)
+  unsigned vmask = 0, cmask = 0;
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j) {
+    const int pos = lane + 32 * j;
+    const bool in1 = pos >= o1;
+    const bool valid = in1 ? (pos < o1 + c1) : (pos < c0);
+    vmask |= (unsigned)valid << j;
+    cmask |= (unsigned)in1 << j;
+  }
+  for (int64_t e = e_lo + (int64_t)blockIdx.x * wpb + wib; e < e_hi; e += (int64_t)gridDim.x * wpb) {
+    const int ra = from[e] - 1, rb = to[e] - 1;
+    const int a = node_of_row[ra], b = node_of_row[rb];
+    auto put = [&](double st_v, int code, int it) {
+      if (lane == 0) {
+        stat[e] = st_v;
+        status[e] = code;
+        iters[e] = it;
+        if (coef)
+          for (int j = 0; j < 4; ++j) coef[(size_t)e * 4 + j] = nan("");
+      }
+    };
+    if (ra == rb || bad[a] || bad[b]) {
+      bool self = (ra == rb) && !bad[a];
+      put(self ? 0.0 : nan(""), self ? MDEGGS_EDGE_SELFLOOP : MDEGGS_EDGE_NONFINITE, 0);
+      continue;
+    }
+    double ma[2], mb[2], sxa[2], syb[2];
+    bool singular = false;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      ma[k] = mean[(size_t)a * 2 + k];
+      mb[k] = mean[(size_t)b * 2 + k];
+      sxa[k] = sxx[(size_t)a * 2 + k];
+      syb[k] = sxx[(size_t)b * 2 + k];
+      if (L.cnt[k] < 2 || !(sxa[k] > 1e-14 * (sxa[k] + (double)L.cnt[k] * ma[k] * ma[k]))) singular = true;
+    }
+    if (singular) {  // rlm(): "'x' is singular: singular fits are not implemented in 'rlm'"
+      put(nan(""), MDEGGS_EDGE_SINGULAR, 0);
+      continue;
+    }
+    if (syb[0] == 0.0 && syb[1] == 0.0) {  // constant response: exact fit
+      put(0.0, MDEGGS_EDGE_SELFLOOP, 0);
+      continue;
+    }
+    __syncwarp();
+    {
+      const double* ga = D + (size_t)a * L.npad;
+      const double* gb = D + (size_t)b * L.npad;
+      for (int i = lane; i < L.npad; i += 32) {
+        sa[i] = __ldg(ga + i);
+        sb[i] = __ldg(gb + i);
+      }
+    }
+    __syncwarp();
+    const double nk[2] = {(double)c0, (double)c1};
+    // ---- init = "ls" ----
+    double sxy[2];
+    {
+      double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+      for (int j = 0; j < ITEMS; ++j) {
+        if (!(vmask >> j & 1)) continue;
+        const int pos = lane + 32 * j;
+        const int c = cmask >> j & 1;
+        const double t = (sa[pos] - ma[c]) * (sb[pos] - mb[c]);
+        if (c) acc1 += t;
+        else acc0 += t;
+      }
+      sxy[0] = warp_sum(acc0);
+      sxy[1] = warp_sum(acc1);
+    }
+    double slope[2], icpt[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      slope[k] = sxy[k] / sxa[k];
+      icpt[k] = mb[k] - slope[k] * ma[k];
+    }
+    unsigned long long keys[ITEMS];
+    unsigned long long kmin, kmax;
+    auto residual_keys = [&]() {  // |b - icpt_c - slope_c a| as order-preserving bit patterns; padding -> ~0
+      kmin = ~0ull;
+      kmax = 0ull;
+#pragma unroll
+      for (int j = 0; j < ITEMS; ++j) {
+        unsigned long long k = ~0ull;
+        if (vmask >> j & 1) {
+          const int pos = lane + 32 * j;
+          const int c = cmask >> j & 1;
+          const double r = sb[pos] - icpt[c] - slope[c] * sa[pos];
+          k = (unsigned long long)__double_as_longlong(fabs(r));
+          kmin = k < kmin ? k : kmin;
+          kmax = k > kmax ? k : kmax;
+        }
+        keys[j] = k;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long x = __shfl_xor_sync(0xffffffffu, kmin, o), y = __shfl_xor_sync(0xffffffffu, kmax, o);
+        kmin = x < kmin ? x : kmin;
+        kmax = y > kmax ? y : kmax;
+      }
+    };
+    auto median_abs = [&]() -> double {
+      if (n & 1) return __longlong_as_double((long long)warp_select_reg<ITEMS>(keys, n / 2, kmin, kmax, n, s_cand[wib], lane));
+      unsigned long long k1 = warp_select_reg<ITEMS>(keys, n / 2 - 1, kmin, kmax, n, s_cand[wib], lane);
+      int c_le = 0;
+      unsigned long long nxt = ~0ull;
+#pragma unroll
+      for (int j = 0; j < ITEMS; ++j) {
+        c_le += (keys[j] <= k1);
+        if (keys[j] > k1 && keys[j] < nxt) nxt = keys[j];
+      }
+      c_le = __reduce_add_sync(0xffffffffu, c_le);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long other = __shfl_xor_sync(0xffffffffu, nxt, o);
+        nxt = other < nxt ? other : nxt;
+      }
+      unsigned long long k2 = (c_le > n / 2) ? k1 : nxt;
+      return __ddiv_rn(__dadd_rn(__longlong_as_double((long long)k1), __longlong_as_double((long long)k2)), 2.0);
+    };
+    double scale = 0.0;
+    bool done = false, zero_scale = false;
+    int it = 0;
+    for (it = 1; it <= 20; ++it) {
+      residual_keys();
+      scale = median_abs() / 0.6745;
+      if (scale == 0.0) {
+        zero_scale = true;
+        done = true;
+        break;
+      }
+      // sum of squared residuals under the current parameters (closed form, unweighted moments)
+      double old_ss = 0.0;
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const double off = mb[k] - icpt[k] - slope[k] * ma[k];
+        old_ss += syb[k] - 2.0 * slope[k] * sxy[k] + slope[k] * slope[k] * sxa[k] + nk[k] * off * off;
+      }
+      double acc[2][5] = {{0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}};
+#pragma unroll
+      for (int j = 0; j < ITEMS; ++j) {
+        if (!(vmask >> j & 1)) continue;
+        const int pos = lane + 32 * j;
+        const int c = cmask >> j & 1;
+        const double u = __longlong_as_double((long long)keys[j]) / scale;  // |r| / s
+        const double w = (u <= kh) ? 1.0 : kh / u;                              // psi.huber weight pmin(1, k/|u|)
+        const double da = sa[pos] - ma[c], db = sb[pos] - mb[c];
+        const double wda = w * da;
+        if (c) {
+          acc[1][0] += w;
+          acc[1][1] += wda;
+          acc[1][2] = fma(w, db, acc[1][2]);
+          acc[1][3] = fma(wda, da, acc[1][3]);
+          acc[1][4] = fma(wda, db, acc[1][4]);
+        } else {
+          acc[0][0] += w;
+          acc[0][1] += wda;
+          acc[0][2] = fma(w, db, acc[0][2]);
+          acc[0][3] = fma(wda, da, acc[0][3]);
+          acc[0][4] = fma(wda, db, acc[0][4]);
+        }
+      }
+      double diff = 0.0;
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const double sw = warp_sum(acc[k][0]), swa = warp_sum(acc[k][1]), swb = warp_sum(acc[k][2]);
+        const double swaa = warp_sum(acc[k][3]), swab = warp_sum(acc[k][4]);
+        const double dma = swa / sw, dmb = swb / sw;
+        const double wsxx = swaa - swa * dma, wsxy = swab - swa * dmb;
+        const double s_new = wsxy / wsxx;
+        const double i_new = (mb[k] + dmb) - s_new * (ma[k] + dma);
+        const double di = i_new - icpt[k], ds = s_new - slope[k];
+        const double suma = nk[k] * ma[k], suma2 = sxa[k] + nk[k] * ma[k] * ma[k];
+        diff += nk[k] * di * di + 2.0 * di * ds * suma + ds * ds * suma2;
+        slope[k] = s_new;
+        icpt[k] = i_new;
+      }
+      const double conv = sqrt(fmax(diff, 0.0) / fmax(old_ss, 1e-20));  // irls.delta
+      if (conv <= 1e-4) {
+        done = true;
+        break;
+      }
+    }
+    if (it > 20) it = 20;
+    if (zero_scale) {
+      put(nan(""), MDEGGS_EDGE_ZERO_SCALE, it);
+      continue;
+    }
+    // ---- summary.rlm + Wald F of coefficient `tested_coef` (f.robftest) ----
+    residual_keys();  // final residuals, scale of the last iteration
+    double S = 0.0, npp = 0.0;
+    double fw[2][3] = {{0, 0, 0}, {0, 0, 0}};
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+      if (!(vmask >> j & 1)) continue;
+      const int pos = lane + 32 * j;
+      const int c = cmask >> j & 1;
+      const double ar = __longlong_as_double((long long)keys[j]);
+      const double u = ar / scale;
+      const double w = (u <= kh) ? 1.0 : kh / u;
+      const double rw = ar * w;
+      S = fma(rw, rw, S);
+      npp += (u <= kh) ? 1.0 : 0.0;
+      const double da = sa[pos] - ma[c];
+      const double wda = w * da;
+      if (c) {
+        fw[1][0] += w;
+        fw[1][1] += wda;
+        fw[1][2] = fma(wda, da, fw[1][2]);
+      } else {
+        fw[0][0] += w;
+        fw[0][1] += wda;
+        fw[0][2] = fma(wda, da, fw[0][2]);
+      }
+    }
+    S = warp_sum(S);
+    npp = warp_sum(npp);
+    double W2[2], wa2[2], waa2[2], sumw = 0.0;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      W2[k] = warp_sum(fw[k][0]);
+      wa2[k] = warp_sum(fw[k][1]);
+      waa2[k] = warp_sum(fw[k][2]);
+      sumw += W2[k];
+    }
+    const double rdf = (double)(n - 4);
+    S /= rdf;
+    const double mn = npp / (double)n;
+    const double var_pp = (double)n * mn * (1.0 - mn) / (double)(n - 1);
+    const double kappa = 1.0 + 4.0 * var_pp / ((double)n * mn * mn);
+    const double stddev = sqrt(S) * (kappa / mn);
+    double v_icpt[2], v_slope[2];
+    double cov_scale = 1.0;
+    if (cov_mode == MDEGGS_RLM_COV_XTWX) {
+      cov_scale = sumw / (double)n;  // X~ = X sqrt(w / mean(w))  =>  cov.unscaled = mean(w) (X'WX)^-1
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        double dm = wa2[k] / W2[k];
+        double mk = ma[k] + dm, sx = waa2[k] - wa2[k] * dm;
+        v_icpt[k] = 1.0 / W2[k] + mk * mk / sx;
+        v_slope[k] = 1.0 / sx;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        v_icpt[k] = 1.0 / nk[k] + ma[k] * ma[k] / sxa[k];
+        v_slope[k] = 1.0 / sxa[k];
+      }
+    }
+    const double beta[4] = {icpt[0], slope[0], icpt[1] - icpt[0], slope[1] - slope[0]};
+    const double cov[4] = {v_icpt[0], v_slope[0], v_icpt[0] + v_icpt[1], v_slope[0] + v_slope[1]};
+    const int v = tested_coef - 1;
+    const double var_v = stddev * stddev * cov_scale * cov[v];
+    const double F = beta[v] * beta[v] / var_v;
+    if (lane == 0) {
+      stat[e] = F;
+      status[e] = done ? MDEGGS_EDGE_OK : MDEGGS_EDGE_NOT_CONVERGED;
+      iters[e] = it;
+      if (coef)
+        for (int j = 0; j < 4; ++j) coef[(size_t)e * 4 + j] = beta[j];
+    }
+  }
+}
+
+template <int ITEMS>
+inline void launch_fit_rlm_reg(cudaStream_t stream, const double* D, const SegLayout& L, const int32_t* from,
+                               const int32_t* to, const int32_t* node_of_row, const double* mean, const double* sxx,
+                               const uint8_t* bad, int64_t e_lo, int64_t e_hi, int tested_coef, int cov_mode, double* stat,
+                               int32_t* status, double* coef, int32_t* iters, const int32_t* err) {
+  const size_t per_warp = (size_t)L.npad * 16;
+  const int wpb = 8;
+  const size_t smem = per_warp * wpb;
+  int64_t want = (e_hi - e_lo + wpb - 1) / wpb;
+  unsigned grid = (unsigned)(want < 148 * 32 ? want : 148 * 32);
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(k_fit_rlm_reg<ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  k_fit_rlm_reg<ITEMS><<<grid, wpb * 32, smem, stream>>>(D, L, from, to, node_of_row, mean, sxx, bad, e_lo, e_hi,
+                                                        tested_coef, cov_mode, stat, status, coef, iters, err);
+}
+
 // returns 0 on success, non-zero if even the residual-only variant does not fit in shared memory
 inline int launch_fit_rlm(int64_t& launches, cudaStream_t stream, const double* D, const SegLayout& L,
                           const int32_t* from, const int32_t* to, const int32_t* node_of_row, const double* mean,
                           const double* sxx, const uint8_t* bad, int64_t e_lo, int64_t e_hi, int tested_coef,
                           int cov_mode, double* stat, int32_t* status, double* coef, int32_t* iters, const int32_t* err) {
+  if (L.npad <= 32 * 32) {  // register-resident keys: n up to ~1,000 samples
+#define MDEGGS_RLM(IT)                                                                                                 \
+  launch_fit_rlm_reg<IT>(stream, D, L, from, to, node_of_row, mean, sxx, bad, e_lo, e_hi, tested_coef, cov_mode, stat, \
+                         status, coef, iters, err)
+    if (L.npad <= 32 * 4) MDEGGS_RLM(4);
+    else if (L.npad <= 32 * 8) MDEGGS_RLM(8);
+    else if (L.npad <= 32 * 16) MDEGGS_RLM(16);
+    else MDEGGS_RLM(32);
+#undef MDEGGS_RLM
+    ++launches;
+    return 0;
+  }
   const size_t budget = 200 * 1024;
   const size_t row = (size_t)L.npad * 8;
   bool cache = 3 * row * 2 <= budget;  // at least two warps per CTA with A, B, r resident

@@ -21,7 +21,7 @@ _LIB: C.CDLL | None = None
 # every symbol include/mdeggs.h declares (tests check the library exports all of them)
 ABI_SYMBOLS = (
     "mdeggs_create", "mdeggs_create_rank", "mdeggs_nccl_unique_id", "mdeggs_destroy", "mdeggs_run_omic",
-    "mdeggs_pair_features", "mdeggs_last_stats", "mdeggs_set_option", "mdeggs_last_error", "mdeggs_strerror", "mdeggs_abi_version",
+    "mdeggs_pair_features", "mdeggs_measure_fp64_peak", "mdeggs_last_stats", "mdeggs_set_option", "mdeggs_last_error", "mdeggs_strerror", "mdeggs_abi_version",
     "mdeggs_dev_pt", "mdeggs_dev_pf_upper", "mdeggs_dev_p_two_sided_ref",
 )
 
@@ -48,6 +48,7 @@ def load_library() -> C.CDLL:
     L.mdeggs_pair_features.argtypes = [vp, vp, i64, C.c_int32, vp, vp, C.c_int32, C.c_int32, C.c_int32, vp]
     L.mdeggs_last_stats.argtypes = [vp, C.POINTER(_abi.CStats)]
     L.mdeggs_set_option.argtypes = [vp, C.c_char_p, i64]
+    L.mdeggs_measure_fp64_peak.argtypes = [vp, C.POINTER(C.c_double)]
     L.mdeggs_last_error.argtypes = [vp]
     L.mdeggs_last_error.restype = C.c_char_p
     L.mdeggs_strerror.argtypes = [i]
@@ -133,6 +134,12 @@ class Engine:
     def set_option(self, name: str, value: int) -> None:
         """"graph": 1/0 CUDA-graph replay of repeated identical calls; "fit_path": -1 auto, 0 streaming, 1 dense."""
         self._check(self._lib.mdeggs_set_option(self._ctx, name.encode(), int(value)), "mdeggs_set_option")
+
+    def fp64_peak_tflops(self) -> float:
+        """Measured FP64 FMA peak of the GPU (DFMA-chain microbenchmark)."""
+        v = C.c_double()
+        self._check(self._lib.mdeggs_measure_fp64_peak(self._ctx, C.byref(v)), "mdeggs_measure_fp64_peak")
+        return v.value
 
     def stats(self) -> dict:
         st = _abi.CStats()
