@@ -80,16 +80,15 @@ struct Shard {
     if (e == cudaSuccess) h_stage_cap = bytes + 256;
     return e;
   }
-  DevBuf assay, from, to, flags, excl, node_of_row, rowlist, scal, src_of_pos, pct, cutoff, D, keys, keys_sorted,
-      cub_tmp, cub_tmp2, mean, sxx, med, bad, stat, status, p_edge, coef, iters, act, counters, sortk, sortk2, idx,
+  DevBuf assay, from, to, flags, excl, node_of_row, rowlist, scal, src_of_pos, pct, cutoff, D, cub_tmp, mean, sxx, med, bad, stat, status, p_edge, coef, iters, act, counters, sortk, sortk2, idx,
       idx2, ps, sa, sb, tile_cnt, tile_base, seg_n, tile_min, tile_carry, padj_best, cat_best, cat, padj, med_out,
-      small_out, rlm_ws, rsel_hist, rsel_state, rsel_cand, dense_S, cf_tab, sxy;
+      small_out, rsel_hist, rsel_state, rsel_cand, dense_S, cf_tab, sxy;
   void release_all() {
     DevBuf* all[] = {&assay, &from, &to, &flags, &excl, &node_of_row, &rowlist, &scal, &src_of_pos, &pct, &cutoff,
-                     &D, &keys, &keys_sorted, &cub_tmp, &cub_tmp2, &mean, &sxx, &med, &bad, &stat, &status, &p_edge,
+                     &D, &cub_tmp, &mean, &sxx, &med, &bad, &stat, &status, &p_edge,
                      &coef, &iters, &act, &counters, &sortk, &sortk2, &idx, &idx2, &ps, &sa, &sb, &tile_cnt,
                      &tile_base, &seg_n, &tile_min, &tile_carry, &padj_best, &cat_best, &cat, &padj, &med_out,
-                     &small_out, &rlm_ws, &rsel_hist, &rsel_state, &rsel_cand, &dense_S, &cf_tab, &sxy};
+                     &small_out, &rsel_hist, &rsel_state, &rsel_cand, &dense_S, &cf_tab, &sxy};
     for (DevBuf* b : all) b->release();
   }
 };

@@ -669,22 +669,6 @@ __global__ void __launch_bounds__(256) k_percolate(const int32_t* __restrict__ f
   }
 }
 
-// cat row of one percentile chosen on the device (best)
-__global__ void k_cat_row(const int32_t* __restrict__ from, const int32_t* __restrict__ to,
-                          const int32_t* __restrict__ node_of_row, const uint8_t* __restrict__ act, int act_stride,
-                          int64_t E, const int32_t* __restrict__ best, int8_t* __restrict__ cat_out,
-                          const int32_t* __restrict__ err) {
-  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= E || *err) return;
-  int p = *best - 1;
-  int c = 0;
-  if (p >= 0) {
-    int a = node_of_row[from[e] - 1], b = node_of_row[to[e] - 1];
-    c = edge_category(act[(size_t)p * act_stride + a], act[(size_t)p * act_stride + b]);
-  }
-  cat_out[e] = (int8_t)c;
-}
-
 // rows of the device-chosen best percentile: category row (recomputed from the masks) and, when the adjusted
 // values of every percentile are still in the scratch matrix, its p.adj row (else a BH pass is rerun for it)
 __global__ void k_best_rows(const int32_t* __restrict__ from, const int32_t* __restrict__ to,
