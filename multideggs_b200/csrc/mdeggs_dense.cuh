@@ -129,13 +129,13 @@ __global__ void __launch_bounds__(256, 1) k_dense_moments(const double* __restri
 }
 
 // [min, max] over this rank's edges of the smaller node index of the edge: the rows of S it will read
-__global__ void k_edge_row_range(const int32_t* __restrict__ from, const int32_t* __restrict__ to,
-                                 const int32_t* __restrict__ node_of_row, int64_t e_lo, int64_t e_hi,
+__global__ void k_edge_row_range(const int32_t* __restrict__ ea, const int32_t* __restrict__ eb,
+                                 int64_t e_lo, int64_t e_hi,
                                  int32_t* __restrict__ row_range, const int32_t* __restrict__ err) {
   if (*err) return;
   int lo = 0x7fffffff, hi = -1;
   for (int64_t e = e_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < e_hi; e += (int64_t)gridDim.x * blockDim.x) {
-    int a = node_of_row[from[e] - 1], b = node_of_row[to[e] - 1];
+    int a = ea[e], b = eb[e];
     int i = a < b ? a : b;
     lo = i < lo ? i : lo;
     hi = i > hi ? i : hi;

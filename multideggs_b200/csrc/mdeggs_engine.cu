@@ -59,7 +59,7 @@ struct DevBuf {
 enum Ev { EV_START, EV_H2D, EV_GATHER, EV_STATS, EV_FIT, EV_TAIL, EV_COLL, EV_PERC, EV_ADJ, EV_END, EV_Q0, EV_Q1, EV_COUNT };
 
 // scalar slots in the `scal` buffer (8-byte each)
-enum Scal { SC_NNODES = 0, SC_ERR = 1, SC_BEST = 2, SC_NVALID = 3, SC_ROWLO = 4, SC_ROWHI = 5, SC_COUNT = 8 };
+enum Scal { SC_NNODES = 0, SC_ERR = 1, SC_BEST = 2, SC_NVALID = 3, SC_ROWLO = 4, SC_ROWHI = 5, SC_DONE = 6, SC_COUNT = 8 };
 
 struct Shard {
   int device = 0, rank = 0, world = 1;
@@ -80,11 +80,11 @@ struct Shard {
     if (e == cudaSuccess) h_stage_cap = bytes + 256;
     return e;
   }
-  DevBuf assay, from, to, flags, excl, node_of_row, rowlist, scal, src_of_pos, pct, cutoff, D, cub_tmp, mean, sxx, med, bad, stat, status, p_edge, coef, iters, act, counters, sortk, sortk2, idx,
+  DevBuf assay, from, to, ea, eb, excl, node_of_row, rowlist, scal, src_of_pos, pct, cutoff, D, cub_tmp, mean, sxx, med, bad, stat, status, p_edge, coef, iters, act, counters, sortk, sortk2, idx,
       idx2, ps, sa, sb, tile_cnt, tile_base, seg_n, tile_min, tile_carry, padj_best, cat_best, cat, padj, med_out,
       small_out, rsel_hist, rsel_state, rsel_cand, dense_S, cf_tab, sxy;
   void release_all() {
-    DevBuf* all[] = {&assay, &from, &to, &flags, &excl, &node_of_row, &rowlist, &scal, &src_of_pos, &pct, &cutoff,
+    DevBuf* all[] = {&assay, &from, &to, &ea, &eb, &excl, &node_of_row, &rowlist, &scal, &src_of_pos, &pct, &cutoff,
                      &D, &cub_tmp, &mean, &sxx, &med, &bad, &stat, &status, &p_edge,
                      &coef, &iters, &act, &counters, &sortk, &sortk2, &idx, &idx2, &ps, &sa, &sb, &tile_cnt,
                      &tile_base, &seg_n, &tile_min, &tile_carry, &padj_best, &cat_best, &cat, &padj, &med_out,
@@ -121,6 +121,16 @@ struct mdeggs_ctx {
   int64_t graph_launches = 0;
   int64_t rsel_cap_override = 0;  // option "rsel_cap": shrink the candidate list to exercise the overflow path (tests)
   int fit_path_override = -1;  // -1 auto, 0 force streaming, 1 force dense (MDEGGS_FIT_PATH, tests)
+  // MDEGGS_TRACE=1 / option "trace": an event after every eager launch, timeline printed to stderr after the call
+  int trace = 0;
+  struct TraceRec {
+    const char* name;
+    cudaStream_t stream;
+    cudaEvent_t ev;
+  };
+  std::vector<TraceRec> trace_recs;
+  std::vector<cudaEvent_t> trace_pool;
+  size_t trace_used = 0;
 };
 
 namespace {
@@ -160,10 +170,23 @@ void set_err(mdeggs_ctx* c, const char* fmt, ...) {
     if (!ctx->capturing) CU(cudaEventRecord((ev), (stream))); \
   } while (0)
 
+void trace_mark(mdeggs_ctx* ctx, const char* name, cudaStream_t stream) {
+  if (!ctx->trace || ctx->capturing) return;
+  if (ctx->trace_used == ctx->trace_pool.size()) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    ctx->trace_pool.push_back(e);
+  }
+  cudaEvent_t e = ctx->trace_pool[ctx->trace_used++];
+  cudaEventRecord(e, stream);
+  ctx->trace_recs.push_back({name, stream, e});
+}
+
 #define LAUNCH(kernel, grid, block, smem, stream, ...)                                         \
   do {                                                                                         \
     kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                                \
     ++ctx->launches;                                                                           \
+    if (ctx->trace) trace_mark(ctx, #kernel, stream);                                      \
     if (ctx->debug_sync && !ctx->capturing) { /* MDEGGS_DEBUG_SYNC=1: pinpoint a failing launch */ \
       cudaError_t le_ = cudaGetLastError();                                                    \
       if (le_ == cudaSuccess) le_ = cudaStreamSynchronize(stream);                             \
@@ -227,8 +250,8 @@ void launch_fit_stream(mdeggs_ctx* ctx, Shard& s, const SegLayout& L, int64_t e_
   int64_t want_blocks = (ne + 7) / 8;  // 8 warps per CTA, one edge per warp per trip
   int64_t cap = 148 * 8 * 16;          // at most 16 waves of 8 CTAs/SM; warps loop beyond that
   unsigned grid = (unsigned)(want_blocks < cap ? want_blocks : cap);
-  LAUNCH(k_fit_stream<K>, grid, 256, 0, s.s_main, s.D.as<double>(), L, s.from.as<int32_t>(), s.to.as<int32_t>(),
-         s.node_of_row.as<int32_t>(), s.mean.as<double>(), s.bad.as<uint8_t>(), e_lo, e_hi, s.sxy.as<double>(),
+  LAUNCH(k_fit_stream<K>, grid, 256, 0, s.s_main, s.D.as<double>(), L, s.ea.as<int32_t>(), s.eb.as<int32_t>(),
+         s.mean.as<double>(), s.bad.as<uint8_t>(), e_lo, e_hi, s.sxy.as<double>(),
          s.scal.as<int32_t>() + 2 * SC_ERR);
 }
 
@@ -236,7 +259,7 @@ template <int K>
 void launch_finish(mdeggs_ctx* ctx, Shard& s, const SegLayout& L, int src, int nn, int64_t e_lo, int64_t e_hi, int mode,
                    double df1, double df2, const TailConsts& tc, const double* d_lbeta, double* coef) {
   LAUNCH(k_finish<K>, blocks_for(e_hi - e_lo, 128), 128, 0, s.s_main, src, s.sxy.as<double>(), s.dense_S.as<double>(),
-         nn, L, s.from.as<int32_t>(), s.to.as<int32_t>(), s.node_of_row.as<int32_t>(), s.mean.as<double>(),
+         nn, L, s.ea.as<int32_t>(), s.eb.as<int32_t>(), s.mean.as<double>(),
          s.sxx.as<double>(), s.bad.as<uint8_t>(), e_lo, e_hi, mode, df1, df2, tc, d_lbeta, s.stat.as<double>(),
          s.status.as<int32_t>(), coef, s.p_edge.as<double>(), s.scal.as<int32_t>() + 2 * SC_ERR);
 }
@@ -390,6 +413,7 @@ int stage_inputs(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const Host
   CU(s.pct.ensure((size_t)(in->P > 0 ? in->P : 1) * 8));
   if (pct_bytes) CU(cudaMemcpyAsync(s.pct.p, (char*)s.h_stage + pct_off, pct_bytes, cudaMemcpyHostToDevice, s.s_main));
   CU(cudaEventRecord(s.ev[EV_H2D], s.s_main));
+  trace_mark(ctx, "(inputs staged)", s.s_main);
   return MDEGGS_OK;
 }
 
@@ -401,25 +425,29 @@ int run_shard_front(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, int32_t
   const int32_t* d_from = s.from.as<int32_t>();
   const int32_t* d_to = s.to.as<int32_t>();
   // ---- K0 node filter ----
-  CU(s.flags.ensure((size_t)G * 4));
-  CU(s.excl.ensure((size_t)G * 4));
+  // one memset clears the scalars (node count, error flag, "done" counter) and the row bitmap behind them
+  const int W = (G + 31) >> 5;
+  CU(s.scal.ensure(SC_COUNT * 8 + (size_t)W * 4));
+  CU(s.excl.ensure((size_t)W * 4));
   CU(s.node_of_row.ensure((size_t)G * 4));
   CU(s.rowlist.ensure((size_t)G * 4));
-  CU(cudaMemsetAsync(s.flags.p, 0, (size_t)G * 4, s.s_main));
-  CU(cudaMemsetAsync(s.scal.p, 0, SC_COUNT * 8, s.s_main));
-  if (E > 0) {
-    int64_t nb = (E + 255) / 256;
-    unsigned grid = (unsigned)(nb < 148 * 32 ? nb : 148 * 32);
-    LAUNCH(k_mark_nodes, grid, 256, 0, s.s_main, d_from, d_to, E, G, s.flags.as<int32_t>(),
+  CU(s.ea.ensure((size_t)(E > 0 ? E : 1) * 4));
+  CU(s.eb.ensure((size_t)(E > 0 ? E : 1) * 4));
+  CU(cudaMemsetAsync(s.scal.p, 0, SC_COUNT * 8 + (size_t)W * 4, s.s_main));
+  unsigned int* d_bitmap = reinterpret_cast<unsigned int*>(s.scal.as<char>() + SC_COUNT * 8);
+  {
+    // each CTA flushes its shared-memory bitmap (W atomicOr at most): few, fat CTAs
+    int64_t nb = (E + 1023) / 1024;
+    unsigned grid = (unsigned)(nb < 1 ? 1 : (nb < 148 * 4 ? nb : 148 * 4));
+    const size_t smem = G <= K0_SMEM_ROWS ? (size_t)W * 4 : 0;
+    LAUNCH(k_mark_nodes, grid, 256, smem, s.s_main, d_from, d_to, E, G, d_bitmap, s.excl.as<int32_t>(),
+           s.scal.as<int32_t>() + 2 * SC_NNODES, s.scal.as<unsigned int>() + 2 * SC_DONE,
+           s.scal.as<int32_t>() + 2 * SC_ERR);
+    const int64_t nt = (int64_t)G > E ? (int64_t)G : E;
+    LAUNCH(k_build_nodes, blocks_for(nt, 256), 256, 0, s.s_main, d_bitmap, s.excl.as<int32_t>(), G, d_from, d_to, E,
+           s.node_of_row.as<int32_t>(), s.rowlist.as<int32_t>(), s.ea.as<int32_t>(), s.eb.as<int32_t>(),
            s.scal.as<int32_t>() + 2 * SC_ERR);
   }
-  size_t tmp_bytes = 0;
-  cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, s.flags.as<int32_t>(), s.excl.as<int32_t>(), G, s.s_main);
-  CU(s.cub_tmp.ensure(tmp_bytes));
-  CU(cub::DeviceScan::ExclusiveSum(s.cub_tmp.p, tmp_bytes, s.flags.as<int32_t>(), s.excl.as<int32_t>(), G, s.s_main));
-  ctx->launches += 2;
-  LAUNCH(k_build_rowlist, blocks_for(G, 256), 256, 0, s.s_main, s.flags.as<int32_t>(), s.excl.as<int32_t>(), G,
-         s.node_of_row.as<int32_t>(), s.rowlist.as<int32_t>(), s.scal.as<int32_t>() + 2 * SC_NNODES);
   // No mid-pipeline host read: buffers and grids are sized for the upper bound min(G, 2E) of the node count,
   // kernels read the real count from device memory, and an out-of-range edge index raises a device flag that
   // makes every later edge kernel exit at once; the flag and the count are read after the final sync.
@@ -571,11 +599,12 @@ int run_shard_main(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
   ctx->stats.fit_path = is_rlm ? 2 : (use_dense ? 1 : 0);
   if (e_hi > e_lo) {
     if (is_rlm) {
-      int rc = launch_fit_rlm(ctx->launches, s.s_main, s.D.as<double>(), L, s.from.as<int32_t>(), s.to.as<int32_t>(),
-                              s.node_of_row.as<int32_t>(), s.mean.as<double>(), s.sxx.as<double>(),
+      int rc = launch_fit_rlm(ctx->launches, s.s_main, s.D.as<double>(), L, s.ea.as<int32_t>(), s.eb.as<int32_t>(),
+                              s.mean.as<double>(), s.sxx.as<double>(),
                               s.bad.as<uint8_t>(), e_lo, e_hi, in->tested_coef, in->rlm_cov_mode,
                               s.stat.as<double>(), s.status.as<int32_t>(), d_coef, s.iters.as<int32_t>(),
                               s.scal.as<int32_t>() + 2 * SC_ERR);
+      trace_mark(ctx, "k_fit_rlm", s.s_main);
       if (rc != 0) {
         set_err(ctx, "rlm kernel configuration failed (n too large for shared memory?)");
         return MDEGGS_EUNSUPPORTED;
@@ -590,8 +619,8 @@ int run_shard_main(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
         CU(cudaMemsetAsync(rr, 0x7f, 4, s.s_main));                     // row_range[0] = huge
         CU(cudaMemsetAsync(rr + 1, 0xff, 4, s.s_main));                 // row_range[1] = -1
         int64_t nb = (e_hi - e_lo + 255) / 256;
-        LAUNCH(k_edge_row_range, (unsigned)(nb < 148 * 8 ? nb : 148 * 8), 256, 0, s.s_main, s.from.as<int32_t>(),
-               s.to.as<int32_t>(), s.node_of_row.as<int32_t>(), e_lo, e_hi, rr, s.scal.as<int32_t>() + 2 * SC_ERR);
+        LAUNCH(k_edge_row_range, (unsigned)(nb < 148 * 8 ? nb : 148 * 8), 256, 0, s.s_main, s.ea.as<int32_t>(),
+               s.eb.as<int32_t>(), e_lo, e_hi, rr, s.scal.as<int32_t>() + 2 * SC_ERR);
         d_range = rr;
       }
       LAUNCH(k_dense_moments, grid, 256, 0, s.s_main, s.D.as<double>(), L, s.mean.as<double>(), (int)n_nodes, ntl,
@@ -717,12 +746,14 @@ int run_shard_back(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
                                        s.sortk2.as<unsigned long long>(), s.idx.as<int32_t>(), s.idx2.as<int32_t>(), E,
                                        0, 64, s.s_main));
     ctx->launches += 10;
+    trace_mark(ctx, "cub::SortPairs", s.s_main);
     LAUNCH(k_gather_sorted, blocks_for(E, 256), 256, 0, s.s_main, s.sortk2.as<unsigned long long>(),
-           s.idx2.as<int32_t>(), s.from.as<int32_t>(), s.to.as<int32_t>(), s.node_of_row.as<int32_t>(), E,
+           s.idx2.as<int32_t>(), s.ea.as<int32_t>(), s.eb.as<int32_t>(), E,
            s.ps.as<double>(), s.sa.as<int32_t>(), s.sb.as<int32_t>(), s.scal.as<unsigned long long>() + SC_NVALID,
            s.scal.as<int32_t>() + 2 * SC_ERR);
   }
   CU(cudaStreamWaitEvent(s.s_main, s.ev_join, 0));  // cut-offs ready
+  trace_mark(ctx, "(join quantile stream)", s.s_main);
   // counters: tot[P] fail[P] sig[P] sig_raw[P] (u64), then out: tot_out[P] sig_out[P] fail_out[P] (i64)
   CU(s.counters.ensure((size_t)Pn * 8 * 7));
   CU(cudaMemsetAsync(s.counters.p, 0, (size_t)Pn * 8 * 7, s.s_main));
@@ -747,8 +778,8 @@ int run_shard_back(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
     LAUNCH(k_actmask, blocks_for((int64_t)P * n_nodes, 256), 256, 0, s.s_main, s.med.as<double>(),
            s.cutoff.as<double>(), d_nn, P, K, act_stride, s.act.as<uint8_t>());
     if (E > 0)
-      LAUNCH(k_percolate, blocks_for(E, 256), 256, (size_t)3 * P * sizeof(unsigned), s.s_main, s.from.as<int32_t>(),
-             s.to.as<int32_t>(), s.node_of_row.as<int32_t>(), s.status.as<int32_t>(), s.p_edge.as<double>(),
+      LAUNCH(k_percolate, blocks_for(E, 256), 256, (size_t)3 * P * sizeof(unsigned), s.s_main, s.ea.as<int32_t>(),
+             s.eb.as<int32_t>(), s.status.as<int32_t>(), s.p_edge.as<double>(),
              s.act.as<uint8_t>(), act_stride, E, P, c_tot, c_fail, c_raw, d_cat, s.scal.as<int32_t>() + 2 * SC_ERR);
   }
   EVREC(s.ev[EV_PERC], s.s_main);
@@ -849,8 +880,8 @@ int run_shard_back2(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const m
     if (rc) return rc;
   }
   if (want_cat_best || row_copy)
-    LAUNCH(k_best_rows, blocks_for(E, 256), 256, 0, s.s_main, s.from.as<int32_t>(), s.to.as<int32_t>(),
-           s.node_of_row.as<int32_t>(), s.act.as<uint8_t>(), act_stride, E, d_best,
+    LAUNCH(k_best_rows, blocks_for(E, 256), 256, 0, s.s_main, s.ea.as<int32_t>(), s.eb.as<int32_t>(),
+           s.act.as<uint8_t>(), act_stride, E, d_best,
            want_cat_best ? s.cat_best.as<int8_t>() : nullptr, row_copy ? d_padj : nullptr,
            row_copy ? s.padj_best.as<double>() : nullptr, s.scal.as<int32_t>() + 2 * SC_ERR);
   if (emit && out->median) {
@@ -935,6 +966,7 @@ int emit_outputs(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const mdeg
     }
   }
   CU(cudaEventRecord(s.ev[EV_END], s.s_main));
+  trace_mark(ctx, "(outputs copied)", s.s_main);
   return MDEGGS_OK;
 }
 
@@ -978,6 +1010,7 @@ int mdeggs_create(mdeggs_ctx** out, const int* device_ids, int n_dev) {
   if (const char* fp = getenv("MDEGGS_FIT_PATH")) ctx->fit_path_override = atoi(fp);
   if (const char* g = getenv("MDEGGS_GRAPH")) ctx->use_graph = atoi(g);
   if (const char* g = getenv("MDEGGS_DEBUG_SYNC")) ctx->debug_sync = atoi(g);
+  if (const char* g = getenv("MDEGGS_TRACE")) ctx->trace = atoi(g);
   ctx->shards.resize((size_t)n_dev);
   for (int i = 0; i < n_dev; ++i) {
     ctx->shards[(size_t)i].device = device_ids[i];
@@ -1025,6 +1058,7 @@ int mdeggs_create_rank(mdeggs_ctx** out, int device_id, int rank, int world, con
   if (const char* fp = getenv("MDEGGS_FIT_PATH")) ctx->fit_path_override = atoi(fp);
   if (const char* g = getenv("MDEGGS_GRAPH")) ctx->use_graph = atoi(g);
   if (const char* g = getenv("MDEGGS_DEBUG_SYNC")) ctx->debug_sync = atoi(g);
+  if (const char* g = getenv("MDEGGS_TRACE")) ctx->trace = atoi(g);
   ctx->shards.resize(1);
   Shard& s = ctx->shards[0];
   s.device = device_id;
@@ -1055,6 +1089,7 @@ int mdeggs_create_rank(mdeggs_ctx** out, int device_id, int rank, int world, con
 int mdeggs_destroy(mdeggs_ctx* ctx) {
   if (!ctx) return MDEGGS_OK;
   if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
+  for (cudaEvent_t e : ctx->trace_pool) cudaEventDestroy(e);
   for (Shard& s : ctx->shards) {
     cudaSetDevice(s.device);
     cudaDeviceSynchronize();
@@ -1106,6 +1141,8 @@ int mdeggs_run_omic(mdeggs_ctx* ctx, const mdeggs_problem* in, mdeggs_result* ou
   if (rc) return rc;
   ctx->launches = 0;
   memset(&ctx->stats, 0, sizeof ctx->stats);
+  ctx->trace_recs.clear();
+  ctx->trace_used = 0;
   const int src_device = ctx->shards[0].device;
   Shard& sh0 = ctx->shards[0];
   // ---- phase A: inputs (eager) ----
@@ -1129,7 +1166,7 @@ int mdeggs_run_omic(mdeggs_ctx* ctx, const mdeggs_problem* in, mdeggs_result* ou
     return r;
   };
   int32_t n_nodes = (int32_t)(2 * in->E < (int64_t)in->G ? 2 * in->E : (int64_t)in->G);
-  bool graph_ok = ctx->use_graph && ctx->shards.size() == 1 && sh0.world == 1;
+  bool graph_ok = ctx->use_graph && !ctx->trace && ctx->shards.size() == 1 && sh0.world == 1;
   bool replayed = false;
   if (graph_ok) {
     GraphKey key;
@@ -1228,6 +1265,16 @@ int mdeggs_run_omic(mdeggs_ctx* ctx, const mdeggs_problem* in, mdeggs_result* ou
     }
     n_nodes = (int32_t)host_scal[SC_NNODES];
   }
+  if (ctx->trace && !ctx->trace_recs.empty()) {  // timeline of this call: end time of every launch, per stream
+    float prev[2] = {0.f, 0.f};
+    fprintf(stderr, "[mdeggs trace] %-34s %-6s %10s %10s\n", "launch", "stream", "end_us", "delta_us");
+    for (const auto& r : ctx->trace_recs) {
+      const int sid = r.stream == s0.s_sort ? 1 : 0;
+      const float t = ev_ms(s0.ev[EV_START], r.ev) * 1e3f;
+      fprintf(stderr, "[mdeggs trace] %-34s %-6s %10.1f %10.1f\n", r.name, sid ? "side" : "main", t, t - prev[sid]);
+      prev[sid] = t;
+    }
+  }
   // ---- stats ----
   (void)replayed;
   mdeggs_stats& st = ctx->stats;
@@ -1266,6 +1313,10 @@ int mdeggs_set_option(mdeggs_ctx* ctx, const char* name, int64_t value) {
       ctx->graph_exec = nullptr;
     }
     ctx->key_valid = false;
+    return MDEGGS_OK;
+  }
+  if (!strcmp(name, "trace")) {
+    ctx->trace = (int)value;
     return MDEGGS_OK;
   }
   if (!strcmp(name, "rsel_cap")) {

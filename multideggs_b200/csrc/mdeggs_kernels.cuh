@@ -44,30 +44,95 @@ __device__ __forceinline__ double warp_sum(double v) {
 
 // ------------------------------------------------------------------------------------------------
 // K0: node filter   (core_functions.R:333-336: nodes <- unique(c(from,to)); assayData[rownames %in% nodes,])
+//   k_mark_nodes : every CTA marks the end points of its edges in a shared-memory bitmap of the G rows (G/8 bytes;
+//                  direct global atomicOr when G > K0_SMEM_ROWS), ORs the non-zero words into the global bitmap;
+//                  the LAST CTA to finish turns the bitmap into per-word exclusive popcount prefixes + n_nodes.
+//   k_build_nodes: thread per row -> node_of_row / rowlist;  thread per edge -> node ids (ea, eb) of its end
+//                  points, read by every later edge kernel instead of from/to + a dependent node_of_row look-up.
 // ------------------------------------------------------------------------------------------------
-__global__ void k_mark_nodes(const int32_t* __restrict__ from, const int32_t* __restrict__ to, int64_t E, int G,
-                             int32_t* __restrict__ flags, int32_t* __restrict__ err) {
-  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+constexpr int K0_SMEM_ROWS = 1 << 18;  // 32 KB bitmap
+
+__global__ void __launch_bounds__(256) k_mark_nodes(const int32_t* __restrict__ from, const int32_t* __restrict__ to,
+                                                    int64_t E, int G, unsigned int* __restrict__ bitmap,
+                                                    int32_t* __restrict__ word_base, int32_t* __restrict__ n_nodes,
+                                                    unsigned int* __restrict__ done, int32_t* __restrict__ err) {
+  extern __shared__ unsigned int s_bits[];
+  __shared__ int s_last;
+  const int W = (G + 31) >> 5;
+  const bool use_smem = G <= K0_SMEM_ROWS;
+  if (use_smem) {
+    for (int w = threadIdx.x; w < W; w += blockDim.x) s_bits[w] = 0u;
+    __syncthreads();
+  }
+  unsigned int* bits = use_smem ? s_bits : bitmap;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  bool bad_idx = false;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += stride) {
-    int a = from[e], b = to[e];
-    if (a < 1 || a > G || b < 1 || b > G) {
-      *err = 1;
+    const int a = from[e] - 1, b = to[e] - 1;
+    if (a < 0 || a >= G || b < 0 || b >= G) {
+      bad_idx = true;
       continue;
     }
-    if (!flags[a - 1]) flags[a - 1] = 1;
-    if (!flags[b - 1]) flags[b - 1] = 1;
+    const unsigned ma = 1u << (a & 31), mb = 1u << (b & 31);
+    if (!(bits[a >> 5] & ma)) atomicOr(&bits[a >> 5], ma);
+    if (!(bits[b >> 5] & mb)) atomicOr(&bits[b >> 5], mb);
+  }
+  if (bad_idx) *err = 1;
+  if (use_smem) {
+    __syncthreads();
+    for (int w = threadIdx.x; w < W; w += blockDim.x) {
+      const unsigned v = s_bits[w];
+      if (v) atomicOr(&bitmap[w], v);
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(done, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // last CTA: exclusive prefix of the per-word popcounts (each thread owns a contiguous run of words)
+  typedef cub::BlockScan<int, 256> Scan;
+  __shared__ typename Scan::TempStorage tmp;
+  const int per = (W + 255) / 256;
+  const int w0 = threadIdx.x * per, w1 = min(W, w0 + per);
+  int mine = 0;
+  for (int w = w0; w < w1; ++w) mine += __popc(__ldcg(bitmap + w));
+  int ex, total;
+  Scan(tmp).ExclusiveSum(mine, ex, total);
+  for (int w = w0; w < w1; ++w) {
+    word_base[w] = ex;
+    ex += __popc(__ldcg(bitmap + w));
+  }
+  if (threadIdx.x == 0) {
+    *n_nodes = total;
+    *done = 0u;
   }
 }
 
-__global__ void k_build_rowlist(const int32_t* __restrict__ flags, const int32_t* __restrict__ excl, int G,
-                                int32_t* __restrict__ node_of_row, int32_t* __restrict__ rowlist,
-                                int32_t* __restrict__ n_nodes) {
-  int g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= G) return;
-  int f = flags[g], pos = excl[g];
-  node_of_row[g] = f ? pos : -1;
-  if (f) rowlist[pos] = g;
-  if (g == G - 1) *n_nodes = pos + f;
+__device__ __forceinline__ int node_index(const unsigned int* __restrict__ bitmap,
+                                          const int32_t* __restrict__ word_base, int row) {
+  return word_base[row >> 5] + __popc(bitmap[row >> 5] & ((1u << (row & 31)) - 1u));
+}
+
+__global__ void __launch_bounds__(256) k_build_nodes(const unsigned int* __restrict__ bitmap,
+                                                     const int32_t* __restrict__ word_base, int G,
+                                                     const int32_t* __restrict__ from, const int32_t* __restrict__ to,
+                                                     int64_t E, int32_t* __restrict__ node_of_row,
+                                                     int32_t* __restrict__ rowlist, int32_t* __restrict__ ea,
+                                                     int32_t* __restrict__ eb, const int32_t* __restrict__ err) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < G) {
+    const int g = (int)i;
+    const bool f = (bitmap[g >> 5] >> (g & 31)) & 1u;
+    const int pos = node_index(bitmap, word_base, g);
+    node_of_row[g] = f ? pos : -1;
+    if (f) rowlist[pos] = g;
+  }
+  if (i < E && !*err) {
+    ea[i] = node_index(bitmap, word_base, from[i] - 1);
+    eb[i] = node_index(bitmap, word_base, to[i] - 1);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -513,9 +578,8 @@ __device__ __forceinline__ void finish_pair(const SegLayout& L, const double* __
 // lanes behind a scalar epilogue.
 template <int K>
 __global__ void __launch_bounds__(256, 4) k_fit_stream(const double* __restrict__ D, SegLayout L,
-                                                       const int32_t* __restrict__ from,
-                                                       const int32_t* __restrict__ to,
-                                                       const int32_t* __restrict__ node_of_row,
+                                                       const int32_t* __restrict__ ea,
+                                                       const int32_t* __restrict__ eb,
                                                        const double* __restrict__ mean,
                                                        const uint8_t* __restrict__ bad, int64_t e_lo, int64_t e_hi,
                                                        double* __restrict__ sxy, const int32_t* __restrict__ err) {
@@ -524,9 +588,8 @@ __global__ void __launch_bounds__(256, 4) k_fit_stream(const double* __restrict_
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t e = e_lo + warp0; e < e_hi; e += nwarps) {
-    const int ra = from[e] - 1, rb = to[e] - 1;
-    const int a = node_of_row[ra], b = node_of_row[rb];
-    if (ra == rb || bad[a] || bad[b]) continue;  // k_finish classifies these edges; their moments are not read
+    const int a = ea[e], b = eb[e];
+    if (a == b || bad[a] || bad[b]) continue;  // k_finish classifies these edges; their moments are not read
     const double2* __restrict__ pa = reinterpret_cast<const double2*>(D + (size_t)a * L.npad);
     const double2* __restrict__ pb = reinterpret_cast<const double2*>(D + (size_t)b * L.npad);
     double mine = 0.0;
@@ -557,9 +620,8 @@ __global__ void __launch_bounds__(256, 4) k_fit_stream(const double* __restrict_
 // ------------------------------------------------------------------------------------------------
 template <int K>
 __global__ void __launch_bounds__(128) k_finish(int src, const double* __restrict__ sxy, const double* __restrict__ S,
-                                                int nn, SegLayout L, const int32_t* __restrict__ from,
-                                                const int32_t* __restrict__ to,
-                                                const int32_t* __restrict__ node_of_row,
+                                                int nn, SegLayout L, const int32_t* __restrict__ ea,
+                                                const int32_t* __restrict__ eb,
                                                 const double* __restrict__ mean, const double* __restrict__ sxx,
                                                 const uint8_t* __restrict__ bad, int64_t e_lo, int64_t e_hi, int mode,
                                                 double df1, double df2, TailConsts tc,
@@ -570,10 +632,9 @@ __global__ void __launch_bounds__(128) k_finish(int src, const double* __restric
   if (e >= e_hi || *err) return;
   tc.lbeta_ab = *lbeta_p;
   if (src != 2) {
-    const int ra = from[e] - 1, rb = to[e] - 1;
-    const int a = node_of_row[ra], b = node_of_row[rb];
-    if (ra == rb || bad[a] || bad[b]) {
-      const bool self = (ra == rb) && !bad[a];
+    const int a = ea[e], b = eb[e];
+    if (a == b || bad[a] || bad[b]) {
+      const bool self = (a == b) && !bad[a];
       stat[e] = self ? 0.0 : nan("");
       status[e] = self ? MDEGGS_EDGE_SELFLOOP : MDEGGS_EDGE_NONFINITE;
       if (coef)
@@ -623,8 +684,7 @@ __device__ __forceinline__ int edge_category(unsigned ma, unsigned mb) {
 }
 
 // counts per percentile: tot_edges (773-779), hard failures, and for padj "none" the raw p < 0.05 count (796-808)
-__global__ void __launch_bounds__(256) k_percolate(const int32_t* __restrict__ from, const int32_t* __restrict__ to,
-                                                   const int32_t* __restrict__ node_of_row,
+__global__ void __launch_bounds__(256) k_percolate(const int32_t* __restrict__ ea, const int32_t* __restrict__ eb,
                                                    const int32_t* __restrict__ status,
                                                    const double* __restrict__ p_edge,
                                                    const uint8_t* __restrict__ act, int act_stride, int64_t E, int P,
@@ -641,8 +701,8 @@ __global__ void __launch_bounds__(256) k_percolate(const int32_t* __restrict__ f
   int a = 0, b = 0, st = 0;
   double pv = 1.0;
   if (live) {
-    a = node_of_row[from[e] - 1];
-    b = node_of_row[to[e] - 1];
+    a = ea[e];
+    b = eb[e];
     st = status[e];
     pv = p_edge[e];
   }
@@ -671,8 +731,8 @@ __global__ void __launch_bounds__(256) k_percolate(const int32_t* __restrict__ f
 
 // rows of the device-chosen best percentile: category row (recomputed from the masks) and, when the adjusted
 // values of every percentile are still in the scratch matrix, its p.adj row (else a BH pass is rerun for it)
-__global__ void k_best_rows(const int32_t* __restrict__ from, const int32_t* __restrict__ to,
-                            const int32_t* __restrict__ node_of_row, const uint8_t* __restrict__ act, int act_stride,
+__global__ void k_best_rows(const int32_t* __restrict__ ea, const int32_t* __restrict__ eb,
+                            const uint8_t* __restrict__ act, int act_stride,
                             int64_t E, const int32_t* __restrict__ best, int8_t* __restrict__ cat_out,
                             const double* __restrict__ padj_all, double* __restrict__ padj_best,
                             const int32_t* __restrict__ err) {
@@ -682,8 +742,7 @@ __global__ void k_best_rows(const int32_t* __restrict__ from, const int32_t* __r
   if (cat_out) {
     int c = 0;
     if (p >= 0) {
-      int a = node_of_row[from[e] - 1], b = node_of_row[to[e] - 1];
-      c = edge_category(act[(size_t)p * act_stride + a], act[(size_t)p * act_stride + b]);
+      c = edge_category(act[(size_t)p * act_stride + ea[e]], act[(size_t)p * act_stride + eb[e]]);
     }
     cat_out[e] = (int8_t)c;
   }
@@ -712,8 +771,8 @@ __global__ void k_sort_keys(const double* __restrict__ p_edge, int64_t E, unsign
 }
 
 __global__ void k_gather_sorted(const unsigned long long* __restrict__ keys_sorted,
-                                const int32_t* __restrict__ idx_sorted, const int32_t* __restrict__ from,
-                                const int32_t* __restrict__ to, const int32_t* __restrict__ node_of_row, int64_t E,
+                                const int32_t* __restrict__ idx_sorted, const int32_t* __restrict__ ea,
+                                const int32_t* __restrict__ eb, int64_t E,
                                 double* __restrict__ ps, int32_t* __restrict__ sa, int32_t* __restrict__ sb,
                                 unsigned long long* __restrict__ n_valid, const int32_t* __restrict__ err) {
   int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -723,8 +782,8 @@ __global__ void k_gather_sorted(const unsigned long long* __restrict__ keys_sort
     int32_t e = idx_sorted[j];
     valid = (k != ~0ull);
     ps[j] = valid ? dkey_inv(k) : nan("");
-    sa[j] = node_of_row[from[e] - 1];
-    sb[j] = node_of_row[to[e] - 1];
+    sa[j] = ea[e];
+    sb[j] = eb[e];
   }
   unsigned m = __ballot_sync(0xffffffffu, valid);
   if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_valid, (unsigned long long)__popc(m));

@@ -65,8 +65,7 @@ __device__ __forceinline__ double warp_median_abs(const double* r, const SegLayo
 
 template <bool CACHE_AB>
 __global__ void __launch_bounds__(256) k_fit_rlm(const double* __restrict__ D, SegLayout L,
-                                                 const int32_t* __restrict__ from, const int32_t* __restrict__ to,
-                                                 const int32_t* __restrict__ node_of_row,
+                                                 const int32_t* __restrict__ ea, const int32_t* __restrict__ eb,
                                                  const double* __restrict__ mean, const double* __restrict__ sxx,
                                                  const uint8_t* __restrict__ bad, int64_t e_lo, int64_t e_hi,
                                                  int tested_coef, int cov_mode, double* __restrict__ stat,
@@ -83,8 +82,7 @@ __global__ void __launch_bounds__(256) k_fit_rlm(const double* __restrict__ D, S
   const double kh = 1.345;
   const int n = L.n;
   for (int64_t e = e_lo + (int64_t)blockIdx.x * wpb + wib; e < e_hi; e += (int64_t)gridDim.x * wpb) {
-    const int ra = from[e] - 1, rb = to[e] - 1;
-    const int a = node_of_row[ra], b = node_of_row[rb];
+    const int a = ea[e], b = eb[e];
     auto put = [&](double st_v, int code, int it) {
       if (lane == 0) {
         stat[e] = st_v;
@@ -94,8 +92,8 @@ __global__ void __launch_bounds__(256) k_fit_rlm(const double* __restrict__ D, S
           for (int j = 0; j < 4; ++j) coef[(size_t)e * 4 + j] = nan("");
       }
     };
-    if (ra == rb || bad[a] || bad[b]) {
-      bool self = (ra == rb) && !bad[a];
+    if (a == b || bad[a] || bad[b]) {
+      bool self = (a == b) && !bad[a];
       put(self ? 0.0 : nan(""), self ? MDEGGS_EDGE_SELFLOOP : MDEGGS_EDGE_NONFINITE, 0);
       continue;
     }
@@ -273,8 +271,7 @@ __global__ void __launch_bounds__(256) k_fit_rlm(const double* __restrict__ D, S
 // selection, one pass for the Huber weights + 5 weighted moments per category.
 template <int ITEMS>
 __global__ void __launch_bounds__(256) k_fit_rlm_reg(const double* __restrict__ D, SegLayout L,
-                                                     const int32_t* __restrict__ from, const int32_t* __restrict__ to,
-                                                     const int32_t* __restrict__ node_of_row,
+                                                     const int32_t* __restrict__ ea, const int32_t* __restrict__ eb,
                                                      const double* __restrict__ mean, const double* __restrict__ sxx,
                                                      const uint8_t* __restrict__ bad, int64_t e_lo, int64_t e_hi,
                                                      int tested_coef, int cov_mode, double* __restrict__ stat,
@@ -299,8 +296,7 @@ __global__ void __launch_bounds__(256) k_fit_rlm_reg(const double* __restrict__ 
     cmask |= (unsigned)in1 << j;
   }
   for (int64_t e = e_lo + (int64_t)blockIdx.x * wpb + wib; e < e_hi; e += (int64_t)gridDim.x * wpb) {
-    const int ra = from[e] - 1, rb = to[e] - 1;
-    const int a = node_of_row[ra], b = node_of_row[rb];
+    const int a = ea[e], b = eb[e];
     auto put = [&](double st_v, int code, int it) {
       if (lane == 0) {
         stat[e] = st_v;
@@ -310,8 +306,8 @@ __global__ void __launch_bounds__(256) k_fit_rlm_reg(const double* __restrict__ 
           for (int j = 0; j < 4; ++j) coef[(size_t)e * 4 + j] = nan("");
       }
     };
-    if (ra == rb || bad[a] || bad[b]) {
-      bool self = (ra == rb) && !bad[a];
+    if (a == b || bad[a] || bad[b]) {
+      bool self = (a == b) && !bad[a];
       put(self ? 0.0 : nan(""), self ? MDEGGS_EDGE_SELFLOOP : MDEGGS_EDGE_NONFINITE, 0);
       continue;
     }
@@ -555,8 +551,8 @@ __global__ void __launch_bounds__(256) k_fit_rlm_reg(const double* __restrict__ 
 }
 
 template <int ITEMS>
-inline void launch_fit_rlm_reg(cudaStream_t stream, const double* D, const SegLayout& L, const int32_t* from,
-                               const int32_t* to, const int32_t* node_of_row, const double* mean, const double* sxx,
+inline void launch_fit_rlm_reg(cudaStream_t stream, const double* D, const SegLayout& L, const int32_t* ea,
+                               const int32_t* eb, const double* mean, const double* sxx,
                                const uint8_t* bad, int64_t e_lo, int64_t e_hi, int tested_coef, int cov_mode, double* stat,
                                int32_t* status, double* coef, int32_t* iters, const int32_t* err) {
   const size_t per_warp = (size_t)L.npad * 16;
@@ -566,18 +562,18 @@ inline void launch_fit_rlm_reg(cudaStream_t stream, const double* D, const SegLa
   unsigned grid = (unsigned)(want < 148 * 32 ? want : 148 * 32);
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(k_fit_rlm_reg<ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  k_fit_rlm_reg<ITEMS><<<grid, wpb * 32, smem, stream>>>(D, L, from, to, node_of_row, mean, sxx, bad, e_lo, e_hi,
+  k_fit_rlm_reg<ITEMS><<<grid, wpb * 32, smem, stream>>>(D, L, ea, eb, mean, sxx, bad, e_lo, e_hi,
                                                         tested_coef, cov_mode, stat, status, coef, iters, err);
 }
 
 // returns 0 on success, non-zero if even the residual-only variant does not fit in shared memory
 inline int launch_fit_rlm(int64_t& launches, cudaStream_t stream, const double* D, const SegLayout& L,
-                          const int32_t* from, const int32_t* to, const int32_t* node_of_row, const double* mean,
+                          const int32_t* ea, const int32_t* eb, const double* mean,
                           const double* sxx, const uint8_t* bad, int64_t e_lo, int64_t e_hi, int tested_coef,
                           int cov_mode, double* stat, int32_t* status, double* coef, int32_t* iters, const int32_t* err) {
   if (L.npad <= 32 * 32) {  // register-resident keys: n up to ~1,000 samples
 #define MDEGGS_RLM(IT)                                                                                                 \
-  launch_fit_rlm_reg<IT>(stream, D, L, from, to, node_of_row, mean, sxx, bad, e_lo, e_hi, tested_coef, cov_mode, stat, \
+  launch_fit_rlm_reg<IT>(stream, D, L, ea, eb, mean, sxx, bad, e_lo, e_hi, tested_coef, cov_mode, stat, \
                          status, coef, iters, err)
     if (L.npad <= 32 * 4) MDEGGS_RLM(4);
     else if (L.npad <= 32 * 8) MDEGGS_RLM(8);
@@ -601,12 +597,12 @@ inline int launch_fit_rlm(int64_t& launches, cudaStream_t stream, const double* 
   if (cache) {
     if (smem > 48 * 1024)
       cudaFuncSetAttribute(k_fit_rlm<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
-    k_fit_rlm<true><<<grid, wpb * 32, smem, stream>>>(D, L, from, to, node_of_row, mean, sxx, bad, e_lo, e_hi,
+    k_fit_rlm<true><<<grid, wpb * 32, smem, stream>>>(D, L, ea, eb, mean, sxx, bad, e_lo, e_hi,
                                                      tested_coef, cov_mode, stat, status, coef, iters, err);
   } else {
     if (smem > 48 * 1024)
       cudaFuncSetAttribute(k_fit_rlm<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
-    k_fit_rlm<false><<<grid, wpb * 32, smem, stream>>>(D, L, from, to, node_of_row, mean, sxx, bad, e_lo, e_hi,
+    k_fit_rlm<false><<<grid, wpb * 32, smem, stream>>>(D, L, ea, eb, mean, sxx, bad, e_lo, e_hi,
                                                       tested_coef, cov_mode, stat, status, coef, iters, err);
   }
   ++launches;
