@@ -124,7 +124,8 @@ typedef struct mdeggs_stats {
   int64_t kernel_launches; /* CUDA kernels launched by the last call (this library's + CUB's)           */
   int64_t h2d_bytes, d2h_bytes;
   int32_t fit_path;       /* bits 0-7: 0 warp-per-edge streaming, 1 dense tile cross-moments, 2 rlm IRLS;
-                             bit 8: the compute phase was replayed from a CUDA graph                       */
+                             bit 8: the compute phase was replayed from a CUDA graph;
+                             bit 9: K8 ordered the edges through p-value buckets (no radix sort)          */
   int32_t n_ranks;
   float ms_total;         /* device time of the whole pipeline (CUDA events on the engine stream)       */
   float ms_h2d, ms_gather, ms_stats, ms_quantile, ms_fit, ms_tail, ms_collective, ms_percolate, ms_adjust, ms_d2h;
@@ -156,6 +157,9 @@ int mdeggs_last_stats(const mdeggs_ctx* ctx, mdeggs_stats* out);
 /* Engine options: "graph" (1 = replay the compute phase from a CUDA graph when a call repeats with identical
  * shapes and buffers [default], 0 = always launch eagerly, which also keeps the per-stage timings);
  * "fit_path" (-1 = choose streaming vs dense-tile pair fits automatically [default], 0 = streaming, 1 = dense);
+ * "sort_path" (-1 = K8 orders the edges through p-value buckets up to 4M edges and with a CUB radix sort beyond
+ * [default], 0 = always the radix sort, 1 = buckets whenever possible);
+ * "trace" (1 = print the end time of every launch of the next calls to stderr; implies eager launches);
  * "rsel_cap" (tests: cap the quantile candidate list so that the overflow path is exercised; 0 = default). */
 int mdeggs_set_option(mdeggs_ctx* ctx, const char* name, int64_t value);
 const char* mdeggs_last_error(const mdeggs_ctx* ctx);

@@ -1,0 +1,373 @@
+// mdeggs_bsort.cuh — K8 front end for small and medium edge counts: ordering all edges by p-value without a
+// multi-pass device radix sort.
+//
+// stats::p.adjust (core_functions.R:1027-1035) needs each (percentile, category) segment in p order.  The raw p of
+// an edge does not depend on the percentile, so all edges are ordered once.  A 64-bit LSD radix sort is 8 digit
+// passes plus histogram/scan kernels: ~11 dependent launches that, for the 10^4..10^6 edges of a network, are pure
+// launch latency (cfg3: 53,035 edges, ~100 us).  Here instead:
+//   1. the kernel that produces p (k_finish) drops every edge into one of NB monotone buckets of its p-value
+//      (bs_bucket: one bucket per binade below 2^-10, equal-width buckets above — balanced for uniform null p-values
+//      and for the heavy left tail of true signals) with a warp-aggregated atomic that also hands the edge its slot
+//      inside the bucket; the last CTA to finish turns the bucket counts into offsets;
+//   2. k_bsort_scatter writes (key, edge) to offset[bucket] + slot;
+//   3. k_bsort_sort: one CTA per run of whole buckets (~BS_CAP..2 BS_CAP elements) sorts the run in shared memory
+//      (bitonic on (key, edge id), so the order is deterministic) and emits what the BH passes read: p in ascending
+//      order, the node ids of the two end points, the edge id.
+// Three short launches after k_finish.  A bucket that alone exceeds the shared-memory capacity (a pathological
+// concentration of distinct p-values; a group of IDENTICAL p-values needs no ordering at all since every p.adjust
+// method is invariant to the order of ties) is sorted by its CTA in global memory (slow, correct).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "mdeggs_kernels.cuh"
+
+namespace mdeggs {
+
+constexpr int BS_NLOG = 1013;       // buckets 0..1012: biased exponent of p < 2^-10 (0 also holds p <= 0)
+constexpr int BS_CAP = 1024;        // run granularity; shared memory holds 2 * BS_CAP elements
+constexpr int BS_SORT_THREADS = 512;
+constexpr int64_t BS_MAX_E = 1 << 22;  // beyond this the CUB radix sort is used
+
+__host__ __device__ __forceinline__ int bs_nlin(int64_t E) {
+  int64_t v = E / 16;
+  v = v < 1024 ? 1024 : (v > 32768 ? 32768 : v);
+  return (int)v;
+}
+// total buckets: BS_NLOG + nlin + 1 (the last one holds NaN)
+__host__ __device__ __forceinline__ int bs_nbuckets(int64_t E) { return BS_NLOG + bs_nlin(E) + 1; }
+
+__device__ __forceinline__ int bs_bucket(double p, int nlin, double scale) {
+  if (isnan(p)) return BS_NLOG + nlin;
+  if (!(p > 0.0)) return 0;
+  if (p < 0x1p-10) return (int)((__double_as_longlong(p) >> 52) & 0x7ff);  // 0..1012
+  int b = (int)((p - 0x1p-10) * scale);                                    // monotone in p
+  b = b > nlin - 1 ? nlin - 1 : b;
+  return BS_NLOG + b;
+}
+__host__ __device__ __forceinline__ double bs_scale(int nlin) { return (double)nlin / (1.0 - 0x1p-10); }
+
+struct BsArgs {
+  int* count;        // [NB + 1]: bucket counts; count[NB] is the "CTAs done" counter (all zeroed before the run)
+  int* base;         // [NB + 1]: exclusive prefix of the counts (written by the last CTA)
+  int32_t* slot;     // [E]: position of the edge inside its bucket
+  unsigned long long* n_valid;  // E - #NaN, for the BH passes
+  int nlin;
+  double scale;
+  int64_t E;
+};
+
+// One call per thread of a kernel that covers edges; `live` threads contribute p.  Must be reached by every thread of
+// the CTA (no early returns before it).  `n_ctas` CTAs take part in total.
+__device__ __forceinline__ void bs_count(const BsArgs& B, bool live, int64_t e, double p, unsigned n_ctas) {
+  const int NB = BS_NLOG + B.nlin + 1;
+  const int lane = threadIdx.x & 31;
+  int b = live ? bs_bucket(p, B.nlin, B.scale) : -1 - lane;  // dead lanes never match anyone
+  const unsigned peers = __match_any_sync(0xffffffffu, b);
+  if (live) {
+    const int leader = __ffs(peers) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(&B.count[b], __popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    B.slot[e] = base + __popc(peers & ((1u << lane) - 1u));
+  }
+  // last CTA: counts -> offsets
+  __shared__ int s_is_last;
+  __shared__ int s_warp_tot[32];
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_is_last = (atomicAdd(&B.count[NB], 1) == (int)n_ctas - 1);
+  __syncthreads();
+  if (!s_is_last) return;
+  __threadfence();
+  const int nthr = blockDim.x, nwarp = nthr >> 5, wid = threadIdx.x >> 5;
+  constexpr int ITEMS = 8;  // independent loads per thread and round
+  int carry = 0;
+  for (int c0 = 0; c0 < NB; c0 += nthr * ITEMS) {
+    const int i0 = c0 + threadIdx.x * ITEMS;
+    int v[ITEMS], mine = 0;
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+      v[j] = i0 + j < NB ? __ldcg(B.count + i0 + j) : 0;
+      mine += v[j];
+    }
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp_tot[wid] = incl;
+    __syncthreads();
+    int woff = 0, tot = 0;
+    for (int w = 0; w < nwarp; ++w) {
+      const int t = s_warp_tot[w];
+      woff += w < wid ? t : 0;
+      tot += t;
+    }
+    int run = carry + woff + incl - mine;
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j)
+      if (i0 + j < NB) {
+        B.base[i0 + j] = run;
+        run += v[j];
+      }
+    carry += tot;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    B.base[NB] = carry;  // == number of edges counted
+    *B.n_valid = (unsigned long long)(carry - __ldcg(B.count + NB - 1));
+  }
+}
+
+// stand-alone counting pass (multi-GPU: the p-values arrive through the all-gather, after k_finish)
+__global__ void __launch_bounds__(256) k_bsort_count(BsArgs B, const double* __restrict__ p_edge,
+                                                     const int32_t* __restrict__ err) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = e < B.E && !*err;
+  bs_count(B, live, e, live ? p_edge[e] : 0.0, gridDim.x);
+}
+
+// ------------------------------------------------------------------------------------------------
+// finish, one thread per edge: closed-form statistic from the cross moments, then the tail probability
+//   src 0: moments from k_fit_stream (sxy[e][K]);  src 1: moments from the dense matrices S[k][i][j];
+//   src 2: statistic and status already written by k_fit_rlm
+//   mode 0: 2 * (1 - pt(|t|, df2))            core_functions.R:1072
+//   mode 1: pf(F, df1, df2, lower.tail=FALSE)  core_functions.R:968 (aov) / 920 (f.robftest)
+//   do_bs: also drop the edge into its p-value bucket (single-GPU runs: every edge is finished here)
+// ------------------------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(128) k_finish(int src, const double* __restrict__ sxy, const double* __restrict__ S,
+                                                int nn, SegLayout L, const int32_t* __restrict__ ea,
+                                                const int32_t* __restrict__ eb,
+                                                const double* __restrict__ mean, const double* __restrict__ sxx,
+                                                const uint8_t* __restrict__ bad, int64_t e_lo, int64_t e_hi, int mode,
+                                                double df1, double df2, TailConsts tc,
+                                                const double* __restrict__ lbeta_p, double* __restrict__ stat,
+                                                int32_t* __restrict__ status, double* __restrict__ coef,
+                                                double* __restrict__ p_out, const int32_t* __restrict__ err,
+                                                int do_bs, BsArgs B) {
+  const int64_t e = e_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = e < e_hi && !*err;
+  double p = 0.0;
+  if (live) {
+  tc.lbeta_ab = *lbeta_p;
+  if (src != 2) {
+    const int a = ea[e], b = eb[e];
+    if (a == b || bad[a] || bad[b]) {
+      const bool self = (a == b) && !bad[a];
+      stat[e] = self ? 0.0 : nan("");
+      status[e] = self ? MDEGGS_EDGE_SELFLOOP : MDEGGS_EDGE_NONFINITE;
+      if (coef)
+        for (int j = 0; j < 2 * K; ++j) coef[(size_t)e * 2 * K + j] = nan("");
+    } else {
+      PairMoments<K> pm;
+      if (src == 0) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) pm.sxy[k] = sxy[(size_t)e * K + k];
+      } else {
+        const int i = a < b ? a : b, j = a < b ? b : a;
+#pragma unroll
+        for (int k = 0; k < K; ++k) pm.sxy[k] = L.cnt[k] ? __ldg(S + ((size_t)k * nn + i) * nn + j) : 0.0;
+      }
+      finish_pair<K>(L, mean, sxx, a, b, pm, stat + e, status + e, coef ? coef + (size_t)e * 2 * K : nullptr);
+    }
+  }
+  const int st = status[e];
+  if (st == MDEGGS_EDGE_SINGULAR || st == MDEGGS_EDGE_NONFINITE || st == MDEGGS_EDGE_ZERO_SCALE) p = nan("");
+  else if (st == MDEGGS_EDGE_SELFLOOP) p = 1.0;
+  else p = (mode == 0) ? p_two_sided_ref_tab(tc, stat[e], df2) : pf_upper_tab(tc, stat[e], df1, df2);
+  p_out[e] = p;
+  }
+  if (do_bs) bs_count(B, live, e, p, gridDim.x);  // reached by every thread of the CTA
+}
+
+
+__global__ void __launch_bounds__(256) k_bsort_scatter(BsArgs B, const double* __restrict__ p_edge,
+                                                       unsigned long long* __restrict__ bkey,
+                                                       int32_t* __restrict__ bidx, const int32_t* __restrict__ err) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= B.E || *err) return;
+  const double p = p_edge[e];
+  const int pos = B.base[bs_bucket(p, B.nlin, B.scale)] + B.slot[e];
+  bkey[pos] = dkey(p);
+  bidx[pos] = (int32_t)e;
+}
+
+__device__ __forceinline__ bool bs_less(unsigned long long ka, int ia, unsigned long long kb, int ib) {
+  return ka < kb || (ka == kb && ia < ib);
+}
+
+// Bitonic sort in the "flip" formulation: every compare-exchange leaves the smaller element at the lower index, so
+// virtual +infinity padding above n never has to move and the network works for any n (pairs whose upper index is
+// >= n are skipped).  Sorts by (key, edge id).
+template <class Mem>
+__device__ __forceinline__ void bs_bitonic(Mem mem, int n, int n2) {
+  for (int k = 2; k <= n2; k <<= 1) {
+    const int hk = k >> 1;
+    for (int t = threadIdx.x; t < (n2 >> 1); t += blockDim.x) {  // flip step: i <-> mirrored partner in its k-block
+      const int blk = t / hk, w = t - blk * hk;
+      const int i = blk * k + w, x = blk * k + (k - 1 - w);
+      if (x < n) mem.cas(i, x);
+    }
+    mem.sync();
+    for (int j = hk >> 1; j > 0; j >>= 1) {
+      for (int t = threadIdx.x; t < (n2 >> 1); t += blockDim.x) {
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));  // index with bit j clear
+        const int x = i | j;
+        if (x < n) mem.cas(i, x);
+      }
+      mem.sync();
+    }
+  }
+}
+
+struct BsSmem {
+  unsigned long long* k;
+  int* i;
+  __device__ __forceinline__ void cas(int a, int b) const {
+    const unsigned long long ka = k[a], kb = k[b];
+    const int ia = i[a], ib = i[b];
+    if (bs_less(kb, ib, ka, ia)) {
+      k[a] = kb;
+      k[b] = ka;
+      i[a] = ib;
+      i[b] = ia;
+    }
+  }
+  __device__ __forceinline__ void sync() const { __syncthreads(); }
+};
+struct BsGmem {
+  unsigned long long* k;
+  int32_t* i;
+  __device__ __forceinline__ void cas(int a, int b) const {
+    const unsigned long long ka = __ldcg(k + a), kb = __ldcg(k + b);
+    const int ia = __ldcg(i + a), ib = __ldcg(i + b);
+    if (bs_less(kb, ib, ka, ia)) {
+      __stcg(k + a, kb);
+      __stcg(k + b, ka);
+      __stcg(i + a, ib);
+      __stcg(i + b, ia);
+    }
+  }
+  __device__ __forceinline__ void sync() const {
+    __threadfence_block();
+    __syncthreads();
+  }
+};
+
+// slow path for one oversize bucket [lo, hi): nothing to do when all keys are equal (any order of a tie group gives
+// the same adjusted p-values), else the same network run by this CTA directly on global memory
+__device__ void bs_sort_global(unsigned long long* __restrict__ bkey, int32_t* __restrict__ bidx, int lo, int hi) {
+  __shared__ unsigned long long s_min, s_max;
+  if (threadIdx.x == 0) {
+    s_min = ~0ull;
+    s_max = 0ull;
+  }
+  __syncthreads();
+  unsigned long long mn = ~0ull, mx = 0ull;
+  for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    const unsigned long long k = bkey[i];
+    mn = k < mn ? k : mn;
+    mx = k > mx ? k : mx;
+  }
+  atomicMin(&s_min, mn);
+  atomicMax(&s_max, mx);
+  __syncthreads();
+  const bool tie_group = s_min == s_max;
+  __syncthreads();
+  if (tie_group) return;
+  const int n = hi - lo;
+  int n2 = 1;
+  while (n2 < n) n2 <<= 1;
+  BsGmem g{bkey + lo, bidx + lo};
+  bs_bitonic(g, n, n2);
+}
+
+// one CTA per run r: the whole buckets whose first element lies in [r BS_CAP, (r+1) BS_CAP)
+__global__ void __launch_bounds__(BS_SORT_THREADS) k_bsort_sort(BsArgs B, unsigned long long* __restrict__ bkey,
+                                                               int32_t* __restrict__ bidx,
+                                                               const int32_t* __restrict__ ea,
+                                                               const int32_t* __restrict__ eb,
+                                                               double* __restrict__ ps, int32_t* __restrict__ sa,
+                                                               int32_t* __restrict__ sb, int32_t* __restrict__ sidx,
+                                                               const int32_t* __restrict__ err) {
+  __shared__ unsigned long long sk[2 * BS_CAP];
+  __shared__ int si[2 * BS_CAP];
+  __shared__ int s_b[2];
+  if (*err) return;
+  const int NB = BS_NLOG + B.nlin + 1;
+  const int r = blockIdx.x;
+  if (threadIdx.x < 2) {  // first bucket whose offset is >= (r + t) * BS_CAP
+    const long long target = (long long)(r + threadIdx.x) * BS_CAP;
+    int lo = 0, hi = NB;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if ((long long)B.base[mid] >= target) hi = mid;
+      else lo = mid + 1;
+    }
+    s_b[threadIdx.x] = lo;
+  }
+  __syncthreads();
+  const int bf = s_b[0], bl = s_b[1];
+  if (bf >= bl) return;  // no bucket starts in this window (an oversize bucket of an earlier run covers it)
+  const int lo = B.base[bf], hi = B.base[bl];
+  const int n = hi - lo;
+  if (n <= 0) return;
+  if (n <= 2 * BS_CAP) {
+    int n2 = 1;
+    while (n2 < n) n2 <<= 1;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      sk[i] = bkey[lo + i];
+      si[i] = bidx[lo + i];
+    }
+    __syncthreads();
+    bs_bitonic(BsSmem{sk, si}, n, n2);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const unsigned long long k = sk[i];
+      const int e = si[i];
+      ps[lo + i] = k != ~0ull ? dkey_inv(k) : nan("");
+      sa[lo + i] = ea[e];
+      sb[lo + i] = eb[e];
+      sidx[lo + i] = e;
+    }
+    return;
+  }
+  // the run holds an oversize bucket: bucket by bucket
+  for (int b = bf; b < bl; ++b) {
+    const int blo = B.base[b], bhi = B.base[b + 1];
+    const int bn = bhi - blo;
+    if (bn <= 0) continue;  // uniform across the CTA
+    if (bn <= 2 * BS_CAP) {
+      int n2 = 1;
+      while (n2 < bn) n2 <<= 1;
+      for (int i = threadIdx.x; i < bn; i += blockDim.x) {
+        sk[i] = bkey[blo + i];
+        si[i] = bidx[blo + i];
+      }
+      __syncthreads();
+      bs_bitonic(BsSmem{sk, si}, bn, n2);
+      for (int i = threadIdx.x; i < bn; i += blockDim.x) {
+        bkey[blo + i] = sk[i];
+        bidx[blo + i] = si[i];
+      }
+      __syncthreads();
+    } else {
+      bs_sort_global(bkey, bidx, blo, bhi);
+      __syncthreads();
+    }
+  }
+  __threadfence_block();
+  __syncthreads();
+  for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    const unsigned long long k = bkey[i];
+    const int e = bidx[i];
+    ps[i] = k != ~0ull ? dkey_inv(k) : nan("");
+    sa[i] = ea[e];
+    sb[i] = eb[e];
+    sidx[i] = e;
+  }
+}
+
+}  // namespace mdeggs

@@ -22,6 +22,7 @@
 #include <vector>
 
 #include "mdeggs.h"
+#include "mdeggs_bsort.cuh"
 #include "mdeggs_dense.cuh"
 #include "mdeggs_kernels.cuh"
 #include "mdeggs_rlm.cuh"
@@ -69,6 +70,8 @@ struct Shard {
   nccl_comm_t comm = nullptr;
   bool smem_attr_set = false, rsel_attr_set = false;  // cudaFuncSetAttribute is per device
   int64_t row_off = 0, ld_eff = 0;  // the device copy of the assay starts at host row `row_off`
+  std::vector<char> stage_shadow;   // host copy of what stage_dev currently holds
+  const void* stage_shadow_dev = nullptr;
   void* h_stage = nullptr;          // pinned host staging for the tiny per-call inputs (src_of_pos, pct, df)
   size_t h_stage_cap = 0;
   cudaError_t ensure_stage(size_t bytes) {
@@ -80,11 +83,11 @@ struct Shard {
     if (e == cudaSuccess) h_stage_cap = bytes + 256;
     return e;
   }
-  DevBuf assay, from, to, ea, eb, excl, node_of_row, rowlist, scal, src_of_pos, pct, cutoff, D, cub_tmp, mean, sxx, med, bad, stat, status, p_edge, coef, iters, act, counters, sortk, sortk2, idx,
+  DevBuf assay, from, to, ea, eb, stage_dev, bs_count, bs_slot, excl, node_of_row, rowlist, scal, src_of_pos, pct, cutoff, D, cub_tmp, mean, sxx, med, bad, stat, status, p_edge, coef, iters, act, counters, sortk, sortk2, idx,
       idx2, ps, sa, sb, tile_cnt, tile_base, seg_n, tile_min, tile_carry, padj_best, cat_best, cat, padj, med_out,
       small_out, rsel_hist, rsel_state, rsel_cand, dense_S, cf_tab, sxy;
   void release_all() {
-    DevBuf* all[] = {&assay, &from, &to, &ea, &eb, &excl, &node_of_row, &rowlist, &scal, &src_of_pos, &pct, &cutoff,
+    DevBuf* all[] = {&assay, &from, &to, &ea, &eb, &stage_dev, &bs_count, &bs_slot, &excl, &node_of_row, &rowlist, &scal, &src_of_pos, &pct, &cutoff,
                      &D, &cub_tmp, &mean, &sxx, &med, &bad, &stat, &status, &p_edge,
                      &coef, &iters, &act, &counters, &sortk, &sortk2, &idx, &idx2, &ps, &sa, &sb, &tile_cnt,
                      &tile_base, &seg_n, &tile_min, &tile_carry, &padj_best, &cat_best, &cat, &padj, &med_out,
@@ -121,6 +124,7 @@ struct mdeggs_ctx {
   int64_t graph_launches = 0;
   int64_t rsel_cap_override = 0;  // option "rsel_cap": shrink the candidate list to exercise the overflow path (tests)
   int fit_path_override = -1;  // -1 auto, 0 force streaming, 1 force dense (MDEGGS_FIT_PATH, tests)
+  int sort_path_override = -1; // -1 auto, 0 force the CUB radix sort, 1 force the bucket ordering (option "sort_path")
   // MDEGGS_TRACE=1 / option "trace": an event after every eager launch, timeline printed to stderr after the call
   int trace = 0;
   struct TraceRec {
@@ -243,6 +247,18 @@ int build_layout(mdeggs_ctx* ctx, const mdeggs_problem* in, HostLayout& H) {
   return MDEGGS_OK;
 }
 
+bool device_adjust(const mdeggs_problem* in) {
+  return in->padj == MDEGGS_PADJ_BONFERRONI || in->padj == MDEGGS_PADJ_BH || in->padj == MDEGGS_PADJ_HOLM ||
+         in->padj == MDEGGS_PADJ_HOCHBERG || in->padj == MDEGGS_PADJ_BY;
+}
+// K8 ordering by p-value buckets (mdeggs_bsort.cuh) instead of the multi-pass radix sort
+bool use_bucket_order(const mdeggs_ctx* ctx, const mdeggs_problem* in, int32_t n_nodes) {
+  if (!(device_adjust(in) && in->E > 0 && in->P > 0 && n_nodes > 0)) return false;
+  if (ctx->sort_path_override >= 0) return ctx->sort_path_override == 1 && in->E <= BS_MAX_E;
+  return in->E <= BS_MAX_E;
+}
+BsArgs make_bs_args(Shard& s, int64_t E);
+
 template <int K>
 void launch_fit_stream(mdeggs_ctx* ctx, Shard& s, const SegLayout& L, int64_t e_lo, int64_t e_hi) {
   int64_t ne = e_hi - e_lo;
@@ -257,11 +273,25 @@ void launch_fit_stream(mdeggs_ctx* ctx, Shard& s, const SegLayout& L, int64_t e_
 
 template <int K>
 void launch_finish(mdeggs_ctx* ctx, Shard& s, const SegLayout& L, int src, int nn, int64_t e_lo, int64_t e_hi, int mode,
-                   double df1, double df2, const TailConsts& tc, const double* d_lbeta, double* coef) {
+                   double df1, double df2, const TailConsts& tc, const double* d_lbeta, double* coef, int do_bs,
+                   const BsArgs& B) {
   LAUNCH(k_finish<K>, blocks_for(e_hi - e_lo, 128), 128, 0, s.s_main, src, s.sxy.as<double>(), s.dense_S.as<double>(),
          nn, L, s.ea.as<int32_t>(), s.eb.as<int32_t>(), s.mean.as<double>(),
          s.sxx.as<double>(), s.bad.as<uint8_t>(), e_lo, e_hi, mode, df1, df2, tc, d_lbeta, s.stat.as<double>(),
-         s.status.as<int32_t>(), coef, s.p_edge.as<double>(), s.scal.as<int32_t>() + 2 * SC_ERR);
+         s.status.as<int32_t>(), coef, s.p_edge.as<double>(), s.scal.as<int32_t>() + 2 * SC_ERR, do_bs, B);
+}
+
+BsArgs make_bs_args(Shard& s, int64_t E) {
+  BsArgs B;
+  const int NB = bs_nbuckets(E);
+  B.count = s.bs_count.as<int>();
+  B.base = B.count + (NB + 1);
+  B.slot = s.bs_slot.as<int32_t>();
+  B.n_valid = s.scal.as<unsigned long long>() + SC_NVALID;
+  B.nlin = bs_nlin(E);
+  B.scale = bs_scale(B.nlin);
+  B.E = E;
+  return B;
 }
 
 int copy_out(mdeggs_ctx* ctx, Shard& s, void* dst, const void* src, size_t bytes, int mem) {
@@ -403,15 +433,24 @@ int stage_inputs(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const Host
     s.from.p = (void*)d_from;
     s.to.p = (void*)d_to;  // cap stays 0 => never freed by us
   }
+  // src_of_pos and the percentile vector travel as ONE small block, and only when they differ from what the device
+  // already holds (repeated calls with the same sample layout: nestedcv folds of equal size, benchmarks)
   const size_t sop_bytes = H.src_of_pos.size() * 4, pct_bytes = (size_t)(in->P > 0 ? in->P : 0) * 8;
   const size_t pct_off = (sop_bytes + 15) & ~(size_t)15;
-  CU(s.ensure_stage(pct_off + pct_bytes + 32));
-  memcpy(s.h_stage, H.src_of_pos.data(), sop_bytes);
-  if (pct_bytes) memcpy((char*)s.h_stage + pct_off, in->pct, pct_bytes);
-  CU(s.src_of_pos.ensure(sop_bytes));
-  CU(cudaMemcpyAsync(s.src_of_pos.p, s.h_stage, sop_bytes, cudaMemcpyHostToDevice, s.s_main));
-  CU(s.pct.ensure((size_t)(in->P > 0 ? in->P : 1) * 8));
-  if (pct_bytes) CU(cudaMemcpyAsync(s.pct.p, (char*)s.h_stage + pct_off, pct_bytes, cudaMemcpyHostToDevice, s.s_main));
+  const size_t blk = pct_off + (pct_bytes ? pct_bytes : 8);
+  CU(s.ensure_stage(blk + 64));
+  CU(s.stage_dev.ensure(blk));
+  std::vector<char> cur(blk, 0);
+  memcpy(cur.data(), H.src_of_pos.data(), sop_bytes);
+  if (pct_bytes) memcpy(cur.data() + pct_off, in->pct, pct_bytes);
+  if (s.stage_shadow_dev != s.stage_dev.p || cur != s.stage_shadow) {
+    memcpy(s.h_stage, cur.data(), blk);
+    CU(cudaMemcpyAsync(s.stage_dev.p, s.h_stage, blk, cudaMemcpyHostToDevice, s.s_main));
+    s.stage_shadow.swap(cur);
+    s.stage_shadow_dev = s.stage_dev.p;
+  }
+  s.src_of_pos.p = s.stage_dev.p;  // borrowed views (cap == 0: never freed through these slots)
+  s.pct.p = s.stage_dev.as<char>() + pct_off;
   CU(cudaEventRecord(s.ev[EV_H2D], s.s_main));
   trace_mark(ctx, "(inputs staged)", s.s_main);
   return MDEGGS_OK;
@@ -661,14 +700,26 @@ int run_shard_main(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
     tc.e_ba = s.cf_tab.as<double>() + CF_TABLE_LEN;
     const double* d_lbeta = s.cf_tab.as<double>() + 2 * CF_TABLE_LEN;
     const int src = is_rlm ? 2 : (use_dense ? 1 : 0);
+    // single GPU: every edge passes through this launch, which then also feeds the p-value buckets of K8
+    const bool bs = use_bucket_order(ctx, in, n_nodes);
+    const int do_bs = bs && s.world == 1;
+    BsArgs B;
+    memset(&B, 0, sizeof B);
+    if (bs) {
+      const int NB = bs_nbuckets(E);
+      CU(s.bs_count.ensure((size_t)2 * (NB + 1) * 4));
+      CU(s.bs_slot.ensure((size_t)E * 4));
+      CU(cudaMemsetAsync(s.bs_count.p, 0, (size_t)(NB + 1) * 4, s.s_main));
+      B = make_bs_args(s, E);
+    }
     switch (K) {
-      case 2: launch_finish<2>(ctx, s, L, src, n_nodes, e_lo, e_hi, tail_mode, df1, df2, tc, d_lbeta, d_coef); break;
-      case 3: launch_finish<3>(ctx, s, L, src, n_nodes, e_lo, e_hi, tail_mode, df1, df2, tc, d_lbeta, d_coef); break;
-      case 4: launch_finish<4>(ctx, s, L, src, n_nodes, e_lo, e_hi, tail_mode, df1, df2, tc, d_lbeta, d_coef); break;
-      case 5: launch_finish<5>(ctx, s, L, src, n_nodes, e_lo, e_hi, tail_mode, df1, df2, tc, d_lbeta, d_coef); break;
-      case 6: launch_finish<6>(ctx, s, L, src, n_nodes, e_lo, e_hi, tail_mode, df1, df2, tc, d_lbeta, d_coef); break;
-      case 7: launch_finish<7>(ctx, s, L, src, n_nodes, e_lo, e_hi, tail_mode, df1, df2, tc, d_lbeta, d_coef); break;
-      default: launch_finish<8>(ctx, s, L, src, n_nodes, e_lo, e_hi, tail_mode, df1, df2, tc, d_lbeta, d_coef); break;
+      case 2: launch_finish<2>(ctx, s, L, src, n_nodes, e_lo, e_hi, tail_mode, df1, df2, tc, d_lbeta, d_coef, do_bs, B); break;
+      case 3: launch_finish<3>(ctx, s, L, src, n_nodes, e_lo, e_hi, tail_mode, df1, df2, tc, d_lbeta, d_coef, do_bs, B); break;
+      case 4: launch_finish<4>(ctx, s, L, src, n_nodes, e_lo, e_hi, tail_mode, df1, df2, tc, d_lbeta, d_coef, do_bs, B); break;
+      case 5: launch_finish<5>(ctx, s, L, src, n_nodes, e_lo, e_hi, tail_mode, df1, df2, tc, d_lbeta, d_coef, do_bs, B); break;
+      case 6: launch_finish<6>(ctx, s, L, src, n_nodes, e_lo, e_hi, tail_mode, df1, df2, tc, d_lbeta, d_coef, do_bs, B); break;
+      case 7: launch_finish<7>(ctx, s, L, src, n_nodes, e_lo, e_hi, tail_mode, df1, df2, tc, d_lbeta, d_coef, do_bs, B); break;
+      default: launch_finish<8>(ctx, s, L, src, n_nodes, e_lo, e_hi, tail_mode, df1, df2, tc, d_lbeta, d_coef, do_bs, B); break;
     }
   }
   EVREC(s.ev[EV_TAIL], s.s_main);
@@ -736,21 +787,43 @@ int run_shard_back(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
     CU(s.ps.ensure((size_t)E * 8));
     CU(s.sa.ensure((size_t)E * 4));
     CU(s.sb.ensure((size_t)E * 4));
-    LAUNCH(k_sort_keys, blocks_for(E, 256), 256, 0, s.s_main, s.p_edge.as<double>(), E,
-           s.sortk.as<unsigned long long>(), s.idx.as<int32_t>());
-    size_t tb = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, tb, s.sortk.as<unsigned long long>(), s.sortk2.as<unsigned long long>(),
-                                    s.idx.as<int32_t>(), s.idx2.as<int32_t>(), E, 0, 64, s.s_main);
-    CU(s.cub_tmp.ensure(tb));
-    CU(cub::DeviceRadixSort::SortPairs(s.cub_tmp.p, tb, s.sortk.as<unsigned long long>(),
-                                       s.sortk2.as<unsigned long long>(), s.idx.as<int32_t>(), s.idx2.as<int32_t>(), E,
-                                       0, 64, s.s_main));
-    ctx->launches += 10;
-    trace_mark(ctx, "cub::SortPairs", s.s_main);
-    LAUNCH(k_gather_sorted, blocks_for(E, 256), 256, 0, s.s_main, s.sortk2.as<unsigned long long>(),
-           s.idx2.as<int32_t>(), s.ea.as<int32_t>(), s.eb.as<int32_t>(), E,
-           s.ps.as<double>(), s.sa.as<int32_t>(), s.sb.as<int32_t>(), s.scal.as<unsigned long long>() + SC_NVALID,
-           s.scal.as<int32_t>() + 2 * SC_ERR);
+    if (use_bucket_order(ctx, in, n_nodes)) {
+      // bucket ordering (mdeggs_bsort.cuh): counts/slots came out of k_finish (single GPU) or from a counting pass
+      // over the all-gathered p-values; scatter into buckets, then one CTA per run of buckets sorts in shared memory
+      BsArgs B;
+      if (s.world > 1) {
+        const int NB = bs_nbuckets(E);
+        CU(s.bs_count.ensure((size_t)2 * (NB + 1) * 4));
+        CU(s.bs_slot.ensure((size_t)E * 4));
+        CU(cudaMemsetAsync(s.bs_count.p, 0, (size_t)(NB + 1) * 4, s.s_main));
+        B = make_bs_args(s, E);
+        LAUNCH(k_bsort_count, blocks_for(E, 256), 256, 0, s.s_main, B, s.p_edge.as<double>(),
+               s.scal.as<int32_t>() + 2 * SC_ERR);
+      } else {
+        B = make_bs_args(s, E);
+      }
+      LAUNCH(k_bsort_scatter, blocks_for(E, 256), 256, 0, s.s_main, B, s.p_edge.as<double>(),
+             s.sortk.as<unsigned long long>(), s.idx.as<int32_t>(), s.scal.as<int32_t>() + 2 * SC_ERR);
+      LAUNCH(k_bsort_sort, blocks_for(E, BS_CAP), BS_SORT_THREADS, 0, s.s_main, B, s.sortk.as<unsigned long long>(),
+             s.idx.as<int32_t>(), s.ea.as<int32_t>(), s.eb.as<int32_t>(), s.ps.as<double>(), s.sa.as<int32_t>(),
+             s.sb.as<int32_t>(), s.idx2.as<int32_t>(), s.scal.as<int32_t>() + 2 * SC_ERR);
+    } else {
+      LAUNCH(k_sort_keys, blocks_for(E, 256), 256, 0, s.s_main, s.p_edge.as<double>(), E,
+             s.sortk.as<unsigned long long>(), s.idx.as<int32_t>());
+      size_t tb = 0;
+      cub::DeviceRadixSort::SortPairs(nullptr, tb, s.sortk.as<unsigned long long>(), s.sortk2.as<unsigned long long>(),
+                                      s.idx.as<int32_t>(), s.idx2.as<int32_t>(), E, 0, 64, s.s_main);
+      CU(s.cub_tmp.ensure(tb));
+      CU(cub::DeviceRadixSort::SortPairs(s.cub_tmp.p, tb, s.sortk.as<unsigned long long>(),
+                                         s.sortk2.as<unsigned long long>(), s.idx.as<int32_t>(), s.idx2.as<int32_t>(), E,
+                                         0, 64, s.s_main));
+      ctx->launches += 10;
+      trace_mark(ctx, "cub::SortPairs", s.s_main);
+      LAUNCH(k_gather_sorted, blocks_for(E, 256), 256, 0, s.s_main, s.sortk2.as<unsigned long long>(),
+             s.idx2.as<int32_t>(), s.ea.as<int32_t>(), s.eb.as<int32_t>(), E,
+             s.ps.as<double>(), s.sa.as<int32_t>(), s.sb.as<int32_t>(), s.scal.as<unsigned long long>() + SC_NVALID,
+             s.scal.as<int32_t>() + 2 * SC_ERR);
+    }
   }
   CU(cudaStreamWaitEvent(s.s_main, s.ev_join, 0));  // cut-offs ready
   trace_mark(ctx, "(join quantile stream)", s.s_main);
@@ -965,6 +1038,8 @@ int emit_outputs(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const mdeg
       CU(cudaMemcpyAsync(out->df, st, 16, cudaMemcpyHostToDevice, s.s_main));
     }
   }
+  // node count + error flag ride along to pinned memory (read after the final sync, no extra blocking copy)
+  CU(cudaMemcpyAsync((char*)s.h_stage + s.h_stage_cap - 48, s.scal.p, 16, cudaMemcpyDeviceToHost, s.s_main));
   CU(cudaEventRecord(s.ev[EV_END], s.s_main));
   trace_mark(ctx, "(outputs copied)", s.s_main);
   return MDEGGS_OK;
@@ -1257,8 +1332,8 @@ int mdeggs_run_omic(mdeggs_ctx* ctx, const mdeggs_problem* in, mdeggs_result* ou
   CU(cudaGetLastError());  // kernel launches are not checked one by one: surface any launch failure here
   Shard& s0 = ctx->shards[0];
   {
-    long long host_scal[2] = {0, 0};
-    CU(cudaMemcpy(host_scal, s0.scal.p, 16, cudaMemcpyDeviceToHost));
+    long long host_scal[2];
+    memcpy(host_scal, (char*)s0.h_stage + s0.h_stage_cap - 48, 16);
     if ((int32_t)host_scal[SC_ERR] != 0) {
       set_err(ctx, "from/to contain an index outside 1..G");
       return MDEGGS_EINVAL;
@@ -1294,6 +1369,7 @@ int mdeggs_run_omic(mdeggs_ctx* ctx, const mdeggs_problem* in, mdeggs_result* ou
   st.ms_percolate = ev_ms(s0.ev[EV_COLL], s0.ev[EV_PERC]);
   st.ms_adjust = ev_ms(s0.ev[EV_PERC], s0.ev[EV_ADJ]);
   st.ms_d2h = ev_ms(s0.ev[EV_ADJ], s0.ev[EV_END]);
+  if (use_bucket_order(ctx, in, n_nodes)) st.fit_path |= 0x200;  // bit 9: K8 ordering by p-value buckets (no radix sort)
   if (replayed) {  // graph replay: no stage boundaries inside the graph; everything between H2D and D2H is compute
     st.ms_gather = st.ms_stats = st.ms_quantile = st.ms_fit = st.ms_tail = st.ms_collective = st.ms_percolate = 0.f;
     st.ms_adjust = 0.f;
@@ -1321,6 +1397,11 @@ int mdeggs_set_option(mdeggs_ctx* ctx, const char* name, int64_t value) {
   }
   if (!strcmp(name, "rsel_cap")) {
     ctx->rsel_cap_override = value;
+    ctx->key_valid = false;
+    return MDEGGS_OK;
+  }
+  if (!strcmp(name, "sort_path")) {
+    ctx->sort_path_override = (int)value;
     ctx->key_valid = false;
     return MDEGGS_OK;
   }

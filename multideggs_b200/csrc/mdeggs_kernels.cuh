@@ -611,54 +611,7 @@ __global__ void __launch_bounds__(256, 4) k_fit_stream(const double* __restrict_
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// finish, one thread per edge: closed-form statistic from the cross moments, then the tail probability
-//   src 0: moments from k_fit_stream (sxy[e][K]);  src 1: moments from the dense matrices S[k][i][j];
-//   src 2: statistic and status already written by k_fit_rlm
-//   mode 0: 2 * (1 - pt(|t|, df2))            core_functions.R:1072
-//   mode 1: pf(F, df1, df2, lower.tail=FALSE)  core_functions.R:968 (aov) / 920 (f.robftest)
-// ------------------------------------------------------------------------------------------------
-template <int K>
-__global__ void __launch_bounds__(128) k_finish(int src, const double* __restrict__ sxy, const double* __restrict__ S,
-                                                int nn, SegLayout L, const int32_t* __restrict__ ea,
-                                                const int32_t* __restrict__ eb,
-                                                const double* __restrict__ mean, const double* __restrict__ sxx,
-                                                const uint8_t* __restrict__ bad, int64_t e_lo, int64_t e_hi, int mode,
-                                                double df1, double df2, TailConsts tc,
-                                                const double* __restrict__ lbeta_p, double* __restrict__ stat,
-                                                int32_t* __restrict__ status, double* __restrict__ coef,
-                                                double* __restrict__ p_out, const int32_t* __restrict__ err) {
-  const int64_t e = e_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= e_hi || *err) return;
-  tc.lbeta_ab = *lbeta_p;
-  if (src != 2) {
-    const int a = ea[e], b = eb[e];
-    if (a == b || bad[a] || bad[b]) {
-      const bool self = (a == b) && !bad[a];
-      stat[e] = self ? 0.0 : nan("");
-      status[e] = self ? MDEGGS_EDGE_SELFLOOP : MDEGGS_EDGE_NONFINITE;
-      if (coef)
-        for (int j = 0; j < 2 * K; ++j) coef[(size_t)e * 2 * K + j] = nan("");
-    } else {
-      PairMoments<K> pm;
-      if (src == 0) {
-#pragma unroll
-        for (int k = 0; k < K; ++k) pm.sxy[k] = sxy[(size_t)e * K + k];
-      } else {
-        const int i = a < b ? a : b, j = a < b ? b : a;
-#pragma unroll
-        for (int k = 0; k < K; ++k) pm.sxy[k] = L.cnt[k] ? __ldg(S + ((size_t)k * nn + i) * nn + j) : 0.0;
-      }
-      finish_pair<K>(L, mean, sxx, a, b, pm, stat + e, status + e, coef ? coef + (size_t)e * 2 * K : nullptr);
-    }
-  }
-  const int st = status[e];
-  double p;
-  if (st == MDEGGS_EDGE_SINGULAR || st == MDEGGS_EDGE_NONFINITE || st == MDEGGS_EDGE_ZERO_SCALE) p = nan("");
-  else if (st == MDEGGS_EDGE_SELFLOOP) p = 1.0;
-  else p = (mode == 0) ? p_two_sided_ref_tab(tc, stat[e], df2) : pf_upper_tab(tc, stat[e], df1, df2);
-  p_out[e] = p;
-}
+// (k_finish itself lives in mdeggs_bsort.cuh: it also feeds the p-value bucket counts of the K8 ordering)
 
 // ------------------------------------------------------------------------------------------------
 // K7: percolation masks   (calc_pvalues_percentile, core_functions.R:723-779)

@@ -209,13 +209,13 @@ def test_dense_tile_path_matches_oracle(oracle, nf, n, K, monkeypatch):
     to = np.where(flip, iu[sel], ju[sel]) + 1
     prob.from_idx, prob.to_idx = fr.astype(np.int32), to.astype(np.int32)
     gpu = eng.run_omic(prob, ALL_FIELDS)
-    assert eng.stats()["fit_path"] == 1
+    assert eng.stats()["fit_path"] & 0xff == 1
     ref = oracle.run_omic(prob, ALL_FIELDS)
     assert_parity(gpu, ref, prob, what=f"dense nf{nf} n{n} K{K}: ")
     monkeypatch.setenv("MDEGGS_FIT_PATH", "0")
     eng0 = md.Engine([0])
     gpu0 = eng0.run_omic(prob, ALL_FIELDS)
-    assert eng0.stats()["fit_path"] == 0
+    assert eng0.stats()["fit_path"] & 0xff == 0
     assert np.array_equal(gpu0["status"], gpu["status"]) and np.array_equal(gpu0["cat_best"], gpu["cat_best"])
     assert np.allclose(gpu0["stat"], gpu["stat"], rtol=1e-10, atol=0, equal_nan=True)
     eng.close()
@@ -420,3 +420,58 @@ def test_invalid_edge_index_is_reported(engine):
         engine.run_omic(prob)
     big = synth.random_problem(30, 20, 40, 2, 79)   # the context stays usable afterwards
     assert engine.run_omic(big)["best"].shape == (1,)
+
+
+@pytest.mark.parametrize("padj", [_abi.PADJ_BH, _abi.PADJ_HOLM, _abi.PADJ_HOCHBERG, _abi.PADJ_BY, _abi.PADJ_BONFERRONI])
+def test_bucket_order_equals_radix_sort(padj):
+    """K8 ordering through p-value buckets (default up to 4M edges) must give bit-identical adjusted values,
+    counts and best percentile as the CUB radix-sort path, including tie groups (p == 1 self-loops, NaN)."""
+    eng = md.Engine([0])
+    eng.set_option("graph", 0)
+    want = ("p_edge", "padj", "padj_best", "sig_count", "tot_edges", "best", "cat_best", "status")
+    for K, seed, E in ((2, 11, 5000), (3, 12, 40000)):
+        prob = synth.random_problem(300, 64, E, K, seed, _abi.METHOD_LM, padj)
+        prob.from_idx[:50] = prob.to_idx[:50]              # self-loops: a tie group at p == 1
+        prob.assay[7, 3] = np.nan                          # a non-finite gene: NaN p-values (sorted last)
+        eng.set_option("sort_path", 0)
+        ref = eng.run_omic(prob, want)
+        assert not (eng.stats()["fit_path"] & 0x200)
+        eng.set_option("sort_path", 1)
+        got = eng.run_omic(prob, want)
+        assert eng.stats()["fit_path"] & 0x200, "bucket ordering did not engage"
+        for k in want:
+            assert np.array_equal(got[k], ref[k], equal_nan=True), (K, k)
+    eng.close()
+
+
+def test_bucket_order_oversize_buckets(oracle):
+    """Degenerate p-value distributions: thousands of identical p-values (one oversize tie bucket) and thousands of
+    distinct p-values inside one bucket (global-memory sort path)."""
+    eng = md.Engine([0])
+    eng.set_option("graph", 0)
+    rng = np.random.default_rng(5)
+    G, n, K = 400, 40, 2
+    # (a) all edges are the same gene pair repeated -> one huge tie group; (b) edges between near-identical genes:
+    # tiny p-values of almost the same magnitude -> one binade bucket with thousands of distinct keys
+    base = rng.normal(5, 1, size=n)
+    assay = rng.normal(5, 1, size=(G, n))
+    grp = (np.arange(n) % 2 + 1).astype(np.int32)
+    sign = np.where(grp == 1, 1.0, -1.0)
+    for g in range(200):
+        assay[g] = base * sign + rng.normal(0, 1e-3, size=n) if g % 2 else base + rng.normal(0, 1e-3, size=n)
+    assay = np.asfortranarray(assay)
+    E = 6000
+    fr = np.concatenate([np.full(3000, 301), 2 * rng.integers(0, 100, 3000) + 1]).astype(np.int32)
+    to = np.concatenate([np.full(3000, 302), 2 * rng.integers(0, 100, 3000) + 2]).astype(np.int32)
+    prob = _abi.Problem(assay=assay, from_idx=fr, to_idx=to, group=grp, K=K, pct=np.array([0.1, 0.5]),
+                     method=_abi.METHOD_LM, padj=_abi.PADJ_BH)
+    want = ("p_edge", "padj", "sig_count", "tot_edges", "best", "status")
+    eng.set_option("sort_path", 0)
+    ref = eng.run_omic(prob, want)
+    eng.set_option("sort_path", 1)
+    got = eng.run_omic(prob, want)
+    for k in want:
+        assert np.array_equal(got[k], ref[k], equal_nan=True), k
+    orc = oracle.run_omic(prob, want)
+    assert np.array_equal(got["sig_count"], orc["sig_count"])
+    eng.close()
