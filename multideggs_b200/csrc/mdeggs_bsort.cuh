@@ -8,10 +8,11 @@
 //   1. the kernel that produces p (k_finish) drops every edge into one of NB monotone buckets of its p-value
 //      (bs_bucket: one bucket per binade below 2^-10, equal-width buckets above — balanced for uniform null p-values
 //      and for the heavy left tail of true signals) with a warp-aggregated atomic that also hands the edge its slot
-//      inside the bucket; the last CTA to finish turns the bucket counts into offsets;
-//   2. k_bsort_scatter writes (key, edge) to offset[bucket] + slot;
-//   3. k_bsort_sort: one CTA per run of whole buckets (~BS_CAP..2 BS_CAP elements) sorts the run in shared memory
-//      (bitonic on (key, edge id), so the order is deterministic) and emits what the BH passes read: p in ascending
+//      inside the bucket;
+//   2. k_bsort_scatter turns the bucket counts into offsets (every CTA scans the few thousand counts itself) and
+//      writes (key, edge) to offset[bucket] + slot;
+//   3. k_bsort_sort: one CTA per run of whole buckets (~BS_CAP..2 BS_CAP elements) orders the run in shared memory
+//      (a warp ranks each small bucket by (key, edge id), so the order is deterministic) and emits what the BH passes read: p in ascending
 //      order, the node ids of the two end points, the edge id.
 // Three short launches after k_finish.  A bucket that alone exceeds the shared-memory capacity (a pathological
 // concentration of distinct p-values; a group of IDENTICAL p-values needs no ordering at all since every p.adjust
@@ -27,6 +28,8 @@ namespace mdeggs {
 constexpr int BS_NLOG = 1013;       // buckets 0..1012: biased exponent of p < 2^-10 (0 also holds p <= 0)
 constexpr int BS_CAP = 1024;        // run granularity; shared memory holds 2 * BS_CAP elements
 constexpr int BS_SORT_THREADS = 512;
+constexpr int BS_RUN_BUCKETS = 2048;  // bucket offsets of a run kept in shared memory
+constexpr int BS_WARP_MAX = 128;    // largest bucket a single warp ranks by itself
 constexpr int64_t BS_MAX_E = 1 << 22;  // beyond this the CUB radix sort is used
 
 __host__ __device__ __forceinline__ int bs_nlin(int64_t E) {
@@ -48,8 +51,8 @@ __device__ __forceinline__ int bs_bucket(double p, int nlin, double scale) {
 __host__ __device__ __forceinline__ double bs_scale(int nlin) { return (double)nlin / (1.0 - 0x1p-10); }
 
 struct BsArgs {
-  int* count;        // [NB + 1]: bucket counts; count[NB] is the "CTAs done" counter (all zeroed before the run)
-  int* base;         // [NB + 1]: exclusive prefix of the counts (written by the last CTA)
+  int* count;        // [NB + 1]: bucket counts (zeroed before the run)
+  int* base;         // [NB + 1]: exclusive prefix of the counts
   int32_t* slot;     // [E]: position of the edge inside its bucket
   unsigned long long* n_valid;  // E - #NaN, for the BH passes
   int nlin;
@@ -57,10 +60,8 @@ struct BsArgs {
   int64_t E;
 };
 
-// One call per thread of a kernel that covers edges; `live` threads contribute p.  Must be reached by every thread of
-// the CTA (no early returns before it).  `n_ctas` CTAs take part in total.
-__device__ __forceinline__ void bs_count(const BsArgs& B, bool live, int64_t e, double p, unsigned n_ctas) {
-  const int NB = BS_NLOG + B.nlin + 1;
+// One call per thread of a kernel that covers edges; `live` threads contribute p.  Must be reached by whole warps.
+__device__ __forceinline__ void bs_count(const BsArgs& B, bool live, int64_t e, double p) {
   const int lane = threadIdx.x & 31;
   int b = live ? bs_bucket(p, B.nlin, B.scale) : -1 - lane;  // dead lanes never match anyone
   const unsigned peers = __match_any_sync(0xffffffffu, b);
@@ -71,24 +72,29 @@ __device__ __forceinline__ void bs_count(const BsArgs& B, bool live, int64_t e, 
     base = __shfl_sync(peers, base, leader);
     B.slot[e] = base + __popc(peers & ((1u << lane) - 1u));
   }
-  // last CTA: counts -> offsets
-  __shared__ int s_is_last;
-  __shared__ int s_warp_tot[32];
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) s_is_last = (atomicAdd(&B.count[NB], 1) == (int)n_ctas - 1);
-  __syncthreads();
-  if (!s_is_last) return;
-  __threadfence();
-  const int nthr = blockDim.x, nwarp = nthr >> 5, wid = threadIdx.x >> 5;
-  constexpr int ITEMS = 8;  // independent loads per thread and round
+}
+
+// exclusive prefix of count[0..NB) by one CTA into `out` (shared or global); returns the total to every thread.
+// `s_warp_tot` is a 32-int shared scratch.
+__device__ __forceinline__ int bs_scan_counts(const int* __restrict__ count, int NB, int* __restrict__ out,
+                                              int* __restrict__ s_warp_tot) {
+  const int nthr = blockDim.x, nwarp = nthr >> 5, wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int ITEMS = 4;  // one 16-byte load / store per thread and round (count and out are 16-byte aligned and
+                            // padded to a multiple of 4 entries)
   int carry = 0;
   for (int c0 = 0; c0 < NB; c0 += nthr * ITEMS) {
     const int i0 = c0 + threadIdx.x * ITEMS;
-    int v[ITEMS], mine = 0;
+    int v[ITEMS] = {0, 0, 0, 0}, mine = 0;
+    if (i0 < NB) {
+      const int4 q = __ldcg(reinterpret_cast<const int4*>(count + i0));
+      v[0] = q.x;
+      v[1] = q.y;
+      v[2] = q.z;
+      v[3] = q.w;
+    }
 #pragma unroll
     for (int j = 0; j < ITEMS; ++j) {
-      v[j] = i0 + j < NB ? __ldcg(B.count + i0 + j) : 0;
+      v[j] = i0 + j < NB ? v[j] : 0;
       mine += v[j];
     }
     int incl = mine;
@@ -105,20 +111,12 @@ __device__ __forceinline__ void bs_count(const BsArgs& B, bool live, int64_t e, 
       woff += w < wid ? t : 0;
       tot += t;
     }
-    int run = carry + woff + incl - mine;
-#pragma unroll
-    for (int j = 0; j < ITEMS; ++j)
-      if (i0 + j < NB) {
-        B.base[i0 + j] = run;
-        run += v[j];
-      }
+    const int run = carry + woff + incl - mine;
+    if (i0 < NB) *reinterpret_cast<int4*>(out + i0) = make_int4(run, run + v[0], run + v[0] + v[1], run + v[0] + v[1] + v[2]);
     carry += tot;
     __syncthreads();
   }
-  if (threadIdx.x == 0) {
-    B.base[NB] = carry;  // == number of edges counted
-    *B.n_valid = (unsigned long long)(carry - __ldcg(B.count + NB - 1));
-  }
+  return carry;
 }
 
 // stand-alone counting pass (multi-GPU: the p-values arrive through the all-gather, after k_finish)
@@ -126,7 +124,18 @@ __global__ void __launch_bounds__(256) k_bsort_count(BsArgs B, const double* __r
                                                      const int32_t* __restrict__ err) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = e < B.E && !*err;
-  bs_count(B, live, e, live ? p_edge[e] : 0.0, gridDim.x);
+  bs_count(B, live, e, live ? p_edge[e] : 0.0);
+}
+
+// bucket offsets for large bucket counts (otherwise every scatter CTA scans the counts itself)
+__global__ void __launch_bounds__(1024) k_bsort_scan(BsArgs B) {
+  __shared__ int s_warp_tot[32];
+  const int NB = BS_NLOG + B.nlin + 1;
+  const int total = bs_scan_counts(B.count, NB, B.base, s_warp_tot);
+  if (threadIdx.x == 0) {
+    B.base[NB] = total;
+    *B.n_valid = (unsigned long long)(total - __ldcg(B.count + NB - 1));
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -180,17 +189,36 @@ __global__ void __launch_bounds__(128) k_finish(int src, const double* __restric
   else p = (mode == 0) ? p_two_sided_ref_tab(tc, stat[e], df2) : pf_upper_tab(tc, stat[e], df1, df2);
   p_out[e] = p;
   }
-  if (do_bs) bs_count(B, live, e, p, gridDim.x);  // reached by every thread of the CTA
+  if (do_bs) bs_count(B, live, e, p);  // reached by every thread of the CTA
 }
 
 
-__global__ void __launch_bounds__(256) k_bsort_scatter(BsArgs B, const double* __restrict__ p_edge,
+// scan_in_cta: the bucket offsets are not in B.base yet: every CTA computes them from the counts in shared memory
+// (NB <= BS_SCAN_SMEM), CTA 0 publishes them for k_bsort_sort and the BH passes
+constexpr int BS_SCAN_SMEM = 8192;
+__global__ void __launch_bounds__(256) k_bsort_scatter(BsArgs B, int scan_in_cta, const double* __restrict__ p_edge,
                                                        unsigned long long* __restrict__ bkey,
                                                        int32_t* __restrict__ bidx, const int32_t* __restrict__ err) {
+  extern __shared__ int s_base[];  // NB ints when scan_in_cta
+  __shared__ int s_warp_tot[32];
+  if (*err) return;
+  const int* base = B.base;
+  if (scan_in_cta) {
+    const int NB = BS_NLOG + B.nlin + 1;
+    const int total = bs_scan_counts(B.count, NB, s_base, s_warp_tot);
+    if (blockIdx.x == 0) {
+      for (int i = threadIdx.x; i < NB; i += blockDim.x) B.base[i] = s_base[i];
+      if (threadIdx.x == 0) {
+        B.base[NB] = total;
+        *B.n_valid = (unsigned long long)(total - __ldcg(B.count + NB - 1));
+      }
+    }
+    base = s_base;
+  }
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= B.E || *err) return;
+  if (e >= B.E) return;
   const double p = p_edge[e];
-  const int pos = B.base[bs_bucket(p, B.nlin, B.scale)] + B.slot[e];
+  const int pos = base[bs_bucket(p, B.nlin, B.scale)] + B.slot[e];
   bkey[pos] = dkey(p);
   bidx[pos] = (int32_t)e;
 }
@@ -316,21 +344,75 @@ __global__ void __launch_bounds__(BS_SORT_THREADS) k_bsort_sort(BsArgs B, unsign
   const int n = hi - lo;
   if (n <= 0) return;
   if (n <= 2 * BS_CAP) {
-    int n2 = 1;
-    while (n2 < n) n2 <<= 1;
+    // The run fits in shared memory.  Buckets are tiny on average (~16 edges): a warp takes a bucket of up to
+    // BS_WARP_MAX elements and ranks each element against the whole bucket with broadcast shared-memory reads (no
+    // barrier, no sorting network); the rare larger bucket is sorted by the whole CTA afterwards.
+    __shared__ int s_big[64];
+    __shared__ int s_nbig;
+    __shared__ int s_bb[BS_RUN_BUCKETS + 1];  // offsets of this run's buckets (run 0 alone spans the ~1000 binade buckets)
+    const int nbk = bl - bf;
+    const bool bb_smem = nbk <= BS_RUN_BUCKETS;
+    if (bb_smem)
+      for (int i = threadIdx.x; i <= nbk; i += blockDim.x) s_bb[i] = B.base[bf + i];
+    auto bucket_base = [&](int b) { return bb_smem ? s_bb[b - bf] : B.base[b]; };
+    if (threadIdx.x == 0) s_nbig = 0;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
       sk[i] = bkey[lo + i];
       si[i] = bidx[lo + i];
     }
     __syncthreads();
-    bs_bitonic(BsSmem{sk, si}, n, n2);
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      const unsigned long long k = sk[i];
-      const int e = si[i];
-      ps[lo + i] = k != ~0ull ? dkey_inv(k) : nan("");
-      sa[lo + i] = ea[e];
-      sb[lo + i] = eb[e];
-      sidx[lo + i] = e;
+    auto emit = [&](int pos, unsigned long long k, int e) {
+      ps[pos] = k != ~0ull ? dkey_inv(k) : nan("");
+      sa[pos] = ea[e];
+      sb[pos] = eb[e];
+      sidx[pos] = e;
+    };
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    for (int b = bf + warp; b < bl; b += nwarp) {
+      const int blo = bucket_base(b) - lo, bn = bucket_base(b + 1) - bucket_base(b);
+      if (bn <= 0) continue;
+      if (bn > BS_WARP_MAX) {
+        if (lane == 0) {
+          const int at = atomicAdd(&s_nbig, 1);
+          if (at < 64) s_big[at] = b;
+        }
+        continue;
+      }
+      unsigned long long mk[BS_WARP_MAX / 32];
+      int me[BS_WARP_MAX / 32], rk[BS_WARP_MAX / 32];
+#pragma unroll
+      for (int u = 0; u < BS_WARP_MAX / 32; ++u) {
+        const int i = u * 32 + lane;
+        mk[u] = i < bn ? sk[blo + i] : ~0ull;
+        me[u] = i < bn ? si[blo + i] : 0x7fffffff;
+        rk[u] = 0;
+      }
+      for (int t = 0; t < bn; ++t) {
+        const unsigned long long k = sk[blo + t];  // broadcast
+        const int e = si[blo + t];
+#pragma unroll
+        for (int u = 0; u < BS_WARP_MAX / 32; ++u) rk[u] += bs_less(k, e, mk[u], me[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < BS_WARP_MAX / 32; ++u)
+        if (u * 32 + lane < bn) emit(lo + blo + rk[u], mk[u], me[u]);
+    }
+    __syncthreads();
+    const int nbig = s_nbig;
+    if (nbig > 64) {  // (cannot happen: 64 buckets of > BS_WARP_MAX elements do not fit a run) sort the whole run
+      int n2 = 1;
+      while (n2 < n) n2 <<= 1;
+      bs_bitonic(BsSmem{sk, si}, n, n2);
+      for (int i = threadIdx.x; i < n; i += blockDim.x) emit(lo + i, sk[i], si[i]);
+      return;
+    }
+    for (int q = 0; q < nbig; ++q) {
+      const int b = s_big[q];
+      const int blo = B.base[b] - lo, bn = B.base[b + 1] - B.base[b];
+      int n2 = 1;
+      while (n2 < bn) n2 <<= 1;
+      bs_bitonic(BsSmem{sk + blo, si + blo}, bn, n2);
+      for (int i = threadIdx.x; i < bn; i += blockDim.x) emit(lo + blo + i, sk[blo + i], si[blo + i]);
     }
     return;
   }

@@ -2,7 +2,7 @@
 //
 // One `mdeggs_run_omic` call = one omic layer of get_diffNetworks_singleOmic (R/core_functions.R:258-529)
 // from "edges selected" to "best percentile chosen".  Pipeline per GPU (stream s_main unless noted):
-//   H2D -> K0 node filter -> K1 gather/transposition -> { K3 radix sort + quantiles on s_sort }
+//   H2D -> K0 node filter -> K1 gather/transposition (+ K3 value histogram) -> { K3 quantile selection on s_sort }
 //        -> K2 gene stats -> K4/K5/K6 pair fits on this rank's edge block -> tail probabilities
 //        -> [NCCL all-gather of p/status over NVLink when world > 1] -> K7 percolation masks
 //        -> K8 sort-once + per-(percentile,category) Bonferroni/BH + counts -> best percentile -> D2H
@@ -26,7 +26,7 @@
 #include "mdeggs_dense.cuh"
 #include "mdeggs_kernels.cuh"
 #include "mdeggs_rlm.cuh"
-#include "mdeggs_select.cuh"
+#include "mdeggs_qsel.cuh"
 #include "nccl_dl.h"
 
 using namespace mdeggs;
@@ -66,7 +66,7 @@ struct Shard {
   int device = 0, rank = 0, world = 1;
   cudaStream_t s_main = nullptr, s_sort = nullptr;
   cudaEvent_t ev[EV_COUNT] = {};
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_sample = nullptr;
   nccl_comm_t comm = nullptr;
   bool smem_attr_set = false, rsel_attr_set = false;  // cudaFuncSetAttribute is per device
   int64_t row_off = 0, ld_eff = 0;  // the device copy of the assay starts at host row `row_off`
@@ -205,10 +205,15 @@ inline unsigned blocks_for(int64_t n, int threads) { return (unsigned)((n + thre
 int init_shard(mdeggs_ctx* ctx, Shard& s) {
   CU(cudaSetDevice(s.device));
   CU(cudaStreamCreate(&s.s_main));
-  CU(cudaStreamCreate(&s.s_sort));
+  {  // the side stream carries short kernels that must not queue behind the big grids of the main stream
+    int prio_lo = 0, prio_hi = 0;
+    CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    CU(cudaStreamCreateWithPriority(&s.s_sort, cudaStreamDefault, prio_hi));
+  }
   for (int i = 0; i < EV_COUNT; ++i) CU(cudaEventCreate(&s.ev[i]));
   CU(cudaEventCreateWithFlags(&s.ev_fork, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&s.ev_join, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&s.ev_sample, cudaEventDisableTiming));
   CU(s.scal.ensure(SC_COUNT * 8));
   return MDEGGS_OK;
 }
@@ -247,6 +252,14 @@ int build_layout(mdeggs_ctx* ctx, const mdeggs_problem* in, HostLayout& H) {
   return MDEGGS_OK;
 }
 
+unsigned int qs_cand_capacity(const mdeggs_ctx* ctx, const mdeggs_problem* in) {
+  // candidates of all slots together: a few thousand per slot for continuous data; bounded by the matrix itself
+  const long long n_upper = (long long)(2 * in->E < (int64_t)in->G ? 2 * in->E : (int64_t)in->G) * in->n;
+  unsigned int cap = (unsigned int)(n_upper < (long long)QS_CAND_MAX ? n_upper : (long long)QS_CAND_MAX);
+  if (cap < 1024) cap = 1024;
+  if (ctx->rsel_cap_override > 0 && (unsigned int)ctx->rsel_cap_override < cap) cap = (unsigned int)ctx->rsel_cap_override;
+  return cap;
+}
 bool device_adjust(const mdeggs_problem* in) {
   return in->padj == MDEGGS_PADJ_BONFERRONI || in->padj == MDEGGS_PADJ_BH || in->padj == MDEGGS_PADJ_HOLM ||
          in->padj == MDEGGS_PADJ_HOCHBERG || in->padj == MDEGGS_PADJ_BY;
@@ -258,6 +271,7 @@ bool use_bucket_order(const mdeggs_ctx* ctx, const mdeggs_problem* in, int32_t n
   return in->E <= BS_MAX_E;
 }
 BsArgs make_bs_args(Shard& s, int64_t E);
+inline int bs_padded(int NB) { return ((NB + 1 + 3) & ~3) + 4; }  // entries per array: 16-byte vector access past NB
 
 template <int K>
 void launch_fit_stream(mdeggs_ctx* ctx, Shard& s, const SegLayout& L, int64_t e_lo, int64_t e_hi) {
@@ -285,7 +299,7 @@ BsArgs make_bs_args(Shard& s, int64_t E) {
   BsArgs B;
   const int NB = bs_nbuckets(E);
   B.count = s.bs_count.as<int>();
-  B.base = B.count + (NB + 1);
+  B.base = B.count + bs_padded(NB);
   B.slot = s.bs_slot.as<int32_t>();
   B.n_valid = s.scal.as<unsigned long long>() + SC_NVALID;
   B.nlin = bs_nlin(E);
@@ -463,6 +477,26 @@ int run_shard_front(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, int32_t
   CU(cudaSetDevice(s.device));
   const int32_t* d_from = s.from.as<int32_t>();
   const int32_t* d_to = s.to.as<int32_t>();
+  // K3 S0 on the side stream, beside K0: sample -> knots of the quantile bins (needs only the inputs)
+  if (E > 0 && in->P > 0) {
+    const int P = in->P, n = in->n;
+    if ((size_t)QS_BINS * 4 > s.rsel_hist.cap) {  // the scan kernel leaves the histogram zeroed for the next call
+      CU(s.rsel_hist.ensure((size_t)QS_BINS * 4));
+      CU(cudaMemsetAsync(s.rsel_hist.p, 0, (size_t)QS_BINS * 4, s.s_main));
+    }
+    CU(s.rsel_state.ensure(sizeof(QsState)));
+    CU(s.rsel_cand.ensure((size_t)qs_cand_capacity(ctx, in) * 8));
+    if (!s.rsel_attr_set) {
+      CU(cudaFuncSetAttribute(k_qs_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, QS_FIN_CAP * 8));
+      s.rsel_attr_set = true;
+    }
+    CU(cudaEventRecord(s.ev_fork, s.s_main));
+    CU(cudaStreamWaitEvent(s.s_sort, s.ev_fork, 0));
+    const int S = QS_SAMPLE;
+    LAUNCH(k_qs_sample, 1, QS_SAMPLE_THREADS, 0, s.s_sort, s.assay.as<double>(), s.ld_eff, s.row_off,
+           in->layout == MDEGGS_LAYOUT_COLMAJOR ? 1 : 0, d_from, d_to, E, G, n, S, s.rsel_state.as<QsState>());
+    CU(cudaEventRecord(s.ev_sample, s.s_sort));
+  }
   // ---- K0 node filter ----
   // one memset clears the scalars (node count, error flag, "done" counter) and the row bitmap behind them
   const int W = (G + 31) >> 5;
@@ -510,57 +544,40 @@ int run_shard_main(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
   CU(s.med.ensure(nn * K * 8));
   CU(s.bad.ensure(nn));
   CU(s.cutoff.ensure((size_t)(P > 0 ? P : 1) * 8));
+  // K3 (exact quantiles of the whole node-filtered matrix, mdeggs_qsel.cuh) is threaded through the pipeline:
+  //   S0 sample -> knots (one CTA) ; S1 histogram fused into the gather ; S2 scan (one CTA) ; S3 compaction (the
+  //   only extra read of D) ; S4 finish on the side stream.  Full-grid kernels are NOT overlapped with each other:
+  //   measured, two of them side by side only slow each other down (resident CTAs = loads in flight).
+  const bool do_q = n_nodes > 0 && P > 0;  // == the condition under which run_shard_front launched S0
+  QsState* d_st = do_q ? s.rsel_state.as<QsState>() : nullptr;
+  const unsigned int cand_cap = do_q ? qs_cand_capacity(ctx, in) : 0;
+  if (do_q) CU(cudaStreamWaitEvent(s.s_main, s.ev_sample, 0));  // knots ready
   if (n_nodes > 0) {
+    unsigned int* d_hist = do_q ? s.rsel_hist.as<unsigned int>() : nullptr;
+    const unsigned grid = 148 * 4;  // persistent CTAs: one histogram flush each
     if (in->layout == MDEGGS_LAYOUT_COLMAJOR) {
-      dim3 grid((unsigned)((L.npad + 31) / 32), (unsigned)((n_nodes + 31) / 32));
       LAUNCH(k_gather_colmajor, grid, 256, 0, s.s_main, s.assay.as<double>(), s.ld_eff, s.row_off, s.rowlist.as<int32_t>(), d_nn,
-             s.src_of_pos.as<int32_t>(), L.npad, n, s.D.as<double>());
+             s.src_of_pos.as<int32_t>(), L.npad, n, s.D.as<double>(), d_st, d_hist);
     } else {
-      dim3 grid((unsigned)((L.npad + 255) / 256), (unsigned)n_nodes);
       LAUNCH(k_gather_rowmajor, grid, 256, 0, s.s_main, s.assay.as<double>(), s.ld_eff, s.row_off, s.rowlist.as<int32_t>(), d_nn,
-             s.src_of_pos.as<int32_t>(), L.npad, n, s.D.as<double>());
+             s.src_of_pos.as<int32_t>(), L.npad, n, s.D.as<double>(), d_st, d_hist);
     }
   }
   EVREC(s.ev[EV_GATHER], s.s_main);
-  // ---- K3 on the side stream: radix-select every percentile's two order statistics (no sort) ----
+  EVREC(s.ev[EV_Q0], s.s_main);
+  if (do_q) {
+    LAUNCH(k_qs_scan, 1, 1024, 0, s.s_main, d_st, s.rsel_hist.as<unsigned int>(), d_nn, n, s.pct.as<double>(), P,
+           cand_cap);
+    LAUNCH(k_qs_compact, 148 * 4, 256, (size_t)QS_FILTER_CELLS / 8, s.s_main, s.D.as<double>(), s.src_of_pos.as<int32_t>(), L.npad, d_nn, d_st,
+           s.rsel_cand.as<unsigned long long>());
+  }
+  // S4 (one small CTA per slot) runs on the side stream next to K2; K7 joins it
   CU(cudaEventRecord(s.ev_fork, s.s_main));
   CU(cudaStreamWaitEvent(s.s_sort, s.ev_fork, 0));
-  EVREC(s.ev[EV_Q0], s.s_sort);
-  if (n_nodes > 0 && P > 0) {
-    const size_t hist_bytes = (size_t)2 * P * RSEL_BINS * sizeof(unsigned int);
-    CU(s.rsel_hist.ensure(hist_bytes));
-    CU(s.rsel_state.ensure(sizeof(RselState) + 16));
-    CU(cudaMemsetAsync(s.rsel_hist.p, 0, hist_bytes, s.s_sort));
-    CU(cudaMemsetAsync(s.rsel_state.p, 0, sizeof(RselState) + 16, s.s_sort));
-    RselState* d_st = s.rsel_state.as<RselState>();
-    unsigned long long* d_nan = reinterpret_cast<unsigned long long*>(s.rsel_state.as<char>() + sizeof(RselState));
-    const size_t hsmem = (size_t)RSEL_SMEM_SLOTS * RSEL_BINS * sizeof(unsigned int);
-    RselCand cand;
-    {
-      size_t total = (size_t)n_nodes * (size_t)n;
-      cand.capacity = (unsigned int)(total < (size_t)(4u << 20) ? total : (size_t)(4u << 20));
-      if (ctx->rsel_cap_override > 0 && (size_t)ctx->rsel_cap_override < cand.capacity) cand.capacity = (unsigned int)ctx->rsel_cap_override;
-      CU(s.rsel_cand.ensure((size_t)cand.capacity * 8));
-      cand.keys = s.rsel_cand.as<unsigned long long>();
-      cand.count = reinterpret_cast<unsigned int*>(s.rsel_state.as<char>() + sizeof(RselState) + 8);
-    }
-    const unsigned big_grid = 148 * 6, small_grid = 148;
-    // two digit passes over D (24 key bits), one compaction pass, one finishing kernel
-    for (int pass = 0; pass < 2; ++pass) {
-      LAUNCH(k_rsel_pass<0>, big_grid, 256, hsmem, s.s_sort, s.D.as<double>(), s.src_of_pos.as<int32_t>(), L.npad,
-             d_nn, pass, d_st, s.rsel_hist.as<unsigned int>(), d_nan, cand);
-      LAUNCH(k_rsel_scan, (unsigned)(pass == 0 ? 1 : 2 * P), 256, 0, s.s_sort, pass, d_st,
-             s.rsel_hist.as<unsigned int>(), d_nan, d_nn, n, s.pct.as<double>(), P, s.cutoff.as<double>());
-    }
-    LAUNCH(k_rsel_pass<1>, big_grid, 256, 0, s.s_sort, s.D.as<double>(), s.src_of_pos.as<int32_t>(), L.npad, d_nn, 2,
-           d_st, s.rsel_hist.as<unsigned int>(), d_nan, cand);
-    if (!s.rsel_attr_set) {
-      CU(cudaFuncSetAttribute(k_rsel_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, RSEL_FIN_CAP * 8));
-      s.rsel_attr_set = true;
-    }
-    LAUNCH(k_rsel_finish, (unsigned)(2 * P), RSEL_FIN_THREADS, (size_t)RSEL_FIN_CAP * 8, s.s_sort, s.D.as<double>(),
-           s.src_of_pos.as<int32_t>(), L.npad, d_nn, d_st, cand, s.pct.as<double>(), P, s.cutoff.as<double>());
-    (void)small_grid;
+  if (do_q) {
+    LAUNCH(k_qs_finish, (unsigned)(2 * P), QS_FIN_THREADS, (size_t)QS_FIN_CAP * 8, s.s_sort, s.D.as<double>(),
+           s.src_of_pos.as<int32_t>(), L.npad, d_nn, d_st, s.rsel_cand.as<unsigned long long>(), s.pct.as<double>(), P,
+           s.cutoff.as<double>());
   } else if (P > 0) {
     LAUNCH(k_fill_f64, 1, 64, 0, s.s_sort, s.cutoff.as<double>(), (int64_t)P, nan(""));
   }
@@ -707,7 +724,7 @@ int run_shard_main(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
     memset(&B, 0, sizeof B);
     if (bs) {
       const int NB = bs_nbuckets(E);
-      CU(s.bs_count.ensure((size_t)2 * (NB + 1) * 4));
+      CU(s.bs_count.ensure((size_t)2 * bs_padded(NB) * 4));
       CU(s.bs_slot.ensure((size_t)E * 4));
       CU(cudaMemsetAsync(s.bs_count.p, 0, (size_t)(NB + 1) * 4, s.s_main));
       B = make_bs_args(s, E);
@@ -792,18 +809,21 @@ int run_shard_back(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
       // over the all-gathered p-values; scatter into buckets, then one CTA per run of buckets sorts in shared memory
       BsArgs B;
       if (s.world > 1) {
-        const int NB = bs_nbuckets(E);
-        CU(s.bs_count.ensure((size_t)2 * (NB + 1) * 4));
+        CU(s.bs_count.ensure((size_t)2 * bs_padded(bs_nbuckets(E)) * 4));
         CU(s.bs_slot.ensure((size_t)E * 4));
-        CU(cudaMemsetAsync(s.bs_count.p, 0, (size_t)(NB + 1) * 4, s.s_main));
+        CU(cudaMemsetAsync(s.bs_count.p, 0, (size_t)(bs_nbuckets(E) + 1) * 4, s.s_main));
         B = make_bs_args(s, E);
         LAUNCH(k_bsort_count, blocks_for(E, 256), 256, 0, s.s_main, B, s.p_edge.as<double>(),
                s.scal.as<int32_t>() + 2 * SC_ERR);
       } else {
         B = make_bs_args(s, E);
       }
-      LAUNCH(k_bsort_scatter, blocks_for(E, 256), 256, 0, s.s_main, B, s.p_edge.as<double>(),
-             s.sortk.as<unsigned long long>(), s.idx.as<int32_t>(), s.scal.as<int32_t>() + 2 * SC_ERR);
+      const int NB = bs_nbuckets(E);
+      const int scan_in_cta = NB <= BS_SCAN_SMEM;
+      if (!scan_in_cta) LAUNCH(k_bsort_scan, 1, 1024, 0, s.s_main, B);
+      LAUNCH(k_bsort_scatter, blocks_for(E, 256), 256, scan_in_cta ? (size_t)bs_padded(NB) * 4 : 0, s.s_main, B, scan_in_cta,
+             s.p_edge.as<double>(), s.sortk.as<unsigned long long>(), s.idx.as<int32_t>(),
+             s.scal.as<int32_t>() + 2 * SC_ERR);
       LAUNCH(k_bsort_sort, blocks_for(E, BS_CAP), BS_SORT_THREADS, 0, s.s_main, B, s.sortk.as<unsigned long long>(),
              s.idx.as<int32_t>(), s.ea.as<int32_t>(), s.eb.as<int32_t>(), s.ps.as<double>(), s.sa.as<int32_t>(),
              s.sb.as<int32_t>(), s.idx2.as<int32_t>(), s.scal.as<int32_t>() + 2 * SC_ERR);
@@ -1175,6 +1195,7 @@ int mdeggs_destroy(mdeggs_ctx* ctx) {
       if (s.ev[i]) cudaEventDestroy(s.ev[i]);
     if (s.ev_fork) cudaEventDestroy(s.ev_fork);
     if (s.ev_join) cudaEventDestroy(s.ev_join);
+    if (s.ev_sample) cudaEventDestroy(s.ev_sample);
     if (s.s_main) cudaStreamDestroy(s.s_main);
     if (s.s_sort) cudaStreamDestroy(s.s_sort);
   }
@@ -1203,8 +1224,8 @@ int mdeggs_run_omic(mdeggs_ctx* ctx, const mdeggs_problem* in, mdeggs_result* ou
     set_err(ctx, "tested_coef must be 1..4");
     return MDEGGS_EINVAL;
   }
-  if (2 * in->P > RSEL_MAX_T) {
-    set_err(ctx, "more than %d percentiles are not supported", RSEL_MAX_T / 2);
+  if (2 * in->P >= QS_MAX_T) {  // slot ids travel as bytes, 0xff = none
+    set_err(ctx, "more than %d percentiles are not supported", QS_MAX_T / 2 - 1);
     return MDEGGS_EUNSUPPORTED;
   }
   if (in->n <= 2 * in->K) {

@@ -135,60 +135,7 @@ __global__ void __launch_bounds__(256) k_build_nodes(const unsigned int* __restr
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// K1: gather + transposition  (replaces the per-pair `assayData[gene, ]` row look-ups, core_functions.R:880-881)
-//   in : R column-major G x n (gene fastest)  or row-major (sample fastest)
-//   out: D[node][pos] with category-contiguous samples
-// 32x32 smem tile, coalesced on both sides. Padding positions (src < 0) are written by k_gene_stats.
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_gather_colmajor(const double* __restrict__ assay, int64_t ld,
-                                                         int64_t row_off, const int32_t* __restrict__ rowlist,
-                                                         const int32_t* __restrict__ n_nodes_p,
-                                                         const int32_t* __restrict__ src_of_pos, int npad, int n,
-                                                         double* __restrict__ D) {
-  __shared__ double tile[32][33];
-  const int n_nodes = *n_nodes_p;
-  const int node0 = blockIdx.y * 32, pos0 = blockIdx.x * 32;
-  if (node0 >= n_nodes) return;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
-  const int node_r = node0 + tx;
-  const int64_t row = node_r < n_nodes ? rowlist[node_r] - row_off : -1;  // device copy starts at host row row_off
-#pragma unroll
-  for (int j = ty; j < 32; j += 8) {
-    int pos = pos0 + j;
-    int s = pos < npad ? src_of_pos[pos] : -1;
-    double v = 0.0;
-    if (s >= 0 && row >= 0) v = __ldg(assay + row + (int64_t)s * ld);
-    tile[j][tx] = v;
-  }
-  __syncthreads();
-  const int pos_w = pos0 + tx;
-  const int s_w = pos_w < npad ? src_of_pos[pos_w] : -1;
-#pragma unroll
-  for (int i = ty; i < 32; i += 8) {
-    int node = node0 + i;
-    if (node < n_nodes && s_w >= 0) {
-      D[(size_t)node * npad + pos_w] = tile[tx][i];
-    }
-  }
-}
-
-__global__ void __launch_bounds__(256) k_gather_rowmajor(const double* __restrict__ assay, int64_t ld,
-                                                         int64_t row_off, const int32_t* __restrict__ rowlist,
-                                                         const int32_t* __restrict__ n_nodes_p,
-                                                         const int32_t* __restrict__ src_of_pos, int npad, int n,
-                                                         double* __restrict__ D) {
-  const int n_nodes = *n_nodes_p;
-  const int node = blockIdx.y;
-  if (node >= n_nodes) return;
-  const int64_t row = rowlist[node] - row_off;
-  for (int pos = blockIdx.x * blockDim.x + threadIdx.x; pos < npad; pos += gridDim.x * blockDim.x) {
-    int s = src_of_pos[pos];
-    if (s >= 0) {
-      D[(size_t)node * npad + pos] = __ldg(assay + row * ld + s);
-    }
-  }
-}
+// (K1 gather kernels live in mdeggs_qsel.cuh: they also build the value histogram of the quantile selection)
 
 // ------------------------------------------------------------------------------------------------
 // K2: per-gene, per-category statistics

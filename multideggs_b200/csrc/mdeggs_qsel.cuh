@@ -1,0 +1,750 @@
+// mdeggs_qsel.cuh — K3: exact multi-quantile selection over the whole node-filtered matrix without a sort, and the
+// K1 gather kernels that carry its first pass.
+//
+// Replaces  cut_off <- stats::quantile(as.matrix(assayData), prob = percentile, na.rm = TRUE)
+// (R/core_functions.R:718), which the reference recomputes for each of the 13-15 percentiles.  Type 7 needs two
+// order statistics per percentile (floor/ceil of 1 + (N-1) p): T = 2P target ranks out of N ~ 8.4e6 values.
+//
+//   S0 k_qs_sample  one CTA: a stratified sample of the node rows of the input matrix, sorted in shared memory ->
+//                   65 knots at sample quantiles (uniform in the middle, halving towards both tails).  Knot cell c,
+//                   split into 64 equal-width sub-bins, defines a MONOTONE map value -> bin in [0, 4096) evaluated
+//                   in FP32 on (x - sample minimum); bins hold roughly N/4096 values whatever the distribution, and
+//                   a value that fills a whole cell of the sample gets a bin of its own.
+//   S1 (fused into the K1 gather kernels) exact 4,096-bin histogram of everything that is written to D,
+//                   shared-memory privatised per persistent CTA; NaN skipped (na.rm = TRUE).
+//   S2 k_qs_scan    one CTA: prefix sums; each target rank -> (bin, rank inside the bin); the <= 2P distinct bins
+//                   become "slots" with exact candidate counts and offsets in the candidate buffer.
+//   S3 k_qs_compact the only extra read of D: values of slot bins are appended to their slot's list (staged per CTA in
+//                   shared memory: one global atomic per CTA and slot).  Slots too fat for the shared-memory finish
+//                   (tie groups) are not copied; their min/max key is tracked instead.
+//   S4 k_qs_finish  one CTA per slot: radix select (12-bit digits below the common key prefix) of every target rank
+//                   over the slot's candidates in shared memory; a fat slot whose min == max (a pure tie group)
+//                   answers immediately, any other fat slot runs the same select straight over D (slow, correct).
+//                   The last CTA evaluates the type-7 interpolation  q = (1-h) x[lo] + h x[hi]  in R's order.
+// Versus a full 64-bit radix sort of the matrix: one extra read of D instead of ~16 read+write sweeps.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "mdeggs_kernels.cuh"
+
+namespace mdeggs {
+
+constexpr int QS_MAX_T = 256;        // 2 * P
+constexpr int QS_CELLS = 64;         // knot cells
+constexpr int QS_SUB = 64;           // equal-width sub-bins per cell
+constexpr int QS_BINS = QS_CELLS * QS_SUB;
+constexpr int QS_SAMPLE = 1024;      // sample size (a single-CTA sort: kept small; it only shapes the bins)
+constexpr int QS_SAMPLE_MAX = QS_SAMPLE;
+constexpr int QS_SAMPLE_THREADS = 256;
+constexpr int QS_FIN_CAP = 16384;    // keys a finish CTA keeps in shared memory (128 KB); longer lists stay in L2
+constexpr unsigned int QS_SLOT_MAX = 1u << 20;  // slots with more values are not compacted ("fat": tie groups)
+constexpr unsigned int QS_CAND_MAX = 8u << 20;  // candidate buffer, keys
+constexpr int QS_FIN_THREADS = 512;
+constexpr int QS_STAGE = 2048;       // per-CTA staging entries of the compaction pass
+
+constexpr int QS_TAB = 4096;         // uniform value cells of the knot look-up table
+struct QsKnots {
+  double base;                 // sample minimum; bins are evaluated on xf = (float)(x - base)
+  float knot[QS_CELLS + 1];
+  float scale[QS_CELLS];
+  float inv_w;                 // QS_TAB / (sample range): uniform cell index = (int)(xf * inv_w)
+  // per uniform cell: low 6 bits = first knot cell that can hold its values, top 2 bits = 0: exactly that cell,
+  // 1: that cell or the next, 2: anything (binary search)
+  unsigned char tab[QS_TAB];
+};
+static_assert(sizeof(QsKnots) % 8 == 0, "QsKnots is copied as 8-byte words");
+
+struct QsState {
+  long long N;                         // non-NaN values
+  int U;                               // slots (distinct target bins)
+  unsigned int done;                   // finish CTAs completed
+  int t_slot[QS_MAX_T];                // per target
+  long long t_rank[QS_MAX_T];          // per target: 0-based rank inside its bin
+  unsigned long long t_key[QS_MAX_T];  // per target: selected key
+  int slot_bin[QS_MAX_T];
+  unsigned int slot_count[QS_MAX_T];   // values in the slot's bin
+  unsigned int slot_off[QS_MAX_T];     // offset of the slot's list in the candidate buffer
+  unsigned int slot_cursor[QS_MAX_T];  // append cursor
+  int slot_fat[QS_MAX_T];              // 1: not compacted (too many values, or the buffer would overflow)
+  unsigned long long slot_min[QS_MAX_T], slot_max[QS_MAX_T];  // fat slots: key range
+  // compaction pre-filter: bit i set <=> uniform value cell i (QS_FILTER_CELLS over the sample range) may hold a value
+  // of a slot bin; everything else is skipped without evaluating the bin map
+  unsigned int cand_bits[65536 / 32];
+  QsKnots knots;
+};
+constexpr int QS_FILTER_CELLS = 65536;
+
+// monotone map value -> bin.  `kn` points at a shared-memory copy of the knots.  NaN never reaches here.
+__device__ __forceinline__ int qs_cell_search(const QsKnots* __restrict__ kn, float xf) {
+  int c = 0;
+#pragma unroll
+  for (int step = QS_CELLS / 2; step > 0; step >>= 1)
+    if (xf >= kn->knot[c + step]) c += step;  // last c in [0, 63] with knot[c] <= xf (c = 0 below knot[0])
+  return c;
+}
+__device__ __forceinline__ int qs_tab_index(float xf, float inv_w, int cells) {
+  int idx = (int)(xf * inv_w);  // saturating conversion; NaN (inf * 0) -> 0
+  return idx < 0 ? 0 : (idx > cells - 1 ? cells - 1 : idx);
+}
+__device__ __forceinline__ int qs_bin(const QsKnots* __restrict__ kn, double x) {
+  const float xf = (float)(x - kn->base);  // monotone; +-inf and overflow stay ordered
+  const unsigned e = kn->tab[qs_tab_index(xf, kn->inv_w, QS_TAB)];
+  int c = (int)(e & 63u);
+  if (e & 0x80u) c = qs_cell_search(kn, xf);
+  else if (e & 0x40u) c += (xf >= kn->knot[c + 1]);
+  int sub = (int)((xf - kn->knot[c]) * kn->scale[c]);  // NaN products (inf * 0) convert to 0
+  sub = sub < 0 ? 0 : (sub > QS_SUB - 1 ? QS_SUB - 1 : sub);
+  return c * QS_SUB + sub;
+}
+
+__device__ __forceinline__ void qs_hist_add(const QsKnots* __restrict__ kn, unsigned int* __restrict__ s_hist, double v) {
+  if (!isnan(v)) atomicAdd(&s_hist[qs_bin(kn, v)], 1u);
+}
+__device__ __forceinline__ void qs_load_knots(QsKnots* __restrict__ dst, const QsState* __restrict__ st) {
+  for (int i = threadIdx.x; i < (int)(sizeof(QsKnots) / 8); i += blockDim.x)
+    reinterpret_cast<double*>(dst)[i] = reinterpret_cast<const double*>(&st->knots)[i];
+}
+__device__ __forceinline__ void qs_flush_hist(const unsigned int* __restrict__ s_hist, unsigned int* __restrict__ hist) {
+  for (int i = threadIdx.x; i < QS_BINS; i += blockDim.x) {
+    const unsigned int c = s_hist[i];
+    if (c) atomicAdd(&hist[i], c);
+  }
+}
+
+// position of knot c on the sample-rank axis, in 1/1024 of (m - 1): 0 1 2 4 8 | 26 44 ... 998 | 1016 1020 1022 1023 1024
+__device__ __forceinline__ int qs_knot_pos(int c) {
+  if (c < 5) return c == 0 ? 0 : 1 << (c - 1);
+  if (c > 59) return c == 64 ? 1024 : 1024 - (1 << (63 - c));
+  return 8 + (c - 4) * 18;
+}
+
+// ---- S0 ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(QS_SAMPLE_THREADS) k_qs_sample(const double* __restrict__ assay, int64_t ld,
+                                                                 int64_t row_off, int colmajor,
+                                                                 const int32_t* __restrict__ from,
+                                                                 const int32_t* __restrict__ to, int64_t E, int G,
+                                                                 int n, int S, QsState* __restrict__ st) {
+  // Rows are drawn through the edge list (end points of edges ARE the node rows), so the kernel needs nothing from
+  // K0 and runs beside it.  Hub genes are drawn more often: harmless, the sample only shapes the bins.
+  __shared__ unsigned long long sk[QS_SAMPLE_MAX];
+  __shared__ int s_m;
+  const long long ends = 2 * E;
+  const long long total = ends * n;
+  if (threadIdx.x == 0) s_m = 0;
+  for (int i = threadIdx.x; i < S; i += blockDim.x) sk[i] = ~0ull;
+  __syncthreads();
+  auto row_of_end = [&](long long j) -> int64_t {  // j in [0, 2E): from[0..E) then to[0..E); -1 when out of range
+    const int r = (j < E ? from[j] : to[j - E]) - 1;
+    return (r >= 0 && r < G) ? (int64_t)r - row_off : -1;
+  };
+  if (total > S) {
+    const unsigned jit = (unsigned)(ends / S + 1);
+    for (int i0 = 0; i0 < S; i0 += 4 * QS_SAMPLE_THREADS) {  // 4 independent draws per thread in flight
+      int64_t off[4];
+      double v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * QS_SAMPLE_THREADS + threadIdx.x;
+        const unsigned h = (unsigned)i * 2654435761u;
+        long long j = ((long long)i * ends) / S + (long long)((h >> 20) % jit);
+        j = j < ends ? j : ends - 1;
+        const int smp = (int)((h >> 4) % (unsigned)n);
+        const int64_t row = row_of_end(j);
+        off[u] = row < 0 ? -1 : (colmajor ? row + (int64_t)smp * ld : row * ld + smp);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = off[u] >= 0 ? __ldg(assay + off[u]) : nan("");
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const unsigned long long k = dkey(v[u]);
+        if (k != ~0ull) sk[atomicAdd(&s_m, 1)] = k;
+      }
+    }
+  } else {
+    for (int li = threadIdx.x; li < (int)total; li += blockDim.x) {
+      const int64_t row = row_of_end(li / n);
+      const int smp = li % n;
+      const unsigned long long k =
+          row < 0 ? ~0ull : dkey(colmajor ? assay[row + (int64_t)smp * ld] : assay[row * ld + smp]);
+      if (k != ~0ull) sk[atomicAdd(&s_m, 1)] = k;
+    }
+  }
+  __syncthreads();
+  const int m = s_m;
+  // bitonic sort of the S slots (unused slots hold the maximum key and stay at the end); the pairs of a thread are
+  // loaded together so that their shared-memory latencies overlap
+  for (int k = 2; k <= S; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t0 = 0; t0 < S / 2; t0 += QS_SAMPLE_THREADS * 4) {
+        unsigned long long a[4], b[4];
+        int ii[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int t = t0 + u * QS_SAMPLE_THREADS + threadIdx.x;
+          ii[u] = t < S / 2 ? (((t & ~(j - 1)) << 1) | (t & (j - 1))) : -1;
+          if (ii[u] >= 0) {
+            a[u] = sk[ii[u]];
+            b[u] = sk[ii[u] | j];
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (ii[u] >= 0 && ((a[u] > b[u]) == ((ii[u] & k) == 0))) {
+            sk[ii[u]] = b[u];
+            sk[ii[u] | j] = a[u];
+          }
+      }
+      __syncthreads();
+    }
+  }
+  const double base = m > 0 ? dkey_inv(sk[0]) : 0.0;
+  auto knot_at = [&](int c) -> float {
+    if (m <= 0) return 0.f;
+    const int r = (int)(((long long)qs_knot_pos(c) * (m - 1) + 512) >> 10);
+    return (float)(dkey_inv(sk[r]) - base);
+  };
+  __shared__ float s_knot[QS_CELLS + 1];
+  if (threadIdx.x <= QS_CELLS) {
+    const float v = knot_at(threadIdx.x);
+    s_knot[threadIdx.x] = v;
+    st->knots.knot[threadIdx.x] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < QS_CELLS) {
+    const float lo = s_knot[threadIdx.x], hi = s_knot[threadIdx.x + 1];
+    float sc = (float)QS_SUB / (hi - lo);
+    if (!(hi > lo) || !isfinite(sc)) sc = 0.f;
+    st->knots.scale[threadIdx.x] = sc;
+  }
+  // look-up table over QS_TAB uniform cells of [0, sample range]: knot cells that the values of uniform cell i can
+  // fall into, padded by one uniform cell on both sides against rounding of the index computation
+  const float range = s_knot[QS_CELLS];
+  float inv_w = range > 0.f ? (float)QS_TAB / range : 0.f;
+  if (!isfinite(inv_w)) inv_w = 0.f;
+  const float w = inv_w > 0.f ? 1.f / inv_w : 0.f;
+  if (threadIdx.x == 0) {
+    st->knots.base = base;
+    st->knots.inv_w = inv_w;
+  }
+  auto cell_of = [&](float xf) {
+    int c = 0;
+#pragma unroll
+    for (int step = QS_CELLS / 2; step > 0; step >>= 1)
+      if (xf >= s_knot[c + step]) c += step;
+    return c;
+  };
+  for (int i = threadIdx.x; i < QS_TAB; i += blockDim.x) {
+    const int c_lo = inv_w > 0.f ? cell_of(((float)i - 1.f) * w) : 0;
+    const int c_hi = inv_w > 0.f && i < QS_TAB - 1 ? cell_of(((float)i + 2.f) * w) : QS_CELLS - 1;
+    const int d = c_hi - c_lo;
+    st->knots.tab[i] = (unsigned char)(c_lo | (d == 0 ? 0 : (d == 1 ? 0x40 : 0x80)));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1: gather + transposition  (replaces the per-pair `assayData[gene, ]` row look-ups, core_functions.R:880-881)
+//   in : R column-major G x n (gene fastest)  or row-major (sample fastest)
+//   out: D[node][pos] with category-contiguous samples
+// Persistent CTAs (a multiple of the SM count) walk the tiles; every value written to D is also counted in the
+// CTA's shared-memory copy of the quantile histogram (S1), flushed once per CTA.  Column-major input goes through a
+// 32x32 shared-memory transposition tile, coalesced on both sides.  Padding positions (src < 0) are written by K2.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_gather_colmajor(const double* __restrict__ assay, int64_t ld,
+                                                         int64_t row_off, const int32_t* __restrict__ rowlist,
+                                                         const int32_t* __restrict__ n_nodes_p,
+                                                         const int32_t* __restrict__ src_of_pos, int npad, int n,
+                                                         double* __restrict__ D, const QsState* __restrict__ st,
+                                                         unsigned int* __restrict__ hist) {
+  __shared__ double tile[32][33];
+  __shared__ QsKnots kn;
+  __shared__ unsigned int s_hist[QS_BINS];
+  const bool do_hist = hist != nullptr;
+  if (do_hist) {
+    qs_load_knots(&kn, st);
+    for (int i = threadIdx.x; i < QS_BINS; i += blockDim.x) s_hist[i] = 0u;
+  }
+  __syncthreads();
+  const int n_nodes = *n_nodes_p;
+  const int n_tx = (npad + 31) / 32, n_ty = (n_nodes + 31) / 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (long long tile_id = blockIdx.x; tile_id < (long long)n_tx * n_ty; tile_id += gridDim.x) {
+    const int node0 = (int)(tile_id / n_tx) * 32, pos0 = (int)(tile_id % n_tx) * 32;
+    const int node_r = node0 + tx;
+    const int64_t row = node_r < n_nodes ? rowlist[node_r] - row_off : -1;  // device copy starts at host row row_off
+    double v[4];
+    bool ok[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {  // the 4 loads of this thread are issued before any of them is binned
+      const int pos = pos0 + ty + 8 * q;
+      const int s = pos < npad ? src_of_pos[pos] : -1;
+      ok[q] = s >= 0 && row >= 0;
+      v[q] = ok[q] ? __ldg(assay + row + (int64_t)s * ld) : 0.0;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) tile[ty + 8 * q][tx] = v[q];
+    __syncthreads();
+    if (do_hist) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (ok[q]) qs_hist_add(&kn, s_hist, v[q]);
+    }
+    const int pos_w = pos0 + tx;
+    const int s_w = pos_w < npad ? src_of_pos[pos_w] : -1;
+#pragma unroll
+    for (int i = ty; i < 32; i += 8) {
+      const int node = node0 + i;
+      if (node < n_nodes && s_w >= 0) D[(size_t)node * npad + pos_w] = tile[tx][i];
+    }
+    __syncthreads();
+  }
+  if (do_hist) qs_flush_hist(s_hist, hist);
+}
+
+__global__ void __launch_bounds__(256) k_gather_rowmajor(const double* __restrict__ assay, int64_t ld,
+                                                         int64_t row_off, const int32_t* __restrict__ rowlist,
+                                                         const int32_t* __restrict__ n_nodes_p,
+                                                         const int32_t* __restrict__ src_of_pos, int npad, int n,
+                                                         double* __restrict__ D, const QsState* __restrict__ st,
+                                                         unsigned int* __restrict__ hist) {
+  __shared__ QsKnots kn;
+  __shared__ unsigned int s_hist[QS_BINS];
+  const bool do_hist = hist != nullptr;
+  if (do_hist) {
+    qs_load_knots(&kn, st);
+    for (int i = threadIdx.x; i < QS_BINS; i += blockDim.x) s_hist[i] = 0u;
+  }
+  __syncthreads();
+  const int n_nodes = *n_nodes_p;
+  for (int node = blockIdx.x; node < n_nodes; node += gridDim.x) {
+    const int64_t row = rowlist[node] - row_off;
+    for (int pos = threadIdx.x; pos < npad; pos += blockDim.x) {
+      const int s = src_of_pos[pos];
+      if (s >= 0) {
+        const double v = __ldg(assay + row * ld + s);
+        if (do_hist) qs_hist_add(&kn, s_hist, v);
+        D[(size_t)node * npad + pos] = v;
+      }
+    }
+  }
+  __syncthreads();
+  if (do_hist) qs_flush_hist(s_hist, hist);
+}
+
+// ---- S2 ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_qs_scan(QsState* __restrict__ st, unsigned int* __restrict__ hist,
+                                                  const int32_t* __restrict__ n_nodes_p, int n,
+                                                  const double* __restrict__ pct, int P, unsigned int cand_capacity) {
+  __shared__ unsigned long long cum[QS_BINS + 1];
+  __shared__ unsigned long long s_warp[32];
+  __shared__ int s_tbin[QS_MAX_T], s_first[QS_MAX_T];
+  __shared__ unsigned int s_slot_cnt[QS_MAX_T];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  constexpr int PER = QS_BINS / 1024;
+  unsigned long long v[PER], mine = 0;
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    v[j] = hist[tid * PER + j];
+    mine += v[j];
+    hist[tid * PER + j] = 0u;  // clean slate for the next call
+  }
+  unsigned long long incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) s_warp[wid] = incl;
+  __syncthreads();
+  unsigned long long woff = 0;
+  for (int w = 0; w < wid; ++w) woff += s_warp[w];
+  unsigned long long run = woff + incl - mine;
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    cum[tid * PER + j] = run;
+    run += v[j];
+  }
+  if (tid == 1023) cum[QS_BINS] = run;
+  __syncthreads();
+  const long long N = (long long)cum[QS_BINS];  // == n_nodes * n - nan_count
+  const int T = 2 * P;
+  if (tid == 0) {
+    st->N = N;
+    st->done = 0u;
+  }
+  (void)n_nodes_p;
+  (void)n;
+  if (tid < T) {
+    const int p = tid >> 1;
+    long long ilo = 1, ihi = 1;
+    if (N > 0) {
+      const double idx = __dadd_rn(1.0, __dmul_rn((double)(N - 1), pct[p]));
+      ilo = (long long)floor(idx);
+      ihi = (long long)ceil(idx);
+      ilo = ilo < 1 ? 1 : (ilo > N ? N : ilo);
+      ihi = ihi < 1 ? 1 : (ihi > N ? N : ihi);
+    }
+    const unsigned long long r = (unsigned long long)(((tid & 1) ? ihi : ilo) - 1);
+    int lo = 0, hi = QS_BINS - 1;  // largest b with cum[b] <= r
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (cum[mid] <= r) lo = mid;
+      else hi = mid - 1;
+    }
+    s_tbin[tid] = lo;
+    st->t_rank[tid] = (long long)(r - cum[lo]);
+    st->t_key[tid] = 0ull;
+  }
+  __syncthreads();
+  // distinct target bins -> slots, in ascending bin order (T <= 256, O(T^2) in parallel)
+  if (tid < T) {
+    int first = 1;
+    for (int u = 0; u < tid; ++u) first &= (s_tbin[u] != s_tbin[tid]);
+    s_first[tid] = first;
+  }
+  __syncthreads();
+  if (tid < T) {
+    int sl = 0;
+    for (int u = 0; u < T; ++u) sl += (s_first[u] && s_tbin[u] < s_tbin[tid]);
+    st->t_slot[tid] = sl;
+    if (s_first[tid]) {
+      const int b = s_tbin[tid];
+      st->slot_bin[sl] = b;
+      s_slot_cnt[sl] = (unsigned int)(cum[b + 1] - cum[b]);
+      st->slot_count[sl] = s_slot_cnt[sl];
+    }
+  }
+  __threadfence_block();
+  __syncthreads();
+  if (tid == 0) {
+    int U = 0;
+    for (int u = 0; u < T; ++u) U += s_first[u];
+    st->U = U;
+    unsigned long long off = 0;
+    for (int s = 0; s < U; ++s) {
+      const unsigned int c = s_slot_cnt[s];
+      const bool fat = c > QS_SLOT_MAX || off + c > (unsigned long long)cand_capacity;
+      st->slot_fat[s] = fat ? 1 : 0;
+      st->slot_off[s] = (unsigned int)off;
+      st->slot_cursor[s] = 0u;
+      st->slot_min[s] = ~0ull;
+      st->slot_max[s] = 0ull;
+      if (!fat) off += c;
+    }
+  }
+  // compaction pre-filter bitmap (cum[] is no longer needed: its storage is reused)
+  unsigned int* bits = reinterpret_cast<unsigned int*>(cum);
+  for (int i = tid; i < QS_FILTER_CELLS / 32; i += 1024) bits[i] = 0u;
+  __syncthreads();
+  if (tid < T && s_first[tid]) {
+    const int b = s_tbin[tid], c = b / QS_SUB, sub = b % QS_SUB;
+    const float k0 = st->knots.knot[c], k1 = st->knots.knot[c + 1], sc = st->knots.scale[c];
+    const float inv16 = st->knots.inv_w * (float)(QS_FILTER_CELLS / QS_TAB);
+    float lo = k0, hi = k1;
+    if (sc > 0.f) {
+      if (sub > 0) lo = k0 + (float)sub / sc;
+      if (sub < QS_SUB - 1) hi = k0 + (float)(sub + 1) / sc;
+    }
+    int i0 = (c == 0 && sub == 0) ? 0 : qs_tab_index(lo, inv16, QS_FILTER_CELLS) - 2;
+    int i1 = (c == QS_CELLS - 1 && (sub == QS_SUB - 1 || !(sc > 0.f))) ? QS_FILTER_CELLS - 1
+                                                                       : qs_tab_index(hi, inv16, QS_FILTER_CELLS) + 2;
+    if (!(inv16 > 0.f)) {
+      i0 = 0;
+      i1 = QS_FILTER_CELLS - 1;
+    }
+    i0 = i0 < 0 ? 0 : i0;
+    i1 = i1 > QS_FILTER_CELLS - 1 ? QS_FILTER_CELLS - 1 : i1;
+    for (int i = i0; i <= i1; ++i) atomicOr(&bits[i >> 5], 1u << (i & 31));
+  }
+  __syncthreads();
+  for (int i = tid; i < QS_FILTER_CELLS / 32; i += 1024) st->cand_bits[i] = bits[i];
+}
+
+// ---- S3 ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_qs_compact(const double* __restrict__ D, const int32_t* __restrict__ src_of_pos,
+                                                    int npad, const int32_t* __restrict__ n_nodes_p,
+                                                    QsState* __restrict__ st, unsigned long long* __restrict__ cand) {
+  __shared__ QsKnots kn;
+  __shared__ unsigned char s_slot_of_bin[QS_BINS];
+  __shared__ unsigned long long s_key[QS_STAGE];
+  __shared__ unsigned char s_stage_slot[QS_STAGE];
+  __shared__ unsigned int s_n;  // staged entries
+  __shared__ unsigned int s_cnt[QS_MAX_T], s_base[QS_MAX_T], s_fill[QS_MAX_T];
+  __shared__ unsigned long long s_min[QS_MAX_T], s_max[QS_MAX_T];
+  __shared__ unsigned char s_fat[QS_MAX_T];
+  extern __shared__ unsigned int s_bits[];  // QS_FILTER_CELLS / 32 words
+  qs_load_knots(&kn, st);
+  for (int i = threadIdx.x; i < QS_FILTER_CELLS / 32; i += blockDim.x) s_bits[i] = st->cand_bits[i];
+  const float inv16 = st->knots.inv_w * (float)(QS_FILTER_CELLS / QS_TAB);
+  const double base = st->knots.base;
+  const int U = st->U;
+  for (int i = threadIdx.x; i < QS_BINS; i += blockDim.x) s_slot_of_bin[i] = 0xff;
+  if (threadIdx.x == 0) s_n = 0u;
+  for (int i = threadIdx.x; i < QS_MAX_T; i += blockDim.x) {
+    s_cnt[i] = s_fill[i] = 0u;
+    s_min[i] = ~0ull;
+    s_max[i] = 0ull;
+    s_fat[i] = i < U ? (unsigned char)st->slot_fat[i] : 0;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < U; i += blockDim.x) s_slot_of_bin[st->slot_bin[i]] = (unsigned char)i;
+  __syncthreads();
+
+  const int n_nodes = *n_nodes_p;
+  const int half = npad >> 1;  // double2 units per row (npad is a multiple of 4)
+
+  auto visit = [&](double v) {
+    if (isnan(v)) return;  // na.rm = TRUE
+    const int fi = qs_tab_index((float)(v - base), inv16, QS_FILTER_CELLS);
+    if (!((s_bits[fi >> 5] >> (fi & 31)) & 1u)) return;  // ~99% of the values leave here
+    const unsigned sl = s_slot_of_bin[qs_bin(&kn, v)];
+    if (sl == 0xff) return;
+    const unsigned long long k = dkey(v);
+    if (s_fat[sl]) {  // not copied: only the key range of the bin is needed
+      if (k < s_min[sl]) atomicMin(&s_min[sl], k);
+      if (k > s_max[sl]) atomicMax(&s_max[sl], k);
+      return;
+    }
+    const unsigned at = atomicAdd(&s_n, 1u);
+    if (at < (unsigned)QS_STAGE) {
+      s_key[at] = k;
+      s_stage_slot[at] = (unsigned char)sl;
+    } else {  // staging full between two flush points: straight to the slot's list
+      const unsigned pos = atomicAdd(&st->slot_cursor[sl], 1u);
+      if (pos < st->slot_count[sl]) cand[st->slot_off[sl] + pos] = k;
+    }
+  };
+  auto flush = [&]() {  // called by the whole CTA
+    const unsigned ns = s_n < (unsigned)QS_STAGE ? s_n : (unsigned)QS_STAGE;
+    for (unsigned i = threadIdx.x; i < ns; i += blockDim.x) atomicAdd(&s_cnt[s_stage_slot[i]], 1u);
+    __syncthreads();
+    for (int i = threadIdx.x; i < U; i += blockDim.x)
+      if (s_cnt[i]) s_base[i] = atomicAdd(&st->slot_cursor[i], s_cnt[i]);
+    __syncthreads();
+    for (unsigned i = threadIdx.x; i < ns; i += blockDim.x) {
+      const unsigned sl = s_stage_slot[i];
+      const unsigned pos = s_base[sl] + atomicAdd(&s_fill[sl], 1u);
+      if (pos < st->slot_count[sl]) cand[st->slot_off[sl] + pos] = s_key[i];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < U; i += blockDim.x) s_cnt[i] = s_fill[i] = 0u;
+    if (threadIdx.x == 0) s_n = 0u;
+    __syncthreads();
+  };
+
+  // each CTA takes 4 rows at a time so that every thread has 4 independent 16-byte loads in flight
+  for (int row0 = blockIdx.x * 4; row0 < n_nodes; row0 += gridDim.x * 4) {
+    for (int c = threadIdx.x; c < half; c += blockDim.x) {
+      double2 v[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+        v[r] = (row0 + r < n_nodes) ? __ldg(reinterpret_cast<const double2*>(D + (size_t)(row0 + r) * npad) + c)
+                                    : make_double2(0.0, 0.0);
+      const bool ok0 = src_of_pos[2 * c] >= 0, ok1 = src_of_pos[2 * c + 1] >= 0;  // padding slots are skipped
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        if (row0 + r >= n_nodes) break;
+        if (ok0) visit(v[r].x);
+        if (ok1) visit(v[r].y);
+      }
+    }
+    __syncthreads();
+    if (s_n >= (unsigned)QS_STAGE / 2) flush();  // uniform: s_n is read after the barrier
+  }
+  __syncthreads();
+  flush();
+  for (int i = threadIdx.x; i < U; i += blockDim.x)
+    if (s_fat[i] && s_min[i] <= s_max[i]) {
+      atomicMin(&st->slot_min[i], s_min[i]);
+      atomicMax(&st->slot_max[i], s_max[i]);
+    }
+}
+
+// ---- S4 ------------------------------------------------------------------------------------------
+// Key of 0-based rank `rank` among the keys visited by for_each(fn), all inside [kmin, kmax]: MSD radix select with
+// 12-bit digits starting below the common prefix of kmin / kmax.  Called by the whole CTA.
+template <class ForEach>
+__device__ __forceinline__ unsigned long long qs_digit_select(ForEach&& for_each, unsigned long long kmin,
+                                                              unsigned long long kmax, long long rank,
+                                                              unsigned int* hist /* [4096] shared */,
+                                                              long long* s_scan /* [blockDim.x] shared */,
+                                                              unsigned long long* s_pfx, long long* s_rank) {
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  if (kmin == kmax) return kmin;
+  const int top = 63 - __clzll((long long)(kmin ^ kmax));  // highest differing bit
+  if (tid == 0) {
+    *s_pfx = top == 63 ? 0ull : (kmin >> (top + 1));  // fixed high bits, right aligned
+    *s_rank = rank;
+  }
+  __syncthreads();
+  int remaining = top + 1;  // undecided low bits
+  while (remaining > 0) {
+    const int width = remaining < 12 ? remaining : 12;
+    const int nbins = 1 << width;
+    const int shift = remaining - width;
+    for (int i = tid; i < 4096; i += nthr) hist[i] = 0;
+    __syncthreads();
+    const unsigned long long pfx = *s_pfx;
+    const bool no_fixed = remaining == 64;
+    for_each([&](unsigned long long k) {
+      if (no_fixed || (k >> remaining) == pfx)
+        atomicAdd(&hist[(unsigned int)((k >> shift) & (unsigned long long)(nbins - 1))], 1u);
+    });
+    __syncthreads();
+    const int per = 4096 / nthr;
+    long long loc = 0;
+    for (int j = 0; j < per; ++j) loc += hist[tid * per + j];
+    s_scan[tid] = loc;
+    __syncthreads();
+    if (tid < 32) {  // exclusive scan of the per-thread totals by one warp
+      long long carry = 0;
+      for (int i0 = 0; i0 < nthr; i0 += 32) {
+        const long long v = s_scan[i0 + tid];
+        long long incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const long long t = __shfl_up_sync(0xffffffffu, incl, o);
+          if (tid >= o) incl += t;
+        }
+        s_scan[i0 + tid] = carry + incl - v;
+        carry += __shfl_sync(0xffffffffu, incl, 31);
+      }
+    }
+    __syncthreads();
+    const long long r = *s_rank;
+    long long run = s_scan[tid];
+    int found = -1;
+    long long found_base = 0;
+    for (int j = 0; j < per; ++j) {
+      const int b = tid * per + j;
+      const long long h = hist[b];
+      if (b < nbins && r >= run && r < run + h) {
+        found = b;
+        found_base = run;
+      }
+      run += h;
+    }
+    __syncthreads();
+    if (found >= 0) {  // exactly one thread
+      *s_pfx = (pfx << width) | (unsigned long long)found;
+      *s_rank = r - found_base;
+    }
+    __syncthreads();
+    remaining -= width;
+  }
+  const unsigned long long res = *s_pfx;
+  __syncthreads();
+  return res;
+}
+
+__global__ void __launch_bounds__(QS_FIN_THREADS) k_qs_finish(const double* __restrict__ D,
+                                                             const int32_t* __restrict__ src_of_pos, int npad,
+                                                             const int32_t* __restrict__ n_nodes_p,
+                                                             QsState* __restrict__ st,
+                                                             const unsigned long long* __restrict__ cand,
+                                                             const double* __restrict__ pct, int P,
+                                                             double* __restrict__ cutoff) {
+  extern __shared__ unsigned long long fk[];  // QS_FIN_CAP keys
+  __shared__ QsKnots kn;
+  __shared__ unsigned int hist[4096];
+  __shared__ long long s_scan[QS_FIN_THREADS];
+  __shared__ unsigned long long s_pfx, s_min, s_max;
+  __shared__ long long s_rank;
+  __shared__ int s_last;
+  const int tid = threadIdx.x, s = blockIdx.x;
+  const int T = 2 * P;
+  const int U = st->U;
+  if (s >= U) return;
+  const unsigned int c = st->slot_count[s];
+  if (!st->slot_fat[s]) {
+    const unsigned long long* list = cand + st->slot_off[s];
+    if (tid == 0) {
+      s_min = ~0ull;
+      s_max = 0ull;
+    }
+    __syncthreads();
+    const bool in_smem = c <= (unsigned)QS_FIN_CAP;
+    unsigned long long mn = ~0ull, mx = 0ull;
+    for (unsigned int i = tid; i < c; i += QS_FIN_THREADS) {
+      const unsigned long long k = list[i];
+      if (in_smem) fk[i] = k;
+      mn = k < mn ? k : mn;
+      mx = k > mx ? k : mx;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long a = __shfl_xor_sync(0xffffffffu, mn, o), b = __shfl_xor_sync(0xffffffffu, mx, o);
+      mn = a < mn ? a : mn;
+      mx = b > mx ? b : mx;
+    }
+    if ((tid & 31) == 0 && mn <= mx) {
+      atomicMin(&s_min, mn);
+      atomicMax(&s_max, mx);
+    }
+    __syncthreads();
+    const unsigned long long kmin = s_min, kmax = s_max;
+    auto for_each_cand = [&](auto&& fn) {
+      if (in_smem) {
+        for (unsigned int i = tid; i < c; i += QS_FIN_THREADS) fn(fk[i]);
+      } else {
+        for (unsigned int i = tid; i < c; i += QS_FIN_THREADS) fn(__ldg(list + i));
+      }
+    };
+    for (int t = 0; t < T; ++t) {
+      if (st->t_slot[t] != s) continue;  // uniform across the CTA
+      const unsigned long long key = c > 0 ? qs_digit_select(for_each_cand, kmin, kmax, st->t_rank[t], hist, s_scan, &s_pfx, &s_rank) : ~0ull;
+      if (tid == 0) st->t_key[t] = key;
+    }
+  } else if (st->slot_min[s] == st->slot_max[s]) {
+    // a pure tie group: every rank inside it is the same key
+    for (int t = tid; t < T; t += QS_FIN_THREADS)
+      if (st->t_slot[t] == s) st->t_key[t] = st->slot_min[s];
+  } else {
+    // slow path: the same select straight over D, filtered by the bin map
+    qs_load_knots(&kn, st);
+    __syncthreads();
+    const int my_bin = st->slot_bin[s];
+    const int n_nodes = *n_nodes_p;
+    const int half = npad >> 1;
+    auto for_each_in_bin = [&](auto&& fn) {
+      for (int row = 0; row < n_nodes; ++row) {
+        const double2* R2 = reinterpret_cast<const double2*>(D + (size_t)row * npad);
+        for (int cc = tid; cc < half; cc += QS_FIN_THREADS) {
+          const double2 v = __ldg(R2 + cc);
+          if (src_of_pos[2 * cc] >= 0 && !isnan(v.x) && qs_bin(&kn, v.x) == my_bin) fn(dkey(v.x));
+          if (src_of_pos[2 * cc + 1] >= 0 && !isnan(v.y) && qs_bin(&kn, v.y) == my_bin) fn(dkey(v.y));
+        }
+      }
+    };
+    for (int t = 0; t < T; ++t) {
+      if (st->t_slot[t] != s) continue;  // uniform across the CTA
+      const unsigned long long key = qs_digit_select(for_each_in_bin, st->slot_min[s], st->slot_max[s], st->t_rank[t], hist, s_scan, &s_pfx, &s_rank);
+      if (tid == 0) st->t_key[t] = key;
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(&st->done, 1u) == (unsigned)(U - 1));
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const long long N = st->N;
+  volatile unsigned long long* tk = st->t_key;
+  for (int p = tid; p < P; p += QS_FIN_THREADS) {
+    if (N <= 0) {
+      cutoff[p] = nan("");
+      continue;
+    }
+    const double idx = __dadd_rn(1.0, __dmul_rn((double)(N - 1), pct[p]));
+    const double lo = floor(idx);
+    double q = dkey_inv(tk[2 * p]);
+    const double xh = dkey_inv(tk[2 * p + 1]);
+    if (idx > lo && xh != q) {
+      const double hfrac = __dsub_rn(idx, lo);
+      q = __dadd_rn(__dmul_rn(__dsub_rn(1.0, hfrac), q), __dmul_rn(hfrac, xh));
+    }
+    cutoff[p] = q;
+  }
+}
+
+}  // namespace mdeggs
