@@ -6,7 +6,7 @@
 // passes plus histogram/scan kernels: ~11 dependent launches that, for the 10^4..10^6 edges of a network, are pure
 // launch latency (cfg3: 53,035 edges, ~100 us).  Here instead:
 //   1. the kernel that produces p (k_finish) drops every edge into one of NB monotone buckets of its p-value
-//      (bs_bucket: one bucket per binade below 2^-10, equal-width buckets above — balanced for uniform null p-values
+//      (bs_bucket: two buckets per binade below 2^-10, equal-width buckets above — balanced for uniform null p-values
 //      and for the heavy left tail of true signals) with a warp-aggregated atomic that also hands the edge its slot
 //      inside the bucket;
 //   2. k_bsort_scatter turns the bucket counts into offsets (every CTA scans the few thousand counts itself) and
@@ -25,11 +25,10 @@
 
 namespace mdeggs {
 
-constexpr int BS_NLOG = 1013;       // buckets 0..1012: biased exponent of p < 2^-10 (0 also holds p <= 0)
-constexpr int BS_CAP = 1024;        // run granularity; shared memory holds 2 * BS_CAP elements
-constexpr int BS_SORT_THREADS = 512;
-constexpr int BS_RUN_BUCKETS = 2048;  // bucket offsets of a run kept in shared memory
-constexpr int BS_WARP_MAX = 128;    // largest bucket a single warp ranks by itself
+constexpr int BS_NLOG = 2026;       // buckets 0..2025: (biased exponent, top mantissa bit) of p < 2^-10 (0 also holds p <= 0)
+constexpr int BS_CAP = 512;         // run granularity; shared memory holds 2 * BS_CAP elements
+constexpr int BS_SORT_THREADS = 256;
+constexpr int BS_WARP_MAX = 32;     // largest bucket whose elements are ranked by counting
 constexpr int64_t BS_MAX_E = 1 << 22;  // beyond this the CUB radix sort is used
 
 __host__ __device__ __forceinline__ int bs_nlin(int64_t E) {
@@ -43,7 +42,7 @@ __host__ __device__ __forceinline__ int bs_nbuckets(int64_t E) { return BS_NLOG 
 __device__ __forceinline__ int bs_bucket(double p, int nlin, double scale) {
   if (isnan(p)) return BS_NLOG + nlin;
   if (!(p > 0.0)) return 0;
-  if (p < 0x1p-10) return (int)((__double_as_longlong(p) >> 52) & 0x7ff);  // 0..1012
+  if (p < 0x1p-10) return (int)((__double_as_longlong(p) >> 51) & 0xfff);  // 0..2025
   int b = (int)((p - 0x1p-10) * scale);                                    // monotone in p
   b = b > nlin - 1 ? nlin - 1 : b;
   return BS_NLOG + b;
@@ -231,17 +230,18 @@ __device__ __forceinline__ bool bs_less(unsigned long long ka, int ia, unsigned 
 // virtual +infinity padding above n never has to move and the network works for any n (pairs whose upper index is
 // >= n are skipped).  Sorts by (key, edge id).
 template <class Mem>
-__device__ __forceinline__ void bs_bitonic(Mem mem, int n, int n2) {
+__device__ __forceinline__ void bs_bitonic(Mem mem, int n, int n2, int tid0 = -1, int nthr0 = 0) {
+  const int tid = tid0 < 0 ? (int)threadIdx.x : tid0, nthr = tid0 < 0 ? (int)blockDim.x : nthr0;
   for (int k = 2; k <= n2; k <<= 1) {
     const int hk = k >> 1;
-    for (int t = threadIdx.x; t < (n2 >> 1); t += blockDim.x) {  // flip step: i <-> mirrored partner in its k-block
+    for (int t = tid; t < (n2 >> 1); t += nthr) {  // flip step: i <-> mirrored partner in its k-block
       const int blk = t / hk, w = t - blk * hk;
       const int i = blk * k + w, x = blk * k + (k - 1 - w);
       if (x < n) mem.cas(i, x);
     }
     mem.sync();
     for (int j = hk >> 1; j > 0; j >>= 1) {
-      for (int t = threadIdx.x; t < (n2 >> 1); t += blockDim.x) {
+      for (int t = tid; t < (n2 >> 1); t += nthr) {
         const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));  // index with bit j clear
         const int x = i | j;
         if (x < n) mem.cas(i, x);
@@ -265,6 +265,12 @@ struct BsSmem {
     }
   }
   __device__ __forceinline__ void sync() const { __syncthreads(); }
+};
+struct BsSmemWarp {  // one warp sorting its own range of shared memory
+  unsigned long long* k;
+  int* i;
+  __device__ __forceinline__ void cas(int a, int b) const { BsSmem{k, i}.cas(a, b); }
+  __device__ __forceinline__ void sync() const { __syncwarp(); }
 };
 struct BsGmem {
   unsigned long long* k;
@@ -344,21 +350,33 @@ __global__ void __launch_bounds__(BS_SORT_THREADS) k_bsort_sort(BsArgs B, unsign
   const int n = hi - lo;
   if (n <= 0) return;
   if (n <= 2 * BS_CAP) {
-    // The run fits in shared memory.  Buckets are tiny on average (~16 edges): a warp takes a bucket of up to
-    // BS_WARP_MAX elements and ranks each element against the whole bucket with broadcast shared-memory reads (no
-    // barrier, no sorting network); the rare larger bucket is sorted by the whole CTA afterwards.
-    __shared__ int s_big[64];
+    // The run fits in shared memory.  Buckets are tiny (16 edges on average, 1-3 in the binade buckets of the small
+    // p-values), so the work is spread per ELEMENT, not per bucket: a thread per bucket marks its elements with the
+    // bucket's range, then a thread per element ranks its (key, edge id) inside that range with a short loop of
+    // shared-memory reads.  No barrier-separated sorting network, no serial walk over buckets.  The rare bucket of
+    // more than BS_WARP_MAX elements is sorted in place by one warp (warp-synchronous network).
+    __shared__ unsigned short s_st[2 * BS_CAP], s_cn[2 * BS_CAP];
+    __shared__ int s_big[2 * BS_CAP / BS_WARP_MAX];
     __shared__ int s_nbig;
-    __shared__ int s_bb[BS_RUN_BUCKETS + 1];  // offsets of this run's buckets (run 0 alone spans the ~1000 binade buckets)
-    const int nbk = bl - bf;
-    const bool bb_smem = nbk <= BS_RUN_BUCKETS;
-    if (bb_smem)
-      for (int i = threadIdx.x; i <= nbk; i += blockDim.x) s_bb[i] = B.base[bf + i];
-    auto bucket_base = [&](int b) { return bb_smem ? s_bb[b - bf] : B.base[b]; };
     if (threadIdx.x == 0) s_nbig = 0;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
       sk[i] = bkey[lo + i];
       si[i] = bidx[lo + i];
+      s_cn[i] = 0;
+    }
+    __syncthreads();
+    for (int b = bf + threadIdx.x; b < bl; b += blockDim.x) {
+      const int o = B.base[b], bn = B.base[b + 1] - o;
+      if (bn <= 0) continue;
+      const int blo = o - lo;
+      if (bn <= BS_WARP_MAX) {
+        for (int q = blo; q < blo + bn; ++q) {
+          s_st[q] = (unsigned short)blo;
+          s_cn[q] = (unsigned short)bn;
+        }
+      } else {
+        s_big[atomicAdd(&s_nbig, 1)] = b;
+      }
     }
     __syncthreads();
     auto emit = [&](int pos, unsigned long long k, int e) {
@@ -367,52 +385,25 @@ __global__ void __launch_bounds__(BS_SORT_THREADS) k_bsort_sort(BsArgs B, unsign
       sb[pos] = eb[e];
       sidx[pos] = e;
     };
+    for (int q = threadIdx.x; q < n; q += blockDim.x) {
+      const int bn = s_cn[q];
+      if (bn == 0) continue;  // member of a larger bucket
+      const int blo = s_st[q];
+      const unsigned long long mk = sk[q];
+      const int me = si[q];
+      int rk = 0;
+      for (int t = 0; t < bn; ++t) rk += bs_less(sk[blo + t], si[blo + t], mk, me);
+      emit(lo + blo + rk, mk, me);
+    }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-    for (int b = bf + warp; b < bl; b += nwarp) {
-      const int blo = bucket_base(b) - lo, bn = bucket_base(b + 1) - bucket_base(b);
-      if (bn <= 0) continue;
-      if (bn > BS_WARP_MAX) {
-        if (lane == 0) {
-          const int at = atomicAdd(&s_nbig, 1);
-          if (at < 64) s_big[at] = b;
-        }
-        continue;
-      }
-      unsigned long long mk[BS_WARP_MAX / 32];
-      int me[BS_WARP_MAX / 32], rk[BS_WARP_MAX / 32];
-#pragma unroll
-      for (int u = 0; u < BS_WARP_MAX / 32; ++u) {
-        const int i = u * 32 + lane;
-        mk[u] = i < bn ? sk[blo + i] : ~0ull;
-        me[u] = i < bn ? si[blo + i] : 0x7fffffff;
-        rk[u] = 0;
-      }
-      for (int t = 0; t < bn; ++t) {
-        const unsigned long long k = sk[blo + t];  // broadcast
-        const int e = si[blo + t];
-#pragma unroll
-        for (int u = 0; u < BS_WARP_MAX / 32; ++u) rk[u] += bs_less(k, e, mk[u], me[u]);
-      }
-#pragma unroll
-      for (int u = 0; u < BS_WARP_MAX / 32; ++u)
-        if (u * 32 + lane < bn) emit(lo + blo + rk[u], mk[u], me[u]);
-    }
-    __syncthreads();
     const int nbig = s_nbig;
-    if (nbig > 64) {  // (cannot happen: 64 buckets of > BS_WARP_MAX elements do not fit a run) sort the whole run
-      int n2 = 1;
-      while (n2 < n) n2 <<= 1;
-      bs_bitonic(BsSmem{sk, si}, n, n2);
-      for (int i = threadIdx.x; i < n; i += blockDim.x) emit(lo + i, sk[i], si[i]);
-      return;
-    }
-    for (int q = 0; q < nbig; ++q) {
-      const int b = s_big[q];
+    for (int i = warp; i < nbig; i += nwarp) {
+      const int b = s_big[i];
       const int blo = B.base[b] - lo, bn = B.base[b + 1] - B.base[b];
       int n2 = 1;
       while (n2 < bn) n2 <<= 1;
-      bs_bitonic(BsSmem{sk + blo, si + blo}, bn, n2);
-      for (int i = threadIdx.x; i < bn; i += blockDim.x) emit(lo + blo + i, sk[blo + i], si[blo + i]);
+      bs_bitonic(BsSmemWarp{sk + blo, si + blo}, bn, n2, lane, 32);
+      for (int t = lane; t < bn; t += 32) emit(lo + blo + t, sk[blo + t], si[blo + t]);
     }
     return;
   }

@@ -83,11 +83,11 @@ struct Shard {
     if (e == cudaSuccess) h_stage_cap = bytes + 256;
     return e;
   }
-  DevBuf assay, from, to, ea, eb, stage_dev, bs_count, bs_slot, excl, node_of_row, rowlist, scal, src_of_pos, pct, cutoff, D, cub_tmp, mean, sxx, med, bad, stat, status, p_edge, coef, iters, act, counters, sortk, sortk2, idx,
+  DevBuf assay, from, to, ea, eb, stage_dev, bs_count, bs_slot, seg_done, excl, node_of_row, rowlist, scal, src_of_pos, pct, cutoff, D, cub_tmp, mean, sxx, med, bad, stat, status, p_edge, coef, iters, act, counters, sortk, sortk2, idx,
       idx2, ps, sa, sb, tile_cnt, tile_base, seg_n, tile_min, tile_carry, padj_best, cat_best, cat, padj, med_out,
       small_out, rsel_hist, rsel_state, rsel_cand, dense_S, cf_tab, sxy;
   void release_all() {
-    DevBuf* all[] = {&assay, &from, &to, &ea, &eb, &stage_dev, &bs_count, &bs_slot, &excl, &node_of_row, &rowlist, &scal, &src_of_pos, &pct, &cutoff,
+    DevBuf* all[] = {&assay, &from, &to, &ea, &eb, &stage_dev, &bs_count, &bs_slot, &seg_done, &excl, &node_of_row, &rowlist, &scal, &src_of_pos, &pct, &cutoff,
                      &D, &cub_tmp, &mean, &sxx, &med, &bad, &stat, &status, &p_edge,
                      &coef, &iters, &act, &counters, &sortk, &sortk2, &idx, &idx2, &ps, &sa, &sb, &tile_cnt,
                      &tile_base, &seg_n, &tile_min, &tile_carry, &padj_best, &cat_best, &cat, &padj, &med_out,
@@ -200,6 +200,8 @@ void trace_mark(mdeggs_ctx* ctx, const char* name, cudaStream_t stream) {
     }                                                                                          \
   } while (0)
 
+// layout of the packed small results (see k_select_best)
+size_t small_block_bytes(int P) { return (size_t)4 * (P > 0 ? P : 1) * 8 + 16 + 16; }
 inline unsigned blocks_for(int64_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
 
 int init_shard(mdeggs_ctx* ctx, Shard& s) {
@@ -222,6 +224,18 @@ struct HostLayout {
   SegLayout L;
   std::vector<int32_t> src_of_pos;
 };
+
+void result_df(const mdeggs_problem* in, const HostLayout& H, double* dfh) {
+  if (in->K == 2) {
+    dfh[0] = 1.0;
+    dfh[1] = (double)(in->n - 4);
+  } else {
+    int Ke = 0;
+    for (int k = 0; k < in->K; ++k) Ke += H.L.cnt[k] > 0;
+    dfh[0] = (double)(Ke - 1);
+    dfh[1] = (double)(in->n - 2 * Ke);
+  }
+}
 
 int build_layout(mdeggs_ctx* ctx, const mdeggs_problem* in, HostLayout& H) {
   SegLayout& L = H.L;
@@ -341,17 +355,23 @@ int run_adjust(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, int n_segmen
   A.tot = s.counters.as<unsigned long long>();  // c_tot[P], filled by k_percolate
   A.reuse_tiles = reuse_tiles ? 1 : 0;
   dim3 grid((unsigned)ntiles, (unsigned)n_segments);
-  if (!reuse_tiles) {
-    LAUNCH(k_bh_count, grid, BH_THREADS, 0, s.s_main, A, s.tile_cnt.as<int32_t>());
-    LAUNCH(k_bh_scan_tiles, n_segments, 256, 0, s.s_main, s.tile_cnt.as<int32_t>(), ntiles,
-           s.tile_base.as<long long>(), s.seg_n.as<long long>());
+  // per-segment "CTAs done" counters of the fused tile passes: zero when first allocated, re-armed by the kernels
+  {
+    const size_t need = (size_t)in->P * in->K * 2 * sizeof(int);
+    if (need > s.seg_done.cap) {
+      CU(s.seg_done.ensure(need));
+      CU(cudaMemsetAsync(s.seg_done.p, 0, s.seg_done.cap, s.s_main));
+    }
   }
-  if (in->padj != MDEGGS_PADJ_BONFERRONI && !reuse_tiles) {
+  int* done_a = s.seg_done.as<int>();
+  int* done_b = done_a + (size_t)in->P * in->K;
+  if (!reuse_tiles)
+    LAUNCH(k_bh_count, grid, BH_THREADS, 0, s.s_main, A, s.tile_cnt.as<int32_t>(), s.tile_base.as<long long>(),
+           s.seg_n.as<long long>(), done_a);
+  if (in->padj != MDEGGS_PADJ_BONFERRONI && !reuse_tiles)
     LAUNCH(k_bh_tilemin, grid, BH_THREADS, 0, s.s_main, A, in->padj, s.tile_cnt.as<int32_t>(),
-           s.tile_base.as<long long>(), s.seg_n.as<long long>(), s.tile_min.as<double>());
-    LAUNCH(k_bh_suffix_min, n_segments, 256, 0, s.s_main, s.tile_min.as<double>(), ntiles, in->padj,
-           s.tile_carry.as<double>());
-  }
+           s.tile_base.as<long long>(), s.seg_n.as<long long>(), s.tile_min.as<double>(),
+           s.tile_carry.as<double>(), done_b);
   LAUNCH(k_bh_final, grid, BH_THREADS, 0, s.s_main, A, in->padj, s.tile_cnt.as<int32_t>(), s.tile_base.as<long long>(),
          s.seg_n.as<long long>(),
          s.tile_carry.as<double>(), sig_dev, padj_out, padj_stride);
@@ -452,7 +472,7 @@ int stage_inputs(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const Host
   const size_t sop_bytes = H.src_of_pos.size() * 4, pct_bytes = (size_t)(in->P > 0 ? in->P : 0) * 8;
   const size_t pct_off = (sop_bytes + 15) & ~(size_t)15;
   const size_t blk = pct_off + (pct_bytes ? pct_bytes : 8);
-  CU(s.ensure_stage(blk + 64));
+  CU(s.ensure_stage(blk + small_block_bytes(in->P) + 128));  // inputs at the front, packed small results at the back
   CU(s.stage_dev.ensure(blk));
   std::vector<char> cur(blk, 0);
   memcpy(cur.data(), H.src_of_pos.data(), sop_bytes);
@@ -581,8 +601,6 @@ int run_shard_main(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
   } else if (P > 0) {
     LAUNCH(k_fill_f64, 1, 64, 0, s.s_sort, s.cutoff.as<double>(), (int64_t)P, nan(""));
   }
-  EVREC(s.ev[EV_Q1], s.s_sort);
-  CU(cudaEventRecord(s.ev_join, s.s_sort));
   // ---- per-run tail tables (depend only on the degrees of freedom) ----
   {
     const bool rlm2 = (K == 2 && in->method == MDEGGS_METHOD_RLM);
@@ -624,6 +642,17 @@ int run_shard_main(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
     }
   }
   EVREC(s.ev[EV_STATS], s.s_main);
+  // K7 activity masks need the medians (K2, this stream) and the cut-offs (S4, side stream): they are computed on
+  // the side stream while the pair fits run
+  CU(s.act.ensure((size_t)(P > 0 ? P : 1) * (n_nodes > 0 ? n_nodes : 1)));
+  if (n_nodes > 0 && P > 0) {
+    CU(cudaEventRecord(s.ev_sample, s.s_main));  // (event reused: "medians ready")
+    CU(cudaStreamWaitEvent(s.s_sort, s.ev_sample, 0));
+    LAUNCH(k_actmask, blocks_for((int64_t)P * n_nodes, 256), 256, 0, s.s_sort, s.med.as<double>(),
+           s.cutoff.as<double>(), d_nn, P, K, n_nodes, s.act.as<uint8_t>());
+  }
+  EVREC(s.ev[EV_Q1], s.s_sort);
+  CU(cudaEventRecord(s.ev_join, s.s_sort));
   // ---- pair fits on this rank's contiguous edge block ----
   const int64_t chunk = (E + s.world - 1) / s.world;
   const int64_t e_lo = (int64_t)s.rank * chunk < E ? (int64_t)s.rank * chunk : E;
@@ -868,8 +897,6 @@ int run_shard_back(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
     }
   }
   if (n_nodes > 0 && P > 0) {
-    LAUNCH(k_actmask, blocks_for((int64_t)P * n_nodes, 256), 256, 0, s.s_main, s.med.as<double>(),
-           s.cutoff.as<double>(), d_nn, P, K, act_stride, s.act.as<uint8_t>());
     if (E > 0)
       LAUNCH(k_percolate, blocks_for(E, 256), 256, (size_t)3 * P * sizeof(unsigned), s.s_main, s.ea.as<int32_t>(),
              s.eb.as<int32_t>(), s.status.as<int32_t>(), s.p_edge.as<double>(),
@@ -956,8 +983,14 @@ int run_shard_back2(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const m
   double* d_padj = nullptr;
   if (keep_all_padj) d_padj = (out->padj && dev_out && emit) ? out->padj : s.padj.as<double>();
   const unsigned long long* sig_src = dev_adjust ? c_sig : c_raw;
-  LAUNCH(k_select_best, 1, 32, 0, s.s_main, c_tot, c_fail, sig_src, P, in->padj == MDEGGS_PADJ_HOST ? 1 : 0, o_tot,
-         o_sig, o_fail, d_best);
+  {
+    double dfh[2];
+    result_df(in, H, dfh);
+    CU(s.small_out.ensure(small_block_bytes(P)));
+    LAUNCH(k_select_best, 1, 32, 0, s.s_main, c_tot, c_fail, sig_src, P, in->padj == MDEGGS_PADJ_HOST ? 1 : 0,
+           s.cutoff.as<double>(), s.scal.as<int32_t>() + 2 * SC_NNODES, s.scal.as<int32_t>() + 2 * SC_ERR, dfh[0],
+           dfh[1], s.small_out.as<long long>(), d_best);
+  }
   // rows of the chosen percentile
   const bool want_cat_best = out->cat_best && E > 0 && in->padj != MDEGGS_PADJ_HOST;
   if (want_cat_best) CU(s.cat_best.ensure((size_t)E));
@@ -986,83 +1019,112 @@ int run_shard_back2(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const m
   return MDEGGS_OK;
 }
 
-// Phase C (always eager): results -> caller buffers
+// Phase C (always eager): results -> caller buffers.  The small results travel as one packed block (k_select_best):
+// device callers get everything through ONE copy kernel, host callers through one D2H per large array plus one for
+// the block, which finish_small_outputs() scatters after the final synchronisation.
 int emit_outputs(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const mdeggs_result* out, const HostLayout& H,
                  int32_t n_nodes) {
   const int G = in->G, K = in->K, P = in->P;
   const int64_t E = in->E;
+  (void)H;
   CU(cudaSetDevice(s.device));
   const int Pn = P > 0 ? P : 1;
-  int32_t* d_best = s.scal.as<int32_t>() + 2 * SC_BEST;
-  unsigned long long* c_tot = s.counters.as<unsigned long long>();
-  long long* o_tot = (long long*)(c_tot + 4 * Pn);
-  long long* o_sig = o_tot + Pn;
-  long long* o_fail = o_tot + 2 * Pn;
   const bool dev_out = in->mem == MDEGGS_MEM_DEVICE;
-  const bool dev_adjust = (in->padj == MDEGGS_PADJ_BONFERRONI || in->padj == MDEGGS_PADJ_BH || in->padj == MDEGGS_PADJ_HOLM ||
-                           in->padj == MDEGGS_PADJ_HOCHBERG || in->padj == MDEGGS_PADJ_BY);
+  const bool dev_adjust = device_adjust(in);
   const int8_t* d_cat = (out->cat && E > 0 && P > 0) ? (dev_out ? out->cat : s.cat.as<int8_t>()) : nullptr;
   const double* d_padj = (dev_adjust && E > 0 && P > 0 && n_nodes > 0 && out->padj)
                              ? (dev_out ? out->padj : s.padj.as<double>())
                              : nullptr;  // (an internal scratch copy used only for the best row is never emitted)
   const bool want_cat_best = out->cat_best && E > 0 && in->padj != MDEGGS_PADJ_HOST;
   const bool want_padj_best = out->padj_best && E > 0 && dev_adjust && n_nodes > 0 && P > 0;
-  const int mem = in->mem;
-  int rc;
-  if ((rc = copy_out(ctx, s, out->cutoff, s.cutoff.p, (size_t)P * 8, mem))) return rc;
-  if (out->median)
-    if ((rc = copy_out(ctx, s, out->median, s.med_out.p, (size_t)G * K * 8, mem))) return rc;
-  if ((rc = copy_out(ctx, s, out->p_edge, s.p_edge.p, (size_t)E * 8, mem))) return rc;
-  if ((rc = copy_out(ctx, s, out->stat, s.stat.p, (size_t)E * 8, mem))) return rc;
-  if ((rc = copy_out(ctx, s, out->coef, s.coef.p, (size_t)E * 2 * K * 8, mem))) return rc;
-  if ((rc = copy_out(ctx, s, out->status, s.status.p, (size_t)E * 4, mem))) return rc;
-  if (out->iters) {
-    if (K == 2 && in->method == MDEGGS_METHOD_RLM) {
-      if ((rc = copy_out(ctx, s, out->iters, s.iters.p, (size_t)E * 4, mem))) return rc;
-    } else if (mem == MDEGGS_MEM_HOST) {
-      memset(out->iters, 0, (size_t)E * 4);
-    } else {
-      CU(cudaMemsetAsync(out->iters, 0, (size_t)E * 4, s.s_main));
+  const bool is_rlm = K == 2 && in->method == MDEGGS_METHOD_RLM;
+  const char* blk = s.small_out.as<char>();
+  const size_t blk_bytes = small_block_bytes(P);
+  struct Item {
+    void* dst;
+    const void* src;
+    size_t bytes;
+  };
+  std::vector<Item> big, small;
+  auto add = [](std::vector<Item>& v, void* dst, const void* src, size_t bytes) {
+    if (dst && bytes) v.push_back({dst, src, bytes});
+  };
+  add(small, out->tot_edges, blk, (size_t)P * 8);
+  add(small, out->sig_count, blk + (size_t)Pn * 8, (size_t)P * 8);
+  add(small, out->fail_count, blk + (size_t)2 * Pn * 8, (size_t)P * 8);
+  add(small, out->cutoff, blk + (size_t)3 * Pn * 8, (size_t)P * 8);
+  add(small, out->best, blk + (size_t)4 * Pn * 8, 4);
+  add(small, out->df, blk + (size_t)4 * Pn * 8 + 16, 16);
+  add(big, out->median, s.med_out.p, (size_t)G * K * 8);
+  add(big, out->p_edge, s.p_edge.p, (size_t)E * 8);
+  add(big, out->stat, s.stat.p, (size_t)E * 8);
+  add(big, out->coef, s.coef.p, (size_t)E * 2 * K * 8);
+  add(big, out->status, s.status.p, (size_t)E * 4);
+  add(big, out->iters, is_rlm ? s.iters.p : nullptr, (size_t)E * 4);  // null source: zeros
+  if (d_cat && d_cat != out->cat) add(big, out->cat, d_cat, (size_t)P * E);
+  if (d_padj && d_padj != out->padj) add(big, out->padj, d_padj, (size_t)P * E * 8);
+  if (want_cat_best) add(big, out->cat_best, s.cat_best.p, (size_t)E);
+  if (want_padj_best) add(big, out->padj_best, s.padj_best.p, (size_t)E * 8);
+  if (dev_out) {
+    EmitTab T;
+    memset(&T, 0, sizeof T);
+    int ne = 0;
+    size_t max_bytes = 0;
+    auto flush = [&]() {
+      if (ne == 0) return;
+      const unsigned gx = (unsigned)((max_bytes / 16 + 255) / 256);
+      dim3 grid(gx < 1 ? 1 : (gx > 148 * 8 ? 148 * 8 : gx), (unsigned)ne);
+      LAUNCH(k_emit, grid, 256, 0, s.s_main, T);
+      memset(&T, 0, sizeof T);
+      ne = 0;
+      max_bytes = 0;
+    };
+    for (const std::vector<Item>* v : {&small, &big})
+      for (const Item& it : *v) {
+        T.dst[ne] = it.dst;
+        T.src[ne] = it.src;
+        T.bytes[ne] = (long long)it.bytes;
+        max_bytes = it.bytes > max_bytes ? it.bytes : max_bytes;
+        if (++ne == EMIT_MAX) flush();
+      }
+    flush();
+  } else {
+    for (const Item& it : big) {
+      if (it.src) {
+        CU(cudaMemcpyAsync(it.dst, it.src, it.bytes, cudaMemcpyDeviceToHost, s.s_main));
+        ctx->stats.d2h_bytes += (int64_t)it.bytes;
+      } else {
+        memset(it.dst, 0, it.bytes);
+      }
     }
   }
-  if (out->cat && d_cat && d_cat != out->cat)
-    if ((rc = copy_out(ctx, s, out->cat, d_cat, (size_t)P * E, mem))) return rc;
-  if (out->padj && d_padj && d_padj != out->padj)
-    if ((rc = copy_out(ctx, s, out->padj, d_padj, (size_t)P * E * 8, mem))) return rc;
-  if ((rc = copy_out(ctx, s, out->tot_edges, o_tot, (size_t)P * 8, mem))) return rc;
-  if ((rc = copy_out(ctx, s, out->sig_count, o_sig, (size_t)P * 8, mem))) return rc;
-  if ((rc = copy_out(ctx, s, out->fail_count, o_fail, (size_t)P * 8, mem))) return rc;
-  if ((rc = copy_out(ctx, s, out->best, d_best, 4, mem))) return rc;
-  if (want_cat_best)
-    if ((rc = copy_out(ctx, s, out->cat_best, s.cat_best.p, (size_t)E, mem))) return rc;
-  if (want_padj_best)
-    if ((rc = copy_out(ctx, s, out->padj_best, s.padj_best.p, (size_t)E * 8, mem))) return rc;
-  if (out->df) {
-    double dfh[2];
-    if (K == 2) {
-      dfh[0] = 1.0;
-      dfh[1] = (double)(in->n - 4);
-    } else {
-      int Ke = 0;
-      for (int k = 0; k < K; ++k) Ke += H.L.cnt[k] > 0;
-      dfh[0] = (double)(Ke - 1);
-      dfh[1] = (double)(in->n - 2 * Ke);
-    }
-    if (mem == MDEGGS_MEM_HOST) {
-      out->df[0] = dfh[0];
-      out->df[1] = dfh[1];
-    } else {  // the tail of the pinned staging block carries the two doubles
-      double* st = reinterpret_cast<double*>((char*)s.h_stage + s.h_stage_cap - 16);
-      st[0] = dfh[0];
-      st[1] = dfh[1];
-      CU(cudaMemcpyAsync(out->df, st, 16, cudaMemcpyHostToDevice, s.s_main));
-    }
-  }
-  // node count + error flag ride along to pinned memory (read after the final sync, no extra blocking copy)
-  CU(cudaMemcpyAsync((char*)s.h_stage + s.h_stage_cap - 48, s.scal.p, 16, cudaMemcpyDeviceToHost, s.s_main));
+  // the packed block always reaches pinned memory: node count + error flag are read after the final sync, and host
+  // callers get their small results from it (finish_small_outputs)
+  CU(cudaMemcpyAsync((char*)s.h_stage + s.h_stage_cap - 64 - blk_bytes, blk, blk_bytes, cudaMemcpyDeviceToHost,
+                     s.s_main));
+  if (!dev_out) ctx->stats.d2h_bytes += (int64_t)blk_bytes;
   CU(cudaEventRecord(s.ev[EV_END], s.s_main));
   trace_mark(ctx, "(outputs copied)", s.s_main);
   return MDEGGS_OK;
+}
+
+// after the final synchronisation: small results from the pinned copy of the packed block -> host caller buffers;
+// returns the node count and the error flag
+void finish_small_outputs(Shard& s, const mdeggs_problem* in, const mdeggs_result* out, int32_t* n_nodes,
+                          int32_t* err_flag) {
+  const int P = in->P, Pn = P > 0 ? P : 1;
+  const size_t blk_bytes = small_block_bytes(P);
+  const char* blk = (const char*)s.h_stage + s.h_stage_cap - 64 - blk_bytes;
+  const int32_t* tail = reinterpret_cast<const int32_t*>(blk + (size_t)4 * Pn * 8);
+  *n_nodes = tail[1];
+  *err_flag = tail[2];
+  if (in->mem != MDEGGS_MEM_HOST) return;
+  if (out->tot_edges) memcpy(out->tot_edges, blk, (size_t)P * 8);
+  if (out->sig_count) memcpy(out->sig_count, blk + (size_t)Pn * 8, (size_t)P * 8);
+  if (out->fail_count) memcpy(out->fail_count, blk + (size_t)2 * Pn * 8, (size_t)P * 8);
+  if (out->cutoff) memcpy(out->cutoff, blk + (size_t)3 * Pn * 8, (size_t)P * 8);
+  if (out->best) memcpy(out->best, tail, 4);
+  if (out->df) memcpy(out->df, tail + 4, 16);
 }
 
 float ev_ms(cudaEvent_t a, cudaEvent_t b) {
@@ -1353,13 +1415,12 @@ int mdeggs_run_omic(mdeggs_ctx* ctx, const mdeggs_problem* in, mdeggs_result* ou
   CU(cudaGetLastError());  // kernel launches are not checked one by one: surface any launch failure here
   Shard& s0 = ctx->shards[0];
   {
-    long long host_scal[2];
-    memcpy(host_scal, (char*)s0.h_stage + s0.h_stage_cap - 48, 16);
-    if ((int32_t)host_scal[SC_ERR] != 0) {
+    int32_t err_flag = 0;
+    finish_small_outputs(s0, in, out, &n_nodes, &err_flag);
+    if (err_flag != 0) {
       set_err(ctx, "from/to contain an index outside 1..G");
       return MDEGGS_EINVAL;
     }
-    n_nodes = (int32_t)host_scal[SC_NNODES];
   }
   if (ctx->trace && !ctx->trace_recs.empty()) {  // timeline of this call: end time of every launch, per stream
     float prev[2] = {0.f, 0.f};

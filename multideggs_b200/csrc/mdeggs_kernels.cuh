@@ -735,12 +735,51 @@ __device__ __forceinline__ void bh_load(const BhArgs& A, int p, int c, int64_t t
   }
 }
 
-// pass A: members per tile
-__global__ void __launch_bounds__(BH_THREADS) k_bh_count(BhArgs A, int32_t* __restrict__ tile_cnt) {
+// exclusive scan of the tile counts of one segment (whole CTA of BH_THREADS); seg_n = members of the segment
+__device__ __forceinline__ void bh_scan_tiles_body(const int32_t* __restrict__ tile_cnt, int ntiles, size_t seg,
+                                                   long long* __restrict__ tile_base, long long* __restrict__ seg_n) {
+  typedef cub::BlockScan<long long, BH_THREADS> Scan;
+  __shared__ typename Scan::TempStorage tmp;
+  __shared__ long long carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const size_t base = seg * ntiles;
+  for (int t0 = 0; t0 < ntiles; t0 += BH_THREADS) {
+    int t = t0 + threadIdx.x;
+    long long v = t < ntiles ? (long long)__ldcg(tile_cnt + base + t) : 0, ex, agg;
+    Scan(tmp).ExclusiveSum(v, ex, agg);
+    if (t < ntiles) tile_base[base + t] = carry + ex;
+    __syncthreads();
+    if (threadIdx.x == 0) carry += agg;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) seg_n[seg] = carry;
+}
+
+// "last CTA of the segment" election: every CTA of a segment calls it once after publishing its tile partial;
+// returns true in exactly one CTA per segment (and re-arms the counter for the next launch)
+__device__ __forceinline__ bool bh_last_of_segment(int* __restrict__ seg_done, size_t seg, int ntiles) {
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int prev = atomicAdd(&seg_done[seg], 1);
+    s_last = prev == ntiles - 1;
+    if (s_last) seg_done[seg] = 0;
+  }
+  __syncthreads();
+  if (s_last) __threadfence();
+  return s_last != 0;
+}
+
+// pass A: members per tile; the last CTA of each segment turns the tile counts into tile offsets (ranks)
+__global__ void __launch_bounds__(BH_THREADS) k_bh_count(BhArgs A, int32_t* __restrict__ tile_cnt,
+                                                        long long* __restrict__ tile_base,
+                                                        long long* __restrict__ seg_n, int* __restrict__ seg_done) {
   int p, c;
   size_t seg;
   if (!bh_segment(A, p, c, seg)) return;
-  if (A.tot && A.tot[p] == 0) {  // nothing is tested at this percentile
+  if (A.tot && A.tot[p] == 0) {  // nothing is tested at this percentile (whole segment: no scan needed either)
     if (threadIdx.x == 0) tile_cnt[seg * A.ntiles + blockIdx.x] = 0;
     return;
   }
@@ -754,28 +793,7 @@ __global__ void __launch_bounds__(BH_THREADS) k_bh_count(BhArgs A, int32_t* __re
   for (int it = 0; it < BH_ITEMS; ++it) s += flag[it];
   int tot = Reduce(tmp).Sum(s);
   if (threadIdx.x == 0) tile_cnt[seg * A.ntiles + blockIdx.x] = tot;
-}
-
-// exclusive scan of the tile counts of each segment (one CTA per segment); seg_n = members of the segment
-__global__ void __launch_bounds__(256) k_bh_scan_tiles(const int32_t* __restrict__ tile_cnt, int ntiles,
-                                                       long long* __restrict__ tile_base,
-                                                       long long* __restrict__ seg_n) {
-  typedef cub::BlockScan<long long, 256> Scan;
-  __shared__ typename Scan::TempStorage tmp;
-  __shared__ long long carry;
-  if (threadIdx.x == 0) carry = 0;
-  __syncthreads();
-  const size_t base = (size_t)blockIdx.x * ntiles;
-  for (int t0 = 0; t0 < ntiles; t0 += 256) {
-    int t = t0 + threadIdx.x;
-    long long v = t < ntiles ? (long long)tile_cnt[base + t] : 0, ex, agg;
-    Scan(tmp).ExclusiveSum(v, ex, agg);
-    if (t < ntiles) tile_base[base + t] = carry + ex;
-    __syncthreads();
-    if (threadIdx.x == 0) carry += agg;
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) seg_n[blockIdx.x] = carry;
+  if (bh_last_of_segment(seg_done, seg, A.ntiles)) bh_scan_tiles_body(tile_cnt, A.ntiles, seg, tile_base, seg_n);
 }
 
 // q = sum(1 / (1:n)) of stats::p.adjust(method = "BY"): summed left to right for small n, asymptotic beyond
@@ -806,60 +824,22 @@ struct MaxOp {
   __device__ __forceinline__ double operator()(double a, double b) const { return a > b ? a : b; }
 };
 
-// pass B: BH values with global ranks -> minimum of each tile
-__global__ void __launch_bounds__(BH_THREADS) k_bh_tilemin(BhArgs A, int mode, const int32_t* __restrict__ tile_cnt,
-                                                          const long long* __restrict__ tile_base,
-                                                          const long long* __restrict__ seg_n,
-                                                          double* __restrict__ tile_min) {
-  int p, c;
-  size_t seg;
-  if (!bh_segment(A, p, c, seg)) return;
-  if (tile_cnt[seg * A.ntiles + blockIdx.x] == 0) {  // no member of this segment in the tile
-    if (threadIdx.x == 0) tile_min[seg * A.ntiles + blockIdx.x] = mode == MDEGGS_PADJ_HOLM ? -INFINITY : INFINITY;
-    return;
-  }
-  typedef cub::BlockScan<int, BH_THREADS> Scan;
-  typedef cub::BlockReduce<double, BH_THREADS> Reduce;
-  __shared__ union {
-    typename Scan::TempStorage scan;
-    typename Reduce::TempStorage red;
-  } tmp;
-  int flag[BH_ITEMS], rank[BH_ITEMS];
-  double pv[BH_ITEMS];
-  bh_load(A, p, c, (int64_t)blockIdx.x * BH_TILE, flag, pv);
-  Scan(tmp.scan).InclusiveSum(flag, rank);
-  __syncthreads();
-  const long long base = tile_base[seg * A.ntiles + blockIdx.x];
-  const double n = (double)seg_n[seg];
-  const bool fwd_max = mode == MDEGGS_PADJ_HOLM;  // holm: cummax over ascending p; others: cummin from the largest p
-  double mn = fwd_max ? -INFINITY : INFINITY;
-  const double num = adj_numerator(mode, n);
-#pragma unroll
-  for (int it = 0; it < BH_ITEMS; ++it)
-    if (flag[it]) {
-      double v = adj_value(mode, n, num, base + rank[it], pv[it]);
-      mn = fwd_max ? fmax(mn, v) : fmin(mn, v);
-    }
-  double tmn = fwd_max ? Reduce(tmp.red).Reduce(mn, MaxOp()) : Reduce(tmp.red).Reduce(mn, MinOp());
-  if (threadIdx.x == 0) tile_min[seg * A.ntiles + blockIdx.x] = tmn;
-}
-
-// carry over the tiles of each segment (one CTA per segment): exclusive suffix-min walking the tiles from the end
-// (BH, hochberg, BY) or exclusive prefix-max walking them from the start (holm)
-__global__ void __launch_bounds__(256) k_bh_suffix_min(const double* __restrict__ tile_min, int ntiles, int mode,
-                                                       double* __restrict__ tile_carry) {
-  typedef cub::BlockScan<double, 256> Scan;
+// carry over the tiles of one segment (whole CTA): exclusive suffix-min walking the tiles from the end (BH, hochberg,
+// BY) or exclusive prefix-max walking them from the start (holm)
+__device__ __forceinline__ void bh_suffix_body(const double* __restrict__ tile_min, int ntiles, int mode, size_t seg,
+                                               double* __restrict__ tile_carry) {
+  typedef cub::BlockScan<double, BH_THREADS> Scan;
   __shared__ typename Scan::TempStorage tmp;
   __shared__ double carry;
   const bool fwd_max = mode == MDEGGS_PADJ_HOLM;
   const double ident = fwd_max ? -INFINITY : INFINITY;
   if (threadIdx.x == 0) carry = ident;
   __syncthreads();
-  const size_t base = (size_t)blockIdx.x * ntiles;
-  for (int t0 = 0; t0 < ntiles; t0 += 256) {
+  const size_t base = seg * ntiles;
+  for (int t0 = 0; t0 < ntiles; t0 += BH_THREADS) {
     int r = t0 + threadIdx.x;                    // position in walking order
     int t = fwd_max ? r : ntiles - 1 - r;        // tile index
-    double v = r < ntiles ? tile_min[base + t] : ident, ex, agg;
+    double v = r < ntiles ? __ldcg(tile_min + base + t) : ident, ex, agg;
     if (fwd_max) Scan(tmp).ExclusiveScan(v, ex, ident, MaxOp(), agg);
     else Scan(tmp).ExclusiveScan(v, ex, ident, MinOp(), agg);
     if (r < ntiles) tile_carry[base + t] = fwd_max ? fmax(carry, ex) : fmin(carry, ex);
@@ -867,6 +847,47 @@ __global__ void __launch_bounds__(256) k_bh_suffix_min(const double* __restrict_
     if (threadIdx.x == 0) carry = fwd_max ? fmax(carry, agg) : fmin(carry, agg);
     __syncthreads();
   }
+}
+
+// pass B: BH values with global ranks -> minimum of each tile; the last CTA of each segment carries them over
+__global__ void __launch_bounds__(BH_THREADS) k_bh_tilemin(BhArgs A, int mode, const int32_t* __restrict__ tile_cnt,
+                                                          const long long* __restrict__ tile_base,
+                                                          const long long* __restrict__ seg_n,
+                                                          double* __restrict__ tile_min,
+                                                          double* __restrict__ tile_carry, int* __restrict__ seg_done) {
+  int p, c;
+  size_t seg;
+  if (!bh_segment(A, p, c, seg)) return;
+  if (A.tot && A.tot[p] == 0) return;  // (same whole-segment exit as pass A)
+  typedef cub::BlockScan<int, BH_THREADS> Scan;
+  typedef cub::BlockReduce<double, BH_THREADS> Reduce;
+  __shared__ union {
+    typename Scan::TempStorage scan;
+    typename Reduce::TempStorage red;
+  } tmp;
+  const bool fwd_max = mode == MDEGGS_PADJ_HOLM;  // holm: cummax over ascending p; others: cummin from the largest p
+  if (tile_cnt[seg * A.ntiles + blockIdx.x] == 0) {  // no member of this segment in the tile
+    if (threadIdx.x == 0) tile_min[seg * A.ntiles + blockIdx.x] = fwd_max ? -INFINITY : INFINITY;
+  } else {
+    int flag[BH_ITEMS], rank[BH_ITEMS];
+    double pv[BH_ITEMS];
+    bh_load(A, p, c, (int64_t)blockIdx.x * BH_TILE, flag, pv);
+    Scan(tmp.scan).InclusiveSum(flag, rank);
+    __syncthreads();
+    const long long base = tile_base[seg * A.ntiles + blockIdx.x];
+    const double n = (double)seg_n[seg];
+    double mn = fwd_max ? -INFINITY : INFINITY;
+    const double num = adj_numerator(mode, n);
+#pragma unroll
+    for (int it = 0; it < BH_ITEMS; ++it)
+      if (flag[it]) {
+        double v = adj_value(mode, n, num, base + rank[it], pv[it]);
+        mn = fwd_max ? fmax(mn, v) : fmin(mn, v);
+      }
+    double tmn = fwd_max ? Reduce(tmp.red).Reduce(mn, MaxOp()) : Reduce(tmp.red).Reduce(mn, MinOp());
+    if (threadIdx.x == 0) tile_min[seg * A.ntiles + blockIdx.x] = tmn;
+  }
+  if (bh_last_of_segment(seg_done, seg, A.ntiles)) bh_suffix_body(tile_min, A.ntiles, mode, seg, tile_carry);
 }
 
 // pass C: adjusted values, count < 0.05, optional scatter to network order
@@ -957,12 +978,23 @@ __global__ void __launch_bounds__(BH_THREADS) k_bh_final(BhArgs A, int mode, con
   }
 }
 
-// which.max(sig_pvalues) over non-NULL percentiles (core_functions.R:475-495): first maximum
+// which.max(sig_pvalues) over non-NULL percentiles (core_functions.R:475-495): first maximum.  Also packs every small
+// result (counts, cut-offs, best, node count, error flag, degrees of freedom) into one contiguous block so that they
+// leave the device in a single copy:  i64 tot[P] sig[P] fail[P] | f64 cutoff[P] | i32 best nn err 0 | f64 df1 df2
 __global__ void k_select_best(const unsigned long long* __restrict__ tot, const unsigned long long* __restrict__ fail,
                               const unsigned long long* __restrict__ sig, int P, int host_adjust,
-                              long long* __restrict__ tot_out, long long* __restrict__ sig_out,
-                              long long* __restrict__ fail_out, int32_t* __restrict__ best) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+                              const double* __restrict__ cutoff, const int32_t* __restrict__ n_nodes,
+                              const int32_t* __restrict__ err, double df1, double df2, long long* __restrict__ blk,
+                              int32_t* __restrict__ best) {
+  if (blockIdx.x != 0) return;
+  const int Pn = P > 0 ? P : 1;
+  long long* tot_out = blk;
+  long long* sig_out = blk + Pn;
+  long long* fail_out = blk + 2 * Pn;
+  double* cut_out = reinterpret_cast<double*>(blk + 3 * Pn);
+  int32_t* tail = reinterpret_cast<int32_t*>(blk + 4 * Pn);
+  for (int p = threadIdx.x; p < P; p += blockDim.x) cut_out[p] = cutoff[p];
+  if (threadIdx.x != 0) return;
   int b = 0;
   long long bv = -1;
   for (int p = 0; p < P; ++p) {
@@ -977,6 +1009,36 @@ __global__ void k_select_best(const unsigned long long* __restrict__ tot, const 
     }
   }
   *best = b;
+  tail[0] = b;
+  tail[1] = *n_nodes;
+  tail[2] = *err;
+  tail[3] = 0;
+  reinterpret_cast<double*>(tail + 4)[0] = df1;
+  reinterpret_cast<double*>(tail + 4)[1] = df2;
+}
+
+// results -> caller's DEVICE buffers: every requested array in one launch (entry = blockIdx.y; src == nullptr: zeros)
+constexpr int EMIT_MAX = 16;
+struct EmitTab {
+  void* dst[EMIT_MAX];
+  const void* src[EMIT_MAX];
+  long long bytes[EMIT_MAX];
+};
+__global__ void __launch_bounds__(256) k_emit(EmitTab T) {
+  const int ent = blockIdx.y;
+  char* dst = static_cast<char*>(T.dst[ent]);
+  const char* src = static_cast<const char*>(T.src[ent]);
+  const long long bytes = T.bytes[ent];
+  const long long stride = (long long)gridDim.x * blockDim.x, t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool vec = ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15) == 0;
+  long long done = 0;
+  if (vec) {
+    const long long nv = bytes >> 4;
+    for (long long i = t0; i < nv; i += stride)
+      reinterpret_cast<uint4*>(dst)[i] = src ? reinterpret_cast<const uint4*>(src)[i] : make_uint4(0, 0, 0, 0);
+    done = nv << 4;
+  }
+  for (long long i = done + t0; i < bytes; i += stride) dst[i] = src ? src[i] : 0;
 }
 
 __global__ void k_fill_f64(double* __restrict__ x, int64_t n, double v) {
