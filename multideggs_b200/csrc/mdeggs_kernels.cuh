@@ -535,23 +535,34 @@ __global__ void __launch_bounds__(256, 4) k_fit_stream(const double* __restrict_
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t e = e_lo + warp0; e < e_hi; e += nwarps) {
+    // No classification here (self-loops, non-finite rows): k_finish does it and never reads their moments, so the
+    // row loads depend on nothing but the two node ids.
     const int a = ea[e], b = eb[e];
-    if (a == b || bad[a] || bad[b]) continue;  // k_finish classifies these edges; their moments are not read
     const double2* __restrict__ pa = reinterpret_cast<const double2*>(D + (size_t)a * L.npad);
     const double2* __restrict__ pb = reinterpret_cast<const double2*>(D + (size_t)b * L.npad);
-    double mine = 0.0;
+    double ma[K], mb[K], acc[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-      const double ma = mean[(size_t)a * K + k], mb = mean[(size_t)b * K + k];
+      ma[k] = mean[(size_t)a * K + k];
+      mb[k] = mean[(size_t)b * K + k];
+    }
+    // all K segments are streamed back to back; the K warp reductions come after the last load has been issued
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
       const int beg = L.off[k] >> 1, end = L.off[k + 1] >> 1;
       double acc0 = 0.0, acc1 = 0.0;
 #pragma unroll 4
       for (int i = beg + lane; i < end; i += 32) {
-        double2 x = __ldg(pa + i), y = __ldg(pb + i);
-        acc0 = fma(x.x - ma, y.x - mb, acc0);
-        acc1 = fma(x.y - ma, y.y - mb, acc1);
+        const double2 x = __ldg(pa + i), y = __ldg(pb + i);
+        acc0 = fma(x.x - ma[k], y.x - mb[k], acc0);
+        acc1 = fma(x.y - ma[k], y.y - mb[k], acc1);
       }
-      double tot = warp_sum(acc0 + acc1);
+      acc[k] = acc0 + acc1;
+    }
+    double mine = 0.0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const double tot = warp_sum(acc[k]);
       if (lane == k) mine = tot;
     }
     if (lane < K) sxy[(size_t)e * K + lane] = mine;

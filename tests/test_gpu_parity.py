@@ -5,7 +5,7 @@ import pytest
 
 import multideggs_b200 as md
 from multideggs_b200 import _abi, host, synth
-from helpers import ALL_FIELDS, assert_parity
+from helpers import ALL_FIELDS, assert_parity, rel_close
 
 pytestmark = pytest.mark.gpu
 
@@ -475,3 +475,87 @@ def test_bucket_order_oversize_buckets(oracle):
     orc = oracle.run_omic(prob, want)
     assert np.array_equal(got["sig_count"], orc["sig_count"])
     eng.close()
+
+
+# ---- BASELINE.json's full sizes -------------------------------------------------------------------------------
+def _bh_properties(res, padj_code=_abi.PADJ_BH):
+    """Size-independent invariants of one result: counts agree with the rows, BH is monotone in p inside a category."""
+    best = int(res["best"][0])
+    assert best >= 1
+    cat, padj, p = res["cat_best"], res["padj_best"], res["p_edge"]
+    tested = cat != 0
+    assert int(tested.sum()) == int(res["tot_edges"][best - 1])
+    assert int(np.sum(padj[tested] < 0.05)) == int(res["sig_count"][best - 1])
+    assert np.all(np.isnan(padj[~tested]))
+    assert np.all((padj[tested] >= p[tested]) | np.isnan(p[tested]))  # an adjusted p never drops below the raw p
+    assert np.nanmax(padj[tested]) <= 1.0
+    for c in np.unique(cat[tested]):
+        m = (cat == c) & ~np.isnan(p)
+        o = np.argsort(p[m], kind="stable")
+        assert np.all(np.diff(padj[m][o]) >= 0), "BH values must be non-decreasing in p inside a segment"
+
+
+def test_cfg3_full_size_vs_oracle(engine, oracle):
+    """Config 3 at BASELINE.json's size (20,000 x 1,000, K = 3, 53,035 edges): whole-result parity with the oracle
+    (the oracle's unique-edge mode needs a couple of seconds for it) plus the size-independent invariants."""
+    wl = synth.cfg3()
+    prob = wl.problem()
+    want = ("cutoff", "median", "p_edge", "stat", "status", "tot_edges", "sig_count", "fail_count", "best",
+            "cat_best", "padj_best")
+    gpu = engine.run_omic(prob, want)
+    ref = oracle.run_omic(prob, want)
+    assert_parity(gpu, ref, prob, what="cfg3-full: ")
+    _bh_properties(gpu)
+    # edge-permutation invariance: per-edge results follow the permutation bit for bit, the counts do not move
+    rng = np.random.default_rng(3)
+    perm = rng.permutation(prob.from_idx.shape[0])
+    prob2 = _abi.Problem(assay=prob.assay, from_idx=prob.from_idx[perm].copy(), to_idx=prob.to_idx[perm].copy(),
+                         group=prob.group, K=prob.K, pct=prob.pct, method=prob.method, padj=prob.padj)
+    gpu2 = engine.run_omic(prob2, want)
+    for k in ("p_edge", "stat", "status", "cat_best", "padj_best"):
+        assert np.array_equal(gpu2[k], gpu[k][perm], equal_nan=True), k
+    for k in ("cutoff", "tot_edges", "sig_count", "best"):
+        assert np.array_equal(gpu2[k], gpu[k]), k
+
+
+def test_cfg5_full_size_sampled_oracle_and_properties(engine, oracle):
+    """Config 5 at BASELINE.json's size (4,000 x 2,000, all 7,998,000 pairs): the oracle re-fits a random sample of
+    the edges (per-edge statistics depend on the two rows only), the rest is covered by invariants and by the
+    streaming and dense-tile fit paths agreeing with each other on every edge."""
+    wl = synth.cfg5()
+    prob = wl.problem()
+    E = prob.from_idx.shape[0]
+    assert E == 7_998_000
+    want = ("p_edge", "stat", "status", "tot_edges", "sig_count", "best", "cat_best", "padj_best", "cutoff")
+    gpu = engine.run_omic(prob, want)
+    assert engine.stats()["fit_path"] & 0xff == 1      # dense tile path chosen for an all-pairs network
+    _bh_properties(gpu)
+    rng = np.random.default_rng(11)
+    pick = np.sort(rng.choice(E, size=4000, replace=False))
+    sub = _abi.Problem(assay=prob.assay, from_idx=prob.from_idx[pick].copy(), to_idx=prob.to_idx[pick].copy(),
+                       group=prob.group, K=prob.K, pct=prob.pct, method=prob.method, padj=prob.padj)
+    ref = oracle.run_omic(sub, ("p_edge", "stat", "status"))
+    assert np.array_equal(gpu["status"][pick], ref["status"])
+    assert rel_close(gpu["stat"][pick], ref["stat"], 1e-9).all()
+    assert rel_close(gpu["p_edge"][pick], ref["p_edge"], 1e-9, 4.5e-16).all()
+    # the cut-offs are order statistics of the whole 4,000 x 2,000 matrix: every row is a node here
+    flat = np.sort(prob.assay, axis=None)
+    N = flat.shape[0]
+    for pc, got in zip(prob.pct, gpu["cutoff"]):
+        idx = 1.0 + (N - 1) * pc
+        lo_i = int(np.floor(idx))
+        q = flat[lo_i - 1]
+        hi_v = flat[int(np.ceil(idx)) - 1]
+        if idx > lo_i and hi_v != q:
+            h = idx - lo_i
+            q = (1.0 - h) * q + h * hi_v
+        assert got == q
+    # streaming path on the same problem: same edges tested, statistics within 1e-9 (different summation order)
+    engine.set_option("fit_path", 0)
+    try:
+        gpu_s = engine.run_omic(prob, ("stat", "status", "tot_edges", "best"))
+    finally:
+        engine.set_option("fit_path", -1)
+    assert np.array_equal(gpu_s["status"], gpu["status"])
+    assert np.array_equal(gpu_s["tot_edges"], gpu["tot_edges"])
+    assert rel_close(gpu_s["stat"], gpu["stat"], 1e-9, 1e-10).all()
