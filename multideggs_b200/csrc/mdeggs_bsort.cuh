@@ -29,11 +29,11 @@ constexpr int BS_NLOG = 2026;       // buckets 0..2025: (biased exponent, top ma
 constexpr int BS_CAP = 512;         // run granularity; shared memory holds 2 * BS_CAP elements
 constexpr int BS_SORT_THREADS = 256;
 constexpr int BS_WARP_MAX = 32;     // largest bucket whose elements are ranked by counting
-constexpr int64_t BS_MAX_E = 1 << 22;  // beyond this the CUB radix sort is used
+constexpr int64_t BS_MAX_E = 1 << 26;  // beyond this the CUB radix sort is used
 
 __host__ __device__ __forceinline__ int bs_nlin(int64_t E) {
   int64_t v = E / 16;
-  v = v < 1024 ? 1024 : (v > 32768 ? 32768 : v);
+  v = v < 1024 ? 1024 : (v > (1 << 20) ? (1 << 20) : v);
   return (int)v;
 }
 // total buckets: BS_NLOG + nlin + 1 (the last one holds NaN)
@@ -126,17 +126,6 @@ __global__ void __launch_bounds__(256) k_bsort_count(BsArgs B, const double* __r
   bs_count(B, live, e, live ? p_edge[e] : 0.0);
 }
 
-// bucket offsets for large bucket counts (otherwise every scatter CTA scans the counts itself)
-__global__ void __launch_bounds__(1024) k_bsort_scan(BsArgs B) {
-  __shared__ int s_warp_tot[32];
-  const int NB = BS_NLOG + B.nlin + 1;
-  const int total = bs_scan_counts(B.count, NB, B.base, s_warp_tot);
-  if (threadIdx.x == 0) {
-    B.base[NB] = total;
-    *B.n_valid = (unsigned long long)(total - __ldcg(B.count + NB - 1));
-  }
-}
-
 // ------------------------------------------------------------------------------------------------
 // finish, one thread per edge: closed-form statistic from the cross moments, then the tail probability
 //   src 0: moments from k_fit_stream (sxy[e][K]);  src 1: moments from the dense matrices S[k][i][j];
@@ -202,6 +191,10 @@ __global__ void __launch_bounds__(256) k_bsort_scatter(BsArgs B, int scan_in_cta
   __shared__ int s_warp_tot[32];
   if (*err) return;
   const int* base = B.base;
+  if (!scan_in_cta && blockIdx.x == 0 && threadIdx.x == 0) {  // offsets came from a device-wide scan of count[0..NB]
+    const int NB = BS_NLOG + B.nlin + 1;
+    *B.n_valid = (unsigned long long)(B.base[NB] - __ldcg(B.count + NB - 1));
+  }
   if (scan_in_cta) {
     const int NB = BS_NLOG + B.nlin + 1;
     const int total = bs_scan_counts(B.count, NB, s_base, s_warp_tot);

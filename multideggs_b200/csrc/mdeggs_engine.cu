@@ -586,7 +586,7 @@ int run_shard_main(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
   EVREC(s.ev[EV_GATHER], s.s_main);
   EVREC(s.ev[EV_Q0], s.s_main);
   if (do_q) {
-    LAUNCH(k_qs_scan, 1, 1024, 0, s.s_main, d_st, s.rsel_hist.as<unsigned int>(), d_nn, n, s.pct.as<double>(), P,
+    LAUNCH(k_qs_scan, 1, QS_SCAN_THREADS, 0, s.s_main, d_st, s.rsel_hist.as<unsigned int>(), d_nn, n, s.pct.as<double>(), P,
            cand_cap);
     LAUNCH(k_qs_compact, 148 * 4, 256, (size_t)QS_FILTER_CELLS / 8, s.s_main, s.D.as<double>(), s.src_of_pos.as<int32_t>(), L.npad, d_nn, d_st,
            s.rsel_cand.as<unsigned long long>());
@@ -849,7 +849,14 @@ int run_shard_back(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
       }
       const int NB = bs_nbuckets(E);
       const int scan_in_cta = NB <= BS_SCAN_SMEM;
-      if (!scan_in_cta) LAUNCH(k_bsort_scan, 1, 1024, 0, s.s_main, B);
+      if (!scan_in_cta) {  // many buckets: device-wide scan of count[0..NB] (count[NB] == 0, so base[NB] = total)
+        size_t tb = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tb, B.count, B.base, NB + 1, s.s_main);
+        CU(s.cub_tmp.ensure(tb));
+        CU(cub::DeviceScan::ExclusiveSum(s.cub_tmp.p, tb, B.count, B.base, NB + 1, s.s_main));
+        ctx->launches += 2;
+        trace_mark(ctx, "cub::ExclusiveSum", s.s_main);
+      }
       LAUNCH(k_bsort_scatter, blocks_for(E, 256), 256, scan_in_cta ? (size_t)bs_padded(NB) * 4 : 0, s.s_main, B, scan_in_cta,
              s.p_edge.as<double>(), s.sortk.as<unsigned long long>(), s.idx.as<int32_t>(),
              s.scal.as<int32_t>() + 2 * SC_ERR);
@@ -896,22 +903,29 @@ int run_shard_back(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
       d_cat = s.cat.as<int8_t>();
     }
   }
-  if (n_nodes > 0 && P > 0) {
-    if (E > 0)
-      LAUNCH(k_percolate, blocks_for(E, 256), 256, (size_t)3 * P * sizeof(unsigned), s.s_main, s.ea.as<int32_t>(),
-             s.eb.as<int32_t>(), s.status.as<int32_t>(), s.p_edge.as<double>(),
-             s.act.as<uint8_t>(), act_stride, E, P, c_tot, c_fail, c_raw, d_cat, s.scal.as<int32_t>() + 2 * SC_ERR);
-  }
-  EVREC(s.ev[EV_PERC], s.s_main);
-  // ---- K8 ----
-  double* d_padj = nullptr;
-  const bool want_padj_best = out->padj_best && do_adjust;
-  // adjusted values of every percentile are kept when they fit a modest scratch matrix, so the best row is a copy
+  // adjusted values of every percentile are kept when they fit a modest scratch matrix (the best row is then a copy);
   // multi-GPU: the (percentile, category) segments are independent, so rank r adjusts percentiles r, r+world, ...
   // and only the per-percentile significant counts are all-reduced; a full P x E p.adj output keeps it replicated
+  double* d_padj = nullptr;
+  const bool want_padj_best = out->padj_best && do_adjust;
   const bool shard_p = do_adjust && s.world > 1 && !out->padj;
   const bool keep_all_padj = do_adjust && !shard_p &&
                              (out->padj || (want_padj_best && (size_t)P * (size_t)E * 8 <= ((size_t)256 << 20)));
+  if (keep_all_padj) {
+    if (out->padj && dev_out && emit) d_padj = out->padj;
+    else {
+      CU(s.padj.ensure((size_t)P * E * 8));
+      d_padj = s.padj.as<double>();
+    }
+  }
+  if (n_nodes > 0 && P > 0) {
+    if (E > 0)  // (also writes NaN into the p.adj rows of the edges that are not tested at a percentile)
+      LAUNCH(k_percolate, blocks_for(E, 256), 256, (size_t)3 * P * sizeof(unsigned), s.s_main, s.ea.as<int32_t>(),
+             s.eb.as<int32_t>(), s.status.as<int32_t>(), s.p_edge.as<double>(), s.act.as<uint8_t>(), act_stride, E, P,
+             c_tot, c_fail, c_raw, d_cat, d_padj, s.scal.as<int32_t>() + 2 * SC_ERR);
+  }
+  EVREC(s.ev[EV_PERC], s.s_main);
+  // ---- K8 ----
   if (do_adjust) {
     const int ntiles = (int)((E + BH_TILE - 1) / BH_TILE);
     const size_t nseg = (size_t)P * K;
@@ -920,16 +934,6 @@ int run_shard_back(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
     CU(s.tile_min.ensure(nseg * ntiles * 8));
     CU(s.tile_carry.ensure(nseg * ntiles * 8));
     CU(s.seg_n.ensure(nseg * 8));
-    if (keep_all_padj) {
-      if (out->padj && dev_out && emit) d_padj = out->padj;
-      else {
-        CU(s.padj.ensure((size_t)P * E * 8));
-        d_padj = s.padj.as<double>();
-      }
-      int64_t tot = (int64_t)P * E;
-      LAUNCH(k_fill_f64, (unsigned)(blocks_for(tot, 256) < 148u * 16 ? blocks_for(tot, 256) : 148u * 16), 256, 0,
-             s.s_main, d_padj, tot, nan(""));
-    }
     const int p0 = shard_p ? s.rank : 0, stride = shard_p ? s.world : 1;
     const int n_loc = p0 < P ? (P - p0 + stride - 1) / stride : 0;
     int rc = run_adjust(ctx, s, in, n_loc * K, p0, stride, nullptr, c_sig, d_padj, E, act_stride);

@@ -602,7 +602,8 @@ __global__ void __launch_bounds__(256) k_percolate(const int32_t* __restrict__ e
                                                    unsigned long long* __restrict__ tot,
                                                    unsigned long long* __restrict__ fail,
                                                    unsigned long long* __restrict__ sig_raw,
-                                                   int8_t* __restrict__ cat_out, const int32_t* __restrict__ err) {
+                                                   int8_t* __restrict__ cat_out, double* __restrict__ padj_nan,
+                                                   const int32_t* __restrict__ err) {
   extern __shared__ unsigned int s_cnt[];  // [3][P]
   if (*err) return;
   for (int i = threadIdx.x; i < 3 * P; i += blockDim.x) s_cnt[i] = 0;
@@ -623,6 +624,7 @@ __global__ void __launch_bounds__(256) k_percolate(const int32_t* __restrict__ e
     int c = 0;
     if (live) c = edge_category(act[(size_t)p * act_stride + a], act[(size_t)p * act_stride + b]);
     if (cat_out && live) cat_out[(size_t)p * E + e] = (int8_t)c;
+    if (padj_nan && live && (c == 0 || isnan(pv))) padj_nan[(size_t)p * E + e] = nan("");  // K8 writes the rest
     unsigned m_t = __ballot_sync(0xffffffffu, c != 0);
     unsigned m_f = __ballot_sync(0xffffffffu, c != 0 && hard);
     unsigned m_s = __ballot_sync(0xffffffffu, c != 0 && pv < 0.05);

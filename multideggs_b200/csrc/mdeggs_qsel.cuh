@@ -41,6 +41,7 @@ constexpr int QS_FIN_CAP = 16384;    // keys a finish CTA keeps in shared memory
 constexpr unsigned int QS_SLOT_MAX = 1u << 20;  // slots with more values are not compacted ("fat": tie groups)
 constexpr unsigned int QS_CAND_MAX = 8u << 20;  // candidate buffer, keys
 constexpr int QS_FIN_THREADS = 512;
+constexpr int QS_SCAN_THREADS = 256;  // >= QS_MAX_T
 constexpr int QS_STAGE = 2048;       // per-CTA staging entries of the compaction pass
 
 constexpr int QS_TAB = 4096;         // uniform value cells of the knot look-up table
@@ -332,7 +333,7 @@ __global__ void __launch_bounds__(256) k_gather_rowmajor(const double* __restric
 }
 
 // ---- S2 ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) k_qs_scan(QsState* __restrict__ st, unsigned int* __restrict__ hist,
+__global__ void __launch_bounds__(QS_SCAN_THREADS) k_qs_scan(QsState* __restrict__ st, unsigned int* __restrict__ hist,
                                                   const int32_t* __restrict__ n_nodes_p, int n,
                                                   const double* __restrict__ pct, int P, unsigned int cand_capacity) {
   __shared__ unsigned long long cum[QS_BINS + 1];
@@ -340,7 +341,7 @@ __global__ void __launch_bounds__(1024) k_qs_scan(QsState* __restrict__ st, unsi
   __shared__ int s_tbin[QS_MAX_T], s_first[QS_MAX_T];
   __shared__ unsigned int s_slot_cnt[QS_MAX_T];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  constexpr int PER = QS_BINS / 1024;
+  constexpr int PER = QS_BINS / QS_SCAN_THREADS;
   unsigned long long v[PER], mine = 0;
 #pragma unroll
   for (int j = 0; j < PER; ++j) {
@@ -364,7 +365,7 @@ __global__ void __launch_bounds__(1024) k_qs_scan(QsState* __restrict__ st, unsi
     cum[tid * PER + j] = run;
     run += v[j];
   }
-  if (tid == 1023) cum[QS_BINS] = run;
+  if (tid == QS_SCAN_THREADS - 1) cum[QS_BINS] = run;
   __syncthreads();
   const long long N = (long long)cum[QS_BINS];  // == n_nodes * n - nan_count
   const int T = 2 * P;
@@ -434,7 +435,7 @@ __global__ void __launch_bounds__(1024) k_qs_scan(QsState* __restrict__ st, unsi
   }
   // compaction pre-filter bitmap (cum[] is no longer needed: its storage is reused)
   unsigned int* bits = reinterpret_cast<unsigned int*>(cum);
-  for (int i = tid; i < QS_FILTER_CELLS / 32; i += 1024) bits[i] = 0u;
+  for (int i = tid; i < QS_FILTER_CELLS / 32; i += QS_SCAN_THREADS) bits[i] = 0u;
   __syncthreads();
   if (tid < T && s_first[tid]) {
     const int b = s_tbin[tid], c = b / QS_SUB, sub = b % QS_SUB;
@@ -457,7 +458,7 @@ __global__ void __launch_bounds__(1024) k_qs_scan(QsState* __restrict__ st, unsi
     for (int i = i0; i <= i1; ++i) atomicOr(&bits[i >> 5], 1u << (i & 31));
   }
   __syncthreads();
-  for (int i = tid; i < QS_FILTER_CELLS / 32; i += 1024) st->cand_bits[i] = bits[i];
+  for (int i = tid; i < QS_FILTER_CELLS / 32; i += QS_SCAN_THREADS) st->cand_bits[i] = bits[i];
 }
 
 // ---- S3 ------------------------------------------------------------------------------------------
