@@ -314,11 +314,26 @@ def run_cuda(args) -> None:
     fit_ms = stage["ms_fit"]
     fit_bytes = E * (16 * n + 16)
     achieved = fit_bytes / (fit_ms * 1e-3) / 1e9 if fit_ms > 0 else None
+    # DRAM traffic of one k_fit_stream launch from the committed ncu --set full capture of this workload
+    # (profiles/r01k_ncu_full_hot_kernels.csv: dram__bytes_read.sum 68.53 MB + dram__bytes_write.sum 4.68 MB): the
+    # gene-major matrix is L2-resident, so DRAM sees it once while the kernel streams 849 MB of algorithmic bytes.
+    traffic = 73_209_856 if name == "cfg3" else None
+    # whole-step algorithmic bytes (SURVEY section 8 d): gather 2*8*G_nodes*n + quantiles 4*8*G_nodes*n + pair fits
+    # + adjust 3*8*sum_p tot_edges[p]
+    g_nodes = int(st["n_nodes"])
+    pipe_bytes = 6 * 8 * g_nodes * n + fit_bytes + 24 * int(keep[5]["tot_edges"].cpu().numpy().sum())
+    step_s = ms / args.steps * 1e-3
     roofline = {"bound": "hbm", "kernel": "k_fit_stream", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": (achieved / peaks["hbm_gbs"]) if achieved else None, "traffic": None,
+                "frac": (achieved / peaks["hbm_gbs"]) if achieved else None, "traffic": traffic,
+                "traffic_source": "profiles/r01k_ncu_full_hot_kernels.csv (ncu --set full, dram read + write per launch)",
                 "peak_source": peaks["source"], "algorithmic_bytes_per_launch": fit_bytes,
                 "kernel_ms": fit_ms, "stage_ms": stage,
-                "stage_note": "stage/kernel times from separate eagerly launched steps (the graph has no stage events)"}
+                "stage_note": "stage/kernel times from separate eagerly launched steps (the graph has no stage events)",
+                "note": "frac > 1: the 67 MB gene-major matrix stays in the 126 MB L2, the kernel is bound by L2 "
+                        "bandwidth/latency, not by HBM (see traffic)",
+                "whole_step": {"algorithmic_bytes": pipe_bytes, "achieved": pipe_bytes / step_s / 1e9,
+                               "frac": pipe_bytes / step_s / 1e9 / peaks["hbm_gbs"], "unit": "GB/s",
+                               "model": "SURVEY 8d whole-pipeline bytes / measured step time, against the HBM peak"}}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
