@@ -301,42 +301,50 @@ __global__ void __launch_bounds__(THREADS) k_gene_stats(double* __restrict__ D, 
 // Register-resident variant of K2 for segments of up to 32*ITEMS samples: one warp per (gene, category), the
 // segment lives in registers as sortable keys, so every counting pass of the selection is ITEMS compares per lane
 // with no shared-memory traffic.  `bad` must be zero-initialised by the caller.
+// Exact k-th smallest (0-based) of the keys a warp holds in registers (ITEMS per lane; unused slots carry ~0, which
+// sorts above every valid key).  Bisection in KEY space with arbitrary pivots: the interval [lo, hi) always holds the
+// answer, cnt_lo / cnt_hi = number of keys below lo / hi.  It starts from the caller's guess bracket [g_lo, g_hi]
+// (e.g. mean -+ 0.3 sd for a median: one counting pass usually leaves a few dozen candidates), halves the key
+// interval until <= 32 keys remain, and ranks those with 32 shuffles.  At most ~64 counting passes whatever the data.
+template <int ITEMS>
+__device__ __forceinline__ int warp_count_below(const unsigned long long (&keys)[ITEMS], unsigned long long pivot) {
+  int c = 0;
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j) c += (keys[j] < pivot);
+  return __reduce_add_sync(0xffffffffu, c);
+}
+
 template <int ITEMS>
 __device__ __forceinline__ unsigned long long warp_select_reg(const unsigned long long (&keys)[ITEMS], int kth,
                                                               unsigned long long kmin, unsigned long long kmax,
-                                                              int n_valid, unsigned long long* scratch32, int lane) {
+                                                              int n_valid, unsigned long long* scratch32, int lane,
+                                                              unsigned long long g_lo = 0ull,
+                                                              unsigned long long g_hi = 0ull) {
   if (kmin == kmax) return kmin;
-  const int top = 63 - __clzll((long long)(kmin ^ kmax));
-  unsigned long long prefix = (top == 63) ? 0ull : (kmin >> (top + 1)) << (top + 1);
+  unsigned long long lo = kmin, hi = kmax + 1ull;  // kmax is a valid key, hence < ~0
   int cnt_lo = 0, cnt_hi = n_valid;
-  int bit = top;
-  for (; bit >= 0 && cnt_hi - cnt_lo > 32; --bit) {
-    const unsigned long long cand = prefix | (1ull << bit);
-    int c = 0;
-    if (bit >= 32) {  // low word of cand is zero: key < cand  <=>  hi(key) < hi(cand), one 32-bit compare
-      const unsigned int ch = (unsigned int)(cand >> 32);
-#pragma unroll
-      for (int j = 0; j < ITEMS; ++j) c += ((unsigned int)(keys[j] >> 32) < ch);
-    } else {
-#pragma unroll
-      for (int j = 0; j < ITEMS; ++j) c += (keys[j] < cand);
-    }
-    c = __reduce_add_sync(0xffffffffu, c);
+  auto narrow = [&](unsigned long long pivot) {
+    if (pivot <= lo || pivot >= hi) return;
+    const int c = warp_count_below<ITEMS>(keys, pivot);
     if (c <= kth) {
-      prefix = cand;
+      lo = pivot;
       cnt_lo = c;
     } else {
+      hi = pivot;
       cnt_hi = c;
     }
+  };
+  if (g_hi > g_lo) {
+    narrow(g_lo);
+    narrow(g_hi);
   }
-  if (bit < 0) return prefix;
-  const unsigned long long span = (bit == 63) ? ~0ull : ((1ull << (bit + 1)) - 1ull);
-  const unsigned long long hi_incl = prefix | span;
+  while (cnt_hi - cnt_lo > 32 && hi - lo > 1ull) narrow(lo + ((hi - lo) >> 1));
+  if (cnt_hi - cnt_lo > 32) return lo;  // hi == lo + 1: more than 32 keys equal to lo
   int base = 0;
 #pragma unroll
   for (int j = 0; j < ITEMS; ++j) {
     const unsigned long long k = keys[j];
-    const bool in = k >= prefix && k <= hi_incl && k != ~0ull;
+    const bool in = k >= lo && k < hi;
     const unsigned mask = __ballot_sync(0xffffffffu, in);
     if (in) scratch32[base + __popc(mask & ((1u << lane) - 1u))] = k;
     base += __popc(mask);
@@ -418,10 +426,18 @@ __global__ void __launch_bounds__(256) k_gene_stats_reg(double* __restrict__ D, 
   double median = nan("");
   if (nn > 0) {
     const unsigned long long kmin = dkey(vmin), kmax = dkey(vmax);
+    // guess bracket for the median: mean -+ 0.3 sd (holds it for anything close to symmetric; otherwise the bisection
+    // simply continues from whichever side the counts point to)
+    unsigned long long g_lo = 0ull, g_hi = 0ull;
+    if (m > 2 && d2 > 0.0 && isfinite(d2)) {
+      const double w = 0.3 * sqrt(d2 / (double)(m - 1));
+      g_lo = dkey(mu - w);
+      g_hi = dkey(mu + w);
+    }
     if (nn & 1) {
-      median = dkey_inv(warp_select_reg<ITEMS>(keys, nn / 2, kmin, kmax, nn, s_cand[wib], lane));
+      median = dkey_inv(warp_select_reg<ITEMS>(keys, nn / 2, kmin, kmax, nn, s_cand[wib], lane, g_lo, g_hi));
     } else {
-      unsigned long long k1 = warp_select_reg<ITEMS>(keys, nn / 2 - 1, kmin, kmax, nn, s_cand[wib], lane);
+      unsigned long long k1 = warp_select_reg<ITEMS>(keys, nn / 2 - 1, kmin, kmax, nn, s_cand[wib], lane, g_lo, g_hi);
       int c_le = 0;
       unsigned long long nxt = ~0ull;
 #pragma unroll
