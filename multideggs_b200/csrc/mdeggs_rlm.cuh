@@ -363,10 +363,9 @@ __global__ void __launch_bounds__(256) k_fit_rlm_reg(const double* __restrict__ 
       icpt[k] = mb[k] - slope[k] * ma[k];
     }
     unsigned long long keys[ITEMS];
-    unsigned long long kmin, kmax;
+    // every valid |r| key lies in [0, bits(+inf)]: the selection needs no min / max pass, it starts from its guess bracket
+    const unsigned long long kmin = 0ull, kmax = 0x7ff0000000000000ull;
     auto residual_keys = [&]() {  // |b - icpt_c - slope_c a| as order-preserving bit patterns; padding -> ~0
-      kmin = ~0ull;
-      kmax = 0ull;
 #pragma unroll
       for (int j = 0; j < ITEMS; ++j) {
         unsigned long long k = ~0ull;
@@ -375,21 +374,21 @@ __global__ void __launch_bounds__(256) k_fit_rlm_reg(const double* __restrict__ 
           const int c = cmask >> j & 1;
           const double r = sb[pos] - icpt[c] - slope[c] * sa[pos];
           k = (unsigned long long)__double_as_longlong(fabs(r));
-          kmin = k < kmin ? k : kmin;
-          kmax = k > kmax ? k : kmax;
         }
         keys[j] = k;
       }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        unsigned long long x = __shfl_xor_sync(0xffffffffu, kmin, o), y = __shfl_xor_sync(0xffffffffu, kmax, o);
-        kmin = x < kmin ? x : kmin;
-        kmax = y > kmax ? y : kmax;
-      }
     };
-    auto median_abs = [&]() -> double {
-      if (n & 1) return __longlong_as_double((long long)warp_select_reg<ITEMS>(keys, n / 2, kmin, kmax, n, s_cand[wib], lane));
-      unsigned long long k1 = warp_select_reg<ITEMS>(keys, n / 2 - 1, kmin, kmax, n, s_cand[wib], lane);
+    // `guess` > 0: expected median of |r| (previous iteration's, or 0.6745 sd of the residuals at the start); the
+    // selection starts from the bracket guess * (1 -+ rel)
+    auto median_abs = [&](double guess, double rel) -> double {
+      unsigned long long g_lo = 0ull, g_hi = 0ull;
+      if (guess > 0.0 && isfinite(guess)) {
+        g_lo = (unsigned long long)__double_as_longlong(guess * (1.0 - rel));
+        g_hi = (unsigned long long)__double_as_longlong(guess * (1.0 + rel));
+      }
+      if (n & 1)
+        return __longlong_as_double((long long)warp_select_reg<ITEMS>(keys, n / 2, kmin, kmax, n, s_cand[wib], lane, g_lo, g_hi));
+      unsigned long long k1 = warp_select_reg<ITEMS>(keys, n / 2 - 1, kmin, kmax, n, s_cand[wib], lane, g_lo, g_hi);
       int c_le = 0;
       unsigned long long nxt = ~0ull;
 #pragma unroll
@@ -406,12 +405,27 @@ __global__ void __launch_bounds__(256) k_fit_rlm_reg(const double* __restrict__ 
       unsigned long long k2 = (c_le > n / 2) ? k1 : nxt;
       return __ddiv_rn(__dadd_rn(__longlong_as_double((long long)k1), __longlong_as_double((long long)k2)), 2.0);
     };
+    double med_prev = 0.0;
     double scale = 0.0;
     bool done = false, zero_scale = false;
     int it = 0;
     for (it = 1; it <= 20; ++it) {
       residual_keys();
-      scale = median_abs() / 0.6745;
+      {
+        double guess = med_prev, rel = 0.1;
+        if (it == 1) {  // residual sd under the least-squares start (closed form) -> MAD of a normal sample
+          double ss = 0.0;
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const double off = mb[k] - icpt[k] - slope[k] * ma[k];
+            ss += syb[k] - 2.0 * slope[k] * sxy[k] + slope[k] * slope[k] * sxa[k] + nk[k] * off * off;
+          }
+          guess = 0.6745 * sqrt(fmax(ss, 0.0) / (double)n);
+          rel = 0.25;
+        }
+        med_prev = median_abs(guess, rel);
+      }
+      scale = med_prev / 0.6745;
       if (scale == 0.0) {
         zero_scale = true;
         done = true;
@@ -425,13 +439,15 @@ __global__ void __launch_bounds__(256) k_fit_rlm_reg(const double* __restrict__ 
         old_ss += syb[k] - 2.0 * slope[k] * sxy[k] + slope[k] * slope[k] * sxa[k] + nk[k] * off * off;
       }
       double acc[2][5] = {{0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}};
+      const double ks = kh * scale;
 #pragma unroll
       for (int j = 0; j < ITEMS; ++j) {
         if (!(vmask >> j & 1)) continue;
         const int pos = lane + 32 * j;
         const int c = cmask >> j & 1;
-        const double u = __longlong_as_double((long long)keys[j]) / scale;  // |r| / s
-        const double w = (u <= kh) ? 1.0 : kh / u;                              // psi.huber weight pmin(1, k/|u|)
+        // psi.huber weight pmin(1, k / |r / s|) with ONE division per sample: k s / |r|
+        const double ar = __longlong_as_double((long long)keys[j]);
+        const double w = (ar <= ks) ? 1.0 : ks / ar;
         const double da = sa[pos] - ma[c], db = sb[pos] - mb[c];
         const double wda = w * da;
         if (c) {
