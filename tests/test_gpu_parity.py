@@ -559,3 +559,97 @@ def test_cfg5_full_size_sampled_oracle_and_properties(engine, oracle):
     assert np.array_equal(gpu_s["status"], gpu["status"])
     assert np.array_equal(gpu_s["tot_edges"], gpu["tot_edges"])
     assert rel_close(gpu_s["stat"], gpu["stat"], 1e-9, 1e-10).all()
+
+
+def _quantile_problem(values: np.ndarray, pct, seed=0, K=2):
+    """Every row is a network node (a ring of edges), so the cut-offs are order statistics of the whole matrix."""
+    G, n = values.shape
+    rng = np.random.default_rng(seed)
+    group = (np.arange(n) % K + 1).astype(np.int32)
+    rng.shuffle(group)
+    fr = np.arange(1, G + 1, dtype=np.int32)
+    to = np.roll(fr, -1)
+    return _abi.Problem(assay=np.asfortranarray(values), from_idx=fr, to_idx=to, group=group, K=K,
+                        pct=np.asarray(pct, dtype=np.float64), method=_abi.METHOD_LM, padj=_abi.PADJ_BH)
+
+
+@pytest.mark.parametrize("kind", ["lognormal_outliers", "counts", "few_values", "constant", "with_nan", "negative",
+                                  "two_genes", "wide_dynamic_range", "sorted_rows", "bimodal_gap"])
+def test_quantile_select_distributions(engine, oracle, kind):
+    """K3 is sample-adaptive: whatever the value distribution (heavy tails, integer counts with huge tie groups,
+    constants, NaN, gaps wider than the sample sees), every cut-off must stay bit-identical to the oracle's type-7
+    quantile of the whole node matrix, for interior and extreme percentiles alike."""
+    import zlib
+    rng = np.random.default_rng(zlib.crc32(kind.encode()))
+    G, n = 600, 96
+    if kind == "lognormal_outliers":
+        v = np.exp(rng.normal(0, 2.5, size=(G, n)))
+        v[rng.integers(0, G, 20), rng.integers(0, n, 20)] = 1e12
+    elif kind == "counts":
+        v = rng.negative_binomial(2, 0.3, size=(G, n)).astype(np.float64)      # integers, ~10 % zeros
+        v[: G // 2] = np.floor(np.log2(1.0 + v[: G // 2]) * 4) / 4
+    elif kind == "few_values":
+        v = rng.choice([0.0, 1.5, 1.5000000001, 7.25], size=(G, n), p=[0.6, 0.2, 0.1, 0.1])
+    elif kind == "constant":
+        v = np.full((G, n), 3.25)
+    elif kind == "with_nan":
+        v = rng.normal(5, 1, size=(G, n))
+        v[rng.random((G, n)) < 0.07] = np.nan
+    elif kind == "negative":
+        v = rng.normal(-3, 4, size=(G, n))
+        v[0, 0], v[1, 1] = -0.0, 0.0
+    elif kind == "two_genes":
+        G = 2
+        v = rng.normal(5, 1, size=(G, n))
+    elif kind == "wide_dynamic_range":
+        v = 10.0 ** rng.uniform(-200, 200, size=(G, n))
+    elif kind == "sorted_rows":
+        v = np.sort(rng.normal(5, 1, size=(G, n)), axis=0)     # the stratified sample sees a biased slice per row
+    else:  # bimodal_gap: two narrow modes, the targets fall on both sides of an empty stretch
+        v = np.where(rng.random((G, n)) < 0.5, rng.normal(1, 1e-6, size=(G, n)), rng.normal(1e6, 1e-3, size=(G, n)))
+    pct = [0.0, 0.001, 0.05, 0.35, 0.5, 0.6, 0.65, 0.9, 0.98, 0.999, 1.0]
+    prob = _quantile_problem(np.asarray(v, dtype=np.float64), pct)
+    want = ("cutoff", "median", "tot_edges", "best")
+    gpu = engine.run_omic(prob, want)
+    ref = oracle.run_omic(prob, want)
+    assert np.array_equal(gpu["cutoff"], ref["cutoff"], equal_nan=True), (kind, gpu["cutoff"], ref["cutoff"])
+    assert np.array_equal(gpu["median"], ref["median"], equal_nan=True), kind
+    assert np.array_equal(gpu["tot_edges"], ref["tot_edges"]), kind
+
+
+def test_quantile_select_large_matrix_with_ties(engine, oracle):
+    """A matrix large enough that tie groups exceed the shared-memory finish (fat slots answered by min == max) while
+    other targets take the regular candidate path; also with a tiny candidate buffer (everything fat -> slow path)."""
+    rng = np.random.default_rng(99)
+    G, n = 3000, 200
+    v = np.round(rng.normal(5, 1, size=(G, n)), 2)
+    v[v < 4.2] = 0.0
+    v[(v > 5.5) & (v < 5.6)] = 5.55
+    pct = [0.01, 0.1, 0.2, 0.25, 0.5, 0.7, 0.72, 0.74, 0.9, 0.99]
+    prob = _quantile_problem(v, pct)
+    ref = oracle.run_omic(prob, ("cutoff",))
+    gpu = engine.run_omic(prob, ("cutoff",))
+    assert np.array_equal(gpu["cutoff"], ref["cutoff"])
+    eng = md.Engine([0])
+    eng.set_option("rsel_cap", 64)
+    gpu2 = eng.run_omic(prob, ("cutoff",))
+    eng.close()
+    assert np.array_equal(gpu2["cutoff"], ref["cutoff"])
+
+
+@pytest.mark.parametrize("E", [1, 2, 33, 120_000])
+def test_bucket_order_edge_counts(oracle, E):
+    """K8 ordering at the extremes: one and two edges, and enough edges for the device-wide bucket scan."""
+    eng = md.Engine([0])
+    G = 20 if E < 100 else 600
+    prob = synth.random_problem(G, 40, E, 2, 500 + E)
+    want = ("p_edge", "padj", "sig_count", "tot_edges", "best")
+    got = eng.run_omic(prob, want)
+    eng.set_option("sort_path", 0)
+    ref_sort = eng.run_omic(prob, want)
+    eng.close()
+    for k in want:
+        assert np.array_equal(got[k], ref_sort[k], equal_nan=True), k
+    if E <= 33:
+        ref = oracle.run_omic(prob, want)
+        assert np.array_equal(got["sig_count"], ref["sig_count"]) and np.array_equal(got["best"], ref["best"])
