@@ -11,6 +11,8 @@ and produces the `mdeggs_problem` handed to the C ABI (include/mdeggs.h).  The c
 """
 from __future__ import annotations
 
+import functools
+
 import gzip
 import os
 import warnings
@@ -357,10 +359,12 @@ def p_adjust(p: np.ndarray, method: str) -> np.ndarray:
     return out
 
 
-def _smooth_spline_df3_last(x: np.ndarray, y: np.ndarray, df: float = 3.0) -> float:
-    """Fitted value at the last knot of the natural cubic smoothing spline whose smoother matrix has
-    trace `df` (Reinsch form).  Stand-in for stats::smooth.spline(lambda, pi0, df = 3) inside
-    qvalue::pi0est — numerically UNPINNED against R (R matches df only to its own optimiser tolerance)."""
+@functools.lru_cache(maxsize=8)
+def _smoother_last_row(x_bytes: bytes, df: float) -> np.ndarray:
+    """Last row of the smoother matrix of the natural cubic smoothing spline on knots `x` whose trace is `df`
+    (Reinsch form).  For fixed knots, unit weights and a target df the penalty parameter does not depend on the
+    data, so the fitted value at the last knot is one dot product with this row."""
+    x = np.frombuffer(x_bytes, dtype=np.float64)
     n = x.shape[0]
     h = np.diff(x)
     Q = np.zeros((n, n - 2))
@@ -375,20 +379,23 @@ def _smooth_spline_df3_last(x: np.ndarray, y: np.ndarray, df: float = 3.0) -> fl
     Kmat = Q @ np.linalg.solve(R, Q.T)
     ev, U = np.linalg.eigh(Kmat)
     ev = np.clip(ev, 0.0, None)
-
-    def trace(lam):
-        return np.sum(1.0 / (1.0 + lam * ev))
-
     lo, hi = 1e-12, 1e12
     for _ in range(200):
         mid = np.sqrt(lo * hi)
-        if trace(mid) > df:
+        if np.sum(1.0 / (1.0 + mid * ev)) > df:
             lo = mid
         else:
             hi = mid
     lam = np.sqrt(lo * hi)
-    fit = U @ ((U.T @ y) / (1.0 + lam * ev))
-    return float(fit[-1])
+    return U[-1] @ (U / (1.0 + lam * ev)).T
+
+
+def _smooth_spline_df3_last(x: np.ndarray, y: np.ndarray, df: float = 3.0) -> float:
+    """Fitted value at the last knot of the natural cubic smoothing spline whose smoother matrix has
+    trace `df`.  Stand-in for stats::smooth.spline(lambda, pi0, df = 3) inside qvalue::pi0est — numerically
+    UNPINNED against R (R matches df only to its own optimiser tolerance)."""
+    row = _smoother_last_row(np.ascontiguousarray(x, dtype=np.float64).tobytes(), float(df))
+    return float(row @ np.asarray(y, dtype=np.float64))
 
 
 def qvalue_or_fallback(p: np.ndarray) -> np.ndarray:
@@ -417,7 +424,8 @@ def qvalue_or_fallback(p: np.ndarray) -> np.ndarray:
             raise ValueError("maximum p-value is smaller than lambda range")
         if m < 2:
             raise ValueError("lfdr density estimate needs at least two p-values")
-        pi0_l = np.array([np.mean(pv >= l) / (1.0 - l) for l in lam])
+        ps_sorted = np.sort(pv)
+        pi0_l = (m - np.searchsorted(ps_sorted, lam, side="left")) / m / (1.0 - lam)
         pi0 = min(_smooth_spline_df3_last(lam, pi0_l, 3.0), 1.0)
         if pi0 <= 0:
             raise ValueError("estimated pi0 <= 0")
