@@ -83,11 +83,11 @@ struct Shard {
     if (e == cudaSuccess) h_stage_cap = bytes + 256;
     return e;
   }
-  DevBuf assay, from, to, ea, eb, stage_dev, bs_count, bs_slot, seg_done, excl, node_of_row, rowlist, scal, src_of_pos, pct, cutoff, D, cub_tmp, mean, sxx, med, bad, stat, status, p_edge, coef, iters, act, counters, sortk, sortk2, idx,
+  DevBuf assay, from, to, ea, eb, stage_dev, bs_count, bs_slot, seg_done, seg_pi0, excl, node_of_row, rowlist, scal, src_of_pos, pct, cutoff, D, cub_tmp, mean, sxx, med, bad, stat, status, p_edge, coef, iters, act, counters, sortk, sortk2, idx,
       idx2, ps, sa, sb, tile_cnt, tile_base, seg_n, tile_min, tile_carry, padj_best, cat_best, cat, padj, med_out,
       small_out, rsel_hist, rsel_state, rsel_cand, dense_S, cf_tab, sxy;
   void release_all() {
-    DevBuf* all[] = {&assay, &from, &to, &ea, &eb, &stage_dev, &bs_count, &bs_slot, &seg_done, &excl, &node_of_row, &rowlist, &scal, &src_of_pos, &pct, &cutoff,
+    DevBuf* all[] = {&assay, &from, &to, &ea, &eb, &stage_dev, &bs_count, &bs_slot, &seg_done, &seg_pi0, &excl, &node_of_row, &rowlist, &scal, &src_of_pos, &pct, &cutoff,
                      &D, &cub_tmp, &mean, &sxx, &med, &bad, &stat, &status, &p_edge,
                      &coef, &iters, &act, &counters, &sortk, &sortk2, &idx, &idx2, &ps, &sa, &sb, &tile_cnt,
                      &tile_base, &seg_n, &tile_min, &tile_carry, &padj_best, &cat_best, &cat, &padj, &med_out,
@@ -276,7 +276,7 @@ unsigned int qs_cand_capacity(const mdeggs_ctx* ctx, const mdeggs_problem* in) {
 }
 bool device_adjust(const mdeggs_problem* in) {
   return in->padj == MDEGGS_PADJ_BONFERRONI || in->padj == MDEGGS_PADJ_BH || in->padj == MDEGGS_PADJ_HOLM ||
-         in->padj == MDEGGS_PADJ_HOCHBERG || in->padj == MDEGGS_PADJ_BY;
+         in->padj == MDEGGS_PADJ_HOCHBERG || in->padj == MDEGGS_PADJ_BY || in->padj == MDEGGS_PADJ_QVALUE;
 }
 // K8 ordering by p-value buckets (mdeggs_bsort.cuh) instead of the multi-pass radix sort
 bool use_bucket_order(const mdeggs_ctx* ctx, const mdeggs_problem* in, int32_t n_nodes) {
@@ -354,6 +354,8 @@ int run_adjust(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, int n_segmen
   A.best = best_dev;
   A.tot = s.counters.as<unsigned long long>();  // c_tot[P], filled by k_percolate
   A.reuse_tiles = reuse_tiles ? 1 : 0;
+  CU(s.seg_pi0.ensure((size_t)in->P * in->K * 8));
+  A.seg_pi0 = s.seg_pi0.as<double>();
   dim3 grid((unsigned)ntiles, (unsigned)n_segments);
   // per-segment "CTAs done" counters of the fused tile passes: zero when first allocated, re-armed by the kernels
   {
@@ -368,6 +370,9 @@ int run_adjust(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, int n_segmen
   if (!reuse_tiles)
     LAUNCH(k_bh_count, grid, BH_THREADS, 0, s.s_main, A, s.tile_cnt.as<int32_t>(), s.tile_base.as<long long>(),
            s.seg_n.as<long long>(), done_a);
+  if (in->padj == MDEGGS_PADJ_QVALUE && !reuse_tiles)
+    LAUNCH(k_qv_pi0, dim3(1, (unsigned)n_segments), BH_THREADS, 0, s.s_main, A, s.tile_base.as<long long>(),
+           s.seg_n.as<long long>(), s.seg_pi0.as<double>());
   if (in->padj != MDEGGS_PADJ_BONFERRONI && !reuse_tiles)
     LAUNCH(k_bh_tilemin, grid, BH_THREADS, 0, s.s_main, A, in->padj, s.tile_cnt.as<int32_t>(),
            s.tile_base.as<long long>(), s.seg_n.as<long long>(), s.tile_min.as<double>(),
@@ -820,8 +825,7 @@ int run_shard_back(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
   int32_t* d_best = s.scal.as<int32_t>() + 2 * SC_BEST;
   const int act_stride = n_nodes > 0 ? n_nodes : 1;
   const int Pn = P > 0 ? P : 1;
-  const bool dev_adjust = (in->padj == MDEGGS_PADJ_BONFERRONI || in->padj == MDEGGS_PADJ_BH || in->padj == MDEGGS_PADJ_HOLM ||
-                           in->padj == MDEGGS_PADJ_HOCHBERG || in->padj == MDEGGS_PADJ_BY);
+  const bool dev_adjust = device_adjust(in);
   const bool do_adjust = dev_adjust && E > 0 && P > 0 && n_nodes > 0;
   if (do_adjust) {
     // The raw p-value of an edge does not depend on the percentile: sort ALL edges by p once. This needs no
@@ -945,8 +949,7 @@ int run_shard_back(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
 // all-reduce of the per-percentile significant counts when the adjustment was sharded over the ranks
 int run_sig_allreduce(mdeggs_ctx* ctx, const mdeggs_problem* in, const mdeggs_result* out) {
   Shard& s0 = ctx->shards[0];
-  const bool dev_adjust = (in->padj == MDEGGS_PADJ_BONFERRONI || in->padj == MDEGGS_PADJ_BH || in->padj == MDEGGS_PADJ_HOLM ||
-                           in->padj == MDEGGS_PADJ_HOCHBERG || in->padj == MDEGGS_PADJ_BY);
+  const bool dev_adjust = device_adjust(in);
   if (!(dev_adjust && s0.world > 1 && !out->padj && in->E > 0 && in->P > 0)) return MDEGGS_OK;
   NcclApi& api = nccl_api();
   const int Pn = in->P;
@@ -977,8 +980,7 @@ int run_shard_back2(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const m
   long long* o_sig = o_tot + Pn;
   long long* o_fail = o_tot + 2 * Pn;
   const bool dev_out = in->mem == MDEGGS_MEM_DEVICE;
-  const bool dev_adjust = (in->padj == MDEGGS_PADJ_BONFERRONI || in->padj == MDEGGS_PADJ_BH || in->padj == MDEGGS_PADJ_HOLM ||
-                           in->padj == MDEGGS_PADJ_HOCHBERG || in->padj == MDEGGS_PADJ_BY);
+  const bool dev_adjust = device_adjust(in);
   const bool do_adjust = dev_adjust && E > 0 && P > 0 && n_nodes > 0;
   const bool want_padj_best = out->padj_best && do_adjust;
   const bool shard_p = do_adjust && s.world > 1 && !out->padj;

@@ -16,6 +16,7 @@
 
 #include "mdeggs.h"
 #include "mdeggs_math.cuh"
+#include "mdeggs_qvalue_tab.h"
 
 namespace mdeggs {
 
@@ -732,6 +733,7 @@ struct BhArgs {
   const unsigned long long* tot;  // tot_edges[P] from k_percolate: percentiles without tested edges are skipped
   int reuse_tiles;      // best-percentile pass: reuse the tile partials of the all-percentile pass (segment index
                         // of percentile p is ((p - p0) / p_stride) * K + c - 1 there)
+  const double* seg_pi0;  // q.value: pi0 of each segment (k_qv_pi0), indexed like the tile partials
 };
 
 // maps blockIdx.y to (percentile p, category c, segment index `seg` into the tile-partial arrays)
@@ -843,6 +845,7 @@ __device__ __forceinline__ double adj_numerator(int mode, double n) {
 }
 __device__ __forceinline__ double adj_value(int mode, double n, double num, long long i, double p) {
   if (mode == MDEGGS_PADJ_BH || mode == MDEGGS_PADJ_BY) return __dmul_rn(__ddiv_rn(num, (double)i), p);  // (n/i) p[o]
+  if (mode == MDEGGS_PADJ_QVALUE) return __ddiv_rn(__dmul_rn(p, n), (double)i);  // qvalue: p[o] * m / i
   return __dmul_rn(__dsub_rn(__dadd_rn(n, 1.0), (double)i), p);  // holm / hochberg: (n + 1 - i) * p[o]
 }
 
@@ -919,6 +922,74 @@ __global__ void __launch_bounds__(BH_THREADS) k_bh_tilemin(BhArgs A, int mode, c
   if (bh_last_of_segment(seg_done, seg, A.ntiles)) bh_suffix_body(tile_min, A.ntiles, mode, seg, tile_carry);
 }
 
+// q.value: pi0 of every segment (qvalue::pi0est, smoother method; core_functions.R:1012-1025)
+//   pi0(lambda_j) = mean(p >= lambda_j) / (1 - lambda_j), lambda = seq(0.05, 0.95, 0.05);
+//   pi0 = min(1, value at the last lambda of smooth.spline(lambda, pi0(lambda), df = 3)) = QV_ROW . pi0(lambda);
+//   qvalue() stops when there are fewer than two p-values, when max(p) < max(lambda) or when pi0 <= 0: the reference
+//   then retries with pi0 = 1 if the category network has more than one row, else returns NA.
+// The members of a segment below lambda_j are counted from the tile offsets of pass A plus one partial tile.
+__global__ void __launch_bounds__(BH_THREADS) k_qv_pi0(BhArgs A, const long long* __restrict__ tile_base,
+                                                      const long long* __restrict__ seg_n,
+                                                      double* __restrict__ seg_pi0) {
+  int p, c;
+  size_t seg;
+  if (!bh_segment(A, p, c, seg)) return;
+  if (A.tot && A.tot[p] == 0) {
+    if (threadIdx.x == 0) seg_pi0[seg] = nan("");
+    return;
+  }
+  __shared__ long long s_J[QV_NLAMBDA], s_lt[QV_NLAMBDA];
+  __shared__ int s_part;
+  const int64_t nv = (int64_t)*A.n_valid;
+  if (threadIdx.x < QV_NLAMBDA) {  // first sorted position whose p is >= lambda_j
+    const double lam = QV_LAMBDA[threadIdx.x];
+    int64_t lo = 0, hi = nv;
+    while (lo < hi) {
+      const int64_t mid = (lo + hi) >> 1;
+      if (A.ps[mid] < lam) lo = mid + 1;
+      else hi = mid;
+    }
+    s_J[threadIdx.x] = lo;
+  }
+  if (threadIdx.x == 0) s_part = 0;
+  __syncthreads();
+  auto member = [&](int64_t q) {
+    return edge_category(A.act[(size_t)p * A.act_stride + A.sa[q]], A.act[(size_t)p * A.act_stride + A.sb[q]]) == c;
+  };
+  for (int j = 0; j <= QV_NLAMBDA; ++j) {  // j == QV_NLAMBDA: members whose p is NaN (sorted last)
+    const int64_t from = j < QV_NLAMBDA ? (s_J[j] / BH_TILE) * BH_TILE : nv;
+    const int64_t to = j < QV_NLAMBDA ? s_J[j] : A.E;
+    int cnt = 0;
+    for (int64_t q = from + threadIdx.x; q < to; q += BH_THREADS) cnt += member(q);
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&s_part, cnt);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      if (j < QV_NLAMBDA) {
+        const int64_t tile = s_J[j] / BH_TILE;
+        s_lt[j] = (tile < A.ntiles ? tile_base[seg * A.ntiles + tile] : seg_n[seg]) + s_part;
+      } else {
+        // thread 0 finishes: pi0 and the fallback rule
+        const long long m = seg_n[seg], m_all = m + s_part;
+        double pi0 = 0.0;
+        bool ok = m >= 2 && (m - s_lt[QV_NLAMBDA - 1]) > 0;  // at least two p-values, max(p) >= max(lambda)
+        if (ok) {
+          for (int l = 0; l < QV_NLAMBDA; ++l) {
+            const double frac = __ddiv_rn((double)(m - s_lt[l]), (double)m);
+            pi0 = fma(QV_ROW[l], __ddiv_rn(frac, __dsub_rn(1.0, QV_LAMBDA[l])), pi0);
+          }
+          pi0 = fmin(pi0, 1.0);
+          ok = pi0 > 0.0;
+        }
+        if (!ok) pi0 = m_all > 1 ? 1.0 : nan("");
+        seg_pi0[seg] = pi0;
+      }
+      s_part = 0;
+    }
+    __syncthreads();
+  }
+}
+
 // pass C: adjusted values, count < 0.05, optional scatter to network order
 //   mode 1 bonferroni: pmin(1, n * p);  mode 2 BH: pmin(1, cummin((n/i) * p[o]))[ro]
 __global__ void __launch_bounds__(BH_THREADS) k_bh_final(BhArgs A, int mode, const int32_t* __restrict__ tile_cnt,
@@ -985,6 +1056,11 @@ __global__ void __launch_bounds__(BH_THREADS) k_bh_final(BhArgs A, int mode, con
 #pragma unroll
     for (int it = 0; it < BH_ITEMS; ++it)
       q[it] = fwd_max ? fmin(1.0, fmax(run_it[it], fmax(others, carry))) : fmin(1.0, fmin(run_it[it], fmin(others, carry)));
+    if (mode == MDEGGS_PADJ_QVALUE) {  // qvalues = pi0 * pmin(1, cummin(p[o] m / i)); pi0 NaN: the reference returns NA
+      const double pi0 = A.seg_pi0[seg];
+#pragma unroll
+      for (int it = 0; it < BH_ITEMS; ++it) q[it] = __dmul_rn(pi0, q[it]);
+    }
     __syncthreads();
   } else {
 #pragma unroll

@@ -229,7 +229,9 @@ def _padj_code(padj_method: str) -> int:
         return _abi.PADJ_HOCHBERG
     if padj_method == "BY":
         return _abi.PADJ_BY
-    if padj_method in ("q.value", "hommel"):
+    if padj_method == "q.value":
+        return _abi.PADJ_QVALUE   # pi0 smoother + q-values on the device (SURVEY section 8 f, N1)
+    if padj_method == "hommel":
         return _abi.PADJ_HOST
     raise ValueError(f"padj_method must be one of {P_ADJUST_METHODS + ('q.value',)}")
 

@@ -63,8 +63,100 @@ def lib() -> C.CDLL:
     return _LIB
 
 
+def _qvalue_smoother_last(x: np.ndarray, y: np.ndarray, df: float = 3.0) -> float:
+    """Value at the last knot of the natural cubic smoothing spline (Reinsch form) whose smoother has trace df:
+    restatement of what qvalue::pi0est(pi0.method = "smoother") asks of stats::smooth.spline(lambda, pi0, df = 3).
+    Solves (I + a K) f = y directly for the a that gives trace df (bisection on a)."""
+    n = x.shape[0]
+    h = np.diff(x)
+    Q = np.zeros((n, n - 2))
+    R = np.zeros((n - 2, n - 2))
+    for j in range(n - 2):
+        Q[j:j + 3, j] = [1.0 / h[j], -1.0 / h[j] - 1.0 / h[j + 1], 1.0 / h[j + 1]]
+        R[j, j] = (h[j] + h[j + 1]) / 3.0
+        if j + 1 < n - 2:
+            R[j, j + 1] = R[j + 1, j] = h[j + 1] / 6.0
+    K = Q @ np.linalg.solve(R, Q.T)
+    eye = np.eye(n)
+    lo, hi = 1e-12, 1e12
+    for _ in range(200):
+        mid = np.sqrt(lo * hi)
+        if np.trace(np.linalg.inv(eye + mid * K)) > df:
+            lo = mid
+        else:
+            hi = mid
+    return float(np.linalg.solve(eye + np.sqrt(lo * hi) * K, y)[-1])
+
+
+def qvalue(p: np.ndarray) -> np.ndarray:
+    """`padj_method = "q.value"` of calc_pvalues_network (core_functions.R:1012-1025): qvalue::qvalue(p)$qvalues
+    (pi0 by the smoother over lambda = seq(0.05, 0.95, 0.05); qvalues = pi0 * pmin(1, cummin(p[o] * m / i)) with o the
+    decreasing order); on any qvalue() error retry with pi0 = 1 when there is more than one row, else NA."""
+    p = np.asarray(p, dtype=np.float64)
+    ok = ~np.isnan(p)
+    pv = p[ok]
+    m = pv.shape[0]
+
+    def q_of(pi0):
+        o = np.argsort(-pv, kind="stable")
+        cm = np.minimum.accumulate(pv[o] * m / np.arange(m, 0, -1, dtype=np.float64))
+        q = np.empty(m)
+        q[o] = pi0 * np.minimum(1.0, cm)
+        out = np.full(p.shape[0], np.nan)
+        out[ok] = q
+        return out
+
+    lam = seq(0.05, 0.95, 0.05)
+    good = m >= 2 and pv.min() >= 0 and pv.max() <= 1 and pv.max() >= lam.max()
+    if good:
+        pi0_l = np.array([np.mean(pv >= l) / (1.0 - l) for l in lam])
+        pi0 = min(_qvalue_smoother_last(lam, pi0_l), 1.0)
+        good = pi0 > 0
+    if good:
+        return q_of(pi0)
+    return q_of(1.0) if p.shape[0] > 1 else np.full(p.shape[0], np.nan)
+
+
+def _run_omic_qvalue(problem: _abi.Problem, want, mode: int, nthreads: int) -> dict[str, np.ndarray]:
+    """PADJ_QVALUE: the C restatement returns raw p-values and the category of every edge at every percentile; the
+    q-values, the significant-pair counts and the best percentile (core_functions.R:796-827, 471-495) follow here."""
+    import copy
+    raw = copy.copy(problem)
+    raw.padj = _abi.PADJ_HOST
+    need = tuple(dict.fromkeys(tuple(w for w in want if w not in ("padj", "padj_best", "cat_best", "sig_count", "best"))
+                               + ("p_edge", "cat", "tot_edges", "fail_count")))
+    res = run_omic(raw, need, mode, nthreads)
+    G, n, E, K, P = problem.dims
+    p_edge, cat, tot, fail = res["p_edge"], res["cat"].reshape(P, E), res["tot_edges"], res["fail_count"]
+    padj = np.full((P, E), np.nan)
+    sig = np.full(P, -1, dtype=np.int64)
+    for pi in range(P):
+        if tot[pi] <= 0:
+            continue
+        cnt = 0
+        for k in range(1, K + 1):
+            msk = cat[pi] == k
+            if msk.any():
+                padj[pi, msk] = qvalue(p_edge[msk])
+                cnt += int(np.sum(padj[pi, msk] < 0.05))
+        sig[pi] = cnt
+    best, bv = 0, -1
+    for pi in range(P):
+        if tot[pi] > 0 and fail[pi] == 0 and sig[pi] > bv:
+            best, bv = pi + 1, sig[pi]
+    out = dict(res)
+    out["padj"] = padj
+    out["sig_count"] = sig
+    out["best"] = np.array([best], dtype=np.int32)
+    out["padj_best"] = padj[best - 1].copy() if best > 0 else np.full(E, np.nan)
+    out["cat_best"] = cat[best - 1].copy() if best > 0 else np.zeros(E, dtype=np.int8)
+    return {k: v for k, v in out.items() if k in want}
+
+
 def run_omic(problem: _abi.Problem, want=tuple(_abi.RESULT_FIELDS), mode: int = MODE_UNIQUE,
              nthreads: int = 0) -> dict[str, np.ndarray]:
+    if problem.padj == _abi.PADJ_QVALUE:
+        return _run_omic_qvalue(problem, tuple(want), mode, nthreads)
     cprob = problem.to_c()
     cres, arrays = _abi.alloc_result(problem.dims, want)
     rc = lib().mdeggs_oracle_run_omic(C.byref(cprob), C.byref(cres), mode, nthreads)

@@ -653,3 +653,42 @@ def test_bucket_order_edge_counts(oracle, E):
     if E <= 33:
         ref = oracle.run_omic(prob, want)
         assert np.array_equal(got["sig_count"], ref["sig_count"]) and np.array_equal(got["best"], ref["best"])
+
+
+@pytest.mark.parametrize("G,n,E,K,seed", [(60, 30, 200, 2, 41), (300, 64, 5000, 2, 42), (200, 90, 3000, 3, 43),
+                                          (40, 24, 60, 2, 44), (500, 40, 20000, 2, 45)])
+def test_device_qvalue_matches_oracle(engine, oracle, G, n, E, K, seed):
+    """padj "q.value" on the device (pi0 smoother + q-values per (percentile, category) segment) against the oracle's
+    restatement of qvalue::qvalue, including the reference's fallback rules (core_functions.R:1012-1025)."""
+    prob = synth.random_problem(G, n, E, K, seed, _abi.METHOD_LM, _abi.PADJ_QVALUE,
+                                pct=_abi.r_seq(0.25, 0.98, 0.05))
+    want = ("p_edge", "status", "cat", "padj", "padj_best", "cat_best", "sig_count", "tot_edges", "fail_count", "best")
+    gpu = engine.run_omic(prob, want)
+    ref = oracle.run_omic(prob, want)
+    assert_parity(gpu, ref, prob, what=f"q.value G{G} E{E} K{K}: ")
+
+
+def test_device_qvalue_fallback_branches(engine, oracle):
+    """Segments where qvalue() errors: a single tested edge (NA), all p-values below max(lambda) (pi0 = 1 retry)."""
+    rng = np.random.default_rng(77)
+    G, n = 40, 60
+    grp = (np.arange(n) % 2 + 1).astype(np.int32)
+    v = rng.normal(5, 1, size=(G, n))
+    # strongly planted pairs: every tested p-value is tiny (< 0.95 = max lambda) -> qvalue() stops -> pi0 = 1
+    for g in range(0, 20, 2):
+        z = rng.normal(0, 1, n)
+        v[g] = 5 + 2 * z
+        v[g + 1] = 5 + 2 * np.where(grp == 1, z, -z) + rng.normal(0, 0.05, n)
+    fr = np.arange(1, 20, 2, dtype=np.int32)
+    to = fr + 1
+    prob = _abi.Problem(assay=np.asfortranarray(v), from_idx=fr, to_idx=to.astype(np.int32), group=grp, K=2,
+                        pct=np.array([0.0, 0.2, 0.5]), method=_abi.METHOD_LM, padj=_abi.PADJ_QVALUE)
+    want = ("p_edge", "cat", "padj", "sig_count", "tot_edges", "best", "padj_best")
+    gpu = engine.run_omic(prob, want)
+    ref = oracle.run_omic(prob, want)
+    assert_parity(gpu, ref, prob, what="q.value fallback: ")
+    assert ref["tot_edges"].max() > 0
+    one = _abi.Problem(assay=np.asfortranarray(v), from_idx=fr[:1].copy(), to_idx=to[:1].astype(np.int32), group=grp,
+                       K=2, pct=np.array([0.0]), method=_abi.METHOD_LM, padj=_abi.PADJ_QVALUE)
+    g1, r1 = engine.run_omic(one, want), oracle.run_omic(one, want)
+    assert_parity(g1, r1, one, what="q.value single row: ")
