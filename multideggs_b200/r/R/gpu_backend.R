@@ -19,7 +19,10 @@
   if (padj_method == "holm") return(4L)
   if (padj_method == "hochberg") return(5L)
   if (padj_method == "BY") return(6L)
-  3L  # q.value, hommel: raw p + masks come back, R adjusts each segment
+  # q.value: the device estimates pi0 (smoother over lambda = seq(.05,.95,.05)) and returns q-values (code 7).
+  # options(multiDEGGs.qvalue_on_host = TRUE) keeps Bioconductor's qvalue::qvalue in the loop instead (code 3).
+  if (padj_method == "q.value" && !isTRUE(getOption("multiDEGGs.qvalue_on_host"))) return(7L)
+  3L  # hommel (or host-side q.value): raw p + masks come back, R adjusts each segment
 }
 
 get_diffNetworks_singleOmic <- function(assayData, assayDataName, metadata, regression_method,
