@@ -236,6 +236,42 @@ def _padj_code(padj_method: str) -> int:
     raise ValueError(f"padj_method must be one of {P_ADJUST_METHODS + ('q.value',)}")
 
 
+_NET_MATCH_CACHE: dict = {}
+
+
+def _match_network(network, genes: np.ndarray, assayDataName: str):
+    """edges <- network rows whose two ends are rownames (match(): first occurrence), duplicates removed keeping the
+    first (core_functions.R:319-331), as 1-based row indices.  Repeated calls with the same network object and the
+    same rownames (nestedcv folds) reuse the result."""
+    net = omic_network() if network is None else network
+    ident = "builtin" if network is None else (id(net), str(net["from"].iloc[0]), str(net["to"].iloc[-1])) if len(net) else id(net)
+    key = (ident, len(net), hash(genes.tobytes()), genes.shape[0])
+    hit = _NET_MATCH_CACHE.get(key)
+    if hit is not None:
+        return hit
+    first: dict[str, int] = {}
+    for i, g in enumerate(genes.tolist()):
+        first.setdefault(g, i + 1)  # match(): first occurrence
+    nf = pd.Series(net["from"].to_numpy(dtype=object)).map(first)
+    nt = pd.Series(net["to"].to_numpy(dtype=object)).map(first)
+    ok = (nf.notna() & nt.notna()).to_numpy()
+    fr = nf.to_numpy()[ok].astype(np.int64)
+    to = nt.to_numpy()[ok].astype(np.int64)
+    if fr.size == 0:
+        raise ValueError(f"Rownames of {assayDataName} don't match any link of the biological\n"
+                         "    network. Check if names need conversion to gene symbols or entrez IDs. \n"
+                         "    Alternatively, provide more data.")
+    # remove duplicate edges, keep first (core_functions.R:329-331)
+    k2 = fr * (len(genes) + 1) + to
+    _, first_pos = np.unique(k2, return_index=True)
+    sel = np.sort(first_pos)
+    out = (fr[sel].astype(np.int32), to[sel].astype(np.int32))
+    if len(_NET_MATCH_CACHE) >= 8:
+        _NET_MATCH_CACHE.pop(next(iter(_NET_MATCH_CACHE)))
+    _NET_MATCH_CACHE[key] = out
+    return out
+
+
 def prepare_omic(assayData, assayDataName: str, metadata: Factor, regression_method: str, network,
                  percentile_vector, padj_method: str, tested_coef: int = 3,
                  rlm_cov_mode: int = _abi.RLM_COV_XTWX) -> OmicPrep:
@@ -269,24 +305,7 @@ def prepare_omic(assayData, assayDataName: str, metadata: Factor, regression_met
         fr = np.asarray(network.from_idx, dtype=np.int32)
         to = np.asarray(network.to_idx, dtype=np.int32)
     else:
-        net = omic_network() if network is None else network
-        first: dict[str, int] = {}
-        for i, g in enumerate(genes.tolist()):
-            first.setdefault(g, i + 1)  # match(): first occurrence
-        nf = pd.Series(net["from"].to_numpy(dtype=object)).map(first)
-        nt = pd.Series(net["to"].to_numpy(dtype=object)).map(first)
-        ok = (nf.notna() & nt.notna()).to_numpy()
-        fr = nf.to_numpy()[ok].astype(np.int64)
-        to = nt.to_numpy()[ok].astype(np.int64)
-        if fr.size == 0:
-            raise ValueError(f"Rownames of {assayDataName} don't match any link of the biological\n"
-                             "    network. Check if names need conversion to gene symbols or entrez IDs. \n"
-                             "    Alternatively, provide more data.")
-        # remove duplicate edges, keep first (core_functions.R:329-331)
-        key = fr * (len(genes) + 1) + to
-        _, first_pos = np.unique(key, return_index=True)
-        sel = np.sort(first_pos)
-        fr, to = fr[sel].astype(np.int32), to[sel].astype(np.int32)
+        fr, to = _match_network(network, genes, assayDataName)
     K = len(metadata.levels)
     if K > _abi.MAX_K:
         raise ValueError(f"more than {_abi.MAX_K} categories are not supported by the GPU engine")
