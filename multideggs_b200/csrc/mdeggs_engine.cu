@@ -827,6 +827,52 @@ int run_shard_back(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
   const int Pn = P > 0 ? P : 1;
   const bool dev_adjust = device_adjust(in);
   const bool do_adjust = dev_adjust && E > 0 && P > 0 && n_nodes > 0;
+  // K7 percolation (category of every edge at every percentile, counts) does not need the p order: it runs on the side
+  // stream, after the activity masks, while the main stream orders the edges; both join before K8
+  CU(cudaEventRecord(s.ev_fork, s.s_main));  // p-values and status of every edge are final
+  CU(cudaStreamWaitEvent(s.s_sort, s.ev_fork, 0));
+  // counters: tot[P] fail[P] sig[P] sig_raw[P] (u64), then out: tot_out[P] sig_out[P] fail_out[P] (i64)
+  CU(s.counters.ensure((size_t)Pn * 8 * 7));
+  CU(cudaMemsetAsync(s.counters.p, 0, (size_t)Pn * 8 * 7, s.s_sort));
+  unsigned long long* c_tot = s.counters.as<unsigned long long>();
+  unsigned long long* c_fail = c_tot + Pn;
+  unsigned long long* c_sig = c_tot + 2 * Pn;
+  unsigned long long* c_raw = c_tot + 3 * Pn;
+  long long* o_tot = (long long*)(c_tot + 4 * Pn);
+  long long* o_sig = o_tot + Pn;
+  long long* o_fail = o_tot + 2 * Pn;
+  CU(s.act.ensure((size_t)Pn * act_stride));
+  const bool dev_out = in->mem == MDEGGS_MEM_DEVICE;
+  int8_t* d_cat = nullptr;
+  if (out->cat && E > 0 && P > 0) {
+    if (dev_out && emit) d_cat = out->cat;
+    else {
+      CU(s.cat.ensure((size_t)P * E));
+      d_cat = s.cat.as<int8_t>();
+    }
+  }
+  // adjusted values of every percentile are kept when they fit a modest scratch matrix (the best row is then a copy);
+  // multi-GPU: the (percentile, category) segments are independent, so rank r adjusts percentiles r, r+world, ...
+  // and only the per-percentile significant counts are all-reduced; a full P x E p.adj output keeps it replicated
+  double* d_padj = nullptr;
+  const bool want_padj_best = out->padj_best && do_adjust;
+  const bool shard_p = do_adjust && s.world > 1 && !out->padj;
+  const bool keep_all_padj = do_adjust && !shard_p &&
+                             (out->padj || (want_padj_best && (size_t)P * (size_t)E * 8 <= ((size_t)256 << 20)));
+  if (keep_all_padj) {
+    if (out->padj && dev_out && emit) d_padj = out->padj;
+    else {
+      CU(s.padj.ensure((size_t)P * E * 8));
+      d_padj = s.padj.as<double>();
+    }
+  }
+  if (n_nodes > 0 && P > 0) {
+    if (E > 0)  // (also writes NaN into the p.adj rows of the edges that are not tested at a percentile)
+      LAUNCH(k_percolate, blocks_for(E, 256), 256, (size_t)3 * P * sizeof(unsigned), s.s_sort, s.ea.as<int32_t>(),
+             s.eb.as<int32_t>(), s.status.as<int32_t>(), s.p_edge.as<double>(), s.act.as<uint8_t>(), act_stride, E, P,
+             c_tot, c_fail, c_raw, d_cat, d_padj, s.scal.as<int32_t>() + 2 * SC_ERR);
+  }
+  CU(cudaEventRecord(s.ev_join, s.s_sort));
   if (do_adjust) {
     // The raw p-value of an edge does not depend on the percentile: sort ALL edges by p once. This needs no
     // cut-off, so it is enqueued BEFORE joining the quantile stream and overlaps the tail of the radix select.
@@ -885,49 +931,8 @@ int run_shard_back(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
              s.scal.as<int32_t>() + 2 * SC_ERR);
     }
   }
-  CU(cudaStreamWaitEvent(s.s_main, s.ev_join, 0));  // cut-offs ready
-  trace_mark(ctx, "(join quantile stream)", s.s_main);
-  // counters: tot[P] fail[P] sig[P] sig_raw[P] (u64), then out: tot_out[P] sig_out[P] fail_out[P] (i64)
-  CU(s.counters.ensure((size_t)Pn * 8 * 7));
-  CU(cudaMemsetAsync(s.counters.p, 0, (size_t)Pn * 8 * 7, s.s_main));
-  unsigned long long* c_tot = s.counters.as<unsigned long long>();
-  unsigned long long* c_fail = c_tot + Pn;
-  unsigned long long* c_sig = c_tot + 2 * Pn;
-  unsigned long long* c_raw = c_tot + 3 * Pn;
-  long long* o_tot = (long long*)(c_tot + 4 * Pn);
-  long long* o_sig = o_tot + Pn;
-  long long* o_fail = o_tot + 2 * Pn;
-  CU(s.act.ensure((size_t)Pn * act_stride));
-  const bool dev_out = in->mem == MDEGGS_MEM_DEVICE;
-  int8_t* d_cat = nullptr;
-  if (out->cat && E > 0 && P > 0) {
-    if (dev_out && emit) d_cat = out->cat;
-    else {
-      CU(s.cat.ensure((size_t)P * E));
-      d_cat = s.cat.as<int8_t>();
-    }
-  }
-  // adjusted values of every percentile are kept when they fit a modest scratch matrix (the best row is then a copy);
-  // multi-GPU: the (percentile, category) segments are independent, so rank r adjusts percentiles r, r+world, ...
-  // and only the per-percentile significant counts are all-reduced; a full P x E p.adj output keeps it replicated
-  double* d_padj = nullptr;
-  const bool want_padj_best = out->padj_best && do_adjust;
-  const bool shard_p = do_adjust && s.world > 1 && !out->padj;
-  const bool keep_all_padj = do_adjust && !shard_p &&
-                             (out->padj || (want_padj_best && (size_t)P * (size_t)E * 8 <= ((size_t)256 << 20)));
-  if (keep_all_padj) {
-    if (out->padj && dev_out && emit) d_padj = out->padj;
-    else {
-      CU(s.padj.ensure((size_t)P * E * 8));
-      d_padj = s.padj.as<double>();
-    }
-  }
-  if (n_nodes > 0 && P > 0) {
-    if (E > 0)  // (also writes NaN into the p.adj rows of the edges that are not tested at a percentile)
-      LAUNCH(k_percolate, blocks_for(E, 256), 256, (size_t)3 * P * sizeof(unsigned), s.s_main, s.ea.as<int32_t>(),
-             s.eb.as<int32_t>(), s.status.as<int32_t>(), s.p_edge.as<double>(), s.act.as<uint8_t>(), act_stride, E, P,
-             c_tot, c_fail, c_raw, d_cat, d_padj, s.scal.as<int32_t>() + 2 * SC_ERR);
-  }
+  CU(cudaStreamWaitEvent(s.s_main, s.ev_join, 0));  // categories, counts (and NaN rows of the p.adj scratch) ready
+  trace_mark(ctx, "(join side stream)", s.s_main);
   EVREC(s.ev[EV_PERC], s.s_main);
   // ---- K8 ----
   if (do_adjust) {

@@ -219,11 +219,22 @@ __device__ inline double p_two_sided_ref_tab(const TailConsts& tc, double t, dou
   return __dmul_rn(2.0, __dsub_rn(1.0, u));
 }
 
+// pf(f, 2, d2, lower.tail = FALSE) in closed form: with d1 = 2 the incomplete beta I_x(d2/2, 1) is x^(d2/2),
+// x = d2 / (d2 + 2 f).  Three categories (the interaction F of aov has d1 = K - 1 = 2) therefore need no continued
+// fraction at all.  log1p keeps full precision when x is close to 1 (small F), log(x) when it is not.
+__device__ __forceinline__ double pf_upper_d1_2(double f, double d2) {
+  const double den = d2 + 2.0 * f;
+  const double x = d2 / den, y = 2.0 * f / den;  // x + y == 1
+  const double lg = x < 0.5 ? log(x) : log1p(-y);
+  return exp(0.5 * d2 * lg);
+}
+
 // pf(f, d1, d2, lower.tail = FALSE) with tc = {d1/2, d2/2}
 __device__ inline double pf_upper_tab(const TailConsts& tc, double f, double d1, double d2) {
   if (isnan(f)) return nan("");
   if (f <= 0.0) return 1.0;
   if (isinf(f)) return 0.0;
+  if (d1 == 2.0) return pf_upper_d1_2(f, d2);
   double den = d2 + d1 * f;
   if (d1 * f > d2) return pbeta_xy_tab(tc, true, d2 / den, d1 * f / den, true);
   return pbeta_xy_tab(tc, false, d1 * f / den, d2 / den, false);
