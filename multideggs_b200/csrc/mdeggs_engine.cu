@@ -18,6 +18,7 @@
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -83,11 +84,11 @@ struct Shard {
     if (e == cudaSuccess) h_stage_cap = bytes + 256;
     return e;
   }
-  DevBuf assay, from, to, ea, eb, stage_dev, bs_count, bs_slot, seg_done, seg_pi0, excl, node_of_row, rowlist, scal, src_of_pos, pct, cutoff, D, cub_tmp, mean, sxx, med, bad, stat, status, p_edge, coef, iters, act, counters, sortk, sortk2, idx,
+  DevBuf assay, from, to, ea, eb, stage_dev, bs_count, bs_slot, seg_done, seg_pi0, B16, stamps, excl, node_of_row, rowlist, scal, src_of_pos, pct, cutoff, D, cub_tmp, mean, sxx, med, bad, stat, status, p_edge, coef, iters, act, counters, sortk, sortk2, idx,
       idx2, ps, sa, sb, tile_cnt, tile_base, seg_n, tile_min, tile_carry, padj_best, cat_best, cat, padj, med_out,
       small_out, rsel_hist, rsel_state, rsel_cand, dense_S, cf_tab, sxy;
   void release_all() {
-    DevBuf* all[] = {&assay, &from, &to, &ea, &eb, &stage_dev, &bs_count, &bs_slot, &seg_done, &seg_pi0, &excl, &node_of_row, &rowlist, &scal, &src_of_pos, &pct, &cutoff,
+    DevBuf* all[] = {&assay, &from, &to, &ea, &eb, &stage_dev, &bs_count, &bs_slot, &seg_done, &seg_pi0, &B16, &stamps, &excl, &node_of_row, &rowlist, &scal, &src_of_pos, &pct, &cutoff,
                      &D, &cub_tmp, &mean, &sxx, &med, &bad, &stat, &status, &p_edge,
                      &coef, &iters, &act, &counters, &sortk, &sortk2, &idx, &idx2, &ps, &sa, &sb, &tile_cnt,
                      &tile_base, &seg_n, &tile_min, &tile_carry, &padj_best, &cat_best, &cat, &padj, &med_out,
@@ -106,6 +107,8 @@ struct GraphKey {
   const void *d_assay, *d_from, *d_to;
   int64_t row_off, ld_eff;
   size_t dense_cap;
+  const void* h_stage;  // k_select_best writes the packed small results into this pinned block
+  size_t h_stage_cap;
 };
 
 struct mdeggs_ctx {
@@ -286,6 +289,12 @@ bool use_bucket_order(const mdeggs_ctx* ctx, const mdeggs_problem* in, int32_t n
 }
 BsArgs make_bs_args(Shard& s, int64_t E);
 inline int bs_padded(int NB) { return ((NB + 1 + 3) & ~3) + 4; }  // entries per array: 16-byte vector access past NB
+
+__global__ void k_stamp(unsigned long long* slot) {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  *slot = t;
+}
 
 template <int K>
 void launch_fit_stream(mdeggs_ctx* ctx, Shard& s, const SegLayout& L, int64_t e_lo, int64_t e_hi) {
@@ -502,6 +511,10 @@ int run_shard_front(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, int32_t
   CU(cudaSetDevice(s.device));
   const int32_t* d_from = s.from.as<int32_t>();
   const int32_t* d_to = s.to.as<int32_t>();
+  if (getenv("MDEGGS_HOSTTIME")) {  // diagnostics: GPU-side time stamps around the compute phase
+    CU(s.stamps.ensure(64));
+    LAUNCH(k_stamp, 1, 1, 0, s.s_main, s.stamps.as<unsigned long long>());
+  }
   // K3 S0 on the side stream, beside K0: sample -> knots of the quantile bins (needs only the inputs)
   if (E > 0 && in->P > 0) {
     const int P = in->P, n = in->n;
@@ -564,6 +577,7 @@ int run_shard_main(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
   const size_t nn = (size_t)(n_nodes > 0 ? n_nodes : 1);
   // ---- K1 gather ----
   CU(s.D.ensure(nn * (size_t)L.npad * 8));
+  if (P > 0) CU(s.B16.ensure(nn * (size_t)L.npad * 2 + 16));
   CU(s.mean.ensure(nn * K * 8));
   CU(s.sxx.ensure(nn * K * 8));
   CU(s.med.ensure(nn * K * 8));
@@ -582,10 +596,10 @@ int run_shard_main(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
     const unsigned grid = 148 * 4;  // persistent CTAs: one histogram flush each
     if (in->layout == MDEGGS_LAYOUT_COLMAJOR) {
       LAUNCH(k_gather_colmajor, grid, 256, 0, s.s_main, s.assay.as<double>(), s.ld_eff, s.row_off, s.rowlist.as<int32_t>(), d_nn,
-             s.src_of_pos.as<int32_t>(), L.npad, n, s.D.as<double>(), d_st, d_hist);
+             s.src_of_pos.as<int32_t>(), L.npad, n, s.D.as<double>(), d_st, d_hist, s.B16.as<unsigned short>());
     } else {
       LAUNCH(k_gather_rowmajor, grid, 256, 0, s.s_main, s.assay.as<double>(), s.ld_eff, s.row_off, s.rowlist.as<int32_t>(), d_nn,
-             s.src_of_pos.as<int32_t>(), L.npad, n, s.D.as<double>(), d_st, d_hist);
+             s.src_of_pos.as<int32_t>(), L.npad, n, s.D.as<double>(), d_st, d_hist, s.B16.as<unsigned short>());
     }
   }
   EVREC(s.ev[EV_GATHER], s.s_main);
@@ -593,18 +607,6 @@ int run_shard_main(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
   if (do_q) {
     LAUNCH(k_qs_scan, 1, QS_SCAN_THREADS, 0, s.s_main, d_st, s.rsel_hist.as<unsigned int>(), d_nn, n, s.pct.as<double>(), P,
            cand_cap);
-    LAUNCH(k_qs_compact, 148 * 4, 256, (size_t)QS_FILTER_CELLS / 8, s.s_main, s.D.as<double>(), s.src_of_pos.as<int32_t>(), L.npad, d_nn, d_st,
-           s.rsel_cand.as<unsigned long long>());
-  }
-  // S4 (one small CTA per slot) runs on the side stream next to K2; K7 joins it
-  CU(cudaEventRecord(s.ev_fork, s.s_main));
-  CU(cudaStreamWaitEvent(s.s_sort, s.ev_fork, 0));
-  if (do_q) {
-    LAUNCH(k_qs_finish, (unsigned)(2 * P), QS_FIN_THREADS, (size_t)QS_FIN_CAP * 8, s.s_sort, s.D.as<double>(),
-           s.src_of_pos.as<int32_t>(), L.npad, d_nn, d_st, s.rsel_cand.as<unsigned long long>(), s.pct.as<double>(), P,
-           s.cutoff.as<double>());
-  } else if (P > 0) {
-    LAUNCH(k_fill_f64, 1, 64, 0, s.s_sort, s.cutoff.as<double>(), (int64_t)P, nan(""));
   }
   // ---- per-run tail tables (depend only on the degrees of freedom) ----
   {
@@ -617,7 +619,21 @@ int run_shard_main(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
     LAUNCH(k_cf_tables, 1, 256, 0, s.s_main, ta, tdf2 / 2.0, s.cf_tab.as<double>(), s.cf_tab.as<double>() + CF_TABLE_LEN,
            s.cf_tab.as<double>() + 2 * CF_TABLE_LEN);
   }
-  // ---- K2 gene stats ----
+  // ---- K2 gene stats (+ K3 S3: the values of the quantile slots are appended to their lists here) ----
+  QsCompactArgs QC;
+  memset(&QC, 0, sizeof QC);
+  if (do_q) {
+    QC.B16 = s.B16.as<unsigned short>();
+    QC.U = &d_st->U;
+    QC.slot_bin = d_st->slot_bin;
+    QC.slot_fat = d_st->slot_fat;
+    QC.slot_count = d_st->slot_count;
+    QC.slot_off = d_st->slot_off;
+    QC.slot_cursor = d_st->slot_cursor;
+    QC.slot_min = d_st->slot_min;
+    QC.slot_max = d_st->slot_max;
+    QC.cand = s.rsel_cand.as<unsigned long long>();
+  }
   if (n_nodes > 0) {
     int max_cnt = 0;
     for (int k = 0; k < K; ++k) max_cnt = L.cnt[k] > max_cnt ? L.cnt[k] : max_cnt;
@@ -626,7 +642,7 @@ int run_shard_main(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
       const unsigned grid = (unsigned)(((long long)n_nodes * K + 7) / 8);
 #define MDEGGS_GS(IT)                                                                                          \
   LAUNCH(k_gene_stats_reg<IT>, grid, 256, 0, s.s_main, s.D.as<double>(), L, d_nn, s.mean.as<double>(),        \
-         s.sxx.as<double>(), s.med.as<double>(), s.bad.as<uint8_t>())
+         s.sxx.as<double>(), s.med.as<double>(), s.bad.as<uint8_t>(), QC)
       if (max_cnt <= 32 * 2) MDEGGS_GS(2);
       else if (max_cnt <= 32 * 4) MDEGGS_GS(4);
       else if (max_cnt <= 32 * 8) MDEGGS_GS(8);
@@ -643,10 +659,20 @@ int run_shard_main(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
         s.smem_attr_set = true;
       }
       LAUNCH(k_gene_stats<128>, (unsigned)n_nodes, 128, use_smem ? smem : 0, s.s_main, s.D.as<double>(), L, d_nn,
-             s.mean.as<double>(), s.sxx.as<double>(), s.med.as<double>(), s.bad.as<uint8_t>(), use_smem);
+             s.mean.as<double>(), s.sxx.as<double>(), s.med.as<double>(), s.bad.as<uint8_t>(), use_smem, QC);
     }
   }
   EVREC(s.ev[EV_STATS], s.s_main);
+  // S4 (one small CTA per slot) runs on the side stream next to the pair fits; K7 joins it
+  CU(cudaEventRecord(s.ev_fork, s.s_main));
+  CU(cudaStreamWaitEvent(s.s_sort, s.ev_fork, 0));
+  if (do_q) {
+    LAUNCH(k_qs_finish, (unsigned)(2 * P), QS_FIN_THREADS, (size_t)QS_FIN_CAP * 8, s.s_sort, s.D.as<double>(),
+           s.B16.as<unsigned short>(), L.npad, d_nn, d_st, s.rsel_cand.as<unsigned long long>(), s.pct.as<double>(), P,
+           s.cutoff.as<double>());
+  } else if (P > 0) {
+    LAUNCH(k_fill_f64, 1, 64, 0, s.s_sort, s.cutoff.as<double>(), (int64_t)P, nan(""));
+  }
   // K7 activity masks need the medians (K2, this stream) and the cut-offs (S4, side stream): they are computed on
   // the side stream while the pair fits run
   CU(s.act.ensure((size_t)(P > 0 ? P : 1) * (n_nodes > 0 ? n_nodes : 1)));
@@ -1000,7 +1026,9 @@ int run_shard_back2(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const m
     CU(s.small_out.ensure(small_block_bytes(P)));
     LAUNCH(k_select_best, 1, 32, 0, s.s_main, c_tot, c_fail, sig_src, P, in->padj == MDEGGS_PADJ_HOST ? 1 : 0,
            s.cutoff.as<double>(), s.scal.as<int32_t>() + 2 * SC_NNODES, s.scal.as<int32_t>() + 2 * SC_ERR, dfh[0],
-           dfh[1], s.small_out.as<long long>(), d_best);
+           dfh[1], s.small_out.as<long long>(),
+           emit ? reinterpret_cast<long long*>((char*)s.h_stage + s.h_stage_cap - 64 - small_block_bytes(P)) : nullptr,
+           d_best);
   }
   // rows of the chosen percentile
   const bool want_cat_best = out->cat_best && E > 0 && in->padj != MDEGGS_PADJ_HOST;
@@ -1026,6 +1054,7 @@ int run_shard_back2(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const m
     LAUNCH(k_scatter_median, blocks_for((int64_t)G * K, 256), 256, 0, s.s_main, s.med.as<double>(),
            s.node_of_row.as<int32_t>(), G, K, s.med_out.as<double>());
   }
+  if (getenv("MDEGGS_HOSTTIME")) LAUNCH(k_stamp, 1, 1, 0, s.s_main, s.stamps.as<unsigned long long>() + 1);
   EVREC(s.ev[EV_ADJ], s.s_main);
   return MDEGGS_OK;
 }
@@ -1109,10 +1138,9 @@ int emit_outputs(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const mdeg
       }
     }
   }
-  // the packed block always reaches pinned memory: node count + error flag are read after the final sync, and host
-  // callers get their small results from it (finish_small_outputs)
-  CU(cudaMemcpyAsync((char*)s.h_stage + s.h_stage_cap - 64 - blk_bytes, blk, blk_bytes, cudaMemcpyDeviceToHost,
-                     s.s_main));
+  // the packed block was also written straight into pinned host memory by k_select_best (mapped, no copy): node
+  // count + error flag are read from it after the final sync, and host callers get their small results from it
+  // (finish_small_outputs)
   if (!dev_out) ctx->stats.d2h_bytes += (int64_t)blk_bytes;
   CU(cudaEventRecord(s.ev[EV_END], s.s_main));
   trace_mark(ctx, "(outputs copied)", s.s_main);
@@ -1305,6 +1333,7 @@ int mdeggs_run_omic(mdeggs_ctx* ctx, const mdeggs_problem* in, mdeggs_result* ou
     set_err(ctx, "n = %d leaves no residual degrees of freedom for K = %d", in->n, in->K);
     return MDEGGS_EINVAL;
   }
+  const auto t_host0 = std::chrono::steady_clock::now();
   HostLayout H;
   int rc = build_layout(ctx, in, H);
   if (rc) return rc;
@@ -1319,6 +1348,7 @@ int mdeggs_run_omic(mdeggs_ctx* ctx, const mdeggs_problem* in, mdeggs_result* ou
     rc = stage_inputs(ctx, s, in, H, src_device);
     if (rc) return rc;
   }
+  if (getenv("MDEGGS_HOSTTIME") && sh0.stamps.p) LAUNCH(k_stamp, 1, 1, 0, sh0.s_main, sh0.stamps.as<unsigned long long>() + 2);
   // ---- phase B: compute, replayed from a CUDA graph when this exact call shape repeats ----
   auto enqueue_compute = [&](int32_t* n_cap) -> int {
     int r = MDEGGS_OK;
@@ -1351,6 +1381,8 @@ int mdeggs_run_omic(mdeggs_ctx* ctx, const mdeggs_problem* in, mdeggs_result* ou
     key.row_off = sh0.row_off;
     key.ld_eff = sh0.ld_eff;
     key.dense_cap = sh0.dense_S.cap;
+    key.h_stage = sh0.h_stage;
+    key.h_stage_cap = sh0.h_stage_cap;
     if (in->mem == MDEGGS_MEM_HOST) {  // host buffers are only touched by the eager phases A and C
       key.in.assay = nullptr;
       key.in.from = key.in.to = nullptr;
@@ -1410,9 +1442,12 @@ int mdeggs_run_omic(mdeggs_ctx* ctx, const mdeggs_problem* in, mdeggs_result* ou
     rc = enqueue_compute(&n_nodes);
     if (rc) return rc;
   }
+  const auto t_host1 = std::chrono::steady_clock::now();
   // ---- phase C: outputs (eager) ----
   rc = emit_outputs(ctx, sh0, in, out, H, n_nodes);
   if (rc) return rc;
+  if (getenv("MDEGGS_HOSTTIME") && sh0.stamps.p) LAUNCH(k_stamp, 1, 1, 0, sh0.s_main, sh0.stamps.as<unsigned long long>() + 3);
+  const auto t_host2 = std::chrono::steady_clock::now();
   for (size_t i = 1; i < ctx->shards.size(); ++i) {
     CU(cudaSetDevice(ctx->shards[i].device));
     CU(cudaEventRecord(ctx->shards[i].ev[EV_END], ctx->shards[i].s_main));
@@ -1432,6 +1467,18 @@ int mdeggs_run_omic(mdeggs_ctx* ctx, const mdeggs_problem* in, mdeggs_result* ou
       set_err(ctx, "from/to contain an index outside 1..G");
       return MDEGGS_EINVAL;
     }
+  }
+  if (ctx->trace >= 2 || getenv("MDEGGS_HOSTTIME")) {
+    const auto t_host3 = std::chrono::steady_clock::now();
+    auto us = [](auto a, auto b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
+    unsigned long long st2[4] = {0, 0, 0, 0};
+    if (s0.stamps.p) cudaMemcpy(st2, s0.stamps.p, 32, cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[mdeggs host] GPU: pre-stamp -> first node %.1f us, compute %.1f us, last node -> after emit %.1f us\n",
+            (double)(st2[0] - st2[2]) * 1e-3, (double)(st2[1] - st2[0]) * 1e-3, (double)(st2[3] - st2[1]) * 1e-3);
+    fprintf(stderr, "[mdeggs host] prep+enqueue %.1f us, emit enqueue %.1f us, sync+finish %.1f us, total %.1f us; "
+            "GPU compute span %.1f us (%s)\n",
+            us(t_host0, t_host1), us(t_host1, t_host2), us(t_host2, t_host3), us(t_host0, t_host3),
+            (double)(st2[1] - st2[0]) * 1e-3, replayed ? "graph" : "eager");
   }
   if (ctx->trace && !ctx->trace_recs.empty()) {  // timeline of this call: end time of every launch, per stream
     float prev[2] = {0.f, 0.f};
@@ -1453,20 +1500,19 @@ int mdeggs_run_omic(mdeggs_ctx* ctx, const mdeggs_problem* in, mdeggs_result* ou
   st.fit_bytes = in->E * (16LL * in->n + 16);
   st.ms_total = ev_ms(s0.ev[EV_START], s0.ev[EV_END]);
   st.ms_h2d = ev_ms(s0.ev[EV_START], s0.ev[EV_H2D]);
-  st.ms_gather = ev_ms(s0.ev[EV_H2D], s0.ev[EV_GATHER]);
-  st.ms_stats = ev_ms(s0.ev[EV_GATHER], s0.ev[EV_STATS]);
-  st.ms_quantile = ev_ms(s0.ev[EV_Q0], s0.ev[EV_Q1]);
-  st.ms_fit = ev_ms(s0.ev[EV_STATS], s0.ev[EV_FIT]);
-  st.ms_tail = ev_ms(s0.ev[EV_FIT], s0.ev[EV_TAIL]);
-  st.ms_collective = ev_ms(s0.ev[EV_TAIL], s0.ev[EV_COLL]);
-  st.ms_percolate = ev_ms(s0.ev[EV_COLL], s0.ev[EV_PERC]);
-  st.ms_adjust = ev_ms(s0.ev[EV_PERC], s0.ev[EV_ADJ]);
   st.ms_d2h = ev_ms(s0.ev[EV_ADJ], s0.ev[EV_END]);
   if (use_bucket_order(ctx, in, n_nodes)) st.fit_path |= 0x200;  // bit 9: K8 ordering by p-value buckets (no radix sort)
   if (replayed) {  // graph replay: no stage boundaries inside the graph; everything between H2D and D2H is compute
-    st.ms_gather = st.ms_stats = st.ms_quantile = st.ms_fit = st.ms_tail = st.ms_collective = st.ms_percolate = 0.f;
-    st.ms_adjust = 0.f;
     st.fit_path |= 0x100;  // bit 8 flags "replayed from a CUDA graph"
+  } else {
+    st.ms_gather = ev_ms(s0.ev[EV_H2D], s0.ev[EV_GATHER]);
+    st.ms_stats = ev_ms(s0.ev[EV_GATHER], s0.ev[EV_STATS]);
+    st.ms_quantile = ev_ms(s0.ev[EV_Q0], s0.ev[EV_Q1]);
+    st.ms_fit = ev_ms(s0.ev[EV_STATS], s0.ev[EV_FIT]);
+    st.ms_tail = ev_ms(s0.ev[EV_FIT], s0.ev[EV_TAIL]);
+    st.ms_collective = ev_ms(s0.ev[EV_TAIL], s0.ev[EV_COLL]);
+    st.ms_percolate = ev_ms(s0.ev[EV_COLL], s0.ev[EV_PERC]);
+    st.ms_adjust = ev_ms(s0.ev[EV_PERC], s0.ev[EV_ADJ]);
   }
   if (out->tot_edges && in->mem == MDEGGS_MEM_HOST)
     for (int p = 0; p < in->P; ++p) st.ref_equiv_tests += out->tot_edges[p];

@@ -139,6 +139,46 @@ __global__ void __launch_bounds__(256) k_build_nodes(const unsigned int* __restr
 // (K1 gather kernels live in mdeggs_qsel.cuh: they also build the value histogram of the quantile selection)
 
 // ------------------------------------------------------------------------------------------------
+// K3 S3 (candidate compaction of the quantile selection, mdeggs_qsel.cuh) rides inside K2: K2 holds every value of D
+// in registers anyway, so it reads the 2-byte bin id the gather kept for each value, looks the bin up in a 4 KB
+// shared table of "slot" bins and appends the few values (~0.6 %) that belong to a slot to that slot's list.
+// ------------------------------------------------------------------------------------------------
+constexpr int QSC_BINS = 4096;
+constexpr unsigned QSC_NO_BIN = 0xffffu;
+struct QsCompactArgs {
+  const unsigned short* B16;  // null: no quantile selection in this run
+  const int* U;               // number of slots
+  const int* slot_bin;
+  const int* slot_fat;        // slots that are not copied (tie groups): only their key range is tracked
+  const unsigned int* slot_count;
+  const unsigned int* slot_off;
+  unsigned int* slot_cursor;
+  unsigned long long *slot_min, *slot_max;
+  unsigned long long* cand;
+};
+// whole CTA; s_tab[QSC_BINS]
+__device__ __forceinline__ void qsc_load_table(const QsCompactArgs& Q, unsigned char* __restrict__ s_tab) {
+  for (int i = threadIdx.x; i < QSC_BINS; i += blockDim.x) s_tab[i] = 0xff;
+  __syncthreads();
+  const int U = *Q.U;
+  for (int i = threadIdx.x; i < U; i += blockDim.x) s_tab[Q.slot_bin[i]] = (unsigned char)i;
+  __syncthreads();
+}
+__device__ __forceinline__ void qsc_visit(const QsCompactArgs& Q, const unsigned char* __restrict__ s_tab, unsigned b,
+                                          unsigned long long key) {
+  if (b >= (unsigned)QSC_BINS) return;  // padding / NaN
+  const unsigned sl = s_tab[b];
+  if (sl == 0xff) return;  // ~99 % of the values leave here
+  if (Q.slot_fat[sl]) {
+    if (key < __ldcg(Q.slot_min + sl)) atomicMin(Q.slot_min + sl, key);
+    if (key > __ldcg(Q.slot_max + sl)) atomicMax(Q.slot_max + sl, key);
+    return;
+  }
+  const unsigned pos = atomicAdd(Q.slot_cursor + sl, 1u);
+  if (pos < Q.slot_count[sl]) Q.cand[Q.slot_off[sl] + pos] = key;
+}
+
+// ------------------------------------------------------------------------------------------------
 // K2: per-gene, per-category statistics
 //   median  — apply(category_vec, 1, stats::median, na.rm = TRUE)   core_functions.R:353-365
 //   mean, centred Sxx — the sufficient statistics of fit_lm_interaction / aov shared by every edge that
@@ -189,9 +229,8 @@ __device__ __forceinline__ unsigned long long warp_select(KeyAt key_at, int m, i
   const int ncand = cnt_hi - cnt_lo;
   unsigned long long mine = lane < ncand ? scratch32[lane] : ~0ull;
   int r = 0;
-#pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    unsigned long long other = __shfl_sync(0xffffffffu, mine, j);
+  for (int j = 0; j < ncand; ++j) {  // broadcast reads of the <= 32 candidates
+    const unsigned long long other = scratch32[j];
     r += (other < mine) || (other == mine && j < lane);
   }
   unsigned hit = __ballot_sync(0xffffffffu, lane < ncand && r == kth - cnt_lo);
@@ -205,10 +244,12 @@ __global__ void __launch_bounds__(THREADS) k_gene_stats(double* __restrict__ D, 
                                                        const int32_t* __restrict__ n_nodes_p,
                                                        double* __restrict__ mean, double* __restrict__ sxx,
                                                        double* __restrict__ med, uint8_t* __restrict__ bad,
-                                                       int use_smem) {
+                                                       int use_smem, QsCompactArgs Q) {
   extern __shared__ double srow[];
   __shared__ int s_bad;
   __shared__ unsigned long long s_cand[THREADS / 32][32];
+  __shared__ unsigned char s_qtab[QSC_BINS];
+  if (Q.B16) qsc_load_table(Q, s_qtab);
   const int node = blockIdx.x;
   if (node >= *n_nodes_p) return;
   double* grow = D + (size_t)node * L.npad;
@@ -233,6 +274,7 @@ __global__ void __launch_bounds__(THREADS) k_gene_stats(double* __restrict__ D, 
       vmax = fmax(vmax, v);
       nn += !isnan(v);
       nf |= !isfinite(v);
+      if (Q.B16) qsc_visit(Q, s_qtab, Q.B16[(size_t)node * L.npad + L.off[k] + i], dkey(v));
     }
     s = warp_sum(s);
 #pragma unroll
@@ -354,9 +396,8 @@ __device__ __forceinline__ unsigned long long warp_select_reg(const unsigned lon
   const int ncand = cnt_hi - cnt_lo;
   unsigned long long mine = lane < ncand ? scratch32[lane] : ~0ull;
   int r = 0;
-#pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    unsigned long long other = __shfl_sync(0xffffffffu, mine, j);
+  for (int j = 0; j < ncand; ++j) {  // broadcast reads of the <= 32 candidates
+    const unsigned long long other = scratch32[j];
     r += (other < mine) || (other == mine && j < lane);
   }
   unsigned hit = __ballot_sync(0xffffffffu, lane < ncand && r == kth - cnt_lo);
@@ -369,8 +410,11 @@ template <int ITEMS>
 __global__ void __launch_bounds__(256) k_gene_stats_reg(double* __restrict__ D, SegLayout L,
                                                         const int32_t* __restrict__ n_nodes_p,
                                                         double* __restrict__ mean, double* __restrict__ sxx,
-                                                        double* __restrict__ med, uint8_t* __restrict__ bad) {
+                                                        double* __restrict__ med, uint8_t* __restrict__ bad,
+                                                        QsCompactArgs Q) {
   __shared__ unsigned long long s_cand[8][32];
+  __shared__ unsigned char s_qtab[QSC_BINS];
+  if (Q.B16) qsc_load_table(Q, s_qtab);
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const long long w = (long long)blockIdx.x * 8 + wib;
   const int node = (int)(w / L.K), k = (int)(w % L.K);
@@ -394,6 +438,14 @@ __global__ void __launch_bounds__(256) k_gene_stats_reg(double* __restrict__ D, 
       nn += !isnan(v);
       nf |= !isfinite(v);
     }
+  }
+  if (Q.B16) {  // K3 S3: the bin ids of this segment (2 bytes per value), slot values appended to their lists
+    const unsigned short* bseg = Q.B16 + (size_t)node * L.npad + L.off[k];
+    unsigned bins[ITEMS];
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) bins[j] = lane + 32 * j < m ? (unsigned)bseg[lane + 32 * j] : QSC_NO_BIN;
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) qsc_visit(Q, s_qtab, bins[j], keys[j]);
   }
   s = warp_sum(s);
 #pragma unroll
@@ -1090,7 +1142,7 @@ __global__ void k_select_best(const unsigned long long* __restrict__ tot, const 
                               const unsigned long long* __restrict__ sig, int P, int host_adjust,
                               const double* __restrict__ cutoff, const int32_t* __restrict__ n_nodes,
                               const int32_t* __restrict__ err, double df1, double df2, long long* __restrict__ blk,
-                              int32_t* __restrict__ best) {
+                              long long* __restrict__ host_blk, int32_t* __restrict__ best) {
   if (blockIdx.x != 0) return;
   const int Pn = P > 0 ? P : 1;
   long long* tot_out = blk;
@@ -1099,6 +1151,7 @@ __global__ void k_select_best(const unsigned long long* __restrict__ tot, const 
   double* cut_out = reinterpret_cast<double*>(blk + 3 * Pn);
   int32_t* tail = reinterpret_cast<int32_t*>(blk + 4 * Pn);
   for (int p = threadIdx.x; p < P; p += blockDim.x) cut_out[p] = cutoff[p];
+  __syncthreads();  // thread 0 copies the whole block to the host below
   if (threadIdx.x != 0) return;
   int b = 0;
   long long bv = -1;
@@ -1120,6 +1173,11 @@ __global__ void k_select_best(const unsigned long long* __restrict__ tot, const 
   tail[3] = 0;
   reinterpret_cast<double*>(tail + 4)[0] = df1;
   reinterpret_cast<double*>(tail + 4)[1] = df2;
+  if (host_blk) {  // the same block straight into the caller's process (mapped pinned memory): no D2H copy afterwards
+    const int words = 4 * Pn + 4;
+    for (int i = 0; i < words; ++i) host_blk[i] = blk[i];  // (cut_out was written by other lanes: see below)
+    __threadfence_system();
+  }
 }
 
 // results -> caller's DEVICE buffers: every requested array in one launch (entry = blockIdx.y; src == nullptr: zeros)

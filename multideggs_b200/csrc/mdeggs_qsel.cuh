@@ -14,14 +14,14 @@
 //                   shared-memory privatised per persistent CTA; NaN skipped (na.rm = TRUE).
 //   S2 k_qs_scan    one CTA: prefix sums; each target rank -> (bin, rank inside the bin); the <= 2P distinct bins
 //                   become "slots" with exact candidate counts and offsets in the candidate buffer.
-//   S3 k_qs_compact the only extra read of D: values of slot bins are appended to their slot's list (staged per CTA in
-//                   shared memory: one global atomic per CTA and slot).  Slots too fat for the shared-memory finish
-//                   (tie groups) are not copied; their min/max key is tracked instead.
+//   S3 k_qs_compact reads the 2-byte bin id that the gather kept for every value (a quarter of D) and appends the values
+//                   of slot bins to their slot's list (staged per CTA in shared memory: one global atomic per CTA and
+//                   slot).  Slots too fat to copy (tie groups) are not copied; their min/max key is tracked instead.
 //   S4 k_qs_finish  one CTA per slot: radix select (12-bit digits below the common key prefix) of every target rank
 //                   over the slot's candidates in shared memory; a fat slot whose min == max (a pure tie group)
 //                   answers immediately, any other fat slot runs the same select straight over D (slow, correct).
 //                   The last CTA evaluates the type-7 interpolation  q = (1-h) x[lo] + h x[hi]  in R's order.
-// Versus a full 64-bit radix sort of the matrix: one extra read of D instead of ~16 read+write sweeps.
+// Versus a full 64-bit radix sort of the matrix: one read of a 2-byte side array instead of ~16 read+write sweeps of D.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -37,13 +37,15 @@ constexpr int QS_BINS = QS_CELLS * QS_SUB;
 constexpr int QS_SAMPLE = 1024;      // sample size (a single-CTA sort: kept small; it only shapes the bins)
 constexpr int QS_SAMPLE_MAX = QS_SAMPLE;
 constexpr int QS_SAMPLE_THREADS = 256;
-constexpr int QS_FIN_CAP = 16384;    // keys a finish CTA keeps in shared memory (128 KB); longer lists stay in L2
+constexpr int QS_FIN_CAP = 4096;     // keys a finish CTA keeps in shared memory (32 KB); longer lists stay in L2
 constexpr unsigned int QS_SLOT_MAX = 1u << 20;  // slots with more values are not compacted ("fat": tie groups)
 constexpr unsigned int QS_CAND_MAX = 8u << 20;  // candidate buffer, keys
-constexpr int QS_FIN_THREADS = 512;
+constexpr int QS_FIN_THREADS = 256;
+constexpr int QS_DIRECT = 256;        // keys ranked directly once a digit pass leaves this few
 constexpr int QS_SCAN_THREADS = 256;  // >= QS_MAX_T
 constexpr int QS_STAGE = 2048;       // per-CTA staging entries of the compaction pass
 
+constexpr int QS_NO_BIN = 0xffff;    // bin id of padding slots and NaN in the per-value bin array
 constexpr int QS_TAB = 4096;         // uniform value cells of the knot look-up table
 struct QsKnots {
   double base;                 // sample minimum; bins are evaluated on xf = (float)(x - base)
@@ -69,12 +71,8 @@ struct QsState {
   unsigned int slot_cursor[QS_MAX_T];  // append cursor
   int slot_fat[QS_MAX_T];              // 1: not compacted (too many values, or the buffer would overflow)
   unsigned long long slot_min[QS_MAX_T], slot_max[QS_MAX_T];  // fat slots: key range
-  // compaction pre-filter: bit i set <=> uniform value cell i (QS_FILTER_CELLS over the sample range) may hold a value
-  // of a slot bin; everything else is skipped without evaluating the bin map
-  unsigned int cand_bits[65536 / 32];
   QsKnots knots;
 };
-constexpr int QS_FILTER_CELLS = 65536;
 
 // monotone map value -> bin.  `kn` points at a shared-memory copy of the knots.  NaN never reaches here.
 __device__ __forceinline__ int qs_cell_search(const QsKnots* __restrict__ kn, float xf) {
@@ -99,9 +97,6 @@ __device__ __forceinline__ int qs_bin(const QsKnots* __restrict__ kn, double x) 
   return c * QS_SUB + sub;
 }
 
-__device__ __forceinline__ void qs_hist_add(const QsKnots* __restrict__ kn, unsigned int* __restrict__ s_hist, double v) {
-  if (!isnan(v)) atomicAdd(&s_hist[qs_bin(kn, v)], 1u);
-}
 __device__ __forceinline__ void qs_load_knots(QsKnots* __restrict__ dst, const QsState* __restrict__ st) {
   for (int i = threadIdx.x; i < (int)(sizeof(QsKnots) / 8); i += blockDim.x)
     reinterpret_cast<double*>(dst)[i] = reinterpret_cast<const double*>(&st->knots)[i];
@@ -256,8 +251,10 @@ __global__ void __launch_bounds__(256) k_gather_colmajor(const double* __restric
                                                          const int32_t* __restrict__ n_nodes_p,
                                                          const int32_t* __restrict__ src_of_pos, int npad, int n,
                                                          double* __restrict__ D, const QsState* __restrict__ st,
-                                                         unsigned int* __restrict__ hist) {
+                                                         unsigned int* __restrict__ hist,
+                                                         unsigned short* __restrict__ B16) {
   __shared__ double tile[32][33];
+  __shared__ unsigned short tile16[32][34];
   __shared__ QsKnots kn;
   __shared__ unsigned int s_hist[QS_BINS];
   const bool do_hist = hist != nullptr;
@@ -284,18 +281,24 @@ __global__ void __launch_bounds__(256) k_gather_colmajor(const double* __restric
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q) tile[ty + 8 * q][tx] = v[q];
-    __syncthreads();
-    if (do_hist) {
+    if (do_hist) {  // bin of every value: counted here, and kept (2 bytes per value) for the compaction pass
 #pragma unroll
-      for (int q = 0; q < 4; ++q)
-        if (ok[q]) qs_hist_add(&kn, s_hist, v[q]);
+      for (int q = 0; q < 4; ++q) {
+        const int b = (ok[q] && !isnan(v[q])) ? qs_bin(&kn, v[q]) : QS_NO_BIN;
+        tile16[ty + 8 * q][tx] = (unsigned short)b;
+        if (b != QS_NO_BIN) atomicAdd(&s_hist[b], 1u);
+      }
     }
+    __syncthreads();
     const int pos_w = pos0 + tx;
     const int s_w = pos_w < npad ? src_of_pos[pos_w] : -1;
 #pragma unroll
     for (int i = ty; i < 32; i += 8) {
       const int node = node0 + i;
-      if (node < n_nodes && s_w >= 0) D[(size_t)node * npad + pos_w] = tile[tx][i];
+      if (node < n_nodes && pos_w < npad) {
+        if (s_w >= 0) D[(size_t)node * npad + pos_w] = tile[tx][i];
+        if (do_hist) B16[(size_t)node * npad + pos_w] = s_w >= 0 ? tile16[tx][i] : (unsigned short)QS_NO_BIN;
+      }
     }
     __syncthreads();
   }
@@ -307,7 +310,8 @@ __global__ void __launch_bounds__(256) k_gather_rowmajor(const double* __restric
                                                          const int32_t* __restrict__ n_nodes_p,
                                                          const int32_t* __restrict__ src_of_pos, int npad, int n,
                                                          double* __restrict__ D, const QsState* __restrict__ st,
-                                                         unsigned int* __restrict__ hist) {
+                                                         unsigned int* __restrict__ hist,
+                                                         unsigned short* __restrict__ B16) {
   __shared__ QsKnots kn;
   __shared__ unsigned int s_hist[QS_BINS];
   const bool do_hist = hist != nullptr;
@@ -321,11 +325,16 @@ __global__ void __launch_bounds__(256) k_gather_rowmajor(const double* __restric
     const int64_t row = rowlist[node] - row_off;
     for (int pos = threadIdx.x; pos < npad; pos += blockDim.x) {
       const int s = src_of_pos[pos];
+      int b = QS_NO_BIN;
       if (s >= 0) {
         const double v = __ldg(assay + row * ld + s);
-        if (do_hist) qs_hist_add(&kn, s_hist, v);
+        if (do_hist && !isnan(v)) {
+          b = qs_bin(&kn, v);
+          atomicAdd(&s_hist[b], 1u);
+        }
         D[(size_t)node * npad + pos] = v;
       }
+      if (do_hist) B16[(size_t)node * npad + pos] = (unsigned short)b;
     }
   }
   __syncthreads();
@@ -433,39 +442,15 @@ __global__ void __launch_bounds__(QS_SCAN_THREADS) k_qs_scan(QsState* __restrict
       if (!fat) off += c;
     }
   }
-  // compaction pre-filter bitmap (cum[] is no longer needed: its storage is reused)
-  unsigned int* bits = reinterpret_cast<unsigned int*>(cum);
-  for (int i = tid; i < QS_FILTER_CELLS / 32; i += QS_SCAN_THREADS) bits[i] = 0u;
-  __syncthreads();
-  if (tid < T && s_first[tid]) {
-    const int b = s_tbin[tid], c = b / QS_SUB, sub = b % QS_SUB;
-    const float k0 = st->knots.knot[c], k1 = st->knots.knot[c + 1], sc = st->knots.scale[c];
-    const float inv16 = st->knots.inv_w * (float)(QS_FILTER_CELLS / QS_TAB);
-    float lo = k0, hi = k1;
-    if (sc > 0.f) {
-      if (sub > 0) lo = k0 + (float)sub / sc;
-      if (sub < QS_SUB - 1) hi = k0 + (float)(sub + 1) / sc;
-    }
-    int i0 = (c == 0 && sub == 0) ? 0 : qs_tab_index(lo, inv16, QS_FILTER_CELLS) - 2;
-    int i1 = (c == QS_CELLS - 1 && (sub == QS_SUB - 1 || !(sc > 0.f))) ? QS_FILTER_CELLS - 1
-                                                                       : qs_tab_index(hi, inv16, QS_FILTER_CELLS) + 2;
-    if (!(inv16 > 0.f)) {
-      i0 = 0;
-      i1 = QS_FILTER_CELLS - 1;
-    }
-    i0 = i0 < 0 ? 0 : i0;
-    i1 = i1 > QS_FILTER_CELLS - 1 ? QS_FILTER_CELLS - 1 : i1;
-    for (int i = i0; i <= i1; ++i) atomicOr(&bits[i >> 5], 1u << (i & 31));
-  }
-  __syncthreads();
-  for (int i = tid; i < QS_FILTER_CELLS / 32; i += QS_SCAN_THREADS) st->cand_bits[i] = bits[i];
 }
 
 // ---- S3 ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_qs_compact(const double* __restrict__ D, const int32_t* __restrict__ src_of_pos,
-                                                    int npad, const int32_t* __restrict__ n_nodes_p,
-                                                    QsState* __restrict__ st, unsigned long long* __restrict__ cand) {
-  __shared__ QsKnots kn;
+// Reads the 2-byte bin id of every value (written by the gather) instead of re-evaluating the bin map on D: 16.8 MB
+// instead of 67 MB on config 3, a table look-up per value, and D itself is touched only for the candidates.
+__global__ void __launch_bounds__(256) k_qs_compact(const double* __restrict__ D,
+                                                    const unsigned short* __restrict__ B16, int npad,
+                                                    const int32_t* __restrict__ n_nodes_p, QsState* __restrict__ st,
+                                                    unsigned long long* __restrict__ cand) {
   __shared__ unsigned char s_slot_of_bin[QS_BINS];
   __shared__ unsigned long long s_key[QS_STAGE];
   __shared__ unsigned char s_stage_slot[QS_STAGE];
@@ -473,11 +458,6 @@ __global__ void __launch_bounds__(256) k_qs_compact(const double* __restrict__ D
   __shared__ unsigned int s_cnt[QS_MAX_T], s_base[QS_MAX_T], s_fill[QS_MAX_T];
   __shared__ unsigned long long s_min[QS_MAX_T], s_max[QS_MAX_T];
   __shared__ unsigned char s_fat[QS_MAX_T];
-  extern __shared__ unsigned int s_bits[];  // QS_FILTER_CELLS / 32 words
-  qs_load_knots(&kn, st);
-  for (int i = threadIdx.x; i < QS_FILTER_CELLS / 32; i += blockDim.x) s_bits[i] = st->cand_bits[i];
-  const float inv16 = st->knots.inv_w * (float)(QS_FILTER_CELLS / QS_TAB);
-  const double base = st->knots.base;
   const int U = st->U;
   for (int i = threadIdx.x; i < QS_BINS; i += blockDim.x) s_slot_of_bin[i] = 0xff;
   if (threadIdx.x == 0) s_n = 0u;
@@ -491,16 +471,11 @@ __global__ void __launch_bounds__(256) k_qs_compact(const double* __restrict__ D
   for (int i = threadIdx.x; i < U; i += blockDim.x) s_slot_of_bin[st->slot_bin[i]] = (unsigned char)i;
   __syncthreads();
 
-  const int n_nodes = *n_nodes_p;
-  const int half = npad >> 1;  // double2 units per row (npad is a multiple of 4)
-
-  auto visit = [&](double v) {
-    if (isnan(v)) return;  // na.rm = TRUE
-    const int fi = qs_tab_index((float)(v - base), inv16, QS_FILTER_CELLS);
-    if (!((s_bits[fi >> 5] >> (fi & 31)) & 1u)) return;  // ~99% of the values leave here
-    const unsigned sl = s_slot_of_bin[qs_bin(&kn, v)];
-    if (sl == 0xff) return;
-    const unsigned long long k = dkey(v);
+  auto visit = [&](unsigned b, long long idx) {
+    if (b == (unsigned)QS_NO_BIN) return;
+    const unsigned sl = s_slot_of_bin[b];
+    if (sl == 0xff) return;  // ~99 % of the values leave here
+    const unsigned long long k = dkey(D[idx]);
     if (s_fat[sl]) {  // not copied: only the key range of the bin is needed
       if (k < s_min[sl]) atomicMin(&s_min[sl], k);
       if (k > s_max[sl]) atomicMax(&s_max[sl], k);
@@ -533,21 +508,24 @@ __global__ void __launch_bounds__(256) k_qs_compact(const double* __restrict__ D
     __syncthreads();
   };
 
-  // each CTA takes 4 rows at a time so that every thread has 4 independent 16-byte loads in flight
-  for (int row0 = blockIdx.x * 4; row0 < n_nodes; row0 += gridDim.x * 4) {
-    for (int c = threadIdx.x; c < half; c += blockDim.x) {
-      double2 v[4];
+  // 4 bin ids (8 bytes) per load, 4 loads in flight per thread; the flat array has n_nodes * npad entries (npad % 4 == 0)
+  const long long groups = (long long)(*n_nodes_p) * npad / 4;
+  const uint2* __restrict__ B4 = reinterpret_cast<const uint2*>(B16);
+  const long long chunk = (long long)blockDim.x * 4;
+  for (long long g0 = (long long)blockIdx.x * chunk; g0 < groups; g0 += (long long)gridDim.x * chunk) {
+    uint2 w[4];
 #pragma unroll
-      for (int r = 0; r < 4; ++r)
-        v[r] = (row0 + r < n_nodes) ? __ldg(reinterpret_cast<const double2*>(D + (size_t)(row0 + r) * npad) + c)
-                                    : make_double2(0.0, 0.0);
-      const bool ok0 = src_of_pos[2 * c] >= 0, ok1 = src_of_pos[2 * c + 1] >= 0;  // padding slots are skipped
+    for (int u = 0; u < 4; ++u) {
+      const long long g = g0 + u * blockDim.x + threadIdx.x;
+      w[u] = g < groups ? __ldg(B4 + g) : make_uint2(0xffffffffu, 0xffffffffu);
+    }
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        if (row0 + r >= n_nodes) break;
-        if (ok0) visit(v[r].x);
-        if (ok1) visit(v[r].y);
-      }
+    for (int u = 0; u < 4; ++u) {
+      const long long idx = (g0 + u * blockDim.x + threadIdx.x) * 4;
+      visit(w[u].x & 0xffffu, idx);
+      visit(w[u].x >> 16, idx + 1);
+      visit(w[u].y & 0xffffu, idx + 2);
+      visit(w[u].y >> 16, idx + 3);
     }
     __syncthreads();
     if (s_n >= (unsigned)QS_STAGE / 2) flush();  // uniform: s_n is read after the barrier
@@ -569,7 +547,9 @@ __device__ __forceinline__ unsigned long long qs_digit_select(ForEach&& for_each
                                                               unsigned long long kmax, long long rank,
                                                               unsigned int* hist /* [4096] shared */,
                                                               long long* s_scan /* [blockDim.x] shared */,
-                                                              unsigned long long* s_pfx, long long* s_rank) {
+                                                              unsigned long long* s_pfx, long long* s_rank,
+                                                              long long* s_direct /* [2] shared */,
+                                                              unsigned long long* s_list /* [QS_DIRECT] shared */) {
   const int tid = threadIdx.x, nthr = blockDim.x;
   if (kmin == kmax) return kmin;
   const int top = 63 - __clzll((long long)(kmin ^ kmax));  // highest differing bit
@@ -629,9 +609,34 @@ __device__ __forceinline__ unsigned long long qs_digit_select(ForEach&& for_each
     if (found >= 0) {  // exactly one thread
       *s_pfx = (pfx << width) | (unsigned long long)found;
       *s_rank = r - found_base;
+      s_direct[0] = (long long)hist[found];
     }
     __syncthreads();
     remaining -= width;
+    // few keys left under the new prefix (the usual case after ONE pass: a slot holds a few thousand keys, the
+    // histogram 4,096 bins): collect them and rank them directly instead of further digit passes
+    if (remaining > 0 && s_direct[0] <= (long long)QS_DIRECT) {
+      const unsigned long long npfx = *s_pfx;
+      const long long rr = *s_rank;
+      if (tid == 0) s_direct[1] = 0;
+      __syncthreads();
+      for_each([&](unsigned long long k) {
+        if ((k >> remaining) == npfx) {
+          const long long at = (long long)atomicAdd(reinterpret_cast<unsigned long long*>(&s_direct[1]), 1ull);
+          if (at < QS_DIRECT) s_list[at] = k;
+        }
+      });
+      __syncthreads();
+      const int cnt = (int)s_direct[1];
+      for (int t = tid; t < cnt; t += nthr) {
+        const unsigned long long mine = s_list[t];
+        int rk = 0;
+        for (int u = 0; u < cnt; ++u) rk += (s_list[u] < mine) || (s_list[u] == mine && u < t);
+        if (rk == (int)rr) *s_pfx = mine;
+      }
+      __syncthreads();
+      remaining = 0;
+    }
   }
   const unsigned long long res = *s_pfx;
   __syncthreads();
@@ -639,18 +644,19 @@ __device__ __forceinline__ unsigned long long qs_digit_select(ForEach&& for_each
 }
 
 __global__ void __launch_bounds__(QS_FIN_THREADS) k_qs_finish(const double* __restrict__ D,
-                                                             const int32_t* __restrict__ src_of_pos, int npad,
+                                                             const unsigned short* __restrict__ B16, int npad,
                                                              const int32_t* __restrict__ n_nodes_p,
                                                              QsState* __restrict__ st,
                                                              const unsigned long long* __restrict__ cand,
                                                              const double* __restrict__ pct, int P,
                                                              double* __restrict__ cutoff) {
   extern __shared__ unsigned long long fk[];  // QS_FIN_CAP keys
-  __shared__ QsKnots kn;
   __shared__ unsigned int hist[4096];
   __shared__ long long s_scan[QS_FIN_THREADS];
   __shared__ unsigned long long s_pfx, s_min, s_max;
   __shared__ long long s_rank;
+  __shared__ long long s_direct[2];
+  __shared__ unsigned long long s_list[QS_DIRECT];
   __shared__ int s_last;
   const int tid = threadIdx.x, s = blockIdx.x;
   const int T = 2 * P;
@@ -693,7 +699,7 @@ __global__ void __launch_bounds__(QS_FIN_THREADS) k_qs_finish(const double* __re
     };
     for (int t = 0; t < T; ++t) {
       if (st->t_slot[t] != s) continue;  // uniform across the CTA
-      const unsigned long long key = c > 0 ? qs_digit_select(for_each_cand, kmin, kmax, st->t_rank[t], hist, s_scan, &s_pfx, &s_rank) : ~0ull;
+      const unsigned long long key = c > 0 ? qs_digit_select(for_each_cand, kmin, kmax, st->t_rank[t], hist, s_scan, &s_pfx, &s_rank, s_direct, s_list) : ~0ull;
       if (tid == 0) st->t_key[t] = key;
     }
   } else if (st->slot_min[s] == st->slot_max[s]) {
@@ -701,25 +707,16 @@ __global__ void __launch_bounds__(QS_FIN_THREADS) k_qs_finish(const double* __re
     for (int t = tid; t < T; t += QS_FIN_THREADS)
       if (st->t_slot[t] == s) st->t_key[t] = st->slot_min[s];
   } else {
-    // slow path: the same select straight over D, filtered by the bin map
-    qs_load_knots(&kn, st);
-    __syncthreads();
-    const int my_bin = st->slot_bin[s];
-    const int n_nodes = *n_nodes_p;
-    const int half = npad >> 1;
+    // slow path: the same select straight over D, filtered by the bin ids
+    const unsigned my_bin = (unsigned)st->slot_bin[s];
+    const long long total = (long long)(*n_nodes_p) * npad;
     auto for_each_in_bin = [&](auto&& fn) {
-      for (int row = 0; row < n_nodes; ++row) {
-        const double2* R2 = reinterpret_cast<const double2*>(D + (size_t)row * npad);
-        for (int cc = tid; cc < half; cc += QS_FIN_THREADS) {
-          const double2 v = __ldg(R2 + cc);
-          if (src_of_pos[2 * cc] >= 0 && !isnan(v.x) && qs_bin(&kn, v.x) == my_bin) fn(dkey(v.x));
-          if (src_of_pos[2 * cc + 1] >= 0 && !isnan(v.y) && qs_bin(&kn, v.y) == my_bin) fn(dkey(v.y));
-        }
-      }
+      for (long long i = tid; i < total; i += QS_FIN_THREADS)
+        if (B16[i] == my_bin) fn(dkey(D[i]));
     };
     for (int t = 0; t < T; ++t) {
       if (st->t_slot[t] != s) continue;  // uniform across the CTA
-      const unsigned long long key = qs_digit_select(for_each_in_bin, st->slot_min[s], st->slot_max[s], st->t_rank[t], hist, s_scan, &s_pfx, &s_rank);
+      const unsigned long long key = qs_digit_select(for_each_in_bin, st->slot_min[s], st->slot_max[s], st->t_rank[t], hist, s_scan, &s_pfx, &s_rank, s_direct, s_list);
       if (tid == 0) st->t_key[t] = key;
     }
   }
