@@ -1143,41 +1143,48 @@ __global__ void k_select_best(const unsigned long long* __restrict__ tot, const 
                               const double* __restrict__ cutoff, const int32_t* __restrict__ n_nodes,
                               const int32_t* __restrict__ err, double df1, double df2, long long* __restrict__ blk,
                               long long* __restrict__ host_blk, int32_t* __restrict__ best) {
-  if (blockIdx.x != 0) return;
+  // one warp: lanes stride over the percentiles, the first maximum is a shuffle arg-max; every word of the block is
+  // written to device memory and (host_blk: mapped pinned memory) straight into the caller's process by its lane
+  if (blockIdx.x != 0 || threadIdx.x >= 32) return;
+  const int lane = threadIdx.x;
   const int Pn = P > 0 ? P : 1;
-  long long* tot_out = blk;
-  long long* sig_out = blk + Pn;
-  long long* fail_out = blk + 2 * Pn;
-  double* cut_out = reinterpret_cast<double*>(blk + 3 * Pn);
-  int32_t* tail = reinterpret_cast<int32_t*>(blk + 4 * Pn);
-  for (int p = threadIdx.x; p < P; p += blockDim.x) cut_out[p] = cutoff[p];
-  __syncthreads();  // thread 0 copies the whole block to the host below
-  if (threadIdx.x != 0) return;
-  int b = 0;
+  auto put = [&](int word, long long v) {
+    blk[word] = v;
+    if (host_blk) host_blk[word] = v;
+  };
   long long bv = -1;
-  for (int p = 0; p < P; ++p) {
-    long long t = (long long)tot[p], s = t > 0 ? (long long)sig[p] : -1;
+  int bp = 0x7fffffff;
+  for (int p = lane; p < P; p += 32) {
+    const long long t = (long long)tot[p], f = (long long)fail[p];
+    long long s = t > 0 ? (long long)sig[p] : -1;
     if (host_adjust) s = -1;
-    tot_out[p] = t;
-    sig_out[p] = s;
-    fail_out[p] = (long long)fail[p];
-    if (!host_adjust && t > 0 && fail[p] == 0 && s > bv) {
+    put(p, t);
+    put(Pn + p, s);
+    put(2 * Pn + p, f);
+    put(3 * Pn + p, __double_as_longlong(cutoff[p]));
+    if (!host_adjust && t > 0 && f == 0 && s > bv) {  // p ascending per lane: keeps the lane's first maximum
       bv = s;
-      b = p + 1;
+      bp = p;
     }
   }
-  *best = b;
-  tail[0] = b;
-  tail[1] = *n_nodes;
-  tail[2] = *err;
-  tail[3] = 0;
-  reinterpret_cast<double*>(tail + 4)[0] = df1;
-  reinterpret_cast<double*>(tail + 4)[1] = df2;
-  if (host_blk) {  // the same block straight into the caller's process (mapped pinned memory): no D2H copy afterwards
-    const int words = 4 * Pn + 4;
-    for (int i = 0; i < words; ++i) host_blk[i] = blk[i];  // (cut_out was written by other lanes: see below)
-    __threadfence_system();
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {  // maximum count, ties -> smallest percentile (which.max: first maximum)
+    const long long ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const int op = __shfl_xor_sync(0xffffffffu, bp, o);
+    if (ov > bv || (ov == bv && op < bp)) {
+      bv = ov;
+      bp = op;
+    }
   }
+  const int b = bv >= 0 ? bp + 1 : 0;
+  if (lane == 0) {
+    *best = b;
+    put(4 * Pn, (long long)(unsigned int)b | ((long long)(unsigned int)*n_nodes << 32));      // i32 best, nn
+    put(4 * Pn + 1, (long long)(unsigned int)*err);                                            // i32 err, 0
+    put(4 * Pn + 2, __double_as_longlong(df1));
+    put(4 * Pn + 3, __double_as_longlong(df2));
+  }
+  if (host_blk) __threadfence_system();
 }
 
 // results -> caller's DEVICE buffers: every requested array in one launch (entry = blockIdx.y; src == nullptr: zeros)
