@@ -184,43 +184,46 @@ __device__ __forceinline__ void qsc_visit(const QsCompactArgs& Q, const unsigned
 //   mean, centred Sxx — the sufficient statistics of fit_lm_interaction / aov shared by every edge that
 //   touches the gene (core_functions.R:1058-1074, 966-968)
 // One CTA per gene, the row staged in shared memory; one warp per category. The exact median is an order
-// statistic found by 64-step bisection on the sortable key (no sort, no scratch).
+// statistic found by bisection in key space (no sort, no scratch).
 // ------------------------------------------------------------------------------------------------
 // Exact k-th smallest (0-based) of m keys held behind `key_at(i)`, one warp.  Keys are known to lie in
 // [kmin, kmax] except NaN keys (== ~0), which sit above every valid key and are never selected (kth < n_valid).
-// Bisection on the key bits starts below the common prefix of kmin/kmax and stops as soon as the candidate
-// interval holds <= 32 keys; those are spread one per lane and ranked with 32 shuffles.  Typical cost for a
-// few hundred values: ~6 counting passes instead of 64.
+// Bisection in KEY space: [lo, hi) always holds the answer, cnt_lo / cnt_hi = number of keys below lo / hi; it
+// starts from the optional guess bracket [g_lo, g_hi], halves the key interval until <= 32 keys remain and ranks
+// those from shared memory.  At most ~64 counting passes whatever the data; a handful for anything well spread.
 template <class KeyAt>
 __device__ __forceinline__ unsigned long long warp_select(KeyAt key_at, int m, int kth, unsigned long long kmin,
                                                           unsigned long long kmax, int n_valid,
-                                                          unsigned long long* scratch32, int lane) {
+                                                          unsigned long long* scratch32, int lane,
+                                                          unsigned long long g_lo = 0ull,
+                                                          unsigned long long g_hi = 0ull) {
   if (kmin == kmax) return kmin;
-  const int top = 63 - __clzll((long long)(kmin ^ kmax));
-  unsigned long long prefix = (top == 63) ? 0ull : (kmin >> (top + 1)) << (top + 1);
-  int cnt_lo = 0, cnt_hi = n_valid;  // keys < prefix, keys < prefix + 2^(bit+1)
-  int bit = top;
-  for (; bit >= 0 && cnt_hi - cnt_lo > 32; --bit) {
-    const unsigned long long cand = prefix | (1ull << bit);
+  unsigned long long lo = kmin, hi = kmax + 1ull;  // kmax is a valid key, hence < ~0
+  int cnt_lo = 0, cnt_hi = n_valid;
+  auto narrow = [&](unsigned long long pivot) {
+    if (pivot <= lo || pivot >= hi) return;
     int c = 0;
-    for (int i = lane; i < m; i += 32) c += (key_at(i) < cand);
+    for (int i = lane; i < m; i += 32) c += (key_at(i) < pivot);
     c = __reduce_add_sync(0xffffffffu, c);
     if (c <= kth) {
-      prefix = cand;
+      lo = pivot;
       cnt_lo = c;
     } else {
+      hi = pivot;
       cnt_hi = c;
     }
+  };
+  if (g_hi > g_lo) {
+    narrow(g_lo);
+    narrow(g_hi);
   }
-  if (bit < 0) return prefix;  // > 32 identical keys: the prefix is the key itself
-  // candidates: prefix <= key < prefix + 2^(bit+1)   (bit+1 == 64 cannot happen here: top < 64 and bit <= top)
-  const unsigned long long span = (bit == 63) ? ~0ull : ((1ull << (bit + 1)) - 1ull);
-  const unsigned long long hi_incl = prefix | span;
+  while (cnt_hi - cnt_lo > 32 && hi - lo > 1ull) narrow(lo + ((hi - lo) >> 1));
+  if (cnt_hi - cnt_lo > 32) return lo;  // hi == lo + 1: more than 32 keys equal to lo
   int base = 0;
   for (int i0 = 0; i0 < m; i0 += 32) {
     int i = i0 + lane;
     unsigned long long k = i < m ? key_at(i) : ~0ull;
-    bool in = i < m && k >= prefix && k <= hi_incl && k != ~0ull;
+    bool in = i < m && k >= lo && k < hi;
     unsigned mask = __ballot_sync(0xffffffffu, in);
     if (in) scratch32[base + __popc(mask & ((1u << lane) - 1u))] = k;
     base += __popc(mask);
