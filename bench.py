@@ -55,7 +55,8 @@ def _peaks() -> dict:
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region: NVML polled every 2 ms from a thread (the timed
+    region of the value leg is ~10 ms, too short for nvidia-smi's 100 ms loop, which is only the fallback)."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -63,8 +64,21 @@ class ClockSampler:
 
     def __init__(self, index: int):
         self.index, self.rows, self.proc = index, [], None
+        self.nvml, self.handle, self.samples, self.stop_flag = None, None, [], False
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].isdigit() else self.index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
@@ -74,11 +88,36 @@ class ClockSampler:
         except OSError:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        while not self.stop_flag:
+            try:
+                sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+                rs = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                self.samples.append((sm, mx, rs))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self) -> dict:
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.t.join(timeout=1)
+            n = self.nvml
+            names = {"hw_slowdown": n.nvmlClocksEventReasonHwSlowdown,
+                     "hw_thermal_slowdown": n.nvmlClocksEventReasonHwThermalSlowdown,
+                     "sw_thermal_slowdown": n.nvmlClocksEventReasonSwThermalSlowdown,
+                     "sw_power_cap": n.nvmlClocksEventReasonSwPowerCap}
+            reasons = sorted(nm for nm, bit in names.items() if any(rs & bit for _, _, rs in self.samples))
+            sm = [x[0] for x in self.samples]
+            return {"sm_mhz": float(np.median(sm)) if sm else None,
+                    "sm_max_mhz": float(max(x[1] for x in self.samples)) if sm else None, "reasons": reasons,
+                    "samples": len(sm), "source": "NVML polled every 2 ms during the timed region"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -100,7 +139,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 100"}
 
 
 def _workload(name: str, seed_offset: int = 0):
