@@ -341,6 +341,8 @@ def run_cuda(args) -> None:
 
     # ---- e2e: host buffers through the C ABI ----
     hprob, hres, hkeep, h2d, d2h = _host_problem(torch, prob)
+    if os.environ.get("MDEGGS_ZERO_COPY"):
+        eng.set_option("zero_copy", int(os.environ["MDEGGS_ZERO_COPY"]))
     for _ in range(args.warmup):
         eng.run_omic_raw(hprob, hres)
     dist_sync()

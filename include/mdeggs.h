@@ -163,6 +163,8 @@ int mdeggs_last_stats(const mdeggs_ctx* ctx, mdeggs_stats* out);
  * "sort_path" (-1 = K8 orders the edges through p-value buckets up to 4M edges and with a CUB radix sort beyond
  * [default], 0 = always the radix sort, 1 = buckets whenever possible);
  * "trace" (1 = print the end time of every launch of the next calls to stderr; implies eager launches);
+ * "zero_copy" (1 = a pinned host assay is read by the gather kernel straight over PCIe instead of being copied first;
+ * measured 2 % slower than the DMA copy on this pool's boxes, hence off by default);
  * "rsel_cap" (tests: cap the quantile candidate list so that the overflow path is exercised; 0 = default). */
 int mdeggs_set_option(mdeggs_ctx* ctx, const char* name, int64_t value);
 const char* mdeggs_last_error(const mdeggs_ctx* ctx);

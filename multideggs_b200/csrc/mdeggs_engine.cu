@@ -127,6 +127,8 @@ struct mdeggs_ctx {
   int64_t graph_launches = 0;
   int64_t rsel_cap_override = 0;  // option "rsel_cap": shrink the candidate list to exercise the overflow path (tests)
   int fit_path_override = -1;  // -1 auto, 0 force streaming, 1 force dense (MDEGGS_FIT_PATH, tests)
+  bool last_zc = false;        // the last call read its assay through zero copy
+  int zero_copy = 0;           // option "zero_copy": pinned host assays are read by the gather straight over PCIe
   int sort_path_override = -1; // -1 auto, 0 force the CUB radix sort, 1 force the bucket ordering (option "sort_path")
   // MDEGGS_TRACE=1 / option "trace": an event after every eager launch, timeline printed to stderr after the call
   int trace = 0;
@@ -403,7 +405,33 @@ int stage_inputs(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const Host
                                                                    : (size_t)in->ld * (size_t)(G - 1) + (size_t)n;
   const double* d_assay;
   const int32_t *d_from, *d_to;
-  if (in->mem == MDEGGS_MEM_HOST) {
+  bool zc = false;
+  if (in->mem == MDEGGS_MEM_HOST && ctx->zero_copy) {  // is the assay in pinned (device-mapped) host memory?
+    cudaPointerAttributes pa;
+    if (cudaPointerGetAttributes(&pa, in->assay) == cudaSuccess && pa.type == cudaMemoryTypeHost && pa.devicePointer)
+      zc = true;
+    else
+      cudaGetLastError();
+  }
+  ctx->last_zc = zc;
+  if (zc) {
+    // zero copy: the gather (and the quantile sample) read the caller's pinned matrix over PCIe themselves; only the
+    // node rows are touched, the transfer overlaps the transposition and no staging copy exists
+    s.row_off = 0;
+    s.ld_eff = in->ld;
+    CU(s.from.ensure((size_t)E * 4 + 4));
+    CU(s.to.ensure((size_t)E * 4 + 4));
+    if (E > 0) {
+      CU(cudaMemcpyAsync(s.from.p, in->from, (size_t)E * 4, cudaMemcpyHostToDevice, s.s_main));
+      CU(cudaMemcpyAsync(s.to.p, in->to, (size_t)E * 4, cudaMemcpyHostToDevice, s.s_main));
+    }
+    ctx->stats.h2d_bytes += (int64_t)((size_t)E * 8);
+    d_assay = in->assay;
+    d_from = s.from.as<int32_t>();
+    d_to = s.to.as<int32_t>();
+    s.assay.release();
+    s.assay.p = (void*)d_assay;  // borrowed (cap stays 0)
+  } else if (in->mem == MDEGGS_MEM_HOST) {
     // Only rows that are network nodes are ever read (core_functions.R:336). For small edge lists the host finds
     // the node-row RANGE [r_lo, r_hi] in one pass over from/to and only that band crosses PCIe (config 3: the
     // 8,405 node genes are the first rows of 20,000 -> 67 MB instead of 160 MB).
@@ -1494,6 +1522,7 @@ int mdeggs_run_omic(mdeggs_ctx* ctx, const mdeggs_problem* in, mdeggs_result* ou
   (void)replayed;
   mdeggs_stats& st = ctx->stats;
   st.n_nodes = n_nodes;
+  if (ctx->last_zc) st.h2d_bytes += (int64_t)n_nodes * in->n * 8;  // node rows read over PCIe by the gather kernel
   st.unique_fits = in->E;
   st.kernel_launches = ctx->launches;
   st.n_ranks = s0.world;
@@ -1536,6 +1565,11 @@ int mdeggs_set_option(mdeggs_ctx* ctx, const char* name, int64_t value) {
   }
   if (!strcmp(name, "rsel_cap")) {
     ctx->rsel_cap_override = value;
+    ctx->key_valid = false;
+    return MDEGGS_OK;
+  }
+  if (!strcmp(name, "zero_copy")) {
+    ctx->zero_copy = (int)value;
     ctx->key_valid = false;
     return MDEGGS_OK;
   }
