@@ -303,7 +303,7 @@ void launch_fit_stream(mdeggs_ctx* ctx, Shard& s, const SegLayout& L, int64_t e_
   int64_t ne = e_hi - e_lo;
   if (ne <= 0) return;
   int64_t want_blocks = (ne + 7) / 8;  // 8 warps per CTA, one edge per warp per trip
-  int64_t cap = 148 * 8 * 16;          // at most 16 waves of 8 CTAs/SM; warps loop beyond that
+  int64_t cap = 148 * 8 * 16;          // at most 16 waves of 8 CTAs/SM (64 resident warps/SM); warps loop beyond that
   unsigned grid = (unsigned)(want_blocks < cap ? want_blocks : cap);
   LAUNCH(k_fit_stream<K>, grid, 256, 0, s.s_main, s.D.as<double>(), L, s.ea.as<int32_t>(), s.eb.as<int32_t>(),
          s.mean.as<double>(), s.bad.as<uint8_t>(), e_lo, e_hi, s.sxy.as<double>(),

@@ -532,6 +532,14 @@ __global__ void __launch_bounds__(256) k_gene_stats_reg(double* __restrict__ D, 
 //   K == 2: t = (slope_2 - slope_1) / sqrt(RSS_full/(n-4) * (1/Sxx_1 + 1/Sxx_2))
 //   K >= 3: RSS_add = sum Syy - (sum Sxy)^2 / sum Sxx;  F = ((RSS_add-RSS_full)/(K-1)) / (RSS_full/(n-2K))
 // ------------------------------------------------------------------------------------------------
+// k_fit_stream build parameters (tools/fit_variants.sh measures alternatives): resident CTAs per SM and unroll depth
+#ifndef FIT_CTAS
+#define FIT_CTAS 8
+#endif
+#ifndef FIT_UNROLL
+#define FIT_UNROLL 1
+#endif
+constexpr int kFitUnroll = FIT_UNROLL;
 template <int K>
 struct PairMoments {
   double sxy[K];
@@ -596,7 +604,7 @@ __device__ __forceinline__ void finish_pair(const SegLayout& L, const double* __
 // (divisions, sqrt) and the tail probability are done one THREAD per edge by k_finish, so no warp ever idles 31
 // lanes behind a scalar epilogue.
 template <int K>
-__global__ void __launch_bounds__(256, 4) k_fit_stream(const double* __restrict__ D, SegLayout L,
+__global__ void __launch_bounds__(256, FIT_CTAS) k_fit_stream(const double* __restrict__ D, SegLayout L,
                                                        const int32_t* __restrict__ ea,
                                                        const int32_t* __restrict__ eb,
                                                        const double* __restrict__ mean,
@@ -612,22 +620,20 @@ __global__ void __launch_bounds__(256, 4) k_fit_stream(const double* __restrict_
     const int a = ea[e], b = eb[e];
     const double2* __restrict__ pa = reinterpret_cast<const double2*>(D + (size_t)a * L.npad);
     const double2* __restrict__ pb = reinterpret_cast<const double2*>(D + (size_t)b * L.npad);
-    double ma[K], mb[K], acc[K];
+    double acc[K];
+    // all K segments are streamed back to back; the K warp reductions come after the last load has been issued.
+    // Few live registers on purpose: the kernel is bound by L2 latency, and what hides it is resident warps (measured:
+    // 64 warps/SM at 32 registers beat 32 warps/SM at 64 registers with deeper unrolling by 12 %).
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-      ma[k] = mean[(size_t)a * K + k];
-      mb[k] = mean[(size_t)b * K + k];
-    }
-    // all K segments are streamed back to back; the K warp reductions come after the last load has been issued
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
+      const double mak = mean[(size_t)a * K + k], mbk = mean[(size_t)b * K + k];
       const int beg = L.off[k] >> 1, end = L.off[k + 1] >> 1;
       double acc0 = 0.0, acc1 = 0.0;
-#pragma unroll 4
+#pragma unroll kFitUnroll
       for (int i = beg + lane; i < end; i += 32) {
         const double2 x = __ldg(pa + i), y = __ldg(pb + i);
-        acc0 = fma(x.x - ma[k], y.x - mb[k], acc0);
-        acc1 = fma(x.y - ma[k], y.y - mb[k], acc1);
+        acc0 = fma(x.x - mak, y.x - mbk, acc0);
+        acc1 = fma(x.y - mak, y.y - mbk, acc1);
       }
       acc[k] = acc0 + acc1;
     }
