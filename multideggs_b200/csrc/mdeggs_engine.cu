@@ -621,7 +621,7 @@ int run_shard_main(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
   if (do_q) CU(cudaStreamWaitEvent(s.s_main, s.ev_sample, 0));  // knots ready
   if (n_nodes > 0) {
     unsigned int* d_hist = do_q ? s.rsel_hist.as<unsigned int>() : nullptr;
-    const unsigned grid = 148 * 4;  // persistent CTAs: one histogram flush each
+    const unsigned grid = 148 * 6;  // persistent CTAs (6 fit an SM's shared memory): one histogram flush each
     if (in->layout == MDEGGS_LAYOUT_COLMAJOR) {
       LAUNCH(k_gather_colmajor, grid, 256, 0, s.s_main, s.assay.as<double>(), s.ld_eff, s.row_off, s.rowlist.as<int32_t>(), d_nn,
              s.src_of_pos.as<int32_t>(), L.npad, n, s.D.as<double>(), d_st, d_hist, s.B16.as<unsigned short>());
