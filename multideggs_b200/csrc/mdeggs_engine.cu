@@ -67,7 +67,7 @@ struct Shard {
   int device = 0, rank = 0, world = 1;
   cudaStream_t s_main = nullptr, s_sort = nullptr;
   cudaEvent_t ev[EV_COUNT] = {};
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_sample = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_sample = nullptr, ev_cf = nullptr;
   nccl_comm_t comm = nullptr;
   bool smem_attr_set = false, rsel_attr_set = false;  // cudaFuncSetAttribute is per device
   int64_t row_off = 0, ld_eff = 0;  // the device copy of the assay starts at host row `row_off`
@@ -221,6 +221,7 @@ int init_shard(mdeggs_ctx* ctx, Shard& s) {
   CU(cudaEventCreateWithFlags(&s.ev_fork, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&s.ev_join, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&s.ev_sample, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&s.ev_cf, cudaEventDisableTiming));
   CU(s.scal.ensure(SC_COUNT * 8));
   return MDEGGS_OK;
 }
@@ -644,8 +645,12 @@ int run_shard_main(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
     const double tdf1 = K == 2 ? 1.0 : (double)(Ke - 1), tdf2 = K == 2 ? (double)(n - 4) : (double)(n - 2 * Ke);
     const double ta = (K == 2 && !rlm2) ? 0.5 : tdf1 / 2.0;
     CU(s.cf_tab.ensure((size_t)(2 * CF_TABLE_LEN + 1) * 8));
-    LAUNCH(k_cf_tables, 1, 256, 0, s.s_main, ta, tdf2 / 2.0, s.cf_tab.as<double>(), s.cf_tab.as<double>() + CF_TABLE_LEN,
+    // a one-CTA kernel nothing depends on until the tails: side stream (idle between the quantile sample and finish)
+    CU(cudaEventRecord(s.ev_fork, s.s_main));
+    CU(cudaStreamWaitEvent(s.s_sort, s.ev_fork, 0));
+    LAUNCH(k_cf_tables, 1, 256, 0, s.s_sort, ta, tdf2 / 2.0, s.cf_tab.as<double>(), s.cf_tab.as<double>() + CF_TABLE_LEN,
            s.cf_tab.as<double>() + 2 * CF_TABLE_LEN);
+    CU(cudaEventRecord(s.ev_cf, s.s_sort));
   }
   // ---- K2 gene stats (+ K3 S3: the values of the quantile slots are appended to their lists here) ----
   QsCompactArgs QC;
@@ -805,6 +810,7 @@ int run_shard_main(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
     tc.e_ba = s.cf_tab.as<double>() + CF_TABLE_LEN;
     const double* d_lbeta = s.cf_tab.as<double>() + 2 * CF_TABLE_LEN;
     const int src = is_rlm ? 2 : (use_dense ? 1 : 0);
+    CU(cudaStreamWaitEvent(s.s_main, s.ev_cf, 0));  // continued-fraction tables (side stream)
     // single GPU: every edge passes through this launch, which then also feeds the p-value buckets of K8
     const bool bs = use_bucket_order(ctx, in, n_nodes);
     const int do_bs = bs && s.world == 1;
@@ -1325,6 +1331,7 @@ int mdeggs_destroy(mdeggs_ctx* ctx) {
     if (s.ev_fork) cudaEventDestroy(s.ev_fork);
     if (s.ev_join) cudaEventDestroy(s.ev_join);
     if (s.ev_sample) cudaEventDestroy(s.ev_sample);
+    if (s.ev_cf) cudaEventDestroy(s.ev_cf);
     if (s.s_main) cudaStreamDestroy(s.s_main);
     if (s.s_sort) cudaStreamDestroy(s.s_sort);
   }
