@@ -551,7 +551,10 @@ int run_shard_front(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, int32_t
       CU(s.rsel_hist.ensure((size_t)QS_BINS * 4));
       CU(cudaMemsetAsync(s.rsel_hist.p, 0, (size_t)QS_BINS * 4, s.s_main));
     }
-    CU(s.rsel_state.ensure(sizeof(QsState)));
+    if (sizeof(QsState) > s.rsel_state.cap) {  // its "CTAs done" counters are zero between calls
+      CU(s.rsel_state.ensure(sizeof(QsState)));
+      CU(cudaMemsetAsync(s.rsel_state.p, 0, sizeof(QsState), s.s_main));
+    }
     CU(s.rsel_cand.ensure((size_t)qs_cand_capacity(ctx, in) * 8));
     if (!s.rsel_attr_set) {
       CU(cudaFuncSetAttribute(k_qs_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, QS_FIN_CAP * 8));
@@ -625,18 +628,16 @@ int run_shard_main(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
     const unsigned grid = 148 * 6;  // persistent CTAs (6 fit an SM's shared memory): one histogram flush each
     if (in->layout == MDEGGS_LAYOUT_COLMAJOR) {
       LAUNCH(k_gather_colmajor, grid, 256, 0, s.s_main, s.assay.as<double>(), s.ld_eff, s.row_off, s.rowlist.as<int32_t>(), d_nn,
-             s.src_of_pos.as<int32_t>(), L.npad, n, s.D.as<double>(), d_st, d_hist, s.B16.as<unsigned short>());
+             s.src_of_pos.as<int32_t>(), L.npad, n, s.D.as<double>(), d_st, d_hist, s.B16.as<unsigned short>(),
+             s.pct.as<double>(), P, cand_cap);
     } else {
       LAUNCH(k_gather_rowmajor, grid, 256, 0, s.s_main, s.assay.as<double>(), s.ld_eff, s.row_off, s.rowlist.as<int32_t>(), d_nn,
-             s.src_of_pos.as<int32_t>(), L.npad, n, s.D.as<double>(), d_st, d_hist, s.B16.as<unsigned short>());
+             s.src_of_pos.as<int32_t>(), L.npad, n, s.D.as<double>(), d_st, d_hist, s.B16.as<unsigned short>(),
+             s.pct.as<double>(), P, cand_cap);
     }
   }
   EVREC(s.ev[EV_GATHER], s.s_main);
   EVREC(s.ev[EV_Q0], s.s_main);
-  if (do_q) {
-    LAUNCH(k_qs_scan, 1, QS_SCAN_THREADS, 0, s.s_main, d_st, s.rsel_hist.as<unsigned int>(), d_nn, n, s.pct.as<double>(), P,
-           cand_cap);
-  }
   // ---- per-run tail tables (depend only on the degrees of freedom) ----
   {
     const bool rlm2 = (K == 2 && in->method == MDEGGS_METHOD_RLM);

@@ -12,7 +12,7 @@
 //                   a value that fills a whole cell of the sample gets a bin of its own.
 //   S1 (fused into the K1 gather kernels) exact 4,096-bin histogram of everything that is written to D,
 //                   shared-memory privatised per persistent CTA; NaN skipped (na.rm = TRUE).
-//   S2 k_qs_scan    one CTA: prefix sums; each target rank -> (bin, rank inside the bin); the <= 2P distinct bins
+//   S2 qs_scan_body run by the last CTA of the gather: prefix sums; each target rank -> (bin, rank inside the bin); the <= 2P distinct bins
 //                   become "slots" with exact candidate counts and offsets in the candidate buffer.
 //   S3 k_qs_compact reads the 2-byte bin id that the gather kept for every value (a quarter of D) and appends the values
 //                   of slot bins to their slot's list (staged per CTA in shared memory: one global atomic per CTA and
@@ -62,6 +62,7 @@ struct QsState {
   long long N;                         // non-NaN values
   int U;                               // slots (distinct target bins)
   unsigned int done;                   // finish CTAs completed
+  unsigned int gather_done;            // gather CTAs that flushed their histogram (zero between calls)
   int t_slot[QS_MAX_T];                // per target
   long long t_rank[QS_MAX_T];          // per target: 0-based rank inside its bin
   unsigned long long t_key[QS_MAX_T];  // per target: selected key
@@ -238,6 +239,10 @@ __global__ void __launch_bounds__(QS_SAMPLE_THREADS) k_qs_sample(const double* _
   }
 }
 
+__device__ __forceinline__ void qs_flush_and_scan(const unsigned int* __restrict__ s_hist, unsigned int* __restrict__ hist,
+                                                  QsState* __restrict__ st, const double* __restrict__ pct, int P,
+                                                  unsigned int cand_capacity);
+
 // ------------------------------------------------------------------------------------------------
 // K1: gather + transposition  (replaces the per-pair `assayData[gene, ]` row look-ups, core_functions.R:880-881)
 //   in : R column-major G x n (gene fastest)  or row-major (sample fastest)
@@ -246,13 +251,15 @@ __global__ void __launch_bounds__(QS_SAMPLE_THREADS) k_qs_sample(const double* _
 // CTA's shared-memory copy of the quantile histogram (S1), flushed once per CTA.  Column-major input goes through a
 // 32x32 shared-memory transposition tile, coalesced on both sides.  Padding positions (src < 0) are written by K2.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_gather_colmajor(const double* __restrict__ assay, int64_t ld,
+__global__ void __launch_bounds__(256, 6) k_gather_colmajor(const double* __restrict__ assay, int64_t ld,
                                                          int64_t row_off, const int32_t* __restrict__ rowlist,
                                                          const int32_t* __restrict__ n_nodes_p,
                                                          const int32_t* __restrict__ src_of_pos, int npad, int n,
-                                                         double* __restrict__ D, const QsState* __restrict__ st,
+                                                         double* __restrict__ D, QsState* __restrict__ st,
                                                          unsigned int* __restrict__ hist,
-                                                         unsigned short* __restrict__ B16) {
+                                                         unsigned short* __restrict__ B16,
+                                                         const double* __restrict__ pct, int P,
+                                                         unsigned int cand_capacity) {
   __shared__ double tile[32][33];
   __shared__ unsigned short tile16[32][34];
   __shared__ QsKnots kn;
@@ -302,16 +309,18 @@ __global__ void __launch_bounds__(256) k_gather_colmajor(const double* __restric
     }
     __syncthreads();
   }
-  if (do_hist) qs_flush_hist(s_hist, hist);
+  if (do_hist) qs_flush_and_scan(s_hist, hist, st, pct, P, cand_capacity);  // the last CTA also runs S2
 }
 
-__global__ void __launch_bounds__(256) k_gather_rowmajor(const double* __restrict__ assay, int64_t ld,
+__global__ void __launch_bounds__(256, 6) k_gather_rowmajor(const double* __restrict__ assay, int64_t ld,
                                                          int64_t row_off, const int32_t* __restrict__ rowlist,
                                                          const int32_t* __restrict__ n_nodes_p,
                                                          const int32_t* __restrict__ src_of_pos, int npad, int n,
-                                                         double* __restrict__ D, const QsState* __restrict__ st,
+                                                         double* __restrict__ D, QsState* __restrict__ st,
                                                          unsigned int* __restrict__ hist,
-                                                         unsigned short* __restrict__ B16) {
+                                                         unsigned short* __restrict__ B16,
+                                                         const double* __restrict__ pct, int P,
+                                                         unsigned int cand_capacity) {
   __shared__ QsKnots kn;
   __shared__ unsigned int s_hist[QS_BINS];
   const bool do_hist = hist != nullptr;
@@ -338,23 +347,25 @@ __global__ void __launch_bounds__(256) k_gather_rowmajor(const double* __restric
     }
   }
   __syncthreads();
-  if (do_hist) qs_flush_hist(s_hist, hist);
+  if (do_hist) qs_flush_and_scan(s_hist, hist, st, pct, P, cand_capacity);  // the last CTA also runs S2
 }
 
 // ---- S2 ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(QS_SCAN_THREADS) k_qs_scan(QsState* __restrict__ st, unsigned int* __restrict__ hist,
-                                                  const int32_t* __restrict__ n_nodes_p, int n,
-                                                  const double* __restrict__ pct, int P, unsigned int cand_capacity) {
-  __shared__ unsigned long long cum[QS_BINS + 1];
-  __shared__ unsigned long long s_warp[32];
+// Run by the LAST CTA of the gather kernel (256 threads) once every CTA has flushed its histogram: prefix sums, each
+// target rank -> (bin, rank inside the bin), distinct target bins -> slots with exact counts and list offsets.  The
+// bins' prefix lives in registers (16 bins per thread); a thread answers the targets that fall into its own range.
+__device__ __forceinline__ void qs_scan_body(QsState* __restrict__ st, unsigned int* __restrict__ hist,
+                                             const double* __restrict__ pct, int P, unsigned int cand_capacity) {
+  __shared__ unsigned long long s_warp[QS_SCAN_THREADS / 32];
+  __shared__ unsigned long long s_rank[QS_MAX_T];
   __shared__ int s_tbin[QS_MAX_T], s_first[QS_MAX_T];
-  __shared__ unsigned int s_slot_cnt[QS_MAX_T];
+  __shared__ unsigned int s_tcnt[QS_MAX_T], s_slot_cnt[QS_MAX_T];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   constexpr int PER = QS_BINS / QS_SCAN_THREADS;
   unsigned long long v[PER], mine = 0;
 #pragma unroll
   for (int j = 0; j < PER; ++j) {
-    v[j] = hist[tid * PER + j];
+    v[j] = __ldcg(hist + tid * PER + j);
     mine += v[j];
     hist[tid * PER + j] = 0u;  // clean slate for the next call
   }
@@ -366,24 +377,18 @@ __global__ void __launch_bounds__(QS_SCAN_THREADS) k_qs_scan(QsState* __restrict
   }
   if (lane == 31) s_warp[wid] = incl;
   __syncthreads();
-  unsigned long long woff = 0;
-  for (int w = 0; w < wid; ++w) woff += s_warp[w];
-  unsigned long long run = woff + incl - mine;
-#pragma unroll
-  for (int j = 0; j < PER; ++j) {
-    cum[tid * PER + j] = run;
-    run += v[j];
+  unsigned long long woff = 0, total = 0;
+  for (int w = 0; w < QS_SCAN_THREADS / 32; ++w) {
+    woff += w < wid ? s_warp[w] : 0ull;
+    total += s_warp[w];
   }
-  if (tid == QS_SCAN_THREADS - 1) cum[QS_BINS] = run;
-  __syncthreads();
-  const long long N = (long long)cum[QS_BINS];  // == n_nodes * n - nan_count
+  const unsigned long long my_start = woff + incl - mine, my_end = my_start + mine;
+  const long long N = (long long)total;  // == number of non-NaN node-row values
   const int T = 2 * P;
   if (tid == 0) {
     st->N = N;
     st->done = 0u;
   }
-  (void)n_nodes_p;
-  (void)n;
   if (tid < T) {
     const int p = tid >> 1;
     long long ilo = 1, ihi = 1;
@@ -394,16 +399,28 @@ __global__ void __launch_bounds__(QS_SCAN_THREADS) k_qs_scan(QsState* __restrict
       ilo = ilo < 1 ? 1 : (ilo > N ? N : ilo);
       ihi = ihi < 1 ? 1 : (ihi > N ? N : ihi);
     }
-    const unsigned long long r = (unsigned long long)(((tid & 1) ? ihi : ilo) - 1);
-    int lo = 0, hi = QS_BINS - 1;  // largest b with cum[b] <= r
-    while (lo < hi) {
-      const int mid = (lo + hi + 1) >> 1;
-      if (cum[mid] <= r) lo = mid;
-      else hi = mid - 1;
-    }
-    s_tbin[tid] = lo;
-    st->t_rank[tid] = (long long)(r - cum[lo]);
+    s_rank[tid] = (unsigned long long)(((tid & 1) ? ihi : ilo) - 1);
+    s_tbin[tid] = QS_BINS - 1;  // N == 0: no thread owns the rank; the last bin (empty) stands in
+    s_tcnt[tid] = 0u;
+    st->t_rank[tid] = 0;
     st->t_key[tid] = 0ull;
+  }
+  __syncthreads();
+  if (mine > 0) {
+    for (int t = 0; t < T; ++t) {
+      const unsigned long long r = s_rank[t];
+      if (r < my_start || r >= my_end) continue;
+      unsigned long long run = my_start;
+#pragma unroll
+      for (int j = 0; j < PER; ++j) {
+        if (r >= run && r < run + v[j]) {
+          s_tbin[t] = tid * PER + j;
+          s_tcnt[t] = (unsigned int)v[j];
+          st->t_rank[t] = (long long)(r - run);
+        }
+        run += v[j];
+      }
+    }
   }
   __syncthreads();
   // distinct target bins -> slots, in ascending bin order (T <= 256, O(T^2) in parallel)
@@ -418,10 +435,9 @@ __global__ void __launch_bounds__(QS_SCAN_THREADS) k_qs_scan(QsState* __restrict
     for (int u = 0; u < T; ++u) sl += (s_first[u] && s_tbin[u] < s_tbin[tid]);
     st->t_slot[tid] = sl;
     if (s_first[tid]) {
-      const int b = s_tbin[tid];
-      st->slot_bin[sl] = b;
-      s_slot_cnt[sl] = (unsigned int)(cum[b + 1] - cum[b]);
-      st->slot_count[sl] = s_slot_cnt[sl];
+      st->slot_bin[sl] = s_tbin[tid];
+      s_slot_cnt[sl] = s_tcnt[tid];
+      st->slot_count[sl] = s_tcnt[tid];
     }
   }
   __threadfence_block();
@@ -444,99 +460,22 @@ __global__ void __launch_bounds__(QS_SCAN_THREADS) k_qs_scan(QsState* __restrict
   }
 }
 
-// ---- S3 ------------------------------------------------------------------------------------------
-// Reads the 2-byte bin id of every value (written by the gather) instead of re-evaluating the bin map on D: 16.8 MB
-// instead of 67 MB on config 3, a table look-up per value, and D itself is touched only for the candidates.
-__global__ void __launch_bounds__(256) k_qs_compact(const double* __restrict__ D,
-                                                    const unsigned short* __restrict__ B16, int npad,
-                                                    const int32_t* __restrict__ n_nodes_p, QsState* __restrict__ st,
-                                                    unsigned long long* __restrict__ cand) {
-  __shared__ unsigned char s_slot_of_bin[QS_BINS];
-  __shared__ unsigned long long s_key[QS_STAGE];
-  __shared__ unsigned char s_stage_slot[QS_STAGE];
-  __shared__ unsigned int s_n;  // staged entries
-  __shared__ unsigned int s_cnt[QS_MAX_T], s_base[QS_MAX_T], s_fill[QS_MAX_T];
-  __shared__ unsigned long long s_min[QS_MAX_T], s_max[QS_MAX_T];
-  __shared__ unsigned char s_fat[QS_MAX_T];
-  const int U = st->U;
-  for (int i = threadIdx.x; i < QS_BINS; i += blockDim.x) s_slot_of_bin[i] = 0xff;
-  if (threadIdx.x == 0) s_n = 0u;
-  for (int i = threadIdx.x; i < QS_MAX_T; i += blockDim.x) {
-    s_cnt[i] = s_fill[i] = 0u;
-    s_min[i] = ~0ull;
-    s_max[i] = 0ull;
-    s_fat[i] = i < U ? (unsigned char)st->slot_fat[i] : 0;
+// whole CTA, at the end of a gather kernel: flush this CTA's histogram; the last CTA to do so runs S2
+__device__ __forceinline__ void qs_flush_and_scan(const unsigned int* __restrict__ s_hist, unsigned int* __restrict__ hist,
+                                                  QsState* __restrict__ st, const double* __restrict__ pct, int P,
+                                                  unsigned int cand_capacity) {
+  __shared__ int s_last;
+  qs_flush_hist(s_hist, hist);
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    s_last = (atomicAdd(&st->gather_done, 1u) == gridDim.x - 1);
+    if (s_last) st->gather_done = 0u;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < U; i += blockDim.x) s_slot_of_bin[st->slot_bin[i]] = (unsigned char)i;
-  __syncthreads();
-
-  auto visit = [&](unsigned b, long long idx) {
-    if (b == (unsigned)QS_NO_BIN) return;
-    const unsigned sl = s_slot_of_bin[b];
-    if (sl == 0xff) return;  // ~99 % of the values leave here
-    const unsigned long long k = dkey(D[idx]);
-    if (s_fat[sl]) {  // not copied: only the key range of the bin is needed
-      if (k < s_min[sl]) atomicMin(&s_min[sl], k);
-      if (k > s_max[sl]) atomicMax(&s_max[sl], k);
-      return;
-    }
-    const unsigned at = atomicAdd(&s_n, 1u);
-    if (at < (unsigned)QS_STAGE) {
-      s_key[at] = k;
-      s_stage_slot[at] = (unsigned char)sl;
-    } else {  // staging full between two flush points: straight to the slot's list
-      const unsigned pos = atomicAdd(&st->slot_cursor[sl], 1u);
-      if (pos < st->slot_count[sl]) cand[st->slot_off[sl] + pos] = k;
-    }
-  };
-  auto flush = [&]() {  // called by the whole CTA
-    const unsigned ns = s_n < (unsigned)QS_STAGE ? s_n : (unsigned)QS_STAGE;
-    for (unsigned i = threadIdx.x; i < ns; i += blockDim.x) atomicAdd(&s_cnt[s_stage_slot[i]], 1u);
-    __syncthreads();
-    for (int i = threadIdx.x; i < U; i += blockDim.x)
-      if (s_cnt[i]) s_base[i] = atomicAdd(&st->slot_cursor[i], s_cnt[i]);
-    __syncthreads();
-    for (unsigned i = threadIdx.x; i < ns; i += blockDim.x) {
-      const unsigned sl = s_stage_slot[i];
-      const unsigned pos = s_base[sl] + atomicAdd(&s_fill[sl], 1u);
-      if (pos < st->slot_count[sl]) cand[st->slot_off[sl] + pos] = s_key[i];
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < U; i += blockDim.x) s_cnt[i] = s_fill[i] = 0u;
-    if (threadIdx.x == 0) s_n = 0u;
-    __syncthreads();
-  };
-
-  // 4 bin ids (8 bytes) per load, 4 loads in flight per thread; the flat array has n_nodes * npad entries (npad % 4 == 0)
-  const long long groups = (long long)(*n_nodes_p) * npad / 4;
-  const uint2* __restrict__ B4 = reinterpret_cast<const uint2*>(B16);
-  const long long chunk = (long long)blockDim.x * 4;
-  for (long long g0 = (long long)blockIdx.x * chunk; g0 < groups; g0 += (long long)gridDim.x * chunk) {
-    uint2 w[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const long long g = g0 + u * blockDim.x + threadIdx.x;
-      w[u] = g < groups ? __ldg(B4 + g) : make_uint2(0xffffffffu, 0xffffffffu);
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const long long idx = (g0 + u * blockDim.x + threadIdx.x) * 4;
-      visit(w[u].x & 0xffffu, idx);
-      visit(w[u].x >> 16, idx + 1);
-      visit(w[u].y & 0xffffu, idx + 2);
-      visit(w[u].y >> 16, idx + 3);
-    }
-    __syncthreads();
-    if (s_n >= (unsigned)QS_STAGE / 2) flush();  // uniform: s_n is read after the barrier
-  }
-  __syncthreads();
-  flush();
-  for (int i = threadIdx.x; i < U; i += blockDim.x)
-    if (s_fat[i] && s_min[i] <= s_max[i]) {
-      atomicMin(&st->slot_min[i], s_min[i]);
-      atomicMax(&st->slot_max[i], s_max[i]);
-    }
+  if (!s_last) return;
+  __threadfence();
+  qs_scan_body(st, hist, pct, P, cand_capacity);
 }
 
 // ---- S4 ------------------------------------------------------------------------------------------
