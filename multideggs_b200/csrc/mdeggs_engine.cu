@@ -70,6 +70,9 @@ struct Shard {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_sample = nullptr, ev_cf = nullptr;
   nccl_comm_t comm = nullptr;
   bool smem_attr_set = false, rsel_attr_set = false;  // cudaFuncSetAttribute is per device
+  bool select_fused = false;  // this call's percentile selection ran inside k_bh_final
+  bool best_rows_in_emit = false;  // this call's best-percentile rows are produced by k_emit (device callers)
+  const double* best_row_src = nullptr;  // ... its p.adj row comes from row best-1 of this P x E matrix
   int64_t row_off = 0, ld_eff = 0;  // the device copy of the assay starts at host row `row_off`
   std::vector<char> stage_shadow;   // host copy of what stage_dev currently holds
   const void* stage_shadow_dev = nullptr;
@@ -342,10 +345,35 @@ int copy_out(mdeggs_ctx* ctx, Shard& s, void* dst, const void* src, size_t bytes
   return MDEGGS_OK;
 }
 
+// arguments of the percentile selection (k_select_best, or the tail of k_bh_final)
+SelArgs make_sel_args(Shard& s, const mdeggs_problem* in, const HostLayout& H, bool emit,
+                      const unsigned long long* sig_src) {
+  const int P = in->P, Pn = P > 0 ? P : 1;
+  double dfh[2];
+  result_df(in, H, dfh);
+  SelArgs S{};
+  S.tot = s.counters.as<unsigned long long>();
+  S.fail = S.tot + Pn;
+  S.sig = sig_src;
+  S.P = P;
+  S.host_adjust = in->padj == MDEGGS_PADJ_HOST ? 1 : 0;
+  S.cutoff = s.cutoff.as<double>();
+  S.n_nodes = s.scal.as<int32_t>() + 2 * SC_NNODES;
+  S.err = s.scal.as<int32_t>() + 2 * SC_ERR;
+  S.df1 = dfh[0];
+  S.df2 = dfh[1];
+  S.blk = s.small_out.as<long long>();
+  S.host_blk =
+      emit ? reinterpret_cast<long long*>((char*)s.h_stage + s.h_stage_cap - 64 - small_block_bytes(P)) : nullptr;
+  S.best = s.scal.as<int32_t>() + 2 * SC_BEST;
+  S.done = nullptr;
+  return S;
+}
+
 // ---- BH / Bonferroni over a block of percentiles (or the device-chosen best one) -----------------
 int run_adjust(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, int n_segments, int p0, int p_stride,
                const int32_t* best_dev, unsigned long long* sig_dev, double* padj_out, int64_t padj_stride,
-               int act_stride, bool reuse_tiles = false) {
+               int act_stride, bool reuse_tiles = false, const SelArgs* sel = nullptr) {
   if (n_segments <= 0) return MDEGGS_OK;
   const int64_t E = in->E;
   const int ntiles = (int)((E + BH_TILE - 1) / BH_TILE);
@@ -391,7 +419,7 @@ int run_adjust(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, int n_segmen
            s.tile_carry.as<double>(), done_b);
   LAUNCH(k_bh_final, grid, BH_THREADS, 0, s.s_main, A, in->padj, s.tile_cnt.as<int32_t>(), s.tile_base.as<long long>(),
          s.seg_n.as<long long>(),
-         s.tile_carry.as<double>(), sig_dev, padj_out, padj_stride);
+         s.tile_carry.as<double>(), sig_dev, padj_out, padj_stride, sel ? *sel : SelArgs{});
   return MDEGGS_OK;
 }
 
@@ -888,13 +916,15 @@ int run_shard_back(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
   const int Pn = P > 0 ? P : 1;
   const bool dev_adjust = device_adjust(in);
   const bool do_adjust = dev_adjust && E > 0 && P > 0 && n_nodes > 0;
+  s.select_fused = false;
   // K7 percolation (category of every edge at every percentile, counts) does not need the p order: it runs on the side
   // stream, after the activity masks, while the main stream orders the edges; both join before K8
   CU(cudaEventRecord(s.ev_fork, s.s_main));  // p-values and status of every edge are final
   CU(cudaStreamWaitEvent(s.s_sort, s.ev_fork, 0));
   // counters: tot[P] fail[P] sig[P] sig_raw[P] (u64), then out: tot_out[P] sig_out[P] fail_out[P] (i64)
-  CU(s.counters.ensure((size_t)Pn * 8 * 7));
-  CU(cudaMemsetAsync(s.counters.p, 0, (size_t)Pn * 8 * 7, s.s_sort));
+  // ... and one word: "CTAs done" counter of the k_bh_final + selection tail
+  CU(s.counters.ensure((size_t)Pn * 8 * 7 + 8));
+  CU(cudaMemsetAsync(s.counters.p, 0, (size_t)Pn * 8 * 7 + 8, s.s_sort));
   unsigned long long* c_tot = s.counters.as<unsigned long long>();
   unsigned long long* c_fail = c_tot + Pn;
   unsigned long long* c_sig = c_tot + 2 * Pn;
@@ -1006,7 +1036,13 @@ int run_shard_back(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
     CU(s.seg_n.ensure(nseg * 8));
     const int p0 = shard_p ? s.rank : 0, stride = shard_p ? s.world : 1;
     const int n_loc = p0 < P ? (P - p0 + stride - 1) / stride : 0;
-    int rc = run_adjust(ctx, s, in, n_loc * K, p0, stride, nullptr, c_sig, d_padj, E, act_stride);
+    // one rank: the percentile selection rides in the last CTA of k_bh_final (with more ranks it follows the all-reduce)
+    s.select_fused = s.world == 1 && n_loc > 0;
+    CU(s.small_out.ensure(small_block_bytes(P)));
+    SelArgs sel = make_sel_args(s, in, H, emit, c_sig);
+    sel.done = reinterpret_cast<unsigned int*>(c_tot + 7 * Pn);
+    int rc = run_adjust(ctx, s, in, n_loc * K, p0, stride, nullptr, c_sig, d_padj, E, act_stride, false,
+                        s.select_fused ? &sel : nullptr);
     if (rc) return rc;
   }
   return MDEGGS_OK;
@@ -1055,15 +1091,9 @@ int run_shard_back2(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const m
   double* d_padj = nullptr;
   if (keep_all_padj) d_padj = (out->padj && dev_out && emit) ? out->padj : s.padj.as<double>();
   const unsigned long long* sig_src = dev_adjust ? c_sig : c_raw;
-  {
-    double dfh[2];
-    result_df(in, H, dfh);
+  if (!s.select_fused) {
     CU(s.small_out.ensure(small_block_bytes(P)));
-    LAUNCH(k_select_best, 1, 32, 0, s.s_main, c_tot, c_fail, sig_src, P, in->padj == MDEGGS_PADJ_HOST ? 1 : 0,
-           s.cutoff.as<double>(), s.scal.as<int32_t>() + 2 * SC_NNODES, s.scal.as<int32_t>() + 2 * SC_ERR, dfh[0],
-           dfh[1], s.small_out.as<long long>(),
-           emit ? reinterpret_cast<long long*>((char*)s.h_stage + s.h_stage_cap - 64 - small_block_bytes(P)) : nullptr,
-           d_best);
+    LAUNCH(k_select_best, 1, 32, 0, s.s_main, make_sel_args(s, in, H, emit, sig_src));
   }
   // rows of the chosen percentile
   const bool want_cat_best = out->cat_best && E > 0 && in->padj != MDEGGS_PADJ_HOST;
@@ -1079,7 +1109,10 @@ int run_shard_back2(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const m
                      : run_adjust(ctx, s, in, K, 0, 1, d_best, nullptr, s.padj_best.as<double>(), E, act_stride, true);
     if (rc) return rc;
   }
-  if (want_cat_best || row_copy)
+  // device callers: these two rows are produced by k_emit straight into the caller's buffers
+  s.best_rows_in_emit = dev_out && emit;
+  s.best_row_src = row_copy ? d_padj : nullptr;
+  if ((want_cat_best || row_copy) && !s.best_rows_in_emit)
     LAUNCH(k_best_rows, blocks_for(E, 256), 256, 0, s.s_main, s.ea.as<int32_t>(), s.eb.as<int32_t>(),
            s.act.as<uint8_t>(), act_stride, E, d_best,
            want_cat_best ? s.cat_best.as<int8_t>() : nullptr, row_copy ? d_padj : nullptr,
@@ -1119,11 +1152,13 @@ int emit_outputs(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const mdeg
     void* dst;
     const void* src;
     size_t bytes;
+    int kind;
   };
   std::vector<Item> big, small;
-  auto add = [](std::vector<Item>& v, void* dst, const void* src, size_t bytes) {
-    if (dst && bytes) v.push_back({dst, src, bytes});
+  auto add = [](std::vector<Item>& v, void* dst, const void* src, size_t bytes, int kind = EMIT_COPY) {
+    if (dst && bytes) v.push_back({dst, src, bytes, kind});
   };
+  const bool rows_here = dev_out && s.best_rows_in_emit;
   add(small, out->tot_edges, blk, (size_t)P * 8);
   add(small, out->sig_count, blk + (size_t)Pn * 8, (size_t)P * 8);
   add(small, out->fail_count, blk + (size_t)2 * Pn * 8, (size_t)P * 8);
@@ -1138,11 +1173,24 @@ int emit_outputs(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const mdeg
   add(big, out->iters, is_rlm ? s.iters.p : nullptr, (size_t)E * 4);  // null source: zeros
   if (d_cat && d_cat != out->cat) add(big, out->cat, d_cat, (size_t)P * E);
   if (d_padj && d_padj != out->padj) add(big, out->padj, d_padj, (size_t)P * E * 8);
-  if (want_cat_best) add(big, out->cat_best, s.cat_best.p, (size_t)E);
-  if (want_padj_best) add(big, out->padj_best, s.padj_best.p, (size_t)E * 8);
+  if (want_cat_best) add(big, out->cat_best, s.cat_best.p, (size_t)E, rows_here ? EMIT_CAT_BEST : EMIT_COPY);
+  if (want_padj_best) {
+    if (rows_here && s.best_row_src) add(big, out->padj_best, s.best_row_src, (size_t)E * 8, EMIT_PADJ_BEST);
+    else add(big, out->padj_best, s.padj_best.p, (size_t)E * 8);
+  }
   if (dev_out) {
     EmitTab T;
-    memset(&T, 0, sizeof T);
+    auto reset = [&]() {
+      memset(&T, 0, sizeof T);
+      T.ea = s.ea.as<int32_t>();
+      T.eb = s.eb.as<int32_t>();
+      T.best = s.scal.as<int32_t>() + 2 * SC_BEST;
+      T.err = s.scal.as<int32_t>() + 2 * SC_ERR;
+      T.act = s.act.as<uint8_t>();
+      T.act_stride = n_nodes > 0 ? n_nodes : 1;
+      T.E = (long long)E;
+    };
+    reset();
     int ne = 0;
     size_t max_bytes = 0;
     auto flush = [&]() {
@@ -1150,7 +1198,7 @@ int emit_outputs(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const mdeg
       const unsigned gx = (unsigned)((max_bytes / 16 + 255) / 256);
       dim3 grid(gx < 1 ? 1 : (gx > 148 * 8 ? 148 * 8 : gx), (unsigned)ne);
       LAUNCH(k_emit, grid, 256, 0, s.s_main, T);
-      memset(&T, 0, sizeof T);
+      reset();
       ne = 0;
       max_bytes = 0;
     };
@@ -1159,6 +1207,7 @@ int emit_outputs(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const mdeg
         T.dst[ne] = it.dst;
         T.src[ne] = it.src;
         T.bytes[ne] = (long long)it.bytes;
+        T.kind[ne] = it.kind;
         max_bytes = it.bytes > max_bytes ? it.bytes : max_bytes;
         if (++ne == EMIT_MAX) flush();
       }

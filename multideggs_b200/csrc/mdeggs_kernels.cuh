@@ -1051,14 +1051,78 @@ __global__ void __launch_bounds__(BH_THREADS) k_qv_pi0(BhArgs A, const long long
   }
 }
 
+// which.max(sig_pvalues) over non-NULL percentiles (core_functions.R:475-495): first maximum.  Also packs every small
+// result (counts, cut-offs, best, node count, error flag, degrees of freedom) into one contiguous block so that they
+// leave the device in a single copy:  i64 tot[P] sig[P] fail[P] | f64 cutoff[P] | i32 best nn err 0 | f64 df1 df2
+struct SelArgs {
+  const unsigned long long *tot, *fail, *sig;
+  int P, host_adjust;
+  const double* cutoff;
+  const int32_t *n_nodes, *err;
+  double df1, df2;
+  long long *blk, *host_blk;
+  int32_t* best;
+  unsigned int* done;  // k_bh_final: "CTAs done" counter of the fused tail (nullptr: selection is a launch of its own)
+};
+
+// one warp: lanes stride over the percentiles, the first maximum is a shuffle arg-max; every word of the block is
+// written to device memory and (host_blk: mapped pinned memory) straight into the caller's process by its lane.
+// Loads bypass L1: inside k_bh_final the counts were produced by other CTAs of the same launch.
+__device__ __forceinline__ void select_best_warp(const SelArgs& S) {
+  const int lane = threadIdx.x & 31;
+  const int P = S.P, Pn = P > 0 ? P : 1;
+  auto put = [&](int word, long long v) {
+    S.blk[word] = v;
+    if (S.host_blk) S.host_blk[word] = v;
+  };
+  long long bv = -1;
+  int bp = 0x7fffffff;
+  for (int p = lane; p < P; p += 32) {
+    const long long t = (long long)__ldcg(S.tot + p), f = (long long)__ldcg(S.fail + p);
+    long long s = t > 0 ? (long long)__ldcg(S.sig + p) : -1;
+    if (S.host_adjust) s = -1;
+    put(p, t);
+    put(Pn + p, s);
+    put(2 * Pn + p, f);
+    put(3 * Pn + p, __double_as_longlong(__ldcg(S.cutoff + p)));
+    if (!S.host_adjust && t > 0 && f == 0 && s > bv) {  // p ascending per lane: keeps the lane's first maximum
+      bv = s;
+      bp = p;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {  // maximum count, ties -> smallest percentile (which.max: first maximum)
+    const long long ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const int op = __shfl_xor_sync(0xffffffffu, bp, o);
+    if (ov > bv || (ov == bv && op < bp)) {
+      bv = ov;
+      bp = op;
+    }
+  }
+  const int b = bv >= 0 ? bp + 1 : 0;
+  if (lane == 0) {
+    *S.best = b;
+    put(4 * Pn, (long long)(unsigned int)b | ((long long)(unsigned int)__ldcg(S.n_nodes) << 32));  // i32 best, nn
+    put(4 * Pn + 1, (long long)(unsigned int)__ldcg(S.err));                                        // i32 err, 0
+    put(4 * Pn + 2, __double_as_longlong(S.df1));
+    put(4 * Pn + 3, __double_as_longlong(S.df2));
+  }
+  if (S.host_blk) __threadfence_system();
+}
+
+__global__ void k_select_best(SelArgs S) {
+  if (blockIdx.x != 0 || threadIdx.x >= 32) return;
+  select_best_warp(S);
+}
+
 // pass C: adjusted values, count < 0.05, optional scatter to network order
 //   mode 1 bonferroni: pmin(1, n * p);  mode 2 BH: pmin(1, cummin((n/i) * p[o]))[ro]
-__global__ void __launch_bounds__(BH_THREADS) k_bh_final(BhArgs A, int mode, const int32_t* __restrict__ tile_cnt,
-                                                        const long long* __restrict__ tile_base,
-                                                        const long long* __restrict__ seg_n,
-                                                        const double* __restrict__ tile_carry,
-                                                        unsigned long long* __restrict__ sig,
-                                                        double* __restrict__ padj_out, int64_t padj_stride) {
+__device__ __forceinline__ void bh_final_body(const BhArgs& A, int mode, const int32_t* __restrict__ tile_cnt,
+                                              const long long* __restrict__ tile_base,
+                                              const long long* __restrict__ seg_n,
+                                              const double* __restrict__ tile_carry,
+                                              unsigned long long* __restrict__ sig, double* __restrict__ padj_out,
+                                              int64_t padj_stride) {
   int p, c;
   size_t seg;
   if (!bh_segment(A, p, c, seg)) return;
@@ -1144,64 +1208,42 @@ __global__ void __launch_bounds__(BH_THREADS) k_bh_final(BhArgs A, int mode, con
   }
 }
 
-// which.max(sig_pvalues) over non-NULL percentiles (core_functions.R:475-495): first maximum.  Also packs every small
-// result (counts, cut-offs, best, node count, error flag, degrees of freedom) into one contiguous block so that they
-// leave the device in a single copy:  i64 tot[P] sig[P] fail[P] | f64 cutoff[P] | i32 best nn err 0 | f64 df1 df2
-__global__ void k_select_best(const unsigned long long* __restrict__ tot, const unsigned long long* __restrict__ fail,
-                              const unsigned long long* __restrict__ sig, int P, int host_adjust,
-                              const double* __restrict__ cutoff, const int32_t* __restrict__ n_nodes,
-                              const int32_t* __restrict__ err, double df1, double df2, long long* __restrict__ blk,
-                              long long* __restrict__ host_blk, int32_t* __restrict__ best) {
-  // one warp: lanes stride over the percentiles, the first maximum is a shuffle arg-max; every word of the block is
-  // written to device memory and (host_blk: mapped pinned memory) straight into the caller's process by its lane
-  if (blockIdx.x != 0 || threadIdx.x >= 32) return;
-  const int lane = threadIdx.x;
-  const int Pn = P > 0 ? P : 1;
-  auto put = [&](int word, long long v) {
-    blk[word] = v;
-    if (host_blk) host_blk[word] = v;
-  };
-  long long bv = -1;
-  int bp = 0x7fffffff;
-  for (int p = lane; p < P; p += 32) {
-    const long long t = (long long)tot[p], f = (long long)fail[p];
-    long long s = t > 0 ? (long long)sig[p] : -1;
-    if (host_adjust) s = -1;
-    put(p, t);
-    put(Pn + p, s);
-    put(2 * Pn + p, f);
-    put(3 * Pn + p, __double_as_longlong(cutoff[p]));
-    if (!host_adjust && t > 0 && f == 0 && s > bv) {  // p ascending per lane: keeps the lane's first maximum
-      bv = s;
-      bp = p;
-    }
+// pass C; with S.done the CTA that finishes last (all significant counts are in) also runs the percentile selection
+__global__ void __launch_bounds__(BH_THREADS) k_bh_final(BhArgs A, int mode, const int32_t* __restrict__ tile_cnt,
+                                                        const long long* __restrict__ tile_base,
+                                                        const long long* __restrict__ seg_n,
+                                                        const double* __restrict__ tile_carry,
+                                                        unsigned long long* __restrict__ sig,
+                                                        double* __restrict__ padj_out, int64_t padj_stride, SelArgs S) {
+  bh_final_body(A, mode, tile_cnt, tile_base, seg_n, tile_carry, sig, padj_out, padj_stride);
+  if (!S.done) return;
+  __shared__ int s_last_cta;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int prev = atomicAdd(S.done, 1u);
+    s_last_cta = prev == gridDim.x * gridDim.y - 1;
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {  // maximum count, ties -> smallest percentile (which.max: first maximum)
-    const long long ov = __shfl_xor_sync(0xffffffffu, bv, o);
-    const int op = __shfl_xor_sync(0xffffffffu, bp, o);
-    if (ov > bv || (ov == bv && op < bp)) {
-      bv = ov;
-      bp = op;
-    }
-  }
-  const int b = bv >= 0 ? bp + 1 : 0;
-  if (lane == 0) {
-    *best = b;
-    put(4 * Pn, (long long)(unsigned int)b | ((long long)(unsigned int)*n_nodes << 32));      // i32 best, nn
-    put(4 * Pn + 1, (long long)(unsigned int)*err);                                            // i32 err, 0
-    put(4 * Pn + 2, __double_as_longlong(df1));
-    put(4 * Pn + 3, __double_as_longlong(df2));
-  }
-  if (host_blk) __threadfence_system();
+  __syncthreads();
+  if (!s_last_cta || threadIdx.x >= 32) return;
+  __threadfence();
+  select_best_warp(S);
 }
 
 // results -> caller's DEVICE buffers: every requested array in one launch (entry = blockIdx.y; src == nullptr: zeros)
 constexpr int EMIT_MAX = 16;
+enum { EMIT_COPY = 0, EMIT_CAT_BEST = 1, EMIT_PADJ_BEST = 2 };
 struct EmitTab {
   void* dst[EMIT_MAX];
   const void* src[EMIT_MAX];
   long long bytes[EMIT_MAX];
+  int kind[EMIT_MAX];
+  // rows of the device-chosen percentile, produced straight into the caller's buffers (what k_best_rows does for
+  // host callers): EMIT_CAT_BEST from the masks, EMIT_PADJ_BEST from row best-1 of the P x E scratch (src)
+  const int32_t *ea, *eb, *best, *err;
+  const uint8_t* act;
+  int act_stride;
+  long long E;
 };
 __global__ void __launch_bounds__(256) k_emit(EmitTab T) {
   const int ent = blockIdx.y;
@@ -1209,6 +1251,20 @@ __global__ void __launch_bounds__(256) k_emit(EmitTab T) {
   const char* src = static_cast<const char*>(T.src[ent]);
   const long long bytes = T.bytes[ent];
   const long long stride = (long long)gridDim.x * blockDim.x, t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (T.kind[ent] != EMIT_COPY) {
+    if (*T.err) return;
+    const int p = *T.best - 1;
+    if (T.kind[ent] == EMIT_CAT_BEST) {
+      const uint8_t* row = T.act + (size_t)(p < 0 ? 0 : p) * T.act_stride;
+      for (long long e = t0; e < T.E; e += stride)
+        dst[e] = p >= 0 ? (char)edge_category(row[T.ea[e]], row[T.eb[e]]) : (char)0;
+    } else {
+      const double* all = reinterpret_cast<const double*>(src);
+      for (long long e = t0; e < T.E; e += stride)
+        reinterpret_cast<double*>(dst)[e] = (p >= 0 && all) ? all[(size_t)p * T.E + e] : nan("");
+    }
+    return;
+  }
   const bool vec = ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15) == 0;
   long long done = 0;
   if (vec) {
