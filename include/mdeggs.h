@@ -147,6 +147,21 @@ int mdeggs_destroy(mdeggs_ctx* ctx);
  * crosses PCIe except `group`, `pct` (tiny) and one 8-byte count. */
 int mdeggs_run_omic(mdeggs_ctx* ctx, const mdeggs_problem* in, mdeggs_result* out);
 
+/* The same call in two halves: mdeggs_submit_omic enqueues the input copies, the whole path and the output copies on
+ * the context's streams and returns without waiting; mdeggs_wait blocks until that work is done, delivers the small
+ * host results and the statistics, and reports errors found on the device. Every buffer named by `in` / `out`
+ * stays borrowed until mdeggs_wait returns. One call may be in flight per context. */
+int mdeggs_submit_omic(mdeggs_ctx* ctx, const mdeggs_problem* in, mdeggs_result* out);
+int mdeggs_wait(mdeggs_ctx* ctx);
+
+/* All omic layers of one get_diffNetworks call (the per-omic loop of core_functions.R:214-234) in one launch set:
+ * layer i is submitted on ctxs[i] (distinct contexts, normally all on the same GPU) before any is waited for, so
+ * the layers' kernels and copies overlap on the device instead of paying one launch/sync latency chain each.
+ * A failing layer does not stop the others (the reference's per-omic tryCatch, core_functions.R:219-233):
+ * layer_rc[i] (optional) receives its code, the return value is the first non-zero one. */
+int mdeggs_run_omics(mdeggs_ctx* const* ctxs, int n_layers, const mdeggs_problem* in, mdeggs_result* out,
+                     int* layer_rc);
+
 /* Feature construction of predict.multiDEGGs_filter (feature_selection_for_ML.R:406-445):
  * out[s + j*n] = x[s + a[j]*ldx] / x[s + b[j]*ldx]  (or product), non-finite -> 0; x is n x G col-major,
  * a/b are 0-based column indices. mem as above. */

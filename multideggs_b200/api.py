@@ -19,7 +19,7 @@ import numpy as np
 import pandas as pd
 
 from . import _abi, host
-from .engine import Engine, default_engine
+from .engine import Engine, default_engine, default_pool
 from .host import NO_LINKS, Assay, Factor, IndexedNetwork
 
 DEFAULT_PERCENTILES = _abi.r_seq(0.35, 0.98, 0.05)   # core_functions.R:137
@@ -87,15 +87,40 @@ def get_diffNetworks(assayData, metadata, category_variable=None, regression_met
     meta = host.tidy_metadata(category_subset=category_subset, metadata=metadata,
                               category_variable=category_variable, id_variable=None, verbose=verbose)
     nets: dict[str, Any] = {}
-    for name, a in assay_list.items():
-        try:  # tryCatch(..., error = function(e) message(conditionMessage(e)))  core_functions.R:219-233
-            nets[name] = get_diffNetworks_singleOmic(a, name, meta, regression_method, mixedModel, id_variable,
-                                                     lmer_ctrl, network, percentile_vector, padj_method,
-                                                     show_progressBar, verbose, cores, engine=engine,
-                                                     tested_coef=tested_coef, rlm_cov_mode=rlm_cov_mode)
-        except (ValueError, ArithmeticError) as e:
-            host.message(str(e))
-            nets[name] = None
+    if engine is None and len(assay_list) > 1:
+        # every layer prepared on the host, then ONE launch set for all of them (mdeggs_run_omics), then assembly;
+        # each step keeps the reference's per-omic tryCatch (core_functions.R:219-233)
+        preps: dict[str, host.OmicPrep] = {}
+        for name, a in assay_list.items():
+            try:
+                if verbose:
+                    host.message(f"Generating {name} network layer...")
+                preps[name] = host.prepare_omic(a, name, meta, regression_method, network, percentile_vector,
+                                                padj_method, tested_coef, rlm_cov_mode)
+            except (ValueError, ArithmeticError) as e:
+                host.message(str(e))
+                nets[name] = None
+        results = default_pool().run_omics([p.problem for p in preps.values()],
+                                           [host.want_fields(p) for p in preps.values()])
+        for (name, prep), res in zip(preps.items(), results):
+            if isinstance(res, Exception):
+                raise res
+            try:
+                nets[name] = host.assemble_networks(prep, res, cores=cores, verbose=verbose)
+            except (ValueError, ArithmeticError) as e:
+                host.message(str(e))
+                nets[name] = None
+        nets = {name: nets[name] for name in assay_list}  # layer order of the input list
+    else:
+        for name, a in assay_list.items():
+            try:  # tryCatch(..., error = function(e) message(conditionMessage(e)))  core_functions.R:219-233
+                nets[name] = get_diffNetworks_singleOmic(a, name, meta, regression_method, mixedModel, id_variable,
+                                                         lmer_ctrl, network, percentile_vector, padj_method,
+                                                         show_progressBar, verbose, cores, engine=engine,
+                                                         tested_coef=tested_coef, rlm_cov_mode=rlm_cov_mode)
+            except (ValueError, ArithmeticError) as e:
+                host.message(str(e))
+                nets[name] = None
     return Deggs(diffNetworks=nets, assayData=assay_list, metadata=meta, regression_method=regression_method,
                  mixedModel=mixedModel, id_variable=id_variable, lmer_ctrl=lmer_ctrl,
                  category_subset=category_subset, padj_method=padj_method)

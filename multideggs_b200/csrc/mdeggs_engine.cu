@@ -143,6 +143,16 @@ struct mdeggs_ctx {
   std::vector<TraceRec> trace_recs;
   std::vector<cudaEvent_t> trace_pool;
   size_t trace_used = 0;
+  // a submitted call that has not been waited for yet (mdeggs_submit_omic / mdeggs_wait)
+  struct Pending {
+    bool active = false;
+    mdeggs_problem in;
+    mdeggs_result out;
+    int32_t n_nodes = 0;
+    bool replayed = false;
+    int src_device = 0;
+    std::chrono::steady_clock::time_point t0, t1, t2;
+  } pend;
 };
 
 namespace {
@@ -1390,7 +1400,34 @@ int mdeggs_destroy(mdeggs_ctx* ctx) {
 }
 
 int mdeggs_run_omic(mdeggs_ctx* ctx, const mdeggs_problem* in, mdeggs_result* out) {
+  int rc = mdeggs_submit_omic(ctx, in, out);
+  if (rc) return rc;
+  return mdeggs_wait(ctx);
+}
+
+int mdeggs_run_omics(mdeggs_ctx* const* ctxs, int n_layers, const mdeggs_problem* in, mdeggs_result* out,
+                     int* layer_rc) {
+  if (n_layers < 0 || (n_layers > 0 && (!ctxs || !in || !out))) return MDEGGS_EINVAL;
+  for (int i = 0; i < n_layers; ++i)
+    for (int j = 0; j < i; ++j)
+      if (ctxs[i] == ctxs[j]) return MDEGGS_EINVAL;  // one context (streams, scratch, staging) per layer in flight
+  int first = MDEGGS_OK;
+  std::vector<int> rcs((size_t)n_layers, MDEGGS_OK);
+  for (int i = 0; i < n_layers; ++i) rcs[i] = mdeggs_submit_omic(ctxs[i], in + i, out + i);
+  for (int i = 0; i < n_layers; ++i) {
+    if (rcs[i] == MDEGGS_OK) rcs[i] = mdeggs_wait(ctxs[i]);
+    if (rcs[i] != MDEGGS_OK && first == MDEGGS_OK) first = rcs[i];
+    if (layer_rc) layer_rc[i] = rcs[i];
+  }
+  return first;
+}
+
+int mdeggs_submit_omic(mdeggs_ctx* ctx, const mdeggs_problem* in, mdeggs_result* out) {
   if (!ctx || !in || !out) return MDEGGS_EINVAL;
+  if (ctx->pend.active) {
+    set_err(ctx, "a submitted call is still pending: call mdeggs_wait first");
+    return MDEGGS_EINVAL;
+  }
   ctx->err.clear();
   if (in->K < 2 || in->K > MDEGGS_MAX_K) {
     set_err(ctx, "K = %d outside 2..%d", in->K, MDEGGS_MAX_K);
@@ -1537,6 +1574,31 @@ int mdeggs_run_omic(mdeggs_ctx* ctx, const mdeggs_problem* in, mdeggs_result* ou
     CU(cudaSetDevice(ctx->shards[i].device));
     CU(cudaEventRecord(ctx->shards[i].ev[EV_END], ctx->shards[i].s_main));
   }
+  ctx->pend.in = *in;
+  ctx->pend.out = *out;
+  ctx->pend.n_nodes = n_nodes;
+  ctx->pend.replayed = replayed;
+  ctx->pend.src_device = src_device;
+  ctx->pend.t0 = t_host0;
+  ctx->pend.t1 = t_host1;
+  ctx->pend.t2 = t_host2;
+  ctx->pend.active = true;
+  return MDEGGS_OK;
+}
+
+int mdeggs_wait(mdeggs_ctx* ctx) {
+  if (!ctx) return MDEGGS_EINVAL;
+  if (!ctx->pend.active) {
+    set_err(ctx, "mdeggs_wait without a submitted call");
+    return MDEGGS_EINVAL;
+  }
+  ctx->pend.active = false;
+  const mdeggs_problem* in = &ctx->pend.in;
+  mdeggs_result* out = &ctx->pend.out;
+  int32_t n_nodes = ctx->pend.n_nodes;
+  const bool replayed = ctx->pend.replayed;
+  const int src_device = ctx->pend.src_device;
+  const auto t_host0 = ctx->pend.t0, t_host1 = ctx->pend.t1, t_host2 = ctx->pend.t2;
   for (Shard& s : ctx->shards) {
     CU(cudaSetDevice(s.device));
     CU(cudaStreamSynchronize(s.s_sort));

@@ -156,9 +156,10 @@ struct QsCompactArgs {
   unsigned long long *slot_min, *slot_max;
   unsigned long long* cand;
 };
-// whole CTA; s_tab[QSC_BINS]
+// whole CTA; s_tab[QSC_BINS], 16-byte aligned
 __device__ __forceinline__ void qsc_load_table(const QsCompactArgs& Q, unsigned char* __restrict__ s_tab) {
-  for (int i = threadIdx.x; i < QSC_BINS; i += blockDim.x) s_tab[i] = 0xff;
+  for (int i = threadIdx.x; i < QSC_BINS / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(s_tab)[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
   __syncthreads();
   const int U = *Q.U;
   for (int i = threadIdx.x; i < U; i += blockDim.x) s_tab[Q.slot_bin[i]] = (unsigned char)i;
@@ -251,7 +252,7 @@ __global__ void __launch_bounds__(THREADS) k_gene_stats(double* __restrict__ D, 
   extern __shared__ double srow[];
   __shared__ int s_bad;
   __shared__ unsigned long long s_cand[THREADS / 32][32];
-  __shared__ unsigned char s_qtab[QSC_BINS];
+  __shared__ __align__(16) unsigned char s_qtab[QSC_BINS];
   if (Q.B16) qsc_load_table(Q, s_qtab);
   const int node = blockIdx.x;
   if (node >= *n_nodes_p) return;
@@ -416,7 +417,7 @@ __global__ void __launch_bounds__(256) k_gene_stats_reg(double* __restrict__ D, 
                                                         double* __restrict__ med, uint8_t* __restrict__ bad,
                                                         QsCompactArgs Q) {
   __shared__ unsigned long long s_cand[8][32];
-  __shared__ unsigned char s_qtab[QSC_BINS];
+  __shared__ __align__(16) unsigned char s_qtab[QSC_BINS];
   if (Q.B16) qsc_load_table(Q, s_qtab);
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const long long w = (long long)blockIdx.x * 8 + wib;

@@ -15,7 +15,7 @@ import numpy as np
 from . import _abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libmdeggs.so")
+LIB_PATH = os.environ.get("MDEGGS_LIB") or os.path.join(_HERE, "csrc", "libmdeggs.so")  # MDEGGS_LIB: A/B builds
 _LIB: C.CDLL | None = None
 
 # every symbol include/mdeggs.h declares (tests check the library exports all of them)
@@ -23,6 +23,7 @@ ABI_SYMBOLS = (
     "mdeggs_create", "mdeggs_create_rank", "mdeggs_nccl_unique_id", "mdeggs_destroy", "mdeggs_run_omic",
     "mdeggs_pair_features", "mdeggs_measure_fp64_peak", "mdeggs_last_stats", "mdeggs_set_option", "mdeggs_last_error", "mdeggs_strerror", "mdeggs_abi_version",
     "mdeggs_dev_pt", "mdeggs_dev_pf_upper", "mdeggs_dev_p_two_sided_ref",
+    "mdeggs_submit_omic", "mdeggs_wait", "mdeggs_run_omics",
 )
 
 
@@ -45,6 +46,10 @@ def load_library() -> C.CDLL:
     L.mdeggs_nccl_unique_id.argtypes = [vp]
     L.mdeggs_destroy.argtypes = [vp]
     L.mdeggs_run_omic.argtypes = [vp, C.POINTER(_abi.CProblem), C.POINTER(_abi.CResult)]
+    L.mdeggs_submit_omic.argtypes = [vp, C.POINTER(_abi.CProblem), C.POINTER(_abi.CResult)]
+    L.mdeggs_wait.argtypes = [vp]
+    L.mdeggs_run_omics.argtypes = [C.POINTER(vp), i, C.POINTER(_abi.CProblem), C.POINTER(_abi.CResult),
+                                   C.POINTER(C.c_int)]
     L.mdeggs_pair_features.argtypes = [vp, vp, i64, C.c_int32, vp, vp, C.c_int32, C.c_int32, C.c_int32, vp]
     L.mdeggs_last_stats.argtypes = [vp, C.POINTER(_abi.CStats)]
     L.mdeggs_set_option.argtypes = [vp, C.c_char_p, i64]
@@ -131,6 +136,13 @@ class Engine:
         """Pre-marshalled structs (device or pinned-host pointers); used by bench.py."""
         self._check(self._lib.mdeggs_run_omic(self._ctx, C.byref(cprob), C.byref(cres)), "mdeggs_run_omic")
 
+    def submit_omic_raw(self, cprob: _abi.CProblem, cres: _abi.CResult) -> None:
+        """First half of run_omic_raw: enqueue and return; the buffers stay borrowed until wait()."""
+        self._check(self._lib.mdeggs_submit_omic(self._ctx, C.byref(cprob), C.byref(cres)), "mdeggs_submit_omic")
+
+    def wait(self) -> None:
+        self._check(self._lib.mdeggs_wait(self._ctx), "mdeggs_wait")
+
     def set_option(self, name: str, value: int) -> None:
         """"graph": 1/0 CUDA-graph replay of repeated identical calls; "fit_path": -1 auto, 0 streaming, 1 dense."""
         self._check(self._lib.mdeggs_set_option(self._ctx, name.encode(), int(value)), "mdeggs_set_option")
@@ -176,7 +188,67 @@ class Engine:
         return self._vec(self._lib.mdeggs_dev_p_two_sided_ref, t, df)
 
 
+class EnginePool:
+    """One engine (context: streams, scratch, staging) per omic layer of a get_diffNetworks call, all on one GPU:
+    mdeggs_run_omics submits every layer before waiting for any, so the layers overlap on the device
+    (the per-omic loop of core_functions.R:214-234 as one launch set)."""
+
+    def __init__(self, device: int = 0):
+        self.device = device
+        self._engines: list[Engine] = []
+
+    def engines(self, n: int) -> list[Engine]:
+        while len(self._engines) < n:
+            self._engines.append(Engine([self.device]))
+        return self._engines[:n]
+
+    def close(self) -> None:
+        for e in self._engines:
+            e.close()
+        self._engines = []
+
+    def run_omics(self, problems: Sequence[_abi.Problem], wants: Sequence[Sequence[str]]):
+        """-> list of (result arrays | EngineError), one per layer; a failing layer does not stop the others."""
+        n = len(problems)
+        if n == 0:
+            return []
+        engs = self.engines(n)
+        lib = engs[0]._lib
+        cprobs = (_abi.CProblem * n)()
+        cress = (_abi.CResult * n)()
+        keep = []
+        for i, (pr, want) in enumerate(zip(problems, wants)):
+            cp = pr.to_c()
+            cr, arrays = _abi.alloc_result(pr.dims, tuple(want))
+            cprobs[i] = cp
+            cress[i] = cr
+            keep.append((cp, cr, arrays))
+        ctxs = (C.c_void_p * n)(*[e._ctx for e in engs])
+        rcs = (C.c_int * n)()
+        lib.mdeggs_run_omics(ctxs, n, cprobs, cress, rcs)
+        out = []
+        for i in range(n):
+            if rcs[i] == 0:
+                out.append(keep[i][2])
+            else:
+                msg = lib.mdeggs_last_error(engs[i]._ctx)
+                out.append(EngineError(f"mdeggs_run_omics[{i}]: {lib.mdeggs_strerror(rcs[i]).decode()}: "
+                                       f"{msg.decode() if msg else ''}"))
+        return out
+
+
 _DEFAULT: Engine | None = None
+_DEFAULT_POOL: EnginePool | None = None
+
+
+def default_pool() -> EnginePool:
+    """Lazily created process-wide pool on the first GPU of MDEGGS_GPUS (default 0)."""
+    global _DEFAULT_POOL
+    if _DEFAULT_POOL is None:
+        env = os.environ.get("MDEGGS_GPUS")
+        _DEFAULT_POOL = EnginePool(int(env.split(",")[0]) if env else 0)
+    return _DEFAULT_POOL
+
 
 
 def default_engine() -> Engine:

@@ -692,3 +692,66 @@ def test_device_qvalue_fallback_branches(engine, oracle):
                        K=2, pct=np.array([0.0]), method=_abi.METHOD_LM, padj=_abi.PADJ_QVALUE)
     g1, r1 = engine.run_omic(one, want), oracle.run_omic(one, want)
     assert_parity(g1, r1, one, what="q.value single row: ")
+
+
+# ---- all omic layers of one call as one launch set (mdeggs_submit_omic / mdeggs_wait / mdeggs_run_omics) ----
+def _frames_equal(a, b):
+    assert type(a) is type(b)
+    if isinstance(a, pd.DataFrame):
+        pd.testing.assert_frame_equal(a, b, check_exact=True)
+    elif isinstance(a, dict):
+        assert list(a) == list(b)
+        for k in a:
+            _frames_equal(a[k], b[k])
+    else:
+        assert a == b
+
+
+@pytest.mark.parametrize("method,padj", [("lm", "bonferroni"), ("rlm", "BH"), ("lm", "q.value")])
+def test_batched_layers_equal_sequential_layers(engine, bundled, method, padj):
+    """get_diffNetworks without an explicit engine runs its layers through mdeggs_run_omics (one context per layer);
+    the result must be identical to the layer-by-layer calls (core_functions.R:214-234)."""
+    assays = {k: bundled[k] for k in ("RNAseq", "Proteomics", "Olink")}
+    kw = dict(assayData=assays, metadata=bundled["metadata"], category_variable="response", regression_method=method,
+              padj_method=padj, verbose=False, show_progressBar=False, cores=1)
+    seq = md.get_diffNetworks(engine=engine, **kw)
+    bat = md.get_diffNetworks(**kw)
+    assert list(bat["diffNetworks"]) == list(seq["diffNetworks"]) == list(assays)
+    _frames_equal(bat["diffNetworks"], seq["diffNetworks"])
+    bat2 = md.get_diffNetworks(**kw)  # second batched call: every context replays its graph
+    _frames_equal(bat2["diffNetworks"], seq["diffNetworks"])
+
+
+def test_run_omics_layers_of_different_shapes_and_a_failing_layer(engine, oracle):
+    from multideggs_b200.engine import EngineError, EnginePool
+    pool = EnginePool(0)
+    probs = [synth.random_problem(60, 40, 150, 2, 1201, _abi.METHOD_LM, _abi.PADJ_BH),
+             synth.random_problem(300, 64, 2500, 3, 1202, _abi.METHOD_LM, _abi.PADJ_BONFERRONI),
+             synth.random_problem(30, 50, 40, 2, 1203, _abi.METHOD_RLM, _abi.PADJ_BH),
+             synth.random_problem(30, 20, 40, 2, 1204)]
+    probs[3].from_idx = probs[3].from_idx.copy()
+    probs[3].from_idx[5] = 31  # outside 1..G: this layer fails, the others must not notice
+    try:
+        for _ in range(2):
+            res = pool.run_omics(probs, [ALL_FIELDS] * 4)
+            assert isinstance(res[3], EngineError) and "outside 1..G" in str(res[3])
+            for pr, got in zip(probs[:3], res[:3]):
+                assert_parity(got, oracle.run_omic(pr, ALL_FIELDS), pr, rtol=1e-8 if pr.method == _abi.METHOD_RLM else 1e-9)
+    finally:
+        pool.close()
+
+
+def test_submit_wait_protocol(engine):
+    from multideggs_b200.engine import EngineError
+    prob = synth.random_problem(50, 40, 120, 2, 1210)
+    ref = engine.run_omic(prob, ALL_FIELDS)
+    cp = prob.to_c()
+    cr, arrays = _abi.alloc_result(prob.dims, tuple(ALL_FIELDS))
+    with pytest.raises(EngineError, match="without a submitted call"):
+        engine.wait()
+    engine.submit_omic_raw(cp, cr)
+    with pytest.raises(EngineError, match="still pending"):
+        engine.submit_omic_raw(cp, cr)
+    engine.wait()
+    for k in ref:
+        np.testing.assert_array_equal(arrays[k], ref[k])
