@@ -25,10 +25,11 @@
   3L  # hommel (or host-side q.value): raw p + masks come back, R adjusts each segment
 }
 
-get_diffNetworks_singleOmic <- function(assayData, assayDataName, metadata, regression_method,
-                                        mixedModel, id_variable, lmer_ctrl, network,
-                                        percentile_vector, padj_method, show_progressBar,
-                                        verbose, cores) {
+# Host preparation of one layer (core_functions.R:280-340): everything up to the engine call.  Returns the argument
+# list of the `.Call` (first eleven entries of mdeggs_R_run without n_gpus, in mdeggs_R_run_layers order) plus what
+# the assembly needs afterwards.
+.mdeggs_prepare_layer <- function(assayData, assayDataName, metadata, regression_method, mixedModel, network,
+                                  percentile_vector, padj_method, verbose) {
   if (verbose) message("Generating ", assayDataName, " network layer...")
   if (mixedModel) stop("mixedModel = TRUE is not supported by the GPU engine; use the CPU implementation")
   if (!(is.matrix(assayData) || is.data.frame(assayData)))
@@ -65,13 +66,21 @@ get_diffNetworks_singleOmic <- function(assayData, assayDataName, metadata, regr
   categories <- levels(metadata)
   K <- length(categories)
   padj_code <- .mdeggs_padj_code(padj_method)
-  res <- .Call("mdeggs_R_run", assayData, as.integer(from_idx), as.integer(to_idx),
-               as.integer(metadata), as.integer(K), as.double(percentile_vector),
-               as.integer(regression_method == "rlm"), padj_code,
-               3L,                                        # f.robftest(var = 3), core_functions.R:920
-               getOption("multiDEGGs.rlm_cov", 0L),       # 0 = XtWX, 1 = XtX
-               as.integer(getOption("multiDEGGs.gpus", 1L)), FALSE)
+  list(args = list(assayData, as.integer(from_idx), as.integer(to_idx),
+                   as.integer(metadata), as.integer(K), as.double(percentile_vector),
+                   as.integer(regression_method == "rlm"), padj_code,
+                   3L,                                    # f.robftest(var = 3), core_functions.R:920
+                   as.integer(getOption("multiDEGGs.rlm_cov", 0L)),  # 0 = XtWX, 1 = XtX
+                   FALSE),                                # want_all
+       gene_names = rownames(assayData), from_idx = from_idx, to_idx = to_idx, categories = categories,
+       padj_code = padj_code)
+}
 
+# Engine results of one layer -> the reference's per-omic list (core_functions.R:471-529)
+.mdeggs_assemble_layer <- function(prep, res, percentile_vector, padj_method, verbose, cores) {
+  from_idx <- prep$from_idx; to_idx <- prep$to_idx
+  categories <- prep$categories; K <- length(categories)
+  padj_code <- prep$padj_code
   P <- length(percentile_vector)
   E <- length(from_idx)
   sig <- res$sig_count
@@ -115,7 +124,7 @@ get_diffNetworks_singleOmic <- function(assayData, assayDataName, metadata, regr
   } else {
     cat_best <- as.integer(res$cat_best); padj_best <- res$padj_best
   }
-  gene_names <- rownames(assayData)
+  gene_names <- prep$gene_names
   final_networks <- lapply(seq_len(K), function(k) {
     rows <- which(cat_best == k)
     if (length(rows) == 0) return("No specific links for this category.")
@@ -129,6 +138,43 @@ get_diffNetworks_singleOmic <- function(assayData, assayDataName, metadata, regr
   final_networks <- append(final_networks, sig[best])
   names(final_networks)[length(final_networks)] <- "sig_pvalues_count"
   final_networks
+}
+
+get_diffNetworks_singleOmic <- function(assayData, assayDataName, metadata, regression_method,
+                                        mixedModel, id_variable, lmer_ctrl, network,
+                                        percentile_vector, padj_method, show_progressBar,
+                                        verbose, cores) {
+  prep <- .mdeggs_prepare_layer(assayData, assayDataName, metadata, regression_method, mixedModel, network,
+                                percentile_vector, padj_method, verbose)
+  a <- prep$args
+  res <- .Call("mdeggs_R_run", a[[1]], a[[2]], a[[3]], a[[4]], a[[5]], a[[6]], a[[7]], a[[8]], a[[9]], a[[10]],
+               as.integer(getOption("multiDEGGs.gpus", 1L)), a[[11]])
+  .mdeggs_assemble_layer(prep, res, percentile_vector, padj_method, verbose, cores)
+}
+
+# Drop-in for the per-omic lapply of get_diffNetworks (core_functions.R:214-234): every layer is prepared on the
+# host, ALL layers run as one launch set (one `.Call`, mdeggs_run_omics: one engine context per layer, the layers
+# overlap on the GPU), then each layer is assembled.  A layer that fails in any of the three steps is reported with
+# message() and becomes NULL, exactly like the reference's per-omic tryCatch (core_functions.R:219-233).
+.mdeggs_diffNetworks_layers <- function(assayDataList, metadata, regression_method, mixedModel, network,
+                                        percentile_vector, padj_method, verbose, cores) {
+  preps <- lapply(names(assayDataList), function(nm)
+    tryCatch(.mdeggs_prepare_layer(assayDataList[[nm]], nm, metadata, regression_method, mixedModel, network,
+                                   percentile_vector, padj_method, verbose),
+             error = function(e) { message(conditionMessage(e)); NULL }))
+  ok <- which(!vapply(preps, is.null, logical(1)))
+  res <- if (length(ok)) .Call("mdeggs_R_run_layers", lapply(preps[ok], `[[`, "args")) else list()
+  out <- vector("list", length(assayDataList))
+  names(out) <- names(assayDataList)
+  for (j in seq_along(ok)) {
+    i <- ok[j]
+    val <- tryCatch({
+      if (is.character(res[[j]])) stop(res[[j]])        # engine error of this layer
+      .mdeggs_assemble_layer(preps[[i]], res[[j]], percentile_vector, padj_method, verbose, cores)
+    }, error = function(e) { message(conditionMessage(e)); NULL })
+    if (!is.null(val)) out[[i]] <- val
+  }
+  out
 }
 
 # feature construction of predict.multiDEGGs_filter (feature_selection_for_ML.R:423-431) on the GPU

@@ -53,10 +53,19 @@ static SEXP i64_to_real(const int64_t* v, int n) {
   return out;
 }
 
-/* .Call("mdeggs_R_run", assay, from_idx, to_idx, group, K, percentiles, method, padj, tested_coef,
- *       rlm_cov_mode, n_gpus, want_all)  ->  named list */
-SEXP mdeggs_R_run(SEXP assay, SEXP from_idx, SEXP to_idx, SEXP group, SEXP K_, SEXP percentiles, SEXP method_,
-                  SEXP padj_, SEXP tested_coef_, SEXP cov_mode_, SEXP n_gpus_, SEXP want_all_) {
+/* One omic layer on the R side of the boundary: the borrowed inputs, the R vectors that receive the results
+ * (allocated and PROTECTed before any GPU work; `np` counts them) and the two C structs handed to the engine. */
+typedef struct {
+  mdeggs_problem in;
+  mdeggs_result out;
+  SEXP cutoff, p_edge, stat, status, df, best, cat_best, padj_best, median, coef, iters, cat, padj_all;
+  int64_t *tot, *sig, *fail;
+  int P, np;
+} layer_t;
+
+/* argument checks + output allocation; may raise an R error (nothing of this layer is on the GPU yet) */
+static void layer_prepare(layer_t* L, SEXP assay, SEXP from_idx, SEXP to_idx, SEXP group, SEXP K_, SEXP percentiles,
+                          SEXP method_, SEXP padj_, SEXP tested_coef_, SEXP cov_mode_, SEXP want_all_) {
   if (TYPEOF(assay) != REALSXP || !Rf_isMatrix(assay)) Rf_error("assay must be a double matrix (genes x samples)");
   if (TYPEOF(from_idx) != INTSXP || TYPEOF(to_idx) != INTSXP || TYPEOF(group) != INTSXP)
     Rf_error("from_idx, to_idx and group must be integer vectors");
@@ -68,105 +77,180 @@ SEXP mdeggs_R_run(SEXP assay, SEXP from_idx, SEXP to_idx, SEXP group, SEXP K_, S
   if (XLENGTH(to_idx) != E) Rf_error("from_idx and to_idx differ in length");
   if (XLENGTH(group) != n) Rf_error("group must have one code per sample (column of assay)");
 
-  mdeggs_problem in;
-  memset(&in, 0, sizeof in);
-  in.assay = REAL(assay);
-  in.ld = G;
-  in.G = G;
-  in.n = n;
-  in.layout = MDEGGS_LAYOUT_COLMAJOR;
-  in.mem = MDEGGS_MEM_HOST;
-  in.from = INTEGER(from_idx);
-  in.to = INTEGER(to_idx);
-  in.E = (int64_t)E;
-  in.group = INTEGER(group);
-  in.K = K;
-  in.pct = REAL(percentiles);
-  in.P = P;
-  in.method = Rf_asInteger(method_);
-  in.padj = padj;
-  in.tested_coef = Rf_asInteger(tested_coef_);
-  in.rlm_cov_mode = Rf_asInteger(cov_mode_);
+  memset(L, 0, sizeof *L);
+  mdeggs_problem* in = &L->in;
+  in->assay = REAL(assay);
+  in->ld = G;
+  in->G = G;
+  in->n = n;
+  in->layout = MDEGGS_LAYOUT_COLMAJOR;
+  in->mem = MDEGGS_MEM_HOST;
+  in->from = INTEGER(from_idx);
+  in->to = INTEGER(to_idx);
+  in->E = (int64_t)E;
+  in->group = INTEGER(group);
+  in->K = K;
+  in->pct = REAL(percentiles);
+  in->P = P;
+  in->method = Rf_asInteger(method_);
+  in->padj = padj;
+  in->tested_coef = Rf_asInteger(tested_coef_);
+  in->rlm_cov_mode = Rf_asInteger(cov_mode_);
 
   /* outputs: allocate + protect everything first */
   int np = 0;
-  SEXP cutoff = PROTECT(Rf_allocVector(REALSXP, P)); ++np;
-  SEXP p_edge = PROTECT(Rf_allocVector(REALSXP, E)); ++np;
-  SEXP stat = PROTECT(Rf_allocVector(REALSXP, E)); ++np;
-  SEXP status = PROTECT(Rf_allocVector(INTSXP, E)); ++np;
-  SEXP df = PROTECT(Rf_allocVector(REALSXP, 2)); ++np;
-  SEXP best = PROTECT(Rf_allocVector(INTSXP, 1)); ++np;
-  SEXP cat_best = PROTECT(Rf_allocVector(RAWSXP, E)); ++np;
-  SEXP padj_best = PROTECT(Rf_allocVector(REALSXP, E)); ++np;
-  SEXP median = R_NilValue, coef = R_NilValue, iters = R_NilValue, cat = R_NilValue, padj_all = R_NilValue;
+  L->P = P;
+  L->cutoff = PROTECT(Rf_allocVector(REALSXP, P)); ++np;
+  L->p_edge = PROTECT(Rf_allocVector(REALSXP, E)); ++np;
+  L->stat = PROTECT(Rf_allocVector(REALSXP, E)); ++np;
+  L->status = PROTECT(Rf_allocVector(INTSXP, E)); ++np;
+  L->df = PROTECT(Rf_allocVector(REALSXP, 2)); ++np;
+  L->best = PROTECT(Rf_allocVector(INTSXP, 1)); ++np;
+  L->cat_best = PROTECT(Rf_allocVector(RAWSXP, E)); ++np;
+  L->padj_best = PROTECT(Rf_allocVector(REALSXP, E)); ++np;
+  L->median = L->coef = L->iters = L->cat = L->padj_all = R_NilValue;
   const int host_adjust = (padj == MDEGGS_PADJ_HOST);
   if (want_all) {
-    median = PROTECT(Rf_allocMatrix(REALSXP, G, K)); ++np;
-    coef = PROTECT(Rf_allocMatrix(REALSXP, 2 * K, (int)E)); ++np;
-    iters = PROTECT(Rf_allocVector(INTSXP, E)); ++np;
+    L->median = PROTECT(Rf_allocMatrix(REALSXP, G, K)); ++np;
+    L->coef = PROTECT(Rf_allocMatrix(REALSXP, 2 * K, (int)E)); ++np;
+    L->iters = PROTECT(Rf_allocVector(INTSXP, E)); ++np;
   }
   if (want_all || host_adjust) {
-    cat = PROTECT(Rf_allocVector(RAWSXP, (R_xlen_t)P * E)); ++np;
+    L->cat = PROTECT(Rf_allocVector(RAWSXP, (R_xlen_t)P * E)); ++np;
   }
   if (want_all && !host_adjust && padj != MDEGGS_PADJ_NONE) {
-    padj_all = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)P * E)); ++np;
+    L->padj_all = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)P * E)); ++np;
   }
-  int64_t* tot = (int64_t*)R_alloc((size_t)(P > 0 ? P : 1), sizeof(int64_t));
-  int64_t* sig = (int64_t*)R_alloc((size_t)(P > 0 ? P : 1), sizeof(int64_t));
-  int64_t* fail = (int64_t*)R_alloc((size_t)(P > 0 ? P : 1), sizeof(int64_t));
-  for (R_xlen_t i = 0; i < E; ++i) REAL(padj_best)[i] = NA_REAL;
+  L->np = np;
+  L->tot = (int64_t*)R_alloc((size_t)(P > 0 ? P : 1), sizeof(int64_t));
+  L->sig = (int64_t*)R_alloc((size_t)(P > 0 ? P : 1), sizeof(int64_t));
+  L->fail = (int64_t*)R_alloc((size_t)(P > 0 ? P : 1), sizeof(int64_t));
+  for (R_xlen_t i = 0; i < E; ++i) REAL(L->padj_best)[i] = NA_REAL;
 
-  mdeggs_result out;
-  memset(&out, 0, sizeof out);
-  out.cutoff = REAL(cutoff);
-  out.p_edge = REAL(p_edge);
-  out.stat = REAL(stat);
-  out.status = INTEGER(status);
-  out.df = REAL(df);
-  out.best = INTEGER(best);
-  out.cat_best = (int8_t*)RAW(cat_best);
-  out.padj_best = REAL(padj_best);
-  out.tot_edges = tot;
-  out.sig_count = sig;
-  out.fail_count = fail;
-  if (median != R_NilValue) out.median = REAL(median);
-  if (coef != R_NilValue) out.coef = REAL(coef);
-  if (iters != R_NilValue) out.iters = INTEGER(iters);
-  if (cat != R_NilValue) out.cat = (int8_t*)RAW(cat);
-  if (padj_all != R_NilValue) out.padj = REAL(padj_all);
+  mdeggs_result* out = &L->out;
+  out->cutoff = REAL(L->cutoff);
+  out->p_edge = REAL(L->p_edge);
+  out->stat = REAL(L->stat);
+  out->status = INTEGER(L->status);
+  out->df = REAL(L->df);
+  out->best = INTEGER(L->best);
+  out->cat_best = (int8_t*)RAW(L->cat_best);
+  out->padj_best = REAL(L->padj_best);
+  out->tot_edges = L->tot;
+  out->sig_count = L->sig;
+  out->fail_count = L->fail;
+  if (L->median != R_NilValue) out->median = REAL(L->median);
+  if (L->coef != R_NilValue) out->coef = REAL(L->coef);
+  if (L->iters != R_NilValue) out->iters = INTEGER(L->iters);
+  if (L->cat != R_NilValue) out->cat = (int8_t*)RAW(L->cat);
+  if (L->padj_all != R_NilValue) out->padj = REAL(L->padj_all);
+}
 
-  mdeggs_ctx* ctx = get_ctx(Rf_asInteger(n_gpus_));
-  int rc = mdeggs_run_omic(ctx, &in, &out); /* returns only after all device work has completed */
-  if (rc != MDEGGS_OK) {
-    char msg[600];
-    snprintf(msg, sizeof msg, "multiDEGGs GPU engine: %s: %s", mdeggs_strerror(rc), mdeggs_last_error(ctx));
-    UNPROTECT(np);
-    Rf_error("%s", msg);
-  }
-
+/* results of one layer -> named R list (2 more PROTECTs, counted in L->np) */
+static SEXP layer_pack(layer_t* L) {
   const char* names[] = {"cutoff", "p_edge", "stat", "status", "df", "best", "cat_best", "padj_best", "tot_edges",
                          "sig_count", "fail_count", "median", "coef", "iters", "cat", "padj"};
   const int nfield = 16;
-  SEXP res = PROTECT(Rf_allocVector(VECSXP, nfield)); ++np;
-  SEXP nms = PROTECT(Rf_allocVector(STRSXP, nfield)); ++np;
+  SEXP res = PROTECT(Rf_allocVector(VECSXP, nfield)); ++L->np;
+  SEXP nms = PROTECT(Rf_allocVector(STRSXP, nfield)); ++L->np;
   for (int i = 0; i < nfield; ++i) SET_STRING_ELT(nms, i, Rf_mkChar(names[i]));
-  SET_VECTOR_ELT(res, 0, cutoff);
-  SET_VECTOR_ELT(res, 1, p_edge);
-  SET_VECTOR_ELT(res, 2, stat);
-  SET_VECTOR_ELT(res, 3, status);
-  SET_VECTOR_ELT(res, 4, df);
-  SET_VECTOR_ELT(res, 5, best);
-  SET_VECTOR_ELT(res, 6, cat_best);
-  SET_VECTOR_ELT(res, 7, padj_best);
-  SET_VECTOR_ELT(res, 8, i64_to_real(tot, P));
-  SET_VECTOR_ELT(res, 9, i64_to_real(sig, P));
-  SET_VECTOR_ELT(res, 10, i64_to_real(fail, P));
-  SET_VECTOR_ELT(res, 11, median);
-  SET_VECTOR_ELT(res, 12, coef);
-  SET_VECTOR_ELT(res, 13, iters);
-  SET_VECTOR_ELT(res, 14, cat);
-  SET_VECTOR_ELT(res, 15, padj_all);
+  SET_VECTOR_ELT(res, 0, L->cutoff);
+  SET_VECTOR_ELT(res, 1, L->p_edge);
+  SET_VECTOR_ELT(res, 2, L->stat);
+  SET_VECTOR_ELT(res, 3, L->status);
+  SET_VECTOR_ELT(res, 4, L->df);
+  SET_VECTOR_ELT(res, 5, L->best);
+  SET_VECTOR_ELT(res, 6, L->cat_best);
+  SET_VECTOR_ELT(res, 7, L->padj_best);
+  SET_VECTOR_ELT(res, 8, i64_to_real(L->tot, L->P));
+  SET_VECTOR_ELT(res, 9, i64_to_real(L->sig, L->P));
+  SET_VECTOR_ELT(res, 10, i64_to_real(L->fail, L->P));
+  SET_VECTOR_ELT(res, 11, L->median);
+  SET_VECTOR_ELT(res, 12, L->coef);
+  SET_VECTOR_ELT(res, 13, L->iters);
+  SET_VECTOR_ELT(res, 14, L->cat);
+  SET_VECTOR_ELT(res, 15, L->padj_all);
   Rf_setAttrib(res, R_NamesSymbol, nms);
+  return res;
+}
+
+/* .Call("mdeggs_R_run", assay, from_idx, to_idx, group, K, percentiles, method, padj, tested_coef,
+ *       rlm_cov_mode, n_gpus, want_all)  ->  named list */
+SEXP mdeggs_R_run(SEXP assay, SEXP from_idx, SEXP to_idx, SEXP group, SEXP K_, SEXP percentiles, SEXP method_,
+                  SEXP padj_, SEXP tested_coef_, SEXP cov_mode_, SEXP n_gpus_, SEXP want_all_) {
+  layer_t L;
+  layer_prepare(&L, assay, from_idx, to_idx, group, K_, percentiles, method_, padj_, tested_coef_, cov_mode_,
+                want_all_);
+  mdeggs_ctx* ctx = get_ctx(Rf_asInteger(n_gpus_));
+  int rc = mdeggs_run_omic(ctx, &L.in, &L.out); /* returns only after all device work has completed */
+  if (rc != MDEGGS_OK) {
+    char msg[600];
+    snprintf(msg, sizeof msg, "multiDEGGs GPU engine: %s: %s", mdeggs_strerror(rc), mdeggs_last_error(ctx));
+    UNPROTECT(L.np);
+    Rf_error("%s", msg);
+  }
+  SEXP res = layer_pack(&L);
+  UNPROTECT(L.np);
+  return res;
+}
+
+/* .Call("mdeggs_R_run_layers", layers): every omic layer of one get_diffNetworks call (the loop of
+ * core_functions.R:214-234) as ONE launch set.  `layers` is a list; each element is the list of the first ten
+ * arguments of mdeggs_R_run followed by want_all (n_gpus does not apply: one single-GPU context per layer).
+ * Returns a list of the same length: the result list of the layer, or a character(1) error message where the
+ * engine failed for that layer (the caller turns it into message() like the reference's per-omic tryCatch). */
+#define MDEGGS_R_MAX_LAYERS 16
+static SEXP g_layer_ctx[MDEGGS_R_MAX_LAYERS];
+
+static mdeggs_ctx* get_layer_ctx(int i) {
+  if (g_layer_ctx[i] != NULL) {
+    mdeggs_ctx* c = (mdeggs_ctx*)R_ExternalPtrAddr(g_layer_ctx[i]);
+    if (c) return c;
+  }
+  int dev = 0;
+  mdeggs_ctx* ctx = NULL;
+  int rc = mdeggs_create(&ctx, &dev, 1);
+  if (rc != MDEGGS_OK) Rf_error("multiDEGGs GPU engine: cannot create context: %s", mdeggs_strerror(rc));
+  g_layer_ctx[i] = R_MakeExternalPtr(ctx, R_NilValue, R_NilValue);
+  R_PreserveObject(g_layer_ctx[i]);
+  R_RegisterCFinalizerEx(g_layer_ctx[i], ctx_finalizer, TRUE);
+  return ctx;
+}
+
+SEXP mdeggs_R_run_layers(SEXP layers) {
+  if (TYPEOF(layers) != VECSXP) Rf_error("layers must be a list");
+  const int nl = (int)XLENGTH(layers);
+  if (nl > MDEGGS_R_MAX_LAYERS) Rf_error("at most %d layers per call", MDEGGS_R_MAX_LAYERS);
+  layer_t* L = (layer_t*)R_alloc((size_t)(nl > 0 ? nl : 1), sizeof(layer_t));
+  mdeggs_ctx* ctxs[MDEGGS_R_MAX_LAYERS];
+  mdeggs_problem in[MDEGGS_R_MAX_LAYERS];
+  mdeggs_result out[MDEGGS_R_MAX_LAYERS];
+  int rcs[MDEGGS_R_MAX_LAYERS];
+  int np = 0;
+  for (int i = 0; i < nl; ++i) { /* every R allocation and every context before any GPU work */
+    SEXP a = VECTOR_ELT(layers, i);
+    if (TYPEOF(a) != VECSXP || XLENGTH(a) != 11) Rf_error("layer %d: expected a list of 11 arguments", i + 1);
+    layer_prepare(&L[i], VECTOR_ELT(a, 0), VECTOR_ELT(a, 1), VECTOR_ELT(a, 2), VECTOR_ELT(a, 3), VECTOR_ELT(a, 4),
+                  VECTOR_ELT(a, 5), VECTOR_ELT(a, 6), VECTOR_ELT(a, 7), VECTOR_ELT(a, 8), VECTOR_ELT(a, 9),
+                  VECTOR_ELT(a, 10));
+    np += L[i].np;
+    ctxs[i] = get_layer_ctx(i);
+    in[i] = L[i].in;
+    out[i] = L[i].out;
+  }
+  mdeggs_run_omics(ctxs, nl, in, out, rcs); /* returns only after the device work of every layer has completed */
+  SEXP res = PROTECT(Rf_allocVector(VECSXP, nl)); ++np;
+  for (int i = 0; i < nl; ++i) {
+    if (rcs[i] == MDEGGS_OK) {
+      const int before = L[i].np;
+      SET_VECTOR_ELT(res, i, layer_pack(&L[i]));
+      np += L[i].np - before;
+    } else {
+      char msg[600];
+      snprintf(msg, sizeof msg, "multiDEGGs GPU engine: %s: %s", mdeggs_strerror(rcs[i]), mdeggs_last_error(ctxs[i]));
+      SET_VECTOR_ELT(res, i, Rf_mkString(msg));
+    }
+  }
   UNPROTECT(np);
   return res;
 }
@@ -185,6 +269,7 @@ SEXP mdeggs_R_pair_features(SEXP x, SEXP a, SEXP b, SEXP ratio) {
 }
 
 static const R_CallMethodDef call_methods[] = {{"mdeggs_R_run", (DL_FUNC)&mdeggs_R_run, 12},
+                                               {"mdeggs_R_run_layers", (DL_FUNC)&mdeggs_R_run_layers, 1},
                                                {"mdeggs_R_pair_features", (DL_FUNC)&mdeggs_R_pair_features, 4},
                                                {NULL, NULL, 0}};
 

@@ -36,6 +36,8 @@ SEXP Rf_setAttrib(SEXP, SEXP, SEXP);
 SEXP Rf_mkChar(const char*);
 void SET_STRING_ELT(SEXP, R_xlen_t, SEXP);
 SEXP SET_VECTOR_ELT(SEXP, R_xlen_t, SEXP);
+SEXP VECTOR_ELT(SEXP, R_xlen_t);
+SEXP Rf_mkString(const char*);
 SEXP R_MakeExternalPtr(void*, SEXP, SEXP);
 void* R_ExternalPtrAddr(SEXP);
 void R_ClearExternalPtr(SEXP);
