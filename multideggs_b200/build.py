@@ -17,7 +17,7 @@ HEADERS = ["mdeggs_kernels.cuh", "mdeggs_math.cuh", "mdeggs_rlm.cuh", "mdeggs_de
 def nvcc_cmd(ptxas_verbose: bool = False) -> list[str]:
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-           "-Xcompiler", "-fPIC,-O2", "-shared", "-ccbin", "g++", "-I", os.path.join(ROOT, "include"), "-I", CSRC,
+           "-Xcompiler", "-fPIC,-O3", "-shared", "-ccbin", "g++", "-I", os.path.join(ROOT, "include"), "-I", CSRC,
            "-o", OUT] + [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl"]
     if ptxas_verbose:
         cmd[1:1] = ["-Xptxas", "-v"]
