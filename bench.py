@@ -283,14 +283,37 @@ def _timed_steps(torch, eng, cprob, cres, steps, warmup, flush, dist_sync):
     return ms, wall, {k: v / steps for k, v in stage.items()}, st
 
 
+def _bind_near_gpu(local: int) -> str:
+    """One process per GPU: run on the CPUs NVML reports as local to this rank's GPU, so that the pinned host buffers
+    (allocated afterwards, first touch) live on the GPU's NUMA node and every rank's host<->device copies use its own
+    memory controllers instead of all ranks sharing those of one socket. Returns a description for the JSON line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[local]) if vis and vis.split(",")[local].isdigit() else local
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return "unchanged (NVML reports no local CPUs inside this process's CPU set)"
+        os.sched_setaffinity(0, cpus)
+        return f"{len(cpus)} CPUs local to the GPU (NVML cpu affinity)"
+    except Exception as e:  # no NVML, no permission: keep the inherited CPU set
+        return f"unchanged ({type(e).__name__})"
+
+
 def run_cuda(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    cpu_binding = _bind_near_gpu(local) if world > 1 and not os.environ.get("MDEGGS_NO_BIND") else "not bound (N = 1)"
     import torch
     import multideggs_b200 as md
     from multideggs_b200 import _abi
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
     if world != args.gpus and world > 1:
         raise SystemExit("--gpus must equal WORLD_SIZE under torchrun")
     if not torch.cuda.is_available():
@@ -394,7 +417,8 @@ def run_cuda(args) -> None:
                    "parallelism": "1 GPU" if world == 1 else f"{world} independent omic layers, one per GPU (no collective)",
                    "l2": "inputs (160 MB) exceed L2; plus a 256 MiB read-modify-write flush between steps (untimed)",
                    "timing": "CUDA events per step on the default stream, max over ranks",
-                   "launch_mode": "compute phase replayed from a CUDA graph" if graph_replayed else "eager launches"},
+                   "launch_mode": "compute phase replayed from a CUDA graph" if graph_replayed else "eager launches",
+                   "host_cpus": cpu_binding},
         "ref_equiv_tests_per_s": world * ref_equiv * args.steps / (ms * 1e-3),
         "result_check": {"best_percentile_index": best, "sig_pairs": int(sig[best - 1]) if best > 0 else 0,
                          "tests_the_reference_would_run": ref_equiv},

@@ -1143,7 +1143,7 @@ int run_shard_back2(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const m
 // device callers get everything through ONE copy kernel, host callers through one D2H per large array plus one for
 // the block, which finish_small_outputs() scatters after the final synchronisation.
 int emit_outputs(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const mdeggs_result* out, const HostLayout& H,
-                 int32_t n_nodes) {
+                 int32_t n_nodes, bool record_end = true) {
   const int G = in->G, K = in->K, P = in->P;
   const int64_t E = in->E;
   (void)H;
@@ -1238,7 +1238,7 @@ int emit_outputs(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const mdeg
   // count + error flag are read from it after the final sync, and host callers get their small results from it
   // (finish_small_outputs)
   if (!dev_out) ctx->stats.d2h_bytes += (int64_t)blk_bytes;
-  CU(cudaEventRecord(s.ev[EV_END], s.s_main));
+  if (record_end) CU(cudaEventRecord(s.ev[EV_END], s.s_main));
   trace_mark(ctx, "(outputs copied)", s.s_main);
   return MDEGGS_OK;
 }
@@ -1487,6 +1487,8 @@ int mdeggs_submit_omic(mdeggs_ctx* ctx, const mdeggs_problem* in, mdeggs_result*
     if ((r = run_sig_allreduce(ctx, in, out))) return r;
     for (size_t i = 0; i < ctx->shards.size(); ++i)
       if ((r = run_shard_back2(ctx, ctx->shards[i], in, out, H, *n_cap, i == 0))) return r;
+    // device callers: the output kernel is part of the captured graph (host callers get eager copies in phase C)
+    if (ctx->capturing && in->mem == MDEGGS_MEM_DEVICE) r = emit_outputs(ctx, ctx->shards[0], in, out, H, *n_cap, false);
     return r;
   };
   int32_t n_nodes = (int32_t)(2 * in->E < (int64_t)in->G ? 2 * in->E : (int64_t)in->G);
@@ -1568,9 +1570,13 @@ int mdeggs_submit_omic(mdeggs_ctx* ctx, const mdeggs_problem* in, mdeggs_result*
     if (rc) return rc;
   }
   const auto t_host1 = std::chrono::steady_clock::now();
-  // ---- phase C: outputs (eager) ----
-  rc = emit_outputs(ctx, sh0, in, out, H, n_nodes);
-  if (rc) return rc;
+  // ---- phase C: outputs (eager; device callers of a replayed graph already have them) ----
+  if (replayed && in->mem == MDEGGS_MEM_DEVICE) {
+    CU(cudaEventRecord(sh0.ev[EV_END], sh0.s_main));
+  } else {
+    rc = emit_outputs(ctx, sh0, in, out, H, n_nodes);
+    if (rc) return rc;
+  }
   if (getenv("MDEGGS_HOSTTIME") && sh0.stamps.p) LAUNCH(k_stamp, 1, 1, 0, sh0.s_main, sh0.stamps.as<unsigned long long>() + 3);
   const auto t_host2 = std::chrono::steady_clock::now();
   for (size_t i = 1; i < ctx->shards.size(); ++i) {

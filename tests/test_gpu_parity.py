@@ -755,3 +755,58 @@ def test_submit_wait_protocol(engine):
     engine.wait()
     for k in ref:
         np.testing.assert_array_equal(arrays[k], ref[k])
+
+
+# ---- device-resident callers (MDEGGS_MEM_DEVICE): what bench.py's `value` leg and a GPU-side pipeline use ----
+def _device_call(torch, prob, want):
+    dev = torch.device("cuda", 0)
+    G, n, E, K, P = prob.dims
+    t_assay = torch.from_numpy(np.ascontiguousarray(np.asfortranarray(prob.assay).T)).to(dev)  # memory: col-major G x n
+    t_from = torch.from_numpy(np.ascontiguousarray(prob.from_idx, dtype=np.int32)).to(dev)
+    t_to = torch.from_numpy(np.ascontiguousarray(prob.to_idx, dtype=np.int32)).to(dev)
+    group = np.ascontiguousarray(prob.group, dtype=np.int32)
+    pct = np.ascontiguousarray(prob.pct, dtype=np.float64)
+    cprob = _abi.CProblem(t_assay.data_ptr(), G, G, n, _abi.LAYOUT_COLMAJOR, _abi.MEM_DEVICE, t_from.data_ptr(),
+                          t_to.data_ptr(), E, group.ctypes.data, K, pct.ctypes.data, P, prob.method, prob.padj,
+                          prob.tested_coef, prob.rlm_cov_mode)
+    cres, outs = _abi.CResult(), {}
+    tdt = {np.float64: torch.float64, np.int32: torch.int32, np.int8: torch.int8, np.int64: torch.int64}
+    for nm in want:
+        dt, shp = _abi.RESULT_FIELDS[nm]
+        t = torch.full(shp(G, n, E, K, P), -7, dtype=tdt[dt], device=dev)  # poison: every field must be written
+        outs[nm] = t
+        setattr(cres, nm, t.data_ptr())
+    return cprob, cres, outs, (t_assay, t_from, t_to, group, pct)
+
+
+@pytest.mark.parametrize("K,method,padj", [(2, _abi.METHOD_LM, _abi.PADJ_BH), (3, _abi.METHOD_LM, _abi.PADJ_HOLM),
+                                           (2, _abi.METHOD_RLM, _abi.PADJ_BONFERRONI), (2, _abi.METHOD_LM, _abi.PADJ_NONE),
+                                           (3, _abi.METHOD_LM, _abi.PADJ_QVALUE)])
+def test_device_resident_caller_equals_host_caller(K, method, padj):
+    """Same pointers, new data on every call: call 1 is eager, call 2 captures the graph (output kernel included) and
+    launches it, calls 3-4 replay it; every result must equal the host-buffer call on the same data, bit for bit."""
+    import torch
+    href = md.Engine([0])
+    eng = md.Engine([0])
+    prob = synth.random_problem(120, 48, 700, K, 1300 + K, method, padj)
+    cprob, cres, outs, keep = _device_call(torch, prob, ALL_FIELDS)
+    try:
+        for it in range(4):
+            fresh = synth.random_problem(120, 48, 700, K, 1310 + 7 * it + K, method, padj)
+            prob.assay[...] = np.asfortranarray(fresh.assay)
+            keep[0].copy_(torch.from_numpy(np.ascontiguousarray(np.asfortranarray(prob.assay).T)))
+            for t in outs.values():
+                t.fill_(-7)
+            eng.run_omic_raw(cprob, cres)
+            torch.cuda.synchronize()
+            ref = href.run_omic(prob, ALL_FIELDS)
+            replayed = bool(eng.stats()["fit_path"] & 0x100)
+            assert replayed == (it >= 1), (it, replayed)
+            for nm in ALL_FIELDS:
+                got = outs[nm].cpu().numpy()
+                if nm in ("padj", "padj_best") and padj == _abi.PADJ_NONE:
+                    continue  # no adjusted values exist: neither caller's buffer is written
+                assert np.array_equal(got, ref[nm], equal_nan=True), (it, nm)
+    finally:
+        eng.close()
+        href.close()
