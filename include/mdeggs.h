@@ -180,7 +180,11 @@ int mdeggs_last_stats(const mdeggs_ctx* ctx, mdeggs_stats* out);
  * "trace" (1 = print the end time of every launch of the next calls to stderr; implies eager launches);
  * "zero_copy" (1 = a pinned host assay is read by the gather kernel straight over PCIe instead of being copied first;
  * measured 2 % slower than the DMA copy on this pool's boxes, hence off by default);
- * "rsel_cap" (tests: cap the quantile candidate list so that the overflow path is exercised; 0 = default). */
+ * "rsel_cap" (tests: cap the quantile candidate list so that the overflow path is exercised; 0 = default);
+ * "padj_keep_cap" (bytes; the P x E matrix of adjusted values is kept in device scratch for the best-percentile row
+ * only up to this size [default 256 MiB], beyond it K8 counts first and re-adjusts the chosen percentile);
+ * "count_only" (1 = when no adjusted value of the all-percentile pass is kept, the significant counts come from a
+ * single rank pass (step-up rule) instead of the cumulative-min passes [default], 0 = always the three passes). */
 int mdeggs_set_option(mdeggs_ctx* ctx, const char* name, int64_t value);
 const char* mdeggs_last_error(const mdeggs_ctx* ctx);
 const char* mdeggs_strerror(int code);

@@ -71,6 +71,7 @@ struct Shard {
   nccl_comm_t comm = nullptr;
   bool smem_attr_set = false, rsel_attr_set = false;  // cudaFuncSetAttribute is per device
   bool select_fused = false;  // this call's percentile selection ran inside k_bh_final
+  bool partials_complete = true;  // the all-percentile K8 left the tile carries behind (false: count-only pass)
   bool best_rows_in_emit = false;  // this call's best-percentile rows are produced by k_emit (device callers)
   const double* best_row_src = nullptr;  // ... its p.adj row comes from row best-1 of this P x E matrix
   int64_t row_off = 0, ld_eff = 0;  // the device copy of the assay starts at host row `row_off`
@@ -87,11 +88,11 @@ struct Shard {
     if (e == cudaSuccess) h_stage_cap = bytes + 256;
     return e;
   }
-  DevBuf assay, from, to, ea, eb, stage_dev, bs_count, bs_slot, seg_done, seg_pi0, B16, stamps, excl, node_of_row, rowlist, scal, src_of_pos, pct, cutoff, D, cub_tmp, mean, sxx, med, bad, stat, status, p_edge, coef, iters, act, counters, sortk, sortk2, idx,
+  DevBuf assay, from, to, ea, eb, stage_dev, bs_count, bs_slot, seg_done, seg_rank, seg_pi0, B16, stamps, excl, node_of_row, rowlist, scal, src_of_pos, pct, cutoff, D, cub_tmp, mean, sxx, med, bad, stat, status, p_edge, coef, iters, act, counters, sortk, sortk2, idx,
       idx2, ps, sa, sb, tile_cnt, tile_base, seg_n, tile_min, tile_carry, padj_best, cat_best, cat, padj, med_out,
       small_out, rsel_hist, rsel_state, rsel_cand, dense_S, cf_tab, sxy;
   void release_all() {
-    DevBuf* all[] = {&assay, &from, &to, &ea, &eb, &stage_dev, &bs_count, &bs_slot, &seg_done, &seg_pi0, &B16, &stamps, &excl, &node_of_row, &rowlist, &scal, &src_of_pos, &pct, &cutoff,
+    DevBuf* all[] = {&assay, &from, &to, &ea, &eb, &stage_dev, &bs_count, &bs_slot, &seg_done, &seg_rank, &seg_pi0, &B16, &stamps, &excl, &node_of_row, &rowlist, &scal, &src_of_pos, &pct, &cutoff,
                      &D, &cub_tmp, &mean, &sxx, &med, &bad, &stat, &status, &p_edge,
                      &coef, &iters, &act, &counters, &sortk, &sortk2, &idx, &idx2, &ps, &sa, &sb, &tile_cnt,
                      &tile_base, &seg_n, &tile_min, &tile_carry, &padj_best, &cat_best, &cat, &padj, &med_out,
@@ -132,6 +133,8 @@ struct mdeggs_ctx {
   int fit_path_override = -1;  // -1 auto, 0 force streaming, 1 force dense (MDEGGS_FIT_PATH, tests)
   bool last_zc = false;        // the last call read its assay through zero copy
   int zero_copy = 0;           // option "zero_copy": pinned host assays are read by the gather straight over PCIe
+  int64_t padj_keep_cap = (int64_t)256 << 20;  // option "padj_keep_cap": largest P x E x 8 scratch kept for the best row
+  int count_only_adjust = 1;   // option "count_only": 0 keeps the three-pass K8 even when no adjusted value is kept (tests)
   int sort_path_override = -1; // -1 auto, 0 force the CUB radix sort, 1 force the bucket ordering (option "sort_path")
   // MDEGGS_TRACE=1 / option "trace": an event after every eager launch, timeline printed to stderr after the call
   int trace = 0;
@@ -383,7 +386,7 @@ SelArgs make_sel_args(Shard& s, const mdeggs_problem* in, const HostLayout& H, b
 // ---- BH / Bonferroni over a block of percentiles (or the device-chosen best one) -----------------
 int run_adjust(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, int n_segments, int p0, int p_stride,
                const int32_t* best_dev, unsigned long long* sig_dev, double* padj_out, int64_t padj_stride,
-               int act_stride, bool reuse_tiles = false, const SelArgs* sel = nullptr) {
+               int act_stride, bool reuse_tiles = false, const SelArgs* sel = nullptr, bool redo_minima = false) {
   if (n_segments <= 0) return MDEGGS_OK;
   const int64_t E = in->E;
   const int ntiles = (int)((E + BH_TILE - 1) / BH_TILE);
@@ -417,13 +420,28 @@ int run_adjust(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, int n_segmen
   }
   int* done_a = s.seg_done.as<int>();
   int* done_b = done_a + (size_t)in->P * in->K;
+  // count-only block (no adjusted value is kept): the significant counts come from one rank pass, see k_bh_sigrank
+  const bool count_only = sig_dev && !padj_out && !best_dev && !reuse_tiles && ctx->count_only_adjust;
+  if (count_only) {
+    const size_t need = (size_t)in->P * in->K * sizeof(unsigned long long);
+    if (need > s.seg_rank.cap) {
+      CU(s.seg_rank.ensure(need));
+      CU(cudaMemsetAsync(s.seg_rank.p, 0, s.seg_rank.cap, s.s_main));
+    }
+  }
   if (!reuse_tiles)
     LAUNCH(k_bh_count, grid, BH_THREADS, 0, s.s_main, A, s.tile_cnt.as<int32_t>(), s.tile_base.as<long long>(),
            s.seg_n.as<long long>(), done_a);
   if (in->padj == MDEGGS_PADJ_QVALUE && !reuse_tiles)
     LAUNCH(k_qv_pi0, dim3(1, (unsigned)n_segments), BH_THREADS, 0, s.s_main, A, s.tile_base.as<long long>(),
            s.seg_n.as<long long>(), s.seg_pi0.as<double>());
-  if (in->padj != MDEGGS_PADJ_BONFERRONI && !reuse_tiles)
+  if (count_only) {
+    LAUNCH(k_bh_sigrank, grid, BH_THREADS, 0, s.s_main, A, in->padj, s.tile_cnt.as<int32_t>(),
+           s.tile_base.as<long long>(), s.seg_n.as<long long>(), s.seg_rank.as<unsigned long long>(), sig_dev, done_b);
+    return MDEGGS_OK;
+  }
+  // (redo_minima: a count-only pass left the tile counts / ranks of every segment but no tile minima)
+  if (in->padj != MDEGGS_PADJ_BONFERRONI && (!reuse_tiles || redo_minima))
     LAUNCH(k_bh_tilemin, grid, BH_THREADS, 0, s.s_main, A, in->padj, s.tile_cnt.as<int32_t>(),
            s.tile_base.as<long long>(), s.seg_n.as<long long>(), s.tile_min.as<double>(),
            s.tile_carry.as<double>(), done_b);
@@ -961,7 +979,7 @@ int run_shard_back(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
   const bool want_padj_best = out->padj_best && do_adjust;
   const bool shard_p = do_adjust && s.world > 1 && !out->padj;
   const bool keep_all_padj = do_adjust && !shard_p &&
-                             (out->padj || (want_padj_best && (size_t)P * (size_t)E * 8 <= ((size_t)256 << 20)));
+                             (out->padj || (want_padj_best && (size_t)P * (size_t)E * 8 <= (size_t)ctx->padj_keep_cap));
   if (keep_all_padj) {
     if (out->padj && dev_out && emit) d_padj = out->padj;
     else {
@@ -1049,7 +1067,9 @@ int run_shard_back(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
     const int p0 = shard_p ? s.rank : 0, stride = shard_p ? s.world : 1;
     const int n_loc = p0 < P ? (P - p0 + stride - 1) / stride : 0;
     // one rank: the percentile selection rides in the last CTA of k_bh_final (with more ranks it follows the all-reduce)
-    s.select_fused = s.world == 1 && n_loc > 0;
+    const bool count_only = !d_padj && ctx->count_only_adjust;  // (run_adjust takes the k_bh_sigrank path)
+    s.select_fused = s.world == 1 && n_loc > 0 && !count_only;
+    s.partials_complete = !count_only;
     CU(s.small_out.ensure(small_block_bytes(P)));
     SelArgs sel = make_sel_args(s, in, H, emit, c_sig);
     sel.done = reinterpret_cast<unsigned int*>(c_tot + 7 * Pn);
@@ -1099,7 +1119,7 @@ int run_shard_back2(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const m
   const bool want_padj_best = out->padj_best && do_adjust;
   const bool shard_p = do_adjust && s.world > 1 && !out->padj;
   const bool keep_all_padj = do_adjust && !shard_p &&
-                             (out->padj || (want_padj_best && (size_t)P * (size_t)E * 8 <= ((size_t)256 << 20)));
+                             (out->padj || (want_padj_best && (size_t)P * (size_t)E * 8 <= (size_t)ctx->padj_keep_cap));
   double* d_padj = nullptr;
   if (keep_all_padj) d_padj = (out->padj && dev_out && emit) ? out->padj : s.padj.as<double>();
   const unsigned long long* sig_src = dev_adjust ? c_sig : c_raw;
@@ -1118,7 +1138,8 @@ int run_shard_back2(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const m
     // single rank: the tile partials of every percentile are still there, only the final pass is repeated;
     // sharded K8: this rank may not own the best percentile, so the whole adjustment is rerun for it
     int rc = shard_p ? run_adjust(ctx, s, in, K, 0, 1, d_best, nullptr, s.padj_best.as<double>(), E, act_stride)
-                     : run_adjust(ctx, s, in, K, 0, 1, d_best, nullptr, s.padj_best.as<double>(), E, act_stride, true);
+                     : run_adjust(ctx, s, in, K, 0, 1, d_best, nullptr, s.padj_best.as<double>(), E, act_stride, true,
+                                  nullptr, !s.partials_complete);
     if (rc) return rc;
   }
   // device callers: these two rows are produced by k_emit straight into the caller's buffers
@@ -1700,6 +1721,16 @@ int mdeggs_set_option(mdeggs_ctx* ctx, const char* name, int64_t value) {
   }
   if (!strcmp(name, "zero_copy")) {
     ctx->zero_copy = (int)value;
+    ctx->key_valid = false;
+    return MDEGGS_OK;
+  }
+  if (!strcmp(name, "padj_keep_cap")) {
+    ctx->padj_keep_cap = value < 0 ? 0 : value;
+    ctx->key_valid = false;
+    return MDEGGS_OK;
+  }
+  if (!strcmp(name, "count_only")) {
+    ctx->count_only_adjust = (int)value;
     ctx->key_valid = false;
     return MDEGGS_OK;
   }

@@ -815,14 +815,30 @@ __device__ __forceinline__ bool bh_segment(const BhArgs& A, int& p, int& c, size
 __device__ __forceinline__ void bh_load(const BhArgs& A, int p, int c, int64_t tile0, int (&flag)[BH_ITEMS],
                                         double (&pv)[BH_ITEMS]) {
   const int64_t nv = (int64_t)*A.n_valid;
+  const int64_t j0 = tile0 + (int64_t)threadIdx.x * BH_ITEMS;
+  const uint8_t* __restrict__ row = A.act + (size_t)p * A.act_stride;
+  static_assert(BH_ITEMS == 4, "vector path below loads 4 items per thread");
+  if (j0 + BH_ITEMS <= nv) {  // whole quad valid: 16-byte loads (j0 is a multiple of 4, the arrays are 256-byte aligned)
+    const int4 a4 = *reinterpret_cast<const int4*>(A.sa + j0);
+    const int4 b4 = *reinterpret_cast<const int4*>(A.sb + j0);
+    const double2 p01 = *reinterpret_cast<const double2*>(A.ps + j0);
+    const double2 p23 = *reinterpret_cast<const double2*>(A.ps + j0 + 2);
+    const int a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+    const double pp[4] = {p01.x, p01.y, p23.x, p23.y};
+#pragma unroll
+    for (int it = 0; it < BH_ITEMS; ++it) {
+      flag[it] = edge_category(row[a[it]], row[b[it]]) == c;
+      pv[it] = pp[it];
+    }
+    return;
+  }
 #pragma unroll
   for (int it = 0; it < BH_ITEMS; ++it) {
-    int64_t j = tile0 + (int64_t)threadIdx.x * BH_ITEMS + it;
+    const int64_t j = j0 + it;
     flag[it] = 0;
     pv[it] = 0.0;
     if (j < nv) {
-      int cc = edge_category(A.act[(size_t)p * A.act_stride + A.sa[j]], A.act[(size_t)p * A.act_stride + A.sb[j]]);
-      flag[it] = (cc == c);
+      flag[it] = edge_category(row[A.sa[j]], row[A.sb[j]]) == c;
       pv[it] = A.ps[j];
     }
   }
@@ -982,6 +998,71 @@ __global__ void __launch_bounds__(BH_THREADS) k_bh_tilemin(BhArgs A, int mode, c
     if (threadIdx.x == 0) tile_min[seg * A.ntiles + blockIdx.x] = tmn;
   }
   if (bh_last_of_segment(seg_done, seg, A.ntiles)) bh_suffix_body(tile_min, A.ntiles, mode, seg, tile_carry);
+}
+
+// Count-only adjustment (no adjusted value leaves the device for this percentile block: big jobs keep only the best
+// percentile's row, which is recomputed afterwards).  The number of members with p.adj < 0.05 needs no cumulative
+// min/max at all: with v_i the value that enters the cummin (BH, BY, hochberg, q.value; i = ascending rank) the
+// adjusted value q_i = f(min_{j >= i} v_j) with f monotone (pmin(1, .), times pi0 for q.value), hence
+//   q_i < 0.05  <=>  some j >= i has f(v_j) < 0.05  <=>  i <= max{ j : f(v_j) < 0.05 }    (the BH step-up rule),
+// and for holm (cummax from the smallest p)  q_i < 0.05  <=>  i < min{ j : f(v_j) >= 0.05 }.
+// So one pass after the rank pass finds, per segment, t_max = max rank with f(v) < 0.05 (holm: max of n + 1 - rank
+// over the members with f(v) >= 0.05, count = n - t_max); the last CTA of the segment adds the count to sig[p] and
+// re-arms the accumulator.  bonferroni: v = n p, same rule.  f(v) is evaluated exactly as k_bh_final evaluates q.
+__global__ void __launch_bounds__(BH_THREADS) k_bh_sigrank(BhArgs A, int mode, const int32_t* __restrict__ tile_cnt,
+                                                          const long long* __restrict__ tile_base,
+                                                          const long long* __restrict__ seg_n,
+                                                          unsigned long long* __restrict__ seg_rank,
+                                                          unsigned long long* __restrict__ sig,
+                                                          int* __restrict__ seg_done) {
+  int p, c;
+  size_t seg;
+  if (!bh_segment(A, p, c, seg)) return;
+  if (A.tot && A.tot[p] == 0) return;  // (same whole-segment exit as pass A)
+  typedef cub::BlockScan<int, BH_THREADS> Scan;
+  typedef cub::BlockReduce<long long, BH_THREADS> Reduce;
+  __shared__ union {
+    typename Scan::TempStorage scan;
+    typename Reduce::TempStorage red;
+  } tmp;
+  const bool holm = mode == MDEGGS_PADJ_HOLM;
+  const long long n_ll = seg_n[seg];
+  if (tile_cnt[seg * A.ntiles + blockIdx.x] != 0) {
+    int flag[BH_ITEMS], rank[BH_ITEMS];
+    double pv[BH_ITEMS];
+    bh_load(A, p, c, (int64_t)blockIdx.x * BH_TILE, flag, pv);
+    Scan(tmp.scan).InclusiveSum(flag, rank);
+    __syncthreads();
+    const long long base = tile_base[seg * A.ntiles + blockIdx.x];
+    const double n = (double)n_ll;
+    const double num = adj_numerator(mode, n);
+    const double pi0 = mode == MDEGGS_PADJ_QVALUE ? A.seg_pi0[seg] : 1.0;
+    long long t = 0;
+#pragma unroll
+    for (int it = 0; it < BH_ITEMS; ++it)
+      if (flag[it]) {
+        const long long i = base + rank[it];
+        double q = mode == MDEGGS_PADJ_BONFERRONI ? __dmul_rn(n, pv[it]) : adj_value(mode, n, num, i, pv[it]);
+        q = fmin(1.0, q);
+        if (mode == MDEGGS_PADJ_QVALUE) q = __dmul_rn(pi0, q);
+        const bool good = q < 0.05;  // (NaN pi0: never significant, as in k_bh_final)
+        if (holm) {
+          if (!good) t = max(t, n_ll + 1 - i);
+        } else if (good) {
+          t = max(t, i);
+        }
+      }
+    t = Reduce(tmp.red).Reduce(t, cub::Max());
+    if (threadIdx.x == 0 && t > 0) atomicMax(seg_rank + seg, (unsigned long long)t);
+  }
+  if (bh_last_of_segment(seg_done, seg, A.ntiles)) {
+    if (threadIdx.x == 0) {
+      const long long tmax = (long long)__ldcg(seg_rank + seg);
+      const long long cnt = holm ? n_ll - tmax : tmax;
+      seg_rank[seg] = 0ull;
+      if (cnt > 0) atomicAdd(&sig[p], (unsigned long long)cnt);
+    }
+  }
 }
 
 // q.value: pi0 of every segment (qvalue::pi0est, smoother method; core_functions.R:1012-1025)

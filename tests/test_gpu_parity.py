@@ -810,3 +810,41 @@ def test_device_resident_caller_equals_host_caller(K, method, padj):
     finally:
         eng.close()
         href.close()
+
+
+# ---- K8 without keeping the adjusted values: significant counts from one rank pass, best row re-adjusted ----
+@pytest.mark.parametrize("padj", [_abi.PADJ_BH, _abi.PADJ_BONFERRONI, _abi.PADJ_HOLM, _abi.PADJ_HOCHBERG, _abi.PADJ_BY,
+                                  _abi.PADJ_QVALUE])
+@pytest.mark.parametrize("K,E,seed", [(2, 3000, 1401), (3, 5000, 1402), (2, 40, 1403)])
+def test_count_only_adjustment_equals_three_pass(padj, K, E, seed):
+    """Big jobs do not keep P x E adjusted values: K8 then counts p.adj < 0.05 with the step-up rule (k_bh_sigrank) and
+    re-adjusts only the chosen percentile.  Forced here on small problems ("padj_keep_cap" = 0) and compared, bit for
+    bit, with the path that keeps everything; also with "count_only" = 0 (three passes + final-pass rerun)."""
+    want = tuple(f for f in ALL_FIELDS if f != "padj")
+    prob = synth.random_problem(200, 60, E, K, seed, _abi.METHOD_LM, padj)
+    # plant some strong pairs so that several percentiles have significant counts > 0
+    rng = np.random.default_rng(seed)
+    a = np.asfortranarray(prob.assay.copy())
+    for e in rng.choice(E, size=max(4, E // 40), replace=False):
+        i, j = prob.from_idx[e] - 1, prob.to_idx[e] - 1
+        cols = np.flatnonzero(np.asarray(prob.group) == 1)
+        a[j, cols] = a[i, cols] * (1.5 + 0.01 * rng.standard_normal(cols.size)) + 0.05 * rng.standard_normal(cols.size)
+    prob.assay[...] = a
+    full = md.Engine([0])
+    engs = {}
+    try:
+        ref = full.run_omic(prob, ALL_FIELDS)
+        assert ref["sig_count"].max() > 0
+        for name, opts in (("count", {"padj_keep_cap": 0}), ("three", {"padj_keep_cap": 0, "count_only": 0})):
+            e = md.Engine([0])
+            engs[name] = e
+            for k, v in opts.items():
+                e.set_option(k, v)
+            for rep in range(3):  # eager, capture, replay
+                got = e.run_omic(prob, want)
+                for f in want:
+                    assert np.array_equal(got[f], ref[f], equal_nan=True), (name, rep, f)
+    finally:
+        full.close()
+        for e in engs.values():
+            e.close()
