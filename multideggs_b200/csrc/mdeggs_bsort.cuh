@@ -134,8 +134,10 @@ __global__ void __launch_bounds__(256) k_bsort_count(BsArgs B, const double* __r
 //   mode 1: pf(F, df1, df2, lower.tail=FALSE)  core_functions.R:968 (aov) / 920 (f.robftest)
 //   do_bs: also drop the edge into its p-value bucket (single-GPU runs: every edge is finished here)
 // ------------------------------------------------------------------------------------------------
+constexpr int FIN_THREADS = 256;  // (<= 256: the queue holds thread ids as bytes)
+constexpr int FIN_CF_BUDGET = 24;  // terms of the first try (6 rounds of 4)
 template <int K>
-__global__ void __launch_bounds__(128) k_finish(int src, const double* __restrict__ sxy, const double* __restrict__ S,
+__global__ void __launch_bounds__(FIN_THREADS) k_finish(int src, const double* __restrict__ sxy, const double* __restrict__ S,
                                                 int nn, SegLayout L, const int32_t* __restrict__ ea,
                                                 const int32_t* __restrict__ eb,
                                                 const double* __restrict__ mean, const double* __restrict__ sxx,
@@ -144,12 +146,14 @@ __global__ void __launch_bounds__(128) k_finish(int src, const double* __restric
                                                 const double* __restrict__ lbeta_p, double* __restrict__ stat,
                                                 int32_t* __restrict__ status, double* __restrict__ coef,
                                                 double* __restrict__ p_out, const int32_t* __restrict__ err,
-                                                int do_bs, BsArgs B) {
+                                                int do_bs, BsArgs B, int32_t* __restrict__ fin_q,
+                                                unsigned int* __restrict__ fin_nq) {
   const int64_t e = e_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = e < e_hi && !*err;
   double p = 0.0;
-  if (live) {
+  bool deferred = false;
   tc.lbeta_ab = *lbeta_p;
+  if (live) {
   if (src != 2) {
     const int a = ea[e], b = eb[e];
     if (a == b || bad[a] || bad[b]) {
@@ -174,10 +178,56 @@ __global__ void __launch_bounds__(128) k_finish(int src, const double* __restric
   const int st = status[e];
   if (st == MDEGGS_EDGE_SINGULAR || st == MDEGGS_EDGE_NONFINITE || st == MDEGGS_EDGE_ZERO_SCALE) p = nan("");
   else if (st == MDEGGS_EDGE_SELFLOOP) p = 1.0;
-  else p = (mode == 0) ? p_two_sided_ref_tab(tc, stat[e], df2) : pf_upper_tab(tc, stat[e], df1, df2);
-  p_out[e] = p;
+  else {
+    // fin_q: first try a short continued fraction (enough away from the mode of the distribution); the edges that
+    // need the long one (O(sqrt(max(a, b))) terms, a deep dependent FP64 chain) are queued for k_finish_slow, where
+    // every lane is such an edge, instead of holding their whole warps here
+    bool ok = true;
+    const double sv = stat[e];
+    const int budget = fin_q ? FIN_CF_BUDGET : CF_TABLE_LEN;
+    p = (mode == 0) ? p_two_sided_ref_tab(tc, sv, df2, budget, fin_q ? &ok : nullptr)
+                    : pf_upper_tab(tc, sv, df1, df2, budget, fin_q ? &ok : nullptr);
+    deferred = !ok;
   }
-  if (do_bs) bs_count(B, live, e, p);  // reached by every thread of the CTA
+  }
+  if (fin_q) {  // warp-aggregated append (whole warps reach this point)
+    const unsigned m = __ballot_sync(0xffffffffu, deferred);
+    if (m) {
+      const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+      unsigned int base = 0;
+      if (lane == leader) base = atomicAdd(fin_nq, (unsigned int)__popc(m));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (deferred) fin_q[base + __popc(m & ((1u << lane) - 1u))] = (int32_t)(e - e_lo);
+    }
+  }
+  const bool done = live && !deferred;
+  if (done) p_out[e] = p;
+  if (do_bs) bs_count(B, done, e, p);  // reached by every thread of the CTA
+}
+
+// the queued edges of k_finish: full-length continued fraction, every lane busy
+__global__ void __launch_bounds__(256) k_finish_slow(const int32_t* __restrict__ fin_q,
+                                                     const unsigned int* __restrict__ fin_nq, int64_t e_lo, int mode,
+                                                     double df1, double df2, TailConsts tc,
+                                                     const double* __restrict__ lbeta_p,
+                                                     const double* __restrict__ stat, double* __restrict__ p_out,
+                                                     const int32_t* __restrict__ err, int do_bs, BsArgs B) {
+  if (*err) return;
+  tc.lbeta_ab = *lbeta_p;
+  const unsigned int nq = *fin_nq;
+  for (unsigned int i0 = blockIdx.x * blockDim.x; i0 < nq; i0 += gridDim.x * blockDim.x) {
+    const unsigned int i = i0 + threadIdx.x;
+    const bool live = i < nq;
+    int64_t e = 0;
+    double p = 0.0;
+    if (live) {
+      e = e_lo + fin_q[i];
+      const double sv = stat[e];
+      p = (mode == 0) ? p_two_sided_ref_tab(tc, sv, df2) : pf_upper_tab(tc, sv, df1, df2);
+      p_out[e] = p;
+    }
+    if (do_bs) bs_count(B, live, e, p);
+  }
 }
 
 

@@ -61,7 +61,8 @@ struct DevBuf {
 enum Ev { EV_START, EV_H2D, EV_GATHER, EV_STATS, EV_FIT, EV_TAIL, EV_COLL, EV_PERC, EV_ADJ, EV_END, EV_Q0, EV_Q1, EV_COUNT };
 
 // scalar slots in the `scal` buffer (8-byte each)
-enum Scal { SC_NNODES = 0, SC_ERR = 1, SC_BEST = 2, SC_NVALID = 3, SC_ROWLO = 4, SC_ROWHI = 5, SC_DONE = 6, SC_COUNT = 8 };
+enum Scal { SC_NNODES = 0, SC_ERR = 1, SC_BEST = 2, SC_NVALID = 3, SC_ROWLO = 4, SC_ROWHI = 5, SC_DONE = 6, SC_FINQ = 7, SC_COUNT = 8 };
+constexpr int64_t FIN_DEFER_MIN_EDGES = 1 << 16;  // below this a second launch costs more than the slow lanes
 
 struct Shard {
   int device = 0, rank = 0, world = 1;
@@ -88,11 +89,11 @@ struct Shard {
     if (e == cudaSuccess) h_stage_cap = bytes + 256;
     return e;
   }
-  DevBuf assay, from, to, ea, eb, stage_dev, bs_count, bs_slot, seg_done, seg_rank, seg_pi0, B16, stamps, excl, node_of_row, rowlist, scal, src_of_pos, pct, cutoff, D, cub_tmp, mean, sxx, med, bad, stat, status, p_edge, coef, iters, act, counters, sortk, sortk2, idx,
+  DevBuf assay, from, to, ea, eb, stage_dev, bs_count, bs_slot, seg_done, seg_rank, fin_q, seg_pi0, B16, stamps, excl, node_of_row, rowlist, scal, src_of_pos, pct, cutoff, D, cub_tmp, mean, sxx, med, bad, stat, status, p_edge, coef, iters, act, counters, sortk, sortk2, idx,
       idx2, ps, sa, sb, tile_cnt, tile_base, seg_n, tile_min, tile_carry, padj_best, cat_best, cat, padj, med_out,
       small_out, rsel_hist, rsel_state, rsel_cand, dense_S, cf_tab, sxy;
   void release_all() {
-    DevBuf* all[] = {&assay, &from, &to, &ea, &eb, &stage_dev, &bs_count, &bs_slot, &seg_done, &seg_rank, &seg_pi0, &B16, &stamps, &excl, &node_of_row, &rowlist, &scal, &src_of_pos, &pct, &cutoff,
+    DevBuf* all[] = {&assay, &from, &to, &ea, &eb, &stage_dev, &bs_count, &bs_slot, &seg_done, &seg_rank, &fin_q, &seg_pi0, &B16, &stamps, &excl, &node_of_row, &rowlist, &scal, &src_of_pos, &pct, &cutoff,
                      &D, &cub_tmp, &mean, &sxx, &med, &bad, &stat, &status, &p_edge,
                      &coef, &iters, &act, &counters, &sortk, &sortk2, &idx, &idx2, &ps, &sa, &sb, &tile_cnt,
                      &tile_base, &seg_n, &tile_min, &tile_carry, &padj_best, &cat_best, &cat, &padj, &med_out,
@@ -331,10 +332,22 @@ template <int K>
 void launch_finish(mdeggs_ctx* ctx, Shard& s, const SegLayout& L, int src, int nn, int64_t e_lo, int64_t e_hi, int mode,
                    double df1, double df2, const TailConsts& tc, const double* d_lbeta, double* coef, int do_bs,
                    const BsArgs& B) {
-  LAUNCH(k_finish<K>, blocks_for(e_hi - e_lo, 128), 128, 0, s.s_main, src, s.sxy.as<double>(), s.dense_S.as<double>(),
+  // tails that need the continued fraction (everything but the closed-form F with 2 numerator degrees of freedom):
+  // on big edge lists the few slow lanes are queued and finished by a second, dense launch
+  const int64_t ne = e_hi - e_lo;
+  const bool defer = ne >= FIN_DEFER_MIN_EDGES && !(mode == 1 && df1 == 2.0);
+  int32_t* fin_q = nullptr;
+  unsigned int* fin_nq = s.scal.as<unsigned int>() + 2 * SC_FINQ;
+  if (defer) fin_q = s.fin_q.as<int32_t>();  // (sized by the caller)
+  LAUNCH(k_finish<K>, blocks_for(ne, FIN_THREADS), FIN_THREADS, 0, s.s_main, src, s.sxy.as<double>(), s.dense_S.as<double>(),
          nn, L, s.ea.as<int32_t>(), s.eb.as<int32_t>(), s.mean.as<double>(),
          s.sxx.as<double>(), s.bad.as<uint8_t>(), e_lo, e_hi, mode, df1, df2, tc, d_lbeta, s.stat.as<double>(),
-         s.status.as<int32_t>(), coef, s.p_edge.as<double>(), s.scal.as<int32_t>() + 2 * SC_ERR, do_bs, B);
+         s.status.as<int32_t>(), coef, s.p_edge.as<double>(), s.scal.as<int32_t>() + 2 * SC_ERR, do_bs, B, fin_q, fin_nq);
+  if (defer) {
+    const unsigned want = blocks_for(ne, 256);
+    LAUNCH(k_finish_slow, want < 148u * 8 ? want : 148u * 8, 256, 0, s.s_main, fin_q, fin_nq, e_lo, mode, df1, df2, tc,
+           d_lbeta, s.stat.as<double>(), s.p_edge.as<double>(), s.scal.as<int32_t>() + 2 * SC_ERR, do_bs, B);
+  }
 }
 
 BsArgs make_bs_args(Shard& s, int64_t E) {
@@ -882,6 +895,7 @@ int run_shard_main(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
       CU(cudaMemsetAsync(s.bs_count.p, 0, (size_t)(NB + 1) * 4, s.s_main));
       B = make_bs_args(s, E);
     }
+    if (e_hi - e_lo >= FIN_DEFER_MIN_EDGES) CU(s.fin_q.ensure((size_t)(e_hi - e_lo) * 4));  // queue of slow tails
     switch (K) {
       case 2: launch_finish<2>(ctx, s, L, src, n_nodes, e_lo, e_hi, tail_mode, df1, df2, tc, d_lbeta, d_coef, do_bs, B); break;
       case 3: launch_finish<3>(ctx, s, L, src, n_nodes, e_lo, e_hi, tail_mode, df1, df2, tc, d_lbeta, d_coef, do_bs, B); break;

@@ -157,10 +157,15 @@ __global__ void k_cf_tables(double a, double b, double* __restrict__ e_ab, doubl
 }
 
 // continued fraction value h(x) = 1/(1 + d_1/(1 + d_2/(1 + ...))), d_j = x e_j
-__device__ inline double beta_cf_tab(const double* __restrict__ e, double a, double b, double x) {
+// `budget` (a multiple of 4) bounds the number of terms; when it is exhausted and `ok` is given, *ok = false and the
+// caller retries later with the full table (k_finish: the slow lanes of a CTA are compacted first, so that a few lanes
+// near the mode of the distribution - O(sqrt(max(a, b))) terms - do not hold their whole warps for the duration)
+__device__ inline double beta_cf_tab(const double* __restrict__ e, double a, double b, double x,
+                                     int budget = CF_TABLE_LEN, bool* ok = nullptr) {
   double Am = 0.0, A = 1.0, Bm = 1.0, B = 1.0;  // (A_0, A_1), (B_0, B_1)
   double f_old = 1.0;
-  for (int j = 0; j < CF_TABLE_LEN; j += 4) {
+  const int jmax = budget < CF_TABLE_LEN ? budget : CF_TABLE_LEN;
+  for (int j = 0; j < jmax; j += 4) {
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       double d = x * __ldg(e + j + u);
@@ -178,11 +183,16 @@ __device__ inline double beta_cf_tab(const double* __restrict__ e, double a, dou
     if (fabs(A - f_old) <= 4e-16 * fabs(A)) return A;
     f_old = A;
   }
+  if (ok) {
+    *ok = false;
+    return 0.0;
+  }
   return beta_cf_dev(a, b, x);  // table exhausted (never seen for |t| < 40, df < 1e6): generic Lentz
 }
 
 // pbeta_xy for the run's (a, b) pair; `swapped` = the caller's first parameter is tc.b
-__device__ inline double pbeta_xy_tab(const TailConsts& tc, bool swapped, double x, double y, bool lower) {
+__device__ inline double pbeta_xy_tab(const TailConsts& tc, bool swapped, double x, double y, bool lower,
+                                      int budget = CF_TABLE_LEN, bool* ok = nullptr) {
   const double a = swapped ? tc.b : tc.a, b = swapped ? tc.a : tc.b;
   if (isnan(x) || isnan(y)) return nan("");
   if (x <= 0.0) return lower ? 0.0 : 1.0;
@@ -191,15 +201,16 @@ __device__ inline double pbeta_xy_tab(const TailConsts& tc, bool swapped, double
   double ly = (y < 0.5) ? log(y) : log1p(-x);
   double front = exp(a * lx + b * ly - tc.lbeta_ab);
   if (x < (a + 1.0) / (a + b + 2.0)) {
-    double w = front * beta_cf_tab(swapped ? tc.e_ba : tc.e_ab, a, b, x) / a;
+    double w = front * beta_cf_tab(swapped ? tc.e_ba : tc.e_ab, a, b, x, budget, ok) / a;
     return lower ? w : 1.0 - w;
   }
-  double w1 = front * beta_cf_tab(swapped ? tc.e_ab : tc.e_ba, b, a, y) / b;
+  double w1 = front * beta_cf_tab(swapped ? tc.e_ab : tc.e_ba, b, a, y, budget, ok) / b;
   return lower ? 1.0 - w1 : w1;
 }
 
 // 2 * (1 - pt(|t|, n)) with tc = {0.5, n/2}: same composition as p_two_sided_ref_dev
-__device__ inline double p_two_sided_ref_tab(const TailConsts& tc, double t, double n) {
+__device__ inline double p_two_sided_ref_tab(const TailConsts& tc, double t, double n, int budget = CF_TABLE_LEN,
+                                             bool* ok = nullptr) {
   if (isnan(t)) return nan("");
   double x = fabs(t), u;
   if (isinf(x)) {
@@ -208,10 +219,10 @@ __device__ inline double p_two_sided_ref_tab(const TailConsts& tc, double t, dou
     double val;
     if (n > x * x) {
       double den = n + x * x;
-      val = pbeta_xy_tab(tc, false, x * x / den, n / den, false);
+      val = pbeta_xy_tab(tc, false, x * x / den, n / den, false, budget, ok);
     } else {
       double nx = 1.0 + (x / n) * x;
-      val = pbeta_xy_tab(tc, true, 1.0 / nx, (x / n) * x / nx, true);
+      val = pbeta_xy_tab(tc, true, 1.0 / nx, (x / n) * x / nx, true, budget, ok);
     }
     val *= 0.5;
     u = (x <= 0.0) ? val : __dadd_rn(__dsub_rn(0.5, val), 0.5);
@@ -230,14 +241,15 @@ __device__ __forceinline__ double pf_upper_d1_2(double f, double d2) {
 }
 
 // pf(f, d1, d2, lower.tail = FALSE) with tc = {d1/2, d2/2}
-__device__ inline double pf_upper_tab(const TailConsts& tc, double f, double d1, double d2) {
+__device__ inline double pf_upper_tab(const TailConsts& tc, double f, double d1, double d2, int budget = CF_TABLE_LEN,
+                                      bool* ok = nullptr) {
   if (isnan(f)) return nan("");
   if (f <= 0.0) return 1.0;
   if (isinf(f)) return 0.0;
   if (d1 == 2.0) return pf_upper_d1_2(f, d2);
   double den = d2 + d1 * f;
-  if (d1 * f > d2) return pbeta_xy_tab(tc, true, d2 / den, d1 * f / den, true);
-  return pbeta_xy_tab(tc, false, d1 * f / den, d2 / den, false);
+  if (d1 * f > d2) return pbeta_xy_tab(tc, true, d2 / den, d1 * f / den, true, budget, ok);
+  return pbeta_xy_tab(tc, false, d1 * f / den, d2 / den, false, budget, ok);
 }
 
 }  // namespace mdeggs
