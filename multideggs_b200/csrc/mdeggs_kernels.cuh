@@ -751,7 +751,10 @@ __global__ void k_best_rows(const int32_t* __restrict__ ea, const int32_t* __res
 // Three passes over 1024-element tiles with tile-level partials (count -> ranks -> suffix-min).
 // ------------------------------------------------------------------------------------------------
 constexpr int BH_THREADS = 256;
-constexpr int BH_ITEMS = 4;
+#ifndef BH_ITEMS_N
+#define BH_ITEMS_N 8
+#endif
+constexpr int BH_ITEMS = BH_ITEMS_N;
 constexpr int BH_TILE = BH_THREADS * BH_ITEMS;
 
 __global__ void k_sort_keys(const double* __restrict__ p_edge, int64_t E, unsigned long long* __restrict__ keys,
@@ -817,18 +820,21 @@ __device__ __forceinline__ void bh_load(const BhArgs& A, int p, int c, int64_t t
   const int64_t nv = (int64_t)*A.n_valid;
   const int64_t j0 = tile0 + (int64_t)threadIdx.x * BH_ITEMS;
   const uint8_t* __restrict__ row = A.act + (size_t)p * A.act_stride;
-  static_assert(BH_ITEMS == 4, "vector path below loads 4 items per thread");
-  if (j0 + BH_ITEMS <= nv) {  // whole quad valid: 16-byte loads (j0 is a multiple of 4, the arrays are 256-byte aligned)
-    const int4 a4 = *reinterpret_cast<const int4*>(A.sa + j0);
-    const int4 b4 = *reinterpret_cast<const int4*>(A.sb + j0);
-    const double2 p01 = *reinterpret_cast<const double2*>(A.ps + j0);
-    const double2 p23 = *reinterpret_cast<const double2*>(A.ps + j0 + 2);
-    const int a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
-    const double pp[4] = {p01.x, p01.y, p23.x, p23.y};
+  static_assert(BH_ITEMS % 4 == 0, "vector path below loads quads");
+  if (j0 + BH_ITEMS <= nv) {  // all items valid: 16-byte loads (j0 is a multiple of 4, the arrays are 256-byte aligned)
 #pragma unroll
-    for (int it = 0; it < BH_ITEMS; ++it) {
-      flag[it] = edge_category(row[a[it]], row[b[it]]) == c;
-      pv[it] = pp[it];
+    for (int q = 0; q < BH_ITEMS / 4; ++q) {
+      const int4 a4 = *reinterpret_cast<const int4*>(A.sa + j0 + 4 * q);
+      const int4 b4 = *reinterpret_cast<const int4*>(A.sb + j0 + 4 * q);
+      const double2 p01 = *reinterpret_cast<const double2*>(A.ps + j0 + 4 * q);
+      const double2 p23 = *reinterpret_cast<const double2*>(A.ps + j0 + 4 * q + 2);
+      const int a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+      const double pp[4] = {p01.x, p01.y, p23.x, p23.y};
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        flag[4 * q + it] = edge_category(row[a[it]], row[b[it]]) == c;
+        pv[4 * q + it] = pp[it];
+      }
     }
     return;
   }
