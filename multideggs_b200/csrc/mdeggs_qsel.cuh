@@ -36,7 +36,8 @@ constexpr int QS_SUB = 64;           // equal-width sub-bins per cell
 constexpr int QS_BINS = QS_CELLS * QS_SUB;
 constexpr int QS_SAMPLE = 1024;      // sample size (a single-CTA sort: kept small; it only shapes the bins)
 constexpr int QS_SAMPLE_MAX = QS_SAMPLE;
-constexpr int QS_SAMPLE_THREADS = 256;
+constexpr int QS_SAMPLE_THREADS = QS_SAMPLE / 2;  // one compare-exchange pair per thread in every sorting step
+static_assert(QS_SAMPLE_THREADS <= 1024 && QS_SAMPLE_THREADS % 32 == 0, "single CTA");
 constexpr int QS_FIN_CAP = 4096;     // keys a finish CTA keeps in shared memory (32 KB); longer lists stay in L2
 constexpr unsigned int QS_SLOT_MAX = 1u << 20;  // slots with more values are not compacted ("fat": tie groups)
 constexpr unsigned int QS_CAND_MAX = 8u << 20;  // candidate buffer, keys
@@ -137,23 +138,23 @@ __global__ void __launch_bounds__(QS_SAMPLE_THREADS) k_qs_sample(const double* _
   };
   if (total > S) {
     const unsigned jit = (unsigned)(ends / S + 1);
-    for (int i0 = 0; i0 < S; i0 += 4 * QS_SAMPLE_THREADS) {  // 4 independent draws per thread in flight
-      int64_t off[4];
-      double v[4];
+    for (int i0 = 0; i0 < S; i0 += 2 * QS_SAMPLE_THREADS) {  // 2 independent draws per thread in flight
+      int64_t off[2];
+      double v[2];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < 2; ++u) {
         const int i = i0 + u * QS_SAMPLE_THREADS + threadIdx.x;
         const unsigned h = (unsigned)i * 2654435761u;
         long long j = ((long long)i * ends) / S + (long long)((h >> 20) % jit);
         j = j < ends ? j : ends - 1;
         const int smp = (int)((h >> 4) % (unsigned)n);
-        const int64_t row = row_of_end(j);
+        const int64_t row = i < S ? row_of_end(j) : -1;
         off[u] = row < 0 ? -1 : (colmajor ? row + (int64_t)smp * ld : row * ld + smp);
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) v[u] = off[u] >= 0 ? __ldg(assay + off[u]) : nan("");
+      for (int u = 0; u < 2; ++u) v[u] = off[u] >= 0 ? __ldg(assay + off[u]) : nan("");
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < 2; ++u) {
         const unsigned long long k = dkey(v[u]);
         if (k != ~0ull) sk[atomicAdd(&s_m, 1)] = k;
       }
@@ -169,30 +170,22 @@ __global__ void __launch_bounds__(QS_SAMPLE_THREADS) k_qs_sample(const double* _
   }
   __syncthreads();
   const int m = s_m;
-  // bitonic sort of the S slots (unused slots hold the maximum key and stay at the end); the pairs of a thread are
-  // loaded together so that their shared-memory latencies overlap
+  // bitonic sort of the S slots (unused slots hold the maximum key and stay at the end), one pair per thread and
+  // step.  For j <= 32 the 32 pairs of a warp live in its own 64 consecutive slots, so those steps (45 of the 55)
+  // only need a warp barrier; a CTA barrier is needed when the step that follows reaches across warps.
   for (int k = 2; k <= S; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int t0 = 0; t0 < S / 2; t0 += QS_SAMPLE_THREADS * 4) {
-        unsigned long long a[4], b[4];
-        int ii[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int t = t0 + u * QS_SAMPLE_THREADS + threadIdx.x;
-          ii[u] = t < S / 2 ? (((t & ~(j - 1)) << 1) | (t & (j - 1))) : -1;
-          if (ii[u] >= 0) {
-            a[u] = sk[ii[u]];
-            b[u] = sk[ii[u] | j];
-          }
+      for (int t = threadIdx.x; t < S / 2; t += QS_SAMPLE_THREADS) {
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        const unsigned long long a = sk[i], b = sk[i | j];
+        if ((a > b) == ((i & k) == 0)) {
+          sk[i] = b;
+          sk[i | j] = a;
         }
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-          if (ii[u] >= 0 && ((a[u] > b[u]) == ((ii[u] & k) == 0))) {
-            sk[ii[u]] = b[u];
-            sk[ii[u] | j] = a[u];
-          }
       }
-      __syncthreads();
+      const int next_j = j > 1 ? (j >> 1) : k;  // first step of the next merge: j' = (2k) / 2
+      if (S / 2 <= QS_SAMPLE_THREADS && j <= 32 && next_j <= 32) __syncwarp();
+      else __syncthreads();
     }
   }
   const double base = m > 0 ? dkey_inv(sk[0]) : 0.0;
