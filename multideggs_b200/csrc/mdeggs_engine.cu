@@ -363,14 +363,6 @@ BsArgs make_bs_args(Shard& s, int64_t E) {
   return B;
 }
 
-int copy_out(mdeggs_ctx* ctx, Shard& s, void* dst, const void* src, size_t bytes, int mem) {
-  if (!dst || bytes == 0) return MDEGGS_OK;
-  CU(cudaMemcpyAsync(dst, src, bytes, mem == MDEGGS_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
-                     s.s_main));
-  if (mem == MDEGGS_MEM_HOST) ctx->stats.d2h_bytes += (int64_t)bytes;
-  return MDEGGS_OK;
-}
-
 // arguments of the percentile selection (k_select_best, or the tail of k_bh_final)
 SelArgs make_sel_args(Shard& s, const mdeggs_problem* in, const HostLayout& H, bool emit,
                       const unsigned long long* sig_src) {
@@ -617,7 +609,7 @@ int run_shard_front(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, int32_t
   }
   // K3 S0 on the side stream, beside K0: sample -> knots of the quantile bins (needs only the inputs)
   if (E > 0 && in->P > 0) {
-    const int P = in->P, n = in->n;
+    const int n = in->n;
     if ((size_t)QS_BINS * 4 > s.rsel_hist.cap) {  // the scan kernel leaves the histogram zeroed for the next call
       CU(s.rsel_hist.ensure((size_t)QS_BINS * 4));
       CU(cudaMemsetAsync(s.rsel_hist.p, 0, (size_t)QS_BINS * 4, s.s_main));
@@ -673,7 +665,7 @@ int run_shard_front(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, int32_t
 int run_shard_main(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const mdeggs_result* out, const HostLayout& H,
                    int32_t n_nodes) {
   const SegLayout& L = H.L;
-  const int G = in->G, n = in->n, K = in->K, P = in->P;
+  const int n = in->n, K = in->K, P = in->P;
   const int64_t E = in->E;
   CU(cudaSetDevice(s.device));
   const int32_t* d_nn = s.scal.as<int32_t>() + 2 * SC_NNODES;
@@ -950,9 +942,8 @@ int run_collective(mdeggs_ctx* ctx, const mdeggs_problem* in, const mdeggs_resul
 
 int run_shard_back(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const mdeggs_result* out, const HostLayout& H,
                    int32_t n_nodes, bool emit) {
-  const int G = in->G, n = in->n, K = in->K, P = in->P;
+  const int K = in->K, P = in->P;
   const int64_t E = in->E;
-  (void)n;
   CU(cudaSetDevice(s.device));
   const int32_t* d_nn = s.scal.as<int32_t>() + 2 * SC_NNODES;
   int32_t* d_best = s.scal.as<int32_t>() + 2 * SC_BEST;
@@ -973,9 +964,6 @@ int run_shard_back(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
   unsigned long long* c_fail = c_tot + Pn;
   unsigned long long* c_sig = c_tot + 2 * Pn;
   unsigned long long* c_raw = c_tot + 3 * Pn;
-  long long* o_tot = (long long*)(c_tot + 4 * Pn);
-  long long* o_sig = o_tot + Pn;
-  long long* o_fail = o_tot + 2 * Pn;
   CU(s.act.ensure((size_t)Pn * act_stride));
   const bool dev_out = in->mem == MDEGGS_MEM_DEVICE;
   int8_t* d_cat = nullptr;
@@ -1121,12 +1109,8 @@ int run_shard_back2(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const m
   const int act_stride = n_nodes > 0 ? n_nodes : 1;
   const int Pn = P > 0 ? P : 1;
   unsigned long long* c_tot = s.counters.as<unsigned long long>();
-  unsigned long long* c_fail = c_tot + Pn;
   unsigned long long* c_sig = c_tot + 2 * Pn;
   unsigned long long* c_raw = c_tot + 3 * Pn;
-  long long* o_tot = (long long*)(c_tot + 4 * Pn);
-  long long* o_sig = o_tot + Pn;
-  long long* o_fail = o_tot + 2 * Pn;
   const bool dev_out = in->mem == MDEGGS_MEM_DEVICE;
   const bool dev_adjust = device_adjust(in);
   const bool do_adjust = dev_adjust && E > 0 && P > 0 && n_nodes > 0;
