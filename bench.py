@@ -388,9 +388,9 @@ def run_cuda(args) -> None:
     fit_bytes = E * (16 * n + 16)
     achieved = fit_bytes / (fit_ms * 1e-3) / 1e9 if fit_ms > 0 else None
     # DRAM traffic of one k_fit_stream launch from the committed ncu --set full capture of this workload
-    # (profiles/r01p_ncu_full_hot_kernels.csv: dram__bytes_read.sum 68.57 MB + dram__bytes_write.sum 3.75 MB): the
+    # (profiles/r01q_ncu_full_hot_kernels.csv: dram__bytes_read.sum 68.59 MB + dram__bytes_write.sum 5.18 MB): the
     # gene-major matrix is L2-resident, so DRAM sees it once while the kernel streams 849 MB of algorithmic bytes.
-    traffic = 72_323_328 if name == "cfg3" else None
+    traffic = 73_770_000 if name == "cfg3" else None
     # whole-step algorithmic bytes (SURVEY section 8 d): gather 2*8*G_nodes*n + quantiles 4*8*G_nodes*n + pair fits
     # + adjust 3*8*sum_p tot_edges[p]
     g_nodes = int(st["n_nodes"])
@@ -398,7 +398,7 @@ def run_cuda(args) -> None:
     step_s = ms / args.steps * 1e-3
     roofline = {"bound": "hbm", "kernel": "k_fit_stream", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": (achieved / peaks["hbm_gbs"]) if achieved else None, "traffic": traffic,
-                "traffic_source": "profiles/r01p_ncu_full_hot_kernels.csv (ncu --set full, dram read + write per launch)",
+                "traffic_source": "profiles/r01q_ncu_full_hot_kernels.csv (ncu --set full, dram read + write per launch)",
                 "peak_source": peaks["source"], "algorithmic_bytes_per_launch": fit_bytes,
                 "kernel_ms": fit_ms, "stage_ms": stage,
                 "stage_note": "stage/kernel times from separate eagerly launched steps (the graph has no stage events)",
