@@ -266,8 +266,18 @@ __global__ void __launch_bounds__(256, 6) k_gather_colmajor(const double* __rest
   const int n_nodes = *n_nodes_p;
   const int n_tx = (npad + 31) / 32, n_ty = (n_nodes + 31) / 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
-  for (long long tile_id = blockIdx.x; tile_id < (long long)n_tx * n_ty; tile_id += gridDim.x) {
-    const int node0 = (int)(tile_id / n_tx) * 32, pos0 = (int)(tile_id % n_tx) * 32;
+  const long long n_tiles = (long long)n_tx * n_ty;
+  const bool small = n_tiles < (1ll << 31);  // 32-bit tile arithmetic (a 64-bit division costs ~15 % of this kernel)
+  for (long long tile_id = blockIdx.x; tile_id < n_tiles; tile_id += gridDim.x) {
+    int node0, pos0;
+    if (small) {
+      const unsigned t = (unsigned)tile_id, q = t / (unsigned)n_tx;
+      node0 = (int)q * 32;
+      pos0 = (int)(t - q * (unsigned)n_tx) * 32;
+    } else {
+      node0 = (int)(tile_id / n_tx) * 32;
+      pos0 = (int)(tile_id % n_tx) * 32;
+    }
     const int node_r = node0 + tx;
     const int64_t row = node_r < n_nodes ? rowlist[node_r] - row_off : -1;  // device copy starts at host row row_off
     double v[4];
