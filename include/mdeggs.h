@@ -40,13 +40,17 @@ extern "C" {
 #define MDEGGS_PADJ_NONE 0       /* "none": count raw p < 0.05 */
 #define MDEGGS_PADJ_BONFERRONI 1 /* "bonferroni" */
 #define MDEGGS_PADJ_BH 2         /* "BH" / "fdr" */
-#define MDEGGS_PADJ_HOST 3       /* "hommel" (or a host-side q.value): raw p + masks returned, the host adjusts each segment */
+#define MDEGGS_PADJ_HOST 3       /* any method adjusted by the host (big hommel jobs, a host-side q.value): raw p + masks returned */
 #define MDEGGS_PADJ_HOLM 4       /* "holm"      pmin(1, cummax((n+1-i) p[o])), o ascending                      */
 #define MDEGGS_PADJ_HOCHBERG 5   /* "hochberg"  pmin(1, cummin((n+1-i) p[o])), o descending                     */
 #define MDEGGS_PADJ_BY 6         /* "BY"        pmin(1, cummin(q n/i p[o])), q = sum(1/(1:n))                   */
 #define MDEGGS_PADJ_QVALUE 7     /* "q.value"   qvalue::qvalue(p)$qvalues = pi0 pmin(1, cummin(p[o] m/i)), pi0 by the
                                     smoother over lambda = seq(.05,.95,.05); on qvalue's errors pi0 = 1 if the
                                     category network has > 1 row, else NA (core_functions.R:1012-1025)              */
+#define MDEGGS_PADJ_HOMMEL 8     /* "hommel"    pmax(pa, p), pa = max over m of the Simes-type bounds of stats::p.adjust;
+                                    O(n^2) per (percentile, category) segment: accepted up to MDEGGS_HOMMEL_MAX_E edges,
+                                    beyond that MDEGGS_EUNSUPPORTED (use MDEGGS_PADJ_HOST and adjust on the host) */
+#define MDEGGS_HOMMEL_MAX_E 65536
 /* rlm covariance used by the Wald test (MASS::summary.rlm `method`) */
 #define MDEGGS_RLM_COV_XTWX 0
 #define MDEGGS_RLM_COV_XTX 1

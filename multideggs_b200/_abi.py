@@ -15,8 +15,9 @@ ABI_VERSION = 1
 MAX_K = 8
 
 METHOD_LM, METHOD_RLM = 0, 1
-PADJ_NONE, PADJ_BONFERRONI, PADJ_BH, PADJ_HOST, PADJ_HOLM, PADJ_HOCHBERG, PADJ_BY, PADJ_QVALUE = 0, 1, 2, 3, 4, 5, 6, 7
-DEVICE_PADJ = (PADJ_BONFERRONI, PADJ_BH, PADJ_HOLM, PADJ_HOCHBERG, PADJ_BY, PADJ_QVALUE)
+PADJ_NONE, PADJ_BONFERRONI, PADJ_BH, PADJ_HOST, PADJ_HOLM, PADJ_HOCHBERG, PADJ_BY, PADJ_QVALUE, PADJ_HOMMEL = range(9)
+DEVICE_PADJ = (PADJ_BONFERRONI, PADJ_BH, PADJ_HOLM, PADJ_HOCHBERG, PADJ_BY, PADJ_QVALUE, PADJ_HOMMEL)
+HOMMEL_MAX_E = 65536   # MDEGGS_HOMMEL_MAX_E: hommel is O(n^2) per segment, larger jobs are adjusted by the host
 RLM_COV_XTWX, RLM_COV_XTX = 0, 1
 LAYOUT_COLMAJOR, LAYOUT_ROWMAJOR = 0, 1
 MEM_HOST, MEM_DEVICE = 0, 1

@@ -89,11 +89,11 @@ struct Shard {
     if (e == cudaSuccess) h_stage_cap = bytes + 256;
     return e;
   }
-  DevBuf assay, from, to, ea, eb, stage_dev, bs_count, bs_slot, seg_done, seg_rank, fin_q, seg_pi0, B16, stamps, excl, node_of_row, rowlist, scal, src_of_pos, pct, cutoff, D, cub_tmp, mean, sxx, med, bad, stat, status, p_edge, coef, iters, act, counters, sortk, sortk2, idx,
+  DevBuf assay, from, to, ea, eb, stage_dev, bs_count, bs_slot, seg_done, seg_rank, fin_q, hm_p, hm_q1, hm_c, hm_sc, hm_idx, hm_off, seg_pi0, B16, stamps, excl, node_of_row, rowlist, scal, src_of_pos, pct, cutoff, D, cub_tmp, mean, sxx, med, bad, stat, status, p_edge, coef, iters, act, counters, sortk, sortk2, idx,
       idx2, ps, sa, sb, tile_cnt, tile_base, seg_n, tile_min, tile_carry, padj_best, cat_best, cat, padj, med_out,
       small_out, rsel_hist, rsel_state, rsel_cand, dense_S, cf_tab, sxy;
   void release_all() {
-    DevBuf* all[] = {&assay, &from, &to, &ea, &eb, &stage_dev, &bs_count, &bs_slot, &seg_done, &seg_rank, &fin_q, &seg_pi0, &B16, &stamps, &excl, &node_of_row, &rowlist, &scal, &src_of_pos, &pct, &cutoff,
+    DevBuf* all[] = {&assay, &from, &to, &ea, &eb, &stage_dev, &bs_count, &bs_slot, &seg_done, &seg_rank, &fin_q, &hm_p, &hm_q1, &hm_c, &hm_sc, &hm_idx, &hm_off, &seg_pi0, &B16, &stamps, &excl, &node_of_row, &rowlist, &scal, &src_of_pos, &pct, &cutoff,
                      &D, &cub_tmp, &mean, &sxx, &med, &bad, &stat, &status, &p_edge,
                      &coef, &iters, &act, &counters, &sortk, &sortk2, &idx, &idx2, &ps, &sa, &sb, &tile_cnt,
                      &tile_base, &seg_n, &tile_min, &tile_carry, &padj_best, &cat_best, &cat, &padj, &med_out,
@@ -299,7 +299,8 @@ unsigned int qs_cand_capacity(const mdeggs_ctx* ctx, const mdeggs_problem* in) {
 }
 bool device_adjust(const mdeggs_problem* in) {
   return in->padj == MDEGGS_PADJ_BONFERRONI || in->padj == MDEGGS_PADJ_BH || in->padj == MDEGGS_PADJ_HOLM ||
-         in->padj == MDEGGS_PADJ_HOCHBERG || in->padj == MDEGGS_PADJ_BY || in->padj == MDEGGS_PADJ_QVALUE;
+         in->padj == MDEGGS_PADJ_HOCHBERG || in->padj == MDEGGS_PADJ_BY || in->padj == MDEGGS_PADJ_QVALUE ||
+         in->padj == MDEGGS_PADJ_HOMMEL;
 }
 // K8 ordering by p-value buckets (mdeggs_bsort.cuh) instead of the multi-pass radix sort
 bool use_bucket_order(const mdeggs_ctx* ctx, const mdeggs_problem* in, int32_t n_nodes) {
@@ -426,7 +427,8 @@ int run_adjust(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, int n_segmen
   int* done_a = s.seg_done.as<int>();
   int* done_b = done_a + (size_t)in->P * in->K;
   // count-only block (no adjusted value is kept): the significant counts come from one rank pass, see k_bh_sigrank
-  const bool count_only = sig_dev && !padj_out && !best_dev && !reuse_tiles && ctx->count_only_adjust;
+  const bool count_only = sig_dev && !padj_out && !best_dev && !reuse_tiles && ctx->count_only_adjust &&
+                          in->padj != MDEGGS_PADJ_HOMMEL;
   if (count_only) {
     const size_t need = (size_t)in->P * in->K * sizeof(unsigned long long);
     if (need > s.seg_rank.cap) {
@@ -440,6 +442,33 @@ int run_adjust(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, int n_segmen
   if (in->padj == MDEGGS_PADJ_QVALUE && !reuse_tiles)
     LAUNCH(k_qv_pi0, dim3(1, (unsigned)n_segments), BH_THREADS, 0, s.s_main, A, s.tile_base.as<long long>(),
            s.seg_n.as<long long>(), s.seg_pi0.as<double>());
+  if (in->padj == MDEGGS_PADJ_HOMMEL) {  // O(n^2) per segment on dense copies of the segments (all-percentile pass only)
+    if (best_dev || reuse_tiles || !sig_dev) {
+      set_err(ctx, "internal: hommel is adjusted in the all-percentile pass only");
+      return MDEGGS_EINVAL;
+    }
+    const size_t tot_cap = (size_t)((n_segments + in->K - 1) / in->K) * (size_t)E;  // sum of the segment sizes at most
+    CU(s.hm_p.ensure(tot_cap * 8));
+    CU(s.hm_q1.ensure(tot_cap * 8));
+    CU(s.hm_c.ensure(tot_cap * 8));
+    CU(s.hm_sc.ensure(tot_cap * 8));
+    CU(s.hm_idx.ensure(tot_cap * 4));
+    CU(s.hm_off.ensure(((size_t)n_segments + 1) * 8 + (size_t)n_segments * 8));
+    long long* seg_off = s.hm_off.as<long long>();
+    double* hinit = reinterpret_cast<double*>(seg_off + n_segments + 1);
+    const unsigned gx = (unsigned)((E + 7) / 8);
+    LAUNCH(k_hm_offsets, 1, 32, 0, s.s_main, A, s.seg_n.as<long long>(), n_segments, seg_off);
+    LAUNCH(k_hm_compact, grid, BH_THREADS, 0, s.s_main, A, s.tile_cnt.as<int32_t>(), s.tile_base.as<long long>(), seg_off,
+           s.hm_p.as<double>(), s.hm_idx.as<int32_t>());
+    LAUNCH(k_hm_q1, dim3(gx, (unsigned)n_segments), 256, 0, s.s_main, A, s.seg_n.as<long long>(), seg_off,
+           s.hm_p.as<double>(), s.hm_q1.as<double>(), s.hm_c.as<double>(), hinit);
+    LAUNCH(k_hm_sufmax, (unsigned)n_segments, BH_THREADS, 0, s.s_main, A, s.seg_n.as<long long>(), seg_off,
+           s.hm_c.as<double>(), s.hm_sc.as<double>());
+    LAUNCH(k_hm_pa, dim3(gx, (unsigned)n_segments), 256, 0, s.s_main, A, s.seg_n.as<long long>(), seg_off,
+           s.hm_p.as<double>(), s.hm_q1.as<double>(), s.hm_sc.as<double>(), hinit, s.hm_idx.as<int32_t>(), sig_dev,
+           padj_out, padj_stride);
+    return MDEGGS_OK;
+  }
   if (count_only) {
     LAUNCH(k_bh_sigrank, grid, BH_THREADS, 0, s.s_main, A, in->padj, s.tile_cnt.as<int32_t>(),
            s.tile_base.as<long long>(), s.seg_n.as<long long>(), s.seg_rank.as<unsigned long long>(), sig_dev, done_b);
@@ -979,9 +1008,10 @@ int run_shard_back(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
   // and only the per-percentile significant counts are all-reduced; a full P x E p.adj output keeps it replicated
   double* d_padj = nullptr;
   const bool want_padj_best = out->padj_best && do_adjust;
-  const bool shard_p = do_adjust && s.world > 1 && !out->padj;
+  const bool shard_p = do_adjust && s.world > 1 && !out->padj && in->padj != MDEGGS_PADJ_HOMMEL;
   const bool keep_all_padj = do_adjust && !shard_p &&
-                             (out->padj || (want_padj_best && (size_t)P * (size_t)E * 8 <= (size_t)ctx->padj_keep_cap));
+                             (out->padj || (want_padj_best && ((size_t)P * (size_t)E * 8 <= (size_t)ctx->padj_keep_cap ||
+                                                                in->padj == MDEGGS_PADJ_HOMMEL)));
   if (keep_all_padj) {
     if (out->padj && dev_out && emit) d_padj = out->padj;
     else {
@@ -1070,7 +1100,7 @@ int run_shard_back(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
     const int n_loc = p0 < P ? (P - p0 + stride - 1) / stride : 0;
     // one rank: the percentile selection rides in the last CTA of k_bh_final (with more ranks it follows the all-reduce)
     const bool count_only = !d_padj && ctx->count_only_adjust;  // (run_adjust takes the k_bh_sigrank path)
-    s.select_fused = s.world == 1 && n_loc > 0 && !count_only;
+    s.select_fused = s.world == 1 && n_loc > 0 && !count_only && in->padj != MDEGGS_PADJ_HOMMEL;
     s.partials_complete = !count_only;
     CU(s.small_out.ensure(small_block_bytes(P)));
     SelArgs sel = make_sel_args(s, in, H, emit, c_sig);
@@ -1086,7 +1116,8 @@ int run_shard_back(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
 int run_sig_allreduce(mdeggs_ctx* ctx, const mdeggs_problem* in, const mdeggs_result* out) {
   Shard& s0 = ctx->shards[0];
   const bool dev_adjust = device_adjust(in);
-  if (!(dev_adjust && s0.world > 1 && !out->padj && in->E > 0 && in->P > 0)) return MDEGGS_OK;
+  if (!(dev_adjust && s0.world > 1 && !out->padj && in->E > 0 && in->P > 0) || in->padj == MDEGGS_PADJ_HOMMEL)
+    return MDEGGS_OK;  // (hommel is not sharded by percentile: every rank already holds every count)
   NcclApi& api = nccl_api();
   const int Pn = in->P;
   NC(api.GroupStart());
@@ -1115,9 +1146,10 @@ int run_shard_back2(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const m
   const bool dev_adjust = device_adjust(in);
   const bool do_adjust = dev_adjust && E > 0 && P > 0 && n_nodes > 0;
   const bool want_padj_best = out->padj_best && do_adjust;
-  const bool shard_p = do_adjust && s.world > 1 && !out->padj;
+  const bool shard_p = do_adjust && s.world > 1 && !out->padj && in->padj != MDEGGS_PADJ_HOMMEL;
   const bool keep_all_padj = do_adjust && !shard_p &&
-                             (out->padj || (want_padj_best && (size_t)P * (size_t)E * 8 <= (size_t)ctx->padj_keep_cap));
+                             (out->padj || (want_padj_best && ((size_t)P * (size_t)E * 8 <= (size_t)ctx->padj_keep_cap ||
+                                                                in->padj == MDEGGS_PADJ_HOMMEL)));
   double* d_padj = nullptr;
   if (keep_all_padj) d_padj = (out->padj && dev_out && emit) ? out->padj : s.padj.as<double>();
   const unsigned long long* sig_src = dev_adjust ? c_sig : c_raw;
@@ -1470,6 +1502,10 @@ int mdeggs_submit_omic(mdeggs_ctx* ctx, const mdeggs_problem* in, mdeggs_result*
   }
   if (2 * in->P >= QS_MAX_T) {  // slot ids travel as bytes, 0xff = none
     set_err(ctx, "more than %d percentiles are not supported", QS_MAX_T / 2 - 1);
+    return MDEGGS_EUNSUPPORTED;
+  }
+  if (in->padj == MDEGGS_PADJ_HOMMEL && in->E > MDEGGS_HOMMEL_MAX_E) {
+    set_err(ctx, "hommel on the device is limited to %d edges (O(n^2) per segment): use MDEGGS_PADJ_HOST", MDEGGS_HOMMEL_MAX_E);
     return MDEGGS_EUNSUPPORTED;
   }
   if (in->n <= 2 * in->K) {

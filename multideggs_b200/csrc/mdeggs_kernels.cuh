@@ -1071,6 +1071,159 @@ __global__ void __launch_bounds__(BH_THREADS) k_bh_sigrank(BhArgs A, int mode, c
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// hommel (stats::p.adjust, core_functions.R:1027-1035).  With p ascending inside a segment of n members R computes
+//   pa = rep(min(n p / i), n);  for m = n-1 .. 2:  q1 = min_{j=2..m} m p[n-m+j] / j,
+//        q[i] = min(m p[i], q1) for i <= n-m+1,  q[i] = q[n-m+1] beyond,  pa = pmax(pa, q);   result pmax(pa, p).
+// The m iterations only meet in the running maximum, so they are independent:
+//   pa[i] = max( init,  max_{m=2..min(n-1, n-i+1)} min(m p[i], q1[m]),  max_{m=n-i+2..n-1} c[m] ),
+//   c[m] = min(m p[n-m+1], q1[m])   (1-based indices)
+// O(n^2) work per segment in two kernels (q1/c per m, then pa per i, a warp each), a suffix maximum of c in between;
+// the members of every segment are first copied into a dense array in rank order (k_hm_compact).
+// ------------------------------------------------------------------------------------------------
+// members of segment `seg` (pass A skips percentiles without tested edges: their seg_n entry is stale)
+__device__ __forceinline__ long long hm_seg_n(const BhArgs& A, const long long* __restrict__ seg_n, int seg) {
+  const int p = A.p0 + (seg / A.K) * A.p_stride;
+  return (A.tot && A.tot[p] == 0) ? 0 : seg_n[seg];
+}
+__global__ void k_hm_offsets(BhArgs A, const long long* __restrict__ seg_n, int n_segments,
+                             long long* __restrict__ seg_off) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  long long acc = 0;
+  for (int sgi = 0; sgi < n_segments; ++sgi) {
+    seg_off[sgi] = acc;
+    acc += hm_seg_n(A, seg_n, sgi);
+  }
+  seg_off[n_segments] = acc;
+}
+
+__global__ void __launch_bounds__(BH_THREADS) k_hm_compact(BhArgs A, const int32_t* __restrict__ tile_cnt,
+                                                          const long long* __restrict__ tile_base,
+                                                          const long long* __restrict__ seg_off,
+                                                          double* __restrict__ hp, int32_t* __restrict__ hidx) {
+  int p, c;
+  size_t seg;
+  if (!bh_segment(A, p, c, seg)) return;
+  if (A.tot && A.tot[p] == 0) return;
+  if (tile_cnt[seg * A.ntiles + blockIdx.x] == 0) return;
+  typedef cub::BlockScan<int, BH_THREADS> Scan;
+  __shared__ typename Scan::TempStorage tmp;
+  int flag[BH_ITEMS], rank[BH_ITEMS];
+  double pv[BH_ITEMS];
+  const int64_t tile0 = (int64_t)blockIdx.x * BH_TILE;
+  bh_load(A, p, c, tile0, flag, pv);
+  Scan(tmp).InclusiveSum(flag, rank);
+  const long long base = seg_off[seg] + tile_base[seg * A.ntiles + blockIdx.x];
+#pragma unroll
+  for (int it = 0; it < BH_ITEMS; ++it)
+    if (flag[it]) {
+      const long long pos = base + rank[it] - 1;
+      hp[pos] = pv[it];
+      hidx[pos] = A.sidx[tile0 + (int64_t)threadIdx.x * BH_ITEMS + it];
+    }
+}
+
+__device__ __forceinline__ double warp_min_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_max_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// one warp per m = 2 .. n-1 of a segment: q1[m], c[m]; CTA 0 of the segment also computes init = min(n p / i)
+__global__ void __launch_bounds__(256) k_hm_q1(BhArgs A, const long long* __restrict__ seg_n,
+                                               const long long* __restrict__ seg_off, const double* __restrict__ hp,
+                                               double* __restrict__ hq1, double* __restrict__ hc,
+                                               double* __restrict__ hinit) {
+  const int seg = blockIdx.y;
+  const long long n = hm_seg_n(A, seg_n, seg);
+  const double* __restrict__ p = hp + seg_off[seg];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const long long m = 2 + (long long)blockIdx.x * 8 + wib;
+  if (m <= n - 1) {
+    const double md = (double)m;
+    double q1 = INFINITY;
+    for (long long j = 2 + lane; j <= m; j += 32)  // p[i2[j-2]], i2 = (n-m+2):n, 0-based index n-m+j-1
+      q1 = fmin(q1, __ddiv_rn(__dmul_rn(md, p[n - m + j - 1]), (double)j));
+    q1 = warp_min_d(q1);
+    if (lane == 0) {
+      hq1[seg_off[seg] + m] = q1;
+      hc[seg_off[seg] + m] = fmin(__dmul_rn(md, p[n - m]), q1);  // q[n-m+1] of this m
+    }
+  }
+  if (blockIdx.x == 0) {
+    __shared__ double s_w[8];
+    const double nd = (double)n;
+    double v = INFINITY;
+    for (long long i = threadIdx.x; i < n; i += 256) v = fmin(v, __ddiv_rn(__dmul_rn(nd, p[i]), (double)(i + 1)));
+    v = warp_min_d(v);
+    if (lane == 0) s_w[wib] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int w = 1; w < 8; ++w) v = fmin(v, s_w[w]);
+      hinit[seg] = v;
+    }
+  }
+}
+
+// suffix maximum of c[m] over m (one CTA per segment): hsc[m] = max_{m' = m .. n-1} c[m']
+__global__ void __launch_bounds__(BH_THREADS) k_hm_sufmax(BhArgs A, const long long* __restrict__ seg_n,
+                                                         const long long* __restrict__ seg_off,
+                                                         const double* __restrict__ hc, double* __restrict__ hsc) {
+  typedef cub::BlockScan<double, BH_THREADS> Scan;
+  __shared__ typename Scan::TempStorage tmp;
+  __shared__ double carry;
+  const int seg = blockIdx.x;
+  const long long n = hm_seg_n(A, seg_n, seg), off = seg_off[seg];
+  if (threadIdx.x == 0) carry = -INFINITY;
+  __syncthreads();
+  const long long cnt = n - 2;  // m = 2 .. n-1, walked from n-1 down
+  for (long long r0 = 0; r0 < cnt; r0 += BH_THREADS) {
+    const long long r = r0 + threadIdx.x, m = n - 1 - r;
+    double v = r < cnt ? hc[off + m] : -INFINITY, inc, agg;
+    Scan(tmp).InclusiveScan(v, inc, MaxOp(), agg);
+    if (r < cnt) hsc[off + m] = fmax(carry, inc);
+    __syncthreads();
+    if (threadIdx.x == 0) carry = fmax(carry, agg);
+    __syncthreads();
+  }
+}
+
+// one warp per member i: pa[i], the adjusted value, its count < 0.05 and the scatter to network order
+__global__ void __launch_bounds__(256) k_hm_pa(BhArgs A, const long long* __restrict__ seg_n,
+                                               const long long* __restrict__ seg_off, const double* __restrict__ hp,
+                                               const double* __restrict__ hq1, const double* __restrict__ hsc,
+                                               const double* __restrict__ hinit, const int32_t* __restrict__ hidx,
+                                               unsigned long long* __restrict__ sig, double* __restrict__ padj_out,
+                                               int64_t padj_stride) {
+  const int seg = blockIdx.y;
+  const int pct = A.p0 + (seg / A.K) * A.p_stride;
+  const long long n = hm_seg_n(A, seg_n, seg), off = seg_off[seg];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const long long i0 = (long long)blockIdx.x * 8 + wib;  // 0-based member
+  if (i0 >= n) return;
+  const double pi = hp[off + i0];
+  double res = pi;  // n <= 1: p.adjust returns p unchanged
+  if (n > 1) {
+    const long long i = i0 + 1;
+    const long long m_hi = (n - 1 < n - i + 1) ? n - 1 : n - i + 1;
+    double t = -INFINITY;
+    for (long long m = 2 + lane; m <= m_hi; m += 32) t = fmax(t, fmin(__dmul_rn((double)m, pi), hq1[off + m]));
+    t = warp_max_d(t);
+    double pa = fmax(hinit[seg], t);
+    if (n - i + 2 <= n - 1 && n - i + 2 >= 2) pa = fmax(pa, hsc[off + n - i + 2]);
+    res = fmax(pa, pi);
+  }
+  if (lane == 0) {
+    if (padj_out) padj_out[(int64_t)pct * padj_stride + hidx[off + i0]] = res;
+    if (res < 0.05) atomicAdd(&sig[pct], 1ull);
+  }
+}
+
 // q.value: pi0 of every segment (qvalue::pi0est, smoother method; core_functions.R:1012-1025)
 //   pi0(lambda_j) = mean(p >= lambda_j) / (1 - lambda_j), lambda = seq(0.05, 0.95, 0.05);
 //   pi0 = min(1, value at the last lambda of smooth.spline(lambda, pi0(lambda), df = 3)) = QV_ROW . pi0(lambda);

@@ -216,7 +216,7 @@ class OmicPrep:
     padj_method: str
 
 
-def _padj_code(padj_method: str) -> int:
+def _padj_code(padj_method: str, n_edges: int = 0) -> int:
     if padj_method == "none":
         return _abi.PADJ_NONE
     if padj_method == "bonferroni":
@@ -231,8 +231,8 @@ def _padj_code(padj_method: str) -> int:
         return _abi.PADJ_BY
     if padj_method == "q.value":
         return _abi.PADJ_QVALUE   # pi0 smoother + q-values on the device (SURVEY section 8 f, N1)
-    if padj_method == "hommel":
-        return _abi.PADJ_HOST
+    if padj_method == "hommel":  # on the device up to MDEGGS_HOMMEL_MAX_E edges, else raw p + masks -> p_adjust() here
+        return _abi.PADJ_HOMMEL if n_edges <= _abi.HOMMEL_MAX_E else _abi.PADJ_HOST
     raise ValueError(f"padj_method must be one of {P_ADJUST_METHODS + ('q.value',)}")
 
 
@@ -314,7 +314,7 @@ def prepare_omic(assayData, assayDataName: str, metadata: Factor, regression_met
                         else np.asfortranarray(values),
                         from_idx=fr, to_idx=to, group=codes.astype(np.int32), K=K,
                         pct=np.asarray(percentile_vector, dtype=np.float64), method=method,
-                        padj=_padj_code(padj_method), tested_coef=tested_coef, rlm_cov_mode=rlm_cov_mode)
+                        padj=_padj_code(padj_method, len(fr)), tested_coef=tested_coef, rlm_cov_mode=rlm_cov_mode)
     return OmicPrep(assayDataName, prob, genes, samples, list(metadata.levels), padj_method)
 
 

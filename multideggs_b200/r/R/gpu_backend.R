@@ -12,7 +12,7 @@
 #
 # Install: see INTEGRATION.md.  NAMESPACE needs `useDynLib(multiDEGGs, .registration = TRUE)`.
 
-.mdeggs_padj_code <- function(padj_method) {
+.mdeggs_padj_code <- function(padj_method, n_edges = 0L) {
   if (padj_method == "none") return(0L)
   if (padj_method == "bonferroni") return(1L)
   if (padj_method %in% c("BH", "fdr")) return(2L)
@@ -22,7 +22,9 @@
   # q.value: the device estimates pi0 (smoother over lambda = seq(.05,.95,.05)) and returns q-values (code 7).
   # options(multiDEGGs.qvalue_on_host = TRUE) keeps Bioconductor's qvalue::qvalue in the loop instead (code 3).
   if (padj_method == "q.value" && !isTRUE(getOption("multiDEGGs.qvalue_on_host"))) return(7L)
-  3L  # hommel (or host-side q.value): raw p + masks come back, R adjusts each segment
+  # hommel: on the device up to 65,536 edges (MDEGGS_HOMMEL_MAX_E; it is O(n^2) per segment), else by R (code 3)
+  if (padj_method == "hommel" && n_edges <= 65536L) return(8L)
+  3L  # big hommel jobs or host-side q.value: raw p + masks come back, R adjusts each segment
 }
 
 # Host preparation of one layer (core_functions.R:280-340): everything up to the engine call.  Returns the argument
@@ -65,7 +67,7 @@
 
   categories <- levels(metadata)
   K <- length(categories)
-  padj_code <- .mdeggs_padj_code(padj_method)
+  padj_code <- .mdeggs_padj_code(padj_method, length(from_idx))
   list(args = list(assayData, as.integer(from_idx), as.integer(to_idx),
                    as.integer(metadata), as.integer(K), as.double(percentile_vector),
                    as.integer(regression_method == "rlm"), padj_code,

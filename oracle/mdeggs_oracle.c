@@ -632,7 +632,7 @@ int orc_fit_rlm(const double* a, const double* b, const double* g01, int n, int 
 
 /* ------------------------------------------------------------------------------------------------
  * stats::p.adjust (core_functions.R:1029).  NaN entries are NA: ignored for n, returned as NaN.
- * method: 0 none, 1 bonferroni, 2 BH, 3 holm, 4 hochberg, 5 BY
+ * method: 0 none, 1 bonferroni, 2 BH, 3 holm, 4 hochberg, 5 BY, 6 hommel
  * ---------------------------------------------------------------------------------------------- */
 typedef struct {
   double p;
@@ -694,6 +694,40 @@ void orc_p_adjust(const double* p, int64_t len, int method, double* out) {
       if (v > run) run = v;
       out[s[j].i] = run < 1.0 ? run : 1.0;
     }
+  } else if (method == 6) {
+    /* hommel, the loop of stats::p.adjust restated literally (n == 2 is "hochberg" there, which this loop reproduces:
+     * it then runs zero times and leaves pmax(min(2 p1, p2), p)):
+     *   q <- pa <- rep(min(n p / i), n)
+     *   for (m in (n-1):2) { i1 <- 1:(n-m+1); i2 <- (n-m+2):n; q1 <- min(m p[i2] / (2:m));
+     *                        q[i1] <- pmin(m p[i1], q1); q[i2] <- q[n-m+1]; pa <- pmax(pa, q) }
+     *   pmax(pa, p)[ro] */
+    qsort(s, (size_t)n, sizeof(pidx), cmp_pidx_asc);
+    double* q = (double*)malloc(sizeof(double) * (size_t)n);
+    double* pa = (double*)malloc(sizeof(double) * (size_t)n);
+    double init = INFINITY;
+    for (int64_t j = 0; j < n; ++j) {
+      double v = nn * s[j].p / (double)(j + 1);
+      if (v < init) init = v;
+    }
+    for (int64_t j = 0; j < n; ++j) q[j] = pa[j] = init;
+    for (int64_t mm = n - 1; mm >= 2; --mm) {
+      const double md = (double)mm;
+      double q1 = INFINITY;
+      for (int64_t j = 2; j <= mm; ++j) { /* i2[j-2] = n-m+j (1-based) */
+        double v = md * s[n - mm + j - 1].p / (double)j;
+        if (v < q1) q1 = v;
+      }
+      for (int64_t i = 0; i < n - mm + 1; ++i) {
+        double v = md * s[i].p;
+        q[i] = v < q1 ? v : q1;
+      }
+      for (int64_t i = n - mm + 1; i < n; ++i) q[i] = q[n - mm];
+      for (int64_t i = 0; i < n; ++i)
+        if (q[i] > pa[i]) pa[i] = q[i];
+    }
+    for (int64_t j = 0; j < n; ++j) out[s[j].i] = pa[j] > s[j].p ? pa[j] : s[j].p;
+    free(q);
+    free(pa);
   }
   free(s);
 }
@@ -857,10 +891,10 @@ int mdeggs_oracle_run_omic(const mdeggs_problem* in, mdeggs_result* out, int mod
   int8_t* cat_all = (int8_t*)malloc((size_t)(P > 0 ? P : 1) * (size_t)(E > 0 ? E : 1));
   double* padj_all = (double*)malloc(sizeof(double) * (size_t)(P > 0 ? P : 1) * (size_t)(E > 0 ? E : 1));
   int padj_method = in->padj;
-  /* ABI code -> orc_p_adjust method (0 none, 1 bonferroni, 2 BH, 3 holm, 4 hochberg, 5 BY) */
+  /* ABI code -> orc_p_adjust method (0 none, 1 bonferroni, 2 BH, 3 holm, 4 hochberg, 5 BY, 6 hommel) */
   const int orc_method = padj_method == MDEGGS_PADJ_BONFERRONI ? 1 : padj_method == MDEGGS_PADJ_BH ? 2
                          : padj_method == MDEGGS_PADJ_HOLM ? 3 : padj_method == MDEGGS_PADJ_HOCHBERG ? 4
-                         : padj_method == MDEGGS_PADJ_BY ? 5 : 0;
+                         : padj_method == MDEGGS_PADJ_BY ? 5 : padj_method == MDEGGS_PADJ_HOMMEL ? 6 : 0;
   const int dev_adjust = orc_method != 0;
   int pthreads = (mode == MDEGGS_ORACLE_MODE_REFERENCE) ? (nthreads < P ? nthreads : P) : nthreads;
   if (pthreads < 1) pthreads = 1;

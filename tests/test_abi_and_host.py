@@ -205,6 +205,13 @@ def test_host_adjust_methods(oracle):
         assert np.all(q >= p - 1e-15) and np.all(q <= 1.0)
     # hommel is between hochberg and bonferroni-holm in power
     assert np.all(host.p_adjust(p, "hommel") <= host.p_adjust(p, "hochberg") + 1e-15)
+    # the C restatement of R's hommel loop (oracle, method 6) and the numpy one agree bit for bit, with ties and NA
+    for n in (1, 2, 3, 4, 9, 64, 257):
+        v = rng.uniform(size=n) ** 3
+        if n > 3:
+            v[2] = v[0]
+            v[1] = np.nan
+        assert np.array_equal(oracle.p_adjust(v, 6), host.p_adjust(v, "hommel"), equal_nan=True), n
     # q.value: max(p) < 0.95 -> qvalue() errors -> pi0 = 1 retry == BH up to the multiply/divide order
     small = p[p < 0.9]
     assert np.allclose(host.qvalue_or_fallback(small), host.p_adjust(small, "BH"), rtol=1e-14)

@@ -848,3 +848,35 @@ def test_count_only_adjustment_equals_three_pass(padj, K, E, seed):
         full.close()
         for e in engs.values():
             e.close()
+
+
+# ---- hommel on the device (SURVEY section 8 f, N2) ----
+@pytest.mark.parametrize("G,n,E,K,seed", [(40, 30, 60, 2, 1501), (120, 64, 900, 2, 1502), (200, 60, 5000, 3, 1503),
+                                          (64, 40, 300, 4, 1504), (30, 24, 3, 2, 1505)])
+def test_device_hommel_matches_oracle(engine, oracle, G, n, E, K, seed):
+    """stats::p.adjust(method = "hommel") per (percentile, category) segment: O(n^2) on the device (k_hm_*), compared
+    with the C restatement of R's loop; segments of 0, 1, 2 and many members occur across the percentiles."""
+    prob = synth.random_problem(G, n, E, K, seed, _abi.METHOD_LM, _abi.PADJ_HOMMEL)
+    for rep in range(3):  # eager, capture, replay
+        gpu, ref = _both(engine, oracle, prob)
+        assert_parity(gpu, ref, prob, what=f"hommel G{G} E{E} K{K} rep{rep}: ")
+    assert ref["tot_edges"].sum() > 0
+    # the same numbers as the host-side adjustment of the raw p-values (the path bigger jobs take)
+    raw = synth.random_problem(G, n, E, K, seed, _abi.METHOD_LM, _abi.PADJ_HOST)
+    r = engine.run_omic(raw, ALL_FIELDS)
+    P = len(prob.pct)
+    cat = r["cat"].reshape(P, E)
+    for pi in range(P):
+        for k in range(1, K + 1):
+            msk = cat[pi] == k
+            if msk.any():
+                exp = host.p_adjust(r["p_edge"][msk], "hommel")
+                assert np.allclose(gpu["padj"].reshape(P, E)[pi, msk], exp, rtol=1e-12, atol=0, equal_nan=True)
+
+
+def test_device_hommel_edge_limit(engine):
+    big = synth.random_problem(400, 20, _abi.HOMMEL_MAX_E + 1, 2, 1510, _abi.METHOD_LM, _abi.PADJ_HOMMEL)
+    with pytest.raises(md.EngineError, match="hommel"):
+        engine.run_omic(big)
+    assert host._padj_code("hommel", _abi.HOMMEL_MAX_E + 1) == _abi.PADJ_HOST
+    assert host._padj_code("hommel", 1000) == _abi.PADJ_HOMMEL
