@@ -5,9 +5,10 @@
 # engine (src/rcall.c -> libmdeggs, include/mdeggs.h).
 #
 # What stays in R (strings, factors, messages, data.frames): sample alignment, edge selection and
-# de-duplication, `levels(metadata)`, the q.value / holm / hochberg / hommel / BY adjustments (run by R's own
-# functions on the raw p-values of each (percentile, category) segment), rownames `from-to`, and every
-# message()/stop() text.  `cores` and `show_progressBar` are accepted and ignored by the GPU path except that
+# de-duplication, `levels(metadata)`, rownames `from-to`, and every
+# message()/stop() text.  Every `padj_method` is adjusted on the device; only hommel on more than 65,536 edges, and
+# q.value when options(multiDEGGs.qvalue_on_host = TRUE), are run by R's own functions on the raw p-values of each
+# (percentile, category) segment.  `cores` and `show_progressBar` are accepted and ignored by the GPU path except that
 # `cores == 1` keeps the reference's error semantics for failing pairs (a failing pair aborts the omic).
 #
 # Install: see INTEGRATION.md.  NAMESPACE needs `useDynLib(multiDEGGs, .registration = TRUE)`.
