@@ -241,7 +241,7 @@ def test_single_process_multi_gpu_matches_one_gpu(engine):
     for fit_path in (0, 1):
         engine.set_option("fit_path", fit_path)
         eng2.set_option("fit_path", fit_path)
-        for padj in (_abi.PADJ_BH, _abi.PADJ_HOLM, _abi.PADJ_BONFERRONI):
+        for padj in (_abi.PADJ_BH, _abi.PADJ_HOLM, _abi.PADJ_BONFERRONI, _abi.PADJ_QVALUE, _abi.PADJ_HOMMEL):
             prob = synth.random_problem(300, 50, 2500, 2, 900 + padj, _abi.METHOD_LM, padj)
             a = engine.run_omic(prob, want)
             b = eng2.run_omic(prob, want)
