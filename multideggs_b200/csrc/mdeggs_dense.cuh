@@ -20,6 +20,7 @@ namespace mdeggs {
 constexpr int DT = 128;   // tile edge (genes)
 constexpr int DKC = 8;    // samples per shared-memory stage (2 stages x 2 tiles = 33 KB static smem)
 constexpr int DLD = DT + 2;  // padded leading dimension of the transposed stage [DKC][DLD]
+constexpr int DENSE_DYN_SMEM = 4 * 256 * 16;  // raw staging slots (cp.async targets), dynamic shared memory
 
 // S[k][i][j] (row-major nn x nn per category), written for tile pairs ti <= tj
 __global__ void __launch_bounds__(256, 1) k_dense_moments(const double* __restrict__ D, SegLayout L,
@@ -62,22 +63,40 @@ __global__ void __launch_bounds__(256, 1) k_dense_moments(const double* __restri
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
 
-  double2 ra_reg[2], rb_reg[2];
+  // Staging of the next 8-sample stage: global -> the thread's OWN four 16-byte slots of `raw` by cp.async (no
+  // registers are held across the 512 FMAs of a stage; with register staging ptxas sank the loads behind the FMA
+  // block and a quarter of the kernel waited for them), then centred + transposed into As/Bs by the same thread.
+  extern __shared__ __align__(16) double2 raw[];  // [4][256]: slot u of thread t at raw[u * 256 + t]
   auto gload = [&](int kk) {  // segment length is a multiple of 4, DKC = 8: guard the tail per double2
     const bool in = kk + 2 * lc < seg_len;
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
-      ra_reg[q] = (in && pa[q]) ? __ldg(reinterpret_cast<const double2*>(pa[q] + kk)) : make_double2(ma[q], ma[q]);
-      rb_reg[q] = (in && pb[q]) ? __ldg(reinterpret_cast<const double2*>(pb[q] + kk)) : make_double2(mb[q], mb[q]);
+      double2* da = raw + (2 * q) * 256 + tid;
+      double2* db = raw + (2 * q + 1) * 256 + tid;
+      if (in && pa[q]) {
+        const unsigned sa = (unsigned)__cvta_generic_to_shared(da);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(pa[q] + kk) : "memory");
+      } else {
+        *da = make_double2(ma[q], ma[q]);
+      }
+      if (in && pb[q]) {
+        const unsigned sb = (unsigned)__cvta_generic_to_shared(db);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sb), "l"(pb[q] + kk) : "memory");
+      } else {
+        *db = make_double2(mb[q], mb[q]);
+      }
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
   };
   auto sstore = [&](int buf) {  // transposed + centred
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
-      As[buf][2 * lc][lr + 64 * q] = ra_reg[q].x - ma[q];
-      As[buf][2 * lc + 1][lr + 64 * q] = ra_reg[q].y - ma[q];
-      Bs[buf][2 * lc][lr + 64 * q] = rb_reg[q].x - mb[q];
-      Bs[buf][2 * lc + 1][lr + 64 * q] = rb_reg[q].y - mb[q];
+      const double2 va = raw[(2 * q) * 256 + tid], vb = raw[(2 * q + 1) * 256 + tid];
+      As[buf][2 * lc][lr + 64 * q] = va.x - ma[q];
+      As[buf][2 * lc + 1][lr + 64 * q] = va.y - ma[q];
+      Bs[buf][2 * lc][lr + 64 * q] = vb.x - mb[q];
+      Bs[buf][2 * lc + 1][lr + 64 * q] = vb.y - mb[q];
     }
   };
   gload(0);

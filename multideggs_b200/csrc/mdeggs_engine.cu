@@ -70,7 +70,7 @@ struct Shard {
   cudaEvent_t ev[EV_COUNT] = {};
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_sample = nullptr, ev_cf = nullptr;
   nccl_comm_t comm = nullptr;
-  bool smem_attr_set = false, rsel_attr_set = false;  // cudaFuncSetAttribute is per device
+  bool smem_attr_set = false, rsel_attr_set = false, dense_attr_set = false;  // cudaFuncSetAttribute is per device
   bool select_fused = false;  // this call's percentile selection ran inside k_bh_final
   bool partials_complete = true;  // the all-percentile K8 left the tile carries behind (false: count-only pass)
   bool best_rows_in_emit = false;  // this call's best-percentile rows are produced by k_emit (device callers)
@@ -865,8 +865,12 @@ int run_shard_main(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
                s.eb.as<int32_t>(), e_lo, e_hi, rr, s.scal.as<int32_t>() + 2 * SC_ERR);
         d_range = rr;
       }
-      LAUNCH(k_dense_moments, grid, 256, 0, s.s_main, s.D.as<double>(), L, s.mean.as<double>(), (int)n_nodes, ntl,
-             d_range, s.dense_S.as<double>());
+      if (!s.dense_attr_set) {  // static tiles + dynamic staging slots exceed the 48 KB default
+        CU(cudaFuncSetAttribute(k_dense_moments, cudaFuncAttributeMaxDynamicSharedMemorySize, DENSE_DYN_SMEM));
+        s.dense_attr_set = true;
+      }
+      LAUNCH(k_dense_moments, grid, 256, DENSE_DYN_SMEM, s.s_main, s.D.as<double>(), L, s.mean.as<double>(),
+             (int)n_nodes, ntl, d_range, s.dense_S.as<double>());
     } else {
       switch (K) {
         case 2: launch_fit_stream<2>(ctx, s, L, e_lo, e_hi); break;
