@@ -20,13 +20,23 @@ namespace mdeggs {
 constexpr int DT = 128;   // tile edge (genes)
 constexpr int DKC = 8;    // samples per shared-memory stage (2 stages x 2 tiles = 33 KB static smem)
 constexpr int DLD = DT + 2;  // padded leading dimension of the transposed stage [DKC][DLD]
-constexpr int DENSE_DYN_SMEM = 4 * 256 * 16;  // raw staging slots (cp.async targets), dynamic shared memory
+
+// Thread tile 8 rows x DCOLS columns: DCOLS = 8 -> 256 threads, 64 accumulators (one 234-register CTA per SM, two
+// warps per scheduler); DCOLS = 4 -> 512 threads, 32 accumulators, four warps per scheduler.  Measured on config 5:
+// 1.80 ms with 8, 1.87 ms with 4 (more warps do not raise the FP64 issue rate, the extra operand loads cost more).
+#ifndef DENSE_COLS
+#define DENSE_COLS 8
+#endif
+constexpr int DCOLS = DENSE_COLS;
+constexpr int DTHREADS = (DT / 8) * (DT / DCOLS);  // 256 or 512
+constexpr int DQ = 512 / DTHREADS;                 // double2 per matrix and stage that a thread stages (2 or 1)
+constexpr int DENSE_DYN_SMEM = 2 * DQ * DTHREADS * 16;  // raw staging slots (cp.async targets), dynamic shared memory
 
 // S[k][i][j] (row-major nn x nn per category), written for tile pairs ti <= tj
-__global__ void __launch_bounds__(256, 1) k_dense_moments(const double* __restrict__ D, SegLayout L,
-                                                          const double* __restrict__ mean, int nn, int ntiles,
-                                                          const int32_t* __restrict__ row_range,
-                                                          double* __restrict__ S) {
+__global__ void __launch_bounds__(DTHREADS, 1) k_dense_moments(const double* __restrict__ D, SegLayout L,
+                                                               const double* __restrict__ mean, int nn, int ntiles,
+                                                               const int32_t* __restrict__ row_range,
+                                                               double* __restrict__ S) {
   __shared__ __align__(16) double As[2][DKC][DLD];
   __shared__ __align__(16) double Bs[2][DKC][DLD];
   // blockIdx.x -> (ti, tj) with ti <= tj  (row-wise enumeration of the upper triangle)
@@ -42,37 +52,39 @@ __global__ void __launch_bounds__(256, 1) k_dense_moments(const double* __restri
   const int seg_beg = L.off[k], seg_len = L.off[k + 1] - L.off[k];
   if (L.cnt[k] == 0) return;
   const int i0 = ti * DT, j0 = tj * DT;
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  // loader mapping: 128 rows x 8 samples = 512 double2; thread handles rows lr + 64 q (q = 0,1), sample pair lc
+  constexpr int NX = DT / DCOLS;  // threads along the columns (16 or 32)
+  constexpr int CG = DCOLS / 2;   // column pairs per thread, NX * 2 columns apart
+  const int tid = threadIdx.x, tx = tid % NX, ty = tid / NX;
+  // loader mapping: 128 rows x 8 samples = 512 double2 per matrix; thread handles rows lr + (128 / DQ) q, sample pair lc
   const int lc = tid & 3, lr = tid >> 2;
-  double ma[2], mb[2];
-  const double* pa[2];
-  const double* pb[2];
+  double ma[DQ], mb[DQ];
+  const double* pa[DQ];
+  const double* pb[DQ];
 #pragma unroll
-  for (int q = 0; q < 2; ++q) {
-    int ra = i0 + lr + 64 * q, rb = j0 + lr + 64 * q;
+  for (int q = 0; q < DQ; ++q) {
+    int ra = i0 + lr + (DT / DQ) * q, rb = j0 + lr + (DT / DQ) * q;
     bool va = ra < nn, vb = rb < nn;
     ma[q] = va ? mean[(size_t)ra * L.K + k] : 0.0;
     mb[q] = vb ? mean[(size_t)rb * L.K + k] : 0.0;
     pa[q] = va ? D + (size_t)ra * L.npad + seg_beg + 2 * lc : nullptr;
     pb[q] = vb ? D + (size_t)rb * L.npad + seg_beg + 2 * lc : nullptr;
   }
-  double acc[8][8];
+  double acc[8][DCOLS];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
+    for (int j = 0; j < DCOLS; ++j) acc[i][j] = 0.0;
 
-  // Staging of the next 8-sample stage: global -> the thread's OWN four 16-byte slots of `raw` by cp.async (no
-  // registers are held across the 512 FMAs of a stage; with register staging ptxas sank the loads behind the FMA
-  // block and a quarter of the kernel waited for them), then centred + transposed into As/Bs by the same thread.
-  extern __shared__ __align__(16) double2 raw[];  // [4][256]: slot u of thread t at raw[u * 256 + t]
+  // Staging of the next 8-sample stage: global -> the thread's OWN 16-byte slots of `raw` by cp.async (no registers
+  // are held across the FMAs of a stage; with register staging ptxas sank the loads behind the FMA block), then
+  // centred + transposed into As/Bs by the same thread.
+  extern __shared__ __align__(16) double2 raw[];  // [2 DQ][DTHREADS]: slot u of thread t at raw[u * DTHREADS + t]
   auto gload = [&](int kk) {  // segment length is a multiple of 4, DKC = 8: guard the tail per double2
     const bool in = kk + 2 * lc < seg_len;
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      double2* da = raw + (2 * q) * 256 + tid;
-      double2* db = raw + (2 * q + 1) * 256 + tid;
+    for (int q = 0; q < DQ; ++q) {
+      double2* da = raw + (2 * q) * DTHREADS + tid;
+      double2* db = raw + (2 * q + 1) * DTHREADS + tid;
       if (in && pa[q]) {
         const unsigned sa = (unsigned)__cvta_generic_to_shared(da);
         asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(pa[q] + kk) : "memory");
@@ -91,12 +103,13 @@ __global__ void __launch_bounds__(256, 1) k_dense_moments(const double* __restri
   auto sstore = [&](int buf) {  // transposed + centred
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const double2 va = raw[(2 * q) * 256 + tid], vb = raw[(2 * q + 1) * 256 + tid];
-      As[buf][2 * lc][lr + 64 * q] = va.x - ma[q];
-      As[buf][2 * lc + 1][lr + 64 * q] = va.y - ma[q];
-      Bs[buf][2 * lc][lr + 64 * q] = vb.x - mb[q];
-      Bs[buf][2 * lc + 1][lr + 64 * q] = vb.y - mb[q];
+    for (int q = 0; q < DQ; ++q) {
+      const double2 va = raw[(2 * q) * DTHREADS + tid], vb = raw[(2 * q + 1) * DTHREADS + tid];
+      const int row = lr + (DT / DQ) * q;
+      As[buf][2 * lc][row] = va.x - ma[q];
+      As[buf][2 * lc + 1][row] = va.y - ma[q];
+      Bs[buf][2 * lc][row] = vb.x - mb[q];
+      Bs[buf][2 * lc + 1][row] = vb.y - mb[q];
     }
   };
   gload(0);
@@ -108,20 +121,23 @@ __global__ void __launch_bounds__(256, 1) k_dense_moments(const double* __restri
     if (more) gload(kk + DKC);
 #pragma unroll
     for (int s = 0; s < DKC; ++s) {
-      double a[8], b[8];
+      double a[8], b[DCOLS];
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         double2 va = *reinterpret_cast<const double2*>(&As[buf][s][ty * 2 + 32 * g]);
-        double2 vb = *reinterpret_cast<const double2*>(&Bs[buf][s][tx * 2 + 32 * g]);
         a[2 * g] = va.x;
         a[2 * g + 1] = va.y;
+      }
+#pragma unroll
+      for (int g = 0; g < CG; ++g) {
+        double2 vb = *reinterpret_cast<const double2*>(&Bs[buf][s][tx * 2 + 2 * NX * g]);
         b[2 * g] = vb.x;
         b[2 * g + 1] = vb.y;
       }
 #pragma unroll
       for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < DCOLS; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
     }
     if (more) {
       sstore(buf ^ 1);
@@ -135,8 +151,8 @@ __global__ void __launch_bounds__(256, 1) k_dense_moments(const double* __restri
     const int r = i0 + ty * 2 + 32 * (i >> 1) + (i & 1);
     if (r >= nn) continue;
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      const int c = j0 + tx * 2 + 32 * g;
+    for (int g = 0; g < CG; ++g) {
+      const int c = j0 + tx * 2 + 2 * NX * g;
       if (c + 1 < nn && !(nn & 1)) {  // 16-byte aligned only when the row pitch is even
         *reinterpret_cast<double2*>(Sk + (size_t)r * nn + c) = make_double2(acc[i][2 * g], acc[i][2 * g + 1]);
       } else {

@@ -869,7 +869,7 @@ int run_shard_main(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
         CU(cudaFuncSetAttribute(k_dense_moments, cudaFuncAttributeMaxDynamicSharedMemorySize, DENSE_DYN_SMEM));
         s.dense_attr_set = true;
       }
-      LAUNCH(k_dense_moments, grid, 256, DENSE_DYN_SMEM, s.s_main, s.D.as<double>(), L, s.mean.as<double>(),
+      LAUNCH(k_dense_moments, grid, DTHREADS, DENSE_DYN_SMEM, s.s_main, s.D.as<double>(), L, s.mean.as<double>(),
              (int)n_nodes, ntl, d_range, s.dense_S.as<double>());
     } else {
       switch (K) {
