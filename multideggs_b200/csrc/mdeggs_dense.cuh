@@ -19,7 +19,15 @@ namespace mdeggs {
 
 constexpr int DT = 128;   // tile edge (genes)
 constexpr int DKC = 8;    // samples per shared-memory stage (2 stages x 2 tiles = 33 KB static smem)
-constexpr int DLD = DT + 2;  // padded leading dimension of the transposed stage [DKC][DLD]
+// DENSE_USE_MMA = 1: the 128 x 128 tile is computed with the FP64 tensor-core instruction mma.sync.m8n8k4 (a warp owns
+// 32 x 64 = 4 x 8 MMA tiles; same 64 accumulators per thread as the FMA form, 8x fewer instructions per flop);
+// 0: 8 x DCOLS FMA thread tiles.
+#ifndef DENSE_USE_MMA
+#define DENSE_USE_MMA 1
+#endif
+// padded leading dimension of the transposed stage [DKC][DLD]: DLD = 8 (mod 16) keeps the 8-row x 4-sample fragment
+// loads of the MMA form at the minimum of two shared-memory wavefronts
+constexpr int DLD = DENSE_USE_MMA ? DT + 8 : DT + 2;
 
 // Thread tile 8 rows x DCOLS columns: DCOLS = 8 -> 256 threads, 64 accumulators (one 234-register CTA per SM, two
 // warps per scheduler); DCOLS = 4 -> 512 threads, 32 accumulators, four warps per scheduler.  Measured on config 5:
@@ -69,11 +77,23 @@ __global__ void __launch_bounds__(DTHREADS, 1) k_dense_moments(const double* __r
     pa[q] = va ? D + (size_t)ra * L.npad + seg_beg + 2 * lc : nullptr;
     pb[q] = vb ? D + (size_t)rb * L.npad + seg_beg + 2 * lc : nullptr;
   }
+#if DENSE_USE_MMA
+  static_assert(DTHREADS == 256, "MMA form: 8 warps, warp tile 32 x 64");
+  const int lane = tid & 31, wid = tid >> 5;
+  const int wrow = (wid >> 1) * 32, wcol = (wid & 1) * 64;  // warp tile origin inside the CTA tile
+  const int fr = lane >> 2, fk = lane & 3;                  // fragment row / sample of this lane
+  double acc[4][8][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+#else
   double acc[8][DCOLS];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
     for (int j = 0; j < DCOLS; ++j) acc[i][j] = 0.0;
+#endif
 
   // Staging of the next 8-sample stage: global -> the thread's OWN 16-byte slots of `raw` by cp.async (no registers
   // are held across the FMAs of a stage; with register staging ptxas sank the loads behind the FMA block), then
@@ -119,6 +139,23 @@ __global__ void __launch_bounds__(DTHREADS, 1) k_dense_moments(const double* __r
   for (int kk = 0; kk < seg_len; kk += DKC) {
     const bool more = kk + DKC < seg_len;
     if (more) gload(kk + DKC);
+#if DENSE_USE_MMA
+#pragma unroll
+    for (int k0 = 0; k0 < DKC; k0 += 4) {  // D[8x8] += A[8 rows x 4 samples] * B[4 samples x 8 rows]
+      double a[4], b[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[buf][k0 + fk][wrow + 8 * i + fr];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) b[j] = Bs[buf][k0 + fk][wcol + 8 * j + fr];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                       : "+d"(acc[i][j][0]), "+d"(acc[i][j][1])
+                       : "d"(a[i]), "d"(b[j]));
+    }
+#else
 #pragma unroll
     for (int s = 0; s < DKC; ++s) {
       double a[8], b[DCOLS];
@@ -139,6 +176,7 @@ __global__ void __launch_bounds__(DTHREADS, 1) k_dense_moments(const double* __r
 #pragma unroll
         for (int j = 0; j < DCOLS; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
     }
+#endif
     if (more) {
       sstore(buf ^ 1);
       __syncthreads();
@@ -146,6 +184,25 @@ __global__ void __launch_bounds__(DTHREADS, 1) k_dense_moments(const double* __r
     }
   }
   double* Sk = S + (size_t)k * nn * nn;
+#if DENSE_USE_MMA
+  (void)tx;
+  (void)ty;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = i0 + wrow + 8 * i + fr;
+    if (r >= nn) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = j0 + wcol + 8 * j + 2 * fk;
+      if (c + 1 < nn && !(nn & 1)) {  // 16-byte aligned only when the row pitch is even
+        *reinterpret_cast<double2*>(Sk + (size_t)r * nn + c) = make_double2(acc[i][j][0], acc[i][j][1]);
+      } else {
+        if (c < nn) Sk[(size_t)r * nn + c] = acc[i][j][0];
+        if (c + 1 < nn) Sk[(size_t)r * nn + c + 1] = acc[i][j][1];
+      }
+    }
+  }
+#else
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int r = i0 + ty * 2 + 32 * (i >> 1) + (i & 1);
@@ -161,6 +218,7 @@ __global__ void __launch_bounds__(DTHREADS, 1) k_dense_moments(const double* __r
       }
     }
   }
+#endif
 }
 
 // [min, max] over this rank's edges of the smaller node index of the edge: the rows of S it will read
