@@ -19,7 +19,7 @@ import numpy as np
 import pandas as pd
 
 from . import _abi, host
-from .engine import Engine, default_engine, default_pool
+from .engine import Engine, OmicError, default_engine, default_pool
 from .host import NO_LINKS, Assay, Factor, IndexedNetwork
 
 DEFAULT_PERCENTILES = _abi.r_seq(0.35, 0.98, 0.05)   # core_functions.R:137
@@ -103,7 +103,11 @@ def get_diffNetworks(assayData, metadata, category_variable=None, regression_met
         results = default_pool().run_omics([p.problem for p in preps.values()],
                                            [host.want_fields(p) for p in preps.values()])
         for (name, prep), res in zip(preps.items(), results):
-            if isinstance(res, Exception):
+            if isinstance(res, OmicError):  # the engine rejected this layer: same tryCatch as any other per-omic error
+                host.message(str(res))
+                nets[name] = None
+                continue
+            if isinstance(res, Exception):  # CUDA / NCCL failure: never swallowed
                 raise res
             try:
                 nets[name] = host.assemble_networks(prep, res, cores=cores, verbose=verbose)
@@ -118,7 +122,7 @@ def get_diffNetworks(assayData, metadata, category_variable=None, regression_met
                                                          lmer_ctrl, network, percentile_vector, padj_method,
                                                          show_progressBar, verbose, cores, engine=engine,
                                                          tested_coef=tested_coef, rlm_cov_mode=rlm_cov_mode)
-            except (ValueError, ArithmeticError) as e:
+            except (ValueError, ArithmeticError, OmicError) as e:
                 host.message(str(e))
                 nets[name] = None
     return Deggs(diffNetworks=nets, assayData=assay_list, metadata=meta, regression_method=regression_method,

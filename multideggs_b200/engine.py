@@ -31,6 +31,16 @@ class EngineError(RuntimeError):
     pass
 
 
+class OmicError(EngineError):
+    """The engine rejected THIS omic layer (MDEGGS_EINVAL / EUNSUPPORTED / ENOMEM: n <= 2K, rlm rows too long for shared
+    memory, an edge index outside 1..G ...).  The host treats it like any other per-omic error of the reference's
+    tryCatch (core_functions.R:219-233): message + NULL layer.  CUDA / NCCL failures and a missing library stay plain
+    EngineError and are never swallowed."""
+
+
+_LAYER_CODES = (-1, -4, -5)  # MDEGGS_EINVAL, MDEGGS_ENOMEM, MDEGGS_EUNSUPPORTED
+
+
 def load_library() -> C.CDLL:
     """dlopen libmdeggs.so and declare prototypes. Raises EngineError if it is not built."""
     global _LIB
@@ -122,7 +132,9 @@ class Engine:
     def _check(self, rc: int, what: str) -> None:
         if rc != 0:
             msg = self._lib.mdeggs_last_error(self._ctx)
-            raise EngineError(f"{what}: {self._lib.mdeggs_strerror(rc).decode()}: {msg.decode() if msg else ''}")
+            cls = OmicError if rc in _LAYER_CODES and what.startswith(("mdeggs_run", "mdeggs_submit", "mdeggs_wait")) \
+                else EngineError
+            raise cls(f"{what}: {self._lib.mdeggs_strerror(rc).decode()}: {msg.decode() if msg else ''}")
 
     # -- the hot path ---------------------------------------------------------------------------
     def run_omic(self, problem: _abi.Problem, want: Sequence[str] = _abi.DEFAULT_WANT) -> dict[str, np.ndarray]:
@@ -232,8 +244,9 @@ class EnginePool:
                 out.append(keep[i][2])
             else:
                 msg = lib.mdeggs_last_error(engs[i]._ctx)
-                out.append(EngineError(f"mdeggs_run_omics[{i}]: {lib.mdeggs_strerror(rcs[i]).decode()}: "
-                                       f"{msg.decode() if msg else ''}"))
+                cls = OmicError if rcs[i] in _LAYER_CODES else EngineError
+                out.append(cls(f"mdeggs_run_omics[{i}]: {lib.mdeggs_strerror(rcs[i]).decode()}: "
+                               f"{msg.decode() if msg else ''}"))
         return out
 
 

@@ -197,6 +197,42 @@ def test_failing_pair_semantics_follow_cores(bundled, oracle):
     assert isinstance(nr, str) or "TNF-TNFRSF1A" not in nr.index
 
 
+def test_one_bad_layer_does_not_stop_the_others(bundled, oracle, monkeypatch):
+    """core_functions.R:219-233: the per-omic tryCatch turns ANY error of a layer into message() + NULL.  An engine-side
+    rejection of one layer (OmicError) must behave the same in the batched multi-omic path and the per-layer path."""
+    import pyoracle
+    from multideggs_b200 import api
+    from multideggs_b200.engine import OmicError
+
+    class FakePool:  # the oracle as the compute of the good layers; the second layer is rejected by "the engine"
+        def run_omics(self, problems, wants):
+            return [OmicError("mdeggs_run_omics[1]: unsupported configuration: test") if i == 1
+                    else pyoracle.run_omic(p, w) for i, (p, w) in enumerate(zip(problems, wants))]
+
+    class FakeEngine:
+        calls = 0
+
+        def run_omic(self, problem, want):
+            FakeEngine.calls += 1
+            if FakeEngine.calls == 2:
+                raise OmicError("mdeggs_run_omic: invalid argument: test")
+            return pyoracle.run_omic(problem, want)
+
+    assays = {k: bundled[k] for k in ("RNAseq", "Proteomics", "Olink")}
+    msgs = []
+    monkeypatch.setattr(host, "_message", msgs.append)
+    monkeypatch.setattr(api, "default_pool", lambda: FakePool())
+    for kw in ({}, {"engine": FakeEngine()}):
+        msgs.clear()
+        deggs = md.get_diffNetworks(assayData=assays, metadata=bundled["metadata"], category_variable="response",
+                                    regression_method="lm", padj_method="bonferroni", verbose=False,
+                                    show_progressBar=False, cores=1, **kw)
+        nets = deggs["diffNetworks"]
+        assert list(nets) == ["RNAseq", "Proteomics", "Olink"]
+        assert nets["Proteomics"] is None and any("test" in m for m in msgs)
+        assert nets["RNAseq"]["sig_pvalues_count"] == 7 and nets["Olink"]["sig_pvalues_count"] == 0
+
+
 def test_host_adjust_methods(oracle):
     rng = np.random.default_rng(3)
     p = rng.uniform(size=50) ** 2

@@ -5,7 +5,7 @@ import pytest
 
 import multideggs_b200 as md
 from multideggs_b200 import _abi, host, synth
-from helpers import ALL_FIELDS, assert_parity, rel_close
+from helpers import ALL_FIELDS, assert_parity, check_r_pinned, rel_close
 
 pytestmark = pytest.mark.gpu
 
@@ -108,6 +108,27 @@ def test_device_tails_match_oracle(engine, oracle):
         assert np.all(np.abs(got - ref) <= 1e-10 * ref + 1e-300), (d1, d2)
 
 
+def test_device_tails_against_mpmath(engine):
+    """The device tail routines checked DIRECTLY against 50-digit mpmath (independent of the oracle, whose tails share
+    the continued-fraction algorithm): pt lower tail at negative t = half the two-sided tail; pf upper tail incl. the
+    closed form for 2 numerator d.f.; the reference's 2*(1-pt(|t|)) within its own 2.2e-16 quantisation."""
+    import oracle_np
+    ts = np.array([1e-6, 0.3, 1.0, 1.8, 2.5, 4.0, 5.5, 9.9, 12.2, 28.8, 40.0])
+    for df in (1.0, 2.0, 5.0, 18.0, 96.0, 996.0, 1996.0, 4e5):
+        true2 = np.array([oracle_np.t_two_sided_mp(float(x), df) for x in ts])
+        rtol = 2e-12 if df <= 2000 else 1e-10     # long continued fractions at df ~ 1e5 accumulate ~1e-11
+        lower = engine.dev_pt(-ts, df)            # pt(-|t|) = P(T < -|t|): no cancellation, meaningful to 1e-300
+        assert np.all(np.abs(lower - true2 / 2) <= rtol * true2 / 2 + 1e-305), df
+        ref = engine.dev_p_two_sided_ref(ts, df)
+        assert np.all(np.abs(ref - true2) <= 1e-9 * true2 + 4.5e-16), df
+        assert np.all((ref / 2.220446049250313e-16) == np.round(ref / 2.220446049250313e-16)), "2.2e-16 grid"
+    fs = np.array([1e-8, 0.1, 0.9, 1.0, 3.7, 25.0, 300.0, 5e3, 1e5])
+    for d1, d2 in ((1.0, 96.0), (2.0, 994.0), (2.0, 6.0), (3.0, 20.0), (7.0, 1992.0), (1.0, 1e5), (2.0, 1994.0)):
+        true = np.array([oracle_np.f_upper_mp(float(x), d1, d2) for x in fs])
+        got = engine.dev_pf_upper(fs, d1, d2)
+        assert np.all(np.abs(got - true) <= 5e-12 * true + 1e-305), (d1, d2)
+
+
 # ---- the reference's own test expectations, through the public API on the GPU ------------------------
 def test_get_diffNetworks_multi_omics(engine, bundled):
     """tests/testthat/test-core_functions.R:2-51"""
@@ -123,6 +144,22 @@ def test_get_diffNetworks_multi_omics(engine, bundled):
     assert deggs["diffNetworks"]["Olink"]["Responder"] == md.NO_LINKS
     nr = deggs["diffNetworks"]["RNAseq"]["Non_responder"]
     assert "TNF" in set(nr["from"]) and "TNFRSF1A" in set(nr["to"])
+
+
+def test_real_R_numbers_held_by_the_reference_on_gpu(engine, bundled):
+    """The reference's vignette screenshots hold real R output of this exact call (lm + bonferroni on the bundled data,
+    vignettes/Differential_Network_Analysis.Rmd:75-83; multiDEGGs_1.png, multiDEGGs_2.png, plot_regressions.png):
+    the engine, through the public API, must print the same numbers (helpers.R_PINNED)."""
+    assays = {k: bundled[k] for k in ("RNAseq", "Proteomics", "Olink")}
+    deggs = md.get_diffNetworks(assayData=assays, metadata=bundled["metadata"], category_variable="response",
+                                regression_method="lm", padj_method="bonferroni", verbose=False,
+                                show_progressBar=False, cores=2, engine=engine)
+    check_r_pinned(deggs["diffNetworks"])
+    # vignettes/Feature_Selection.Rmd:133-136: pairs kept by multiDEGGs_filter on the full bundled data
+    y = bundled["metadata"]["response"].cat.codes.to_numpy() + 1.0
+    res = md.multiDEGGs_filter(y=y, x=bundled["RNAseq"].T, engine=engine)
+    assert set(res["pairs"]["from"] + ":" + res["pairs"]["to"]) == {
+        "TNF:TNFRSF1A", "AKT2:MTOR", "IL1B:IL1R2", "FASLG:FAS", "TGFB3:TGFBR1", "MAP2K2:MAPK3", "FANCD2:FAN1"}
 
 
 def test_get_multiOmics_diffNetworks_rlm_BH(engine, bundled):
@@ -339,18 +376,18 @@ def test_quantile_select_tie_groups_and_overflow(oracle):
     eng.close()
 
 
-def test_cfg4_filter_flow_scaled_down(engine, oracle):
-    """Config 4 (multiDEGGs_filter inside nestedcv folds): q.value path = raw p + masks from the device, host adjusts.
-    The public API on the GPU must select exactly the pairs the same host flow selects from the oracle's numbers."""
+def _cfg4_flow(engine, oracle, wl, folds, raw_parity):
+    """multiDEGGs_filter on the full data and on every training fold (fs:77-90 as nestedcv calls it): the public API on
+    the GPU must select exactly the pairs the same host flow selects from the oracle's numbers; with `raw_parity` the
+    engine's per-edge / per-percentile outputs of every call are also compared field by field."""
     import pandas as pd
     from helpers import oracle_single_omic
-    wl = synth.cfg4(n_features=1500, n_samples=24, planted=0.15)
+    n = wl.assay.values.shape[1]
     x = pd.DataFrame(wl.assay.values.T, index=wl.assay.samples, columns=wl.assay.genes)
     y = wl.group.astype(float)
-    rng = np.random.default_rng(4)
-    folds = np.array_split(rng.permutation(24), 3)
+    n_with_pairs = 0
     for hold in [None] + folds:
-        keep = np.ones(24, dtype=bool)
+        keep = np.ones(n, dtype=bool)
         if hold is not None:
             keep[hold] = False
         xs, ys = x.iloc[keep], y[keep]
@@ -375,6 +412,37 @@ def test_cfg4_filter_flow_scaled_down(engine, oracle):
             assert got_pairs == [] or isinstance(got_pairs, str)
         else:
             assert got_pairs == exp_pairs
+            n_with_pairs += len(exp_pairs) > 0
+        if raw_parity:
+            prep = host.prepare_omic(counts, "assayData1", fac, "lm", None, md.FILTER_PERCENTILES, "q.value")
+            want = ("cutoff", "median", "p_edge", "stat", "status", "tot_edges", "sig_count", "fail_count", "best",
+                    "cat", "cat_best", "padj_best")
+            gpu, ref = _both(engine, oracle, prep.problem, want)
+            assert_parity(gpu, ref, prep.problem, what=f"cfg4 fold (held out {hold}): ")
+    return n_with_pairs
+
+
+def test_cfg4_filter_flow_scaled_down(engine, oracle):
+    """Config 4 (multiDEGGs_filter inside nestedcv folds), scaled down: 1,500 features, 3 folds + full data."""
+    wl = synth.cfg4(n_features=1500, n_samples=24, planted=0.15)
+    folds = np.array_split(np.random.default_rng(4).permutation(24), 3)
+    _cfg4_flow(engine, oracle, wl, folds, raw_parity=False)
+
+
+def test_cfg4_full_size_ten_folds(engine, oracle):
+    """Config 4 at BASELINE size: 5,000 features x 24 samples (12 / 12), 10 stratified folds + the full data = 11 calls
+    of multiDEGGs_filter (15 percentiles, q.value), every call compared with the oracle field by field."""
+    wl = synth.cfg4()
+    assert wl.assay.values.shape == (5000, 24)
+    rng = np.random.default_rng(20261020)
+    folds = [[] for _ in range(10)]
+    for c in (1, 2):  # stratified: deal each category's samples round the folds
+        idx = rng.permutation(np.flatnonzero(wl.group == c))
+        for j, s in enumerate(idx.tolist()):
+            folds[(j + (c - 1) * 5) % 10].append(s)
+    folds = [np.array(sorted(f)) for f in folds]
+    assert sorted(np.concatenate(folds).tolist()) == list(range(24))
+    assert _cfg4_flow(engine, oracle, wl, folds, raw_parity=True) >= 1
 
 
 @pytest.mark.parametrize("padj", ["none", "holm", "hochberg", "BY", "hommel", "q.value"])

@@ -6,7 +6,7 @@ import pytest
 
 import multideggs_b200 as md
 from multideggs_b200 import _abi, host, synth
-from helpers import oracle_single_omic
+from helpers import check_r_pinned, oracle_single_omic
 import oracle_np
 
 
@@ -32,6 +32,20 @@ def test_reference_known_answers_lm_bonferroni(bundled, factor, oracle):
     # survey probe: Proteomics 8/0 with 5 significant, Olink 1/0 with 0 significant
     assert out["Proteomics"]["Non_responder"].shape[0] == 8 and out["Proteomics"]["sig_pvalues_count"] == 5
     assert out["Olink"]["Non_responder"].shape[0] == 1 and out["Olink"]["sig_pvalues_count"] == 0
+
+
+def test_real_R_numbers_held_by_the_reference(bundled, factor, oracle):
+    """lm + bonferroni is pinned to real R output at 2-4 significant digits, incl. the exact 0 and the 2.2e-16 grid."""
+    out = {k: oracle_single_omic(bundled[k], k, factor, "lm", None, md.DEFAULT_PERCENTILES, "bonferroni")
+           for k in ("RNAseq", "Proteomics")}
+    check_r_pinned(out)
+    # vignettes/Feature_Selection.Rmd:133-136: the pairs multiDEGGs_filter keeps on the full bundled data (q.value path)
+    y = pd.Series(bundled["metadata"]["response"].cat.codes.to_numpy() + 1.0, index=bundled["RNAseq"].columns)
+    q = oracle_single_omic(bundled["RNAseq"], "assayData1", host.tidy_metadata(metadata=y), "lm", None,
+                           md.FILTER_PERCENTILES, "q.value")
+    kept = {i.replace("-", ":") for f in q.values() if isinstance(f, pd.DataFrame)
+            for i in f.index[(f["p.adj"] < 0.05).to_numpy()]}
+    assert kept == {"TNF:TNFRSF1A", "AKT2:MTOR", "IL1B:IL1R2", "FASLG:FAS", "TGFB3:TGFBR1", "MAP2K2:MAPK3", "FANCD2:FAN1"}
 
 
 def test_reference_known_answers_rlm_BH(bundled, factor, oracle):
