@@ -64,13 +64,18 @@ extern "C" {
 
 /* per-edge status (never an error of the call; the host decides what R would have done) */
 #define MDEGGS_EDGE_OK 0
-#define MDEGGS_EDGE_SINGULAR 1    /* solve(XtX) would throw (core_functions.R:1068) / rank-deficient design */
+#define MDEGGS_EDGE_SINGULAR 1    /* K == 2: solve(XtX) would throw (core_functions.R:1068) / rlm refuses a singular design */
 #define MDEGGS_EDGE_NONFINITE 2   /* NA/NaN/Inf in either gene row (.lm.fit would error)              */
 #define MDEGGS_EDGE_NOT_CONVERGED 3 /* rlm: 20 IRLS iterations without convergence (R: warning only)  */
 #define MDEGGS_EDGE_ZERO_SCALE 4  /* rlm: MAD scale == 0                                              */
 #define MDEGGS_EDGE_SELFLOOP 5    /* exact fit: from == to (the built-in network has one self-loop) or a response
                                      that is constant inside every category; R returns rounding noise / noise,
                                      the engine returns p = 1, stat = 0 (documented deviation)              */
+#define MDEGGS_EDGE_ALIASED 6     /* K >= 3 only, soft: the predictor is constant inside a category (or the category has
+                                     one sample), so aov() drops the aliased A:metadata column(s) instead of failing
+                                     (core_functions.R:966-968): F and p use the reduced degrees of freedom
+                                     (Ke - 1 - aliased, n - 2 Ke + aliased), not the run's `df`; when no interaction
+                                     column is left the summary table has no third term row and p is NA (NaN)      */
 
 /* error codes */
 #define MDEGGS_OK 0
@@ -179,7 +184,7 @@ int mdeggs_last_stats(const mdeggs_ctx* ctx, mdeggs_stats* out);
 /* Engine options: "graph" (1 = replay the compute phase from a CUDA graph when a call repeats with identical
  * shapes and buffers [default], 0 = always launch eagerly, which also keeps the per-stage timings);
  * "fit_path" (-1 = choose streaming vs dense-tile pair fits automatically [default], 0 = streaming, 1 = dense);
- * "sort_path" (-1 = K8 orders the edges through p-value buckets up to 4M edges and with a CUB radix sort beyond
+ * "sort_path" (-1 = K8 orders the edges through p-value buckets up to 2^26 edges and with a CUB radix sort beyond
  * [default], 0 = always the radix sort, 1 = buckets whenever possible);
  * "trace" (1 = print the end time of every launch of the next calls to stderr; implies eager launches);
  * "zero_copy" (1 = a pinned host assay is read by the gather kernel straight over PCIe instead of being copied first;

@@ -152,6 +152,7 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finish(int src, const double* _
   const bool live = e < e_hi && !*err;
   double p = 0.0;
   bool deferred = false;
+  int n_alias = 0;
   tc.lbeta_ab = *lbeta_p;
   if (live) {
   if (src != 2) {
@@ -172,13 +173,16 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finish(int src, const double* _
 #pragma unroll
         for (int k = 0; k < K; ++k) pm.sxy[k] = L.cnt[k] ? __ldg(S + ((size_t)k * nn + i) * nn + j) : 0.0;
       }
-      finish_pair<K>(L, mean, sxx, a, b, pm, stat + e, status + e, coef ? coef + (size_t)e * 2 * K : nullptr);
+      finish_pair<K>(L, mean, sxx, a, b, pm, stat + e, status + e, coef ? coef + (size_t)e * 2 * K : nullptr, &n_alias);
     }
   }
   const int st = status[e];
   if (st == MDEGGS_EDGE_SINGULAR || st == MDEGGS_EDGE_NONFINITE || st == MDEGGS_EDGE_ZERO_SCALE) p = nan("");
   else if (st == MDEGGS_EDGE_SELFLOOP) p = 1.0;
-  else {
+  else if (st == MDEGGS_EDGE_ALIASED) {  // rare: this edge's own degrees of freedom, generic continued fraction
+    const double sv = stat[e];
+    p = isnan(sv) ? nan("") : pf_upper_dev(sv, df1 - (double)n_alias, df2 + (double)n_alias);
+  } else {
     // fin_q: first try a short continued fraction (enough away from the mode of the distribution); the edges that
     // need the long one (O(sqrt(max(a, b))) terms, a deep dependent FP64 chain) are queued for k_finish_slow, where
     // every lane is such an edge, instead of holding their whole warps here

@@ -5,8 +5,9 @@
 // every edge needs the K within-category centred cross moments Sxy_k(a,b).  When the edge list covers a
 // large fraction of all node pairs, streaming two 16n-byte rows per edge re-reads each gene row thousands of
 // times (config 5: 256 GB of L1/L2 traffic).  Here a CTA stages a 128-gene x 8-sample tile of two row blocks
-// in shared memory (centred on the fly) and accumulates the 128x128 block of cross moments in registers
-// (8x8 per thread, plain FP64 FMAs — no tensor cores), so each row is read nn/128 times instead of ~nn times.
+// in shared memory (centred on the fly) and accumulates the 128x128 block of cross moments in registers with the FP64
+// tensor-core instruction (mma.sync.m8n8k4.f64, 64 accumulators per thread; the 8x8-FMA form stays behind
+// DENSE_USE_MMA = 0), so each row is read nn/128 times instead of ~nn times.  (tcgen05 has no FP64 type.)
 // Only tile pairs with ti <= tj are computed (Sxy is symmetric); k_finish (src 1) then finishes each edge
 // from Sxy[min(a,b)][max(a,b)] with the same closed forms as the streaming path (finish_pair).
 #pragma once

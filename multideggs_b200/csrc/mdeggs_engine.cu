@@ -130,6 +130,7 @@ struct mdeggs_ctx {
   int key_hits = 0;
   cudaGraphExec_t graph_exec = nullptr;
   int64_t graph_launches = 0;
+  int graph_fit_path = 0;    // stats.fit_path of the captured call (run_shard_main does not run on replay)
   int64_t rsel_cap_override = 0;  // option "rsel_cap": shrink the candidate list to exercise the overflow path (tests)
   int fit_path_override = -1;  // -1 auto, 0 force streaming, 1 force dense (MDEGGS_FIT_PATH, tests)
   bool last_zc = false;        // the last call read its assay through zero copy
@@ -852,7 +853,7 @@ int run_shard_main(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
         return MDEGGS_EUNSUPPORTED;
       }
     } else if (use_dense) {
-      // all ranks compute the (replicated) moment matrices; only the edge finishing is sharded
+      // one GPU: all upper-triangular tile pairs; several: only the tile rows this rank's edge block reads (d_range)
       const int ntl = (n_nodes + DT - 1) / DT;
       dim3 grid((unsigned)(ntl * (ntl + 1) / 2), (unsigned)K);
       const int32_t* d_range = nullptr;
@@ -1613,6 +1614,7 @@ int mdeggs_submit_omic(mdeggs_ctx* ctx, const mdeggs_problem* in, mdeggs_result*
           graph_ok = false;
         } else {
           ctx->graph_launches = ctx->launches;
+          ctx->graph_fit_path = ctx->stats.fit_path;
         }
       }
     }
@@ -1620,6 +1622,7 @@ int mdeggs_submit_omic(mdeggs_ctx* ctx, const mdeggs_problem* in, mdeggs_result*
       CU(cudaGraphLaunch(ctx->graph_exec, sh0.s_main));
       CU(cudaEventRecord(sh0.ev[EV_ADJ], sh0.s_main));
       ctx->launches = ctx->graph_launches;
+      ctx->stats.fit_path = ctx->graph_fit_path;
       replayed = true;
     }
   }

@@ -546,35 +546,49 @@ struct PairMoments {
   double sxy[K];
 };
 
+// `n_aliased` (K >= 3): categories whose A:metadata column aov() drops because the predictor is constant inside them;
+// the caller evaluates the tail with (Ke - 1 - n_aliased, n - 2 Ke + n_aliased) degrees of freedom.
 template <int K>
 __device__ __forceinline__ void finish_pair(const SegLayout& L, const double* __restrict__ mean,
                                             const double* __restrict__ sxx, int a, int b,
                                             const PairMoments<K>& pm, double* __restrict__ stat_out,
-                                            int32_t* __restrict__ status_out, double* __restrict__ coef_out) {
+                                            int32_t* __restrict__ status_out, double* __restrict__ coef_out,
+                                            int* __restrict__ n_aliased) {
   double slope[K], icpt[K];
+  bool alias[K];
   double rss = 0.0, s_xy = 0.0, s_xx = 0.0, s_yy = 0.0, inv_sum = 0.0;
-  bool singular = false;
   int Ke = 0;  // categories that have samples in this omic (an empty level is an aliased column in R, quirk q2)
+  int na = 0, last_ok = -1;
 #pragma unroll
   for (int k = 0; k < K; ++k) {
     slope[k] = icpt[k] = nan("");
+    alias[k] = false;
     if (L.cnt[k] == 0) continue;
     ++Ke;
     double ma = mean[(size_t)a * K + k], mb = mean[(size_t)b * K + k];
     double sa = sxx[(size_t)a * K + k], sb = sxx[(size_t)b * K + k];
     double c = pm.sxy[k];
     // LINPACK dqrdc2 declares a column aliased when its residual norm drops below 1e-7 x its norm
-    if (L.cnt[k] < 2 || !(sa > 1e-14 * (sa + (double)L.cnt[k] * ma * ma))) singular = true;
-    slope[k] = c / sa;
-    icpt[k] = mb - slope[k] * ma;
-    rss += sb - c * slope[k];
+    alias[k] = L.cnt[k] < 2 || !(sa > 1e-14 * (sa + (double)L.cnt[k] * ma * ma));
     s_xy += c;
     s_xx += sa;
     s_yy += sb;
+    if (alias[k]) {  // no slope of its own: the category only contributes its spread around the mean
+      ++na;
+      rss += sb;
+      continue;
+    }
+    last_ok = k;
+    slope[k] = c / sa;
+    icpt[k] = mb - slope[k] * ma;
+    rss += sb - c * slope[k];
     inv_sum += 1.0 / sa;
   }
-  if (Ke < 2) singular = true;
+  // K == 2 (lm, core_functions.R:1068): solve(t(X) %*% X) throws on an aliased column -> hard failure.
+  // K >= 3 (aov, core_functions.R:966-968): lm() pivots aliased columns out and the F test keeps the columns left.
+  const bool singular = Ke < 2 || (K == 2 && na > 0);
   const bool exact_fit = !singular && s_yy == 0.0;  // response constant in every category: R returns noise/noise
+  const bool no_test = K > 2 && !singular && Ke - 1 - na <= 0;  // no interaction column left: Pr(>F)[3] is NA
   double stat;
   if (K == 2) {
     double dof = (double)(L.n - 4);
@@ -582,21 +596,31 @@ __device__ __forceinline__ void finish_pair(const SegLayout& L, const double* __
     stat = (slope[1] - slope[0]) / se;
   } else {
     double rss_add = s_yy - s_xy * s_xy / s_xx;
-    double d1 = (double)(Ke - 1), d2 = (double)(L.n - 2 * Ke);
+    double d1 = (double)(Ke - 1 - na), d2 = (double)(L.n - 2 * Ke + na);
     stat = ((rss_add - rss) / d1) / (rss / d2);
   }
-  if (singular) stat = nan("");
+  if (singular || no_test) stat = nan("");
   if (exact_fit) stat = 0.0;
   *stat_out = stat;
-  *status_out = singular ? MDEGGS_EDGE_SINGULAR : (exact_fit ? MDEGGS_EDGE_SELFLOOP : MDEGGS_EDGE_OK);
+  *status_out = singular ? MDEGGS_EDGE_SINGULAR
+                         : (exact_fit ? MDEGGS_EDGE_SELFLOOP : (na > 0 ? MDEGGS_EDGE_ALIASED : MDEGGS_EDGE_OK));
+  *n_aliased = na;
   if (coef_out) {  // R order: (Intercept), A, metadata2..K, A:metadata2..K; NA when the reference level is empty
-    const bool ok = !singular && !exact_fit && L.cnt[0] > 0;
-    coef_out[0] = ok ? icpt[0] : nan("");
-    coef_out[1] = ok ? slope[0] : nan("");
+    const bool ok = !singular && !exact_fit && !no_test && L.cnt[0] > 0;
+    // aliased columns (NA coefficients): A:metadata_j of every category j >= 2 where A is constant; when that is the
+    // reference category itself, lm() instead finds the LAST remaining interaction column dependent, so the common
+    // slope `A` is that category's and its own interaction coefficient is the NA one
+    const int ref = alias[0] ? last_ok : 0;
+    const double b1 = ok ? slope[ref] : nan("");
+    const double b0 = ok ? mean[(size_t)b * K] - b1 * mean[(size_t)a * K] : nan("");
+    coef_out[0] = b0;
+    coef_out[1] = b1;
 #pragma unroll
     for (int k = 1; k < K; ++k) {
-      coef_out[1 + k] = ok ? icpt[k] - icpt[0] : nan("");
-      coef_out[K + k] = ok ? slope[k] - slope[0] : nan("");
+      const bool own = ok && L.cnt[k] > 0 && !alias[k] && k != ref;
+      const double sl = own ? slope[k] : b1;
+      coef_out[1 + k] = (ok && L.cnt[k] > 0) ? (mean[(size_t)b * K + k] - sl * mean[(size_t)a * K + k]) - b0 : nan("");
+      coef_out[K + k] = own ? slope[k] - b1 : nan("");
     }
   }
 }

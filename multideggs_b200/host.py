@@ -244,7 +244,9 @@ def _match_network(network, genes: np.ndarray, assayDataName: str):
     first (core_functions.R:319-331), as 1-based row indices.  Repeated calls with the same network object and the
     same rownames (nestedcv folds) reuse the result."""
     net = omic_network() if network is None else network
-    ident = "builtin" if network is None else (id(net), str(net["from"].iloc[0]), str(net["to"].iloc[-1])) if len(net) else id(net)
+    # user networks are identified by CONTENT (a data.frame mutated in place, or a new one at a recycled id(), must
+    # not hit the entry of the old network)
+    ident = "builtin" if network is None else pd.util.hash_pandas_object(net[["from", "to"]], index=False).values.tobytes()
     key = (ident, len(net), hash(genes.tobytes()), genes.shape[0])
     hit = _NET_MATCH_CACHE.get(key)
     if hit is not None:

@@ -18,9 +18,17 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <unistd.h>
+
 #include "mdeggs.h"
 
+/* Cached contexts are keyed on (process id, number of GPUs):
+ *  - a context created in a parent must never be used in a forked child (mclapply / nestedcv cv.cores > 1): the child
+ *    forgets the parent's pointer WITHOUT destroying it (the CUDA state behind it is not valid there) and creates its
+ *    own on first use;
+ *  - options(multiDEGGs.gpus = ...) changed between calls: the old context is destroyed and a new one is created. */
 static SEXP g_ctx_ptr = NULL; /* external pointer owning the mdeggs_ctx */
+static int g_ctx_pid = 0, g_ctx_gpus = 0;
 
 static void ctx_finalizer(SEXP p) {
   mdeggs_ctx* ctx = (mdeggs_ctx*)R_ExternalPtrAddr(p);
@@ -28,14 +36,25 @@ static void ctx_finalizer(SEXP p) {
   R_ClearExternalPtr(p);
 }
 
+static void forget_ctx(SEXP* slot, int destroy) {
+  if (*slot == NULL) return;
+  if (destroy) ctx_finalizer(*slot);
+  else R_ClearExternalPtr(*slot); /* another process's context: leak it here, never touch it */
+  R_ReleaseObject(*slot);
+  *slot = NULL;
+}
+
 static mdeggs_ctx* get_ctx(int n_gpus) {
+  if (n_gpus < 1) n_gpus = 1;
+  if (n_gpus > 16) n_gpus = 16;
+  const int pid = (int)getpid();
+  if (g_ctx_ptr != NULL && g_ctx_pid != pid) forget_ctx(&g_ctx_ptr, 0);
+  if (g_ctx_ptr != NULL && g_ctx_gpus != n_gpus) forget_ctx(&g_ctx_ptr, 1);
   if (g_ctx_ptr != NULL) {
     mdeggs_ctx* c = (mdeggs_ctx*)R_ExternalPtrAddr(g_ctx_ptr);
     if (c) return c;
   }
   int ids[16];
-  if (n_gpus < 1) n_gpus = 1;
-  if (n_gpus > 16) n_gpus = 16;
   for (int i = 0; i < n_gpus; ++i) ids[i] = i;
   mdeggs_ctx* ctx = NULL;
   int rc = mdeggs_create(&ctx, ids, n_gpus);
@@ -43,6 +62,8 @@ static mdeggs_ctx* get_ctx(int n_gpus) {
   g_ctx_ptr = R_MakeExternalPtr(ctx, R_NilValue, R_NilValue);
   R_PreserveObject(g_ctx_ptr);
   R_RegisterCFinalizerEx(g_ctx_ptr, ctx_finalizer, TRUE);
+  g_ctx_pid = pid;
+  g_ctx_gpus = n_gpus;
   return ctx;
 }
 
@@ -201,8 +222,11 @@ SEXP mdeggs_R_run(SEXP assay, SEXP from_idx, SEXP to_idx, SEXP group, SEXP K_, S
  * engine failed for that layer (the caller turns it into message() like the reference's per-omic tryCatch). */
 #define MDEGGS_R_MAX_LAYERS 16
 static SEXP g_layer_ctx[MDEGGS_R_MAX_LAYERS];
+static int g_layer_pid[MDEGGS_R_MAX_LAYERS];
 
 static mdeggs_ctx* get_layer_ctx(int i) {
+  const int pid = (int)getpid();
+  if (g_layer_ctx[i] != NULL && g_layer_pid[i] != pid) forget_ctx(&g_layer_ctx[i], 0); /* forked child: see get_ctx */
   if (g_layer_ctx[i] != NULL) {
     mdeggs_ctx* c = (mdeggs_ctx*)R_ExternalPtrAddr(g_layer_ctx[i]);
     if (c) return c;
@@ -214,6 +238,7 @@ static mdeggs_ctx* get_layer_ctx(int i) {
   g_layer_ctx[i] = R_MakeExternalPtr(ctx, R_NilValue, R_NilValue);
   R_PreserveObject(g_layer_ctx[i]);
   R_RegisterCFinalizerEx(g_layer_ctx[i], ctx_finalizer, TRUE);
+  g_layer_pid[i] = pid;
   return ctx;
 }
 
@@ -258,7 +283,12 @@ SEXP mdeggs_R_run_layers(SEXP layers) {
 /* .Call("mdeggs_R_pair_features", x, a, b, ratio): predict.multiDEGGs_filter features (fs:423-431) */
 SEXP mdeggs_R_pair_features(SEXP x, SEXP a, SEXP b, SEXP ratio) {
   if (TYPEOF(x) != REALSXP || !Rf_isMatrix(x)) Rf_error("x must be a double matrix (samples x features)");
-  const int n = Rf_nrows(x), np_ = (int)XLENGTH(a);
+  if (TYPEOF(a) != INTSXP || TYPEOF(b) != INTSXP || XLENGTH(a) != XLENGTH(b))
+    Rf_error("a and b must be integer vectors of the same length (0-based column indices)");
+  const int n = Rf_nrows(x), np_ = (int)XLENGTH(a), nc = Rf_ncols(x);
+  for (int j = 0; j < np_; ++j)
+    if (INTEGER(a)[j] < 0 || INTEGER(a)[j] >= nc || INTEGER(b)[j] < 0 || INTEGER(b)[j] >= nc)
+      Rf_error("pair %d refers to a column outside 0..%d", j + 1, nc - 1);
   SEXP out = PROTECT(Rf_allocMatrix(REALSXP, n, np_));
   mdeggs_ctx* ctx = get_ctx(1);
   int rc = mdeggs_pair_features(ctx, REAL(x), n, n, INTEGER(a), INTEGER(b), np_, Rf_asLogical(ratio), MDEGGS_MEM_HOST,

@@ -44,5 +44,6 @@ void R_ClearExternalPtr(SEXP);
 typedef void (*R_CFinalizer_t)(SEXP);
 void R_RegisterCFinalizerEx(SEXP, R_CFinalizer_t, Rboolean);
 void R_PreserveObject(SEXP);
+void R_ReleaseObject(SEXP);
 char* R_alloc(size_t, int);
 #endif

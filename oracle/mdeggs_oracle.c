@@ -480,23 +480,43 @@ int orc_fit_aov(const double* a, const double* b, const int32_t* grp, int n, int
   orc_qr qr;
   double cf[2 * MDEGGS_MAX_K];
   dqrls(X, n, p, b, 1e-7, &qr, cf, resid, eff);
-  if (qr.rank < p) return MDEGGS_EDGE_SINGULAR; /* aliased interaction column: Df/SS rows change in R */
+  /* summary.aov under rank deficiency (A constant inside a category: the RNA-seq gene that is all zero in one group):
+   * lm() pivots the aliased columns to the end, `asgn <- assign[qr$pivot[1:rank]]`, a term keeps df = its number of
+   * non-aliased columns and SS = the sum of their squared effects, a term without any column left has NO row, and
+   * [["Pr(>F)"]][3] is then the Residuals row or out of range: NA.  Nothing throws. */
+  const int r = qr.rank;
+  const int rdf = n - r;
+  if (rdf <= 0) return MDEGGS_EDGE_SINGULAR; /* no F column at all: NULL[3] makes vapply throw */
+  int tdf[4] = {0, 0, 0, 0};
+  double tss[4] = {0.0, 0.0, 0.0, 0.0};
+  int row_term[4], nrows = 0; /* rows of the table without the intercept, in order of first appearance */
+  double cf_orig[2 * MDEGGS_MAX_K];
+  for (int j = 0; j < p; ++j) cf_orig[j] = NAN;
+  for (int j = 0; j < r; ++j) {
+    const int c = qr.pivot[j];
+    const int term = c == 0 ? 0 : (c == 1 ? 1 : (c <= Ke ? 2 : 3));
+    if (term > 0 && tdf[term] == 0) row_term[nrows++] = term;
+    tdf[term]++;
+    tss[term] += eff[j] * eff[j];
+    cf_orig[c] = cf[j];
+  }
+  double rss = 0.0;
+  for (int i = r; i < n; ++i) rss += eff[i] * eff[i];
+  const int aliased = r < p;
+  if (nrows < 3 || row_term[2] != 3) return MDEGGS_EDGE_ALIASED; /* no interaction row: Pr(>F)[3] is NA (soft) */
   if (lev[0] == 0) { /* R order: (Intercept), A, metadata<L2..LK> at 1 + level, A:metadata<L> at K + level */
-    coef[0] = cf[0];
-    coef[1] = cf[1];
+    coef[0] = cf_orig[0];
+    coef[1] = cf_orig[1];
     for (int k = 1; k < Ke; ++k) {
-      coef[1 + lev[k]] = cf[1 + k];
-      coef[K + lev[k]] = cf[Ke + k];
+      coef[1 + lev[k]] = cf_orig[1 + k];
+      coef[K + lev[k]] = cf_orig[Ke + k];
     }
   } /* else: the reference level itself is empty; coefficients are left NA (the F test is unaffected) */
-  double ss_int = 0.0, rss = 0.0;
-  for (int j = Ke + 1; j < p; ++j) ss_int += eff[j] * eff[j];
-  for (int i = p; i < n; ++i) rss += eff[i] * eff[i];
-  double d1 = (double)(Ke - 1), d2 = (double)(n - p);
-  double f = (ss_int / d1) / (rss / d2);
+  double d1 = (double)tdf[3], d2 = (double)rdf;
+  double f = (tss[3] / d1) / (rss / d2);
   *f_out = f;
   *p_out = orc_pf_upper(f, d1, d2);
-  return MDEGGS_EDGE_OK;
+  return aliased ? MDEGGS_EDGE_ALIASED : MDEGGS_EDGE_OK;
 }
 
 /* MASS::rlm(B ~ A * metadata) defaults (psi.huber k = 1.345, init "ls", scale.est "MAD", maxit 20, acc 1e-4,

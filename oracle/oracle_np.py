@@ -69,7 +69,12 @@ def aov_interaction(a, b, grp0, K):
 
     rss_add, _ = rss(X_add)
     rss_full, coef = rss(X_full)
-    d1, d2 = K - 1, n - 2 * K
+    # degrees of freedom from the matrix ranks: with a predictor that is constant inside a category the interaction
+    # loses a column (aov() drops aliased columns, it does not fail); full rank gives (K - 1, n - 2K)
+    r_add, r_full = np.linalg.matrix_rank(X_add, tol=1e-9), np.linalg.matrix_rank(X_full, tol=1e-9)
+    d1, d2 = r_full - r_add, n - r_full
+    if d1 <= 0:
+        return coef, float("nan"), float("nan")   # no A:metadata row in the table: Pr(>F)[3] is NA
     f = ((rss_add - rss_full) / d1) / (rss_full / d2)
     p = float(special.fdtrc(d1, d2, f))
     return coef, f, p

@@ -73,6 +73,34 @@ def test_edge_cases_status(engine, oracle):
     assert_parity(gpu, ref, prob, what="edge cases: ")
 
 
+@pytest.mark.parametrize("K,fit_path", [(3, 0), (4, 0), (3, 1)])
+def test_aov_aliased_columns(engine, oracle, K, fit_path):
+    """K >= 3: a predictor that is constant inside a category (RNA-seq gene all zero in one group) is NOT a failure:
+    aov() drops the aliased A:metadata column (core_functions.R:966-968), status = ALIASED, reduced d.f., fail_count
+    untouched; with a single category left that has a slope, p is NA.  Same through the dense-tile path."""
+    prob = synth.random_problem(40, 90, 160, K, 4100 + K)
+    v = prob.assay.copy()
+    v[2, prob.group == 2] = 0.0                    # constant in a non-reference category
+    v[4, prob.group == 1] = 0.0                    # constant in the reference category
+    v[6, prob.group != 3] = 1.5                    # a slope of its own only in category 3 (K = 3: no interaction left)
+    v[7, :] = 2.0                                  # constant everywhere
+    prob.assay = np.asfortranarray(v)
+    extra = [(3, 1), (3, 9), (5, 2), (5, 11), (7, 12), (8, 13), (1, 3), (2, 5)]   # aliased genes as predictor / response
+    prob.from_idx = np.concatenate([prob.from_idx, [a for a, _ in extra]]).astype(np.int32)
+    prob.to_idx = np.concatenate([prob.to_idx, [b for _, b in extra]]).astype(np.int32)
+    engine.set_option("fit_path", fit_path)
+    try:
+        gpu, ref = _both(engine, oracle, prob)
+    finally:
+        engine.set_option("fit_path", -1)
+    assert engine.stats()["fit_path"] & 0xff == fit_path
+    assert (ref["status"] == _abi.EDGE_ALIASED).sum() >= 4 and not (ref["status"] == _abi.EDGE_SINGULAR).any()
+    assert np.isnan(ref["p_edge"][ref["status"] == _abi.EDGE_ALIASED]).any()
+    assert np.isfinite(ref["p_edge"][ref["status"] == _abi.EDGE_ALIASED]).any()
+    assert ref["fail_count"].sum() == 0
+    assert_parity(gpu, ref, prob, what=f"aliased aov K{K}: ")
+
+
 def test_ties_and_clamped_values(engine, oracle):
     prob = synth.random_problem(60, 50, 200, 3, 51)
     v = np.round(prob.assay, 1)                    # heavy ties: medians / quantiles hit equal values

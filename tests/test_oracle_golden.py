@@ -168,6 +168,45 @@ def test_fits_against_numpy_twin(oracle, seed, n, K):
         assert abs(f - f2) <= 1e-9 * abs(f2) and abs(p - p2) <= 1e-9 * p2
 
 
+def test_aov_with_aliased_interaction_columns(oracle):
+    """K >= 3 goes through aov() (core_functions.R:963-968), which does not fail on a predictor that is constant inside a
+    category (an RNA-seq gene that is all zero in one group): lm() pivots the aliased A:metadata column out, the term
+    keeps the remaining degrees of freedom, and only when no interaction column is left is Pr(>F)[3] NA."""
+    rng = np.random.default_rng(8)
+    n, K = 90, 3
+    grp = np.repeat(np.arange(K), n // K)
+    rng.shuffle(grp)
+    b = 5 + rng.standard_normal(n)
+    for const_in in ([1], [0], [2], [0, 2], [0, 1, 2]):
+        a = 5 + rng.standard_normal(n)
+        for k in const_in:
+            a[grp == k] = 0.0 if k != 1 else 3.25
+        bb = b + 0.8 * a * (grp == 1)
+        st, coef, f, p = oracle.fit_aov(a, bb, grp, K)
+        _, f2, p2 = oracle_np.aov_interaction(a, bb, grp, K)
+        assert st == _abi.EDGE_ALIASED, const_in
+        if len(const_in) >= 2:       # at most one category with a slope of its own: no interaction row at all
+            assert np.isnan(p) and np.isnan(f) and np.isnan(p2) and np.all(np.isnan(coef))
+            continue
+        assert abs(f - f2) <= 1e-9 * abs(f2) and abs(p - p2) <= 1e-9 * p2, const_in
+        # closed form the engine uses: the constant category contributes its Syy to RSS_full and loses one df each way
+        sxx = np.array([np.sum((a[grp == k] - a[grp == k].mean()) ** 2) for k in range(K)])
+        syy = np.array([np.sum((bb[grp == k] - bb[grp == k].mean()) ** 2) for k in range(K)])
+        sxy = np.array([np.sum((a[grp == k] - a[grp == k].mean()) * (bb[grp == k] - bb[grp == k].mean())) for k in range(K)])
+        ok = sxx > 0
+        rss_full = np.sum(syy[ok] - sxy[ok] ** 2 / sxx[ok]) + np.sum(syy[~ok])
+        rss_add = syy.sum() - sxy.sum() ** 2 / sxx.sum()
+        f3 = ((rss_add - rss_full) / (K - 2)) / (rss_full / (n - 2 * K + 1))
+        assert abs(f - f3) <= 1e-9 * abs(f3)
+        # NA coefficient: the aliased category's own interaction, or (reference category constant) the last one
+        na_at = K + (const_in[0] if const_in[0] > 0 else K - 1)
+        assert np.isnan(coef[na_at]) and np.sum(np.isnan(coef)) == 1
+    # a full-rank fit is unchanged
+    a = 5 + rng.standard_normal(n)
+    st, coef, f, p = oracle.fit_aov(a, b, grp, K)
+    assert st == _abi.EDGE_OK and not np.any(np.isnan(coef))
+
+
 @pytest.mark.parametrize("method", ["none", "bonferroni", "BH", "holm", "hochberg", "BY"])
 def test_p_adjust_three_ways(oracle, method):
     rng = np.random.default_rng(11)
