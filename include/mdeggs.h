@@ -180,6 +180,10 @@ int mdeggs_pair_features(mdeggs_ctx* ctx, const double* x, int64_t ldx, int32_t 
 /* Measures this GPU's FP64 FMA peak with a register-only DFMA-chain kernel (TFLOP/s): the denominator of the
  * rlm (K6) roofline, which is FP64-pipe bound (SURVEY section 8 d). */
 int mdeggs_measure_fp64_peak(mdeggs_ctx* ctx, double* tflops_out);
+/* Measures this GPU's L2 -> SM read bandwidth (GB/s) over an L2-resident buffer of `bytes` (>= 1 MiB; use the size of
+ * the gene-major matrix, <= ~100 MB): the denominator of the pair-fit kernel's roofline, whose 16 n + 16 algorithmic
+ * bytes per fit are served by L2, not by HBM (the matrix is read ~12 times per run and fits the 126 MB L2). */
+int mdeggs_measure_l2_peak(mdeggs_ctx* ctx, int64_t bytes, double* gbs_out);
 int mdeggs_last_stats(const mdeggs_ctx* ctx, mdeggs_stats* out);
 /* Engine options: "graph" (1 = replay the compute phase from a CUDA graph when a call repeats with identical
  * shapes and buffers [default], 0 = always launch eagerly, which also keeps the per-stage timings);

@@ -1897,6 +1897,36 @@ int mdeggs_measure_fp64_peak(mdeggs_ctx* ctx, double* tflops_out) {
   return MDEGGS_OK;
 }
 
+int mdeggs_measure_l2_peak(mdeggs_ctx* ctx, int64_t bytes, double* gbs_out) {
+  if (!ctx || !gbs_out || bytes < (1 << 20)) return MDEGGS_EINVAL;
+  Shard& s = ctx->shards[0];
+  CU(cudaSetDevice(s.device));
+  DevBuf buf;
+  const size_t n_vec = (size_t)bytes / 16;
+  if (buf.ensure(n_vec * 16) != cudaSuccess) return MDEGGS_ENOMEM;
+  CU(s.small_out.ensure(64));
+  cudaMemsetAsync(buf.p, 0x5a, n_vec * 16, s.s_main);
+  // enough passes that the launch latency vanishes (>= 4 GB read from L2 per launch)
+  const int passes = (int)(((size_t)4 << 30) / (n_vec * 16)) + 8;
+  float best_ms = 1e30f;
+  int rc = MDEGGS_OK;
+  for (int ctas_per_sm : {4, 8}) {
+    for (int rep = 0; rep < 4; ++rep) {  // the first repetition also brings the buffer into L2
+      cudaEventRecord(s.ev[EV_Q0], s.s_main);
+      LAUNCH(k_l2_read, 148 * ctas_per_sm, 256, 0, s.s_main, buf.as<uint4>(), n_vec, passes,
+             s.small_out.as<unsigned int>());
+      cudaEventRecord(s.ev[EV_Q1], s.s_main);
+      if (cudaStreamSynchronize(s.s_main) != cudaSuccess) rc = MDEGGS_ECUDA;
+      const float ms = ev_ms(s.ev[EV_Q0], s.ev[EV_Q1]);
+      if (rep > 0 && ms > 0.f && ms < best_ms) best_ms = ms;
+    }
+  }
+  buf.release();
+  if (rc) return rc;
+  *gbs_out = (double)(n_vec * 16) * passes / ((double)best_ms * 1e-3) / 1e9;
+  return MDEGGS_OK;
+}
+
 int mdeggs_dev_pt(mdeggs_ctx* ctx, const double* x, const double* df, int64_t n, double* out) {
   return dev_math(ctx, 0, x, df, nullptr, n, out);
 }

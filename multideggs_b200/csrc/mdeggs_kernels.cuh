@@ -1583,6 +1583,25 @@ __global__ void __launch_bounds__(256) k_dfma_peak(int iters, double seed, doubl
   if (t == 12345.678) sink[0] = t;  // never true: keeps the chains alive
 }
 
+// L2 read bandwidth of this GPU for an L2-resident working set (denominator of the pair-fit roofline: the gene-major
+// matrix D, <= 67 MB, stays in the 126 MB L2 while k_fit_stream re-reads it ~12 times).  Every thread keeps 4
+// independent 16-byte loads in flight and bypasses L1 (ld.global.cg), so the figure is L2 -> SM throughput only.
+__global__ void __launch_bounds__(256) k_l2_read(const uint4* __restrict__ buf, size_t n_vec, int passes,
+                                                 unsigned int* __restrict__ sink) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  unsigned int acc = 0;
+  for (int r = 0; r < passes; ++r) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n_vec; i += 4 * stride) {
+      const uint4 a = __ldcg(buf + i), b = __ldcg(buf + i + stride), c = __ldcg(buf + i + 2 * stride),
+                  d = __ldcg(buf + i + 3 * stride);
+      acc += a.x ^ b.y ^ c.z ^ d.w;
+    }
+    for (; i < n_vec; i += stride) acc += __ldcg(buf + i).x;
+  }
+  if (acc == 0x12345678u) sink[0] = acc;  // (practically) never true: keeps the loads alive
+}
+
 // scalar math twins for tests
 __global__ void k_dev_math(int which, const double* __restrict__ x, const double* __restrict__ a,
                            const double* __restrict__ b, int64_t n, double* __restrict__ out) {

@@ -21,7 +21,7 @@ _LIB: C.CDLL | None = None
 # every symbol include/mdeggs.h declares (tests check the library exports all of them)
 ABI_SYMBOLS = (
     "mdeggs_create", "mdeggs_create_rank", "mdeggs_nccl_unique_id", "mdeggs_destroy", "mdeggs_run_omic",
-    "mdeggs_pair_features", "mdeggs_measure_fp64_peak", "mdeggs_last_stats", "mdeggs_set_option", "mdeggs_last_error", "mdeggs_strerror", "mdeggs_abi_version",
+    "mdeggs_pair_features", "mdeggs_measure_fp64_peak", "mdeggs_measure_l2_peak", "mdeggs_last_stats", "mdeggs_set_option", "mdeggs_last_error", "mdeggs_strerror", "mdeggs_abi_version",
     "mdeggs_dev_pt", "mdeggs_dev_pf_upper", "mdeggs_dev_p_two_sided_ref",
     "mdeggs_submit_omic", "mdeggs_wait", "mdeggs_run_omics",
 )
@@ -64,6 +64,7 @@ def load_library() -> C.CDLL:
     L.mdeggs_last_stats.argtypes = [vp, C.POINTER(_abi.CStats)]
     L.mdeggs_set_option.argtypes = [vp, C.c_char_p, i64]
     L.mdeggs_measure_fp64_peak.argtypes = [vp, C.POINTER(C.c_double)]
+    L.mdeggs_measure_l2_peak.argtypes = [vp, i64, C.POINTER(C.c_double)]
     L.mdeggs_last_error.argtypes = [vp]
     L.mdeggs_last_error.restype = C.c_char_p
     L.mdeggs_strerror.argtypes = [i]
@@ -163,6 +164,12 @@ class Engine:
         """Measured FP64 FMA peak of the GPU (DFMA-chain microbenchmark)."""
         v = C.c_double()
         self._check(self._lib.mdeggs_measure_fp64_peak(self._ctx, C.byref(v)), "mdeggs_measure_fp64_peak")
+        return v.value
+
+    def l2_peak_gbs(self, nbytes: int = 64 << 20) -> float:
+        """Measured L2 -> SM read bandwidth over an L2-resident buffer of `nbytes` (GB/s)."""
+        v = C.c_double()
+        self._check(self._lib.mdeggs_measure_l2_peak(self._ctx, int(nbytes), C.byref(v)), "mdeggs_measure_l2_peak")
         return v.value
 
     def stats(self) -> dict:
