@@ -28,6 +28,7 @@
 #include "mdeggs_kernels.cuh"
 #include "mdeggs_rlm.cuh"
 #include "mdeggs_qsel.cuh"
+#include "mdeggs_front.cuh"
 #include "nccl_dl.h"
 
 using namespace mdeggs;
@@ -71,11 +72,22 @@ struct Shard {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_sample = nullptr, ev_cf = nullptr;
   nccl_comm_t comm = nullptr;
   bool smem_attr_set = false, rsel_attr_set = false, dense_attr_set = false;  // cudaFuncSetAttribute is per device
+  unsigned front_attr_mask = 0;  // ... per instantiation of k_front_fused
+  int front_bits = 0;            // this call's front path (see stats.fit_path)
+  int sm_count = 0;
+  // tensor map of the device copy of the assay (k_front_fused), rebuilt when any of its ingredients changes
+  CUtensorMap tmap;
+  struct TmapKey {
+    const void* base;
+    int64_t ld, rows;
+    int n, gb, box1;
+  } tmap_key = {nullptr, 0, 0, 0, 0, 0};
   bool select_fused = false;  // this call's percentile selection ran inside k_bh_final
   bool partials_complete = true;  // the all-percentile K8 left the tile carries behind (false: count-only pass)
   bool best_rows_in_emit = false;  // this call's best-percentile rows are produced by k_emit (device callers)
   const double* best_row_src = nullptr;  // ... its p.adj row comes from row best-1 of this P x E matrix
   int64_t row_off = 0, ld_eff = 0;  // the device copy of the assay starts at host row `row_off`
+  int64_t rows_avail = 0;           // ... and holds this many rows
   std::vector<char> stage_shadow;   // host copy of what stage_dev currently holds
   const void* stage_shadow_dev = nullptr;
   void* h_stage = nullptr;          // pinned host staging for the tiny per-call inputs (src_of_pos, pct, df)
@@ -133,6 +145,7 @@ struct mdeggs_ctx {
   int graph_fit_path = 0;    // stats.fit_path of the captured call (run_shard_main does not run on replay)
   int64_t rsel_cap_override = 0;  // option "rsel_cap": shrink the candidate list to exercise the overflow path (tests)
   int fit_path_override = -1;  // -1 auto, 0 force streaming, 1 force dense (MDEGGS_FIT_PATH, tests)
+  int front_path = -1;         // -1 auto, 0 separate K1 + K2 kernels, 1 fused (TMA when possible), 2 fused with the plain loader
   bool last_zc = false;        // the last call read its assay through zero copy
   int zero_copy = 0;           // option "zero_copy": pinned host assays are read by the gather straight over PCIe
   int64_t padj_keep_cap = (int64_t)256 << 20;  // option "padj_keep_cap": largest P x E x 8 scratch kept for the best row
@@ -241,6 +254,7 @@ int init_shard(mdeggs_ctx* ctx, Shard& s) {
   CU(cudaEventCreateWithFlags(&s.ev_sample, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&s.ev_cf, cudaEventDisableTiming));
   CU(s.scal.ensure(SC_COUNT * 8));
+  CU(cudaDeviceGetAttribute(&s.sm_count, cudaDevAttrMultiProcessorCount, s.device));
   return MDEGGS_OK;
 }
 
@@ -511,6 +525,7 @@ int stage_inputs(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const Host
     // node rows are touched, the transfer overlaps the transposition and no staging copy exists
     s.row_off = 0;
     s.ld_eff = in->ld;
+    s.rows_avail = G;
     CU(s.from.ensure((size_t)E * 4 + 4));
     CU(s.to.ensure((size_t)E * 4 + 4));
     if (E > 0) {
@@ -540,22 +555,23 @@ int stage_inputs(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const Host
         hi = h > hi ? h : hi;
       }
       if (lo >= 1 && hi <= G) {  // out-of-range indices are reported by the device check below
-        r_lo = lo - 1;
+        r_lo = (lo - 1) & ~(int64_t)15;  // the fused front kernel walks 16-row blocks of absolute rows
         r_hi = hi - 1;
       }
     }
     const int64_t band = r_hi - r_lo + 1;
     s.row_off = r_lo;
+    s.rows_avail = band;
     CU(s.from.ensure((size_t)E * 4 + 4));
     CU(s.to.ensure((size_t)E * 4 + 4));
     size_t copied;
     if (in->layout == MDEGGS_LAYOUT_COLMAJOR) {
-      CU(s.assay.ensure((size_t)band * (size_t)n * 8));
-      s.ld_eff = band;
-      if (band == G && in->ld == G) {
+      s.ld_eff = (band + 1) & ~(int64_t)1;  // even: a TMA tensor map needs 16-byte strides
+      CU(s.assay.ensure((size_t)s.ld_eff * (size_t)n * 8));
+      if (band == G && in->ld == G && s.ld_eff == G) {
         CU(cudaMemcpyAsync(s.assay.p, in->assay, (size_t)G * n * 8, cudaMemcpyHostToDevice, s.s_main));
       } else {
-        CU(cudaMemcpy2DAsync(s.assay.p, (size_t)band * 8, in->assay + r_lo, (size_t)in->ld * 8, (size_t)band * 8,
+        CU(cudaMemcpy2DAsync(s.assay.p, (size_t)s.ld_eff * 8, in->assay + r_lo, (size_t)in->ld * 8, (size_t)band * 8,
                              (size_t)n, cudaMemcpyHostToDevice, s.s_main));
       }
       copied = (size_t)band * n * 8;
@@ -576,12 +592,14 @@ int stage_inputs(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const Host
   } else if (s.device == src_device) {
     s.row_off = 0;
     s.ld_eff = in->ld;
+    s.rows_avail = G;
     d_assay = in->assay;
     d_from = in->from;
     d_to = in->to;
   } else {
     s.row_off = 0;
     s.ld_eff = in->ld;
+    s.rows_avail = G;
     CU(s.assay.ensure(assay_elems * 8));
     CU(s.from.ensure((size_t)E * 4 + 4));
     CU(s.to.ensure((size_t)E * 4 + 4));
@@ -692,6 +710,123 @@ int run_shard_front(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, int32_t
   return MDEGGS_OK;
 }
 
+// ---- K1 + K2 fused (mdeggs_front.cuh) --------------------------------------------------------------
+typedef CUresult (*tmap_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+tmap_encode_fn tmap_encoder() {  // the driver entry point is resolved through the runtime: no link against libcuda
+  static tmap_encode_fn fn = []() -> tmap_encode_fn {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    return reinterpret_cast<tmap_encode_fn>(p);
+  }();
+  return fn;
+}
+
+template <int GB, int ITEMS, int NW>
+int launch_front_inst(mdeggs_ctx* ctx, Shard& s, const FrontArgs& A, const FrontPlan& P, unsigned grid, int inst) {
+  if (!(s.front_attr_mask & (1u << inst))) {
+    CU(cudaFuncSetAttribute(k_front_fused<GB, ITEMS, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, FR_SMEM_MAX - 2048));
+    s.front_attr_mask |= 1u << inst;
+  }
+  LAUNCH((k_front_fused<GB, ITEMS, NW>), grid, (NW + FR_PROD_WARPS) * 32, P.smem, s.s_main, s.tmap, A);
+  return MDEGGS_OK;
+}
+
+// returns MDEGGS_OK and *done = true when the fused kernel was launched; *done = false: use the separate K1 + K2
+int launch_front(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const SegLayout& L, int32_t n_nodes, bool do_q,
+                 unsigned int cand_cap, bool* done) {
+  *done = false;
+  if (ctx->front_path == 0 || ctx->last_zc || n_nodes <= 0) return MDEGGS_OK;
+  int max_cnt = 0;
+  for (int k = 0; k < L.K; ++k) max_cnt = L.cnt[k] > max_cnt ? L.cnt[k] : max_cnt;
+  const FrontPlan P = front_plan(L.n, L.K, max_cnt, 256);
+  if (!P.ok) return MDEGGS_OK;
+  const bool colmajor = in->layout == MDEGGS_LAYOUT_COLMAJOR;
+  bool use_tma = ctx->front_path != 2 && colmajor && (s.ld_eff % 2 == 0) && ((uintptr_t)s.assay.p % 16 == 0) &&
+                 tmap_encoder() != nullptr;
+  if (use_tma) {
+    Shard::TmapKey key = {s.assay.p, s.ld_eff, s.rows_avail, L.n, P.GB, P.box1};
+    if (memcmp(&key, &s.tmap_key, sizeof key) != 0) {
+      const cuuint64_t gdim[2] = {(cuuint64_t)s.rows_avail, (cuuint64_t)L.n};
+      const cuuint64_t gstr[1] = {(cuuint64_t)s.ld_eff * 8};
+      const cuuint32_t box[2] = {(cuuint32_t)P.GB, (cuuint32_t)P.box1};
+      const cuuint32_t estr[2] = {1, 1};
+      const CUtensorMapSwizzle sw = P.GB == 16 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                               : (P.GB == 8 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+      const CUresult r = tmap_encoder()(&s.tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, s.assay.p, gdim, gstr, box, estr,
+                                        CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) {
+        use_tma = false;  // (shape outside what a tensor map can describe: the plain loader serves it)
+        memset(&s.tmap_key, 0, sizeof s.tmap_key);
+      } else {
+        s.tmap_key = key;
+      }
+    }
+  }
+  FrontArgs A;
+  memset(&A, 0, sizeof A);
+  A.assay = s.assay.as<double>();
+  A.ld = s.ld_eff;
+  A.row_off = s.row_off;
+  A.rows_avail = s.rows_avail;
+  A.colmajor = colmajor ? 1 : 0;
+  A.use_tma = use_tma ? 1 : 0;
+  A.bitmap = reinterpret_cast<const unsigned int*>(s.scal.as<char>() + SC_COUNT * 8);
+  A.word_base = s.excl.as<int32_t>();
+  A.src_of_pos = s.src_of_pos.as<int32_t>();
+  A.L = L;
+  A.D = s.D.as<double>();
+  A.B16 = do_q ? s.B16.as<unsigned short>() : nullptr;
+  A.mean = s.mean.as<double>();
+  A.sxx = s.sxx.as<double>();
+  A.med = s.med.as<double>();
+  A.bad = s.bad.as<uint8_t>();
+  A.st = do_q ? s.rsel_state.as<QsState>() : nullptr;
+  A.hist = do_q ? s.rsel_hist.as<unsigned int>() : nullptr;
+  A.pct = s.pct.as<double>();
+  A.P = in->P;
+  A.cand_capacity = cand_cap;
+  A.tile_lo = (int)(s.row_off / P.GB);  // (row_off is a multiple of 16)
+  A.tile_hi = (int)((s.row_off + s.rows_avail + P.GB - 1) / P.GB);
+  const int64_t g_tiles = ((int64_t)in->G + P.GB - 1) / P.GB;
+  if (A.tile_hi > g_tiles) A.tile_hi = (int)g_tiles;
+  A.nbox = P.nbox;
+  A.box1 = P.box1;
+  A.stages = P.stages;
+  A.stage_bytes = P.stage_bytes;
+  const int n_tiles = A.tile_hi - A.tile_lo;
+  if (n_tiles <= 0) return MDEGGS_OK;
+  const unsigned grid = (unsigned)(n_tiles < s.sm_count ? n_tiles : s.sm_count);
+  CU(cudaMemsetAsync(s.bad.p, 0, (size_t)n_nodes, s.s_main));
+  int rc = MDEGGS_OK;
+#define MDEGGS_FR(GB_, IT_, NW_, ID_) rc = launch_front_inst<GB_, IT_, NW_>(ctx, s, A, P, grid, ID_)
+#define MDEGGS_FR_GB(IT_, NW_, ID0_)                       \
+  do {                                                     \
+    if (P.GB == 16) MDEGGS_FR(16, IT_, NW_, ID0_);         \
+    else if (P.GB == 8) MDEGGS_FR(8, IT_, NW_, ID0_ + 1);  \
+    else MDEGGS_FR(4, IT_, NW_, ID0_ + 2);                 \
+  } while (0)
+  switch (P.items) {
+    case 4: MDEGGS_FR_GB(4, 24, 0); break;
+    case 12: MDEGGS_FR_GB(12, 24, 3); break;
+    case 20: MDEGGS_FR_GB(20, 16, 6); break;
+    default: MDEGGS_FR_GB(32, 16, 9); break;
+  }
+#undef MDEGGS_FR_GB
+#undef MDEGGS_FR
+  if (rc) return rc;
+  s.front_bits = use_tma ? 0x400 : 0x800;  // fit_path bit 10: fused front kernel fed by TMA, bit 11: by the plain loader
+  *done = true;
+  return MDEGGS_OK;
+}
+
 int run_shard_main(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const mdeggs_result* out, const HostLayout& H,
                    int32_t n_nodes) {
   const SegLayout& L = H.L;
@@ -716,7 +851,14 @@ int run_shard_main(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
   QsState* d_st = do_q ? s.rsel_state.as<QsState>() : nullptr;
   const unsigned int cand_cap = do_q ? qs_cand_capacity(ctx, in) : 0;
   if (do_q) CU(cudaStreamWaitEvent(s.s_main, s.ev_sample, 0));  // knots ready
-  if (n_nodes > 0) {
+  // K1 + K2 as one TMA-fed kernel whenever a tile of the matrix fits the staging ring (mdeggs_front.cuh)
+  bool fused = false;
+  s.front_bits = 0;
+  {
+    int rc = launch_front(ctx, s, in, L, n_nodes, do_q, cand_cap, &fused);
+    if (rc) return rc;
+  }
+  if (n_nodes > 0 && !fused) {
     unsigned int* d_hist = do_q ? s.rsel_hist.as<unsigned int>() : nullptr;
     const unsigned grid = 148 * 6;  // persistent CTAs (6 fit an SM's shared memory): one histogram flush each
     if (in->layout == MDEGGS_LAYOUT_COLMAJOR) {
@@ -761,7 +903,7 @@ int run_shard_main(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
     QC.slot_max = d_st->slot_max;
     QC.cand = s.rsel_cand.as<unsigned long long>();
   }
-  if (n_nodes > 0) {
+  if (n_nodes > 0 && !fused) {
     int max_cnt = 0;
     for (int k = 0; k < K; ++k) max_cnt = L.cnt[k] > max_cnt ? L.cnt[k] : max_cnt;
     if (max_cnt <= 32 * 32) {  // segments fit in registers: one warp per (gene, category)
@@ -788,6 +930,15 @@ int run_shard_main(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
       LAUNCH(k_gene_stats<128>, (unsigned)n_nodes, 128, use_smem ? smem : 0, s.s_main, s.D.as<double>(), L, d_nn,
              s.mean.as<double>(), s.sxx.as<double>(), s.med.as<double>(), s.bad.as<uint8_t>(), use_smem, QC);
     }
+  }
+  if (do_q && fused) {
+    // K3 S3 of the fused front: slot candidates from the bin ids (the separate K2 collects them itself).  On the MAIN
+    // stream, before the pair fits: beside them it takes SM slots from the fit kernel (measured: fits 61 -> 90 us) and
+    // lengthens the quantile chain that K7 waits for.
+    const int64_t nvec = ((int64_t)n_nodes * L.npad + 7) / 8;
+    const int64_t nb = (nvec + 1023) / 1024;  // 4 vectors per thread and round
+    LAUNCH(k_qs_compact, (unsigned)(nb < s.sm_count * 4 ? nb : s.sm_count * 4), 256, 0, s.s_main, s.D.as<double>(),
+           s.B16.as<unsigned short>(), L.npad, d_nn, QC);
   }
   EVREC(s.ev[EV_STATS], s.s_main);
   // S4 (one small CTA per slot) runs on the side stream next to the pair fits; K7 joins it
@@ -839,7 +990,7 @@ int run_shard_main(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
     }
     if (use_dense) CU(s.dense_S.ensure(need));
   }
-  ctx->stats.fit_path = is_rlm ? 2 : (use_dense ? 1 : 0);
+  ctx->stats.fit_path = (is_rlm ? 2 : (use_dense ? 1 : 0)) | s.front_bits;
   if (e_hi > e_lo) {
     if (is_rlm) {
       int rc = launch_fit_rlm(ctx->launches, s.s_main, s.D.as<double>(), L, s.ea.as<int32_t>(), s.eb.as<int32_t>(),
@@ -1359,6 +1510,7 @@ int mdeggs_create(mdeggs_ctx** out, const int* device_ids, int n_dev) {
   if (const char* g = getenv("MDEGGS_GRAPH")) ctx->use_graph = atoi(g);
   if (const char* g = getenv("MDEGGS_DEBUG_SYNC")) ctx->debug_sync = atoi(g);
   if (const char* g = getenv("MDEGGS_TRACE")) ctx->trace = atoi(g);
+  if (const char* g = getenv("MDEGGS_FRONT_PATH")) ctx->front_path = atoi(g);
   ctx->shards.resize((size_t)n_dev);
   for (int i = 0; i < n_dev; ++i) {
     ctx->shards[(size_t)i].device = device_ids[i];
@@ -1407,6 +1559,7 @@ int mdeggs_create_rank(mdeggs_ctx** out, int device_id, int rank, int world, con
   if (const char* g = getenv("MDEGGS_GRAPH")) ctx->use_graph = atoi(g);
   if (const char* g = getenv("MDEGGS_DEBUG_SYNC")) ctx->debug_sync = atoi(g);
   if (const char* g = getenv("MDEGGS_TRACE")) ctx->trace = atoi(g);
+  if (const char* g = getenv("MDEGGS_FRONT_PATH")) ctx->front_path = atoi(g);
   ctx->shards.resize(1);
   Shard& s = ctx->shards[0];
   s.device = device_id;
@@ -1777,6 +1930,11 @@ int mdeggs_set_option(mdeggs_ctx* ctx, const char* name, int64_t value) {
   }
   if (!strcmp(name, "sort_path")) {
     ctx->sort_path_override = (int)value;
+    ctx->key_valid = false;
+    return MDEGGS_OK;
+  }
+  if (!strcmp(name, "front_path")) {
+    ctx->front_path = (int)value;
     ctx->key_valid = false;
     return MDEGGS_OK;
   }

@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(QS_SAMPLE_THREADS) k_qs_sample(const double* _
   }
 }
 
-__device__ __forceinline__ void qs_flush_and_scan(const unsigned int* __restrict__ s_hist, unsigned int* __restrict__ hist,
+__device__ __forceinline__ void qs_flush_and_scan(unsigned int* __restrict__ s_hist, unsigned int* __restrict__ hist,
                                                   QsState* __restrict__ st, const double* __restrict__ pct, int P,
                                                   unsigned int cand_capacity);
 
@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(256, 6) k_gather_colmajor(const double* __rest
   __shared__ double tile[32][33];
   __shared__ unsigned short tile16[32][34];
   __shared__ QsKnots kn;
-  __shared__ unsigned int s_hist[QS_BINS];
+  __shared__ __align__(16) unsigned int s_hist[QS_BINS];
   const bool do_hist = hist != nullptr;
   if (do_hist) {
     qs_load_knots(&kn, st);
@@ -325,7 +325,7 @@ __global__ void __launch_bounds__(256, 6) k_gather_rowmajor(const double* __rest
                                                          const double* __restrict__ pct, int P,
                                                          unsigned int cand_capacity) {
   __shared__ QsKnots kn;
-  __shared__ unsigned int s_hist[QS_BINS];
+  __shared__ __align__(16) unsigned int s_hist[QS_BINS];
   const bool do_hist = hist != nullptr;
   if (do_hist) {
     qs_load_knots(&kn, st);
@@ -357,20 +357,34 @@ __global__ void __launch_bounds__(256, 6) k_gather_rowmajor(const double* __rest
 // Run by the LAST CTA of the gather kernel (256 threads) once every CTA has flushed its histogram: prefix sums, each
 // target rank -> (bin, rank inside the bin), distinct target bins -> slots with exact counts and list offsets.  The
 // bins' prefix lives in registers (16 bins per thread); a thread answers the targets that fall into its own range.
+struct QsScanSmem {  // scratch of qs_scan_body; lives in the CTA's (flushed) shared-memory histogram
+  unsigned long long warp[QS_SCAN_THREADS / 32];
+  unsigned long long rank[QS_MAX_T];
+  int tbin[QS_MAX_T], first[QS_MAX_T];
+  unsigned int tcnt[QS_MAX_T], slot_cnt[QS_MAX_T];
+};
+static_assert(sizeof(QsScanSmem) <= (size_t)QS_BINS * 4, "the scan scratch aliases the histogram");
+
+// Called by every thread of the CTA (blockDim.x >= QS_SCAN_THREADS, a multiple of 32); the first QS_SCAN_THREADS work.
 __device__ __forceinline__ void qs_scan_body(QsState* __restrict__ st, unsigned int* __restrict__ hist,
-                                             const double* __restrict__ pct, int P, unsigned int cand_capacity) {
-  __shared__ unsigned long long s_warp[QS_SCAN_THREADS / 32];
-  __shared__ unsigned long long s_rank[QS_MAX_T];
-  __shared__ int s_tbin[QS_MAX_T], s_first[QS_MAX_T];
-  __shared__ unsigned int s_tcnt[QS_MAX_T], s_slot_cnt[QS_MAX_T];
+                                             const double* __restrict__ pct, int P, unsigned int cand_capacity,
+                                             QsScanSmem* __restrict__ sm) {
+  unsigned long long* s_warp = sm->warp;
+  unsigned long long* s_rank = sm->rank;
+  int *s_tbin = sm->tbin, *s_first = sm->first;
+  unsigned int *s_tcnt = sm->tcnt, *s_slot_cnt = sm->slot_cnt;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const bool act = tid < QS_SCAN_THREADS;
   constexpr int PER = QS_BINS / QS_SCAN_THREADS;
   unsigned long long v[PER], mine = 0;
 #pragma unroll
   for (int j = 0; j < PER; ++j) {
-    v[j] = __ldcg(hist + tid * PER + j);
-    mine += v[j];
-    hist[tid * PER + j] = 0u;  // clean slate for the next call
+    v[j] = 0ull;
+    if (act) {
+      v[j] = __ldcg(hist + tid * PER + j);
+      mine += v[j];
+      hist[tid * PER + j] = 0u;  // clean slate for the next call
+    }
   }
   unsigned long long incl = mine;
 #pragma unroll
@@ -378,7 +392,7 @@ __device__ __forceinline__ void qs_scan_body(QsState* __restrict__ st, unsigned 
     unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
     if (lane >= o) incl += t;
   }
-  if (lane == 31) s_warp[wid] = incl;
+  if (act && lane == 31) s_warp[wid] = incl;
   __syncthreads();
   unsigned long long woff = 0, total = 0;
   for (int w = 0; w < QS_SCAN_THREADS / 32; ++w) {
@@ -464,7 +478,7 @@ __device__ __forceinline__ void qs_scan_body(QsState* __restrict__ st, unsigned 
 }
 
 // whole CTA, at the end of a gather kernel: flush this CTA's histogram; the last CTA to do so runs S2
-__device__ __forceinline__ void qs_flush_and_scan(const unsigned int* __restrict__ s_hist, unsigned int* __restrict__ hist,
+__device__ __forceinline__ void qs_flush_and_scan(unsigned int* __restrict__ s_hist, unsigned int* __restrict__ hist,
                                                   QsState* __restrict__ st, const double* __restrict__ pct, int P,
                                                   unsigned int cand_capacity) {
   __shared__ int s_last;
@@ -478,7 +492,7 @@ __device__ __forceinline__ void qs_flush_and_scan(const unsigned int* __restrict
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  qs_scan_body(st, hist, pct, P, cand_capacity);
+  qs_scan_body(st, hist, pct, P, cand_capacity, reinterpret_cast<QsScanSmem*>(s_hist));  // (histogram flushed: reuse)
 }
 
 // ---- S4 ------------------------------------------------------------------------------------------

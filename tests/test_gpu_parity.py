@@ -976,3 +976,38 @@ def test_device_hommel_edge_limit(engine):
         engine.run_omic(big)
     assert host._padj_code("hommel", _abi.HOMMEL_MAX_E + 1) == _abi.PADJ_HOST
     assert host._padj_code("hommel", 1000) == _abi.PADJ_HOMMEL
+
+
+@pytest.mark.parametrize("G,n,E,K,row_major,with_nan", [
+    (333, 90, 500, 2, False, False),      # odd leading dimension: the tensor map is refused, plain loader
+    (400, 90, 500, 3, False, True),       # even: TMA boxes; NaN-bearing rows
+    (400, 150, 700, 2, True, False),      # row-major: plain loader
+    (96, 1000, 300, 3, False, False),     # config-3 segment size (12 values per lane), 8-row tiles, 5 boxes
+    (64, 1500, 200, 2, False, False),     # 750 per category: 32 values per lane
+    (64, 2000, 200, 2, False, False),     # config-5 sample count: 4-row tiles
+    (5000, 24, 3000, 2, False, False),    # config-4 shape: many tiles of few samples, scattered node rows
+])
+def test_front_paths_agree(oracle, G, n, E, K, row_major, with_nan):
+    """K1 + K2 as one TMA-fed kernel (front_path 1), the same kernel fed by its plain cp.async loader (2) and the
+    separate gather + gene-statistics kernels (0): identical medians / cut-offs / selections, all equal to the oracle."""
+    prob = synth.random_problem(G, n, E, K, 4242 + G + n, row_major=row_major)
+    if with_nan:
+        prob.assay = prob.assay.copy(order="F")
+        prob.assay[int(prob.from_idx[0]) - 1, 3] = np.nan
+        prob.assay[int(prob.to_idx[5]) - 1, [0, 7]] = np.nan
+    ref = oracle.run_omic(prob, ALL_FIELDS)
+    eng = md.Engine([0])
+    eng.set_option("graph", 0)
+    outs = {}
+    for path in (0, 1, 2):
+        eng.set_option("front_path", path)
+        outs[path] = eng.run_omic(prob, ALL_FIELDS)
+        bits = int(eng.stats()["fit_path"])
+        assert bool(bits & 0xC00) == (path != 0), (path, hex(bits))
+        if path == 2:
+            assert bits & 0x800
+        assert_parity(outs[path], ref, prob, what=f"front_path {path}: ")
+    for k in ("median", "cutoff", "status", "cat", "best", "sig_count", "tot_edges"):
+        assert np.array_equal(outs[0][k], outs[1][k], equal_nan=True), k
+        assert np.array_equal(outs[1][k], outs[2][k], equal_nan=True), k
+    eng.close()
