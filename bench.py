@@ -29,7 +29,8 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-os.environ["NCCL_DEBUG"] = os.environ.get("MDEGGS_NCCL_DEBUG", "WARN")
+if "NCCL_DEBUG" not in os.environ:  # (a pre-set level, e.g. the driver's INFO, is kept)
+    os.environ["NCCL_DEBUG"] = "WARN"
 # The contract is ONE JSON line on stdout.  Native libraries (NCCL's version banner) write to file descriptor 1
 # behind Python's back, so fd 1 is pointed at stderr for the whole run and the JSON line goes to the saved descriptor.
 _JSON_FD = os.dup(1)
@@ -52,6 +53,27 @@ def _peaks() -> dict:
             d = json.load(fh)
         return {"hbm_gbs": float(d["hbm_gbs"]), "source": "MEASURED_PEAKS.json (of measured)"}
     return {"hbm_gbs": 6650.0, "source": "B200_PROFILING.md fallback (of fallback)"}
+
+
+def _dram_traffic() -> dict:
+    """Per-kernel DRAM bytes per launch from the committed ncu --set full capture (profiles/dram_traffic.json, written by
+    tools/dram_traffic.py): read at run time so the number follows the profile, never a literal in this file."""
+    path = os.path.join(ROOT, "profiles", "dram_traffic.json")
+    try:
+        with open(path) as fh:
+            return json.load(fh)
+    except (OSError, ValueError):
+        return {}
+
+
+def _config(name: str, prob, st_nodes, world: int, extra: dict | None = None) -> dict:
+    """The workload description both arms print (identical keys)."""
+    G, n, E, K, P = prob.dims
+    cfg = {"workload": name, "genes": int(G), "samples": int(n), "edges": int(E), "categories": int(K),
+           "percentiles": int(P), "padj": "BH", "network_nodes": st_nodes, "parallelism": None, "l2": None,
+           "timing": None, "launch_mode": None, "host_cpus": None, "note": None}
+    cfg.update(extra or {})
+    return cfg
 
 
 class ClockSampler:

@@ -185,8 +185,16 @@ int mdeggs_measure_fp64_peak(mdeggs_ctx* ctx, double* tflops_out);
  * bytes per fit are served by L2, not by HBM (the matrix is read ~12 times per run and fits the 126 MB L2). */
 int mdeggs_measure_l2_peak(mdeggs_ctx* ctx, int64_t bytes, double* gbs_out);
 int mdeggs_last_stats(const mdeggs_ctx* ctx, mdeggs_stats* out);
+/* Per-launch timeline of the last call when option "trace" was 1 (printed to stderr as well), 2 or 3 (silent): entry i =
+ * kernel name, stream (0 main, 1 side) and the time its CUDA event fired, in microseconds after the call's first
+ * event.  bench.py derives the per-kernel durations of its roofline table from it (CUDA events on the launching
+ * stream; traced calls launch eagerly). */
+int mdeggs_trace_count(const mdeggs_ctx* ctx);
+int mdeggs_trace_get(const mdeggs_ctx* ctx, int i, char* name, int name_cap, int* stream_id, float* end_us);
 /* Engine options: "graph" (1 = replay the compute phase from a CUDA graph when a call repeats with identical
  * shapes and buffers [default], 0 = always launch eagerly, which also keeps the per-stage timings);
+ * "front_path" (-1 auto, 0 separate gather + gene-statistics kernels, 1 fused TMA-fed front kernel, 2 the same kernel fed by
+ * its plain loader); "bh_onepass" (1 = the multiple-testing adjustment of small edge lists in one launch [default]);
  * "fit_path" (-1 = choose streaming vs dense-tile pair fits automatically [default], 0 = streaming, 1 = dense);
  * "sort_path" (-1 = K8 orders the edges through p-value buckets up to 2^26 edges and with a CUB radix sort beyond
  * [default], 0 = always the radix sort, 1 = buckets whenever possible);

@@ -101,11 +101,11 @@ struct Shard {
     if (e == cudaSuccess) h_stage_cap = bytes + 256;
     return e;
   }
-  DevBuf assay, from, to, ea, eb, stage_dev, bs_count, bs_slot, seg_done, seg_rank, fin_q, hm_p, hm_q1, hm_c, hm_sc, hm_idx, hm_off, seg_pi0, B16, stamps, excl, node_of_row, rowlist, scal, src_of_pos, pct, cutoff, D, cub_tmp, mean, sxx, med, bad, stat, status, p_edge, coef, iters, act, counters, sortk, sortk2, idx,
+  DevBuf bh1_state, assay, from, to, ea, eb, stage_dev, bs_count, bs_slot, seg_done, seg_rank, fin_q, hm_p, hm_q1, hm_c, hm_sc, hm_idx, hm_off, seg_pi0, B16, stamps, excl, node_of_row, rowlist, scal, src_of_pos, pct, cutoff, D, cub_tmp, mean, sxx, med, bad, stat, status, p_edge, coef, iters, act, counters, sortk, sortk2, idx,
       idx2, ps, sa, sb, tile_cnt, tile_base, seg_n, tile_min, tile_carry, padj_best, cat_best, cat, padj, med_out,
       small_out, rsel_hist, rsel_state, rsel_cand, dense_S, cf_tab, sxy;
   void release_all() {
-    DevBuf* all[] = {&assay, &from, &to, &ea, &eb, &stage_dev, &bs_count, &bs_slot, &seg_done, &seg_rank, &fin_q, &hm_p, &hm_q1, &hm_c, &hm_sc, &hm_idx, &hm_off, &seg_pi0, &B16, &stamps, &excl, &node_of_row, &rowlist, &scal, &src_of_pos, &pct, &cutoff,
+    DevBuf* all[] = {&bh1_state, &assay, &from, &to, &ea, &eb, &stage_dev, &bs_count, &bs_slot, &seg_done, &seg_rank, &fin_q, &hm_p, &hm_q1, &hm_c, &hm_sc, &hm_idx, &hm_off, &seg_pi0, &B16, &stamps, &excl, &node_of_row, &rowlist, &scal, &src_of_pos, &pct, &cutoff,
                      &D, &cub_tmp, &mean, &sxx, &med, &bad, &stat, &status, &p_edge,
                      &coef, &iters, &act, &counters, &sortk, &sortk2, &idx, &idx2, &ps, &sa, &sb, &tile_cnt,
                      &tile_base, &seg_n, &tile_min, &tile_carry, &padj_best, &cat_best, &cat, &padj, &med_out,
@@ -145,6 +145,7 @@ struct mdeggs_ctx {
   int graph_fit_path = 0;    // stats.fit_path of the captured call (run_shard_main does not run on replay)
   int64_t rsel_cap_override = 0;  // option "rsel_cap": shrink the candidate list to exercise the overflow path (tests)
   int fit_path_override = -1;  // -1 auto, 0 force streaming, 1 force dense (MDEGGS_FIT_PATH, tests)
+  int bh_onepass = 1;          // option "bh_onepass": 0 keeps the three-launch K8 for small edge lists too (tests)
   int front_path = -1;         // -1 auto, 0 separate K1 + K2 kernels, 1 fused (TMA when possible), 2 fused with the plain loader
   bool last_zc = false;        // the last call read its assay through zero copy
   int zero_copy = 0;           // option "zero_copy": pinned host assays are read by the gather straight over PCIe
@@ -450,6 +451,20 @@ int run_adjust(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, int n_segmen
       CU(s.seg_rank.ensure(need));
       CU(cudaMemsetAsync(s.seg_rank.p, 0, s.seg_rank.cap, s.s_main));
     }
+  }
+  const bool simple_mode = in->padj == MDEGGS_PADJ_BONFERRONI || in->padj == MDEGGS_PADJ_BH || in->padj == MDEGGS_PADJ_BY ||
+                           in->padj == MDEGGS_PADJ_HOLM || in->padj == MDEGGS_PADJ_HOCHBERG;
+  if (ctx->bh_onepass && simple_mode && !reuse_tiles && !best_dev && !count_only && sig_dev && padj_out &&
+      ntiles <= BH1_MAX_TILES && s.bh1_state.p) {  // (padj_out: no later pass wants this pass's tile partials)
+    // small edge lists: the whole adjustment in one launch (k_bh_onepass); segment sizes came from k_percolate
+    const int Pn = in->P > 0 ? in->P : 1;
+    const unsigned int* seg_cnt = reinterpret_cast<const unsigned int*>(s.counters.as<char>() + (size_t)Pn * 8 * 7 + 8);
+    const size_t words = (size_t)Pn * in->K * ntiles;
+    unsigned long long* st_ext = s.bh1_state.as<unsigned long long>();
+    unsigned int* st_cnt = reinterpret_cast<unsigned int*>(st_ext + words);
+    LAUNCH(k_bh_onepass, grid, BH_THREADS, 0, s.s_main, A, in->padj, seg_cnt, st_cnt, st_ext, sig_dev, padj_out,
+           padj_stride, sel ? *sel : SelArgs{});
+    return MDEGGS_OK;
   }
   if (!reuse_tiles)
     LAUNCH(k_bh_count, grid, BH_THREADS, 0, s.s_main, A, s.tile_cnt.as<int32_t>(), s.tile_base.as<long long>(),
@@ -1143,8 +1158,18 @@ int run_shard_back(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
   CU(cudaStreamWaitEvent(s.s_sort, s.ev_fork, 0));
   // counters: tot[P] fail[P] sig[P] sig_raw[P] (u64), then out: tot_out[P] sig_out[P] fail_out[P] (i64)
   // ... and one word: "CTAs done" counter of the k_bh_final + selection tail
-  CU(s.counters.ensure((size_t)Pn * 8 * 7 + 8));
-  CU(cudaMemsetAsync(s.counters.p, 0, (size_t)Pn * 8 * 7 + 8, s.s_sort));
+  // ... then seg_cnt[P][K] (u32): members of every (percentile, category) segment, for the one-launch K8
+  const size_t counters_bytes = (size_t)Pn * 8 * 7 + 8 + (size_t)Pn * K * 4;
+  CU(s.counters.ensure(counters_bytes));
+  CU(cudaMemsetAsync(s.counters.p, 0, counters_bytes, s.s_sort));
+  unsigned int* d_seg_cnt = reinterpret_cast<unsigned int*>(s.counters.as<char>() + (size_t)Pn * 8 * 7 + 8);
+  const int bh_ntiles = (int)((E + BH_TILE - 1) / BH_TILE);
+  const bool onepass_shape = ctx->bh_onepass && E > 0 && bh_ntiles <= BH1_MAX_TILES;
+  if (onepass_shape) {  // tile words of k_bh_onepass: 0 = not published yet
+    const size_t words = (size_t)Pn * K * bh_ntiles;
+    CU(s.bh1_state.ensure(words * 12));
+    CU(cudaMemsetAsync(s.bh1_state.p, 0, words * 12, s.s_sort));
+  }
   unsigned long long* c_tot = s.counters.as<unsigned long long>();
   unsigned long long* c_fail = c_tot + Pn;
   unsigned long long* c_sig = c_tot + 2 * Pn;
@@ -1177,9 +1202,10 @@ int run_shard_back(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
   }
   if (n_nodes > 0 && P > 0) {
     if (E > 0)  // (also writes NaN into the p.adj rows of the edges that are not tested at a percentile)
-      LAUNCH(k_percolate, blocks_for(E, 256), 256, (size_t)3 * P * sizeof(unsigned), s.s_sort, s.ea.as<int32_t>(),
-             s.eb.as<int32_t>(), s.status.as<int32_t>(), s.p_edge.as<double>(), s.act.as<uint8_t>(), act_stride, E, P,
-             c_tot, c_fail, c_raw, d_cat, d_padj, s.scal.as<int32_t>() + 2 * SC_ERR);
+      LAUNCH(k_percolate, blocks_for(E, 256), 256, (size_t)(3 * P + (onepass_shape ? P * K : 0)) * sizeof(unsigned),
+             s.s_sort, s.ea.as<int32_t>(), s.eb.as<int32_t>(), s.status.as<int32_t>(), s.p_edge.as<double>(),
+             s.act.as<uint8_t>(), act_stride, E, P, c_tot, c_fail, c_raw, d_cat, d_padj,
+             s.scal.as<int32_t>() + 2 * SC_ERR, K, onepass_shape ? d_seg_cnt : nullptr);
   }
   CU(cudaEventRecord(s.ev_join, s.s_sort));
   if (do_adjust) {
@@ -1853,7 +1879,7 @@ int mdeggs_wait(mdeggs_ctx* ctx) {
             us(t_host0, t_host1), us(t_host1, t_host2), us(t_host2, t_host3), us(t_host0, t_host3),
             (double)(st2[1] - st2[0]) * 1e-3, replayed ? "graph" : "eager");
   }
-  if (ctx->trace && !ctx->trace_recs.empty()) {  // timeline of this call: end time of every launch, per stream
+  if (ctx->trace && ctx->trace != 3 && !ctx->trace_recs.empty()) {  // timeline of this call: end time of every launch, per stream
     float prev[2] = {0.f, 0.f};
     fprintf(stderr, "[mdeggs trace] %-34s %-6s %10s %10s\n", "launch", "stream", "end_us", "delta_us");
     for (const auto& r : ctx->trace_recs) {
@@ -1933,6 +1959,11 @@ int mdeggs_set_option(mdeggs_ctx* ctx, const char* name, int64_t value) {
     ctx->key_valid = false;
     return MDEGGS_OK;
   }
+  if (!strcmp(name, "bh_onepass")) {
+    ctx->bh_onepass = (int)value;
+    ctx->key_valid = false;
+    return MDEGGS_OK;
+  }
   if (!strcmp(name, "front_path")) {
     ctx->front_path = (int)value;
     ctx->key_valid = false;
@@ -1944,6 +1975,19 @@ int mdeggs_set_option(mdeggs_ctx* ctx, const char* name, int64_t value) {
     return MDEGGS_OK;
   }
   return MDEGGS_EINVAL;
+}
+
+int mdeggs_trace_count(const mdeggs_ctx* ctx) { return ctx ? (int)ctx->trace_recs.size() : 0; }
+
+int mdeggs_trace_get(const mdeggs_ctx* ctx, int i, char* name, int name_cap, int* stream_id, float* end_us) {
+  if (!ctx || i < 0 || (size_t)i >= ctx->trace_recs.size() || !name || name_cap < 1 || !stream_id || !end_us)
+    return MDEGGS_EINVAL;
+  const auto& r = ctx->trace_recs[(size_t)i];
+  const Shard& s0 = ctx->shards[0];
+  snprintf(name, (size_t)name_cap, "%s", r.name);
+  *stream_id = r.stream == s0.s_sort ? 1 : 0;
+  *end_us = ev_ms(s0.ev[EV_START], r.ev) * 1e3f;
+  return MDEGGS_OK;
 }
 
 int mdeggs_last_stats(const mdeggs_ctx* ctx, mdeggs_stats* out) {

@@ -441,7 +441,7 @@ __global__ void __launch_bounds__((NW + FR_PROD_WARPS) * 32, 1)
 // a slot are looked up in D (just written, L2-resident) and staged in shared memory; a CTA reserves room in a slot's
 // list with ONE global atomic per slot and flush (50,000 same-address atomics would serialise for tens of
 // microseconds), then copies its keys.  Fat slots (tie groups, never copied) only track their key range.
-constexpr int QSC_STAGE = 4096;  // staged keys per CTA between flushes
+constexpr int QSC_STAGE = 2048;  // staged keys per CTA (a CTA sees ~100 hits on continuous data)
 __global__ void __launch_bounds__(256) k_qs_compact(const double* __restrict__ D,
                                                     const unsigned short* __restrict__ B16, int npad,
                                                     const int32_t* __restrict__ n_nodes_p, QsCompactArgs Q) {
@@ -449,77 +449,69 @@ __global__ void __launch_bounds__(256) k_qs_compact(const double* __restrict__ D
   __shared__ unsigned long long st_key[QSC_STAGE];
   __shared__ unsigned char st_slot[QSC_STAGE];
   __shared__ unsigned int s_n, s_cnt[QS_MAX_T], s_base[QS_MAX_T];
-  qsc_load_table(Q, s_tab);
+  const long long total = (long long)(*n_nodes_p) * npad;
   const int U = *Q.U;
   if (threadIdx.x == 0) s_n = 0u;
   for (int i = threadIdx.x; i < QS_MAX_T; i += blockDim.x) s_cnt[i] = 0u;
-  __syncthreads();
-  const long long total = (long long)(*n_nodes_p) * npad;
+  qsc_load_table(Q, s_tab);  // (ends with a CTA barrier)
   const long long nvec = (total + 7) >> 3;
   const uint4* __restrict__ bv = reinterpret_cast<const uint4*>(B16);
-  auto flush = [&]() {  // whole CTA
-    __syncthreads();
-    const unsigned n = s_n < (unsigned)QSC_STAGE ? s_n : (unsigned)QSC_STAGE;
-    for (unsigned i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&s_cnt[st_slot[i]], 1u);
-    __syncthreads();
-    for (int sl = threadIdx.x; sl < U; sl += blockDim.x) {
-      const unsigned c = s_cnt[sl];
-      s_base[sl] = c ? atomicAdd(Q.slot_cursor + sl, c) : 0u;
-      s_cnt[sl] = 0u;  // reused as the running offset inside the reservation, and zero again for the next flush
-    }
-    __syncthreads();
-    for (unsigned i = threadIdx.x; i < n; i += blockDim.x) {
-      const unsigned sl = st_slot[i];
-      const unsigned pos = s_base[sl] + atomicAdd(&s_cnt[sl], 1u);
-      if (pos < Q.slot_count[sl]) Q.cand[Q.slot_off[sl] + pos] = st_key[i];
-    }
-    __syncthreads();
-    for (int sl = threadIdx.x; sl < U; sl += blockDim.x) s_cnt[sl] = 0u;
-    if (threadIdx.x == 0) s_n = 0u;
-    __syncthreads();
-  };
-  constexpr int VPT = 4;  // 16-byte loads in flight per thread and round
-  const long long step = (long long)gridDim.x * blockDim.x * VPT;
-  for (long long i0 = (long long)blockIdx.x * blockDim.x * VPT; i0 < nvec; i0 += step) {  // uniform trip count per CTA
-    uint4 w[VPT];
+  auto visit = [&](const uint4& w, long long i) {
+    const unsigned ws[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
-    for (int r = 0; r < VPT; ++r) {
-      const long long i = i0 + r * (long long)blockDim.x + threadIdx.x;
-      w[r] = i < nvec ? __ldg(bv + i) : make_uint4(~0u, ~0u, ~0u, ~0u);
-    }
-#pragma unroll
-    for (int r = 0; r < VPT; ++r) {
-      const long long i = i0 + r * (long long)blockDim.x + threadIdx.x;
-      const unsigned ws[4] = {w[r].x, w[r].y, w[r].z, w[r].w};
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const unsigned b = (ws[q >> 1] >> (16 * (q & 1))) & 0xffffu;
-        const long long idx = i * 8 + q;
-        if (b < (unsigned)QSC_BINS && idx < total) {
-          const unsigned sl = s_tab[b];
-          if (sl != 0xff) {
-            const unsigned long long key = dkey(D[idx]);
-            if (Q.slot_fat[sl]) {
-              if (key < __ldcg(Q.slot_min + sl)) atomicMin(Q.slot_min + sl, key);
-              if (key > __ldcg(Q.slot_max + sl)) atomicMax(Q.slot_max + sl, key);
-            } else {
-              const unsigned at = atomicAdd(&s_n, 1u);
-              if (at < (unsigned)QSC_STAGE) {
-                st_key[at] = key;
-                st_slot[at] = (unsigned char)sl;
-              } else {  // staging full inside one round (a slot bin that holds a large share of the data): direct append
-                const unsigned pos = atomicAdd(Q.slot_cursor + sl, 1u);
-                if (pos < Q.slot_count[sl]) Q.cand[Q.slot_off[sl] + pos] = key;
-              }
+    for (int q = 0; q < 8; ++q) {
+      const unsigned b = (ws[q >> 1] >> (16 * (q & 1))) & 0xffffu;
+      const long long idx = i * 8 + q;
+      if (b < (unsigned)QSC_BINS && idx < total) {
+        const unsigned sl = s_tab[b];
+        if (sl != 0xff) {
+          const unsigned long long key = dkey(D[idx]);
+          if (Q.slot_fat[sl]) {
+            if (key < __ldcg(Q.slot_min + sl)) atomicMin(Q.slot_min + sl, key);
+            if (key > __ldcg(Q.slot_max + sl)) atomicMax(Q.slot_max + sl, key);
+          } else {
+            const unsigned at = atomicAdd(&s_n, 1u);
+            if (at < (unsigned)QSC_STAGE) {
+              st_key[at] = key;
+              st_slot[at] = (unsigned char)sl;
+            } else {  // staging full (a slot bin that holds a large share of the data): direct append
+              const unsigned pos = atomicAdd(Q.slot_cursor + sl, 1u);
+              if (pos < Q.slot_count[sl]) Q.cand[Q.slot_off[sl] + pos] = key;
             }
           }
         }
       }
     }
-    __syncthreads();
-    if (s_n > (unsigned)(QSC_STAGE / 2)) flush();  // (uniform: s_n is read after the barrier)
+  };
+  constexpr int VPT = 4;  // 16-byte loads in flight per thread
+  const long long step = (long long)gridDim.x * blockDim.x * VPT;
+  for (long long i0 = (long long)blockIdx.x * blockDim.x * VPT + threadIdx.x; i0 < nvec; i0 += step) {
+    uint4 w[VPT];
+#pragma unroll
+    for (int r = 0; r < VPT; ++r) {
+      const long long i = i0 + r * (long long)blockDim.x;
+      w[r] = i < nvec ? __ldg(bv + i) : make_uint4(~0u, ~0u, ~0u, ~0u);
+    }
+#pragma unroll
+    for (int r = 0; r < VPT; ++r) visit(w[r], i0 + r * (long long)blockDim.x);
   }
-  flush();
+  // flush: ONE global atomic per slot and CTA reserves the room, then the staged keys are copied
+  __syncthreads();
+  const unsigned n = s_n < (unsigned)QSC_STAGE ? s_n : (unsigned)QSC_STAGE;
+  if (n == 0u) return;
+  for (unsigned i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&s_cnt[st_slot[i]], 1u);
+  __syncthreads();
+  for (int sl = threadIdx.x; sl < U; sl += blockDim.x) {
+    const unsigned c = s_cnt[sl];
+    s_base[sl] = c ? atomicAdd(Q.slot_cursor + sl, c) : 0u;
+    s_cnt[sl] = 0u;  // reused as the running offset inside the reservation
+  }
+  __syncthreads();
+  for (unsigned i = threadIdx.x; i < n; i += blockDim.x) {
+    const unsigned sl = st_slot[i];
+    const unsigned pos = s_base[sl] + atomicAdd(&s_cnt[sl], 1u);
+    if (pos < Q.slot_count[sl]) Q.cand[Q.slot_off[sl] + pos] = st_key[i];
+  }
 }
 
 // host side: shape of the staging ring for a run, or ok == false when the fused kernel does not apply

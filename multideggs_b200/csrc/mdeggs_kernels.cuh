@@ -706,10 +706,12 @@ __global__ void __launch_bounds__(256) k_percolate(const int32_t* __restrict__ e
                                                    unsigned long long* __restrict__ fail,
                                                    unsigned long long* __restrict__ sig_raw,
                                                    int8_t* __restrict__ cat_out, double* __restrict__ padj_nan,
-                                                   const int32_t* __restrict__ err) {
-  extern __shared__ unsigned int s_cnt[];  // [3][P]
+                                                   const int32_t* __restrict__ err, int K,
+                                                   unsigned int* __restrict__ seg_cnt) {
+  extern __shared__ unsigned int s_cnt[];  // [3][P], then [P][K] when seg_cnt
   if (*err) return;
-  for (int i = threadIdx.x; i < 3 * P; i += blockDim.x) s_cnt[i] = 0;
+  const int n_cnt = 3 * P + (seg_cnt ? P * K : 0);
+  for (int i = threadIdx.x; i < n_cnt; i += blockDim.x) s_cnt[i] = 0;
   __syncthreads();
   int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = e < E;
@@ -736,6 +738,13 @@ __global__ void __launch_bounds__(256) k_percolate(const int32_t* __restrict__ e
       if (m_f) atomicAdd(&s_cnt[P + p], __popc(m_f));
       if (m_s) atomicAdd(&s_cnt[2 * P + p], __popc(m_s));
     }
+    if (seg_cnt && m_t) {  // members of every (percentile, category) segment = n of p.adjust (non-NA p only)
+      const bool member = c != 0 && !isnan(pv);
+      for (int k = 1; k <= K; ++k) {
+        const unsigned m_k = __ballot_sync(0xffffffffu, member && c == k);
+        if (lane == 0 && m_k) atomicAdd(&s_cnt[3 * P + p * K + k - 1], __popc(m_k));
+      }
+    }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < P; i += blockDim.x) {
@@ -743,6 +752,9 @@ __global__ void __launch_bounds__(256) k_percolate(const int32_t* __restrict__ e
     if (s_cnt[P + i]) atomicAdd(&fail[i], (unsigned long long)s_cnt[P + i]);
     if (s_cnt[2 * P + i]) atomicAdd(&sig_raw[i], (unsigned long long)s_cnt[2 * P + i]);
   }
+  if (seg_cnt)
+    for (int i = threadIdx.x; i < P * K; i += blockDim.x)
+      if (s_cnt[3 * P + i]) atomicAdd(&seg_cnt[i], s_cnt[3 * P + i]);
 }
 
 // rows of the device-chosen best percentile: category row (recomputed from the masks) and, when the adjusted
@@ -1481,6 +1493,154 @@ __global__ void __launch_bounds__(BH_THREADS) k_bh_final(BhArgs A, int mode, con
                                                         unsigned long long* __restrict__ sig,
                                                         double* __restrict__ padj_out, int64_t padj_stride, SelArgs S) {
   bh_final_body(A, mode, tile_cnt, tile_base, seg_n, tile_carry, sig, padj_out, padj_stride);
+  if (!S.done) return;
+  __shared__ int s_last_cta;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int prev = atomicAdd(S.done, 1u);
+    s_last_cta = prev == gridDim.x * gridDim.y - 1;
+  }
+  __syncthreads();
+  if (!s_last_cta || threadIdx.x >= 32) return;
+  __threadfence();
+  select_best_warp(S);
+}
+
+// K8 in ONE launch for edge lists of up to BH1_MAX_TILES tiles (config 3: 26): count, rank, adjusted value, cumulative
+// min / max and the significant count of every (percentile, category) segment, with the percentile selection in the
+// CTA that finishes last.  The three-launch form above costs three dependent grid launches plus three "last CTA of the
+// segment" tails of pure latency.  Here the segment sizes n come from k_percolate, tiles are walked from the END of the
+// p order (from the start for holm), and a CTA only needs the aggregates of the tiles walked before it: it publishes
+// (members + 1) and later the sortable key of its extreme value in one word each (0 = not there yet), and one warp
+// reads all predecessors' words at once.  A CTA waits only for CTAs with a smaller blockIdx.x, which the hardware
+// dispatched earlier: no deadlock whatever the residency.
+constexpr int BH1_MAX_TILES = 64;
+__global__ void __launch_bounds__(BH_THREADS) k_bh_onepass(BhArgs A, int mode, const unsigned int* __restrict__ seg_cnt,
+                                                          unsigned int* __restrict__ st_cnt,
+                                                          unsigned long long* __restrict__ st_ext,
+                                                          unsigned long long* __restrict__ sig,
+                                                          double* __restrict__ padj_out, int64_t padj_stride,
+                                                          SelArgs S) {
+  typedef cub::BlockScan<int, BH_THREADS> ScanI;
+  typedef cub::BlockScan<double, BH_THREADS> ScanD;
+  typedef cub::BlockReduce<int, BH_THREADS> ReduceI;
+  typedef cub::BlockReduce<double, BH_THREADS> ReduceD;
+  __shared__ union {
+    typename ScanI::TempStorage si;
+    typename ScanD::TempStorage sd;
+    typename ReduceI::TempStorage ri;
+    typename ReduceD::TempStorage rd;
+  } tmp;
+  __shared__ double tagg_s[BH_THREADS];
+  __shared__ long long s_before;
+  __shared__ double s_carry;
+  __shared__ int s_tile_cnt;
+  const bool fwd = mode == MDEGGS_PADJ_HOLM;  // holm: cummax over ascending p; others: cummin from the largest p
+  const double ident = fwd ? -INFINITY : INFINITY;
+  const int w = blockIdx.x;                       // position in walking order
+  const int tile = fwd ? w : A.ntiles - 1 - w;    // tile in p order
+  const int p = A.p0 + ((int)blockIdx.y / A.K) * A.p_stride, c = (int)blockIdx.y % A.K + 1;
+  const size_t sbase = (size_t)blockIdx.y * A.ntiles;
+  const long long n_ll = (long long)seg_cnt[p * A.K + c - 1];
+  if (A.tot[p] != 0 && n_ll > 0) {
+    int flag[BH_ITEMS], rank[BH_ITEMS];
+    double pv[BH_ITEMS], q[BH_ITEMS];
+    const int64_t tile0 = (int64_t)tile * BH_TILE;
+    bh_load(A, p, c, tile0, flag, pv);
+    int tcnt;
+    ScanI(tmp.si).InclusiveSum(flag, rank, tcnt);
+    if (threadIdx.x == 0) {
+      s_tile_cnt = tcnt;
+      __stcg(st_cnt + sbase + w, (unsigned int)tcnt + 1u);
+      if (tcnt == 0) __stcg(st_ext + sbase + w, dkey(ident));  // nothing to wait for in this tile
+    }
+    __syncthreads();
+    if (s_tile_cnt != 0) {
+      const double n = (double)n_ll;
+      if (mode != MDEGGS_PADJ_BONFERRONI) {
+        // members of the tiles walked before this one
+        if (threadIdx.x < 32) {
+          long long acc = 0;
+          for (int j = threadIdx.x; j < w; j += 32) {
+            unsigned int v;
+            while ((v = __ldcg(st_cnt + sbase + j)) == 0u) __nanosleep(20);
+            acc += (long long)(v - 1u);
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+          if (threadIdx.x == 0) s_before = acc;
+        }
+        __syncthreads();
+        // ascending rank inside the segment
+        const long long base = fwd ? s_before : n_ll - s_before - (long long)s_tile_cnt;
+        double v[BH_ITEMS], run_it[BH_ITEMS];
+        const double num = adj_numerator(mode, n);
+#pragma unroll
+        for (int it = 0; it < BH_ITEMS; ++it) v[it] = flag[it] ? adj_value(mode, n, num, base + rank[it], pv[it]) : ident;
+        double run = ident;
+        if (fwd) {
+#pragma unroll
+          for (int it = 0; it < BH_ITEMS; ++it) {
+            run = fmax(run, v[it]);
+            run_it[it] = run;
+          }
+        } else {
+#pragma unroll
+          for (int it = BH_ITEMS - 1; it >= 0; --it) {
+            run = fmin(run, v[it]);
+            run_it[it] = run;
+          }
+        }
+        // this tile's extreme value -> published; exclusive scan of the thread aggregates in walking order
+        const int wpos = fwd ? threadIdx.x : BH_THREADS - 1 - threadIdx.x;
+        tagg_s[wpos] = run;
+        __syncthreads();
+        double mine = tagg_s[threadIdx.x], ex, agg;
+        if (fwd) ScanD(tmp.sd).ExclusiveScan(mine, ex, ident, MaxOp(), agg);
+        else ScanD(tmp.sd).ExclusiveScan(mine, ex, ident, MinOp(), agg);
+        if (threadIdx.x == 0) __stcg(st_ext + sbase + w, dkey(agg));
+        __syncthreads();
+        tagg_s[threadIdx.x] = ex;
+        __syncthreads();
+        const double others = tagg_s[wpos];
+        // extreme value of the tiles walked before this one
+        if (threadIdx.x < 32) {
+          double acc = ident;
+          for (int j = threadIdx.x; j < w; j += 32) {
+            unsigned long long k;
+            while ((k = __ldcg(st_ext + sbase + j)) == 0ull) __nanosleep(20);
+            const double x = dkey_inv(k);
+            acc = fwd ? fmax(acc, x) : fmin(acc, x);
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const double x = __shfl_xor_sync(0xffffffffu, acc, o);
+            acc = fwd ? fmax(acc, x) : fmin(acc, x);
+          }
+          if (threadIdx.x == 0) s_carry = acc;
+        }
+        __syncthreads();
+        const double carry = s_carry;
+#pragma unroll
+        for (int it = 0; it < BH_ITEMS; ++it)
+          q[it] = fwd ? fmin(1.0, fmax(run_it[it], fmax(others, carry))) : fmin(1.0, fmin(run_it[it], fmin(others, carry)));
+      } else {
+#pragma unroll
+        for (int it = 0; it < BH_ITEMS; ++it) q[it] = fmin(1.0, __dmul_rn(n, pv[it]));
+      }
+      int cnt = 0;
+#pragma unroll
+      for (int it = 0; it < BH_ITEMS; ++it) {
+        if (!flag[it]) continue;
+        cnt += (q[it] < 0.05);
+        if (padj_out) padj_out[(int64_t)p * padj_stride + A.sidx[tile0 + (int64_t)threadIdx.x * BH_ITEMS + it]] = q[it];
+      }
+      __syncthreads();
+      const int tot = ReduceI(tmp.ri).Sum(cnt);
+      if (threadIdx.x == 0 && tot) atomicAdd(&sig[p], (unsigned long long)tot);
+    }
+  }
   if (!S.done) return;
   __shared__ int s_last_cta;
   __syncthreads();

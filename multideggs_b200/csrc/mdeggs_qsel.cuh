@@ -616,11 +616,22 @@ __global__ void __launch_bounds__(QS_FIN_THREADS) k_qs_finish(const double* __re
   __shared__ int s_last;
   const int tid = threadIdx.x, s = blockIdx.x;
   const int T = 2 * P;
+  // everything this CTA needs from the selection state in ONE round of loads (a loop of dependent global reads per
+  // target cost more than the selection itself)
+  __shared__ int sh_tslot[QS_MAX_T];
+  __shared__ long long sh_trank[QS_MAX_T];
+  for (int t = tid; t < T; t += QS_FIN_THREADS) {
+    sh_tslot[t] = st->t_slot[t];
+    sh_trank[t] = st->t_rank[t];
+  }
   const int U = st->U;
+  const unsigned int c = s < U ? st->slot_count[s] : 0u;
+  const int fat = s < U ? st->slot_fat[s] : 0;
+  const unsigned int list_off = s < U ? st->slot_off[s] : 0u;
   if (s >= U) return;
-  const unsigned int c = st->slot_count[s];
-  if (!st->slot_fat[s]) {
-    const unsigned long long* list = cand + st->slot_off[s];
+  __syncthreads();
+  if (!fat) {
+    const unsigned long long* list = cand + list_off;
     if (tid == 0) {
       s_min = ~0ull;
       s_max = 0ull;
@@ -654,14 +665,14 @@ __global__ void __launch_bounds__(QS_FIN_THREADS) k_qs_finish(const double* __re
       }
     };
     for (int t = 0; t < T; ++t) {
-      if (st->t_slot[t] != s) continue;  // uniform across the CTA
-      const unsigned long long key = c > 0 ? qs_digit_select(for_each_cand, kmin, kmax, st->t_rank[t], hist, s_scan, &s_pfx, &s_rank, s_direct, s_list) : ~0ull;
+      if (sh_tslot[t] != s) continue;  // uniform across the CTA
+      const unsigned long long key = c > 0 ? qs_digit_select(for_each_cand, kmin, kmax, sh_trank[t], hist, s_scan, &s_pfx, &s_rank, s_direct, s_list) : ~0ull;
       if (tid == 0) st->t_key[t] = key;
     }
   } else if (st->slot_min[s] == st->slot_max[s]) {
     // a pure tie group: every rank inside it is the same key
     for (int t = tid; t < T; t += QS_FIN_THREADS)
-      if (st->t_slot[t] == s) st->t_key[t] = st->slot_min[s];
+      if (sh_tslot[t] == s) st->t_key[t] = st->slot_min[s];
   } else {
     // slow path: the same select straight over D, filtered by the bin ids
     const unsigned my_bin = (unsigned)st->slot_bin[s];
@@ -671,8 +682,8 @@ __global__ void __launch_bounds__(QS_FIN_THREADS) k_qs_finish(const double* __re
         if (B16[i] == my_bin) fn(dkey(D[i]));
     };
     for (int t = 0; t < T; ++t) {
-      if (st->t_slot[t] != s) continue;  // uniform across the CTA
-      const unsigned long long key = qs_digit_select(for_each_in_bin, st->slot_min[s], st->slot_max[s], st->t_rank[t], hist, s_scan, &s_pfx, &s_rank, s_direct, s_list);
+      if (sh_tslot[t] != s) continue;  // uniform across the CTA
+      const unsigned long long key = qs_digit_select(for_each_in_bin, st->slot_min[s], st->slot_max[s], sh_trank[t], hist, s_scan, &s_pfx, &s_rank, s_direct, s_list);
       if (tid == 0) st->t_key[t] = key;
     }
   }

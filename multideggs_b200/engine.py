@@ -21,7 +21,8 @@ _LIB: C.CDLL | None = None
 # every symbol include/mdeggs.h declares (tests check the library exports all of them)
 ABI_SYMBOLS = (
     "mdeggs_create", "mdeggs_create_rank", "mdeggs_nccl_unique_id", "mdeggs_destroy", "mdeggs_run_omic",
-    "mdeggs_pair_features", "mdeggs_measure_fp64_peak", "mdeggs_measure_l2_peak", "mdeggs_last_stats", "mdeggs_set_option", "mdeggs_last_error", "mdeggs_strerror", "mdeggs_abi_version",
+    "mdeggs_pair_features", "mdeggs_measure_fp64_peak", "mdeggs_measure_l2_peak", "mdeggs_last_stats",
+    "mdeggs_trace_count", "mdeggs_trace_get", "mdeggs_set_option", "mdeggs_last_error", "mdeggs_strerror", "mdeggs_abi_version",
     "mdeggs_dev_pt", "mdeggs_dev_pf_upper", "mdeggs_dev_p_two_sided_ref",
     "mdeggs_submit_omic", "mdeggs_wait", "mdeggs_run_omics",
 )
@@ -65,6 +66,8 @@ def load_library() -> C.CDLL:
     L.mdeggs_set_option.argtypes = [vp, C.c_char_p, i64]
     L.mdeggs_measure_fp64_peak.argtypes = [vp, C.POINTER(C.c_double)]
     L.mdeggs_measure_l2_peak.argtypes = [vp, i64, C.POINTER(C.c_double)]
+    L.mdeggs_trace_count.argtypes = [vp]
+    L.mdeggs_trace_get.argtypes = [vp, i, C.c_char_p, i, C.POINTER(C.c_int), C.POINTER(C.c_float)]
     L.mdeggs_last_error.argtypes = [vp]
     L.mdeggs_last_error.restype = C.c_char_p
     L.mdeggs_strerror.argtypes = [i]
@@ -171,6 +174,16 @@ class Engine:
         v = C.c_double()
         self._check(self._lib.mdeggs_measure_l2_peak(self._ctx, int(nbytes), C.byref(v)), "mdeggs_measure_l2_peak")
         return v.value
+
+    def trace(self) -> list[tuple[str, int, float]]:
+        """(kernel, stream, end_us) of every launch of the last call (option "trace" must be on)."""
+        out = []
+        buf = C.create_string_buffer(64)
+        sid, t = C.c_int(), C.c_float()
+        for k in range(self._lib.mdeggs_trace_count(self._ctx)):
+            self._check(self._lib.mdeggs_trace_get(self._ctx, k, buf, 64, C.byref(sid), C.byref(t)), "mdeggs_trace_get")
+            out.append((buf.value.decode(), sid.value, t.value))
+        return out
 
     def stats(self) -> dict:
         st = _abi.CStats()

@@ -1011,3 +1011,22 @@ def test_front_paths_agree(oracle, G, n, E, K, row_major, with_nan):
         assert np.array_equal(outs[0][k], outs[1][k], equal_nan=True), k
         assert np.array_equal(outs[1][k], outs[2][k], equal_nan=True), k
     eng.close()
+
+
+@pytest.mark.parametrize("padj", [_abi.PADJ_BH, _abi.PADJ_BONFERRONI, _abi.PADJ_HOLM, _abi.PADJ_HOCHBERG, _abi.PADJ_BY])
+@pytest.mark.parametrize("K,E,seed", [(2, 3000, 1601), (3, 9000, 1602), (2, 40, 1603), (3, 100_000, 1604)])
+def test_onepass_adjustment_equals_three_pass(padj, K, E, seed):
+    """K8 in one launch (k_bh_onepass: tile aggregates read back through published words, up to 64 tiles) against the
+    three-launch form: bit-identical adjusted values, counts and selection."""
+    G = 120 if E < 10_000 else 700
+    prob = synth.random_problem(G, 48, E, K, seed, _abi.METHOD_LM, padj)
+    want = ("padj", "padj_best", "cat_best", "sig_count", "tot_edges", "best")
+    eng = md.Engine([0])
+    eng.set_option("graph", 0)
+    res = {}
+    for mode in (1, 0):
+        eng.set_option("bh_onepass", mode)
+        res[mode] = eng.run_omic(prob, want)
+    for k in want:
+        assert np.array_equal(res[0][k], res[1][k], equal_nan=True), k
+    eng.close()
