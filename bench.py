@@ -187,6 +187,9 @@ def run_reference(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1: the reference arm uses every host core this process may run on
+    host_cpus = len(os.sched_getaffinity(0))
+    os.environ["OMP_NUM_THREADS"] = str(host_cpus)
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import pyoracle
     name = args.workload or "cfg3"
@@ -199,21 +202,25 @@ def run_reference(args) -> None:
         pyoracle.run_omic(prob, want, pyoracle.MODE_REFERENCE, 0)
     t0 = time.perf_counter()
     tests = 0
+    n_nodes = None
     for _ in range(args.steps):
         r = pyoracle.run_omic(prob, want, pyoracle.MODE_REFERENCE, 0)
         tests += int(r["tot_edges"].sum())
     dt = time.perf_counter() - t0
     value = E * args.steps / dt
     used = min(cores, len(prob.pct))
+    n_nodes = int(np.unique(np.concatenate([prob.from_idx, prob.to_idx])).size)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": name, "genes": int(prob.assay.shape[0]), "samples": int(prob.assay.shape[1]),
-                   "edges": int(E), "categories": int(prob.K), "percentiles": int(len(prob.pct)), "padj": "BH",
-                   "note": "R is not installed here: CPU restatement of the reference algorithm (oracle/), "
-                           "reference mode = every (percentile, category, edge) refitted, parallel over "
-                           "percentiles only like mclapply"},
+        "config": _config(name, prob, n_nodes, 1, {
+            "parallelism": f"{used} host threads over the percentiles (like mclapply), {cores} available; rank 0 only",
+            "l2": "n/a (host)", "timing": "wall clock around whole jobs; at most 5 steps and 1 warm-up (each step is a "
+                                          "whole job of seconds on the host cores)",
+            "launch_mode": "n/a (host)", "host_cpus": f"{host_cpus} CPUs in this process's affinity mask",
+            "note": "R is not installed here: CPU restatement of the reference algorithm (oracle/), reference mode = "
+                    "every (percentile, category, edge) refitted, parallel over percentiles only like mclapply"}),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": "port",
                          "sample": f"full {name} workload per step, {args.steps} steps, host threads available {cores}"},
         "ref_equiv_tests_per_s": tests / dt,
@@ -327,6 +334,130 @@ def _bind_near_gpu(local: int) -> str:
         return f"unchanged ({type(e).__name__})"
 
 
+def _kernel_table(torch, eng, cprob, cres, flush, steps: int) -> list[dict]:
+    """Per-launch device times of the eager pipeline from CUDA events on the launching streams (engine option "trace" =
+    3: an event after every launch, no printing): duration = this event - the later of (previous event on the same
+    stream, the main-stream event the side stream forked from).  Median over `steps` steps, L2 flushed between them."""
+    eng.set_option("graph", 0)
+    eng.set_option("trace", 3)
+    runs = []
+    for _ in range(steps + 1):
+        flush.add_(1.0)
+        eng.run_omic_raw(cprob, cres)
+        runs.append(eng.trace())
+    eng.set_option("trace", 0)
+    eng.set_option("graph", 1)
+    runs = runs[1:]
+    table = []
+    for i, (name, stream, _) in enumerate(runs[0]):
+        durs = []
+        for tr in runs:
+            if len(tr) != len(runs[0]):
+                continue
+            prev_same = max([t for (_, s, t) in tr[:i] if s == stream], default=0.0)
+            fork = max([t for (_, s, t) in tr[:i] if s == 0], default=0.0) if stream == 1 else 0.0
+            durs.append(tr[i][2] - max(prev_same, fork))
+        table.append({"kernel": name.strip("()").split("<")[0], "stream": "side" if stream else "main",
+                      "us": float(np.median(durs)) if durs else None})
+    return table
+
+
+def _kernel_bytes(G_nodes: int, n: int, npad: int, E: int, K: int, tot_edges_sum: int) -> dict:
+    """Algorithmic bytes per launch of the kernels of a config-3-shaped step."""
+    vals = G_nodes * n
+    return {
+        "k_mark_nodes": ("hbm", 8 * E), "k_build_nodes": ("hbm", 16 * E),
+        # fused K1 + K2: node rows read once (8 B / value), D (8 B) and the bin ids (2 B) written once
+        "k_front_fused": ("hbm", 8 * vals + 10 * G_nodes * npad),
+        "k_gather_colmajor": ("hbm", 8 * vals + 10 * G_nodes * npad), "k_gene_stats_reg": ("hbm", 10 * G_nodes * npad),
+        "k_qs_compact": ("hbm", 2 * G_nodes * npad),
+        # pair fits: rows A and B, two indices, the K cross moments; D is L2-resident => L2 bandwidth is the bound
+        "k_fit_stream": ("l2", E * (16 * n + 16)),
+        "k_finish": ("hbm", E * (8 * K + 8 + 8 + 4 + 8)),
+        "k_percolate": ("hbm", E * (8 + 4 + 8)),
+        "k_bsort_scatter": ("hbm", E * (8 + 4 + 12)), "k_bsort_sort": ("hbm", E * (12 + 8 + 8 + 20)),
+        "k_bh_onepass": ("hbm", 24 * tot_edges_sum), "k_bh_count": ("hbm", 8 * tot_edges_sum),
+        "k_bh_tilemin": ("hbm", 8 * tot_edges_sum), "k_bh_final": ("hbm", 8 * tot_edges_sum),
+    }
+
+
+def _bundled():
+    """The reference's bundled example data (data/*.rda re-encoded by tests/golden/make_golden.py)."""
+    import pandas as pd
+    d = np.load(os.path.join(ROOT, "tests", "golden", "bundled.npz"), allow_pickle=False)
+    out = {}
+    for key, nm in (("rnaseq", "RNAseq"), ("proteomic", "Proteomics"), ("olink", "Olink")):
+        out[nm] = pd.DataFrame(d[f"{key}_x"], index=d[f"{key}_genes"], columns=d[f"{key}_samples"])
+    meta = pd.DataFrame({"response": pd.Categorical(d["meta_response"], categories=list(d["meta_response_levels"]))},
+                        index=d["meta_samples"])
+    return out, meta
+
+
+def _also_small_configs(md, steps: int) -> dict:
+    """BASELINE configs 1, 2 and 4 through the public API (host data frames in, deggs object out): wall clock per call,
+    everything included (host prep, H2D, engine, D2H, data.frame assembly)."""
+    import pandas as pd
+    from multideggs_b200 import synth
+    out = {}
+    assays, meta = _bundled()
+    for key, method, padj in (("cfg1", "lm", "bonferroni"), ("cfg2", "rlm", "BH")):
+        def call():
+            return md.get_diffNetworks(assayData=assays, metadata=meta, category_variable="response",
+                                       regression_method=method, padj_method=padj, verbose=False, show_progressBar=False,
+                                       cores=2)
+        res = call()
+        for _ in range(5):
+            call()
+        ts = []
+        for _ in range(max(20, steps)):
+            t0 = time.perf_counter()
+            call()
+            ts.append(time.perf_counter() - t0)
+        edges = 0
+        for nm in assays:
+            prep_net = res["diffNetworks"].get(nm)
+            edges += 0 if prep_net is None else sum(len(v) for k, v in prep_net.items()
+                                                    if isinstance(v, pd.DataFrame))
+        out[key] = {"workload": f"bundled RNAseq + Proteomics + Olink, {method} + {padj} (BASELINE config {key[-1]})",
+                    "api": "md.get_diffNetworks (three omic layers in flight, mdeggs_run_omics)",
+                    "ms_per_call_median": 1e3 * float(np.median(ts)), "ms_per_call_min": 1e3 * float(np.min(ts)),
+                    "calls": len(ts), "specific_links_reported": int(edges)}
+    wl = synth.cfg4()
+    x = pd.DataFrame(wl.assay.values.T, index=wl.assay.samples, columns=wl.assay.genes)
+    y = wl.group.astype(float)
+    rng = np.random.default_rng(20261020)
+    folds = [[] for _ in range(10)]
+    for c in (1, 2):  # stratified folds, as tests/test_gpu_parity.py::test_cfg4_full_size_ten_folds
+        idx = rng.permutation(np.flatnonzero(wl.group == c))
+        for j, smp in enumerate(idx.tolist()):
+            folds[(j + (c - 1) * 5) % 10].append(smp)
+
+    def run_all():
+        npairs = []
+        for hold in [None] + folds:
+            keep = np.ones(len(y), dtype=bool)
+            if hold is not None:
+                keep[np.asarray(hold)] = False
+            try:
+                r = md.multiDEGGs_filter(y[keep], x.iloc[keep])
+                npairs.append(int(r["pairs"].shape[0]))
+            except ValueError:
+                npairs.append(0)
+        return npairs
+    run_all()
+    ts = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        npairs = run_all()
+        ts.append(time.perf_counter() - t0)
+    E4 = int(wl.problem().dims[2])
+    out["cfg4"] = {"workload": "5,000 features x 24 samples, 15 percentiles, q.value, 10 stratified folds + the full data "
+                               "(BASELINE config 4)", "api": "md.multiDEGGs_filter, 11 calls",
+                   "ms_per_11_calls": 1e3 * float(np.min(ts)), "edges_per_call": E4,
+                   "value": 11 * E4 / float(np.min(ts)), "unit": UNIT, "pairs_kept_per_call": npairs}
+    return out
+
+
 def run_cuda(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -404,43 +535,66 @@ def run_cuda(args) -> None:
     h2d, d2h = int(e2e_stats["h2d_bytes"]), int(e2e_stats["d2h_bytes"])  # bytes the engine actually moved per step
     assert int(hkeep[5]["best"].numpy()[0]) == best, "host and device legs disagree"
 
-    # ---- roofline of the dominant kernel (pair fit): algorithmic bytes E*(16n+16) / its CUDA-event time ----
+    # ---- roofline: every kernel of the step timed by CUDA events on its own stream; the headline entry is the kernel
+    # with the largest time.  Denominators: HBM = MEASURED_PEAKS.json; L2 = measured here, in this run ----
     peaks = _peaks()
-    fit_ms = stage["ms_fit"]
+    l2_peak = eng.l2_peak_gbs(64 << 20)
+    g_nodes = int(st["n_nodes"])
+    npad = sum((int(c) + 3) // 4 * 4 for c in np.bincount(prob.group, minlength=K + 1)[1:])
+    tot_sum = int(keep[5]["tot_edges"].cpu().numpy().sum())
+    ktab = _kernel_table(torch, eng, cprob, cres, flush, max(3, args.steps // 4))
+    kbytes = _kernel_bytes(g_nodes, n, npad, E, K, tot_sum)
+    dram = _dram_traffic()
+    per_launch = dram.get("per_launch", {})
+    kernels = []
+    for row in ktab:
+        nm, us = row["kernel"], row["us"]
+        if nm not in kbytes or not us or us <= 0:
+            continue
+        bound, nbytes = kbytes[nm]
+        pk = l2_peak if bound == "l2" else peaks["hbm_gbs"]
+        ach = nbytes / (us * 1e-6) / 1e9
+        tr = per_launch.get(nm)
+        kernels.append({"kernel": nm, "stream": row["stream"], "us": us, "algorithmic_bytes": int(nbytes), "bound": bound,
+                        "achieved": ach, "peak": pk, "frac": ach / pk,
+                        "traffic": (tr["dram_read_bytes"] + tr["dram_write_bytes"]) if tr else None})
+    top = max(kernels, key=lambda k: k["us"]) if kernels else None
     fit_bytes = E * (16 * n + 16)
-    achieved = fit_bytes / (fit_ms * 1e-3) / 1e9 if fit_ms > 0 else None
-    # DRAM traffic of one k_fit_stream launch from the committed ncu --set full capture of this workload
-    # (profiles/r01q_ncu_full_hot_kernels.csv: dram__bytes_read.sum 68.59 MB + dram__bytes_write.sum 5.18 MB): the
-    # gene-major matrix is L2-resident, so DRAM sees it once while the kernel streams 849 MB of algorithmic bytes.
-    traffic = 73_770_000 if name == "cfg3" else None
     # whole-step algorithmic bytes (SURVEY section 8 d): gather 2*8*G_nodes*n + quantiles 4*8*G_nodes*n + pair fits
     # + adjust 3*8*sum_p tot_edges[p]
-    g_nodes = int(st["n_nodes"])
-    pipe_bytes = 6 * 8 * g_nodes * n + fit_bytes + 24 * int(keep[5]["tot_edges"].cpu().numpy().sum())
+    pipe_bytes = 6 * 8 * g_nodes * n + fit_bytes + 24 * tot_sum
     step_s = ms / args.steps * 1e-3
-    roofline = {"bound": "hbm", "kernel": "k_fit_stream", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": (achieved / peaks["hbm_gbs"]) if achieved else None, "traffic": traffic,
-                "traffic_source": "profiles/r01q_ncu_full_hot_kernels.csv (ncu --set full, dram read + write per launch)",
-                "peak_source": peaks["source"], "algorithmic_bytes_per_launch": fit_bytes,
-                "kernel_ms": fit_ms, "stage_ms": stage,
-                "stage_note": "stage/kernel times from separate eagerly launched steps (the graph has no stage events)",
-                "note": "frac > 1: the 67 MB gene-major matrix stays in the 126 MB L2, the kernel is bound by L2 "
-                        "bandwidth/latency, not by HBM (see traffic)",
-                "whole_step": {"algorithmic_bytes": pipe_bytes, "achieved": pipe_bytes / step_s / 1e9,
-                               "frac": pipe_bytes / step_s / 1e9 / peaks["hbm_gbs"], "unit": "GB/s",
-                               "model": "SURVEY 8d whole-pipeline bytes / measured step time, against the HBM peak"}}
+    roofline = {
+        "bound": top["bound"] if top else None, "kernel": top["kernel"] if top else None,
+        "achieved": top["achieved"] if top else None, "peak": top["peak"] if top else None, "unit": "GB/s",
+        "frac": top["frac"] if top else None, "traffic": top["traffic"] if top else None,
+        "algorithmic_bytes_per_launch": top["algorithmic_bytes"] if top else None,
+        "kernel_us": top["us"] if top else None,
+        "selection": "the kernel with the largest CUDA-event time in the step (table under `kernels`)",
+        "traffic_source": (dram.get("source", "") + " via profiles/dram_traffic.json (ncu --set full, dram read + write "
+                           "per launch, cold cache)") if dram else None,
+        "peak_source": {"hbm": peaks["source"],
+                        "l2": f"own L2 read microbenchmark in this run (mdeggs_measure_l2_peak, 64 MiB buffer): {l2_peak:.0f} GB/s"},
+        "kernels": kernels, "stage_ms": stage,
+        "timing_note": "kernel times: CUDA events after every launch of eagerly launched steps (engine option trace), "
+                       "median; the headline `value` is the graph-replayed step",
+        "whole_step": {"algorithmic_bytes": pipe_bytes, "achieved": pipe_bytes / step_s / 1e9,
+                       "frac": pipe_bytes / step_s / 1e9 / peaks["hbm_gbs"], "unit": "GB/s",
+                       "ncu_dram_bytes_per_step": dram.get("step_total_bytes"),
+                       "model": "SURVEY 8d whole-pipeline bytes / measured step time, against the HBM peak; most of "
+                                "these bytes are L2 hits by construction (see ncu_dram_bytes_per_step)"}}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": name, "genes": G, "samples": n, "edges": E, "categories": K, "percentiles": P,
-                   "padj": "BH", "network_nodes": int(st["n_nodes"]),
-                   "parallelism": "1 GPU" if world == 1 else f"{world} independent omic layers, one per GPU (no collective)",
-                   "l2": "inputs (160 MB) exceed L2; plus a 256 MiB read-modify-write flush between steps (untimed)",
-                   "timing": "CUDA events per step on the default stream, max over ranks",
-                   "launch_mode": "compute phase replayed from a CUDA graph" if graph_replayed else "eager launches",
-                   "host_cpus": cpu_binding},
+        "config": _config(name, prob, int(st["n_nodes"]), world, {
+            "parallelism": "1 GPU" if world == 1 else f"{world} independent omic layers, one per GPU (no collective)",
+            "l2": "inputs (160 MB) exceed L2; plus a 256 MiB read-modify-write flush between steps (untimed)",
+            "timing": "CUDA events per step on the default stream, max over ranks",
+            "launch_mode": "compute phase replayed from a CUDA graph" if graph_replayed else "eager launches",
+            "host_cpus": cpu_binding,
+            "note": "front = one TMA-fed kernel (fit_path bit 10)" if int(st["fit_path"]) & 0x400 else None}),
         "ref_equiv_tests_per_s": world * ref_equiv * args.steps / (ms * 1e-3),
         "result_check": {"best_percentile_index": best, "sig_pairs": int(sig[best - 1]) if best > 0 else 0,
                          "tests_the_reference_would_run": ref_equiv},
@@ -509,6 +663,10 @@ def run_cuda(args) -> None:
         pool.close()
         torch.cuda.empty_cache()
 
+    # ---- also: BASELINE configs 1, 2 and 4 through the public API ----
+    if rank == 0 and world == 1 and not args.no_small:
+        line.setdefault("also", {}).update(_also_small_configs(md, args.steps))
+
     # ---- also: config 5, edges sharded over the ranks + NCCL all-gather of p-values (strong scaling) ----
     if not args.no_cfg5:
         del cprob, cres, keep, hprob, hres, hkeep
@@ -537,7 +695,29 @@ def run_cuda(args) -> None:
             "stage_ms": stage5, "fit_path": int(st5["fit_path"]),
             "fit_GBps_algorithmic": (E5 / world) * (16 * n5 + 16) / (stage5["ms_fit"] * 1e-3) / 1e9 if stage5["ms_fit"] > 0 else None,
             "best": int(keep5[5]["best"].cpu().numpy()[0])}
+        def bits_equal(a, b) -> bool:  # bit for bit, NaN payloads included
+            if a.dtype.is_floating_point:
+                a, b = a.view(torch.int64), b.view(torch.int64)
+            return bool(torch.equal(a, b))
+
+        def same_as_single(cprob_sh, keep_sh, prob_x):
+            """The sharded job's outputs against the same job on this rank's GPU alone; also its single-GPU time."""
+            c1, r1, keep1 = _device_problem(torch, prob_x, dev)
+            eng.set_option("graph", 0)
+            ms1, _, _, _ = _timed_steps(torch, eng, c1, r1, 2, 1, flush, lambda: None)
+            eng.set_option("graph", 1)
+            ok = all(bits_equal(keep_sh[5][k], keep1[5][k]) for k in WANT)
+            t = torch.tensor([1.0 if ok else 0.0], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            del c1, r1, keep1
+            return bool(t.item() > 0.5), ms1 / 2
+
         if world > 1:
+            ok5, ms5_single = same_as_single(c5, keep5, prob5)
+            ms5_single = max_over_ranks(ms5_single)
+            line["result_check"]["sharded_equals_single"] = {"cfg5": ok5}
+            line["cfg5_strong"] = {"n_gpus": world, "ms": ms5 / steps5, "ms_1gpu_same_run": ms5_single,
+                                   "speedup": ms5_single / (ms5 / steps5), "efficiency": ms5_single / (ms5 / steps5) / world}
             # the north-star sharding applied to config 3 itself: ONE job, its 53,035 edges split over the ranks, NCCL
             # all-gather of p-values + all-reduce of the counts (reported as is: the job is too small to gain from it)
             prob3 = _workload(name, seed_offset=0).problem()
@@ -549,8 +729,13 @@ def run_cuda(args) -> None:
                 "all-gather of p-values + status, all-reduce of the significant-pair counts",
                 "value": prob3.dims[2] * args.steps / (ms3 * 1e-3), "unit": UNIT, "ms_per_step": ms3 / args.steps,
                 "stage_ms": stage3, "best": int(keep3[5]["best"].cpu().numpy()[0])}
+            ok3, _ = same_as_single(c3, keep3, prob3)
+            line["result_check"]["sharded_equals_single"]["cfg3"] = ok3
             del c3, r3, keep3
             eng5.close()
+        else:
+            line["cfg5_strong"] = {"n_gpus": 1, "ms": ms5 / steps5, "ms_1gpu_same_run": ms5 / steps5, "speedup": 1.0,
+                                   "efficiency": 1.0}
 
     # ---- also: rlm stress (K6 batched IRLS), FP64-pipe roofline against this GPU's own DFMA peak (rank 0) ----
     if rank == 0 and not args.no_rlm:
@@ -599,6 +784,7 @@ def main() -> None:
     ap.add_argument("--no-cfg5", action="store_true", help="skip the config-5 'also' leg")
     ap.add_argument("--no-batch", action="store_true", help="skip the layers-in-flight 'also' leg")
     ap.add_argument("--no-rlm", action="store_true", help="skip the rlm stress 'also' leg")
+    ap.add_argument("--no-small", action="store_true", help="skip the config 1 / 2 / 4 'also' legs")
     args = ap.parse_args()
     if args.impl == "reference":
         if args.steps > 5:

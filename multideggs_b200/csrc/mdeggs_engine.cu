@@ -951,8 +951,8 @@ int run_shard_main(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
     // stream, before the pair fits: beside them it takes SM slots from the fit kernel (measured: fits 61 -> 90 us) and
     // lengthens the quantile chain that K7 waits for.
     const int64_t nvec = ((int64_t)n_nodes * L.npad + 7) / 8;
-    const int64_t nb = (nvec + 1023) / 1024;  // 4 vectors per thread and round
-    LAUNCH(k_qs_compact, (unsigned)(nb < s.sm_count * 4 ? nb : s.sm_count * 4), 256, 0, s.s_main, s.D.as<double>(),
+    const int64_t nb = (nvec + 4 * QSC_THREADS - 1) / (4 * QSC_THREADS);  // 4 vectors per thread and round
+    LAUNCH(k_qs_compact, (unsigned)(nb < s.sm_count ? nb : s.sm_count), QSC_THREADS, 0, s.s_main, s.D.as<double>(),
            s.B16.as<unsigned short>(), L.npad, d_nn, QC);
   }
   EVREC(s.ev[EV_STATS], s.s_main);
@@ -1866,7 +1866,7 @@ int mdeggs_wait(mdeggs_ctx* ctx) {
       return MDEGGS_EINVAL;
     }
   }
-  if (ctx->trace >= 2 || getenv("MDEGGS_HOSTTIME")) {
+  if (ctx->trace == 2 || getenv("MDEGGS_HOSTTIME")) {
     const auto t_host3 = std::chrono::steady_clock::now();
     auto us = [](auto a, auto b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
     unsigned long long st2[4] = {0, 0, 0, 0};

@@ -442,44 +442,49 @@ __global__ void __launch_bounds__((NW + FR_PROD_WARPS) * 32, 1)
 // list with ONE global atomic per slot and flush (50,000 same-address atomics would serialise for tens of
 // microseconds), then copies its keys.  Fat slots (tie groups, never copied) only track their key range.
 constexpr int QSC_STAGE = 2048;  // staged keys per CTA (a CTA sees ~100 hits on continuous data)
-__global__ void __launch_bounds__(256) k_qs_compact(const double* __restrict__ D,
+constexpr int QSC_THREADS = 1024;  // one fat CTA per SM: the flush costs one same-address global atomic per slot and CTA
+__global__ void __launch_bounds__(QSC_THREADS) k_qs_compact(const double* __restrict__ D,
                                                     const unsigned short* __restrict__ B16, int npad,
                                                     const int32_t* __restrict__ n_nodes_p, QsCompactArgs Q) {
-  __shared__ __align__(16) unsigned char s_tab[QSC_BINS];
+  __shared__ __align__(16) unsigned char s_tab[QSC_BINS + 16];  // [QSC_BINS] = 0xff: where padding / NaN ids land
   __shared__ unsigned long long st_key[QSC_STAGE];
   __shared__ unsigned char st_slot[QSC_STAGE];
   __shared__ unsigned int s_n, s_cnt[QS_MAX_T], s_base[QS_MAX_T];
   const long long total = (long long)(*n_nodes_p) * npad;
   const int U = *Q.U;
   if (threadIdx.x == 0) s_n = 0u;
+  if (threadIdx.x < 16) s_tab[QSC_BINS + threadIdx.x] = 0xff;
   for (int i = threadIdx.x; i < QS_MAX_T; i += blockDim.x) s_cnt[i] = 0u;
   qsc_load_table(Q, s_tab);  // (ends with a CTA barrier)
   const long long nvec = (total + 7) >> 3;
   const uint4* __restrict__ bv = reinterpret_cast<const uint4*>(B16);
+  auto hit = [&](unsigned sl, long long idx) {  // ~0.6 % of the values
+    const unsigned long long key = dkey(D[idx]);
+    if (Q.slot_fat[sl]) {
+      if (key < __ldcg(Q.slot_min + sl)) atomicMin(Q.slot_min + sl, key);
+      if (key > __ldcg(Q.slot_max + sl)) atomicMax(Q.slot_max + sl, key);
+    } else {
+      const unsigned at = atomicAdd(&s_n, 1u);
+      if (at < (unsigned)QSC_STAGE) {
+        st_key[at] = key;
+        st_slot[at] = (unsigned char)sl;
+      } else {  // staging full (a slot bin that holds a large share of the data): direct append
+        const unsigned pos = atomicAdd(Q.slot_cursor + sl, 1u);
+        if (pos < Q.slot_count[sl]) Q.cand[Q.slot_off[sl] + pos] = key;
+      }
+    }
+  };
   auto visit = [&](const uint4& w, long long i) {
     const unsigned ws[4] = {w.x, w.y, w.z, w.w};
+    const bool whole = (i + 1) * 8 <= total;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const unsigned b = (ws[q >> 1] >> (16 * (q & 1))) & 0xffffu;
-      const long long idx = i * 8 + q;
-      if (b < (unsigned)QSC_BINS && idx < total) {
-        const unsigned sl = s_tab[b];
-        if (sl != 0xff) {
-          const unsigned long long key = dkey(D[idx]);
-          if (Q.slot_fat[sl]) {
-            if (key < __ldcg(Q.slot_min + sl)) atomicMin(Q.slot_min + sl, key);
-            if (key > __ldcg(Q.slot_max + sl)) atomicMax(Q.slot_max + sl, key);
-          } else {
-            const unsigned at = atomicAdd(&s_n, 1u);
-            if (at < (unsigned)QSC_STAGE) {
-              st_key[at] = key;
-              st_slot[at] = (unsigned char)sl;
-            } else {  // staging full (a slot bin that holds a large share of the data): direct append
-              const unsigned pos = atomicAdd(Q.slot_cursor + sl, 1u);
-              if (pos < Q.slot_count[sl]) Q.cand[Q.slot_off[sl] + pos] = key;
-            }
-          }
-        }
+    for (int h = 0; h < 4; ++h) {
+      // bin ids >= 4096 (padding, NaN) index the table's spill entry 4096..: clamp with one min instead of a branch
+      const unsigned b0 = min(ws[h] & 0xffffu, (unsigned)QSC_BINS), b1 = min(ws[h] >> 16, (unsigned)QSC_BINS);
+      const unsigned s0 = s_tab[b0], s1 = s_tab[b1];
+      if ((s0 & s1) != 0xffu) {  // at least one of the two is a slot value
+        if (s0 != 0xffu && (whole || i * 8 + 2 * h < total)) hit(s0, i * 8 + 2 * h);
+        if (s1 != 0xffu && (whole || i * 8 + 2 * h + 1 < total)) hit(s1, i * 8 + 2 * h + 1);
       }
     }
   };

@@ -1746,18 +1746,24 @@ __global__ void __launch_bounds__(256) k_dfma_peak(int iters, double seed, doubl
 // L2 read bandwidth of this GPU for an L2-resident working set (denominator of the pair-fit roofline: the gene-major
 // matrix D, <= 67 MB, stays in the 126 MB L2 while k_fit_stream re-reads it ~12 times).  Every thread keeps 4
 // independent 16-byte loads in flight and bypasses L1 (ld.global.cg), so the figure is L2 -> SM throughput only.
+__device__ __forceinline__ uint4 l2_ld_cg(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
 __global__ void __launch_bounds__(256) k_l2_read(const uint4* __restrict__ buf, size_t n_vec, int passes,
                                                  unsigned int* __restrict__ sink) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   unsigned int acc = 0;
   for (int r = 0; r < passes; ++r) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // every pass starts at another CTA's offset: an SM does not re-read what it read in the pass before
+    size_t i = (((size_t)blockIdx.x + (size_t)r * 37) % gridDim.x) * blockDim.x + threadIdx.x;
     for (; i + 3 * stride < n_vec; i += 4 * stride) {
-      const uint4 a = __ldcg(buf + i), b = __ldcg(buf + i + stride), c = __ldcg(buf + i + 2 * stride),
-                  d = __ldcg(buf + i + 3 * stride);
+      const uint4 a = l2_ld_cg(buf + i), b = l2_ld_cg(buf + i + stride), c = l2_ld_cg(buf + i + 2 * stride),
+                  d = l2_ld_cg(buf + i + 3 * stride);
       acc += a.x ^ b.y ^ c.z ^ d.w;
     }
-    for (; i < n_vec; i += stride) acc += __ldcg(buf + i).x;
+    for (; i < n_vec; i += stride) acc += l2_ld_cg(buf + i).x;
   }
   if (acc == 0x12345678u) sink[0] = acc;  // (practically) never true: keeps the loads alive
 }

@@ -38,10 +38,10 @@ constexpr int QS_SAMPLE = 1024;      // sample size (a single-CTA sort: kept sma
 constexpr int QS_SAMPLE_MAX = QS_SAMPLE;
 constexpr int QS_SAMPLE_THREADS = QS_SAMPLE / 2;  // one compare-exchange pair per thread in every sorting step
 static_assert(QS_SAMPLE_THREADS <= 1024 && QS_SAMPLE_THREADS % 32 == 0, "single CTA");
-constexpr int QS_FIN_CAP = 4096;     // keys a finish CTA keeps in shared memory (32 KB); longer lists stay in L2
+constexpr int QS_FIN_CAP = 16384;    // keys a finish CTA keeps in shared memory (128 KB); longer lists stay in L2
 constexpr unsigned int QS_SLOT_MAX = 1u << 20;  // slots with more values are not compacted ("fat": tie groups)
 constexpr unsigned int QS_CAND_MAX = 8u << 20;  // candidate buffer, keys
-constexpr int QS_FIN_THREADS = 256;
+constexpr int QS_FIN_THREADS = 512;
 constexpr int QS_DIRECT = 256;        // keys ranked directly once a digit pass leaves this few
 constexpr int QS_SCAN_THREADS = 256;  // >= QS_MAX_T
 constexpr int QS_STAGE = 2048;       // per-CTA staging entries of the compaction pass
