@@ -65,7 +65,8 @@ extern "C" {
 /* per-edge status (never an error of the call; the host decides what R would have done) */
 #define MDEGGS_EDGE_OK 0
 #define MDEGGS_EDGE_SINGULAR 1    /* K == 2: solve(XtX) would throw (core_functions.R:1068) / rlm refuses a singular design */
-#define MDEGGS_EDGE_NONFINITE 2   /* NA/NaN/Inf in either gene row (.lm.fit would error)              */
+#define MDEGGS_EDGE_NONFINITE 2   /* K == 2 lm: NA/NaN/Inf in either gene row (.lm.fit errors, core_functions.R:1065);
+                                     rlm / aov: an Inf among the pair's complete cases (lm.wfit / lm.fit error)  */
 #define MDEGGS_EDGE_NOT_CONVERGED 3 /* rlm: 20 IRLS iterations without convergence (R: warning only)  */
 #define MDEGGS_EDGE_ZERO_SCALE 4  /* rlm: MAD scale == 0                                              */
 #define MDEGGS_EDGE_SELFLOOP 5    /* exact fit: from == to (the built-in network has one self-loop) or a response
@@ -76,6 +77,11 @@ extern "C" {
                                      (core_functions.R:966-968): F and p use the reduced degrees of freedom
                                      (Ke - 1 - aliased, n - 2 Ke + aliased), not the run's `df`; when no interaction
                                      column is left the summary table has no third term row and p is NA (NaN)      */
+#define MDEGGS_EDGE_NA_OMIT 7     /* rlm and aov only, soft: the samples where either gene is NA/NaN were dropped for this
+                                     pair, as model.frame(na.action = na.omit) does inside rlm() / aov()
+                                     (core_functions.R:916-917, 966-967): the fit, F and p use the n' complete cases and
+                                     their degrees of freedom (K >= 3: Ke' - 1, n' - 2 Ke'; rlm: 1, n' - 4), not the
+                                     run's `df`.  Fewer than 2 levels or no residual d.f. left: MDEGGS_EDGE_SINGULAR   */
 
 /* error codes */
 #define MDEGGS_OK 0

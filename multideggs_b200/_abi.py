@@ -21,7 +21,7 @@ HOMMEL_MAX_E = 65536   # MDEGGS_HOMMEL_MAX_E: hommel is O(n^2) per segment, larg
 RLM_COV_XTWX, RLM_COV_XTX = 0, 1
 LAYOUT_COLMAJOR, LAYOUT_ROWMAJOR = 0, 1
 MEM_HOST, MEM_DEVICE = 0, 1
-EDGE_OK, EDGE_SINGULAR, EDGE_NONFINITE, EDGE_NOT_CONVERGED, EDGE_ZERO_SCALE, EDGE_SELFLOOP, EDGE_ALIASED = 0, 1, 2, 3, 4, 5, 6
+EDGE_OK, EDGE_SINGULAR, EDGE_NONFINITE, EDGE_NOT_CONVERGED, EDGE_ZERO_SCALE, EDGE_SELFLOOP, EDGE_ALIASED, EDGE_NA_OMIT = 0, 1, 2, 3, 4, 5, 6, 7
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)

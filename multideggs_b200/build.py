@@ -10,7 +10,7 @@ CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
 OUT = os.path.join(CSRC, "libmdeggs.so")
 SOURCES = ["mdeggs_engine.cu"]
-HEADERS = ["mdeggs_kernels.cuh", "mdeggs_front.cuh", "mdeggs_math.cuh", "mdeggs_rlm.cuh", "mdeggs_dense.cuh", "mdeggs_qsel.cuh", "mdeggs_bsort.cuh", "mdeggs_qvalue_tab.h", "nccl_dl.h",
+HEADERS = ["mdeggs_kernels.cuh", "mdeggs_napair.cuh", "mdeggs_front.cuh", "mdeggs_math.cuh", "mdeggs_rlm.cuh", "mdeggs_dense.cuh", "mdeggs_qsel.cuh", "mdeggs_bsort.cuh", "mdeggs_qvalue_tab.h", "nccl_dl.h",
            os.path.join(ROOT, "include", "mdeggs.h")]
 
 

@@ -147,17 +147,22 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finish(int src, const double* _
                                                 int32_t* __restrict__ status, double* __restrict__ coef,
                                                 double* __restrict__ p_out, const int32_t* __restrict__ err,
                                                 int do_bs, BsArgs B, int32_t* __restrict__ fin_q,
-                                                unsigned int* __restrict__ fin_nq) {
+                                                unsigned int* __restrict__ fin_nq, int32_t* __restrict__ na_q,
+                                                unsigned int* __restrict__ na_nq) {
   const int64_t e = e_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = e < e_hi && !*err;
   double p = 0.0;
   bool deferred = false;
+  bool na_pair = false;  // rlm / aov: a row of this pair has NA -> complete-case fit by k_fit_na_pairs
   int n_alias = 0;
   tc.lbeta_ab = *lbeta_p;
   if (live) {
   if (src != 2) {
     const int a = ea[e], b = eb[e];
-    if (a == b || bad[a] || bad[b]) {
+    const int bb = bad[a] | bad[b];
+    if (na_q && a != b && (bb & 1)) {  // (an Inf may sit in a sample that the other gene's NA removes)
+      na_pair = true;
+    } else if (a == b || bb) {
       const bool self = (a == b) && !bad[a];
       stat[e] = self ? 0.0 : nan("");
       status[e] = self ? MDEGGS_EDGE_SELFLOOP : MDEGGS_EDGE_NONFINITE;
@@ -175,9 +180,13 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finish(int src, const double* _
       }
       finish_pair<K>(L, mean, sxx, a, b, pm, stat + e, status + e, coef ? coef + (size_t)e * 2 * K : nullptr, &n_alias);
     }
+  } else if (na_q && status[e] == MDEGGS_EDGE_NONFINITE) {  // (k_fit_rlm skipped the pair)
+    const int a = ea[e], b = eb[e];
+    na_pair = a != b && ((bad[a] | bad[b]) & 1);
   }
-  const int st = status[e];
-  if (st == MDEGGS_EDGE_SINGULAR || st == MDEGGS_EDGE_NONFINITE || st == MDEGGS_EDGE_ZERO_SCALE) p = nan("");
+  const int st = na_pair ? MDEGGS_EDGE_NONFINITE : status[e];
+  if (na_pair) p = nan("");
+  else if (st == MDEGGS_EDGE_SINGULAR || st == MDEGGS_EDGE_NONFINITE || st == MDEGGS_EDGE_ZERO_SCALE) p = nan("");
   else if (st == MDEGGS_EDGE_SELFLOOP) p = 1.0;
   else if (st == MDEGGS_EDGE_ALIASED) {  // rare: this edge's own degrees of freedom, generic continued fraction
     const double sv = stat[e];
@@ -204,7 +213,17 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finish(int src, const double* _
       if (deferred) fin_q[base + __popc(m & ((1u << lane) - 1u))] = (int32_t)(e - e_lo);
     }
   }
-  const bool done = live && !deferred;
+  if (na_q) {  // same for the pairs with missing values
+    const unsigned m = __ballot_sync(0xffffffffu, na_pair);
+    if (m) {
+      const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+      unsigned int base = 0;
+      if (lane == leader) base = atomicAdd(na_nq, (unsigned int)__popc(m));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (na_pair) na_q[base + __popc(m & ((1u << lane) - 1u))] = (int32_t)(e - e_lo);
+    }
+  }
+  const bool done = live && !deferred && !na_pair;
   if (done) p_out[e] = p;
   if (do_bs) bs_count(B, done, e, p);  // reached by every thread of the CTA
 }

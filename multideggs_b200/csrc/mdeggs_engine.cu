@@ -27,6 +27,7 @@
 #include "mdeggs_dense.cuh"
 #include "mdeggs_kernels.cuh"
 #include "mdeggs_rlm.cuh"
+#include "mdeggs_napair.cuh"
 #include "mdeggs_qsel.cuh"
 #include "mdeggs_front.cuh"
 #include "nccl_dl.h"
@@ -62,7 +63,7 @@ struct DevBuf {
 enum Ev { EV_START, EV_H2D, EV_GATHER, EV_STATS, EV_FIT, EV_TAIL, EV_COLL, EV_PERC, EV_ADJ, EV_END, EV_Q0, EV_Q1, EV_COUNT };
 
 // scalar slots in the `scal` buffer (8-byte each)
-enum Scal { SC_NNODES = 0, SC_ERR = 1, SC_BEST = 2, SC_NVALID = 3, SC_ROWLO = 4, SC_ROWHI = 5, SC_DONE = 6, SC_FINQ = 7, SC_COUNT = 8 };
+enum Scal { SC_NNODES = 0, SC_ERR = 1, SC_BEST = 2, SC_NVALID = 3, SC_ROWLO = 4, SC_ROWHI = 5, SC_DONE = 6, SC_FINQ = 7, SC_NAQ = 8, SC_COUNT = 10 };
 constexpr int64_t FIN_DEFER_MIN_EDGES = 1 << 16;  // below this a second launch costs more than the slow lanes
 
 struct Shard {
@@ -73,6 +74,7 @@ struct Shard {
   nccl_comm_t comm = nullptr;
   bool smem_attr_set = false, rsel_attr_set = false, dense_attr_set = false;  // cudaFuncSetAttribute is per device
   unsigned front_attr_mask = 0;  // ... per instantiation of k_front_fused
+  unsigned na_attr_mask = 0;     // ... per instantiation of k_fit_na_pairs
   int front_bits = 0;            // this call's front path (see stats.fit_path)
   int sm_count = 0;
   // tensor map of the device copy of the assay (k_front_fused), rebuilt when any of its ingredients changes
@@ -101,11 +103,11 @@ struct Shard {
     if (e == cudaSuccess) h_stage_cap = bytes + 256;
     return e;
   }
-  DevBuf bh1_state, assay, from, to, ea, eb, stage_dev, bs_count, bs_slot, seg_done, seg_rank, fin_q, hm_p, hm_q1, hm_c, hm_sc, hm_idx, hm_off, seg_pi0, B16, stamps, excl, node_of_row, rowlist, scal, src_of_pos, pct, cutoff, D, cub_tmp, mean, sxx, med, bad, stat, status, p_edge, coef, iters, act, counters, sortk, sortk2, idx,
+  DevBuf na_q, bh1_state, assay, from, to, ea, eb, stage_dev, bs_count, bs_slot, seg_done, seg_rank, fin_q, hm_p, hm_q1, hm_c, hm_sc, hm_idx, hm_off, seg_pi0, B16, stamps, excl, node_of_row, rowlist, scal, src_of_pos, pct, cutoff, D, cub_tmp, mean, sxx, med, bad, stat, status, p_edge, coef, iters, act, counters, sortk, sortk2, idx,
       idx2, ps, sa, sb, tile_cnt, tile_base, seg_n, tile_min, tile_carry, padj_best, cat_best, cat, padj, med_out,
       small_out, rsel_hist, rsel_state, rsel_cand, dense_S, cf_tab, sxy;
   void release_all() {
-    DevBuf* all[] = {&bh1_state, &assay, &from, &to, &ea, &eb, &stage_dev, &bs_count, &bs_slot, &seg_done, &seg_rank, &fin_q, &hm_p, &hm_q1, &hm_c, &hm_sc, &hm_idx, &hm_off, &seg_pi0, &B16, &stamps, &excl, &node_of_row, &rowlist, &scal, &src_of_pos, &pct, &cutoff,
+    DevBuf* all[] = {&na_q, &bh1_state, &assay, &from, &to, &ea, &eb, &stage_dev, &bs_count, &bs_slot, &seg_done, &seg_rank, &fin_q, &hm_p, &hm_q1, &hm_c, &hm_sc, &hm_idx, &hm_off, &seg_pi0, &B16, &stamps, &excl, &node_of_row, &rowlist, &scal, &src_of_pos, &pct, &cutoff,
                      &D, &cub_tmp, &mean, &sxx, &med, &bad, &stat, &status, &p_edge,
                      &coef, &iters, &act, &counters, &sortk, &sortk2, &idx, &idx2, &ps, &sa, &sb, &tile_cnt,
                      &tile_base, &seg_n, &tile_min, &tile_carry, &padj_best, &cat_best, &cat, &padj, &med_out,
@@ -333,6 +335,28 @@ __global__ void k_stamp(unsigned long long* slot) {
   *slot = t;
 }
 
+// complete-case fits of the pairs with missing values (rlm and aov only; see mdeggs_napair.cuh)
+struct NaPairPlan {
+  bool on = false;
+  int wpb = 0, is_rlm = 0, tested_coef = 3, cov_mode = 0;
+  size_t smem = 0;
+};
+NaPairPlan na_pair_plan(const mdeggs_problem* in) {
+  NaPairPlan NP;
+  const bool is_rlm = in->K == 2 && in->method == MDEGGS_METHOD_RLM;
+  if (in->K == 2 && !is_rlm) return NP;  // fit_lm_interaction: .lm.fit throws on NA (core_functions.R:1065)
+  const size_t per_warp = (size_t)(is_rlm ? 3 : 2) * (size_t)in->n * 8;
+  const size_t budget = 200 * 1024;
+  if (per_warp > budget) return NP;      // rows too long for shared memory: such pairs keep MDEGGS_EDGE_NONFINITE
+  NP.on = true;
+  NP.wpb = (int)(budget / per_warp) < NA_WARPS ? (int)(budget / per_warp) : NA_WARPS;
+  NP.smem = per_warp * (size_t)NP.wpb;
+  NP.is_rlm = is_rlm ? 1 : 0;
+  NP.tested_coef = in->tested_coef;
+  NP.cov_mode = in->rlm_cov_mode;
+  return NP;
+}
+
 template <int K>
 void launch_fit_stream(mdeggs_ctx* ctx, Shard& s, const SegLayout& L, int64_t e_lo, int64_t e_hi) {
   int64_t ne = e_hi - e_lo;
@@ -348,7 +372,7 @@ void launch_fit_stream(mdeggs_ctx* ctx, Shard& s, const SegLayout& L, int64_t e_
 template <int K>
 void launch_finish(mdeggs_ctx* ctx, Shard& s, const SegLayout& L, int src, int nn, int64_t e_lo, int64_t e_hi, int mode,
                    double df1, double df2, const TailConsts& tc, const double* d_lbeta, double* coef, int do_bs,
-                   const BsArgs& B) {
+                   const BsArgs& B, const NaPairPlan& NP) {
   // tails that need the continued fraction (everything but the closed-form F with 2 numerator degrees of freedom):
   // on big edge lists the few slow lanes are queued and finished by a second, dense launch
   const int64_t ne = e_hi - e_lo;
@@ -359,11 +383,22 @@ void launch_finish(mdeggs_ctx* ctx, Shard& s, const SegLayout& L, int src, int n
   LAUNCH(k_finish<K>, blocks_for(ne, FIN_THREADS), FIN_THREADS, 0, s.s_main, src, s.sxy.as<double>(), s.dense_S.as<double>(),
          nn, L, s.ea.as<int32_t>(), s.eb.as<int32_t>(), s.mean.as<double>(),
          s.sxx.as<double>(), s.bad.as<uint8_t>(), e_lo, e_hi, mode, df1, df2, tc, d_lbeta, s.stat.as<double>(),
-         s.status.as<int32_t>(), coef, s.p_edge.as<double>(), s.scal.as<int32_t>() + 2 * SC_ERR, do_bs, B, fin_q, fin_nq);
+         s.status.as<int32_t>(), coef, s.p_edge.as<double>(), s.scal.as<int32_t>() + 2 * SC_ERR, do_bs, B, fin_q, fin_nq,
+         NP.on ? s.na_q.as<int32_t>() : nullptr, s.scal.as<unsigned int>() + 2 * SC_NAQ);
   if (defer) {
     const unsigned want = blocks_for(ne, 256);
     LAUNCH(k_finish_slow, want < 148u * 8 ? want : 148u * 8, 256, 0, s.s_main, fin_q, fin_nq, e_lo, mode, df1, df2, tc,
            d_lbeta, s.stat.as<double>(), s.p_edge.as<double>(), s.scal.as<int32_t>() + 2 * SC_ERR, do_bs, B);
+  }
+  if (NP.on) {
+    // rlm / aov: complete-case fits of the queued pairs that touch a row with NA (mdeggs_napair.cuh).  The grid is
+    // sized for a modest queue and strides over a longer one; without NA in the data it finds an empty queue and exits.
+    const int64_t want = (ne + NP.wpb - 1) / NP.wpb;
+    const unsigned grid = (unsigned)(want < 148 * 2 ? want : 148 * 2);
+    LAUNCH(k_fit_na_pairs<K>, grid, NP.wpb * 32, NP.smem, s.s_main, s.D.as<double>(), L, s.ea.as<int32_t>(),
+           s.eb.as<int32_t>(), s.na_q.as<int32_t>(), s.scal.as<unsigned int>() + 2 * SC_NAQ, e_lo, NP.is_rlm,
+           NP.tested_coef, NP.cov_mode, s.stat.as<double>(), s.status.as<int32_t>(), coef,
+           NP.is_rlm ? s.iters.as<int32_t>() : nullptr, s.p_edge.as<double>(), s.scal.as<int32_t>() + 2 * SC_ERR, do_bs, B);
   }
 }
 
@@ -1088,14 +1123,32 @@ int run_shard_main(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
       B = make_bs_args(s, E);
     }
     if (e_hi - e_lo >= FIN_DEFER_MIN_EDGES) CU(s.fin_q.ensure((size_t)(e_hi - e_lo) * 4));  // queue of slow tails
+    const NaPairPlan NP = na_pair_plan(in);
+    if (NP.on) {
+      CU(s.na_q.ensure((size_t)(e_hi - e_lo) * 4));
+      if (NP.smem > 48 * 1024 && !(s.na_attr_mask & (1u << K))) {
+        cudaError_t ae = cudaSuccess;
+        switch (K) {
+          case 2: ae = cudaFuncSetAttribute(k_fit_na_pairs<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); break;
+          case 3: ae = cudaFuncSetAttribute(k_fit_na_pairs<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); break;
+          case 4: ae = cudaFuncSetAttribute(k_fit_na_pairs<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); break;
+          case 5: ae = cudaFuncSetAttribute(k_fit_na_pairs<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); break;
+          case 6: ae = cudaFuncSetAttribute(k_fit_na_pairs<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); break;
+          case 7: ae = cudaFuncSetAttribute(k_fit_na_pairs<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); break;
+          default: ae = cudaFuncSetAttribute(k_fit_na_pairs<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); break;
+        }
+        CU(ae);
+        s.na_attr_mask |= 1u << K;
+      }
+    }
     switch (K) {
-      case 2: launch_finish<2>(ctx, s, L, src, n_nodes, e_lo, e_hi, tail_mode, df1, df2, tc, d_lbeta, d_coef, do_bs, B); break;
-      case 3: launch_finish<3>(ctx, s, L, src, n_nodes, e_lo, e_hi, tail_mode, df1, df2, tc, d_lbeta, d_coef, do_bs, B); break;
-      case 4: launch_finish<4>(ctx, s, L, src, n_nodes, e_lo, e_hi, tail_mode, df1, df2, tc, d_lbeta, d_coef, do_bs, B); break;
-      case 5: launch_finish<5>(ctx, s, L, src, n_nodes, e_lo, e_hi, tail_mode, df1, df2, tc, d_lbeta, d_coef, do_bs, B); break;
-      case 6: launch_finish<6>(ctx, s, L, src, n_nodes, e_lo, e_hi, tail_mode, df1, df2, tc, d_lbeta, d_coef, do_bs, B); break;
-      case 7: launch_finish<7>(ctx, s, L, src, n_nodes, e_lo, e_hi, tail_mode, df1, df2, tc, d_lbeta, d_coef, do_bs, B); break;
-      default: launch_finish<8>(ctx, s, L, src, n_nodes, e_lo, e_hi, tail_mode, df1, df2, tc, d_lbeta, d_coef, do_bs, B); break;
+      case 2: launch_finish<2>(ctx, s, L, src, n_nodes, e_lo, e_hi, tail_mode, df1, df2, tc, d_lbeta, d_coef, do_bs, B, NP); break;
+      case 3: launch_finish<3>(ctx, s, L, src, n_nodes, e_lo, e_hi, tail_mode, df1, df2, tc, d_lbeta, d_coef, do_bs, B, NP); break;
+      case 4: launch_finish<4>(ctx, s, L, src, n_nodes, e_lo, e_hi, tail_mode, df1, df2, tc, d_lbeta, d_coef, do_bs, B, NP); break;
+      case 5: launch_finish<5>(ctx, s, L, src, n_nodes, e_lo, e_hi, tail_mode, df1, df2, tc, d_lbeta, d_coef, do_bs, B, NP); break;
+      case 6: launch_finish<6>(ctx, s, L, src, n_nodes, e_lo, e_hi, tail_mode, df1, df2, tc, d_lbeta, d_coef, do_bs, B, NP); break;
+      case 7: launch_finish<7>(ctx, s, L, src, n_nodes, e_lo, e_hi, tail_mode, df1, df2, tc, d_lbeta, d_coef, do_bs, B, NP); break;
+      default: launch_finish<8>(ctx, s, L, src, n_nodes, e_lo, e_hi, tail_mode, df1, df2, tc, d_lbeta, d_coef, do_bs, B, NP); break;
     }
   }
   EVREC(s.ev[EV_TAIL], s.s_main);

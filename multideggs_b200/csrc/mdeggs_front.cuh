@@ -232,7 +232,7 @@ __device__ __forceinline__ void front_unit(const FrontArgs& A, uint32_t sbase, c
     for (int j = 0; j < ITEMS; ++j) {
       if (lane + 32 * j < m) {
         nn += !isnan(v[j]);
-        nf |= !isfinite(v[j]);
+        nf |= nonfinite_bits(v[j]);
       }
     }
     nn = __reduce_add_sync(0xffffffffu, nn);
@@ -294,7 +294,7 @@ __device__ __forceinline__ void front_unit(const FrontArgs& A, uint32_t sbase, c
     A.mean[(size_t)node * L.K + k] = mu;
     A.sxx[(size_t)node * L.K + k] = d2;
     A.med[(size_t)node * L.K + k] = median;
-    if (nf) A.bad[node] = 1;
+    if (nf) mark_bad(A.bad, node, nf);
   }
   if (m + lane < L.off[k + 1] - off) drow[m + lane] = mu;  // padding := segment mean
 }

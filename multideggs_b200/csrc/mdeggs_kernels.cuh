@@ -51,6 +51,13 @@ __device__ __forceinline__ double warp_sum(double v) {
 //   k_build_nodes: thread per row -> node_of_row / rowlist;  thread per edge -> node ids (ea, eb) of its end
 //                  points, read by every later edge kernel instead of from/to + a dependent node_of_row look-up.
 // ------------------------------------------------------------------------------------------------
+// bad[node]: bit 0 = the row holds NA / NaN, bit 1 = it holds +-Inf.  Several warps (one per category) may flag the same
+// node, so the byte is set through an atomic OR on its 32-bit word (the array is 4-byte aligned and padded).
+__device__ __forceinline__ int nonfinite_bits(double v) { return isnan(v) ? 1 : (isinf(v) ? 2 : 0); }
+__device__ __forceinline__ void mark_bad(uint8_t* __restrict__ bad, int node, int bits) {
+  atomicOr(reinterpret_cast<unsigned int*>(bad) + (node >> 2), (unsigned int)bits << ((node & 3) * 8));
+}
+
 constexpr int K0_SMEM_ROWS = 1 << 18;  // 32 KB bitmap
 
 __global__ void __launch_bounds__(256) k_mark_nodes(const int32_t* __restrict__ from, const int32_t* __restrict__ to,
@@ -277,7 +284,7 @@ __global__ void __launch_bounds__(THREADS) k_gene_stats(double* __restrict__ D, 
       vmin = fmin(vmin, v);
       vmax = fmax(vmax, v);
       nn += !isnan(v);
-      nf |= !isfinite(v);
+      nf |= nonfinite_bits(v);
       if (Q.B16) qsc_visit(Q, s_qtab, Q.B16[(size_t)node * L.npad + L.off[k] + i], dkey(v));
     }
     s = warp_sum(s);
@@ -337,7 +344,7 @@ __global__ void __launch_bounds__(THREADS) k_gene_stats(double* __restrict__ D, 
       mean[(size_t)node * L.K + k] = mu;
       sxx[(size_t)node * L.K + k] = d2;
       med[(size_t)node * L.K + k] = median;
-      if (nf) atomicOr(&s_bad, 1);
+      if (nf) atomicOr(&s_bad, nf);
     }
     for (int i = L.off[k] + m + lane; i < L.off[k + 1]; i += 32) grow[i] = mu;  // padding := segment mean
   }
@@ -440,7 +447,7 @@ __global__ void __launch_bounds__(256) k_gene_stats_reg(double* __restrict__ D, 
       vmin = fmin(vmin, v);
       vmax = fmax(vmax, v);
       nn += !isnan(v);
-      nf |= !isfinite(v);
+      nf |= nonfinite_bits(v);
     }
   }
   if (Q.B16) {  // K3 S3: the bin ids of this segment (2 bytes per value), slot values appended to their lists
@@ -516,7 +523,7 @@ __global__ void __launch_bounds__(256) k_gene_stats_reg(double* __restrict__ D, 
     mean[(size_t)node * L.K + k] = mu;
     sxx[(size_t)node * L.K + k] = d2;
     med[(size_t)node * L.K + k] = median;
-    if (nf) bad[node] = 1;
+    if (nf) mark_bad(bad, node, nf);
   }
   for (int i = L.off[k] + m + lane; i < L.off[k + 1]; i += 32) grow[i] = mu;  // padding := segment mean
 }

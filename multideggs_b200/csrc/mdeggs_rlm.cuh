@@ -63,6 +63,151 @@ __device__ __forceinline__ double warp_median_abs(const double* r, const SegLayo
   return __ddiv_rn(__dadd_rn(__longlong_as_double((long long)k1), __longlong_as_double((long long)k2)), 2.0);
 }
 
+// The IRLS itself and the Wald test, one warp: `pa` / `pb` hold the pair's samples category by category as laid out by
+// L (off[k], cnt[k]; L.n of them in total), `r` receives the residuals, ca / cb / sxa are the unweighted per-category
+// means of A and B and the centred sum of squares of A.  Shared by k_fit_rlm (rows of the run's layout) and by
+// k_fit_na_pairs (the complete cases of one pair, mdeggs_napair.cuh).
+__device__ __forceinline__ void rlm_irls_warp(const double* pa, const double* pb, double* r, const SegLayout& L,
+                                              const double (&ca)[2], const double (&cb)[2], const double (&sxa)[2],
+                                              int tested_coef, int cov_mode, unsigned long long* s_cand32, int lane,
+                                              double* F_out, int* status_out, int* iters_out, double (&beta)[4]) {
+  const double kh = 1.345;
+  const int n = L.n;
+  GroupFit gf[2];
+  // ---- init = "ls": ordinary least squares residuals ----
+  for (int k = 0; k < 2; ++k) {
+    double acc = 0.0;
+    for (int i = L.off[k] + lane; i < L.off[k] + L.cnt[k]; i += 32) acc = fma(pa[i] - ca[k], pb[i] - cb[k], acc);
+    acc = warp_sum(acc);
+    gf[k].W = (double)L.cnt[k];
+    gf[k].ma = ca[k];
+    gf[k].mb = cb[k];
+    gf[k].sxx = sxa[k];
+    gf[k].sxy = acc;
+    gf[k].slope = acc / gf[k].sxx;
+    gf[k].icpt = cb[k] - gf[k].slope * ca[k];
+    for (int i = L.off[k] + lane; i < L.off[k] + L.cnt[k]; i += 32) r[i] = pb[i] - gf[k].icpt - gf[k].slope * pa[i];
+  }
+  __syncwarp();
+  double scale = 0.0;
+  bool done = false, zero_scale = false;
+  int it = 0;
+  for (it = 1; it <= 20; ++it) {
+    scale = warp_median_abs(r, L, lane, s_cand32) / 0.6745;
+    if (scale == 0.0) {
+      zero_scale = true;
+      done = true;
+      break;
+    }
+    double diff = 0.0, old_ss = 0.0;
+    for (int k = 0; k < 2; ++k) {
+      double sw = 0.0, swa = 0.0, swb = 0.0, swaa = 0.0, swab = 0.0;
+      for (int i = L.off[k] + lane; i < L.off[k] + L.cnt[k]; i += 32) {
+        double u = fabs(r[i] / scale);
+        double w = (u <= kh) ? 1.0 : kh / u;  // psi.huber weight pmin(1, k/|u|)
+        double da = pa[i] - ca[k], db = pb[i] - cb[k];
+        sw += w;
+        swa = fma(w, da, swa);
+        swb = fma(w, db, swb);
+        swaa = fma(w * da, da, swaa);
+        swab = fma(w * da, db, swab);
+      }
+      sw = warp_sum(sw);
+      swa = warp_sum(swa);
+      swb = warp_sum(swb);
+      swaa = warp_sum(swaa);
+      swab = warp_sum(swab);
+      GroupFit& g = gf[k];
+      g.W = sw;
+      double dma = swa / sw, dmb = swb / sw;
+      g.ma = ca[k] + dma;
+      g.mb = cb[k] + dmb;
+      g.sxx = swaa - swa * dma;
+      g.sxy = swab - swa * dmb;
+      g.slope = g.sxy / g.sxx;
+      g.icpt = g.mb - g.slope * g.ma;
+      for (int i = L.off[k] + lane; i < L.off[k] + L.cnt[k]; i += 32) {
+        double ro = r[i];
+        double rn = pb[i] - g.icpt - g.slope * pa[i];
+        double d = ro - rn;
+        diff = fma(d, d, diff);
+        old_ss = fma(ro, ro, old_ss);
+        r[i] = rn;
+      }
+    }
+    __syncwarp();
+    diff = warp_sum(diff);
+    old_ss = warp_sum(old_ss);
+    double conv = sqrt(diff / fmax(old_ss, 1e-20));  // irls.delta
+    if (conv <= 1e-4) {
+      done = true;
+      break;
+    }
+  }
+  if (it > 20) it = 20;
+  *iters_out = it;
+  if (zero_scale) {
+    *F_out = nan("");
+    *status_out = MDEGGS_EDGE_ZERO_SCALE;
+    return;
+  }
+  // ---- summary.rlm + Wald F of coefficient `tested_coef` (f.robftest) ----
+  double S = 0.0, npp = 0.0, sumw = 0.0;
+  double W2[2] = {0, 0}, wa2[2] = {0, 0}, waa2[2] = {0, 0};
+  for (int k = 0; k < 2; ++k) {
+    double sw = 0.0, swa = 0.0, swaa = 0.0;
+    for (int i = L.off[k] + lane; i < L.off[k] + L.cnt[k]; i += 32) {
+      double u = fabs(r[i] / scale);
+      double w = (u <= kh) ? 1.0 : kh / u;
+      double rw = r[i] * w;
+      S = fma(rw, rw, S);
+      npp += (u <= kh) ? 1.0 : 0.0;
+      double da = pa[i] - ca[k];
+      sw += w;
+      swa = fma(w, da, swa);
+      swaa = fma(w * da, da, swaa);
+    }
+    W2[k] = warp_sum(sw);
+    wa2[k] = warp_sum(swa);
+    waa2[k] = warp_sum(swaa);
+    sumw += W2[k];
+  }
+  S = warp_sum(S);
+  npp = warp_sum(npp);
+  const double rdf = (double)(n - 4);
+  S /= rdf;
+  const double mn = npp / (double)n;
+  const double var_pp = (double)n * mn * (1.0 - mn) / (double)(n - 1);
+  const double kappa = 1.0 + 4.0 * var_pp / ((double)n * mn * mn);
+  const double stddev = sqrt(S) * (kappa / mn);
+  double v_icpt[2], v_slope[2];
+  double cov_scale = 1.0;
+  if (cov_mode == MDEGGS_RLM_COV_XTWX) {
+    cov_scale = sumw / (double)n;  // X~ = X sqrt(w / mean(w))  =>  cov.unscaled = mean(w) (X'WX)^-1
+    for (int k = 0; k < 2; ++k) {
+      double dm = wa2[k] / W2[k];
+      double mk = ca[k] + dm, sx = waa2[k] - wa2[k] * dm;
+      v_icpt[k] = 1.0 / W2[k] + mk * mk / sx;
+      v_slope[k] = 1.0 / sx;
+    }
+  } else {
+    for (int k = 0; k < 2; ++k) {
+      double sx = sxa[k];
+      v_icpt[k] = 1.0 / (double)L.cnt[k] + ca[k] * ca[k] / sx;
+      v_slope[k] = 1.0 / sx;
+    }
+  }
+  beta[0] = gf[0].icpt;
+  beta[1] = gf[0].slope;
+  beta[2] = gf[1].icpt - gf[0].icpt;
+  beta[3] = gf[1].slope - gf[0].slope;
+  double cov[4] = {v_icpt[0], v_slope[0], v_icpt[0] + v_icpt[1], v_slope[0] + v_slope[1]};
+  const int v = tested_coef - 1;
+  const double var_v = stddev * stddev * cov_scale * cov[v];
+  *F_out = beta[v] * beta[v] / var_v;
+  *status_out = done ? MDEGGS_EDGE_OK : MDEGGS_EDGE_NOT_CONVERGED;
+}
+
 template <bool CACHE_AB>
 __global__ void __launch_bounds__(256) k_fit_rlm(const double* __restrict__ D, SegLayout L,
                                                  const int32_t* __restrict__ ea, const int32_t* __restrict__ eb,
@@ -79,8 +224,6 @@ __global__ void __launch_bounds__(256) k_fit_rlm(const double* __restrict__ D, S
   double* r = smem + (size_t)wib * per_warp;
   double* sa = CACHE_AB ? r + L.npad : nullptr;
   double* sb = CACHE_AB ? r + 2 * L.npad : nullptr;
-  const double kh = 1.345;
-  const int n = L.n;
   for (int64_t e = e_lo + (int64_t)blockIdx.x * wpb + wib; e < e_hi; e += (int64_t)gridDim.x * wpb) {
     const int a = ea[e], b = eb[e];
     auto put = [&](double st_v, int code, int it) {
@@ -125,133 +268,17 @@ __global__ void __launch_bounds__(256) k_fit_rlm(const double* __restrict__ D, S
       put(0.0, MDEGGS_EDGE_SELFLOOP, 0);
       continue;
     }
-    GroupFit gf[2];
-    // ---- init = "ls": ordinary least squares residuals ----
-    for (int k = 0; k < 2; ++k) {
-      double acc = 0.0;
-      for (int i = L.off[k] + lane; i < L.off[k] + L.cnt[k]; i += 32) acc = fma(pa[i] - ca[k], pb[i] - cb[k], acc);
-      acc = warp_sum(acc);
-      gf[k].W = (double)L.cnt[k];
-      gf[k].ma = ca[k];
-      gf[k].mb = cb[k];
-      gf[k].sxx = sxx[(size_t)a * 2 + k];
-      gf[k].sxy = acc;
-      gf[k].slope = acc / gf[k].sxx;
-      gf[k].icpt = cb[k] - gf[k].slope * ca[k];
-      for (int i = L.off[k] + lane; i < L.off[k] + L.cnt[k]; i += 32) r[i] = pb[i] - gf[k].icpt - gf[k].slope * pa[i];
+    double F, beta[4];
+    int st_code, it;
+    {
+      const double sxa[2] = {sxx[(size_t)a * 2], sxx[(size_t)a * 2 + 1]};
+      rlm_irls_warp(pa, pb, r, L, ca, cb, sxa, tested_coef, cov_mode, s_cand[wib], lane, &F, &st_code, &it, beta);
     }
-    __syncwarp();
-    double scale = 0.0;
-    bool done = false, zero_scale = false;
-    int it = 0;
-    for (it = 1; it <= 20; ++it) {
-      scale = warp_median_abs(r, L, lane, s_cand[wib]) / 0.6745;
-      if (scale == 0.0) {
-        zero_scale = true;
-        done = true;
-        break;
-      }
-      double diff = 0.0, old_ss = 0.0;
-      for (int k = 0; k < 2; ++k) {
-        double sw = 0.0, swa = 0.0, swb = 0.0, swaa = 0.0, swab = 0.0;
-        for (int i = L.off[k] + lane; i < L.off[k] + L.cnt[k]; i += 32) {
-          double u = fabs(r[i] / scale);
-          double w = (u <= kh) ? 1.0 : kh / u;  // psi.huber weight pmin(1, k/|u|)
-          double da = pa[i] - ca[k], db = pb[i] - cb[k];
-          sw += w;
-          swa = fma(w, da, swa);
-          swb = fma(w, db, swb);
-          swaa = fma(w * da, da, swaa);
-          swab = fma(w * da, db, swab);
-        }
-        sw = warp_sum(sw);
-        swa = warp_sum(swa);
-        swb = warp_sum(swb);
-        swaa = warp_sum(swaa);
-        swab = warp_sum(swab);
-        GroupFit& g = gf[k];
-        g.W = sw;
-        double dma = swa / sw, dmb = swb / sw;
-        g.ma = ca[k] + dma;
-        g.mb = cb[k] + dmb;
-        g.sxx = swaa - swa * dma;
-        g.sxy = swab - swa * dmb;
-        g.slope = g.sxy / g.sxx;
-        g.icpt = g.mb - g.slope * g.ma;
-        for (int i = L.off[k] + lane; i < L.off[k] + L.cnt[k]; i += 32) {
-          double ro = r[i];
-          double rn = pb[i] - g.icpt - g.slope * pa[i];
-          double d = ro - rn;
-          diff = fma(d, d, diff);
-          old_ss = fma(ro, ro, old_ss);
-          r[i] = rn;
-        }
-      }
-      __syncwarp();
-      diff = warp_sum(diff);
-      old_ss = warp_sum(old_ss);
-      double conv = sqrt(diff / fmax(old_ss, 1e-20));  // irls.delta
-      if (conv <= 1e-4) {
-        done = true;
-        break;
-      }
-    }
-    if (it > 20) it = 20;
-    if (zero_scale) {
+    if (st_code == MDEGGS_EDGE_ZERO_SCALE) {
       put(nan(""), MDEGGS_EDGE_ZERO_SCALE, it);
       continue;
     }
-    // ---- summary.rlm + Wald F of coefficient `tested_coef` (f.robftest) ----
-    double S = 0.0, npp = 0.0, sumw = 0.0;
-    double W2[2] = {0, 0}, wa2[2] = {0, 0}, waa2[2] = {0, 0};
-    for (int k = 0; k < 2; ++k) {
-      double sw = 0.0, swa = 0.0, swaa = 0.0;
-      for (int i = L.off[k] + lane; i < L.off[k] + L.cnt[k]; i += 32) {
-        double u = fabs(r[i] / scale);
-        double w = (u <= kh) ? 1.0 : kh / u;
-        double rw = r[i] * w;
-        S = fma(rw, rw, S);
-        npp += (u <= kh) ? 1.0 : 0.0;
-        double da = pa[i] - ca[k];
-        sw += w;
-        swa = fma(w, da, swa);
-        swaa = fma(w * da, da, swaa);
-      }
-      W2[k] = warp_sum(sw);
-      wa2[k] = warp_sum(swa);
-      waa2[k] = warp_sum(swaa);
-      sumw += W2[k];
-    }
-    S = warp_sum(S);
-    npp = warp_sum(npp);
-    const double rdf = (double)(n - 4);
-    S /= rdf;
-    const double mn = npp / (double)n;
-    const double var_pp = (double)n * mn * (1.0 - mn) / (double)(n - 1);
-    const double kappa = 1.0 + 4.0 * var_pp / ((double)n * mn * mn);
-    const double stddev = sqrt(S) * (kappa / mn);
-    double v_icpt[2], v_slope[2];
-    double cov_scale = 1.0;
-    if (cov_mode == MDEGGS_RLM_COV_XTWX) {
-      cov_scale = sumw / (double)n;  // X~ = X sqrt(w / mean(w))  =>  cov.unscaled = mean(w) (X'WX)^-1
-      for (int k = 0; k < 2; ++k) {
-        double dm = wa2[k] / W2[k];
-        double mk = ca[k] + dm, sx = waa2[k] - wa2[k] * dm;
-        v_icpt[k] = 1.0 / W2[k] + mk * mk / sx;
-        v_slope[k] = 1.0 / sx;
-      }
-    } else {
-      for (int k = 0; k < 2; ++k) {
-        double sx = sxx[(size_t)a * 2 + k];
-        v_icpt[k] = 1.0 / (double)L.cnt[k] + ca[k] * ca[k] / sx;
-        v_slope[k] = 1.0 / sx;
-      }
-    }
-    double beta[4] = {gf[0].icpt, gf[0].slope, gf[1].icpt - gf[0].icpt, gf[1].slope - gf[0].slope};
-    double cov[4] = {v_icpt[0], v_slope[0], v_icpt[0] + v_icpt[1], v_slope[0] + v_slope[1]};
-    const int v = tested_coef - 1;
-    const double var_v = stddev * stddev * cov_scale * cov[v];
-    const double F = beta[v] * beta[v] / var_v;
+    const bool done = st_code == MDEGGS_EDGE_OK;
     if (lane == 0) {
       stat[e] = F;
       status[e] = done ? MDEGGS_EDGE_OK : MDEGGS_EDGE_NOT_CONVERGED;

@@ -456,7 +456,7 @@ int orc_fit_aov(const double* a, const double* b, const int32_t* grp, int n, int
   *f_out = NAN;
   *p_out = NAN;
   for (int j = 0; j < 2 * K; ++j) coef[j] = NAN;
-  if (any_nonfinite(a, b, n)) return MDEGGS_EDGE_NONFINITE; /* documented deviation: model.frame would drop rows */
+  if (any_nonfinite(a, b, n)) return MDEGGS_EDGE_NONFINITE; /* (NA rows were dropped by the caller, orc_edge: an Inf is left) */
   /* levels without samples in this omic (quirk q2) give all-zero, aliased columns that lm() pivots out:
    * the test is the one of the Ke non-empty levels, df (Ke-1, n-2Ke) */
   int lev[MDEGGS_MAX_K], Ke = 0, cnt[MDEGGS_MAX_K] = {0};
@@ -759,14 +759,23 @@ static inline double assay_at(const mdeggs_problem* in, int64_t g, int64_t s) {
   return in->layout == MDEGGS_LAYOUT_COLMAJOR ? in->assay[g + s * in->ld] : in->assay[g * in->ld + s];
 }
 
+static int orc_fit_edge_n(const mdeggs_problem* in, int n_eff, const double* rowA, const double* rowB, const double* g01,
+                          const int32_t* grp0, double* ws, double* coef, double* stat, double* p, int* iters);
+
 int mdeggs_oracle_fit_edge(const mdeggs_problem* in, const double* rowA, const double* rowB, const double* g01,
                            const int32_t* grp0, double* ws, double* coef, double* stat, double* p, int* iters) {
+  return orc_fit_edge_n(in, in->n, rowA, rowB, g01, grp0, ws, coef, stat, p, iters);
+}
+
+/* the pair test on n_eff samples (all of them, or the complete cases of the pair) */
+static int orc_fit_edge_n(const mdeggs_problem* in, int n_eff, const double* rowA, const double* rowB, const double* g01,
+                          const int32_t* grp0, double* ws, double* coef, double* stat, double* p, int* iters) {
   *iters = 0;
   if (in->K == 2) {
-    if (in->method == MDEGGS_METHOD_LM) return orc_fit_lm_interaction(rowA, rowB, g01, in->n, ws, coef, stat, p);
-    return orc_fit_rlm(rowA, rowB, g01, in->n, in->tested_coef, in->rlm_cov_mode, ws, coef, stat, p, iters);
+    if (in->method == MDEGGS_METHOD_LM) return orc_fit_lm_interaction(rowA, rowB, g01, n_eff, ws, coef, stat, p);
+    return orc_fit_rlm(rowA, rowB, g01, n_eff, in->tested_coef, in->rlm_cov_mode, ws, coef, stat, p, iters);
   }
-  return orc_fit_aov(rowA, rowB, grp0, in->n, in->K, ws, coef, stat, p);
+  return orc_fit_aov(rowA, rowB, grp0, n_eff, in->K, ws, coef, stat, p);
 }
 
 static int response_is_constant(const double* y, const int32_t* grp0, int n, int K) {
@@ -780,6 +789,75 @@ static int response_is_constant(const double* y, const int32_t* grp0, int n, int
   }
   (void)K;
   return 1;
+}
+
+/* One edge as calc_pvalues_network's vapply body sees it (core_functions.R:869-997), including what happens to
+ * missing values: fit_lm_interaction hands the rows to .lm.fit as they are ("NA/NaN/Inf in 'x'": the error takes the
+ * percentile or the omic down, quirk q3), whereas rlm(B ~ A * metadata) and aov(B ~ A * metadata)
+ * (core_functions.R:916-917, 966-967) build a model frame first: na.action = na.omit drops the samples where either
+ * gene is NA/NaN FOR THIS PAIR, and the fit, its residual degrees of freedom and the tail probability use the n' samples
+ * left.  An Inf that survives still makes lm.fit / lm.wfit throw.  scratch: 3 n doubles + n int32 behind ws. */
+static int orc_edge(const mdeggs_problem* in, int self_loop, const double* ra, const double* rb, const double* g01,
+                    const int32_t* grp0, double* ws, size_t ws_len, double* coef, double* stat, double* p, int* iters) {
+  const int n = in->n, K = in->K, ncoef = 2 * K;
+  const int pairwise = !(K == 2 && in->method == MDEGGS_METHOD_LM);
+  *iters = 0;
+  int n_na = 0;
+  if (pairwise && !self_loop)
+    for (int i = 0; i < n; ++i) n_na += (isnan(ra[i]) || isnan(rb[i]));
+  if (self_loop || (n_na == 0 && response_is_constant(rb, grp0, n, K))) {
+    /* exact fit (self-loop / constant response): R's t is rounding noise; documented deviation shared with the
+     * engine: p = 1, stat = 0.  A singular design still fails first when K == 2: solve() / rlm() throw on the
+     * predictor alone (core_functions.R:1068, 916), whatever the response is. */
+    if (!self_loop && K == 2 && orc_fit_edge_n(in, n, ra, rb, g01, grp0, ws, coef, stat, p, iters) == MDEGGS_EDGE_SINGULAR) {
+      *iters = 0;
+      return MDEGGS_EDGE_SINGULAR;
+    }
+    *iters = 0;
+    *stat = 0.0;
+    *p = 1.0;
+    for (int j = 0; j < ncoef; ++j) coef[j] = NAN;
+    return MDEGGS_EDGE_SELFLOOP;
+  }
+  if (n_na == 0) return orc_fit_edge_n(in, n, ra, rb, g01, grp0, ws, coef, stat, p, iters);
+  /* complete cases of this pair */
+  double* a2 = ws + ws_len;
+  double* b2 = a2 + n;
+  double* g2 = b2 + n;
+  int32_t* grp2 = (int32_t*)(g2 + n);
+  int m = 0;
+  for (int i = 0; i < n; ++i) {
+    if (isnan(ra[i]) || isnan(rb[i])) continue;
+    a2[m] = ra[i];
+    b2[m] = rb[i];
+    g2[m] = g01[i];
+    grp2[m] = grp0[i];
+    ++m;
+  }
+  *stat = NAN;
+  *p = NAN;
+  for (int j = 0; j < ncoef; ++j) coef[j] = NAN;
+  int Ke = 0, cnt[MDEGGS_MAX_K] = {0};
+  for (int i = 0; i < m; ++i) cnt[grp2[i]]++;
+  for (int k = 0; k < K; ++k) Ke += cnt[k] > 0;
+  /* no complete case, a single level left ("contrasts can be applied only to factors with 2 or more levels"), or no
+   * residual degree of freedom: the call fails / has no F row -> hard failure like any other error of the pair */
+  if (m == 0 || Ke < 2 || m <= 2 * Ke) return MDEGGS_EDGE_SINGULAR;
+  if (K == 2 && (cnt[0] == 0 || cnt[1] == 0)) return MDEGGS_EDGE_SINGULAR;
+  if (response_is_constant(b2, grp2, m, K)) {
+    if (K == 2 && orc_fit_edge_n(in, m, a2, b2, g2, grp2, ws, coef, stat, p, iters) == MDEGGS_EDGE_SINGULAR) {
+      *iters = 0;
+      return MDEGGS_EDGE_SINGULAR;
+    }
+    *iters = 0;
+    *stat = 0.0;
+    *p = 1.0;
+    for (int j = 0; j < ncoef; ++j) coef[j] = NAN;
+    return MDEGGS_EDGE_SELFLOOP;
+  }
+  int st = orc_fit_edge_n(in, m, a2, b2, g2, grp2, ws, coef, stat, p, iters);
+  if (st == MDEGGS_EDGE_OK) st = MDEGGS_EDGE_NA_OMIT; /* soft: valid p on this pair's own degrees of freedom */
+  return st;
 }
 
 int mdeggs_oracle_run_omic(const mdeggs_problem* in, mdeggs_result* out, int mode, int nthreads) {
@@ -852,6 +930,7 @@ int mdeggs_oracle_run_omic(const mdeggs_problem* in, mdeggs_result* out, int mod
   }
   const int ncoef = 2 * K;
   const size_t ws_len = (size_t)(2 * K + 8) * (size_t)n;
+  const size_t ws_alloc = ws_len + 4 * (size_t)n; /* + complete-case copies of a pair (orc_edge) */
   if (out->df) {
     if (K == 2) {
       out->df[0] = 1.0;
@@ -872,7 +951,7 @@ int mdeggs_oracle_run_omic(const mdeggs_problem* in, mdeggs_result* out, int mod
                     out->iters || out->coef;
 #pragma omp parallel num_threads(nthreads) if (need_unique)
   {
-    double* ws = (double*)malloc(sizeof(double) * ws_len);
+    double* ws = (double*)malloc(sizeof(double) * ws_alloc);
     double coef[2 * MDEGGS_MAX_K];
 #pragma omp for schedule(dynamic, 64)
     for (int64_t e = 0; e < (need_unique ? E : 0); ++e) {
@@ -881,17 +960,7 @@ int mdeggs_oracle_run_omic(const mdeggs_problem* in, mdeggs_result* out, int mod
       double stat, p;
       int iters;
       int st;
-      if (in->from[e] == in->to[e] || response_is_constant(rb, grp0, n, K)) {
-        /* exact fit (self-loop / constant response): R's t is rounding noise; documented deviation shared
-         * with the engine: p = 1, stat = 0 */
-        st = MDEGGS_EDGE_SELFLOOP;
-        stat = 0.0;
-        p = 1.0;
-        iters = 0;
-        for (int j = 0; j < ncoef; ++j) coef[j] = NAN;
-      } else {
-        st = mdeggs_oracle_fit_edge(in, ra, rb, g01, grp0, ws, coef, &stat, &p, &iters);
-      }
+      st = orc_edge(in, in->from[e] == in->to[e], ra, rb, g01, grp0, ws, ws_len, coef, &stat, &p, &iters);
       p_edge[e] = p;
       st_edge[e] = st;
       if (out->p_edge) out->p_edge[e] = p;
@@ -944,7 +1013,7 @@ int mdeggs_oracle_run_omic(const mdeggs_problem* in, mdeggs_result* out, int mod
     tot[pi] = te;
     fail[pi] = nfail;
     int64_t nsig = 0;
-    double* ws = (double*)malloc(sizeof(double) * ws_len);
+    double* ws = (double*)malloc(sizeof(double) * ws_alloc);
     for (int k = 1; k <= K; ++k) {
       int64_t m = 0;
       for (int64_t e = 0; e < E; ++e) m += (cat[e] == k);
@@ -960,10 +1029,7 @@ int mdeggs_oracle_run_omic(const mdeggs_problem* in, mdeggs_result* out, int mod
           const double* rb = rows + (int64_t)node_of[in->to[e] - 1] * n;
           double coef[2 * MDEGGS_MAX_K], stat, p;
           int iters;
-          int st = MDEGGS_EDGE_SELFLOOP;
-          p = 1.0;
-          if (in->from[e] != in->to[e] && !response_is_constant(rb, grp0, n, K))
-            st = mdeggs_oracle_fit_edge(in, ra, rb, g01, grp0, ws, coef, &stat, &p, &iters);
+          int st = orc_edge(in, in->from[e] == in->to[e], ra, rb, g01, grp0, ws, ws_len, coef, &stat, &p, &iters);
           if (!need_unique && (st == MDEGGS_EDGE_SINGULAR || st == MDEGGS_EDGE_NONFINITE)) ++fail[pi];
           pv[j++] = p;
         } else {

@@ -49,6 +49,51 @@ def test_random_rlm(engine, oracle, G, n, E, seed, coef, cov):
     assert_parity(gpu, ref, prob, rtol=1e-8, what=f"rlm G{G} n{n}: ")
 
 
+def _na_problem(K, method, padj, seed, G=60, n=96, E=400):
+    """random problem with missing values in a quarter of the rows, one row with an Inf as well, and one category of one
+    row reduced to a single complete case (rlm: singular, aov: aliased / fewer levels)"""
+    prob = synth.random_problem(G, n, E, K, seed, method, padj, min_per_group=14)
+    rng = np.random.default_rng(seed + 1000)
+    v = prob.assay
+    na_rows = rng.choice(G, size=G // 4, replace=False)
+    for g in na_rows:
+        v[g, rng.choice(n, size=int(rng.integers(1, 10)), replace=False)] = np.nan
+    v[int(na_rows[0]), 1] = np.inf
+    cols = np.flatnonzero(prob.group == 1)
+    v[int(na_rows[1]), cols[1:]] = np.nan
+    v[int(na_rows[2]), cols] = np.nan                       # a whole category missing for this gene
+    v[int(na_rows[3]), :] = np.nan                          # an all-NA row: no complete case
+    return prob
+
+
+@pytest.mark.parametrize("K,method", [(3, _abi.METHOD_LM), (5, _abi.METHOD_LM), (2, _abi.METHOD_RLM), (2, _abi.METHOD_LM)])
+@pytest.mark.parametrize("padj", [_abi.PADJ_BH, _abi.PADJ_BONFERRONI])
+def test_pairwise_na_removal(engine, oracle, K, method, padj):
+    """rlm() / aov() drop, per pair, the samples where either gene is NA (model.frame, core_functions.R:916-917,
+    966-967) and test on the complete cases; fit_lm_interaction (K == 2, lm) errors instead (core_functions.R:1065)."""
+    prob = _na_problem(K, method, padj, 300 + K)
+    gpu, ref = _both(engine, oracle, prob)
+    assert_parity(gpu, ref, prob, rtol=1e-8 if method == _abi.METHOD_RLM else 1e-9, what=f"NA K{K} m{method}: ")
+    st = ref["status"]
+    if K == 2 and method == _abi.METHOD_LM:
+        assert (st == _abi.EDGE_NONFINITE).sum() > 50 and not (st == _abi.EDGE_NA_OMIT).any()
+    else:
+        assert (st == _abi.EDGE_NA_OMIT).sum() > 50 and (st == _abi.EDGE_NONFINITE).any() and (st == _abi.EDGE_SINGULAR).any()
+        assert np.all(np.isfinite(ref["p_edge"][st == _abi.EDGE_NA_OMIT]))
+
+
+def test_pairwise_na_removal_dense_path_and_sharded_queue(oracle):
+    """same through the dense tile moments (src 1 of k_finish) and with the K8 radix-sort ordering"""
+    prob = _na_problem(3, _abi.METHOD_LM, _abi.PADJ_BH, 411, G=48, n=64, E=900)
+    ref = oracle.run_omic(prob, ALL_FIELDS)
+    eng = md.Engine([0])
+    for opt, val in (("fit_path", 1), ("sort_path", 0), ("front_path", 0), ("bh_onepass", 0)):
+        eng.set_option(opt, val)
+        gpu = eng.run_omic(prob, ALL_FIELDS)
+        assert_parity(gpu, ref, prob, what=f"NA {opt}={val}: ")
+    eng.close()
+
+
 def test_row_major_layout_matches_col_major(engine):
     a = synth.random_problem(50, 40, 120, 2, 31)
     b = synth.random_problem(50, 40, 120, 2, 31, row_major=True)

@@ -207,6 +207,71 @@ def test_aov_with_aliased_interaction_columns(oracle):
     assert st == _abi.EDGE_OK and not np.any(np.isnan(coef))
 
 
+@pytest.mark.parametrize("K,method", [(3, _abi.METHOD_LM), (4, _abi.METHOD_LM), (2, _abi.METHOD_RLM), (2, _abi.METHOD_LM)])
+def test_pairwise_na_removal_like_model_frame(oracle, K, method):
+    """rlm(B ~ A * metadata) and aov(B ~ A * metadata) (core_functions.R:916-917, 966-967) build a model frame:
+    na.omit drops, per pair, the samples where either gene is NA, and the test uses the complete cases and THEIR degrees
+    of freedom; fit_lm_interaction (core_functions.R:1065) hands NA to .lm.fit, which throws.  The oracle's complete-case
+    route is checked against the independent twin run on the complete cases."""
+    prob = synth.random_problem(40, 90, 160, K, 77 + K, method, _abi.PADJ_BH, min_per_group=12)
+    rng = np.random.default_rng(5)
+    v = prob.assay
+    na_rows = rng.choice(40, size=12, replace=False)
+    for g in na_rows:
+        v[g, rng.choice(90, size=int(rng.integers(1, 9)), replace=False)] = np.nan
+    inf_row = int(na_rows[0])
+    v[inf_row, 0] = np.inf                                   # an Inf is not dropped: lm.fit / lm.wfit throw
+    one = int(na_rows[1])                                    # a category that keeps a single complete case
+    cols = np.flatnonzero(prob.group == 1)
+    v[one, cols[1:]] = np.nan
+    res = oracle.run_omic(prob, ("p_edge", "stat", "status", "iters", "fail_count", "tot_edges", "cat"))
+    fr, to = prob.from_idx - 1, prob.to_idx - 1
+    touched = np.isnan(v[fr]).any(axis=1) | np.isnan(v[to]).any(axis=1)
+    assert touched.sum() > 30
+    st = res["status"]
+    if K == 2 and method == _abi.METHOD_LM:
+        assert np.all(st[touched] == _abi.EDGE_NONFINITE) and np.all(np.isnan(res["p_edge"][touched]))
+        return
+    has_inf = np.isinf(v[fr]).any(axis=1) | np.isinf(v[to]).any(axis=1)
+    seen = set()
+    for e in np.flatnonzero(touched):
+        a, b = v[fr[e]], v[to[e]]
+        keep = ~(np.isnan(a) | np.isnan(b))
+        a2, b2, g2 = a[keep], b[keep], prob.group[keep] - 1
+        if np.isinf(a2).any() or np.isinf(b2).any():
+            assert st[e] == _abi.EDGE_NONFINITE and np.isnan(res["p_edge"][e])
+            seen.add("inf")
+            continue
+        cnt = np.bincount(g2, minlength=K)
+        if K == 2 and (cnt < 2).any():
+            assert st[e] == _abi.EDGE_SINGULAR, (e, cnt)     # rlm: "'x' is singular"
+            seen.add("singular")
+            continue
+        if K >= 3:
+            # lm() drops the unused levels of the complete cases (drop.unused.levels = TRUE): renumber them
+            lev = np.flatnonzero(cnt > 0)
+            g3 = np.searchsorted(lev, g2)
+            _, f2, p2 = oracle_np.aov_interaction(a2, b2, g3, len(lev))
+            assert st[e] in (_abi.EDGE_NA_OMIT, _abi.EDGE_ALIASED), (e, st[e])
+            seen.add(int(st[e]))
+            assert abs(res["stat"][e] - f2) <= 1e-9 * abs(f2) and abs(res["p_edge"][e] - p2) <= 1e-9 * p2, e
+        else:
+            _, f2, p2, it2 = oracle_np.rlm_wald(a2, b2, g2.astype(float), 3, "XtWX")
+            assert st[e] in (_abi.EDGE_NA_OMIT, _abi.EDGE_NOT_CONVERGED)
+            seen.add(int(st[e]))
+            assert res["iters"][e] == it2
+            assert abs(res["stat"][e] - f2) <= 1e-8 * abs(f2) and abs(res["p_edge"][e] - p2) <= 1e-7 * p2, e
+    assert _abi.EDGE_NA_OMIT in seen and "inf" in seen
+    assert has_inf.any()
+    # untouched pairs keep the run's degrees of freedom and status
+    assert np.all(np.isin(st[~touched], (_abi.EDGE_OK, _abi.EDGE_SELFLOOP, _abi.EDGE_NOT_CONVERGED)))
+    # soft statuses never count as failures
+    hard = np.isin(st, (_abi.EDGE_SINGULAR, _abi.EDGE_NONFINITE))
+    P, E = len(prob.pct), len(fr)
+    cat = res["cat"].reshape(P, E)
+    assert np.array_equal(res["fail_count"], ((cat != 0) & hard[None, :]).sum(axis=1))
+
+
 @pytest.mark.parametrize("method", ["none", "bonferroni", "BH", "holm", "hochberg", "BY"])
 def test_p_adjust_three_ways(oracle, method):
     rng = np.random.default_rng(11)
