@@ -11,6 +11,7 @@
 // Only tile pairs with ti <= tj are computed (Sxy is symmetric); k_finish (src 1) then finishes each edge
 // from Sxy[min(a,b)][max(a,b)] with the same closed forms as the streaming path (finish_pair).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -220,6 +221,198 @@ __global__ void __launch_bounds__(DTHREADS, 1) k_dense_moments(const double* __r
     }
   }
 #endif
+}
+
+// ------------------------------------------------------------------------------------------------
+// TMA-fed form of the same kernel (the one the engine launches; the cp.async form above stays as the fallback for a
+// driver without cuTensorMapEncodeTiled).
+//
+// Operands come from Dc, a CENTRED gene-major copy of D written by k_center_rows: Dc[node][npadc], every category
+// segment starting on a multiple of DS samples and padded with zeros (x - mean = 0 adds nothing to a cross moment), so
+//   * a stage is two TMA boxes (DS samples x 128 genes of the row block and of the column block, 16 KB each; one on
+//     the diagonal), landing gene-major with the 128-byte hardware swizzle -- no per-thread loads, no transposition,
+//     no centring and no CTA barrier inside the sample loop: a producer warp keeps a ring of DSTAGES stages full
+//     (mbarrier full / empty pairs), the 8 MMA warps only wait on the stage they are about to read;
+//   * a lane fetches its A / B fragments as 16-byte pairs of consecutive samples (s, s + 1) of one gene: the .x halves
+//     feed one m8n8k4 step and the .y halves the next (a sum over samples does not care which four go together), i.e.
+//     12 LDS.128 per 64 MMAs, each at the 4-wavefront minimum thanks to the swizzle.
+// Multi-GPU: `tile_need[ti * ntiles + tj]` (k_mark_tiles over the rank's edge block) lets a CTA whose tile holds no
+// edge of this rank exit at once.
+// ------------------------------------------------------------------------------------------------
+constexpr int DS = 16;                      // samples per stage (128-byte rows: the SWIZZLE_128B span)
+constexpr int DSTAGES = 4;
+constexpr int DTILE_BYTES = DT * DS * 8;    // 16 KB per operand and stage
+constexpr int DENSE_TMA_SMEM = DSTAGES * 2 * DTILE_BYTES + 1024 + 2 * DSTAGES * 8 + 64;
+constexpr int DENSE_TMA_THREADS = 256 + 32;  // 8 MMA warps + the producer warp
+
+struct DenseLayout {  // layout of the centred copy
+  int K, npadc;
+  int off[MDEGGS_MAX_K + 1];  // multiples of DS
+};
+
+// Dc[node][Lc.off[k] + i] = D[node][L.off[k] + i] - mean[node][k] for i < cnt[k], 0 beyond; one warp per (node, k)
+__global__ void __launch_bounds__(256) k_center_rows(const double* __restrict__ D, SegLayout L, DenseLayout Lc,
+                                                     const double* __restrict__ mean,
+                                                     const int32_t* __restrict__ n_nodes_p, double* __restrict__ Dc) {
+  const int nn = *n_nodes_p;
+  const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= (long long)nn * L.K) return;
+  const int node = (int)(w / L.K), k = (int)(w - (long long)node * L.K);
+  const double mu = mean[(size_t)node * L.K + k];
+  const double2* __restrict__ src = reinterpret_cast<const double2*>(D + (size_t)node * L.npad + L.off[k]);
+  double2* __restrict__ dst = reinterpret_cast<double2*>(Dc + (size_t)node * Lc.npadc + Lc.off[k]);
+  const int m = L.cnt[k], len2 = (Lc.off[k + 1] - Lc.off[k]) >> 1, src2 = (L.off[k + 1] - L.off[k]) >> 1;
+  for (int i = lane; i < len2; i += 32) {
+    double2 v = make_double2(0.0, 0.0);
+    if (i < src2) {
+      const double2 x = __ldg(src + i);
+      v.x = 2 * i < m ? x.x - mu : 0.0;
+      v.y = 2 * i + 1 < m ? x.y - mu : 0.0;
+    }
+    dst[i] = v;
+  }
+}
+
+__device__ __forceinline__ uint32_t dn_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void dn_mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+
+__global__ void __launch_bounds__(DENSE_TMA_THREADS, 1)
+    k_dense_tma(const __grid_constant__ CUtensorMap tmap, DenseLayout Lc, SegLayout L, int nn, int ntiles,
+                const uint8_t* __restrict__ tile_need, double* __restrict__ S) {
+  extern __shared__ unsigned char dn_raw[];
+  int ti = 0, rem = blockIdx.x;
+  while (rem >= ntiles - ti) {
+    rem -= ntiles - ti;
+    ++ti;
+  }
+  const int tj = ti + rem;
+  if (tile_need && !tile_need[ti * ntiles + tj]) return;
+  const int k = blockIdx.y;
+  if (L.cnt[k] == 0) return;
+  const int seg_beg = Lc.off[k], nst = (Lc.off[k + 1] - Lc.off[k]) / DS;
+  const int i0 = ti * DT, j0 = tj * DT;
+  const bool diag = ti == tj;
+  unsigned char* base = dn_raw + ((1024u - (dn_smem_u32(dn_raw) & 1023u)) & 1023u);  // swizzle atoms are 1,024 bytes
+  const uint32_t sb = dn_smem_u32(base);
+  const uint32_t bar0 = sb + DSTAGES * 2 * DTILE_BYTES;  // full[DSTAGES], empty[DSTAGES]
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) {
+    for (int i = 0; i < DSTAGES; ++i) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8 * i), "r"(1u) : "memory");
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8 * (DSTAGES + i)), "r"(8u) : "memory");
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  if (wid == 8) {
+    // ===== producer =====
+    if (lane == 0) {
+      const uint32_t bytes = diag ? DTILE_BYTES : 2 * DTILE_BYTES;
+      for (int st = 0; st < nst; ++st) {
+        const int slot = st % DSTAGES, use = st / DSTAGES;
+        const uint32_t full = bar0 + 8 * slot, empty = bar0 + 8 * (DSTAGES + slot);
+        if (use > 0) dn_mbar_wait(empty, (uint32_t)(use - 1) & 1u);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "r"(bytes) : "memory");
+        const uint32_t dstA = sb + (uint32_t)slot * 2 * DTILE_BYTES;
+        const int c0 = seg_beg + st * DS;
+        asm volatile(
+            "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dstA),
+            "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(c0), "r"(i0), "r"(full)
+            : "memory");
+        if (!diag)
+          asm volatile(
+              "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                  dstA + DTILE_BYTES),
+              "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(c0), "r"(j0), "r"(full)
+              : "memory");
+      }
+    }
+    return;
+  }
+  // ===== MMA warps =====
+  const int wrow = (wid >> 1) * 32, wcol = (wid & 1) * 64;  // warp tile origin inside the CTA tile
+  const int fr = lane >> 2, fk = lane & 3;                  // fragment row / sample pair of this lane
+  // byte offset of this lane's 16-byte pair inside a 128-byte gene row, per 8-sample half h: chunk (4 h + fk) ^ (gene & 7)
+  const uint32_t swz0 = (uint32_t)((fk ^ fr) << 4), swz1 = (uint32_t)(((4 + fk) ^ fr) << 4);
+  const uint32_t rowA = (uint32_t)(wrow + fr) * 128u, rowB = (uint32_t)(wcol + fr) * 128u + (diag ? 0u : (uint32_t)DTILE_BYTES);
+  double acc[4][8][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+  for (int st = 0; st < nst; ++st) {
+    const int slot = st % DSTAGES, use = st / DSTAGES;
+    dn_mbar_wait(bar0 + 8 * slot, (uint32_t)use & 1u);
+    const uint32_t stg = sb + (uint32_t)slot * 2 * DTILE_BYTES;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const uint32_t sw = h ? swz1 : swz0;
+      double2 a[4], b[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a[i].x), "=d"(a[i].y) : "r"(stg + rowA + (uint32_t)i * 1024u + sw));
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(b[j].x), "=d"(b[j].y) : "r"(stg + rowB + (uint32_t)j * 1024u + sw));
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                       : "+d"(acc[i][j][0]), "+d"(acc[i][j][1])
+                       : "d"(a[i].x), "d"(b[j].x));
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                       : "+d"(acc[i][j][0]), "+d"(acc[i][j][1])
+                       : "d"(a[i].y), "d"(b[j].y));
+    }
+    __syncwarp();
+    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar0 + 8 * (DSTAGES + slot)) : "memory");
+  }
+  double* Sk = S + (size_t)k * nn * nn;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = i0 + wrow + 8 * i + fr;
+    if (r >= nn) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = j0 + wcol + 8 * j + 2 * fk;
+      if (c + 1 < nn && !(nn & 1)) {  // 16-byte aligned only when the row pitch is even
+        *reinterpret_cast<double2*>(Sk + (size_t)r * nn + c) = make_double2(acc[i][j][0], acc[i][j][1]);
+      } else {
+        if (c < nn) Sk[(size_t)r * nn + c] = acc[i][j][0];
+        if (c + 1 < nn) Sk[(size_t)r * nn + c + 1] = acc[i][j][1];
+      }
+    }
+  }
+}
+
+// multi-GPU: the 128 x 128 tiles of S that hold an edge of this rank's block
+__global__ void k_mark_tiles(const int32_t* __restrict__ ea, const int32_t* __restrict__ eb, int64_t e_lo, int64_t e_hi,
+                             int ntiles, uint8_t* __restrict__ tile_need, const int32_t* __restrict__ err) {
+  if (*err) return;
+  for (int64_t e = e_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < e_hi; e += (int64_t)gridDim.x * blockDim.x) {
+    const int a = ea[e], b = eb[e];
+    const int i = (a < b ? a : b) / DT, j = (a < b ? b : a) / DT;
+    uint8_t* t = tile_need + i * ntiles + j;
+    if (!*t) *t = 1;
+  }
 }
 
 // [min, max] over this rank's edges of the smaller node index of the edge: the rows of S it will read

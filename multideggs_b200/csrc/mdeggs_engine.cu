@@ -84,8 +84,12 @@ struct Shard {
     int64_t ld, rows;
     int n, gb, box1;
   } tmap_key = {nullptr, 0, 0, 0, 0, 0};
+  CUtensorMap dense_tmap;  // ... and of the centred copy Dc (k_dense_tma)
+  TmapKey dense_tmap_key = {nullptr, 0, 0, 0, 0, 0};
+  bool dense_tma_attr_set = false;
   bool select_fused = false;  // this call's percentile selection ran inside k_bh_final
   bool partials_complete = true;  // the all-percentile K8 left the tile carries behind (false: count-only pass)
+  bool tiles_complete = true;     // ... and the member counts of every tile (false: count-only pass that skipped tiles)
   bool best_rows_in_emit = false;  // this call's best-percentile rows are produced by k_emit (device callers)
   const double* best_row_src = nullptr;  // ... its p.adj row comes from row best-1 of this P x E matrix
   int64_t row_off = 0, ld_eff = 0;  // the device copy of the assay starts at host row `row_off`
@@ -103,11 +107,11 @@ struct Shard {
     if (e == cudaSuccess) h_stage_cap = bytes + 256;
     return e;
   }
-  DevBuf na_q, bh1_state, assay, from, to, ea, eb, stage_dev, bs_count, bs_slot, seg_done, seg_rank, fin_q, hm_p, hm_q1, hm_c, hm_sc, hm_idx, hm_off, seg_pi0, B16, stamps, excl, node_of_row, rowlist, scal, src_of_pos, pct, cutoff, D, cub_tmp, mean, sxx, med, bad, stat, status, p_edge, coef, iters, act, counters, sortk, sortk2, idx,
+  DevBuf Dc, tile_need, na_q, bh1_state, assay, from, to, ea, eb, stage_dev, bs_count, bs_slot, seg_done, seg_rank, fin_q, hm_p, hm_q1, hm_c, hm_sc, hm_idx, hm_off, seg_pi0, B16, stamps, excl, node_of_row, rowlist, scal, src_of_pos, pct, cutoff, D, cub_tmp, mean, sxx, med, bad, stat, status, p_edge, coef, iters, act, counters, sortk, sortk2, idx,
       idx2, ps, sa, sb, tile_cnt, tile_base, seg_n, tile_min, tile_carry, padj_best, cat_best, cat, padj, med_out,
       small_out, rsel_hist, rsel_state, rsel_cand, dense_S, cf_tab, sxy;
   void release_all() {
-    DevBuf* all[] = {&na_q, &bh1_state, &assay, &from, &to, &ea, &eb, &stage_dev, &bs_count, &bs_slot, &seg_done, &seg_rank, &fin_q, &hm_p, &hm_q1, &hm_c, &hm_sc, &hm_idx, &hm_off, &seg_pi0, &B16, &stamps, &excl, &node_of_row, &rowlist, &scal, &src_of_pos, &pct, &cutoff,
+    DevBuf* all[] = {&Dc, &tile_need, &na_q, &bh1_state, &assay, &from, &to, &ea, &eb, &stage_dev, &bs_count, &bs_slot, &seg_done, &seg_rank, &fin_q, &hm_p, &hm_q1, &hm_c, &hm_sc, &hm_idx, &hm_off, &seg_pi0, &B16, &stamps, &excl, &node_of_row, &rowlist, &scal, &src_of_pos, &pct, &cutoff,
                      &D, &cub_tmp, &mean, &sxx, &med, &bad, &stat, &status, &p_edge,
                      &coef, &iters, &act, &counters, &sortk, &sortk2, &idx, &idx2, &ps, &sa, &sb, &tile_cnt,
                      &tile_base, &seg_n, &tile_min, &tile_carry, &padj_best, &cat_best, &cat, &padj, &med_out,
@@ -148,10 +152,12 @@ struct mdeggs_ctx {
   int64_t rsel_cap_override = 0;  // option "rsel_cap": shrink the candidate list to exercise the overflow path (tests)
   int fit_path_override = -1;  // -1 auto, 0 force streaming, 1 force dense (MDEGGS_FIT_PATH, tests)
   int bh_onepass = 1;          // option "bh_onepass": 0 keeps the three-launch K8 for small edge lists too (tests)
+  int dense_path = -1;         // option "dense_path": 0 = the cp.async form of the dense moments kernel, else the TMA-fed one
   int front_path = -1;         // -1 auto, 0 separate K1 + K2 kernels, 1 fused (TMA when possible), 2 fused with the plain loader
   bool last_zc = false;        // the last call read its assay through zero copy
   int zero_copy = 0;           // option "zero_copy": pinned host assays are read by the gather straight over PCIe
   int64_t padj_keep_cap = (int64_t)256 << 20;  // option "padj_keep_cap": largest P x E x 8 scratch kept for the best row
+  int count_skip = 1;          // option "count_skip": 0 = the count-only K8 visits every tile of the p order (tests)
   int count_only_adjust = 1;   // option "count_only": 0 keeps the three-pass K8 even when no adjusted value is kept (tests)
   int sort_path_override = -1; // -1 auto, 0 force the CUB radix sort, 1 force the bucket ordering (option "sort_path")
   // MDEGGS_TRACE=1 / option "trace": an event after every eager launch, timeline printed to stderr after the call
@@ -443,7 +449,8 @@ SelArgs make_sel_args(Shard& s, const mdeggs_problem* in, const HostLayout& H, b
 // ---- BH / Bonferroni over a block of percentiles (or the device-chosen best one) -----------------
 int run_adjust(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, int n_segments, int p0, int p_stride,
                const int32_t* best_dev, unsigned long long* sig_dev, double* padj_out, int64_t padj_stride,
-               int act_stride, bool reuse_tiles = false, const SelArgs* sel = nullptr, bool redo_minima = false) {
+               int act_stride, bool reuse_tiles = false, const SelArgs* sel = nullptr, bool redo_minima = false,
+               double skip_thr = 0.0) {
   if (n_segments <= 0) return MDEGGS_OK;
   const int64_t E = in->E;
   const int ntiles = (int)((E + BH_TILE - 1) / BH_TILE);
@@ -466,6 +473,9 @@ int run_adjust(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, int n_segmen
   A.reuse_tiles = reuse_tiles ? 1 : 0;
   CU(s.seg_pi0.ensure((size_t)in->P * in->K * 8));
   A.seg_pi0 = s.seg_pi0.as<double>();
+  A.skip_thr = 0.0;
+  A.seg_cnt = nullptr;
+  A.seg_low = nullptr;
   dim3 grid((unsigned)ntiles, (unsigned)n_segments);
   // per-segment "CTAs done" counters of the fused tile passes: zero when first allocated, re-armed by the kernels
   {
@@ -482,9 +492,15 @@ int run_adjust(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, int n_segmen
                           in->padj != MDEGGS_PADJ_HOMMEL;
   if (count_only) {
     const size_t need = (size_t)in->P * in->K * sizeof(unsigned long long);
-    if (need > s.seg_rank.cap) {
-      CU(s.seg_rank.ensure(need));
+    if (2 * need > s.seg_rank.cap) {  // [P x K] rank accumulators (zero between launches), then [P x K] seg_low
+      CU(s.seg_rank.ensure(2 * need));
       CU(cudaMemsetAsync(s.seg_rank.p, 0, s.seg_rank.cap, s.s_main));
+    }
+    if (skip_thr > 0.0 && in->padj != MDEGGS_PADJ_QVALUE) {  // (q.value scales by pi0 <= 1: its q can fall below p)
+      const int Pn = in->P > 0 ? in->P : 1;
+      A.skip_thr = skip_thr;
+      A.seg_cnt = reinterpret_cast<const unsigned int*>(s.counters.as<char>() + (size_t)Pn * 8 * 7 + 8);
+      A.seg_low = s.seg_rank.as<long long>() + (size_t)in->P * in->K;
     }
   }
   const bool simple_mode = in->padj == MDEGGS_PADJ_BONFERRONI || in->padj == MDEGGS_PADJ_BH || in->padj == MDEGGS_PADJ_BY ||
@@ -1054,11 +1070,20 @@ int run_shard_main(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
         return MDEGGS_EUNSUPPORTED;
       }
     } else if (use_dense) {
-      // one GPU: all upper-triangular tile pairs; several: only the tile rows this rank's edge block reads (d_range)
+      // one GPU: all upper-triangular tile pairs; several: only the tiles that hold an edge of this rank's block
       const int ntl = (n_nodes + DT - 1) / DT;
       dim3 grid((unsigned)(ntl * (ntl + 1) / 2), (unsigned)K);
+      const bool tma = ctx->dense_path != 0 && tmap_encoder() != nullptr;
+      const uint8_t* d_need = nullptr;
       const int32_t* d_range = nullptr;
-      if (s.world > 1) {  // this rank only computes the tile rows its contiguous edge block reads
+      if (s.world > 1 && tma) {
+        CU(s.tile_need.ensure((size_t)ntl * ntl));
+        CU(cudaMemsetAsync(s.tile_need.p, 0, (size_t)ntl * ntl, s.s_main));
+        int64_t nb = (e_hi - e_lo + 255) / 256;
+        LAUNCH(k_mark_tiles, (unsigned)(nb < 148 * 8 ? nb : 148 * 8), 256, 0, s.s_main, s.ea.as<int32_t>(),
+               s.eb.as<int32_t>(), e_lo, e_hi, ntl, s.tile_need.as<uint8_t>(), s.scal.as<int32_t>() + 2 * SC_ERR);
+        d_need = s.tile_need.as<uint8_t>();
+      } else if (s.world > 1) {  // (cp.async form: the tile rows the block reads)
         int32_t* rr = s.scal.as<int32_t>() + 2 * SC_ROWLO;
         CU(cudaMemsetAsync(rr, 0x7f, 4, s.s_main));                     // row_range[0] = huge
         CU(cudaMemsetAsync(rr + 1, 0xff, 4, s.s_main));                 // row_range[1] = -1
@@ -1067,12 +1092,58 @@ int run_shard_main(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
                s.eb.as<int32_t>(), e_lo, e_hi, rr, s.scal.as<int32_t>() + 2 * SC_ERR);
         d_range = rr;
       }
-      if (!s.dense_attr_set) {  // static tiles + dynamic staging slots exceed the 48 KB default
-        CU(cudaFuncSetAttribute(k_dense_moments, cudaFuncAttributeMaxDynamicSharedMemorySize, DENSE_DYN_SMEM));
-        s.dense_attr_set = true;
+      bool launched = false;
+      if (tma) {
+        // centred copy of D with 16-sample aligned, zero-padded category segments, then the TMA-fed MMA kernel
+        DenseLayout Lc;
+        memset(&Lc, 0, sizeof Lc);
+        Lc.K = K;
+        int off = 0;
+        for (int k = 0; k < K; ++k) {
+          Lc.off[k] = off;
+          off += (L.cnt[k] + DS - 1) / DS * DS;
+        }
+        Lc.off[K] = off;
+        Lc.npadc = off > 0 ? off : DS;
+        CU(s.Dc.ensure(nn * (size_t)Lc.npadc * 8));
+        Shard::TmapKey key = {s.Dc.p, Lc.npadc, (int64_t)n_nodes, 0, DT, DS};
+        bool ok = true;
+        if (memcmp(&key, &s.dense_tmap_key, sizeof key) != 0) {
+          const cuuint64_t gdim[2] = {(cuuint64_t)Lc.npadc, (cuuint64_t)n_nodes};
+          const cuuint64_t gstr[1] = {(cuuint64_t)Lc.npadc * 8};
+          const cuuint32_t box[2] = {(cuuint32_t)DS, (cuuint32_t)DT};
+          const cuuint32_t estr[2] = {1, 1};
+          const CUresult r = tmap_encoder()(&s.dense_tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, s.Dc.p, gdim, gstr, box, estr,
+                                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+          ok = r == CUDA_SUCCESS;
+          if (ok) s.dense_tmap_key = key;
+          else memset(&s.dense_tmap_key, 0, sizeof s.dense_tmap_key);
+        }
+        if (ok) {
+          if (!s.dense_tma_attr_set) {
+            CU(cudaFuncSetAttribute(k_dense_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, DENSE_TMA_SMEM));
+            s.dense_tma_attr_set = true;
+          }
+          LAUNCH(k_center_rows, blocks_for((int64_t)n_nodes * K * 32, 256), 256, 0, s.s_main, s.D.as<double>(), L, Lc,
+                 s.mean.as<double>(), d_nn, s.Dc.as<double>());
+          LAUNCH(k_dense_tma, grid, DENSE_TMA_THREADS, DENSE_TMA_SMEM, s.s_main, s.dense_tmap, Lc, L, (int)n_nodes, ntl,
+                 d_need, s.dense_S.as<double>());
+          launched = true;
+        }
       }
-      LAUNCH(k_dense_moments, grid, DTHREADS, DENSE_DYN_SMEM, s.s_main, s.D.as<double>(), L, s.mean.as<double>(),
-             (int)n_nodes, ntl, d_range, s.dense_S.as<double>());
+      if (!launched) {
+        if (d_need && !d_range) {
+          set_err(ctx, "internal: dense fallback without its row range");
+          return MDEGGS_ECUDA;
+        }
+        if (!s.dense_attr_set) {  // static tiles + dynamic staging slots exceed the 48 KB default
+          CU(cudaFuncSetAttribute(k_dense_moments, cudaFuncAttributeMaxDynamicSharedMemorySize, DENSE_DYN_SMEM));
+          s.dense_attr_set = true;
+        }
+        LAUNCH(k_dense_moments, grid, DTHREADS, DENSE_DYN_SMEM, s.s_main, s.D.as<double>(), L, s.mean.as<double>(),
+               (int)n_nodes, ntl, d_range, s.dense_S.as<double>());
+      }
     } else {
       switch (K) {
         case 2: launch_fit_stream<2>(ctx, s, L, e_lo, e_hi); break;
@@ -1218,6 +1289,9 @@ int run_shard_back(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
   unsigned int* d_seg_cnt = reinterpret_cast<unsigned int*>(s.counters.as<char>() + (size_t)Pn * 8 * 7 + 8);
   const int bh_ntiles = (int)((E + BH_TILE - 1) / BH_TILE);
   const bool onepass_shape = ctx->bh_onepass && E > 0 && bh_ntiles <= BH1_MAX_TILES;
+  // count-only K8 of big jobs skips the tiles of the p order beyond 0.05: the segment sizes then come from k_percolate
+  const bool skip_shape = ctx->count_skip && do_adjust && in->padj != MDEGGS_PADJ_QVALUE && in->padj != MDEGGS_PADJ_HOMMEL;
+  const bool want_seg_cnt = onepass_shape || skip_shape;
   if (onepass_shape) {  // tile words of k_bh_onepass: 0 = not published yet
     const size_t words = (size_t)Pn * K * bh_ntiles;
     CU(s.bh1_state.ensure(words * 12));
@@ -1255,10 +1329,10 @@ int run_shard_back(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
   }
   if (n_nodes > 0 && P > 0) {
     if (E > 0)  // (also writes NaN into the p.adj rows of the edges that are not tested at a percentile)
-      LAUNCH(k_percolate, blocks_for(E, 256), 256, (size_t)(3 * P + (onepass_shape ? P * K : 0)) * sizeof(unsigned),
+      LAUNCH(k_percolate, blocks_for(E, 256), 256, (size_t)(3 * P + (want_seg_cnt ? P * K : 0)) * sizeof(unsigned),
              s.s_sort, s.ea.as<int32_t>(), s.eb.as<int32_t>(), s.status.as<int32_t>(), s.p_edge.as<double>(),
              s.act.as<uint8_t>(), act_stride, E, P, c_tot, c_fail, c_raw, d_cat, d_padj,
-             s.scal.as<int32_t>() + 2 * SC_ERR, K, onepass_shape ? d_seg_cnt : nullptr);
+             s.scal.as<int32_t>() + 2 * SC_ERR, K, want_seg_cnt ? d_seg_cnt : nullptr);
   }
   CU(cudaEventRecord(s.ev_join, s.s_sort));
   if (do_adjust) {
@@ -1337,11 +1411,13 @@ int run_shard_back(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
     const bool count_only = !d_padj && ctx->count_only_adjust;  // (run_adjust takes the k_bh_sigrank path)
     s.select_fused = s.world == 1 && n_loc > 0 && !count_only && in->padj != MDEGGS_PADJ_HOMMEL;
     s.partials_complete = !count_only;
+    const bool skip = count_only && skip_shape;
+    s.tiles_complete = !skip;
     CU(s.small_out.ensure(small_block_bytes(P)));
     SelArgs sel = make_sel_args(s, in, H, emit, c_sig);
     sel.done = reinterpret_cast<unsigned int*>(c_tot + 7 * Pn);
     int rc = run_adjust(ctx, s, in, n_loc * K, p0, stride, nullptr, c_sig, d_padj, E, act_stride, false,
-                        s.select_fused ? &sel : nullptr);
+                        s.select_fused ? &sel : nullptr, false, skip ? 0.05 : 0.0);
     if (rc) return rc;
   }
   return MDEGGS_OK;
@@ -1402,7 +1478,8 @@ int run_shard_back2(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const m
            s.padj_best.as<double>(), E, nan(""));
     // single rank: the tile partials of every percentile are still there, only the final pass is repeated;
     // sharded K8: this rank may not own the best percentile, so the whole adjustment is rerun for it
-    int rc = shard_p ? run_adjust(ctx, s, in, K, 0, 1, d_best, nullptr, s.padj_best.as<double>(), E, act_stride)
+    int rc = (shard_p || !s.tiles_complete)
+                 ? run_adjust(ctx, s, in, K, 0, 1, d_best, nullptr, s.padj_best.as<double>(), E, act_stride)
                      : run_adjust(ctx, s, in, K, 0, 1, d_best, nullptr, s.padj_best.as<double>(), E, act_stride, true,
                                   nullptr, !s.partials_complete);
     if (rc) return rc;
@@ -2002,6 +2079,11 @@ int mdeggs_set_option(mdeggs_ctx* ctx, const char* name, int64_t value) {
     ctx->key_valid = false;
     return MDEGGS_OK;
   }
+  if (!strcmp(name, "count_skip")) {
+    ctx->count_skip = (int)value;
+    ctx->key_valid = false;
+    return MDEGGS_OK;
+  }
   if (!strcmp(name, "count_only")) {
     ctx->count_only_adjust = (int)value;
     ctx->key_valid = false;
@@ -2014,6 +2096,11 @@ int mdeggs_set_option(mdeggs_ctx* ctx, const char* name, int64_t value) {
   }
   if (!strcmp(name, "bh_onepass")) {
     ctx->bh_onepass = (int)value;
+    ctx->key_valid = false;
+    return MDEGGS_OK;
+  }
+  if (!strcmp(name, "dense_path")) {
+    ctx->dense_path = (int)value;
     ctx->key_valid = false;
     return MDEGGS_OK;
   }

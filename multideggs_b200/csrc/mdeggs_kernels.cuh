@@ -842,7 +842,21 @@ struct BhArgs {
   int reuse_tiles;      // best-percentile pass: reuse the tile partials of the all-percentile pass (segment index
                         // of percentile p is ((p - p0) / p_stride) * K + c - 1 there)
   const double* seg_pi0;  // q.value: pi0 of each segment (k_qv_pi0), indexed like the tile partials
+  // count-only passes (k_bh_count + k_bh_sigrank): no adjusted value below 0.05 can come from p >= 0.05 (every method's
+  // factor n/i, n + 1 - i, q n/i is >= 1), so the tiles of the p order that start at or beyond `skip_thr` are neither
+  // loaded nor counted; the segment sizes then come from k_percolate (`seg_cnt[p * K + c - 1]`) and `seg_low[seg]` keeps
+  // the members that were counted (holm needs the rank of the first member beyond).  skip_thr <= 0: every tile is visited.
+  double skip_thr;
+  const unsigned int* seg_cnt;
+  long long* seg_low;
 };
+
+// true for a tile of the p order that a count-only pass may skip (same answer in every thread of the CTA)
+__device__ __forceinline__ bool bh_skip_tile(const BhArgs& A) {
+  if (!(A.skip_thr > 0.0)) return false;
+  const int64_t tile0 = (int64_t)blockIdx.x * BH_TILE;
+  return tile0 >= (int64_t)*A.n_valid || A.ps[tile0] >= A.skip_thr;
+}
 
 // maps blockIdx.y to (percentile p, category c, segment index `seg` into the tile-partial arrays)
 __device__ __forceinline__ bool bh_segment(const BhArgs& A, int& p, int& c, size_t& seg) {
@@ -943,15 +957,24 @@ __global__ void __launch_bounds__(BH_THREADS) k_bh_count(BhArgs A, int32_t* __re
   }
   typedef cub::BlockReduce<int, BH_THREADS> Reduce;
   __shared__ typename Reduce::TempStorage tmp;
-  int flag[BH_ITEMS];
-  double pv[BH_ITEMS];
-  bh_load(A, p, c, (int64_t)blockIdx.x * BH_TILE, flag, pv);
-  int s = 0;
+  int tot = 0;
+  if (!bh_skip_tile(A)) {
+    int flag[BH_ITEMS];
+    double pv[BH_ITEMS];
+    bh_load(A, p, c, (int64_t)blockIdx.x * BH_TILE, flag, pv);
+    int s = 0;
 #pragma unroll
-  for (int it = 0; it < BH_ITEMS; ++it) s += flag[it];
-  int tot = Reduce(tmp).Sum(s);
+    for (int it = 0; it < BH_ITEMS; ++it) s += flag[it];
+    tot = Reduce(tmp).Sum(s);
+  }
   if (threadIdx.x == 0) tile_cnt[seg * A.ntiles + blockIdx.x] = tot;
-  if (bh_last_of_segment(seg_done, seg, A.ntiles)) bh_scan_tiles_body(tile_cnt, A.ntiles, seg, tile_base, seg_n);
+  if (bh_last_of_segment(seg_done, seg, A.ntiles)) {
+    bh_scan_tiles_body(tile_cnt, A.ntiles, seg, tile_base, seg_n);
+    if (A.skip_thr > 0.0 && threadIdx.x == 0) {  // (thread 0 wrote seg_n[seg] = members counted)
+      A.seg_low[seg] = seg_n[seg];
+      seg_n[seg] = (long long)A.seg_cnt[(size_t)p * A.K + (c - 1)];
+    }
+  }
 }
 
 // q = sum(1 / (1:n)) of stats::p.adjust(method = "BY"): summed left to right for small n, asymptotic beyond
@@ -1076,7 +1099,7 @@ __global__ void __launch_bounds__(BH_THREADS) k_bh_sigrank(BhArgs A, int mode, c
   } tmp;
   const bool holm = mode == MDEGGS_PADJ_HOLM;
   const long long n_ll = seg_n[seg];
-  if (tile_cnt[seg * A.ntiles + blockIdx.x] != 0) {
+  if (tile_cnt[seg * A.ntiles + blockIdx.x] != 0) {  // (a skipped tile has count 0)
     int flag[BH_ITEMS], rank[BH_ITEMS];
     double pv[BH_ITEMS];
     bh_load(A, p, c, (int64_t)blockIdx.x * BH_TILE, flag, pv);
@@ -1106,7 +1129,11 @@ __global__ void __launch_bounds__(BH_THREADS) k_bh_sigrank(BhArgs A, int mode, c
   }
   if (bh_last_of_segment(seg_done, seg, A.ntiles)) {
     if (threadIdx.x == 0) {
-      const long long tmax = (long long)__ldcg(seg_rank + seg);
+      long long tmax = (long long)__ldcg(seg_rank + seg);
+      if (holm && A.skip_thr > 0.0) {  // the first member of the skipped tiles fails the test: rank counted + 1
+        const long long low = A.seg_low[seg];
+        if (low < n_ll) tmax = max(tmax, n_ll - low);
+      }
       const long long cnt = holm ? n_ll - tmax : tmax;
       seg_rank[seg] = 0ull;
       if (cnt > 0) atomicAdd(&sig[p], (unsigned long long)cnt);

@@ -328,6 +328,12 @@ def test_dense_tile_path_matches_oracle(oracle, nf, n, K, monkeypatch):
     assert eng0.stats()["fit_path"] & 0xff == 0
     assert np.array_equal(gpu0["status"], gpu["status"]) and np.array_equal(gpu0["cat_best"], gpu["cat_best"])
     assert np.allclose(gpu0["stat"], gpu["stat"], rtol=1e-10, atol=0, equal_nan=True)
+    # the cp.async form of the dense kernel (kept for drivers without tensor maps) against the TMA-fed one
+    eng.set_option("dense_path", 0)
+    gpu1 = eng.run_omic(prob, ALL_FIELDS)
+    assert eng.stats()["fit_path"] & 0xff == 1
+    assert np.array_equal(gpu1["status"], gpu["status"]) and np.array_equal(gpu1["cat_best"], gpu["cat_best"])
+    assert np.allclose(gpu1["stat"], gpu["stat"], rtol=1e-9, atol=1e-12, equal_nan=True)
     eng.close()
     eng0.close()
 
@@ -989,6 +995,38 @@ def test_count_only_adjustment_equals_three_pass(padj, K, E, seed):
         full.close()
         for e in engs.values():
             e.close()
+
+
+@pytest.mark.parametrize("padj", [_abi.PADJ_BH, _abi.PADJ_BONFERRONI, _abi.PADJ_HOLM, _abi.PADJ_HOCHBERG, _abi.PADJ_BY])
+def test_count_only_skips_tiles_beyond_005(padj):
+    """The count-only K8 does not visit the tiles of the p order that start at p >= 0.05 (no adjusted value below 0.05 can
+    come from there; segment sizes from k_percolate; holm takes the rank of the first skipped member).  Many tiles, strong
+    and null pairs, NaN p-values: counts, best percentile and its rows equal the path that keeps everything."""
+    want = tuple(f for f in ALL_FIELDS if f != "padj")
+    for K, seed in ((2, 1451), (3, 1452)):
+        prob = synth.random_problem(300, 48, 30000, K, seed, _abi.METHOD_LM, padj, shift=1.2)
+        prob.assay[5, 2] = np.nan
+        rng = np.random.default_rng(seed)
+        a = np.asfortranarray(prob.assay.copy())
+        for e in rng.choice(30000, size=1500, replace=False):
+            i, j = prob.from_idx[e] - 1, prob.to_idx[e] - 1
+            cols = np.flatnonzero(np.asarray(prob.group) == 1 + int(e) % K)
+            a[j, cols] = a[i, cols] * 1.5 + 0.05 * rng.standard_normal(cols.size)
+        prob.assay[...] = a
+        full, cnt, noskip = md.Engine([0]), md.Engine([0]), md.Engine([0])
+        try:
+            cnt.set_option("padj_keep_cap", 0)
+            noskip.set_option("padj_keep_cap", 0)
+            noskip.set_option("count_skip", 0)
+            ref = full.run_omic(prob, ALL_FIELDS)
+            assert (ref["sig_count"] > 0).sum() >= 2
+            for e in (cnt, noskip):
+                got = e.run_omic(prob, want)
+                for f in want:
+                    assert np.array_equal(got[f], ref[f], equal_nan=True), (K, f)
+        finally:
+            for e in (full, cnt, noskip):
+                e.close()
 
 
 # ---- hommel on the device (SURVEY section 8 f, N2) ----
