@@ -52,16 +52,27 @@ __host__ __device__ __forceinline__ double bs_scale(int nlin) { return (double)n
 struct BsArgs {
   int* count;        // [NB + 1]: bucket counts (zeroed before the run)
   int* base;         // [NB + 1]: exclusive prefix of the counts
-  int32_t* slot;     // [E]: position of the edge inside its bucket
-  unsigned long long* n_valid;  // E - #NaN, for the BH passes
+  int32_t* slot;     // [E]: position of the edge inside its bucket; -1: the edge is not part of the order
+  unsigned long long* n_valid;  // ordered edges - #NaN, for the BH passes
+  unsigned long long* n_order;  // ordered edges (NaN p-values included)
   int nlin;
   double scale;
   int64_t E;
+  // Only edges that are tested at SOME percentile can be a member of a (percentile, category) segment: the others are
+  // left out of the order altogether (neither counted, scattered nor sorted).  act_t[node][nch] holds the activity
+  // masks of a node for 16 percentiles per 16-byte chunk (k_actmask); null: every edge is ordered.
+  const uint4* act_t;
+  int nch;
+  const int32_t *ea, *eb;
 };
 
 // One call per thread of a kernel that covers edges; `live` threads contribute p.  Must be reached by whole warps.
 __device__ __forceinline__ void bs_count(const BsArgs& B, bool live, int64_t e, double p) {
   const int lane = threadIdx.x & 31;
+  if (live && B.act_t && !edge_tested_any(B.act_t, B.nch, B.ea[e], B.eb[e])) {
+    B.slot[e] = -1;
+    live = false;
+  }
   int b = live ? bs_bucket(p, B.nlin, B.scale) : -1 - lane;  // dead lanes never match anyone
   const unsigned peers = __match_any_sync(0xffffffffu, b);
   if (live) {
@@ -267,6 +278,7 @@ __global__ void __launch_bounds__(256) k_bsort_scatter(BsArgs B, int scan_in_cta
   if (!scan_in_cta && blockIdx.x == 0 && threadIdx.x == 0) {  // offsets came from a device-wide scan of count[0..NB]
     const int NB = BS_NLOG + B.nlin + 1;
     *B.n_valid = (unsigned long long)(B.base[NB] - __ldcg(B.count + NB - 1));
+    *B.n_order = (unsigned long long)B.base[NB];
   }
   if (scan_in_cta) {
     const int NB = BS_NLOG + B.nlin + 1;
@@ -276,14 +288,17 @@ __global__ void __launch_bounds__(256) k_bsort_scatter(BsArgs B, int scan_in_cta
       if (threadIdx.x == 0) {
         B.base[NB] = total;
         *B.n_valid = (unsigned long long)(total - __ldcg(B.count + NB - 1));
+        *B.n_order = (unsigned long long)total;
       }
     }
     base = s_base;
   }
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= B.E) return;
+  const int sl = B.slot[e];
+  if (sl < 0) return;  // not part of the order
   const double p = p_edge[e];
-  const int pos = base[bs_bucket(p, B.nlin, B.scale)] + B.slot[e];
+  const int pos = base[bs_bucket(p, B.nlin, B.scale)] + sl;
   bkey[pos] = dkey(p);
   bidx[pos] = (int32_t)e;
 }

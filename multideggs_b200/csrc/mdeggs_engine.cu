@@ -63,7 +63,7 @@ struct DevBuf {
 enum Ev { EV_START, EV_H2D, EV_GATHER, EV_STATS, EV_FIT, EV_TAIL, EV_COLL, EV_PERC, EV_ADJ, EV_END, EV_Q0, EV_Q1, EV_COUNT };
 
 // scalar slots in the `scal` buffer (8-byte each)
-enum Scal { SC_NNODES = 0, SC_ERR = 1, SC_BEST = 2, SC_NVALID = 3, SC_ROWLO = 4, SC_ROWHI = 5, SC_DONE = 6, SC_FINQ = 7, SC_NAQ = 8, SC_COUNT = 10 };
+enum Scal { SC_NNODES = 0, SC_ERR = 1, SC_BEST = 2, SC_NVALID = 3, SC_ROWLO = 4, SC_ROWHI = 5, SC_DONE = 6, SC_FINQ = 7, SC_NAQ = 8, SC_NORDER = 9, SC_COUNT = 10 };
 constexpr int64_t FIN_DEFER_MIN_EDGES = 1 << 16;  // below this a second launch costs more than the slow lanes
 
 struct Shard {
@@ -87,6 +87,8 @@ struct Shard {
   CUtensorMap dense_tmap;  // ... and of the centred copy Dc (k_dense_tma)
   TmapKey dense_tmap_key = {nullptr, 0, 0, 0, 0, 0};
   bool dense_tma_attr_set = false;
+  int act_nch = 1;                 // 16-percentile chunks of the packed activity masks act_t[node][act_nch]
+  bool order_tested_only = false;  // this call's K8 order holds only the edges tested at some percentile
   bool select_fused = false;  // this call's percentile selection ran inside k_bh_final
   bool partials_complete = true;  // the all-percentile K8 left the tile carries behind (false: count-only pass)
   bool tiles_complete = true;     // ... and the member counts of every tile (false: count-only pass that skipped tiles)
@@ -107,11 +109,11 @@ struct Shard {
     if (e == cudaSuccess) h_stage_cap = bytes + 256;
     return e;
   }
-  DevBuf Dc, tile_need, na_q, bh1_state, assay, from, to, ea, eb, stage_dev, bs_count, bs_slot, seg_done, seg_rank, fin_q, hm_p, hm_q1, hm_c, hm_sc, hm_idx, hm_off, seg_pi0, B16, stamps, excl, node_of_row, rowlist, scal, src_of_pos, pct, cutoff, D, cub_tmp, mean, sxx, med, bad, stat, status, p_edge, coef, iters, act, counters, sortk, sortk2, idx,
+  DevBuf act_t, Dc, tile_need, na_q, bh1_state, assay, from, to, ea, eb, stage_dev, bs_count, bs_slot, seg_done, seg_rank, fin_q, hm_p, hm_q1, hm_c, hm_sc, hm_idx, hm_off, seg_pi0, B16, stamps, excl, node_of_row, rowlist, scal, src_of_pos, pct, cutoff, D, cub_tmp, mean, sxx, med, bad, stat, status, p_edge, coef, iters, act, counters, sortk, sortk2, idx,
       idx2, ps, sa, sb, tile_cnt, tile_base, seg_n, tile_min, tile_carry, padj_best, cat_best, cat, padj, med_out,
       small_out, rsel_hist, rsel_state, rsel_cand, dense_S, cf_tab, sxy;
   void release_all() {
-    DevBuf* all[] = {&Dc, &tile_need, &na_q, &bh1_state, &assay, &from, &to, &ea, &eb, &stage_dev, &bs_count, &bs_slot, &seg_done, &seg_rank, &fin_q, &hm_p, &hm_q1, &hm_c, &hm_sc, &hm_idx, &hm_off, &seg_pi0, &B16, &stamps, &excl, &node_of_row, &rowlist, &scal, &src_of_pos, &pct, &cutoff,
+    DevBuf* all[] = {&act_t, &Dc, &tile_need, &na_q, &bh1_state, &assay, &from, &to, &ea, &eb, &stage_dev, &bs_count, &bs_slot, &seg_done, &seg_rank, &fin_q, &hm_p, &hm_q1, &hm_c, &hm_sc, &hm_idx, &hm_off, &seg_pi0, &B16, &stamps, &excl, &node_of_row, &rowlist, &scal, &src_of_pos, &pct, &cutoff,
                      &D, &cub_tmp, &mean, &sxx, &med, &bad, &stat, &status, &p_edge,
                      &coef, &iters, &act, &counters, &sortk, &sortk2, &idx, &idx2, &ps, &sa, &sb, &tile_cnt,
                      &tile_base, &seg_n, &tile_min, &tile_carry, &padj_best, &cat_best, &cat, &padj, &med_out,
@@ -152,6 +154,7 @@ struct mdeggs_ctx {
   int64_t rsel_cap_override = 0;  // option "rsel_cap": shrink the candidate list to exercise the overflow path (tests)
   int fit_path_override = -1;  // -1 auto, 0 force streaming, 1 force dense (MDEGGS_FIT_PATH, tests)
   int bh_onepass = 1;          // option "bh_onepass": 0 keeps the three-launch K8 for small edge lists too (tests)
+  int order_filter = 1;        // option "order_filter": 0 = K8 orders every edge, tested somewhere or not (tests)
   int dense_path = -1;         // option "dense_path": 0 = the cp.async form of the dense moments kernel, else the TMA-fed one
   int front_path = -1;         // -1 auto, 0 separate K1 + K2 kernels, 1 fused (TMA when possible), 2 fused with the plain loader
   bool last_zc = false;        // the last call read its assay through zero copy
@@ -415,9 +418,14 @@ BsArgs make_bs_args(Shard& s, int64_t E) {
   B.base = B.count + bs_padded(NB);
   B.slot = s.bs_slot.as<int32_t>();
   B.n_valid = s.scal.as<unsigned long long>() + SC_NVALID;
+  B.n_order = s.scal.as<unsigned long long>() + SC_NORDER;
   B.nlin = bs_nlin(E);
   B.scale = bs_scale(B.nlin);
   B.E = E;
+  B.act_t = s.order_tested_only ? s.act_t.as<uint4>() : nullptr;
+  B.nch = s.act_nch;
+  B.ea = s.ea.as<int32_t>();
+  B.eb = s.eb.as<int32_t>();
   return B;
 }
 
@@ -463,6 +471,7 @@ int run_adjust(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, int n_segmen
   A.act_stride = act_stride;
   A.E = E;
   A.n_valid = s.scal.as<unsigned long long>() + SC_NVALID;
+  A.n_order = s.scal.as<unsigned long long>() + SC_NORDER;
   A.K = in->K;
   A.P = in->P;
   A.ntiles = ntiles;
@@ -1020,11 +1029,15 @@ int run_shard_main(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
   // K7 activity masks need the medians (K2, this stream) and the cut-offs (S4, side stream): they are computed on
   // the side stream while the pair fits run
   CU(s.act.ensure((size_t)(P > 0 ? P : 1) * (n_nodes > 0 ? n_nodes : 1)));
+  s.act_nch = P > 0 ? (P + 15) / 16 : 1;
+  CU(s.act_t.ensure((size_t)s.act_nch * (n_nodes > 0 ? n_nodes : 1) * 16));
+  s.order_tested_only = false;
   if (n_nodes > 0 && P > 0) {
     CU(cudaEventRecord(s.ev_sample, s.s_main));  // (event reused: "medians ready")
     CU(cudaStreamWaitEvent(s.s_sort, s.ev_sample, 0));
-    LAUNCH(k_actmask, blocks_for((int64_t)P * n_nodes, 256), 256, 0, s.s_sort, s.med.as<double>(),
-           s.cutoff.as<double>(), d_nn, P, K, n_nodes, s.act.as<uint8_t>());
+    LAUNCH(k_actmask, blocks_for((int64_t)s.act_nch * n_nodes, 256), 256, 0, s.s_sort, s.med.as<double>(),
+           s.cutoff.as<double>(), d_nn, P, K, n_nodes, s.act.as<uint8_t>(), s.act_t.as<uint4>(), s.act_nch);
+    s.order_tested_only = ctx->order_filter != 0;
   }
   EVREC(s.ev[EV_Q1], s.s_sort);
   CU(cudaEventRecord(s.ev_join, s.s_sort));
@@ -1181,6 +1194,7 @@ int run_shard_main(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
     const double* d_lbeta = s.cf_tab.as<double>() + 2 * CF_TABLE_LEN;
     const int src = is_rlm ? 2 : (use_dense ? 1 : 0);
     CU(cudaStreamWaitEvent(s.s_main, s.ev_cf, 0));  // continued-fraction tables (side stream)
+    if (s.order_tested_only) CU(cudaStreamWaitEvent(s.s_main, s.ev_join, 0));  // activity masks (k_finish filters the order)
     // single GPU: every edge passes through this launch, which then also feeds the p-value buckets of K8
     const bool bs = use_bucket_order(ctx, in, n_nodes);
     const int do_bs = bs && s.world == 1;
@@ -1331,7 +1345,7 @@ int run_shard_back(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
     if (E > 0)  // (also writes NaN into the p.adj rows of the edges that are not tested at a percentile)
       LAUNCH(k_percolate, blocks_for(E, 256), 256, (size_t)(3 * P + (want_seg_cnt ? P * K : 0)) * sizeof(unsigned),
              s.s_sort, s.ea.as<int32_t>(), s.eb.as<int32_t>(), s.status.as<int32_t>(), s.p_edge.as<double>(),
-             s.act.as<uint8_t>(), act_stride, E, P, c_tot, c_fail, c_raw, d_cat, d_padj,
+             s.act_t.as<uint4>(), s.act_nch, E, P, c_tot, c_fail, c_raw, d_cat, d_padj,
              s.scal.as<int32_t>() + 2 * SC_ERR, K, want_seg_cnt ? d_seg_cnt : nullptr);
   }
   CU(cudaEventRecord(s.ev_join, s.s_sort));
@@ -1390,7 +1404,7 @@ int run_shard_back(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
       LAUNCH(k_gather_sorted, blocks_for(E, 256), 256, 0, s.s_main, s.sortk2.as<unsigned long long>(),
              s.idx2.as<int32_t>(), s.ea.as<int32_t>(), s.eb.as<int32_t>(), E,
              s.ps.as<double>(), s.sa.as<int32_t>(), s.sb.as<int32_t>(), s.scal.as<unsigned long long>() + SC_NVALID,
-             s.scal.as<int32_t>() + 2 * SC_ERR);
+             s.scal.as<unsigned long long>() + SC_NORDER, s.scal.as<int32_t>() + 2 * SC_ERR);
     }
   }
   CU(cudaStreamWaitEvent(s.s_main, s.ev_join, 0));  // categories, counts (and NaN rows of the p.adj scratch) ready
@@ -2096,6 +2110,11 @@ int mdeggs_set_option(mdeggs_ctx* ctx, const char* name, int64_t value) {
   }
   if (!strcmp(name, "bh_onepass")) {
     ctx->bh_onepass = (int)value;
+    ctx->key_valid = false;
+    return MDEGGS_OK;
+  }
+  if (!strcmp(name, "order_filter")) {
+    ctx->order_filter = (int)value;
     ctx->key_valid = false;
     return MDEGGS_OK;
   }

@@ -686,17 +686,27 @@ __global__ void __launch_bounds__(256, FIT_CTAS) k_fit_stream(const double* __re
 //   act[p][node] bit k  <=>  median_k(node) > cut_off_p           (core_functions.R:724, strict >)
 //   an edge is tested at percentile p iff both ends are active in EXACTLY one category (745-770)
 // ------------------------------------------------------------------------------------------------
+// thread per (node, chunk of 16 percentiles): writes act[p][node] and the transposed, packed act_t[node][chunk]
 __global__ void k_actmask(const double* __restrict__ med, const double* __restrict__ cutoff,
                           const int32_t* __restrict__ n_nodes_p, int P, int K, int act_stride,
-                          uint8_t* __restrict__ act) {
+                          uint8_t* __restrict__ act, uint4* __restrict__ act_t, int nch) {
   const int n_nodes = *n_nodes_p;
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (int64_t)P * n_nodes) return;
-  int p = (int)(i / n_nodes), node = (int)(i % n_nodes);
-  double c = cutoff[p];
-  unsigned m = 0;
-  for (int k = 0; k < K; ++k) m |= (unsigned)(med[(size_t)node * K + k] > c) << k;  // NaN median: never active
-  act[(size_t)p * act_stride + node] = (uint8_t)m;
+  if (i >= (int64_t)nch * n_nodes) return;
+  const int node = (int)(i / nch), ch = (int)(i - (int64_t)node * nch);
+  double m_k[MDEGGS_MAX_K];
+  for (int k = 0; k < K; ++k) m_k[k] = med[(size_t)node * K + k];
+  unsigned w[4] = {0u, 0u, 0u, 0u};
+  for (int j = 0; j < 16; ++j) {
+    const int p = ch * 16 + j;
+    if (p >= P) break;
+    const double c = cutoff[p];
+    unsigned m = 0;
+    for (int k = 0; k < K; ++k) m |= (unsigned)(m_k[k] > c) << k;  // NaN median: never active
+    act[(size_t)p * act_stride + node] = (uint8_t)m;
+    w[j >> 2] |= m << (8 * (j & 3));
+  }
+  act_t[(size_t)node * nch + ch] = make_uint4(w[0], w[1], w[2], w[3]);
 }
 
 __device__ __forceinline__ int edge_category(unsigned ma, unsigned mb) {
@@ -704,11 +714,29 @@ __device__ __forceinline__ int edge_category(unsigned ma, unsigned mb) {
   return (m != 0 && (m & (m - 1)) == 0) ? __ffs(m) : 0;  // 1-based category, 0 = none or shared
 }
 
-// counts per percentile: tot_edges (773-779), hard failures, and for padj "none" the raw p < 0.05 count (796-808)
+// bytes of x with exactly one bit set -> 0xff in that byte (SIMD within a register)
+__device__ __forceinline__ unsigned single_bit_bytes(unsigned x) {
+  return __vcmpeq4(x & __vsub4(x, 0x01010101u), 0u) & __vcmpne4(x, 0u);
+}
+// is the edge (a, b) specific to exactly one category at any percentile (core_functions.R:745-770)?
+__device__ __forceinline__ bool edge_tested_any(const uint4* __restrict__ act_t, int nch, int a, int b) {
+  unsigned r = 0u;
+  for (int ch = 0; ch < nch; ++ch) {
+    const uint4 x = __ldg(act_t + (size_t)a * nch + ch), y = __ldg(act_t + (size_t)b * nch + ch);
+    r |= single_bit_bytes(x.x & y.x) | single_bit_bytes(x.y & y.y) | single_bit_bytes(x.z & y.z) |
+         single_bit_bytes(x.w & y.w);
+  }
+  return r != 0u;
+}
+
+// counts per percentile: tot_edges (773-779), hard failures, and for padj "none" the raw p < 0.05 count (796-808).
+// A thread reads the packed masks of its edge's two end points (16 percentiles per 16-byte load) and walks the
+// percentiles in registers; a percentile where no edge of the warp is tested costs one ballot, the others one ballot per
+// category (the per-edge properties - hard failure, raw p < 0.05, p not NA - are warp masks computed once).
 __global__ void __launch_bounds__(256) k_percolate(const int32_t* __restrict__ ea, const int32_t* __restrict__ eb,
                                                    const int32_t* __restrict__ status,
                                                    const double* __restrict__ p_edge,
-                                                   const uint8_t* __restrict__ act, int act_stride, int64_t E, int P,
+                                                   const uint4* __restrict__ act_t, int nch, int64_t E, int P,
                                                    unsigned long long* __restrict__ tot,
                                                    unsigned long long* __restrict__ fail,
                                                    unsigned long long* __restrict__ sig_raw,
@@ -732,24 +760,45 @@ __global__ void __launch_bounds__(256) k_percolate(const int32_t* __restrict__ e
   }
   const bool hard = (st == MDEGGS_EDGE_SINGULAR || st == MDEGGS_EDGE_NONFINITE);
   const int lane = threadIdx.x & 31;
-  for (int p = 0; p < P; ++p) {
-    int c = 0;
-    if (live) c = edge_category(act[(size_t)p * act_stride + a], act[(size_t)p * act_stride + b]);
-    if (cat_out && live) cat_out[(size_t)p * E + e] = (int8_t)c;
-    if (padj_nan && live && (c == 0 || isnan(pv))) padj_nan[(size_t)p * E + e] = nan("");  // K8 writes the rest
-    unsigned m_t = __ballot_sync(0xffffffffu, c != 0);
-    unsigned m_f = __ballot_sync(0xffffffffu, c != 0 && hard);
-    unsigned m_s = __ballot_sync(0xffffffffu, c != 0 && pv < 0.05);
-    if (lane == 0) {
-      if (m_t) atomicAdd(&s_cnt[p], __popc(m_t));
-      if (m_f) atomicAdd(&s_cnt[P + p], __popc(m_f));
-      if (m_s) atomicAdd(&s_cnt[2 * P + p], __popc(m_s));
+  const unsigned w_hard = __ballot_sync(0xffffffffu, hard);
+  const unsigned w_sig = __ballot_sync(0xffffffffu, pv < 0.05);
+  const unsigned w_val = __ballot_sync(0xffffffffu, !isnan(pv));
+  for (int ch = 0; ch < nch; ++ch) {
+    uint4 x = make_uint4(0u, 0u, 0u, 0u);
+    if (live) {
+      const uint4 ma = __ldg(act_t + (size_t)a * nch + ch), mb = __ldg(act_t + (size_t)b * nch + ch);
+      x = make_uint4(ma.x & mb.x, ma.y & mb.y, ma.z & mb.z, ma.w & mb.w);
     }
-    if (seg_cnt && m_t) {  // members of every (percentile, category) segment = n of p.adjust (non-NA p only)
-      const bool member = c != 0 && !isnan(pv);
-      for (int k = 1; k <= K; ++k) {
-        const unsigned m_k = __ballot_sync(0xffffffffu, member && c == k);
-        if (lane == 0 && m_k) atomicAdd(&s_cnt[3 * P + p * K + k - 1], __popc(m_k));
+    const unsigned xw[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int p0 = ch * 16 + q * 4;
+      if (p0 >= P) break;
+      // nothing tested in these four percentiles anywhere in the warp (and no row to write): next word
+      const bool any4 = __any_sync(0xffffffffu, single_bit_bytes(xw[q]) != 0u);
+      if (!any4 && !cat_out && !padj_nan) continue;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int p = p0 + j;
+        if (p >= P) break;
+        const unsigned m = (xw[q] >> (8 * j)) & 0xffu;
+        const int c = (m != 0u && (m & (m - 1u)) == 0u) ? __ffs(m) : 0;
+        if (cat_out && live) cat_out[(size_t)p * E + e] = (int8_t)c;
+        if (padj_nan && live && (c == 0 || isnan(pv))) padj_nan[(size_t)p * E + e] = nan("");  // K8 writes the rest
+        if (!any4) continue;
+        const unsigned m_t = __ballot_sync(0xffffffffu, c != 0);
+        if (!m_t) continue;
+        if (lane == 0) {
+          atomicAdd(&s_cnt[p], __popc(m_t));
+          if (m_t & w_hard) atomicAdd(&s_cnt[P + p], __popc(m_t & w_hard));
+          if (m_t & w_sig) atomicAdd(&s_cnt[2 * P + p], __popc(m_t & w_sig));
+        }
+        if (seg_cnt) {  // members of every (percentile, category) segment = n of p.adjust (non-NA p only)
+          for (int k = 1; k <= K; ++k) {
+            const unsigned m_k = __ballot_sync(0xffffffffu, c == k) & w_val;
+            if (lane == 0 && m_k) atomicAdd(&s_cnt[3 * P + p * K + k - 1], __popc(m_k));
+          }
+        }
       }
     }
   }
@@ -812,8 +861,10 @@ __global__ void k_gather_sorted(const unsigned long long* __restrict__ keys_sort
                                 const int32_t* __restrict__ idx_sorted, const int32_t* __restrict__ ea,
                                 const int32_t* __restrict__ eb, int64_t E,
                                 double* __restrict__ ps, int32_t* __restrict__ sa, int32_t* __restrict__ sb,
-                                unsigned long long* __restrict__ n_valid, const int32_t* __restrict__ err) {
+                                unsigned long long* __restrict__ n_valid, unsigned long long* __restrict__ n_order,
+                                const int32_t* __restrict__ err) {
   int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j == 0) *n_order = (unsigned long long)E;  // the radix sort orders every edge
   bool valid = false;
   if (j < E && !*err) {
     unsigned long long k = keys_sorted[j];
@@ -834,6 +885,7 @@ struct BhArgs {
   int act_stride;
   int64_t E;
   const unsigned long long* n_valid;
+  const unsigned long long* n_order;  // edges in the order (NaN p-values included, sorted last): <= E
   int K, P, ntiles;
   int p0, p_stride;     // segment y -> percentile p = p0 + (y / K) * p_stride, category c = y % K + 1
                         // (multi-GPU: rank r adjusts percentiles r, r + world, ...)
@@ -1330,7 +1382,7 @@ __global__ void __launch_bounds__(BH_THREADS) k_qv_pi0(BhArgs A, const long long
   };
   for (int j = 0; j <= QV_NLAMBDA; ++j) {  // j == QV_NLAMBDA: members whose p is NaN (sorted last)
     const int64_t from = j < QV_NLAMBDA ? (s_J[j] / BH_TILE) * BH_TILE : nv;
-    const int64_t to = j < QV_NLAMBDA ? s_J[j] : A.E;
+    const int64_t to = j < QV_NLAMBDA ? s_J[j] : (int64_t)*A.n_order;
     int cnt = 0;
     for (int64_t q = from + threadIdx.x; q < to; q += BH_THREADS) cnt += member(q);
     cnt = __reduce_add_sync(0xffffffffu, cnt);
