@@ -55,6 +55,7 @@ struct BsArgs {
   int32_t* slot;     // [E]: position of the edge inside its bucket; -1: the edge is not part of the order
   unsigned long long* n_valid;  // ordered edges - #NaN, for the BH passes
   unsigned long long* n_order;  // ordered edges (NaN p-values included)
+  unsigned long long* n_low;    // ordered edges in the buckets up to the one of p = 0.05 (count-only K8 stops there)
   int nlin;
   double scale;
   int64_t E;
@@ -279,6 +280,7 @@ __global__ void __launch_bounds__(256) k_bsort_scatter(BsArgs B, int scan_in_cta
     const int NB = BS_NLOG + B.nlin + 1;
     *B.n_valid = (unsigned long long)(B.base[NB] - __ldcg(B.count + NB - 1));
     *B.n_order = (unsigned long long)B.base[NB];
+    *B.n_low = (unsigned long long)B.base[bs_bucket(0.05, B.nlin, B.scale) + 1];
   }
   if (scan_in_cta) {
     const int NB = BS_NLOG + B.nlin + 1;
@@ -289,6 +291,8 @@ __global__ void __launch_bounds__(256) k_bsort_scatter(BsArgs B, int scan_in_cta
         B.base[NB] = total;
         *B.n_valid = (unsigned long long)(total - __ldcg(B.count + NB - 1));
         *B.n_order = (unsigned long long)total;
+        const int bq = bs_bucket(0.05, B.nlin, B.scale) + 1;
+        *B.n_low = (unsigned long long)(bq < NB ? s_base[bq] : total);
       }
     }
     base = s_base;

@@ -63,7 +63,7 @@ struct DevBuf {
 enum Ev { EV_START, EV_H2D, EV_GATHER, EV_STATS, EV_FIT, EV_TAIL, EV_COLL, EV_PERC, EV_ADJ, EV_END, EV_Q0, EV_Q1, EV_COUNT };
 
 // scalar slots in the `scal` buffer (8-byte each)
-enum Scal { SC_NNODES = 0, SC_ERR = 1, SC_BEST = 2, SC_NVALID = 3, SC_ROWLO = 4, SC_ROWHI = 5, SC_DONE = 6, SC_FINQ = 7, SC_NAQ = 8, SC_NORDER = 9, SC_COUNT = 10 };
+enum Scal { SC_NNODES = 0, SC_ERR = 1, SC_BEST = 2, SC_NVALID = 3, SC_ROWLO = 4, SC_ROWHI = 5, SC_DONE = 6, SC_FINQ = 7, SC_NAQ = 8, SC_NORDER = 9, SC_NLOW = 10, SC_COUNT = 12 };
 constexpr int64_t FIN_DEFER_MIN_EDGES = 1 << 16;  // below this a second launch costs more than the slow lanes
 
 struct Shard {
@@ -419,6 +419,7 @@ BsArgs make_bs_args(Shard& s, int64_t E) {
   B.slot = s.bs_slot.as<int32_t>();
   B.n_valid = s.scal.as<unsigned long long>() + SC_NVALID;
   B.n_order = s.scal.as<unsigned long long>() + SC_NORDER;
+  B.n_low = s.scal.as<unsigned long long>() + SC_NLOW;
   B.nlin = bs_nlin(E);
   B.scale = bs_scale(B.nlin);
   B.E = E;
@@ -483,6 +484,7 @@ int run_adjust(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, int n_segmen
   CU(s.seg_pi0.ensure((size_t)in->P * in->K * 8));
   A.seg_pi0 = s.seg_pi0.as<double>();
   A.skip_thr = 0.0;
+  A.n_low = s.scal.as<unsigned long long>() + SC_NLOW;
   A.seg_cnt = nullptr;
   A.seg_low = nullptr;
   dim3 grid((unsigned)ntiles, (unsigned)n_segments);
@@ -505,7 +507,7 @@ int run_adjust(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, int n_segmen
       CU(s.seg_rank.ensure(2 * need));
       CU(cudaMemsetAsync(s.seg_rank.p, 0, s.seg_rank.cap, s.s_main));
     }
-    if (skip_thr > 0.0 && in->padj != MDEGGS_PADJ_QVALUE) {  // (q.value scales by pi0 <= 1: its q can fall below p)
+    if (skip_thr > 0.0 && in->padj != MDEGGS_PADJ_QVALUE && use_bucket_order(ctx, in, 1)) {  // (q.value scales by pi0 <= 1: its q can fall below p)
       const int Pn = in->P > 0 ? in->P : 1;
       A.skip_thr = skip_thr;
       A.seg_cnt = reinterpret_cast<const unsigned int*>(s.counters.as<char>() + (size_t)Pn * 8 * 7 + 8);
@@ -526,9 +528,11 @@ int run_adjust(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, int n_segmen
            padj_stride, sel ? *sel : SelArgs{});
     return MDEGGS_OK;
   }
+  // count-only passes walk the tiles with the grid's stride: a capped grid (most tiles are skipped, see bh_tiles_visited)
+  const dim3 grid_c((unsigned)(ntiles < 2 * s.sm_count ? ntiles : 2 * s.sm_count), (unsigned)n_segments);
   if (!reuse_tiles)
-    LAUNCH(k_bh_count, grid, BH_THREADS, 0, s.s_main, A, s.tile_cnt.as<int32_t>(), s.tile_base.as<long long>(),
-           s.seg_n.as<long long>(), done_a);
+    LAUNCH(k_bh_count, (count_only ? grid_c : grid), BH_THREADS, 0, s.s_main, A, s.tile_cnt.as<int32_t>(),
+           s.tile_base.as<long long>(), s.seg_n.as<long long>(), done_a);
   if (in->padj == MDEGGS_PADJ_QVALUE && !reuse_tiles)
     LAUNCH(k_qv_pi0, dim3(1, (unsigned)n_segments), BH_THREADS, 0, s.s_main, A, s.tile_base.as<long long>(),
            s.seg_n.as<long long>(), s.seg_pi0.as<double>());
@@ -560,7 +564,7 @@ int run_adjust(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, int n_segmen
     return MDEGGS_OK;
   }
   if (count_only) {
-    LAUNCH(k_bh_sigrank, grid, BH_THREADS, 0, s.s_main, A, in->padj, s.tile_cnt.as<int32_t>(),
+    LAUNCH(k_bh_sigrank, grid_c, BH_THREADS, 0, s.s_main, A, in->padj, s.tile_cnt.as<int32_t>(),
            s.tile_base.as<long long>(), s.seg_n.as<long long>(), s.seg_rank.as<unsigned long long>(), sig_dev, done_b);
     return MDEGGS_OK;
   }
@@ -1304,7 +1308,8 @@ int run_shard_back(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
   const int bh_ntiles = (int)((E + BH_TILE - 1) / BH_TILE);
   const bool onepass_shape = ctx->bh_onepass && E > 0 && bh_ntiles <= BH1_MAX_TILES;
   // count-only K8 of big jobs skips the tiles of the p order beyond 0.05: the segment sizes then come from k_percolate
-  const bool skip_shape = ctx->count_skip && do_adjust && in->padj != MDEGGS_PADJ_QVALUE && in->padj != MDEGGS_PADJ_HOMMEL;
+  const bool skip_shape = ctx->count_skip && do_adjust && in->padj != MDEGGS_PADJ_QVALUE && in->padj != MDEGGS_PADJ_HOMMEL &&
+                          use_bucket_order(ctx, in, n_nodes);  // (n_low comes from the bucket offsets)
   const bool want_seg_cnt = onepass_shape || skip_shape;
   if (onepass_shape) {  // tile words of k_bh_onepass: 0 = not published yet
     const size_t words = (size_t)Pn * K * bh_ntiles;

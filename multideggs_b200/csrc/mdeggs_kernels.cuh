@@ -896,18 +896,21 @@ struct BhArgs {
   const double* seg_pi0;  // q.value: pi0 of each segment (k_qv_pi0), indexed like the tile partials
   // count-only passes (k_bh_count + k_bh_sigrank): no adjusted value below 0.05 can come from p >= 0.05 (every method's
   // factor n/i, n + 1 - i, q n/i is >= 1), so the tiles of the p order that start at or beyond `skip_thr` are neither
-  // loaded nor counted; the segment sizes then come from k_percolate (`seg_cnt[p * K + c - 1]`) and `seg_low[seg]` keeps
+  // loaded nor counted (see bh_tiles_visited); the segment sizes then come from k_percolate (`seg_cnt[p * K + c - 1]`) and `seg_low[seg]` keeps
   // the members that were counted (holm needs the rank of the first member beyond).  skip_thr <= 0: every tile is visited.
   double skip_thr;
+  const unsigned long long* n_low;
   const unsigned int* seg_cnt;
   long long* seg_low;
 };
 
-// true for a tile of the p order that a count-only pass may skip (same answer in every thread of the CTA)
-__device__ __forceinline__ bool bh_skip_tile(const BhArgs& A) {
-  if (!(A.skip_thr > 0.0)) return false;
-  const int64_t tile0 = (int64_t)blockIdx.x * BH_TILE;
-  return tile0 >= (int64_t)*A.n_valid || A.ps[tile0] >= A.skip_thr;
+// Count-only passes with skip_thr > 0 visit only the first bh_tiles_visited() tiles of the p order: `n_low` = ordered
+// edges in the p-value buckets up to the one that holds skip_thr (k_bsort_scatter), so every p < skip_thr lies in a
+// visited tile.  The other CTAs leave before any barrier or counter (same answer in every thread of a CTA).
+__device__ __forceinline__ int bh_tiles_visited(const BhArgs& A) {
+  if (!(A.skip_thr > 0.0)) return A.ntiles;
+  const long long t = ((long long)*A.n_low + BH_TILE - 1) / BH_TILE;
+  return t < (long long)A.ntiles ? (int)t : A.ntiles;
 }
 
 // maps blockIdx.y to (percentile p, category c, segment index `seg` into the tile-partial arrays)
@@ -961,18 +964,20 @@ __device__ __forceinline__ void bh_load(const BhArgs& A, int p, int c, int64_t t
 
 // exclusive scan of the tile counts of one segment (whole CTA of BH_THREADS); seg_n = members of the segment
 __device__ __forceinline__ void bh_scan_tiles_body(const int32_t* __restrict__ tile_cnt, int ntiles, size_t seg,
-                                                   long long* __restrict__ tile_base, long long* __restrict__ seg_n) {
+                                                   long long* __restrict__ tile_base, long long* __restrict__ seg_n,
+                                                   int n_scan = -1) {
   typedef cub::BlockScan<long long, BH_THREADS> Scan;
   __shared__ typename Scan::TempStorage tmp;
   __shared__ long long carry;
   if (threadIdx.x == 0) carry = 0;
   __syncthreads();
   const size_t base = seg * ntiles;
-  for (int t0 = 0; t0 < ntiles; t0 += BH_THREADS) {
+  const int nt = n_scan >= 0 ? n_scan : ntiles;  // (count-only passes: only the visited tiles hold a count)
+  for (int t0 = 0; t0 < nt; t0 += BH_THREADS) {
     int t = t0 + threadIdx.x;
-    long long v = t < ntiles ? (long long)__ldcg(tile_cnt + base + t) : 0, ex, agg;
+    long long v = t < nt ? (long long)__ldcg(tile_cnt + base + t) : 0, ex, agg;
     Scan(tmp).ExclusiveSum(v, ex, agg);
-    if (t < ntiles) tile_base[base + t] = carry + ex;
+    if (t < nt) tile_base[base + t] = carry + ex;
     __syncthreads();
     if (threadIdx.x == 0) carry += agg;
     __syncthreads();
@@ -1007,21 +1012,26 @@ __global__ void __launch_bounds__(BH_THREADS) k_bh_count(BhArgs A, int32_t* __re
     if (threadIdx.x == 0) tile_cnt[seg * A.ntiles + blockIdx.x] = 0;
     return;
   }
+  // a CTA walks the visited tiles with the grid's stride (count-only passes are launched with a capped grid: the
+  // 100,000 CTAs of a full grid that would only find out they have nothing to do cost more than the counting itself)
+  const int n_vis = bh_tiles_visited(A);
+  const int n_cta = n_vis < (int)gridDim.x ? n_vis : (int)gridDim.x;
+  if ((int)blockIdx.x >= n_cta) return;
   typedef cub::BlockReduce<int, BH_THREADS> Reduce;
   __shared__ typename Reduce::TempStorage tmp;
-  int tot = 0;
-  if (!bh_skip_tile(A)) {
+  for (int tile = blockIdx.x; tile < n_vis; tile += gridDim.x) {
     int flag[BH_ITEMS];
     double pv[BH_ITEMS];
-    bh_load(A, p, c, (int64_t)blockIdx.x * BH_TILE, flag, pv);
+    bh_load(A, p, c, (int64_t)tile * BH_TILE, flag, pv);
     int s = 0;
 #pragma unroll
     for (int it = 0; it < BH_ITEMS; ++it) s += flag[it];
-    tot = Reduce(tmp).Sum(s);
+    const int tot = Reduce(tmp).Sum(s);
+    if (threadIdx.x == 0) tile_cnt[seg * A.ntiles + tile] = tot;
+    __syncthreads();
   }
-  if (threadIdx.x == 0) tile_cnt[seg * A.ntiles + blockIdx.x] = tot;
-  if (bh_last_of_segment(seg_done, seg, A.ntiles)) {
-    bh_scan_tiles_body(tile_cnt, A.ntiles, seg, tile_base, seg_n);
+  if (bh_last_of_segment(seg_done, seg, n_cta)) {
+    bh_scan_tiles_body(tile_cnt, A.ntiles, seg, tile_base, seg_n, n_vis);
     if (A.skip_thr > 0.0 && threadIdx.x == 0) {  // (thread 0 wrote seg_n[seg] = members counted)
       A.seg_low[seg] = seg_n[seg];
       seg_n[seg] = (long long)A.seg_cnt[(size_t)p * A.K + (c - 1)];
@@ -1143,6 +1153,9 @@ __global__ void __launch_bounds__(BH_THREADS) k_bh_sigrank(BhArgs A, int mode, c
   size_t seg;
   if (!bh_segment(A, p, c, seg)) return;
   if (A.tot && A.tot[p] == 0) return;  // (same whole-segment exit as pass A)
+  const int n_vis = bh_tiles_visited(A);
+  const int n_cta = n_vis < (int)gridDim.x ? n_vis : (int)gridDim.x;  // (tile-stride walk, see k_bh_count)
+  if ((int)blockIdx.x >= n_cta) return;
   typedef cub::BlockScan<int, BH_THREADS> Scan;
   typedef cub::BlockReduce<long long, BH_THREADS> Reduce;
   __shared__ union {
@@ -1151,17 +1164,18 @@ __global__ void __launch_bounds__(BH_THREADS) k_bh_sigrank(BhArgs A, int mode, c
   } tmp;
   const bool holm = mode == MDEGGS_PADJ_HOLM;
   const long long n_ll = seg_n[seg];
-  if (tile_cnt[seg * A.ntiles + blockIdx.x] != 0) {  // (a skipped tile has count 0)
+  const double n = (double)n_ll;
+  const double num = adj_numerator(mode, n);
+  const double pi0 = mode == MDEGGS_PADJ_QVALUE ? A.seg_pi0[seg] : 1.0;
+  long long t = 0;
+  for (int tile = blockIdx.x; tile < n_vis; tile += gridDim.x) {
+    if (tile_cnt[seg * A.ntiles + tile] == 0) continue;  // (same for every thread of the CTA)
     int flag[BH_ITEMS], rank[BH_ITEMS];
     double pv[BH_ITEMS];
-    bh_load(A, p, c, (int64_t)blockIdx.x * BH_TILE, flag, pv);
+    bh_load(A, p, c, (int64_t)tile * BH_TILE, flag, pv);
     Scan(tmp.scan).InclusiveSum(flag, rank);
     __syncthreads();
-    const long long base = tile_base[seg * A.ntiles + blockIdx.x];
-    const double n = (double)n_ll;
-    const double num = adj_numerator(mode, n);
-    const double pi0 = mode == MDEGGS_PADJ_QVALUE ? A.seg_pi0[seg] : 1.0;
-    long long t = 0;
+    const long long base = tile_base[seg * A.ntiles + tile];
 #pragma unroll
     for (int it = 0; it < BH_ITEMS; ++it)
       if (flag[it]) {
@@ -1176,10 +1190,10 @@ __global__ void __launch_bounds__(BH_THREADS) k_bh_sigrank(BhArgs A, int mode, c
           t = max(t, i);
         }
       }
-    t = Reduce(tmp.red).Reduce(t, cub::Max());
-    if (threadIdx.x == 0 && t > 0) atomicMax(seg_rank + seg, (unsigned long long)t);
   }
-  if (bh_last_of_segment(seg_done, seg, A.ntiles)) {
+  t = Reduce(tmp.red).Reduce(t, cub::Max());
+  if (threadIdx.x == 0 && t > 0) atomicMax(seg_rank + seg, (unsigned long long)t);
+  if (bh_last_of_segment(seg_done, seg, n_cta)) {
     if (threadIdx.x == 0) {
       long long tmax = (long long)__ldcg(seg_rank + seg);
       if (holm && A.skip_thr > 0.0) {  // the first member of the skipped tiles fails the test: rank counted + 1
