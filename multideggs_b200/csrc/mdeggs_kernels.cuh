@@ -394,14 +394,24 @@ __device__ __forceinline__ unsigned long long warp_select_reg(const unsigned lon
   }
   while (cnt_hi - cnt_lo > 32 && hi - lo > 1ull) narrow(lo + ((hi - lo) >> 1));
   if (cnt_hi - cnt_lo > 32) return lo;  // hi == lo + 1: more than 32 keys equal to lo
-  int base = 0;
+  // the <= 32 keys left go to scratch (their order there is irrelevant): each lane counts its own, one warp prefix
+  // sum hands out the slots (a ballot per item cost 8 instructions x ITEMS)
+  int mine_n = 0;
 #pragma unroll
-  for (int j = 0; j < ITEMS; ++j) {
-    const unsigned long long k = keys[j];
-    const bool in = k >= lo && k < hi;
-    const unsigned mask = __ballot_sync(0xffffffffu, in);
-    if (in) scratch32[base + __popc(mask & ((1u << lane) - 1u))] = k;
-    base += __popc(mask);
+  for (int j = 0; j < ITEMS; ++j) mine_n += (keys[j] >= lo && keys[j] < hi);
+  int at = mine_n;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, at, o);
+    if (lane >= o) at += t;
+  }
+  at -= mine_n;
+  if (mine_n) {
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+      const unsigned long long k = keys[j];
+      if (k >= lo && k < hi) scratch32[at++] = k;
+    }
   }
   __syncwarp();
   const int ncand = cnt_hi - cnt_lo;

@@ -19,6 +19,18 @@
 
 namespace mdeggs {
 
+// 1 / x for a positive normal double: hardware seed (MUFU.RCP64H, ~20 bits) + two Newton steps (4 FMAs), within an ulp or
+// two of the correctly rounded quotient; the IEEE division costs ~4x as many instructions and sat on 19 % of the IRLS
+// kernel's issue slots (one per sample and iteration, for the Huber weight k s / |r|)
+__device__ __forceinline__ double rcp_newton(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-x, y, 1.0);
+  return fma(y, e, y);
+}
+
 struct GroupFit {
   double W, ma, mb, sxx, sxy, slope, icpt;
 };
@@ -296,8 +308,14 @@ __global__ void __launch_bounds__(256) k_fit_rlm(const double* __restrict__ D, S
 //   sum (r_old - r_new)^2 = n di^2 + 2 di ds sum(a) + ds^2 sum(a^2),   sum r_old^2 = Syy - 2 s Sxy + s^2 Sxx + n (mb - i - s ma)^2
 // are closed forms in the unweighted per-gene moments of K2.  Per IRLS iteration: one pass for the residual keys, the
 // selection, one pass for the Huber weights + 5 weighted moments per category.
+// warps per CTA of the register-resident kernel: as many as the register file holds (one CTA per SM at 32 items)
 template <int ITEMS>
-__global__ void __launch_bounds__(256) k_fit_rlm_reg(const double* __restrict__ D, SegLayout L,
+struct RlmRegWarps {
+  static constexpr int value = ITEMS >= 32 ? 12 : (ITEMS >= 16 ? 12 : (ITEMS >= 8 ? 12 : 16));
+};
+
+template <int ITEMS>
+__global__ void __launch_bounds__(RlmRegWarps<ITEMS>::value * 32) k_fit_rlm_reg(const double* __restrict__ D, SegLayout L,
                                                      const int32_t* __restrict__ ea, const int32_t* __restrict__ eb,
                                                      const double* __restrict__ mean, const double* __restrict__ sxx,
                                                      const uint8_t* __restrict__ bad, int64_t e_lo, int64_t e_hi,
@@ -305,7 +323,7 @@ __global__ void __launch_bounds__(256) k_fit_rlm_reg(const double* __restrict__ 
                                                      int32_t* __restrict__ status, double* __restrict__ coef,
                                                      int32_t* __restrict__ iters, const int32_t* __restrict__ err) {
   extern __shared__ double smem[];  // per warp: A row, B row (npad doubles each)
-  __shared__ unsigned long long s_cand[8][32];
+  __shared__ unsigned long long s_cand[RlmRegWarps<ITEMS>::value][32];
   if (*err) return;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   double* sa = smem + (size_t)wib * 2 * L.npad;
@@ -439,8 +457,7 @@ __global__ void __launch_bounds__(256) k_fit_rlm_reg(const double* __restrict__ 
     for (it = 1; it <= 20; ++it) {
       residual_keys();
       {
-        double guess = med_prev, rel = 0.1;
-        if (it == 1) {  // residual sd under the least-squares start (closed form) -> MAD of a normal sample
+        double guess = med_prev, rel = 0.1;        if (it == 1) {  // residual sd under the least-squares start (closed form) -> MAD of a normal sample
           double ss = 0.0;
 #pragma unroll
           for (int k = 0; k < 2; ++k) {
@@ -474,7 +491,7 @@ __global__ void __launch_bounds__(256) k_fit_rlm_reg(const double* __restrict__ 
         const int c = cmask >> j & 1;
         // psi.huber weight pmin(1, k / |r / s|) with ONE division per sample: k s / |r|
         const double ar = __longlong_as_double((long long)keys[j]);
-        const double w = (ar <= ks) ? 1.0 : ks / ar;
+        const double w = (ar <= ks) ? 1.0 : ks * rcp_newton(ar);
         const double da = sa[pos] - ma[c], db = sb[pos] - mb[c];
         const double wda = w * da;
         if (c) {
@@ -528,7 +545,7 @@ __global__ void __launch_bounds__(256) k_fit_rlm_reg(const double* __restrict__ 
       const int c = cmask >> j & 1;
       const double ar = __longlong_as_double((long long)keys[j]);
       const double u = ar / scale;
-      const double w = (u <= kh) ? 1.0 : kh / u;
+      const double w = (u <= kh) ? 1.0 : (kh * scale) * rcp_newton(ar);
       const double rw = ar * w;
       S = fma(rw, rw, S);
       npp += (u <= kh) ? 1.0 : 0.0;
@@ -599,7 +616,7 @@ inline void launch_fit_rlm_reg(cudaStream_t stream, const double* D, const SegLa
                                const uint8_t* bad, int64_t e_lo, int64_t e_hi, int tested_coef, int cov_mode, double* stat,
                                int32_t* status, double* coef, int32_t* iters, const int32_t* err) {
   const size_t per_warp = (size_t)L.npad * 16;
-  const int wpb = 8;
+  const int wpb = RlmRegWarps<ITEMS>::value;
   const size_t smem = per_warp * wpb;
   int64_t want = (e_hi - e_lo + wpb - 1) / wpb;
   unsigned grid = (unsigned)(want < 148 * 32 ? want : 148 * 32);
