@@ -183,6 +183,16 @@ int mdeggs_run_omics(mdeggs_ctx* const* ctxs, int n_layers, const mdeggs_problem
 int mdeggs_pair_features(mdeggs_ctx* ctx, const double* x, int64_t ldx, int32_t n, const int32_t* a,
                          const int32_t* b, int32_t n_pairs, int32_t ratio, int32_t mem, double* out);
 
+/* Per-category sufficient statistics of gene pairs, from the gene-major matrix and the per-gene moments that the LAST
+ * completed mdeggs_run_omic of this context left on the device: the refit behind the per-category regression lines and
+ * confidence bands of plot_regressions (plotting_functions.R:125-162: lm(y ~ x) inside each category +
+ * predict(interval = "confidence")) without sending the rows again.  a_rows / b_rows: 1-based gene rows as in from / to
+ * (host memory); out (host): out[(j K + k) 6 + 0..5] = n_k, mean_A, mean_B, Sxx_A, Syy_B, Sxy of pair j in category k
+ * (centred sums over the category's samples); NaN for a row that was no network node of that run.
+ * slope = Sxy / Sxx_A, intercept = mean_B - slope mean_A, sigma^2 = (Syy_B - slope Sxy) / (n_k - 2),
+ * se(fit at x0)^2 = sigma^2 (1 / n_k + (x0 - mean_A)^2 / Sxx_A). */
+int mdeggs_pair_moments(mdeggs_ctx* ctx, const int32_t* a_rows, const int32_t* b_rows, int32_t n_pairs, double* out);
+
 /* Measures this GPU's FP64 FMA peak with a register-only DFMA-chain kernel (TFLOP/s): the denominator of the
  * rlm (K6) roofline, which is FP64-pipe bound (SURVEY section 8 d). */
 int mdeggs_measure_fp64_peak(mdeggs_ctx* ctx, double* tflops_out);

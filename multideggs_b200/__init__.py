@@ -7,7 +7,7 @@ from ._abi import (METHOD_LM, METHOD_RLM, PADJ_BH, PADJ_BONFERRONI, PADJ_HOST, P
                    RLM_COV_XTX, Problem, r_seq)
 from .api import (DEFAULT_PERCENTILES, FILTER_PERCENTILES, Deggs, MultiDEGGsFilter, get_diffNetworks,
                   get_diffNetworks_singleOmic, get_multiOmics_diffNetworks, get_sig_deggs, multiDEGGs_filter,
-                  predict)
+                  plot_regressions_data, predict)
 from .engine import Engine, EngineError, OmicError, default_engine, load_library
 from .host import NO_LINKS, Assay, Factor, IndexedNetwork, omic_network, tidy_metadata
 

@@ -197,6 +197,81 @@ def get_multiOmics_diffNetworks(deggs_object: Deggs, sig_threshold=0.05) -> dict
 # ----------------------------------------------------------------------------------------------
 # nestedcv glue (feature_selection_for_ML.R)
 # ----------------------------------------------------------------------------------------------
+def plot_regressions_data(deggs_object: Deggs, assayDataName=1, gene_A: str | None = None, gene_B: str | None = None, *,
+                          engine: Engine | None = None, n_points: int = 100, level: float = 0.95) -> dict:
+    """The numbers behind plot_regressions (plotting_functions.R:60-240) without the drawing: the pair's interaction
+    p-value, what the figure prints (`Padj` looked up in the object, plotting_functions.R:175-190), and for each category
+    the line lm(y ~ x) with its confidence band at `n_points` abscissae (predict(interval = "confidence"), 125-172).
+
+    The pair goes through the engine as a one-edge network; the per-category lines are then rebuilt from the moments that
+    run left on the device (`mdeggs_pair_moments`: n_k, means, Sxx, Syy, Sxy), no second pass over the rows on the host.
+    regression_method "rlm" draws MASS::rlm(y ~ x) per category in R, a robust fit with its own scale per category; that
+    drawing glue is not mirrored (NotImplementedError), the interaction p-value of the rlm branch is."""
+    from scipy import stats as _st
+    if not isinstance(deggs_object, Deggs):
+        raise ValueError("deggs_object must be of class deggs")
+    assay_list = deggs_object["assayData"]
+    name = list(assay_list.keys())[assayDataName - 1] if isinstance(assayDataName, int) else assayDataName
+    assay = host.Assay.coerce(assay_list[name])
+    genes = set(assay.genes.tolist())
+    if gene_A not in genes:
+        raise ValueError(f"gene_A is not in rownames({name})")
+    if gene_B not in genes:
+        raise ValueError(f"gene_B is not in rownames({name})")
+    metadata: Factor = deggs_object["metadata"]
+    method = deggs_object["regression_method"]
+    net = pd.DataFrame({"from": [gene_A], "to": [gene_B]})
+    prep = host.prepare_omic(assay, name, metadata, method, net, [0.0], "none")
+    eng = engine if engine is not None else default_engine()
+    res = eng.run_omic(prep.problem, ("p_edge", "stat", "status", "df"))
+    K = prep.problem.K
+    stat, df = float(res["stat"][0]), res["df"]
+    if K == 2 and method == "lm":
+        # coef(summary(lmfit))[4, 4]: the plain two-sided t tail 2 pt(-|t|), not the reference's 2 (1 - pt(|t|))
+        p_interaction = float(2.0 * eng.dev_pt(-abs(stat), df[1])[0]) if np.isfinite(stat) else float("nan")
+    else:
+        p_interaction = float(res["p_edge"][0])
+    padj_method = deggs_object["padj_method"]
+    sig_interaction = p_interaction
+    if padj_method != "none":
+        entry = _omic_entry(deggs_object, name) or {}
+        frames = [v for k, v in entry.items() if isinstance(v, pd.DataFrame) and k in prep.categories and v.shape[0]]
+        sig_interaction = float("nan")
+        if frames:
+            allf = pd.concat(frames, axis=0)
+            hit = allf[(allf["from"] == gene_A) & (allf["to"] == gene_B)]
+            if hit.shape[0] == 0:
+                hit = allf[(allf["from"] == gene_B) & (allf["to"] == gene_A)]
+            if hit.shape[0] > 0:
+                sig_interaction = float(hit["p.adj"].iloc[0])
+    if method != "lm":
+        raise NotImplementedError("per-category MASS::rlm(y ~ x) lines are drawing glue outside the hot path; "
+                                  f"interaction p = {p_interaction!r}")
+    mom = eng.pair_moments(prep.problem.from_idx, prep.problem.to_idx, K)[0]          # [K, 6]
+    x = prep.problem.assay[int(prep.problem.from_idx[0]) - 1]
+    lo, hi = float(np.nanmin(x)), float(np.nanmax(x))
+    adj = (hi - lo) * 0.05
+    new_x = np.linspace(lo - adj, hi + adj, n_points)
+    lines = {}
+    for k, cat in enumerate(prep.categories):
+        n_k, ma, mb, sxx, syy, sxy = (float(v) for v in mom[k])
+        if n_k < 1:
+            lines[cat] = None                                                        # no sample of this category here
+            continue
+        slope = sxy / sxx if sxx > 0 else float("nan")
+        icpt = mb - slope * ma
+        rdf = n_k - 2
+        sigma2 = (syy - slope * sxy) / rdf if rdf > 0 else float("nan")
+        fit = icpt + slope * new_x
+        se = np.sqrt(sigma2 * (1.0 / n_k + (new_x - ma) ** 2 / sxx)) if sxx > 0 else np.full_like(new_x, np.nan)
+        tq = float(_st.t.ppf(0.5 + level / 2.0, rdf)) if rdf > 0 else float("nan")
+        lines[cat] = {"intercept": icpt, "slope": slope, "sigma": float(np.sqrt(sigma2)) if sigma2 >= 0 else float("nan"),
+                      "n": int(n_k), "fit": fit, "lwr": fit - tq * se, "upr": fit + tq * se}
+    return {"assayDataName": name, "gene_A": gene_A, "gene_B": gene_B, "categories": list(prep.categories),
+            "p_interaction": p_interaction, "sig_interaction": sig_interaction,
+            "prefix": "P" if padj_method == "none" else "Padj", "new_x": new_x, "lines": lines}
+
+
 class MultiDEGGsFilter(dict):
     """S3 class "multiDEGGs_filter": list(keep = <names>, pairs = <data.frame>)."""
 

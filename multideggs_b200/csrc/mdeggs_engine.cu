@@ -173,12 +173,17 @@ struct mdeggs_ctx {
   std::vector<TraceRec> trace_recs;
   std::vector<cudaEvent_t> trace_pool;
   size_t trace_used = 0;
+  // what the last completed call left on the device (mdeggs_pair_moments reads it)
+  bool last_valid = false;
+  SegLayout last_L;
+  int last_G = 0;
   // a submitted call that has not been waited for yet (mdeggs_submit_omic / mdeggs_wait)
   struct Pending {
     bool active = false;
     mdeggs_problem in;
     mdeggs_result out;
     int32_t n_nodes = 0;
+    SegLayout L;
     bool replayed = false;
     int src_device = 0;
     std::chrono::steady_clock::time_point t0, t1, t2, tA;
@@ -1976,7 +1981,9 @@ int mdeggs_submit_omic(mdeggs_ctx* ctx, const mdeggs_problem* in, mdeggs_result*
   ctx->pend.in = *in;
   ctx->pend.out = *out;
   ctx->pend.n_nodes = n_nodes;
+  ctx->pend.L = H.L;
   ctx->pend.replayed = replayed;
+  ctx->last_valid = false;
   ctx->pend.src_device = src_device;
   ctx->pend.t0 = t_host0;
   ctx->pend.t1 = t_host1;
@@ -2038,6 +2045,9 @@ int mdeggs_wait(mdeggs_ctx* ctx) {
       prev[sid] = t;
     }
   }
+  ctx->last_valid = n_nodes > 0;
+  ctx->last_L = ctx->pend.L;
+  ctx->last_G = in->G;
   // ---- stats ----
   (void)replayed;
   mdeggs_stats& st = ctx->stats;
@@ -2210,6 +2220,41 @@ int mdeggs_pair_features(mdeggs_ctx* ctx, const double* x, int64_t ldx, int32_t 
     if (cudaStreamSynchronize(s.s_main) != cudaSuccess) rc = MDEGGS_ECUDA;
   } while (0);
   dx.release();
+  da.release();
+  db.release();
+  dout.release();
+  return rc;
+}
+
+int mdeggs_pair_moments(mdeggs_ctx* ctx, const int32_t* a_rows, const int32_t* b_rows, int32_t n_pairs, double* out) {
+  if (!ctx || !a_rows || !b_rows || !out || n_pairs < 0) return MDEGGS_EINVAL;
+  if (ctx->pend.active) {
+    set_err(ctx, "a submitted call is still pending: call mdeggs_wait first");
+    return MDEGGS_EINVAL;
+  }
+  if (!ctx->last_valid) {
+    set_err(ctx, "mdeggs_pair_moments needs a completed mdeggs_run_omic on this context");
+    return MDEGGS_EINVAL;
+  }
+  if (n_pairs == 0) return MDEGGS_OK;
+  Shard& s = ctx->shards[0];
+  CU(cudaSetDevice(s.device));
+  const SegLayout& L = ctx->last_L;
+  const size_t n_out = (size_t)n_pairs * L.K * 6;
+  DevBuf da, db, dout;
+  int rc = MDEGGS_OK;
+  if (da.ensure((size_t)n_pairs * 4) != cudaSuccess || db.ensure((size_t)n_pairs * 4) != cudaSuccess ||
+      dout.ensure(n_out * 8) != cudaSuccess) {
+    rc = MDEGGS_ENOMEM;
+  } else {
+    cudaMemcpyAsync(da.p, a_rows, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, s.s_main);
+    cudaMemcpyAsync(db.p, b_rows, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, s.s_main);
+    LAUNCH(k_pair_moments, blocks_for((int64_t)n_pairs * 32, 256), 256, 0, s.s_main, s.D.as<double>(), L,
+           s.node_of_row.as<int32_t>(), ctx->last_G, da.as<int32_t>(), db.as<int32_t>(), (int)n_pairs, s.mean.as<double>(),
+           s.sxx.as<double>(), dout.as<double>());
+    cudaMemcpyAsync(out, dout.p, n_out * 8, cudaMemcpyDeviceToHost, s.s_main);
+    if (cudaStreamSynchronize(s.s_main) != cudaSuccess) rc = MDEGGS_ECUDA;
+  }
   da.release();
   db.release();
   dout.release();

@@ -1837,6 +1837,43 @@ __global__ void k_pair_features(const double* __restrict__ x, int64_t ldx, int n
   out[i] = isfinite(r) ? r : 0.0;
 }
 
+// Per-category sufficient statistics of gene pairs from the gene-major matrix and the per-gene moments that the last
+// run left on the device: what the per-category regression lines of plot_regressions need
+// (plotting_functions.R:125-162: lm(y ~ x) inside each category, predict(interval = "confidence")).  One warp per pair.
+// out[(j K + k) 6 + 0..5] = n_k, mean_A, mean_B, Sxx_A, Syy_B, Sxy;  NaN when a row is no network node of that run.
+__global__ void __launch_bounds__(256) k_pair_moments(const double* __restrict__ D, SegLayout L,
+                                                      const int32_t* __restrict__ node_of_row, int G,
+                                                      const int32_t* __restrict__ a_rows,
+                                                      const int32_t* __restrict__ b_rows, int n_pairs,
+                                                      const double* __restrict__ mean, const double* __restrict__ sxx,
+                                                      double* __restrict__ out) {
+  const int j = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (j >= n_pairs) return;
+  const int ra = a_rows[j] - 1, rb = b_rows[j] - 1;
+  const int na = (ra >= 0 && ra < G) ? node_of_row[ra] : -1, nb = (rb >= 0 && rb < G) ? node_of_row[rb] : -1;
+  for (int k = 0; k < L.K; ++k) {
+    double* o = out + ((size_t)j * L.K + k) * 6;
+    if (na < 0 || nb < 0) {
+      if (lane < 6) o[lane] = nan("");
+      continue;
+    }
+    const double ma = mean[(size_t)na * L.K + k], mb = mean[(size_t)nb * L.K + k];
+    const double* __restrict__ pa = D + (size_t)na * L.npad;
+    const double* __restrict__ pb = D + (size_t)nb * L.npad;
+    double acc = 0.0;
+    for (int i = L.off[k] + lane; i < L.off[k] + L.cnt[k]; i += 32) acc = fma(pa[i] - ma, pb[i] - mb, acc);
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      o[0] = (double)L.cnt[k];
+      o[1] = ma;
+      o[2] = mb;
+      o[3] = sxx[(size_t)na * L.K + k];
+      o[4] = sxx[(size_t)nb * L.K + k];
+      o[5] = acc;
+    }
+  }
+}
+
 // FP64 FMA peak of this GPU (denominator of the rlm roofline, SURVEY §8 d): 16 independent DFMA chains per thread
 __global__ void __launch_bounds__(256) k_dfma_peak(int iters, double seed, double* __restrict__ sink) {
   double a[16];

@@ -21,7 +21,7 @@ _LIB: C.CDLL | None = None
 # every symbol include/mdeggs.h declares (tests check the library exports all of them)
 ABI_SYMBOLS = (
     "mdeggs_create", "mdeggs_create_rank", "mdeggs_nccl_unique_id", "mdeggs_destroy", "mdeggs_run_omic",
-    "mdeggs_pair_features", "mdeggs_measure_fp64_peak", "mdeggs_measure_l2_peak", "mdeggs_last_stats",
+    "mdeggs_pair_features", "mdeggs_pair_moments", "mdeggs_measure_fp64_peak", "mdeggs_measure_l2_peak", "mdeggs_last_stats",
     "mdeggs_trace_count", "mdeggs_trace_get", "mdeggs_set_option", "mdeggs_last_error", "mdeggs_strerror", "mdeggs_abi_version",
     "mdeggs_dev_pt", "mdeggs_dev_pf_upper", "mdeggs_dev_p_two_sided_ref",
     "mdeggs_submit_omic", "mdeggs_wait", "mdeggs_run_omics",
@@ -62,6 +62,7 @@ def load_library() -> C.CDLL:
     L.mdeggs_run_omics.argtypes = [C.POINTER(vp), i, C.POINTER(_abi.CProblem), C.POINTER(_abi.CResult),
                                    C.POINTER(C.c_int)]
     L.mdeggs_pair_features.argtypes = [vp, vp, i64, C.c_int32, vp, vp, C.c_int32, C.c_int32, C.c_int32, vp]
+    L.mdeggs_pair_moments.argtypes = [vp, vp, vp, C.c_int32, vp]
     L.mdeggs_last_stats.argtypes = [vp, C.POINTER(_abi.CStats)]
     L.mdeggs_set_option.argtypes = [vp, C.c_char_p, i64]
     L.mdeggs_measure_fp64_peak.argtypes = [vp, C.POINTER(C.c_double)]
@@ -200,6 +201,16 @@ class Engine:
         self._check(self._lib.mdeggs_pair_features(self._ctx, x.ctypes.data, max(n, 1), n, a.ctypes.data,
                                                    b.ctypes.data, a.shape[0], int(ratio), _abi.MEM_HOST,
                                                    out.ctypes.data), "mdeggs_pair_features")
+        return out
+
+    def pair_moments(self, a_rows: np.ndarray, b_rows: np.ndarray, K: int) -> np.ndarray:
+        """[n_pairs, K, 6] = n_k, mean_A, mean_B, Sxx_A, Syy_B, Sxy per pair and category, from what the last run_omic of
+        this engine left on the device (the plot_regressions refit, plotting_functions.R:125-162). Rows are 1-based."""
+        a = np.ascontiguousarray(a_rows, dtype=np.int32)
+        b = np.ascontiguousarray(b_rows, dtype=np.int32)
+        out = np.empty((a.shape[0], K, 6), dtype=np.float64)
+        self._check(self._lib.mdeggs_pair_moments(self._ctx, a.ctypes.data, b.ctypes.data, a.shape[0], out.ctypes.data),
+                    "mdeggs_pair_moments")
         return out
 
     # -- device math twins (tests) --------------------------------------------------------------

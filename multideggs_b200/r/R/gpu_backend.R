@@ -190,3 +190,21 @@ get_diffNetworks_singleOmic <- function(assayData, assayDataName, metadata, regr
   rownames(out) <- rownames(x)
   out
 }
+
+# per-category regression lines of plot_regressions (plotting_functions.R:125-172) from the moments the last engine run
+# left on the device: list(intercept, slope, sigma, n, mean_x, sxx) per category, enough for abline() and for the
+# confidence band  fit +- qt(0.975, n - 2) * sigma * sqrt(1 / n + (x0 - mean_x)^2 / sxx)
+.mdeggs_pair_lines <- function(from_idx, to_idx, categories) {
+  K <- length(categories)
+  m <- .Call("mdeggs_R_pair_moments", as.integer(from_idx), as.integer(to_idx), as.integer(K))
+  lapply(seq_along(from_idx), function(j) {
+    out <- lapply(seq_len(K), function(k) {
+      v <- m[, k, j]
+      slope <- v[6] / v[4]
+      list(intercept = v[3] - slope * v[2], slope = slope, n = v[1], mean_x = v[2], sxx = v[4],
+           sigma = sqrt((v[5] - slope * v[6]) / (v[1] - 2)))
+    })
+    names(out) <- categories
+    out
+  })
+}

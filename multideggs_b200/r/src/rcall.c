@@ -298,9 +298,26 @@ SEXP mdeggs_R_pair_features(SEXP x, SEXP a, SEXP b, SEXP ratio) {
   return out;
 }
 
+/* .Call("mdeggs_R_pair_moments", from_idx, to_idx, K): per-category n, means, Sxx, Syy, Sxy of gene pairs from what the
+ * last mdeggs_R_run of this process left on the device: the lm(y ~ x) lines and confidence bands of plot_regressions
+ * (plotting_functions.R:125-172).  Returns a 6 x K x n_pairs array. */
+SEXP mdeggs_R_pair_moments(SEXP a, SEXP b, SEXP K) {
+  if (TYPEOF(a) != INTSXP || TYPEOF(b) != INTSXP || XLENGTH(a) != XLENGTH(b))
+    Rf_error("from_idx and to_idx must be integer vectors of the same length (1-based gene rows)");
+  const int np_ = (int)XLENGTH(a), k = Rf_asInteger(K);
+  if (k < 2 || k > MDEGGS_MAX_K) Rf_error("K outside 2..%d", MDEGGS_MAX_K);
+  SEXP out = PROTECT(Rf_alloc3DArray(REALSXP, 6, k, np_));
+  mdeggs_ctx* ctx = get_ctx(1);
+  int rc = mdeggs_pair_moments(ctx, INTEGER(a), INTEGER(b), np_, REAL(out));
+  UNPROTECT(1);
+  if (rc != MDEGGS_OK) Rf_error("multiDEGGs GPU engine: %s (%s)", mdeggs_strerror(rc), mdeggs_last_error(ctx));
+  return out;
+}
+
 static const R_CallMethodDef call_methods[] = {{"mdeggs_R_run", (DL_FUNC)&mdeggs_R_run, 12},
                                                {"mdeggs_R_run_layers", (DL_FUNC)&mdeggs_R_run_layers, 1},
                                                {"mdeggs_R_pair_features", (DL_FUNC)&mdeggs_R_pair_features, 4},
+                                               {"mdeggs_R_pair_moments", (DL_FUNC)&mdeggs_R_pair_moments, 3},
                                                {NULL, NULL, 0}};
 
 void R_init_multiDEGGs(DllInfo* dll) {

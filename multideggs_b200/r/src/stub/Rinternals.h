@@ -22,6 +22,7 @@ Rbyte* RAW(SEXP);
 R_xlen_t XLENGTH(SEXP);
 SEXP Rf_allocVector(unsigned int, R_xlen_t);
 SEXP Rf_allocMatrix(unsigned int, int, int);
+SEXP Rf_alloc3DArray(unsigned int, int, int, int);
 SEXP Rf_protect(SEXP);
 void Rf_unprotect(int);
 #define PROTECT(s) Rf_protect(s)

@@ -49,6 +49,52 @@ def test_random_rlm(engine, oracle, G, n, E, seed, coef, cov):
     assert_parity(gpu, ref, prob, rtol=1e-8, what=f"rlm G{G} n{n}: ")
 
 
+def test_plot_regressions_refit_from_cached_moments(engine, bundled, oracle):
+    """plot_regressions (plotting_functions.R:125-172): interaction p of the pair, the printed Padj, and per category the
+    line lm(y ~ x) with its confidence band, rebuilt from the moments the engine run left on the device
+    (mdeggs_pair_moments).  Checked against numpy fits on the bundled data and against the R-printed Padj = 0.0017 of
+    AKT2 ~ MTOR (vignettes/plot_regressions.png)."""
+    from scipy import stats as st
+    deggs = md.get_diffNetworks(assayData={k: bundled[k] for k in ("RNAseq", "Proteomics", "Olink")},
+                                metadata=bundled["metadata"], category_variable="response", regression_method="lm",
+                                padj_method="bonferroni", verbose=False, show_progressBar=False, cores=1)
+    d = md.plot_regressions_data(deggs, "RNAseq", "AKT2", "MTOR", engine=engine)
+    assert d["prefix"] == "Padj" and f"{d['sig_interaction']:.2g}" == "0.0017"
+    assay = bundled["RNAseq"]
+    fac = host.tidy_metadata(metadata=bundled["metadata"], category_variable="response")
+    grp = pd.Series(fac.values, index=fac.names)[assay.columns]
+    x, y = assay.loc["AKT2"].to_numpy(), assay.loc["MTOR"].to_numpy()
+    # interaction p: coef(summary(lm(y ~ x * g)))[4, 4] = 2 pt(-|t|)
+    st_, coef, t, p_ref = oracle.fit_lm(x, y, (grp.to_numpy() == d["categories"][1]).astype(float))
+    assert abs(d["p_interaction"] - 2 * st.t.sf(abs(t), len(x) - 4)) <= 1e-9 * d["p_interaction"]
+    for cat in d["categories"]:
+        m = (grp == cat).to_numpy()
+        slope, icpt = np.polyfit(x[m], y[m], 1)
+        L = d["lines"][cat]
+        assert abs(L["slope"] - slope) <= 1e-9 * abs(slope) and abs(L["intercept"] - icpt) <= 1e-9 * abs(icpt) + 1e-12
+        resid = y[m] - (icpt + slope * x[m])
+        sigma = np.sqrt(resid @ resid / (m.sum() - 2))
+        se = sigma * np.sqrt(1 / m.sum() + (d["new_x"] - x[m].mean()) ** 2 / np.sum((x[m] - x[m].mean()) ** 2))
+        tq = st.t.ppf(0.975, m.sum() - 2)
+        assert np.allclose(L["lwr"], icpt + slope * d["new_x"] - tq * se, rtol=1e-9, atol=1e-12)
+        assert np.allclose(L["upr"], icpt + slope * d["new_x"] + tq * se, rtol=1e-9, atol=1e-12)
+    assert len(d["new_x"]) == 100 and d["new_x"][0] < x.min() and d["new_x"][-1] > x.max()
+    # raw moments of several pairs at once, a row that is no node of the run -> NaN
+    prep = host.prepare_omic(assay, "RNAseq", fac, "lm", None, md.DEFAULT_PERCENTILES, "bonferroni")
+    engine.run_omic(prep.problem, ("best",))
+    fr, to = prep.problem.from_idx[:5], prep.problem.to_idx[:5]
+    mom = engine.pair_moments(fr, to, 2)
+    for j in range(5):
+        for k, cat in enumerate(d["categories"]):
+            m = (grp == cat).to_numpy()
+            a, b = prep.problem.assay[fr[j] - 1][m], prep.problem.assay[to[j] - 1][m]
+            want = [m.sum(), a.mean(), b.mean(), np.sum((a - a.mean()) ** 2), np.sum((b - b.mean()) ** 2),
+                    np.sum((a - a.mean()) * (b - b.mean()))]
+            assert np.allclose(mom[j, k], want, rtol=1e-10, atol=1e-12), (j, k)
+    with pytest.raises(ValueError):
+        md.plot_regressions_data(deggs, "RNAseq", "NOT_A_GENE", "MTOR", engine=engine)
+
+
 def _na_problem(K, method, padj, seed, G=60, n=96, E=400):
     """random problem with missing values in a quarter of the rows, one row with an Inf as well, and one category of one
     row reduced to a single complete case (rlm: singular, aov: aliased / fewer levels)"""
