@@ -682,11 +682,16 @@ def run_cuda(args) -> None:
             eng5 = md.Engine.for_rank(local, rank, world, bytes(uid.cpu().numpy().tobytes()))
         else:
             eng5 = eng
-        eng5.set_option("graph", 0)  # large kernels: launch overhead is irrelevant, keep the stage timings
         c5, r5, keep5 = _device_problem(torch, prob5, dev)
-        ms5, _, stage5, st5 = _timed_steps(torch, eng5, c5, r5, max(2, args.steps // 4), 2, flush, dist_sync)
-        ms5 = max_over_ranks(ms5)
         steps5 = max(2, args.steps // 4)
+        # timed with the compute phase (NCCL collectives included) replayed from a CUDA graph, like the main line; two
+        # eager steps afterwards give the per-stage times
+        eng5.set_option("graph", 1)
+        ms5, _, _, _ = _timed_steps(torch, eng5, c5, r5, steps5, 3, flush, dist_sync)
+        ms5 = max_over_ranks(ms5)
+        eng5.set_option("graph", 0)
+        _, _, stage5, st5 = _timed_steps(torch, eng5, c5, r5, 2, 1, flush, dist_sync)
+        eng5.set_option("graph", 1)
         E5, n5 = prob5.dims[2], prob5.dims[1]
         line.setdefault("also", {})["cfg5"] = {
             "workload": name5, "edges": E5, "samples": n5, "features": prob5.dims[0], "scaling": "strong",

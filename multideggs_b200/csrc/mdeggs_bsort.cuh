@@ -67,10 +67,11 @@ struct BsArgs {
   const int32_t *ea, *eb;
 };
 
-// One call per thread of a kernel that covers edges; `live` threads contribute p.  Must be reached by whole warps.
-__device__ __forceinline__ void bs_count(const BsArgs& B, bool live, int64_t e, double p) {
+// One call per thread of a kernel that covers edges; `live` threads contribute p, `tested` = the edge is tested at some
+// percentile (the others stay out of the order).  Must be reached by whole warps.
+__device__ __forceinline__ void bs_count_flag(const BsArgs& B, bool live, bool tested, int64_t e, double p) {
   const int lane = threadIdx.x & 31;
-  if (live && B.act_t && !edge_tested_any(B.act_t, B.nch, B.ea[e], B.eb[e])) {
+  if (live && !tested) {
     B.slot[e] = -1;
     live = false;
   }
@@ -83,6 +84,10 @@ __device__ __forceinline__ void bs_count(const BsArgs& B, bool live, int64_t e, 
     base = __shfl_sync(peers, base, leader);
     B.slot[e] = base + __popc(peers & ((1u << lane) - 1u));
   }
+}
+__device__ __forceinline__ void bs_count(const BsArgs& B, bool live, int64_t e, double p) {
+  const bool tested = !(live && B.act_t) || edge_tested_any(B.act_t, B.nch, B.ea[e], B.eb[e]);
+  bs_count_flag(B, live, tested, e, p);
 }
 
 // exclusive prefix of count[0..NB) by one CTA into `out` (shared or global); returns the total to every thread.
@@ -129,6 +134,14 @@ __device__ __forceinline__ int bs_scan_counts(const int* __restrict__ count, int
   }
   return carry;
 }
+
+// tail of k_percolate in multi-GPU runs: the bucket of every gathered p-value
+struct PercolateBucketTail {
+  BsArgs B;
+  __device__ __forceinline__ void operator()(bool live, bool tested, int64_t e, double p) const {
+    bs_count_flag(B, live, tested, e, p);
+  }
+};
 
 // stand-alone counting pass (multi-GPU: the p-values arrive through the all-gather, after k_finish)
 __global__ void __launch_bounds__(256) k_bsort_count(BsArgs B, const double* __restrict__ p_edge,

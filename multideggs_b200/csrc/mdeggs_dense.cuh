@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(DTHREADS, 1) k_dense_moments(const double* __r
 //   * a lane fetches its A / B fragments as 16-byte pairs of consecutive samples (s, s + 1) of one gene: the .x halves
 //     feed one m8n8k4 step and the .y halves the next (a sum over samples does not care which four go together), i.e.
 //     12 LDS.128 per 64 MMAs, each at the 4-wavefront minimum thanks to the swizzle.
-// Multi-GPU: `tile_need[ti * ntiles + tj]` (k_mark_tiles over the rank's edge block) lets a CTA whose tile holds no
+// Multi-GPU: bit ti * ntiles + tj of `tile_bits` (k_mark_tiles over the rank's edge block) lets a CTA whose tile holds no
 // edge of this rank exit at once.
 // ------------------------------------------------------------------------------------------------
 constexpr int DS = 16;                      // samples per stage (128-byte rows: the SWIZZLE_128B span)
@@ -290,7 +290,7 @@ __device__ __forceinline__ void dn_mbar_wait(uint32_t bar, uint32_t parity) {
 
 __global__ void __launch_bounds__(DENSE_TMA_THREADS, 1)
     k_dense_tma(const __grid_constant__ CUtensorMap tmap, DenseLayout Lc, SegLayout L, int nn, int ntiles,
-                const uint8_t* __restrict__ tile_need, double* __restrict__ S) {
+                const unsigned int* __restrict__ tile_bits, double* __restrict__ S) {
   extern __shared__ unsigned char dn_raw[];
   int ti = 0, rem = blockIdx.x;
   while (rem >= ntiles - ti) {
@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(DENSE_TMA_THREADS, 1)
     ++ti;
   }
   const int tj = ti + rem;
-  if (tile_need && !tile_need[ti * ntiles + tj]) return;
+  if (tile_bits && !((tile_bits[(ti * ntiles + tj) >> 5] >> ((ti * ntiles + tj) & 31)) & 1u)) return;
   const int k = blockIdx.y;
   if (L.cnt[k] == 0) return;
   const int seg_beg = Lc.off[k], nst = (Lc.off[k + 1] - Lc.off[k]) / DS;
@@ -403,18 +403,34 @@ __global__ void __launch_bounds__(DENSE_TMA_THREADS, 1)
   }
 }
 
-// multi-GPU: the 128 x 128 tiles of S that hold an edge of this rank's block
-__global__ void k_mark_tiles(const int32_t* __restrict__ ea, const int32_t* __restrict__ eb, int64_t e_lo, int64_t e_hi,
-                             int ntiles, uint8_t* __restrict__ tile_need, const int32_t* __restrict__ err) {
+// multi-GPU: the 128 x 128 tiles of S that hold an edge of this rank's block.  Each CTA marks a shared-memory bitmap and
+// publishes it with one atomic OR per non-zero word (plain stores of a million threads to the same few bytes serialise
+// in L2: measured 175 us for 10^6 edges).
+constexpr int DENSE_MARK_WORDS = 2048;  // up to 65,536 tile pairs in shared memory (256 x 256 tiles = 32,768 nodes)
+__global__ void __launch_bounds__(256) k_mark_tiles(const int32_t* __restrict__ ea, const int32_t* __restrict__ eb,
+                                                    int64_t e_lo, int64_t e_hi, int ntiles,
+                                                    unsigned int* __restrict__ tile_bits, const int32_t* __restrict__ err) {
+  __shared__ unsigned int s_bits[DENSE_MARK_WORDS];
   if (*err) return;
+  const int W = (ntiles * ntiles + 31) >> 5;
+  const bool in_smem = W <= DENSE_MARK_WORDS;
+  if (in_smem) {
+    for (int w = threadIdx.x; w < W; w += blockDim.x) s_bits[w] = 0u;
+    __syncthreads();
+  }
+  unsigned int* bits = in_smem ? s_bits : tile_bits;
   for (int64_t e = e_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < e_hi; e += (int64_t)gridDim.x * blockDim.x) {
     const int a = ea[e], b = eb[e];
-    const int i = (a < b ? a : b) / DT, j = (a < b ? b : a) / DT;
-    uint8_t* t = tile_need + i * ntiles + j;
-    if (!*t) *t = 1;
+    const int t = ((a < b ? a : b) / DT) * ntiles + (a < b ? b : a) / DT;
+    const unsigned m = 1u << (t & 31);
+    if (!(bits[t >> 5] & m)) atomicOr(&bits[t >> 5], m);
+  }
+  if (in_smem) {
+    __syncthreads();
+    for (int w = threadIdx.x; w < W; w += blockDim.x)
+      if (s_bits[w]) atomicOr(&tile_bits[w], s_bits[w]);
   }
 }
-
 // [min, max] over this rank's edges of the smaller node index of the edge: the rows of S it will read
 __global__ void k_edge_row_range(const int32_t* __restrict__ ea, const int32_t* __restrict__ eb,
                                  int64_t e_lo, int64_t e_hi,

@@ -1096,15 +1096,16 @@ int run_shard_main(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
       const int ntl = (n_nodes + DT - 1) / DT;
       dim3 grid((unsigned)(ntl * (ntl + 1) / 2), (unsigned)K);
       const bool tma = ctx->dense_path != 0 && tmap_encoder() != nullptr;
-      const uint8_t* d_need = nullptr;
+      const unsigned int* d_need = nullptr;
       const int32_t* d_range = nullptr;
       if (s.world > 1 && tma) {
-        CU(s.tile_need.ensure((size_t)ntl * ntl));
-        CU(cudaMemsetAsync(s.tile_need.p, 0, (size_t)ntl * ntl, s.s_main));
-        int64_t nb = (e_hi - e_lo + 255) / 256;
-        LAUNCH(k_mark_tiles, (unsigned)(nb < 148 * 8 ? nb : 148 * 8), 256, 0, s.s_main, s.ea.as<int32_t>(),
-               s.eb.as<int32_t>(), e_lo, e_hi, ntl, s.tile_need.as<uint8_t>(), s.scal.as<int32_t>() + 2 * SC_ERR);
-        d_need = s.tile_need.as<uint8_t>();
+        const size_t wbytes = (((size_t)ntl * ntl + 31) / 32) * 4;
+        CU(s.tile_need.ensure(wbytes));
+        CU(cudaMemsetAsync(s.tile_need.p, 0, wbytes, s.s_main));
+        int64_t nb = (e_hi - e_lo + 1023) / 1024;
+        LAUNCH(k_mark_tiles, (unsigned)(nb < 1 ? 1 : (nb < 148 * 4 ? nb : 148 * 4)), 256, 0, s.s_main, s.ea.as<int32_t>(),
+               s.eb.as<int32_t>(), e_lo, e_hi, ntl, s.tile_need.as<unsigned int>(), s.scal.as<int32_t>() + 2 * SC_ERR);
+        d_need = s.tile_need.as<unsigned int>();
       } else if (s.world > 1) {  // (cp.async form: the tile rows the block reads)
         int32_t* rr = s.scal.as<int32_t>() + 2 * SC_ROWLO;
         CU(cudaMemsetAsync(rr, 0x7f, 4, s.s_main));                     // row_range[0] = huge
@@ -1283,6 +1284,7 @@ int run_collective(mdeggs_ctx* ctx, const mdeggs_problem* in, const mdeggs_resul
   for (Shard& s : ctx->shards) {
     CU(cudaSetDevice(s.device));
     EVREC(s.ev[EV_COLL], s.s_main);
+    if (s0.world > 1 && E > 0) trace_mark(ctx, "(ncclAllGather p, status)", s.s_main);
   }
   return MDEGGS_OK;
 }
@@ -1301,6 +1303,14 @@ int run_shard_back(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
   s.select_fused = false;
   // K7 percolation (category of every edge at every percentile, counts) does not need the p order: it runs on the side
   // stream, after the activity masks, while the main stream orders the edges; both join before K8
+  // several ranks: the p-values arrived through the all-gather, so the bucket counting could not ride in k_finish; it
+  // rides in k_percolate instead (its buffers are cleared before the side stream forks off)
+  const bool count_in_percolate = do_adjust && s.world > 1 && use_bucket_order(ctx, in, n_nodes) && s.order_tested_only;
+  if (count_in_percolate) {
+    CU(s.bs_count.ensure((size_t)2 * bs_padded(bs_nbuckets(E)) * 4));
+    CU(s.bs_slot.ensure((size_t)E * 4));
+    CU(cudaMemsetAsync(s.bs_count.p, 0, (size_t)(bs_nbuckets(E) + 1) * 4, s.s_main));
+  }
   CU(cudaEventRecord(s.ev_fork, s.s_main));  // p-values and status of every edge are final
   CU(cudaStreamWaitEvent(s.s_sort, s.ev_fork, 0));
   // counters: tot[P] fail[P] sig[P] sig_raw[P] (u64), then out: tot_out[P] sig_out[P] fail_out[P] (i64)
@@ -1351,12 +1361,19 @@ int run_shard_back(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
       d_padj = s.padj.as<double>();
     }
   }
-  if (n_nodes > 0 && P > 0) {
-    if (E > 0)  // (also writes NaN into the p.adj rows of the edges that are not tested at a percentile)
-      LAUNCH(k_percolate, blocks_for(E, 256), 256, (size_t)(3 * P + (want_seg_cnt ? P * K : 0)) * sizeof(unsigned),
-             s.s_sort, s.ea.as<int32_t>(), s.eb.as<int32_t>(), s.status.as<int32_t>(), s.p_edge.as<double>(),
-             s.act_t.as<uint4>(), s.act_nch, E, P, c_tot, c_fail, c_raw, d_cat, d_padj,
-             s.scal.as<int32_t>() + 2 * SC_ERR, K, want_seg_cnt ? d_seg_cnt : nullptr);
+  if (n_nodes > 0 && P > 0 && E > 0) {
+    // (also writes NaN into the p.adj rows of the edges that are not tested at a percentile)
+    const size_t pc_smem = (size_t)(3 * P + (want_seg_cnt ? P * K : 0)) * sizeof(unsigned);
+    if (count_in_percolate) {  // several ranks: the gathered p-values are dropped into their buckets in the same pass
+      PercolateBucketTail tail{make_bs_args(s, E)};
+      LAUNCH(k_percolate<PercolateBucketTail>, blocks_for(E, 256), 256, pc_smem, s.s_sort, tail, s.ea.as<int32_t>(),
+             s.eb.as<int32_t>(), s.status.as<int32_t>(), s.p_edge.as<double>(), s.act_t.as<uint4>(), s.act_nch, E, P, c_tot,
+             c_fail, c_raw, d_cat, d_padj, s.scal.as<int32_t>() + 2 * SC_ERR, K, want_seg_cnt ? d_seg_cnt : nullptr);
+    } else {
+      LAUNCH(k_percolate<PercolateNoTail>, blocks_for(E, 256), 256, pc_smem, s.s_sort, PercolateNoTail{}, s.ea.as<int32_t>(),
+             s.eb.as<int32_t>(), s.status.as<int32_t>(), s.p_edge.as<double>(), s.act_t.as<uint4>(), s.act_nch, E, P, c_tot,
+             c_fail, c_raw, d_cat, d_padj, s.scal.as<int32_t>() + 2 * SC_ERR, K, want_seg_cnt ? d_seg_cnt : nullptr);
+    }
   }
   CU(cudaEventRecord(s.ev_join, s.s_sort));
   if (do_adjust) {
@@ -1373,7 +1390,10 @@ int run_shard_back(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
       // bucket ordering (mdeggs_bsort.cuh): counts/slots came out of k_finish (single GPU) or from a counting pass
       // over the all-gathered p-values; scatter into buckets, then one CTA per run of buckets sorts in shared memory
       BsArgs B;
-      if (s.world > 1) {
+      if (count_in_percolate) {
+        B = make_bs_args(s, E);
+        CU(cudaStreamWaitEvent(s.s_main, s.ev_join, 0));  // bucket counts (k_percolate on the side stream)
+      } else if (s.world > 1) {
         CU(s.bs_count.ensure((size_t)2 * bs_padded(bs_nbuckets(E)) * 4));
         CU(s.bs_slot.ensure((size_t)E * 4));
         CU(cudaMemsetAsync(s.bs_count.p, 0, (size_t)(bs_nbuckets(E) + 1) * 4, s.s_main));
@@ -1462,6 +1482,7 @@ int run_sig_allreduce(mdeggs_ctx* ctx, const mdeggs_problem* in, const mdeggs_re
     NC(api.AllReduce(c_sig, c_sig, (size_t)Pn, NCCL_UINT64, NCCL_SUM, s.comm, s.s_main));
   }
   NC(api.GroupEnd());
+  for (Shard& s : ctx->shards) trace_mark(ctx, "(ncclAllReduce sig counts)", s.s_main);
   return MDEGGS_OK;
 }
 
@@ -1885,7 +1906,8 @@ int mdeggs_submit_omic(mdeggs_ctx* ctx, const mdeggs_problem* in, mdeggs_result*
     return r;
   };
   int32_t n_nodes = (int32_t)(2 * in->E < (int64_t)in->G ? 2 * in->E : (int64_t)in->G);
-  bool graph_ok = ctx->use_graph && !ctx->trace && ctx->shards.size() == 1 && sh0.world == 1;
+  // (one process per GPU: the NCCL collectives of the call are captured with it, every rank captures at the same call)
+  bool graph_ok = ctx->use_graph && !ctx->trace && ctx->shards.size() == 1;
   bool replayed = false;
   if (graph_ok) {
     GraphKey key;

@@ -743,7 +743,13 @@ __device__ __forceinline__ bool edge_tested_any(const uint4* __restrict__ act_t,
 // A thread reads the packed masks of its edge's two end points (16 percentiles per 16-byte load) and walks the
 // percentiles in registers; a percentile where no edge of the warp is tested costs one ballot, the others one ballot per
 // category (the per-edge properties - hard failure, raw p < 0.05, p not NA - are warp masks computed once).
-__global__ void __launch_bounds__(256) k_percolate(const int32_t* __restrict__ ea, const int32_t* __restrict__ eb,
+// `Tail` is called once per thread at the end with (live, tested at some percentile, edge, p): multi-GPU runs drop the
+// edge into its p-value bucket there (mdeggs_bsort.cuh), one pass over the gathered p-values instead of two.
+struct PercolateNoTail {
+  __device__ __forceinline__ void operator()(bool, bool, int64_t, double) const {}
+};
+template <class Tail>
+__global__ void __launch_bounds__(256) k_percolate(Tail tail, const int32_t* __restrict__ ea, const int32_t* __restrict__ eb,
                                                    const int32_t* __restrict__ status,
                                                    const double* __restrict__ p_edge,
                                                    const uint4* __restrict__ act_t, int nch, int64_t E, int P,
@@ -773,6 +779,7 @@ __global__ void __launch_bounds__(256) k_percolate(const int32_t* __restrict__ e
   const unsigned w_hard = __ballot_sync(0xffffffffu, hard);
   const unsigned w_sig = __ballot_sync(0xffffffffu, pv < 0.05);
   const unsigned w_val = __ballot_sync(0xffffffffu, !isnan(pv));
+  unsigned tested_bits = 0u;
   for (int ch = 0; ch < nch; ++ch) {
     uint4 x = make_uint4(0u, 0u, 0u, 0u);
     if (live) {
@@ -785,7 +792,9 @@ __global__ void __launch_bounds__(256) k_percolate(const int32_t* __restrict__ e
       const int p0 = ch * 16 + q * 4;
       if (p0 >= P) break;
       // nothing tested in these four percentiles anywhere in the warp (and no row to write): next word
-      const bool any4 = __any_sync(0xffffffffu, single_bit_bytes(xw[q]) != 0u);
+      const unsigned sb4 = single_bit_bytes(xw[q]);
+      tested_bits |= sb4;
+      const bool any4 = __any_sync(0xffffffffu, sb4 != 0u);
       if (!any4 && !cat_out && !padj_nan) continue;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -812,6 +821,7 @@ __global__ void __launch_bounds__(256) k_percolate(const int32_t* __restrict__ e
       }
     }
   }
+  tail(live, tested_bits != 0u, e, pv);  // (reached by whole warps)
   __syncthreads();
   for (int i = threadIdx.x; i < P; i += blockDim.x) {
     if (s_cnt[i]) atomicAdd(&tot[i], (unsigned long long)s_cnt[i]);
