@@ -109,11 +109,11 @@ struct Shard {
     if (e == cudaSuccess) h_stage_cap = bytes + 256;
     return e;
   }
-  DevBuf act_t, Dc, tile_need, na_q, bh1_state, assay, from, to, ea, eb, stage_dev, bs_count, bs_slot, seg_done, seg_rank, fin_q, hm_p, hm_q1, hm_c, hm_sc, hm_idx, hm_off, seg_pi0, B16, stamps, excl, node_of_row, rowlist, scal, src_of_pos, pct, cutoff, D, cub_tmp, mean, sxx, med, bad, stat, status, p_edge, coef, iters, act, counters, sortk, sortk2, idx,
+  DevBuf st8, act_t, Dc, tile_need, na_q, bh1_state, assay, from, to, ea, eb, stage_dev, bs_count, bs_slot, seg_done, seg_rank, fin_q, hm_p, hm_q1, hm_c, hm_sc, hm_idx, hm_off, seg_pi0, B16, stamps, excl, node_of_row, rowlist, scal, src_of_pos, pct, cutoff, D, cub_tmp, mean, sxx, med, bad, stat, status, p_edge, coef, iters, act, counters, sortk, sortk2, idx,
       idx2, ps, sa, sb, tile_cnt, tile_base, seg_n, tile_min, tile_carry, padj_best, cat_best, cat, padj, med_out,
       small_out, rsel_hist, rsel_state, rsel_cand, dense_S, cf_tab, sxy;
   void release_all() {
-    DevBuf* all[] = {&act_t, &Dc, &tile_need, &na_q, &bh1_state, &assay, &from, &to, &ea, &eb, &stage_dev, &bs_count, &bs_slot, &seg_done, &seg_rank, &fin_q, &hm_p, &hm_q1, &hm_c, &hm_sc, &hm_idx, &hm_off, &seg_pi0, &B16, &stamps, &excl, &node_of_row, &rowlist, &scal, &src_of_pos, &pct, &cutoff,
+    DevBuf* all[] = {&st8, &act_t, &Dc, &tile_need, &na_q, &bh1_state, &assay, &from, &to, &ea, &eb, &stage_dev, &bs_count, &bs_slot, &seg_done, &seg_rank, &fin_q, &hm_p, &hm_q1, &hm_c, &hm_sc, &hm_idx, &hm_off, &seg_pi0, &B16, &stamps, &excl, &node_of_row, &rowlist, &scal, &src_of_pos, &pct, &cutoff,
                      &D, &cub_tmp, &mean, &sxx, &med, &bad, &stat, &status, &p_edge,
                      &coef, &iters, &act, &counters, &sortk, &sortk2, &idx, &idx2, &ps, &sa, &sb, &tile_cnt,
                      &tile_base, &seg_n, &tile_min, &tile_carry, &padj_best, &cat_best, &cat, &padj, &med_out,
@@ -1258,13 +1258,22 @@ int run_collective(mdeggs_ctx* ctx, const mdeggs_problem* in, const mdeggs_resul
     NcclApi& api = nccl_api();
     const int64_t chunk = (E + s0.world - 1) / s0.world;
     const bool is_rlm = (in->K == 2 && in->method == MDEGGS_METHOD_RLM);
+    for (Shard& s : ctx->shards) {  // status codes as bytes
+      CU(cudaSetDevice(s.device));
+      CU(s.st8.ensure((size_t)chunk * s0.world));
+      const int64_t lo = (int64_t)s.rank * chunk < E ? (int64_t)s.rank * chunk : E;
+      const int64_t n_own = lo + chunk < E ? chunk : E - lo;
+      if (n_own > 0)
+        LAUNCH(k_pack_status, blocks_for(n_own, 256), 256, 0, s.s_main, s.status.as<int32_t>() + lo, n_own,
+               s.st8.as<int8_t>() + lo);
+    }
     NC(api.GroupStart());
     for (Shard& s : ctx->shards) {
       CU(cudaSetDevice(s.device));
       char* pe = (char*)s.p_edge.p;
-      char* st = (char*)s.status.p;
+      char* st = (char*)s.st8.p;
       NC(api.AllGather(pe + (size_t)s.rank * chunk * 8, pe, (size_t)chunk, NCCL_FLOAT64, s.comm, s.s_main));
-      NC(api.AllGather(st + (size_t)s.rank * chunk * 4, st, (size_t)chunk, NCCL_INT32, s.comm, s.s_main));
+      NC(api.AllGather(st + (size_t)s.rank * chunk, st, (size_t)chunk, NCCL_INT8, s.comm, s.s_main));
       if (out->stat) {
         char* x = (char*)s.stat.p;
         NC(api.AllGather(x + (size_t)s.rank * chunk * 8, x, (size_t)chunk, NCCL_FLOAT64, s.comm, s.s_main));
@@ -1280,6 +1289,10 @@ int run_collective(mdeggs_ctx* ctx, const mdeggs_problem* in, const mdeggs_resul
       }
     }
     NC(api.GroupEnd());
+    for (Shard& s : ctx->shards) {
+      CU(cudaSetDevice(s.device));
+      LAUNCH(k_unpack_status, blocks_for(E, 256), 256, 0, s.s_main, s.st8.as<int8_t>(), E, s.status.as<int32_t>());
+    }
   }
   for (Shard& s : ctx->shards) {
     CU(cudaSetDevice(s.device));

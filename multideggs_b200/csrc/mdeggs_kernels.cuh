@@ -1847,6 +1847,16 @@ __global__ void k_pair_features(const double* __restrict__ x, int64_t ldx, int n
   out[i] = isfinite(r) ? r : 0.0;
 }
 
+// per-edge status codes travel between the ranks as bytes (a quarter of the all-gather's status payload)
+__global__ void k_pack_status(const int32_t* __restrict__ status, int64_t n, int8_t* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (int8_t)status[i];
+}
+__global__ void k_unpack_status(const int8_t* __restrict__ in, int64_t n, int32_t* __restrict__ status) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) status[i] = (int32_t)in[i];
+}
+
 // Per-category sufficient statistics of gene pairs from the gene-major matrix and the per-gene moments that the last
 // run left on the device: what the per-category regression lines of plot_regressions need
 // (plotting_functions.R:125-162: lm(y ~ x) inside each category, predict(interval = "confidence")).  One warp per pair.
