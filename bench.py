@@ -534,6 +534,35 @@ def run_cuda(args) -> None:
     e2e_stage = {k: v for k, v in e2e_stats.items() if k.startswith("ms_")}
     h2d, d2h = int(e2e_stats["h2d_bytes"]), int(e2e_stats["d2h_bytes"])  # bytes the engine actually moved per step
     assert int(hkeep[5]["best"].numpy()[0]) == best, "host and device legs disagree"
+    # the same job with the gene rows shuffled: the node rows are then scattered over all G rows of the host matrix
+    # instead of leading it, the band of node rows is the whole matrix, and everything crosses PCIe (a host-side gather of
+    # the node rows out of the column-major matrix would read the same 160 MB at a fraction of the link's speed)
+    e2e_shuf = None
+    if rank == 0 and world == 1:
+        rng_s = np.random.default_rng(99)
+        perm = rng_s.permutation(G)                       # new row i holds old row perm[i]
+        inv = np.empty(G, dtype=np.int64)
+        inv[perm] = np.arange(G)
+        from multideggs_b200 import _abi as _A
+        sprob = _A.Problem(assay=np.asfortranarray(prob.assay[perm]), from_idx=(inv[prob.from_idx - 1] + 1).astype(np.int32),
+                           to_idx=(inv[prob.to_idx - 1] + 1).astype(np.int32), group=prob.group, K=K, pct=prob.pct,
+                           method=prob.method, padj=prob.padj, tested_coef=prob.tested_coef, rlm_cov_mode=prob.rlm_cov_mode)
+        sp, sr, sk, _, _ = _host_problem(torch, sprob)
+        for _ in range(args.warmup):
+            eng.run_omic_raw(sp, sr)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            eng.run_omic_raw(sp, sr)
+        torch.cuda.synchronize()
+        dt_s = time.perf_counter() - t0
+        st_s = eng.stats()
+        assert int(sk[5]["best"].numpy()[0]) == best, "shuffled rows change the result"
+        e2e_shuf = {"value": E * args.steps / dt_s, "unit": UNIT, "ms_per_step": 1e3 * dt_s / args.steps,
+                    "h2d_bytes_per_step": int(st_s["h2d_bytes"]), "d2h_bytes_per_step": int(st_s["d2h_bytes"]),
+                    "note": "gene rows of the host matrix shuffled: node rows scattered over all rows, the whole matrix "
+                            "crosses PCIe"}
+        del sp, sr, sk, sprob
 
     # ---- roofline: every kernel of the step timed by CUDA events on its own stream; the headline entry is the kernel
     # with the largest time.  Denominators: HBM = MEASURED_PEAKS.json; L2 = measured here, in this run ----
@@ -603,6 +632,7 @@ def run_cuda(args) -> None:
                 "host_input_bytes": int(prob.assay.nbytes + 8 * E),
                 "api": "mdeggs_run_omic (C ABI) with pinned host buffers; only the band of network-node rows of the "
                        "assay crosses PCIe"},
+        "e2e_shuffled_rows": e2e_shuf,
         "gpu_launches": int(st["kernel_launches"]) * args.steps,
         "clocks": clocks,
         "roofline": roofline,
@@ -700,6 +730,21 @@ def run_cuda(args) -> None:
             "stage_ms": stage5, "fit_path": int(st5["fit_path"]),
             "fit_GBps_algorithmic": (E5 / world) * (16 * n5 + 16) / (stage5["ms_fit"] * 1e-3) / 1e9 if stage5["ms_fit"] > 0 else None,
             "best": int(keep5[5]["best"].cpu().numpy()[0])}
+        if world == 1:  # per-kernel times of the config-5 step and the FP64 roofline of the dense moments kernel
+            kt5 = _kernel_table(torch, eng5, c5, r5, flush, 2)
+            nn5 = int(st5["n_nodes"])
+            dense_us = next((r["us"] for r in kt5 if r["kernel"] == "k_dense_tma"), None)
+            fp64_peak = eng5.fp64_peak_tflops()
+            flops5 = float(nn5) * nn5 * n5  # nn^2 / 2 pairs x n samples x 2 flops (FMA) over all categories
+            line["also"]["cfg5"]["kernels_us"] = {r["kernel"]: round(r["us"], 1) for r in kt5 if r["us"]}
+            if dense_us:
+                line["also"]["cfg5"]["dense_roofline"] = {
+                    "kernel": "k_dense_tma", "bound": "fp64", "us": dense_us, "flops": flops5,
+                    "achieved": flops5 / (dense_us * 1e-6) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
+                    "frac": flops5 / (dense_us * 1e-6) / 1e12 / fp64_peak,
+                    "peak_source": "own DFMA-chain microbenchmark in this run (mdeggs_measure_fp64_peak)",
+                    "flops_model": "upper-triangular 128 x 128 tile pairs: nn^2 / 2 pairs x n samples x 2 flops"}
+
         def bits_equal(a, b) -> bool:  # bit for bit, NaN payloads included
             if a.dtype.is_floating_point:
                 a, b = a.view(torch.int64), b.view(torch.int64)
