@@ -964,12 +964,13 @@ int run_shard_main(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
     for (int k = 0; k < K; ++k) Ke += L.cnt[k] > 0;
     const double tdf1 = K == 2 ? 1.0 : (double)(Ke - 1), tdf2 = K == 2 ? (double)(n - 4) : (double)(n - 2 * Ke);
     const double ta = (K == 2 && !rlm2) ? 0.5 : tdf1 / 2.0;
-    CU(s.cf_tab.ensure((size_t)(2 * CF_TABLE_LEN + 1) * 8));
+    CU(s.cf_tab.ensure((size_t)CF_TABLE_DOUBLES * 8));
     // a one-CTA kernel nothing depends on until the tails: side stream (idle between the quantile sample and finish)
     CU(cudaEventRecord(s.ev_fork, s.s_main));
     CU(cudaStreamWaitEvent(s.s_sort, s.ev_fork, 0));
     LAUNCH(k_cf_tables, 1, 256, 0, s.s_sort, ta, tdf2 / 2.0, s.cf_tab.as<double>(), s.cf_tab.as<double>() + CF_TABLE_LEN,
-           s.cf_tab.as<double>() + 2 * CF_TABLE_LEN);
+           s.cf_tab.as<double>() + 2 * CF_TABLE_LEN, s.cf_tab.as<double>() + 2 * CF_TABLE_LEN + 2,
+           s.cf_tab.as<double>() + 3 * CF_TABLE_LEN + 2);
     CU(cudaEventRecord(s.ev_cf, s.s_sort));
   }
   // ---- K2 gene stats (+ K3 S3: the values of the quantile slots are appended to their lists here) ----
@@ -1194,13 +1195,15 @@ int run_shard_main(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
     tail_mode = 1;
   }
   if (e_hi > e_lo) {
-    CU(s.cf_tab.ensure((size_t)(2 * CF_TABLE_LEN + 1) * 8));
+    CU(s.cf_tab.ensure((size_t)CF_TABLE_DOUBLES * 8));
     TailConsts tc;
     tc.a = tail_mode == 0 ? 0.5 : df1 / 2.0;
     tc.b = df2 / 2.0;
     tc.lbeta_ab = 0.0;
     tc.e_ab = s.cf_tab.as<double>();
     tc.e_ba = s.cf_tab.as<double>() + CF_TABLE_LEN;
+    tc.c_ab = s.cf_tab.as<double>() + 2 * CF_TABLE_LEN + 2;
+    tc.c_ba = s.cf_tab.as<double>() + 3 * CF_TABLE_LEN + 2;
     const double* d_lbeta = s.cf_tab.as<double>() + 2 * CF_TABLE_LEN;
     const int src = is_rlm ? 2 : (use_dense ? 1 : 0);
     CU(cudaStreamWaitEvent(s.s_main, s.ev_cf, 0));  // continued-fraction tables (side stream)

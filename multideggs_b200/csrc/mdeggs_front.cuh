@@ -109,21 +109,19 @@ __device__ __forceinline__ double fr_lds(uint32_t addr) {
 
 // Exact k-th smallest (0-based) of the non-NaN values a warp holds in registers (ITEMS per lane, unused slots NaN),
 // and, when `want_next`, the (k+1)-th as well (the two middle values of an even-sized segment).
-// Same bisection in KEY space as warp_select_reg, but the values stay doubles: a counting pass is one FP64 compare per
-// item (NaN compares false = sorts above everything), and only the pivot travels between key and value space.  Once
-// <= 32 values remain in [lo, hi) they are dropped into shared memory (order irrelevant) and ranked by all pairs.
+// Bisection in KEY space, the values stay doubles: a counting pass is one FP64 compare per item (NaN compares false =
+// sorts above everything), only the pivot travels between key and value space.  The bracket starts from the caller's
+// guess [g_lo, g_hi); the minimum and maximum of the segment are only computed when the guess misses (or there is
+// none): they bound the key range the halvings have to cross.  Once <= 32 values remain in [lo, hi) each goes to one
+// lane (through shared memory, order irrelevant) and the warp quick-selects among its lanes with ballots: a pivot is
+// the value of the lowest lane still in play, ~2 ln(32) rounds of a dozen instructions instead of 32 x 32 comparisons.
 template <int ITEMS>
-__device__ __forceinline__ double warp_select_dbl(const double (&v)[ITEMS], int kth, double vmin, double vmax,
-                                                  int n_valid, double* scratch32, unsigned int* scratch_n, int lane,
-                                                  bool have_guess, double g_lo, double g_hi, bool want_next,
-                                                  double* next_out) {
-  if (vmin == vmax) {
-    *next_out = vmin;
-    return vmin;
-  }
-  unsigned long long lo = dkey(vmin), hi = dkey(vmax) + 1ull;
-  double lo_d = vmin, hi_d = 0.0;
-  bool hi_open = true;  // hi == key(vmax) + 1 has no double of its own: no upper test needed, every value is <= vmax
+__device__ __forceinline__ double warp_select_dbl(const double (&v)[ITEMS], int kth, int n_valid, double* scratch32,
+                                                  unsigned int* scratch_n, int lane, bool have_guess, double g_lo,
+                                                  double g_hi, bool want_next, double* next_out) {
+  unsigned long long lo = 0ull, hi = ~0ull;  // every non-NaN key lies in [lo, hi): dkey(NaN) == ~0
+  double lo_d = -INFINITY, hi_d = 0.0;
+  bool hi_open = true, lo_open = true;  // no value is below lo / at or above hi yet: no test needed on that side
   int cnt_lo = 0, cnt_hi = n_valid;
   auto narrow = [&](unsigned long long pk) {
     if (pk <= lo || pk >= hi) return;
@@ -135,6 +133,7 @@ __device__ __forceinline__ double warp_select_dbl(const double (&v)[ITEMS], int 
     if (c <= kth) {
       lo = pk;
       lo_d = pd;
+      lo_open = false;
       cnt_lo = c;
     } else {
       hi = pk;
@@ -146,6 +145,26 @@ __device__ __forceinline__ double warp_select_dbl(const double (&v)[ITEMS], int 
   if (have_guess) {
     narrow(dkey(g_lo));
     narrow(dkey(g_hi));
+  }
+  if (cnt_hi - cnt_lo > 32 && (lo_open || hi_open)) {
+    // the guess missed on one side (or there was none): bound that side by the segment's extreme value
+    double mn = INFINITY, mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+      mn = fr_min(mn, v[j]);
+      mx = fr_max(mx, v[j]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mn = fr_min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+      mx = fr_max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if (lo_open) {  // every value is >= mn: count below is 0
+      lo = dkey(mn);
+      lo_d = mn;
+      lo_open = false;
+    }
+    if (hi_open) hi = dkey(mx) + 1ull;  // (stays "open": every value is <= mx, no upper test needed)
   }
   while (cnt_hi - cnt_lo > 32 && hi - lo > 1ull) narrow(lo + ((hi - lo) >> 1));
   double res, nxt;
@@ -160,22 +179,43 @@ __device__ __forceinline__ double warp_select_dbl(const double (&v)[ITEMS], int 
 #pragma unroll
     for (int j = 0; j < ITEMS; ++j) {
       const double x = v[j];
-      if (x >= lo_d && (hi_open || x < hi_d)) scratch32[atomicAdd(scratch_n, 1u)] = x;
+      if ((lo_open ? x == x : x >= lo_d) && (hi_open || x < hi_d)) scratch32[atomicAdd(scratch_n, 1u)] = x;
     }
     __syncwarp();
     const int ncand = cnt_hi - cnt_lo;
     const double mine = lane < ncand ? scratch32[lane] : 0.0;
-    int r = 0;
-    for (int j = 0; j < ncand; ++j) {  // broadcast reads of the <= 32 candidates
-      const double other = scratch32[j];
-      r += (other < mine) || (other == mine && j < lane);
+    // quick-select among the lanes: `act` = lanes still in play, `want` = rank wanted among them
+    unsigned act = ncand >= 32 ? 0xffffffffu : ((1u << ncand) - 1u);
+    int want = kth - cnt_lo;
+    res = 0.0;
+    unsigned above = 0u;  // lanes known to hold values > res when the loop ends
+    for (;;) {
+      const double pv = __shfl_sync(0xffffffffu, mine, __ffs(act) - 1);
+      const bool in = (act >> lane) & 1u;
+      const unsigned lt = __ballot_sync(0xffffffffu, in && mine < pv);
+      const unsigned eq = __ballot_sync(0xffffffffu, in && mine == pv);
+      const int nlt = __popc(lt), neq = __popc(eq);
+      if (want < nlt) {
+        above |= act & ~lt;
+        act = lt;
+      } else if (want < nlt + neq) {
+        res = pv;
+        above |= act & ~(lt | eq);
+        have_next = want + 1 < nlt + neq;  // another copy of the same value follows
+        break;
+      } else {
+        want -= nlt + neq;
+        act &= ~(lt | eq);
+      }
     }
-    const int want = kth - cnt_lo;
-    const unsigned hit = __ballot_sync(0xffffffffu, lane < ncand && r == want);
-    const unsigned hit2 = __ballot_sync(0xffffffffu, lane < ncand && r == want + 1);
-    res = __shfl_sync(0xffffffffu, mine, __ffs(hit) - 1);
-    have_next = hit2 != 0u;
-    nxt = __shfl_sync(0xffffffffu, mine, have_next ? __ffs(hit2) - 1 : 0);
+    nxt = res;
+    if (want_next && !have_next) {  // smallest candidate above res (if any)
+      double mn = ((above >> lane) & 1u) ? mine : INFINITY;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mn = fr_min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+      have_next = above != 0u;
+      nxt = mn;
+    }
     __syncwarp();
   }
   if (want_next) {
@@ -208,23 +248,22 @@ __device__ __forceinline__ void front_unit(const FrontArgs& A, uint32_t sbase, c
 #pragma unroll
   for (int j = 0; j < ITEMS; ++j) v[j] = fr_lds(sbase + (tab[lane + 32 * j] ^ g8));  // NaN past the segment
   double* __restrict__ drow = A.D + (size_t)node * L.npad + off;
-  double s = 0.0, vmin = INFINITY, vmax = -INFINITY;
+  // `same`: every value of the segment equals the first one (a gene that is constant inside the category: exact zero
+  // spread, an aliased column in R).  One equality test per value; the minimum and maximum are not needed here.
+  const double v00 = __shfl_sync(0xffffffffu, v[0], 0);
+  double s = 0.0;
+  bool same = m > 0;
 #pragma unroll
   for (int j = 0; j < ITEMS; ++j) {
     const double x = v[j];
     if (lane + 32 * j < m) {
       drow[lane + 32 * j] = x;
       s += x;
+      same = same && (x == v00);
     }
-    vmin = fr_min(vmin, x);
-    vmax = fr_max(vmax, x);
   }
   s = warp_sum(s);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    vmin = fr_min(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
-    vmax = fr_max(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
-  }
+  same = __all_sync(0xffffffffu, same);
   int nn = m, nf = 0;
   if (!isfinite(s)) {  // a NaN / Inf in the segment (or an overflowing sum): count exactly
     nn = 0;
@@ -268,12 +307,14 @@ __device__ __forceinline__ void front_unit(const FrontArgs& A, uint32_t sbase, c
     mu += c;
     d2 -= d1 * c;
   }
-  if (m > 0 && vmin == vmax) {  // constant inside the category: exact zero spread (aliased column in R)
-    mu = vmin;
+  if (same) {  // constant inside the category: exact zero spread (aliased column in R)
+    mu = v00;
     d2 = 0.0;
   }
   double median = nan("");
-  if (nn > 0) {
+  if (same) {
+    median = v00;
+  } else if (nn > 0) {
     // guess bracket for the median: mean -+ c sd with c ~ 40 / m (about 32 values of a bell-shaped segment), at least
     // 2.5 standard errors of the median; a miss only costs further halvings
     bool guess = false;
@@ -286,8 +327,8 @@ __device__ __forceinline__ void front_unit(const FrontArgs& A, uint32_t sbase, c
       guess = g_hi > g_lo;
     }
     double k2;
-    const double k1 = warp_select_dbl<ITEMS>(v, (nn - 1) / 2, vmin, vmax, nn, scratch32, scratch_n, lane, guess, g_lo,
-                                             g_hi, !(nn & 1), &k2);
+    const double k1 = warp_select_dbl<ITEMS>(v, (nn - 1) / 2, nn, scratch32, scratch_n, lane, guess, g_lo, g_hi,
+                                             !(nn & 1), &k2);
     median = (nn & 1) ? k1 : __ddiv_rn(__dadd_rn(k1, k2), 2.0);
   }
   if (lane == 0) {

@@ -139,11 +139,14 @@ struct TailConsts {
   double lbeta_ab;    // log Beta(a, b)
   const double* e_ab;  // e_j for I_x(a, b),  j = 1..CF_TABLE_LEN
   const double* e_ba;  // e_j for I_x(b, a)
+  const double* c_ab;  // c_k = (a + b + k - 1) / (a + k), k = 1..CF_TABLE_LEN: term ratios of the power series of I_x(a, b)
+  const double* c_ba;  // ... of I_x(b, a)
 };
+constexpr int CF_TABLE_DOUBLES = 4 * CF_TABLE_LEN + 2;  // e_ab, e_ba, lbeta (+ pad), c_ab, c_ba
 
 // e_1 = -(a+b)/(a+1); e_{2m} = m(b-m)/((a+2m-1)(a+2m)); e_{2m+1} = -(a+m)(a+b+m)/((a+2m)(a+2m+1))
 __global__ void k_cf_tables(double a, double b, double* __restrict__ e_ab, double* __restrict__ e_ba,
-                            double* __restrict__ lbeta_out) {
+                            double* __restrict__ lbeta_out, double* __restrict__ c_ab, double* __restrict__ c_ba) {
   for (int j = threadIdx.x + 1; j <= CF_TABLE_LEN; j += blockDim.x) {
     for (int o = 0; o < 2; ++o) {
       double p = o ? b : a, q = o ? a : b;
@@ -151,10 +154,34 @@ __global__ void k_cf_tables(double a, double b, double* __restrict__ e_ab, doubl
       if (j & 1) e = -(p + m) * (p + q + m) / ((p + 2.0 * m) * (p + 2.0 * m + 1.0));
       else e = m * (q - m) / ((p + 2.0 * m - 1.0) * (p + 2.0 * m));
       (o ? e_ba : e_ab)[j - 1] = e;
+      (o ? c_ba : c_ab)[j - 1] = (p + q + (double)(j - 1)) / (p + (double)j);
     }
   }
   if (threadIdx.x == 0) *lbeta_out = lbeta_dev(a, b);
 }
+
+// Power series of the incomplete beta on the side below the mode:
+//   I_x(a, b) = x^a (1 - x)^b / (a B(a, b)) * sum_{k >= 0} t_k,   t_0 = 1,  t_k = t_{k-1} c_k x,
+// all terms positive (no cancellation), one multiply and one add per term on the dependent chain and NO division,
+// against 2 FMAs per term + a division every 4 terms for the continued fraction.  The ratio c_k x falls with k, so the
+// terms rise to a maximum near k ~ x (a + b) and then decay faster than geometrically: ~x (a + b) + 30 terms.
+// `budget` / `ok` as for beta_cf_tab.  Returns the sum.
+__device__ inline double beta_series_tab(const double* __restrict__ c, double x, int budget = CF_TABLE_LEN,
+                                         bool* ok = nullptr) {
+  double term = 1.0, sum = 1.0;
+  const int jmax = budget < CF_TABLE_LEN ? budget : CF_TABLE_LEN;
+  for (int j = 0; j < jmax; j += 4) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      term *= x * __ldg(c + j + u);
+      sum += term;
+    }
+    if (term <= 1e-18 * sum) return sum;  // (only reached on the decaying side: a rising term is >= t_0 = 1)
+  }
+  if (ok) *ok = false;
+  return -1.0;  // (callers check `ok` or the sign)
+}
+constexpr double BETA_SERIES_MAX_XAB = 14.0;  // x (a + b) up to which the series is used beyond the mode switch (~70 terms)
 
 // continued fraction value h(x) = 1/(1 + d_1/(1 + d_2/(1 + ...))), d_j = x e_j
 // `budget` (a multiple of 4) bounds the number of terms; when it is exhausted and `ok` is given, *ok = false and the
@@ -190,7 +217,10 @@ __device__ inline double beta_cf_tab(const double* __restrict__ e, double a, dou
   return beta_cf_dev(a, b, x);  // table exhausted (never seen for |t| < 40, df < 1e6): generic Lentz
 }
 
-// pbeta_xy for the run's (a, b) pair; `swapped` = the caller's first parameter is tc.b
+// pbeta_xy for the run's (a, b) pair; `swapped` = the caller's first parameter is tc.b.
+// Where x (a + b) <= 14 the power series replaces the continued fractions: below the mode switch of pbeta
+// (x < (a + 1) / (a + b + 2)) and on the stretch beyond it where the complementary fraction needs O(sqrt(max(a, b)))
+// terms (|t| up to ~5 at 2,000 degrees of freedom), as long as the wanted tail 1 - w keeps its relative accuracy.
 __device__ inline double pbeta_xy_tab(const TailConsts& tc, bool swapped, double x, double y, bool lower,
                                       int budget = CF_TABLE_LEN, bool* ok = nullptr) {
   const double a = swapped ? tc.b : tc.a, b = swapped ? tc.a : tc.b;
@@ -200,7 +230,19 @@ __device__ inline double pbeta_xy_tab(const TailConsts& tc, bool swapped, double
   double lx = (x < 0.5) ? log(x) : log1p(-y);
   double ly = (y < 0.5) ? log(y) : log1p(-x);
   double front = exp(a * lx + b * ly - tc.lbeta_ab);
-  if (x < (a + 1.0) / (a + b + 2.0)) {
+  const bool below = x < (a + 1.0) / (a + b + 2.0);
+  if (x * (a + b) <= BETA_SERIES_MAX_XAB) {  // (beyond that the series needs more terms than the fractions)
+    bool conv = true;
+    const double sum = beta_series_tab(swapped ? tc.c_ba : tc.c_ab, x, budget, &conv);
+    if (conv) {
+      const double w = front * sum / a;
+      if (below || lower || 1.0 - w >= 1e-5) return lower ? w : 1.0 - w;
+    } else if (ok) {  // out of budget: the caller retries with the full table
+      *ok = false;
+      return 0.0;
+    }
+  }
+  if (below) {
     double w = front * beta_cf_tab(swapped ? tc.e_ba : tc.e_ab, a, b, x, budget, ok) / a;
     return lower ? w : 1.0 - w;
   }

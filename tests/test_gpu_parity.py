@@ -617,7 +617,7 @@ def test_invalid_edge_index_is_reported(engine):
 
 @pytest.mark.parametrize("padj", [_abi.PADJ_BH, _abi.PADJ_HOLM, _abi.PADJ_HOCHBERG, _abi.PADJ_BY, _abi.PADJ_BONFERRONI])
 def test_bucket_order_equals_radix_sort(padj):
-    """K8 ordering through p-value buckets (default up to 4M edges) must give bit-identical adjusted values,
+    """K8 ordering through p-value buckets (default up to 2^26 edges) must give bit-identical adjusted values,
     counts and best percentile as the CUB radix-sort path, including tie groups (p == 1 self-loops, NaN)."""
     eng = md.Engine([0])
     eng.set_option("graph", 0)
