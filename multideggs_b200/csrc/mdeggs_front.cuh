@@ -482,37 +482,47 @@ __global__ void __launch_bounds__((NW + FR_PROD_WARPS) * 32, 1)
 // a slot are looked up in D (just written, L2-resident) and staged in shared memory; a CTA reserves room in a slot's
 // list with ONE global atomic per slot and flush (50,000 same-address atomics would serialise for tens of
 // microseconds), then copies its keys.  Fat slots (tie groups, never copied) only track their key range.
-constexpr int QSC_STAGE = 2048;  // staged keys per CTA (a CTA sees ~100 hits on continuous data)
+constexpr int QSC_STAGE = 2048;  // staged hits per CTA (a CTA sees ~350 on continuous data)
 constexpr int QSC_THREADS = 1024;  // one fat CTA per SM: the flush costs one same-address global atomic per slot and CTA
 __global__ void __launch_bounds__(QSC_THREADS) k_qs_compact(const double* __restrict__ D,
                                                     const unsigned short* __restrict__ B16, int npad,
                                                     const int32_t* __restrict__ n_nodes_p, QsCompactArgs Q) {
   __shared__ __align__(16) unsigned char s_tab[QSC_BINS + 16];  // [QSC_BINS] = 0xff: where padding / NaN ids land
-  __shared__ unsigned long long st_key[QSC_STAGE];
+  __shared__ unsigned long long st_key[QSC_STAGE];              // phase 1: position of the hit in D; phase 2: its key
   __shared__ unsigned char st_slot[QSC_STAGE];
+  __shared__ unsigned char s_fat[QS_MAX_T];
   __shared__ unsigned int s_n, s_cnt[QS_MAX_T], s_base[QS_MAX_T];
   const long long total = (long long)(*n_nodes_p) * npad;
   const int U = *Q.U;
   if (threadIdx.x == 0) s_n = 0u;
   if (threadIdx.x < 16) s_tab[QSC_BINS + threadIdx.x] = 0xff;
-  for (int i = threadIdx.x; i < QS_MAX_T; i += blockDim.x) s_cnt[i] = 0u;
+  for (int i = threadIdx.x; i < QS_MAX_T; i += blockDim.x) {
+    s_cnt[i] = 0u;
+    s_fat[i] = i < U ? (unsigned char)(Q.slot_fat[i] != 0) : 0;
+  }
   qsc_load_table(Q, s_tab);  // (ends with a CTA barrier)
   const long long nvec = (total + 7) >> 3;
   const uint4* __restrict__ bv = reinterpret_cast<const uint4*>(B16);
-  auto hit = [&](unsigned sl, long long idx) {  // ~0.6 % of the values
+  // Phase 1 only RECORDS the hits (position + slot): the look-up of the value in D is a dependent global load, and a
+  // warp that does it inside the scan pays its latency once per hit position (~6 of the 32 ids a lane visits per round
+  // have a hit somewhere in the warp).  Phase 2 fetches all recorded values at once, one hit per thread.
+  auto hit_direct = [&](unsigned sl, long long idx) {  // staging full (a slot bin that holds a large share of the data)
     const unsigned long long key = dkey(D[idx]);
-    if (Q.slot_fat[sl]) {
+    if (s_fat[sl]) {
       if (key < __ldcg(Q.slot_min + sl)) atomicMin(Q.slot_min + sl, key);
       if (key > __ldcg(Q.slot_max + sl)) atomicMax(Q.slot_max + sl, key);
     } else {
-      const unsigned at = atomicAdd(&s_n, 1u);
-      if (at < (unsigned)QSC_STAGE) {
-        st_key[at] = key;
-        st_slot[at] = (unsigned char)sl;
-      } else {  // staging full (a slot bin that holds a large share of the data): direct append
-        const unsigned pos = atomicAdd(Q.slot_cursor + sl, 1u);
-        if (pos < Q.slot_count[sl]) Q.cand[Q.slot_off[sl] + pos] = key;
-      }
+      const unsigned pos = atomicAdd(Q.slot_cursor + sl, 1u);
+      if (pos < Q.slot_count[sl]) Q.cand[Q.slot_off[sl] + pos] = key;
+    }
+  };
+  auto hit = [&](unsigned sl, long long idx) {  // ~0.6 % of the values
+    const unsigned at = atomicAdd(&s_n, 1u);
+    if (at < (unsigned)QSC_STAGE) {
+      st_key[at] = (unsigned long long)idx;
+      st_slot[at] = (unsigned char)sl;
+    } else {
+      hit_direct(sl, idx);
     }
   };
   auto visit = [&](const uint4& w, long long i) {
@@ -541,12 +551,24 @@ __global__ void __launch_bounds__(QSC_THREADS) k_qs_compact(const double* __rest
 #pragma unroll
     for (int r = 0; r < VPT; ++r) visit(w[r], i0 + r * (long long)blockDim.x);
   }
-  // flush: ONE global atomic per slot and CTA reserves the room, then the staged keys are copied
   __syncthreads();
   const unsigned n = s_n < (unsigned)QSC_STAGE ? s_n : (unsigned)QSC_STAGE;
   if (n == 0u) return;
-  for (unsigned i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&s_cnt[st_slot[i]], 1u);
+  // Phase 2: the values of the recorded hits; fat slots (tie groups, never copied) only track their key range
+  for (unsigned i = threadIdx.x; i < n; i += blockDim.x) {
+    const unsigned sl = st_slot[i];
+    const unsigned long long key = dkey(D[(long long)st_key[i]]);
+    st_key[i] = key;
+    if (s_fat[sl]) {
+      if (key < __ldcg(Q.slot_min + sl)) atomicMin(Q.slot_min + sl, key);
+      if (key > __ldcg(Q.slot_max + sl)) atomicMax(Q.slot_max + sl, key);
+      st_slot[i] = 0xff;  // nothing to copy
+    } else {
+      atomicAdd(&s_cnt[sl], 1u);
+    }
+  }
   __syncthreads();
+  // flush: ONE global atomic per slot and CTA reserves the room, then the staged keys are copied
   for (int sl = threadIdx.x; sl < U; sl += blockDim.x) {
     const unsigned c = s_cnt[sl];
     s_base[sl] = c ? atomicAdd(Q.slot_cursor + sl, c) : 0u;
@@ -555,6 +577,7 @@ __global__ void __launch_bounds__(QSC_THREADS) k_qs_compact(const double* __rest
   __syncthreads();
   for (unsigned i = threadIdx.x; i < n; i += blockDim.x) {
     const unsigned sl = st_slot[i];
+    if (sl == 0xffu) continue;
     const unsigned pos = s_base[sl] + atomicAdd(&s_cnt[sl], 1u);
     if (pos < Q.slot_count[sl]) Q.cand[Q.slot_off[sl] + pos] = st_key[i];
   }
