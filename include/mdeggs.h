@@ -143,7 +143,9 @@ typedef struct mdeggs_stats {
   int64_t h2d_bytes, d2h_bytes;
   int32_t fit_path;       /* bits 0-7: 0 warp-per-edge streaming, 1 dense tile cross-moments, 2 rlm IRLS;
                              bit 8: the compute phase was replayed from a CUDA graph;
-                             bit 9: K8 ordered the edges through p-value buckets (no radix sort)          */
+                             bit 9: K8 ordered the edges through p-value buckets (no radix sort);
+                             bit 10 / 11: fused front kernel fed by TMA / by its plain loader;
+                             bit 12: ... while the host matrix was still streaming in (option "h2d_pipeline")   */
   int32_t n_ranks;
   float ms_total;         /* device time of the whole pipeline (CUDA events on the engine stream)       */
   float ms_h2d, ms_gather, ms_stats, ms_quantile, ms_fit, ms_tail, ms_collective, ms_percolate, ms_adjust, ms_d2h;
@@ -215,6 +217,9 @@ int mdeggs_trace_get(const mdeggs_ctx* ctx, int i, char* name, int name_cap, int
  * "sort_path" (-1 = K8 orders the edges through p-value buckets up to 2^26 edges and with a CUB radix sort beyond
  * [default], 0 = always the radix sort, 1 = buckets whenever possible);
  * "trace" (1 = print the end time of every launch of the next calls to stderr; implies eager launches);
+ * "h2d_pipeline" (1 = the band of a column-major HOST matrix crosses PCIe in row chunks of 12 MB on two copy streams while
+ * the compute phase already runs: the TMA loader of the front kernel waits for the chunk that holds its tile [default];
+ * 0 = the whole band is copied before the compute phase starts; n > 1 = chunks of n MB);
  * "zero_copy" (1 = a pinned host assay is read by the gather kernel straight over PCIe instead of being copied first;
  * measured 2 % slower than the DMA copy on this pool's boxes, hence off by default);
  * "rsel_cap" (tests: cap the quantile candidate list so that the overflow path is exercised; 0 = default);

@@ -68,9 +68,15 @@ constexpr int64_t FIN_DEFER_MIN_EDGES = 1 << 16;  // below this a second launch 
 
 struct Shard {
   int device = 0, rank = 0, world = 1;
-  cudaStream_t s_main = nullptr, s_sort = nullptr;
+  cudaStream_t s_main = nullptr, s_sort = nullptr, s_copy = nullptr, s_copy2 = nullptr;
   cudaEvent_t ev[EV_COUNT] = {};
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_sample = nullptr, ev_cf = nullptr;
+  cudaEvent_t ev_copy_go = nullptr, ev_copy_done = nullptr, ev_copy2_done = nullptr;
+  // streamed input copy (stage_inputs): the band of a host matrix crosses PCIe in row chunks on s_copy while the
+  // compute phase already runs; chunk c is complete once gate[c] != 0 (a stream-ordered 32-bit write behind its copy)
+  bool gated = false;
+  int gate_chunks = 0;
+  int64_t gate_rows = 0;  // rows per chunk (a multiple of 16)
   nccl_comm_t comm = nullptr;
   bool smem_attr_set = false, rsel_attr_set = false, dense_attr_set = false;  // cudaFuncSetAttribute is per device
   unsigned front_attr_mask = 0;  // ... per instantiation of k_front_fused
@@ -109,11 +115,11 @@ struct Shard {
     if (e == cudaSuccess) h_stage_cap = bytes + 256;
     return e;
   }
-  DevBuf st8, act_t, Dc, tile_need, na_q, bh1_state, assay, from, to, ea, eb, stage_dev, bs_count, bs_slot, seg_done, seg_rank, fin_q, hm_p, hm_q1, hm_c, hm_sc, hm_idx, hm_off, seg_pi0, B16, stamps, excl, node_of_row, rowlist, scal, src_of_pos, pct, cutoff, D, cub_tmp, mean, sxx, med, bad, stat, status, p_edge, coef, iters, act, counters, sortk, sortk2, idx,
+  DevBuf gate, st8, act_t, Dc, tile_need, na_q, bh1_state, assay, from, to, ea, eb, stage_dev, bs_count, bs_slot, seg_done, seg_rank, fin_q, hm_p, hm_q1, hm_c, hm_sc, hm_idx, hm_off, seg_pi0, B16, stamps, excl, node_of_row, rowlist, scal, src_of_pos, pct, cutoff, D, cub_tmp, mean, sxx, med, bad, stat, status, p_edge, coef, iters, act, counters, sortk, sortk2, idx,
       idx2, ps, sa, sb, tile_cnt, tile_base, seg_n, tile_min, tile_carry, padj_best, cat_best, cat, padj, med_out,
       small_out, rsel_hist, rsel_state, rsel_cand, dense_S, cf_tab, sxy;
   void release_all() {
-    DevBuf* all[] = {&st8, &act_t, &Dc, &tile_need, &na_q, &bh1_state, &assay, &from, &to, &ea, &eb, &stage_dev, &bs_count, &bs_slot, &seg_done, &seg_rank, &fin_q, &hm_p, &hm_q1, &hm_c, &hm_sc, &hm_idx, &hm_off, &seg_pi0, &B16, &stamps, &excl, &node_of_row, &rowlist, &scal, &src_of_pos, &pct, &cutoff,
+    DevBuf* all[] = {&gate, &st8, &act_t, &Dc, &tile_need, &na_q, &bh1_state, &assay, &from, &to, &ea, &eb, &stage_dev, &bs_count, &bs_slot, &seg_done, &seg_rank, &fin_q, &hm_p, &hm_q1, &hm_c, &hm_sc, &hm_idx, &hm_off, &seg_pi0, &B16, &stamps, &excl, &node_of_row, &rowlist, &scal, &src_of_pos, &pct, &cutoff,
                      &D, &cub_tmp, &mean, &sxx, &med, &bad, &stat, &status, &p_edge,
                      &coef, &iters, &act, &counters, &sortk, &sortk2, &idx, &idx2, &ps, &sa, &sb, &tile_cnt,
                      &tile_base, &seg_n, &tile_min, &tile_carry, &padj_best, &cat_best, &cat, &padj, &med_out,
@@ -131,6 +137,7 @@ struct GraphKey {
   SegLayout L;
   const void *d_assay, *d_from, *d_to;
   int64_t row_off, ld_eff;
+  int64_t gate_rows;  // 0: the input copy is complete before the compute phase starts
   size_t dense_cap;
   const void* h_stage;  // k_select_best writes the packed small results into this pinned block
   size_t h_stage_cap;
@@ -158,6 +165,8 @@ struct mdeggs_ctx {
   int dense_path = -1;         // option "dense_path": 0 = the cp.async form of the dense moments kernel, else the TMA-fed one
   int front_path = -1;         // -1 auto, 0 separate K1 + K2 kernels, 1 fused (TMA when possible), 2 fused with the plain loader
   bool last_zc = false;        // the last call read its assay through zero copy
+  int copy_streams = 2;        // option "copy_streams": streams the chunks of a streamed input copy alternate between
+  int h2d_pipeline = 1;        // option "h2d_pipeline": 0 = the whole band is copied before the compute phase starts
   int zero_copy = 0;           // option "zero_copy": pinned host assays are read by the gather straight over PCIe
   int64_t padj_keep_cap = (int64_t)256 << 20;  // option "padj_keep_cap": largest P x E x 8 scratch kept for the best row
   int count_skip = 1;          // option "count_skip": 0 = the count-only K8 visits every tile of the p order (tests)
@@ -270,6 +279,12 @@ int init_shard(mdeggs_ctx* ctx, Shard& s) {
   CU(cudaEventCreateWithFlags(&s.ev_join, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&s.ev_sample, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&s.ev_cf, cudaEventDisableTiming));
+  CU(cudaStreamCreateWithFlags(&s.s_copy, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&s.s_copy2, cudaStreamNonBlocking));
+  CU(cudaEventCreateWithFlags(&s.ev_copy2_done, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&s.ev_copy_go, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&s.ev_copy_done, cudaEventDisableTiming));
+  CU(s.gate.ensure(GATE_MAX_CHUNKS * 4));
   CU(s.scal.ensure(SC_COUNT * 8));
   CU(cudaDeviceGetAttribute(&s.sm_count, cudaDevAttrMultiProcessorCount, s.device));
   return MDEGGS_OK;
@@ -584,12 +599,32 @@ int run_adjust(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, int n_segmen
   return MDEGGS_OK;
 }
 
+int front_prepare(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const SegLayout& L, int32_t n_nodes, FrontPlan* Pout,
+                  bool* use_tma_out, bool* ok);
+
+// cuStreamWriteValue32 (a stream-ordered, fenced 32-bit write), resolved through the runtime like the tensor-map encoder
+typedef CUresult (*stream_write32_fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+stream_write32_fn stream_write32() {
+  static stream_write32_fn fn = []() -> stream_write32_fn {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    return reinterpret_cast<stream_write32_fn>(p);
+  }();
+  return fn;
+}
+
 // Phase A (always eager): caller inputs -> device, tiny per-call tables through pinned staging.
 int stage_inputs(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const HostLayout& H, int src_device) {
   const int G = in->G, n = in->n;
   const int64_t E = in->E;
   CU(cudaSetDevice(s.device));
   CU(cudaEventRecord(s.ev[EV_START], s.s_main));
+  s.gated = false;
   // ---- inputs ----
   const size_t assay_elems = (in->layout == MDEGGS_LAYOUT_COLMAJOR) ? (size_t)in->ld * (size_t)(n - 1) + (size_t)G
                                                                    : (size_t)in->ld * (size_t)(G - 1) + (size_t)n;
@@ -649,25 +684,76 @@ int stage_inputs(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const Host
     CU(s.from.ensure((size_t)E * 4 + 4));
     CU(s.to.ensure((size_t)E * 4 + 4));
     size_t copied;
+    s.gated = false;
+    if (E > 0) {  // (the edge list first: K0 only needs it, and it is what a streamed matrix copy is hidden behind)
+      CU(cudaMemcpyAsync(s.from.p, in->from, (size_t)E * 4, cudaMemcpyHostToDevice, s.s_main));
+      CU(cudaMemcpyAsync(s.to.p, in->to, (size_t)E * 4, cudaMemcpyHostToDevice, s.s_main));
+    }
     if (in->layout == MDEGGS_LAYOUT_COLMAJOR) {
       s.ld_eff = (band + 1) & ~(int64_t)1;  // even: a TMA tensor map needs 16-byte strides
       CU(s.assay.ensure((size_t)s.ld_eff * (size_t)n * 8));
-      if (band == G && in->ld == G && s.ld_eff == G) {
+      copied = (size_t)band * n * 8;
+      // Streamed copy: when the TMA-fed front kernel serves the call, the band crosses PCIe in row chunks on s_copy and
+      // the compute phase starts at once: K0 and the graph launch hide behind the first chunk, the front kernel works
+      // on chunk c while chunk c + 1 is in flight (its loader waits on gate[c], mdeggs_kernels.cuh: gate_wait).
+      int64_t chunk_rows = 0;
+      int chunks = 0;
+      if (ctx->h2d_pipeline && E > 0 && stream_write32()) {
+        const size_t chunk_bytes = (size_t)(ctx->h2d_pipeline > 1 ? ctx->h2d_pipeline : 12) << 20;
+        int64_t c = (int64_t)(copied / chunk_bytes);
+        c = c > GATE_MAX_CHUNKS ? GATE_MAX_CHUNKS : c;
+        if (c >= 2) {
+          chunk_rows = (((band + c - 1) / c) + 15) & ~(int64_t)15;
+          chunks = (int)((band + chunk_rows - 1) / chunk_rows);
+          FrontPlan FP;
+          bool tma = false, ok = false;
+          const int64_t cap = 2 * E < (int64_t)G ? 2 * E : (int64_t)G;
+          int rc = front_prepare(ctx, s, in, H.L, (int32_t)cap, &FP, &tma, &ok);
+          if (rc) return rc;
+          if (!ok || !tma || chunks < 2) chunks = 0;
+        }
+      }
+      if (chunks >= 2) {
+        s.gated = true;
+        s.gate_rows = chunk_rows;
+        s.gate_chunks = chunks;
+        // (the copy streams do not wait for s_main: the previous call of this context has been waited for, so nothing
+        // reads the device copy or the gate words any more)
+        CU(cudaMemsetAsync(s.gate.p, 0, GATE_MAX_CHUNKS * 4, s.s_copy));
+        CU(cudaEventRecord(s.ev_copy_go, s.s_copy));
+        // chunks alternate between two copy streams: the set-up of one chunk's DMA and the flag write behind the other
+        // (~10 us per chunk on one stream) no longer leave the link idle; chunks may then land slightly out of order,
+        // which the loader tolerates (it waits for the chunk of its own tile)
+        const int ncs = ctx->copy_streams >= 2 ? 2 : 1;
+        cudaStream_t cs[2] = {s.s_copy, s.s_copy2};
+        for (int i = 1; i < ncs; ++i) CU(cudaStreamWaitEvent(cs[i], s.ev_copy_go, 0));
+        for (int c = 0; c < chunks; ++c) {
+          const int64_t r0 = (int64_t)c * chunk_rows;
+          const int64_t rows = band - r0 < chunk_rows ? band - r0 : chunk_rows;
+          cudaStream_t st = cs[c % ncs];
+          CU(cudaMemcpy2DAsync(s.assay.as<double>() + r0, (size_t)s.ld_eff * 8, in->assay + r_lo + r0,
+                               (size_t)in->ld * 8, (size_t)rows * 8, (size_t)n, cudaMemcpyHostToDevice, st));
+          if (stream_write32()((CUstream)st, (CUdeviceptr)(s.gate.as<unsigned int>() + c), 1u, 0u) != CUDA_SUCCESS) {
+            set_err(ctx, "cuStreamWriteValue32 failed");
+            return MDEGGS_ECUDA;
+          }
+        }
+        if (ncs == 2) {
+          CU(cudaEventRecord(s.ev_copy2_done, s.s_copy2));
+          CU(cudaStreamWaitEvent(s.s_copy, s.ev_copy2_done, 0));
+        }
+        CU(cudaEventRecord(s.ev_copy_done, s.s_copy));
+      } else if (band == G && in->ld == G && s.ld_eff == G) {
         CU(cudaMemcpyAsync(s.assay.p, in->assay, (size_t)G * n * 8, cudaMemcpyHostToDevice, s.s_main));
       } else {
         CU(cudaMemcpy2DAsync(s.assay.p, (size_t)s.ld_eff * 8, in->assay + r_lo, (size_t)in->ld * 8, (size_t)band * 8,
                              (size_t)n, cudaMemcpyHostToDevice, s.s_main));
       }
-      copied = (size_t)band * n * 8;
     } else {
       s.ld_eff = in->ld;
       copied = ((size_t)in->ld * (size_t)(band - 1) + (size_t)n) * 8;
       CU(s.assay.ensure(copied));
       CU(cudaMemcpyAsync(s.assay.p, in->assay + (size_t)r_lo * in->ld, copied, cudaMemcpyHostToDevice, s.s_main));
-    }
-    if (E > 0) {
-      CU(cudaMemcpyAsync(s.from.p, in->from, (size_t)E * 4, cudaMemcpyHostToDevice, s.s_main));
-      CU(cudaMemcpyAsync(s.to.p, in->to, (size_t)E * 4, cudaMemcpyHostToDevice, s.s_main));
     }
     ctx->stats.h2d_bytes += (int64_t)(copied + (size_t)E * 8);
     d_assay = s.assay.as<double>();
@@ -759,7 +845,9 @@ int run_shard_front(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, int32_t
     CU(cudaStreamWaitEvent(s.s_sort, s.ev_fork, 0));
     const int S = QS_SAMPLE;
     LAUNCH(k_qs_sample, 1, QS_SAMPLE_THREADS, 0, s.s_sort, s.assay.as<double>(), s.ld_eff, s.row_off,
-           in->layout == MDEGGS_LAYOUT_COLMAJOR ? 1 : 0, d_from, d_to, E, G, n, S, s.rsel_state.as<QsState>());
+           in->layout == MDEGGS_LAYOUT_COLMAJOR ? 1 : 0, d_from, d_to, E, G, n, S, s.rsel_state.as<QsState>(),
+           s.gated ? s.gate.as<unsigned int>() : (const unsigned int*)nullptr, s.gate_rows,
+           (int32_t*)nullptr);  // (K0's memset of the error flag runs beside this kernel: the front kernel reports)
     CU(cudaEventRecord(s.ev_sample, s.s_sort));
   }
   // ---- K0 node filter ----
@@ -822,10 +910,13 @@ int launch_front_inst(mdeggs_ctx* ctx, Shard& s, const FrontArgs& A, const Front
   return MDEGGS_OK;
 }
 
-// returns MDEGGS_OK and *done = true when the fused kernel was launched; *done = false: use the separate K1 + K2
-int launch_front(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const SegLayout& L, int32_t n_nodes, bool do_q,
-                 unsigned int cand_cap, bool* done) {
-  *done = false;
+// Shape of the fused front kernel for this call and, when the device copy of the matrix can be described by one, its
+// tensor map (cached in the shard).  *ok = false: the separate K1 + K2 kernels serve the call.  Called by stage_inputs
+// (the streamed input copy needs to know whether the TMA-fed kernel will run) and by launch_front.
+int front_prepare(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const SegLayout& L, int32_t n_nodes, FrontPlan* Pout,
+                  bool* use_tma_out, bool* ok) {
+  *ok = false;
+  *use_tma_out = false;
   if (ctx->front_path == 0 || ctx->last_zc || n_nodes <= 0) return MDEGGS_OK;
   int max_cnt = 0;
   for (int k = 0; k < L.K; ++k) max_cnt = L.cnt[k] > max_cnt ? L.cnt[k] : max_cnt;
@@ -854,6 +945,24 @@ int launch_front(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const SegL
       }
     }
   }
+  *Pout = P;
+  *use_tma_out = use_tma;
+  *ok = true;
+  return MDEGGS_OK;
+}
+
+// returns MDEGGS_OK and *done = true when the fused kernel was launched; *done = false: use the separate K1 + K2
+int launch_front(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const SegLayout& L, int32_t n_nodes, bool do_q,
+                 unsigned int cand_cap, bool* done) {
+  *done = false;
+  FrontPlan P{};
+  bool use_tma = false, ok = false;
+  {
+    int rc = front_prepare(ctx, s, in, L, n_nodes, &P, &use_tma, &ok);
+    if (rc) return rc;
+  }
+  if (!ok) return MDEGGS_OK;
+  const bool colmajor = in->layout == MDEGGS_LAYOUT_COLMAJOR;
   FrontArgs A;
   memset(&A, 0, sizeof A);
   A.assay = s.assay.as<double>();
@@ -885,6 +994,12 @@ int launch_front(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const SegL
   A.box1 = P.box1;
   A.stages = P.stages;
   A.stage_bytes = P.stage_bytes;
+  if (s.gated && use_tma) {  // (stage_inputs only streams the copy when this kernel, TMA-fed, serves the call)
+    A.gate = s.gate.as<unsigned int>();
+    A.gate_rows = (int)s.gate_rows;
+    A.gate_chunks = s.gate_chunks;
+    A.err = s.scal.as<int32_t>() + 2 * SC_ERR;
+  }
   const int n_tiles = A.tile_hi - A.tile_lo;
   if (n_tiles <= 0) return MDEGGS_OK;
   const unsigned grid = (unsigned)(n_tiles < s.sm_count ? n_tiles : s.sm_count);
@@ -907,6 +1022,7 @@ int launch_front(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const SegL
 #undef MDEGGS_FR
   if (rc) return rc;
   s.front_bits = use_tma ? 0x400 : 0x800;  // fit_path bit 10: fused front kernel fed by TMA, bit 11: by the plain loader
+  if (A.gate) s.front_bits |= 0x1000;      // bit 12: ... while the input copy was still streaming in (stage_inputs)
   *done = true;
   return MDEGGS_OK;
 }
@@ -1822,6 +1938,8 @@ int mdeggs_destroy(mdeggs_ctx* ctx) {
     if (s.ev_cf) cudaEventDestroy(s.ev_cf);
     if (s.s_main) cudaStreamDestroy(s.s_main);
     if (s.s_sort) cudaStreamDestroy(s.s_sort);
+    if (s.s_copy) cudaStreamDestroy(s.s_copy);
+    if (s.s_copy2) cudaStreamDestroy(s.s_copy2);
   }
   delete ctx;
   return MDEGGS_OK;
@@ -1938,6 +2056,7 @@ int mdeggs_submit_omic(mdeggs_ctx* ctx, const mdeggs_problem* in, mdeggs_result*
     key.d_to = sh0.to.p;
     key.row_off = sh0.row_off;
     key.ld_eff = sh0.ld_eff;
+    key.gate_rows = sh0.gated ? sh0.gate_rows : 0;
     key.dense_cap = sh0.dense_S.cap;
     key.h_stage = sh0.h_stage;
     key.h_stage_cap = sh0.h_stage_cap;
@@ -2002,6 +2121,12 @@ int mdeggs_submit_omic(mdeggs_ctx* ctx, const mdeggs_problem* in, mdeggs_result*
     rc = enqueue_compute(&n_nodes);
     if (rc) return rc;
   }
+  for (Shard& s : ctx->shards)  // a streamed input copy ends inside the compute phase: the call is not over before it
+    if (s.gated) {
+      CU(cudaSetDevice(s.device));
+      CU(cudaStreamWaitEvent(s.s_main, s.ev_copy_done, 0));
+    }
+  CU(cudaSetDevice(sh0.device));
   const auto t_host1 = std::chrono::steady_clock::now();
   // ---- phase C: outputs (eager; device callers of a replayed graph already have them) ----
   if (replayed && in->mem == MDEGGS_MEM_DEVICE) {
@@ -2055,6 +2180,10 @@ int mdeggs_wait(mdeggs_ctx* ctx) {
   {
     int32_t err_flag = 0;
     finish_small_outputs(s0, in, out, &n_nodes, &err_flag);
+    if (err_flag == GATE_ERR) {
+      set_err(ctx, "the streamed input copy did not arrive (option h2d_pipeline = 0 disables it)");
+      return MDEGGS_ECUDA;
+    }
     if (err_flag != 0) {
       set_err(ctx, "from/to contain an index outside 1..G");
       return MDEGGS_EINVAL;
@@ -2134,6 +2263,14 @@ int mdeggs_set_option(mdeggs_ctx* ctx, const char* name, int64_t value) {
   if (!strcmp(name, "rsel_cap")) {
     ctx->rsel_cap_override = value;
     ctx->key_valid = false;
+    return MDEGGS_OK;
+  }
+  if (!strcmp(name, "h2d_pipeline")) {  // 0 off, 1 on (12 MB chunks), > 1: chunk size in MB
+    ctx->h2d_pipeline = (int)value;
+    return MDEGGS_OK;
+  }
+  if (!strcmp(name, "copy_streams")) {
+    ctx->copy_streams = (int)value;
     return MDEGGS_OK;
   }
   if (!strcmp(name, "zero_copy")) {

@@ -50,6 +50,11 @@ struct FrontArgs {
   int tile_lo, tile_hi;        // tiles (blocks of GB absolute rows) to visit
   int nbox, box1, stages;
   uint32_t stage_bytes;
+  // streamed input copy: rows of chunk c = [row_off + c gate_rows, row_off + (c + 1) gate_rows) are on the device once
+  // gate[c] != 0 (null: the whole matrix is there); only the TMA loader honours it (it reads through L2, never L1)
+  const unsigned int* gate;
+  int gate_rows, gate_chunks;
+  int32_t* err;
 };
 
 // ---- PTX helpers (mbarrier pipeline, TMA) --------------------------------------------------------
@@ -403,10 +408,19 @@ __global__ void __launch_bounds__((NW + FR_PROD_WARPS) * 32, 1)
     // ===== producers =====
     const int ptid = tid - NW * 32;
     if (!A.use_tma || ptid == 0) {
-      int it = 0;
+      int it = 0, chunk_ready = -1;
       for (int t = A.tile_lo + (int)blockIdx.x; t < A.tile_hi; t += (int)gridDim.x) {
         int nb;
         if (!tile_bits(t, &nb)) continue;
+        if (A.gate) {  // the chunk that holds the tile's last row (chunks land in order)
+          int c = (int)(((int64_t)t * GB + (GB - 1) - A.row_off) / A.gate_rows);
+          c = c < A.gate_chunks ? c : A.gate_chunks - 1;
+          if (c > chunk_ready) {
+            gate_wait(A.gate, c, A.err);
+            asm volatile("fence.proxy.async.global;" ::: "memory");  // the TMA reads what the copy engine wrote
+            chunk_ready = c;
+          }
+        }
         const int stg = it % S, use = it / S;
         const uint32_t full = bar0 + 8 * stg, empty = bar0 + 8 * (FR_MAX_STAGES + stg);
         if (use > 0) fr_mbar_wait(empty, (uint32_t)(use - 1) & 1u);

@@ -43,6 +43,32 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+// Streamed input copy (engine: stage_inputs).  The band of a host matrix crosses PCIe in row chunks on a copy stream
+// while the compute phase already runs; behind every chunk the copy stream performs a stream-ordered 32-bit write
+// (cuStreamWriteValue32: fenced after the chunk's DMA) of gate[c] = 1.  A kernel that is about to read rows of chunk c
+// polls the word with a system-scope acquire load.  Everything a kernel waits for was enqueued BEFORE the kernel, so
+// the wait always ends; the time-out (2 s of the global timer) only guards against a failed copy: it raises the
+// device error flag (value 2) and lets the kernel run on.
+constexpr int GATE_MAX_CHUNKS = 32;
+constexpr int GATE_ERR = 2;
+__device__ __forceinline__ void gate_wait(const unsigned int* __restrict__ gate, int c, int32_t* __restrict__ err) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(gate + c) : "memory");
+  if (v) return;
+  unsigned long long t0, t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (;;) {
+    __nanosleep(200);
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(gate + c) : "memory");
+    if (v) return;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    if (t - t0 > 2000000000ull) {
+      if (err) atomicMax(err, GATE_ERR);
+      return;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // K0: node filter   (core_functions.R:333-336: nodes <- unique(c(from,to)); assayData[rownames %in% nodes,])
 //   k_mark_nodes : every CTA marks the end points of its edges in a shared-memory bitmap of the G rows (G/8 bytes;

@@ -122,41 +122,63 @@ __global__ void __launch_bounds__(QS_SAMPLE_THREADS) k_qs_sample(const double* _
                                                                  int64_t row_off, int colmajor,
                                                                  const int32_t* __restrict__ from,
                                                                  const int32_t* __restrict__ to, int64_t E, int G,
-                                                                 int n, int S, QsState* __restrict__ st) {
+                                                                 int n, int S, QsState* __restrict__ st,
+                                                                 const unsigned int* __restrict__ gate,
+                                                                 int64_t row_limit, int32_t* __restrict__ err) {
   // Rows are drawn through the edge list (end points of edges ARE the node rows), so the kernel needs nothing from
   // K0 and runs beside it.  Hub genes are drawn more often: harmless, the sample only shapes the bins.
+  // Streamed input copy (`gate` != null): only the first chunk of rows, [0, row_limit) of the device copy, is waited
+  // for and sampled; draws that land elsewhere are dropped and the drawing is repeated (other edges of the same strata)
+  // until the sample is three quarters full.  A sample that is not representative only unbalances the bins.
   __shared__ unsigned long long sk[QS_SAMPLE_MAX];
   __shared__ int s_m;
   const long long ends = 2 * E;
   const long long total = ends * n;
-  if (threadIdx.x == 0) s_m = 0;
+  if (threadIdx.x == 0) {
+    s_m = 0;
+    if (gate) gate_wait(gate, 0, err);
+  }
   for (int i = threadIdx.x; i < S; i += blockDim.x) sk[i] = ~0ull;
   __syncthreads();
   auto row_of_end = [&](long long j) -> int64_t {  // j in [0, 2E): from[0..E) then to[0..E); -1 when out of range
     const int r = (j < E ? from[j] : to[j - E]) - 1;
-    return (r >= 0 && r < G) ? (int64_t)r - row_off : -1;
+    if (r < 0 || r >= G) return -1;
+    const int64_t rel = (int64_t)r - row_off;
+    return (gate && (rel < 0 || rel >= row_limit)) ? -1 : rel;
   };
   if (total > S) {
     const unsigned jit = (unsigned)(ends / S + 1);
-    for (int i0 = 0; i0 < S; i0 += 2 * QS_SAMPLE_THREADS) {  // 2 independent draws per thread in flight
-      int64_t off[2];
-      double v[2];
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int i = i0 + u * QS_SAMPLE_THREADS + threadIdx.x;
-        const unsigned h = (unsigned)i * 2654435761u;
-        long long j = ((long long)i * ends) / S + (long long)((h >> 20) % jit);
-        j = j < ends ? j : ends - 1;
-        const int smp = (int)((h >> 4) % (unsigned)n);
-        const int64_t row = i < S ? row_of_end(j) : -1;
-        off[u] = row < 0 ? -1 : (colmajor ? row + (int64_t)smp * ld : row * ld + smp);
+    const int rounds = gate ? 12 : 1;
+    for (int rd = 0; rd < rounds; ++rd) {
+      if (rd > 0) {  // (uniform decision: nobody adds to s_m between the two barriers)
+        __syncthreads();
+        const int have = s_m;
+        __syncthreads();
+        if (have >= S - S / 4) break;
       }
+      for (int i0 = 0; i0 < S; i0 += 2 * QS_SAMPLE_THREADS) {  // 2 independent draws per thread in flight
+        int64_t off[2];
+        double v[2];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) v[u] = off[u] >= 0 ? __ldg(assay + off[u]) : nan("");
+        for (int u = 0; u < 2; ++u) {
+          const int i = i0 + u * QS_SAMPLE_THREADS + threadIdx.x;
+          const unsigned h = (unsigned)(i + rd * S) * 2654435761u;
+          long long j = ((long long)i * ends) / S + (long long)((h >> 20) % jit);
+          j = j < ends ? j : ends - 1;
+          const int smp = (int)((h >> 4) % (unsigned)n);
+          const int64_t row = i < S ? row_of_end(j) : -1;
+          off[u] = row < 0 ? -1 : (colmajor ? row + (int64_t)smp * ld : row * ld + smp);
+        }
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const unsigned long long k = dkey(v[u]);
-        if (k != ~0ull) sk[atomicAdd(&s_m, 1)] = k;
+        for (int u = 0; u < 2; ++u) v[u] = off[u] >= 0 ? __ldg(assay + off[u]) : nan("");
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const unsigned long long k = dkey(v[u]);
+          if (k != ~0ull) {
+            const int at = atomicAdd(&s_m, 1);
+            if (at < S) sk[at] = k;
+          }
+        }
       }
     }
   } else {
@@ -169,7 +191,7 @@ __global__ void __launch_bounds__(QS_SAMPLE_THREADS) k_qs_sample(const double* _
     }
   }
   __syncthreads();
-  const int m = s_m;
+  const int m = s_m < S ? s_m : S;
   // bitonic sort of the S slots (unused slots hold the maximum key and stay at the end), one pair per thread and
   // step.  For j <= 32 the 32 pairs of a warp live in its own 64 consecutive slots, so those steps (45 of the 55)
   // only need a warp barrier; a CTA barrier is needed when the step that follows reaches across warps.

@@ -1159,3 +1159,27 @@ def test_onepass_adjustment_equals_three_pass(padj, K, E, seed):
     for k in want:
         assert np.array_equal(res[0][k], res[1][k], equal_nan=True), k
     eng.close()
+
+
+@pytest.mark.parametrize("chunk_mb", [1, 2])
+def test_streamed_input_copy_equals_plain_copy(oracle, chunk_mb):
+    """Host matrices cross PCIe in row chunks while the compute phase already runs (option h2d_pipeline; the front
+    kernel's TMA loader waits for the chunk of its tile, the quantile sample only draws from the first chunk): every
+    output equals the copy-first run bit for bit, eagerly and replayed from the CUDA graph, and matches the oracle."""
+    prob = synth.random_problem(2600, 700, 4000, 3, 7711)   # 14.6 MB column-major
+    ref = oracle.run_omic(prob, ALL_FIELDS)
+    eng = md.Engine([0])
+    eng.set_option("h2d_pipeline", 0)
+    plain = eng.run_omic(prob, ALL_FIELDS)
+    assert not int(eng.stats()["fit_path"]) & 0x1000
+    assert_parity(plain, ref, prob, what="copy first: ")
+    eng.set_option("h2d_pipeline", chunk_mb)
+    for rep in range(4):                                     # the third call captures the graph, the fourth replays it
+        got = eng.run_omic(prob, ALL_FIELDS)
+        bits = int(eng.stats()["fit_path"])
+        assert bits & 0x1000, hex(bits)
+        if rep == 3:
+            assert bits & 0x100, hex(bits)
+        for k in ALL_FIELDS:
+            assert np.array_equal(got[k], plain[k], equal_nan=True), (k, rep)
+    eng.close()
