@@ -535,9 +535,10 @@ def run_cuda(args) -> None:
     h2d, d2h = int(e2e_stats["h2d_bytes"]), int(e2e_stats["d2h_bytes"])  # bytes the engine actually moved per step
     assert int(hkeep[5]["best"].numpy()[0]) == best, "host and device legs disagree"
     # the same job with the gene rows shuffled: the node rows are then scattered over all G rows of the host matrix
-    # instead of leading it, the band of node rows is the whole matrix, and everything crosses PCIe (a host-side gather of
-    # the node rows out of the column-major matrix would read the same 160 MB at a fraction of the link's speed)
+    # instead of leading it and the band of node rows is the whole matrix; the engine's host threads gather the node rows
+    # into pinned staging chunk by chunk (option host_pack) and only those 67 MB cross PCIe, behind the enqueued compute
     e2e_shuf = None
+    e2e_page = None
     if rank == 0 and world == 1:
         rng_s = np.random.default_rng(99)
         perm = rng_s.permutation(G)                       # new row i holds old row perm[i]
@@ -560,9 +561,30 @@ def run_cuda(args) -> None:
         assert int(sk[5]["best"].numpy()[0]) == best, "shuffled rows change the result"
         e2e_shuf = {"value": E * args.steps / dt_s, "unit": UNIT, "ms_per_step": 1e3 * dt_s / args.steps,
                     "h2d_bytes_per_step": int(st_s["h2d_bytes"]), "d2h_bytes_per_step": int(st_s["d2h_bytes"]),
-                    "note": "gene rows of the host matrix shuffled: node rows scattered over all rows, the whole matrix "
-                            "crosses PCIe"}
+                    "host_packed": bool(int(st_s["fit_path"]) & 0x2000),
+                    "note": "gene rows of the host matrix shuffled: node rows scattered over all 20,000 rows; the engine's "
+                            "host threads pack the node rows into pinned staging in row chunks, each chunk is sent while "
+                            "the next is packed and the front kernel consumes them as they land (option host_pack)"}
         del sp, sr, sk, sprob
+        # the matrix in PAGEABLE host memory (what R hands to the .Call shim: an R matrix is never pinned)
+        from multideggs_b200 import _abi as _A2
+        pc = prob.to_c()
+        pr, parr = _A2.alloc_result(prob.dims, ("p_edge", "stat", "status", "tot_edges", "sig_count", "best", "cat_best",
+                                                "padj_best"))
+        e2e_page = {"unit": "ms per step", "note": "same job, assay / edge list / results in pageable numpy memory"}
+        for label, hp in (("host_pack_0_driver_staged_copy", 0), ("host_pack_1", 1)):
+            eng.set_option("host_pack", hp)
+            for _ in range(args.warmup):
+                eng.run_omic_raw(pc, pr)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                eng.run_omic_raw(pc, pr)
+            torch.cuda.synchronize()
+            e2e_page[label] = 1e3 * (time.perf_counter() - t0) / args.steps
+            assert int(parr["best"][0]) == best, "pageable leg disagrees"
+        eng.set_option("host_pack", 1)
+        del pc, pr, parr
 
     # ---- roofline: every kernel of the step timed by CUDA events on its own stream; the headline entry is the kernel
     # with the largest time.  Denominators: HBM = MEASURED_PEAKS.json; L2 = measured here, in this run ----
@@ -633,6 +655,7 @@ def run_cuda(args) -> None:
                 "api": "mdeggs_run_omic (C ABI) with pinned host buffers; only the band of network-node rows of the "
                        "assay crosses PCIe"},
         "e2e_shuffled_rows": e2e_shuf,
+        "e2e_pageable": e2e_page,
         "gpu_launches": int(st["kernel_launches"]) * args.steps,
         "clocks": clocks,
         "roofline": roofline,

@@ -145,7 +145,8 @@ typedef struct mdeggs_stats {
                              bit 8: the compute phase was replayed from a CUDA graph;
                              bit 9: K8 ordered the edges through p-value buckets (no radix sort);
                              bit 10 / 11: fused front kernel fed by TMA / by its plain loader;
-                             bit 12: ... while the host matrix was still streaming in (option "h2d_pipeline")   */
+                             bit 12: ... while the host matrix was still streaming in (option "h2d_pipeline");
+                             bit 13: the call ran on host-packed node rows (option "host_pack")                  */
   int32_t n_ranks;
   float ms_total;         /* device time of the whole pipeline (CUDA events on the engine stream)       */
   float ms_h2d, ms_gather, ms_stats, ms_quantile, ms_fit, ms_tail, ms_collective, ms_percolate, ms_adjust, ms_d2h;
@@ -195,6 +196,14 @@ int mdeggs_pair_features(mdeggs_ctx* ctx, const double* x, int64_t ldx, int32_t 
  * se(fit at x0)^2 = sigma^2 (1 / n_k + (x0 - mean_A)^2 / Sxx_A). */
 int mdeggs_pair_moments(mdeggs_ctx* ctx, const int32_t* a_rows, const int32_t* b_rows, int32_t n_pairs, double* out);
 
+/* Host-only utility (no GPU needed), the packing step of option "host_pack" on its own: the rows of the column-major
+ * G x n matrix `src` (leading dimension ld) that are end points of the edge list (core_functions.R:333-336) are gathered,
+ * in ascending row order, into the column-major block dst (leading dimension ld_dst >= node count) by the engine's pool
+ * of packing threads, in row chunks of chunk_rows (0 = one chunk).  rows_out (optional) receives the 0-based source row
+ * of every packed row, *n_nodes the node count; dst == NULL only counts. */
+int mdeggs_host_pack_rows(const double* src, int64_t ld, int32_t G, int32_t n, const int32_t* from, const int32_t* to,
+                          int64_t E, int32_t chunk_rows, double* dst, int64_t ld_dst, int32_t* rows_out, int32_t* n_nodes);
+
 /* Measures this GPU's FP64 FMA peak with a register-only DFMA-chain kernel (TFLOP/s): the denominator of the
  * rlm (K6) roofline, which is FP64-pipe bound (SURVEY section 8 d). */
 int mdeggs_measure_fp64_peak(mdeggs_ctx* ctx, double* tflops_out);
@@ -220,6 +229,11 @@ int mdeggs_trace_get(const mdeggs_ctx* ctx, int i, char* name, int name_cap, int
  * "h2d_pipeline" (1 = the band of a column-major HOST matrix crosses PCIe in row chunks of 12 MB on two copy streams while
  * the compute phase already runs: the TMA loader of the front kernel waits for the chunk that holds its tile [default];
  * 0 = the whole band is copied before the compute phase starts; n > 1 = chunks of n MB);
+ * "host_pack" (1 = a column-major host matrix that is PAGEABLE, or whose network-node rows cover less than 3/4 of the
+ * band they span, is not copied as it is: worker threads gather exactly the node rows into pinned staging, row chunk by
+ * row chunk, and every finished chunk is sent while the next one is packed and while the front kernel already works
+ * on the chunks that arrived; the call then runs on the packed problem, results are identical [default]; 0 = never;
+ * 2 = whenever the input is a column-major host matrix; MDEGGS_PACK_THREADS caps the threads [all the process may use]);
  * "zero_copy" (1 = a pinned host assay is read by the gather kernel straight over PCIe instead of being copied first;
  * measured 2 % slower than the DMA copy on this pool's boxes, hence off by default);
  * "rsel_cap" (tests: cap the quantile candidate list so that the overflow path is exercised; 0 = default);

@@ -10,7 +10,7 @@ CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
 OUT = os.path.join(CSRC, "libmdeggs.so")
 SOURCES = ["mdeggs_engine.cu"]
-HEADERS = ["mdeggs_kernels.cuh", "mdeggs_napair.cuh", "mdeggs_front.cuh", "mdeggs_math.cuh", "mdeggs_rlm.cuh", "mdeggs_dense.cuh", "mdeggs_qsel.cuh", "mdeggs_bsort.cuh", "mdeggs_qvalue_tab.h", "nccl_dl.h",
+HEADERS = ["mdeggs_kernels.cuh", "mdeggs_napair.cuh", "mdeggs_front.cuh", "mdeggs_hostpack.h", "mdeggs_math.cuh", "mdeggs_rlm.cuh", "mdeggs_dense.cuh", "mdeggs_qsel.cuh", "mdeggs_bsort.cuh", "mdeggs_qvalue_tab.h", "nccl_dl.h",
            os.path.join(ROOT, "include", "mdeggs.h")]
 
 
@@ -18,7 +18,7 @@ def nvcc_cmd(ptxas_verbose: bool = False) -> list[str]:
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
            "-Xcompiler", "-fPIC,-O3", "-shared", "-ccbin", "g++", "-I", os.path.join(ROOT, "include"), "-I", CSRC,
-           "-o", OUT] + [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl"]
+           "-o", OUT] + [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl", "-lpthread"]
     if ptxas_verbose:
         cmd[1:1] = ["-Xptxas", "-v"]
     return cmd

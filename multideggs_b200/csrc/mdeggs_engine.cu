@@ -19,7 +19,9 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include <chrono>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "mdeggs.h"
@@ -30,6 +32,7 @@
 #include "mdeggs_napair.cuh"
 #include "mdeggs_qsel.cuh"
 #include "mdeggs_front.cuh"
+#include "mdeggs_hostpack.h"
 #include "nccl_dl.h"
 
 using namespace mdeggs;
@@ -146,6 +149,7 @@ struct GraphKey {
 struct mdeggs_ctx {
   std::vector<Shard> shards;
   std::string err;
+  std::mutex err_mu;  // (the packing thread of a streamed host-packed call may report an error too)
   mdeggs_stats stats;
   int64_t launches = 0;
   // CUDA-graph replay of the compute phase (K0..K8) for repeated calls with identical shapes and buffers
@@ -165,6 +169,22 @@ struct mdeggs_ctx {
   int dense_path = -1;         // option "dense_path": 0 = the cp.async form of the dense moments kernel, else the TMA-fed one
   int front_path = -1;         // -1 auto, 0 separate K1 + K2 kernels, 1 fused (TMA when possible), 2 fused with the plain loader
   bool last_zc = false;        // the last call read its assay through zero copy
+  // host-side packing of the node rows into pinned staging (mdeggs_hostpack.h)
+  int host_pack = 1;           // option "host_pack": 0 off, 1 auto (pageable or scattered node rows), 2 whenever possible
+  struct HostPack {
+    bool active = false;       // this call runs on the packed problem `in2`
+    bool deferred = false;     // ... and its chunks still have to be packed + sent (submit decides when, see there)
+    bool last_packed = false;  // the last completed call was packed: mdeggs_pair_moments translates row numbers
+    std::vector<int32_t> rows, rank;
+    std::vector<double> med_tmp;   // medians of the packed problem [K x nodes]; mdeggs_wait spreads them over [K x G]
+    double* user_median = nullptr;
+    int32_t user_G = 0;
+    mdeggs_result out2;
+    mdeggs_problem in2;
+    void* h_buf = nullptr;     // pinned: packed matrix | from' | to'
+    size_t h_cap = 0;
+    PackJob job;
+  } pack;
   int copy_streams = 2;        // option "copy_streams": streams the chunks of a streamed input copy alternate between
   int h2d_pipeline = 1;        // option "h2d_pipeline": 0 = the whole band is copied before the compute phase starts
   int zero_copy = 0;           // option "zero_copy": pinned host assays are read by the gather straight over PCIe
@@ -207,6 +227,7 @@ void set_err(mdeggs_ctx* c, const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(buf, sizeof buf, fmt, ap);
   va_end(ap);
+  std::lock_guard<std::mutex> lk(c->err_mu);
   c->err = buf;
 }
 
@@ -618,6 +639,131 @@ stream_write32_fn stream_write32() {
   return fn;
 }
 
+
+// ---- streamed input copy: chunk geometry is in the shard (gate_rows, gate_chunks), see stage_inputs ----
+int copy_chunks_begin(mdeggs_ctx* ctx, Shard& s) {
+  // (the copy streams do not wait for s_main: the previous call of this context has been waited for, so nothing reads
+  // the device copy or the gate words any more)
+  CU(cudaMemsetAsync(s.gate.p, 0, GATE_MAX_CHUNKS * 4, s.s_copy));
+  CU(cudaEventRecord(s.ev_copy_go, s.s_copy));
+  if (ctx->copy_streams >= 2) CU(cudaStreamWaitEvent(s.s_copy2, s.ev_copy_go, 0));
+  // the gates are closed before any kernel of this call can look at them (and the memset never has to find room on an
+  // SM beside the waiting front kernel)
+  CU(cudaStreamWaitEvent(s.s_main, s.ev_copy_go, 0));
+  return MDEGGS_OK;
+}
+// chunk c = rows [c gate_rows, ...) of a column-major host block whose row 0 is `src` (leading dimension ld_src)
+int copy_chunk(mdeggs_ctx* ctx, Shard& s, int c, const double* src, int64_t ld_src, int64_t total_rows, int n) {
+  // chunks alternate between two copy streams: the set-up of one chunk's DMA and the flag write behind the other
+  // (~10 us per chunk on one stream) no longer leave the link idle; chunks may then land slightly out of order,
+  // which the loader tolerates (it waits for the chunk of its own tile)
+  cudaStream_t st = (ctx->copy_streams >= 2 && (c & 1)) ? s.s_copy2 : s.s_copy;
+  const int64_t r0 = (int64_t)c * s.gate_rows;
+  const int64_t rows = total_rows - r0 < s.gate_rows ? total_rows - r0 : s.gate_rows;
+  CU(cudaMemcpy2DAsync(s.assay.as<double>() + r0, (size_t)s.ld_eff * 8, src + r0, (size_t)ld_src * 8, (size_t)rows * 8,
+                       (size_t)n, cudaMemcpyHostToDevice, st));
+  if (stream_write32()((CUstream)st, (CUdeviceptr)(s.gate.as<unsigned int>() + c), 1u, 0u) != CUDA_SUCCESS) {
+    set_err(ctx, "cuStreamWriteValue32 failed");
+    return MDEGGS_ECUDA;
+  }
+  return MDEGGS_OK;
+}
+int copy_chunks_end(mdeggs_ctx* ctx, Shard& s) {
+  if (ctx->copy_streams >= 2) {
+    CU(cudaEventRecord(s.ev_copy2_done, s.s_copy2));
+    CU(cudaStreamWaitEvent(s.s_copy, s.ev_copy2_done, 0));
+  }
+  CU(cudaEventRecord(s.ev_copy_done, s.s_copy));
+  return MDEGGS_OK;
+}
+
+// ---- host-side packing (mdeggs_hostpack.h) ----
+// Decides whether this call runs on the packed problem and prepares it: node rows, renumbered edge list in pinned
+// staging, the packing job.  The matrix itself is packed by run_host_pack.
+int plan_host_pack(mdeggs_ctx* ctx, const mdeggs_problem* in) {
+  mdeggs_ctx::HostPack& K = ctx->pack;
+  K.active = false;
+  K.deferred = false;
+  if (!ctx->host_pack || in->mem != MDEGGS_MEM_HOST || in->layout != MDEGGS_LAYOUT_COLMAJOR || in->E <= 0 ||
+      in->E > ((int64_t)1 << 20) || ctx->shards.size() != 1 || ctx->zero_copy)
+    return MDEGGS_OK;
+  const size_t min_bytes = ctx->host_pack >= 2 ? 0 : ((size_t)2 << 20);
+  if ((size_t)in->G * (size_t)in->n * 8 < min_bytes) return MDEGGS_OK;  // small matrices: the plain copy is as good
+  pack_node_rows(in->from, in->to, in->E, in->G, K.rows, K.rank);
+  const int64_t nn = (int64_t)K.rows.size();
+  if (nn == 0 || (size_t)nn * (size_t)in->n * 8 < min_bytes) return MDEGGS_OK;
+  const int64_t band = (int64_t)K.rows.back() - K.rows.front() + 1;
+  if (ctx->host_pack < 2) {
+    bool pageable = true;
+    cudaPointerAttributes pa;
+    if (cudaPointerGetAttributes(&pa, in->assay) == cudaSuccess) pageable = pa.type == cudaMemoryTypeUnregistered;
+    else cudaGetLastError();
+    // pinned and (nearly) contiguous node rows: the streamed band copy moves the same bytes without touching them
+    if (!pageable && 4 * nn > 3 * band) return MDEGGS_OK;
+  }
+  const int64_t ld_p = (nn + 1) & ~(int64_t)1;
+  const size_t mat_bytes = (size_t)ld_p * (size_t)in->n * 8;
+  const size_t need = mat_bytes + 2 * (size_t)in->E * 4 + 64;
+  if (need > K.h_cap) {
+    if (K.h_buf) cudaFreeHost(K.h_buf);
+    K.h_buf = nullptr;
+    K.h_cap = 0;
+    CU(cudaMallocHost(&K.h_buf, need + need / 8));
+    K.h_cap = need + need / 8;
+  }
+  int32_t* hf = reinterpret_cast<int32_t*>(static_cast<char*>(K.h_buf) + mat_bytes);
+  int32_t* ht = hf + in->E;
+  const int32_t G = in->G;
+  for (int64_t e = 0; e < in->E; ++e) {  // 1-based node ranks; an index outside 1..G stays invalid (0): the device reports it
+    const int32_t a = in->from[e], b = in->to[e];
+    hf[e] = (a >= 1 && a <= G) ? K.rank[(size_t)a - 1] + 1 : 0;
+    ht[e] = (b >= 1 && b <= G) ? K.rank[(size_t)b - 1] + 1 : 0;
+  }
+  K.in2 = *in;
+  K.in2.G = (int32_t)nn;
+  K.in2.ld = ld_p;
+  K.in2.assay = static_cast<const double*>(K.h_buf);
+  K.in2.from = hf;
+  K.in2.to = ht;
+  K.job = PackJob();
+  K.job.src = in->assay;
+  K.job.ld_src = in->ld;
+  K.job.dst = static_cast<double*>(K.h_buf);
+  K.job.ld_dst = ld_p;
+  K.job.rows = K.rows.data();
+  K.job.nn = (int)nn;
+  K.job.n_cols = in->n;
+  K.job.contiguous = band == nn;
+  K.active = true;
+  return MDEGGS_OK;
+}
+
+// Packs the node rows into the pinned staging with the pool.  streamed: chunk by chunk with the shard's gate geometry,
+// every finished chunk is sent at once (the compute phase is already enqueued and waits on the gates); otherwise the
+// staging is simply filled and the caller copies it.
+int run_host_pack(mdeggs_ctx* ctx, Shard& s, bool streamed) {
+  mdeggs_ctx::HostPack& K = ctx->pack;
+  PackJob& J = K.job;
+  J.chunk_rows = streamed ? s.gate_rows : (int64_t)J.nn;
+  J.chunks = streamed ? s.gate_chunks : 1;
+  J.units_per_chunk = (J.n_cols + PACK_COL_BLOCK - 1) / PACK_COL_BLOCK;
+  HostPool& pool = HostPool::get();
+  struct Guard {
+    HostPool& p;
+    ~Guard() { p.finish(); }
+  };
+  int rc = MDEGGS_OK;
+  pool.start(J);  // (streamed: stage_inputs has closed the gates, copy_chunks_begin)
+  Guard g{pool};
+  for (int c = 0; c < J.chunks; ++c) {
+    while (!pool.chunk_done(c))
+      if (!pool.help()) _mm_pause();
+    if (streamed && (rc = copy_chunk(ctx, s, c, J.dst, J.ld_dst, J.nn, J.n_cols))) return rc;
+  }
+  if (streamed) rc = copy_chunks_end(ctx, s);
+  return rc;
+}
+
 // Phase A (always eager): caller inputs -> device, tiny per-call tables through pinned staging.
 int stage_inputs(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const HostLayout& H, int src_device) {
   const int G = in->G, n = in->n;
@@ -699,7 +845,8 @@ int stage_inputs(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const Host
       int64_t chunk_rows = 0;
       int chunks = 0;
       if (ctx->h2d_pipeline && E > 0 && stream_write32()) {
-        const size_t chunk_bytes = (size_t)(ctx->h2d_pipeline > 1 ? ctx->h2d_pipeline : 12) << 20;
+        // (a packed matrix is produced by the host at about the speed of the link: finer chunks, earlier first DMA)
+        const size_t chunk_bytes = (size_t)(ctx->h2d_pipeline > 1 ? ctx->h2d_pipeline : (ctx->pack.active ? 4 : 12)) << 20;
         int64_t c = (int64_t)(copied / chunk_bytes);
         c = c > GATE_MAX_CHUNKS ? GATE_MAX_CHUNKS : c;
         if (c >= 2) {
@@ -713,36 +860,23 @@ int stage_inputs(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const Host
           if (!ok || !tma || chunks < 2) chunks = 0;
         }
       }
+      if (ctx->pack.active && chunks < 2) {  // packed, but not streamed: fill the staging now, the plain copy moves it
+        int rc = run_host_pack(ctx, s, false);
+        if (rc) return rc;
+      }
       if (chunks >= 2) {
         s.gated = true;
         s.gate_rows = chunk_rows;
         s.gate_chunks = chunks;
-        // (the copy streams do not wait for s_main: the previous call of this context has been waited for, so nothing
-        // reads the device copy or the gate words any more)
-        CU(cudaMemsetAsync(s.gate.p, 0, GATE_MAX_CHUNKS * 4, s.s_copy));
-        CU(cudaEventRecord(s.ev_copy_go, s.s_copy));
-        // chunks alternate between two copy streams: the set-up of one chunk's DMA and the flag write behind the other
-        // (~10 us per chunk on one stream) no longer leave the link idle; chunks may then land slightly out of order,
-        // which the loader tolerates (it waits for the chunk of its own tile)
-        const int ncs = ctx->copy_streams >= 2 ? 2 : 1;
-        cudaStream_t cs[2] = {s.s_copy, s.s_copy2};
-        for (int i = 1; i < ncs; ++i) CU(cudaStreamWaitEvent(cs[i], s.ev_copy_go, 0));
-        for (int c = 0; c < chunks; ++c) {
-          const int64_t r0 = (int64_t)c * chunk_rows;
-          const int64_t rows = band - r0 < chunk_rows ? band - r0 : chunk_rows;
-          cudaStream_t st = cs[c % ncs];
-          CU(cudaMemcpy2DAsync(s.assay.as<double>() + r0, (size_t)s.ld_eff * 8, in->assay + r_lo + r0,
-                               (size_t)in->ld * 8, (size_t)rows * 8, (size_t)n, cudaMemcpyHostToDevice, st));
-          if (stream_write32()((CUstream)st, (CUdeviceptr)(s.gate.as<unsigned int>() + c), 1u, 0u) != CUDA_SUCCESS) {
-            set_err(ctx, "cuStreamWriteValue32 failed");
-            return MDEGGS_ECUDA;
-          }
+        int rc = copy_chunks_begin(ctx, s);
+        if (rc) return rc;
+        if (ctx->pack.active) {
+          ctx->pack.deferred = true;  // packed + sent chunk by chunk once the compute phase is enqueued (submit)
+        } else {
+          for (int c = 0; c < chunks && !rc; ++c) rc = copy_chunk(ctx, s, c, in->assay + r_lo, in->ld, band, n);
+          if (!rc) rc = copy_chunks_end(ctx, s);
+          if (rc) return rc;
         }
-        if (ncs == 2) {
-          CU(cudaEventRecord(s.ev_copy2_done, s.s_copy2));
-          CU(cudaStreamWaitEvent(s.s_copy, s.ev_copy2_done, 0));
-        }
-        CU(cudaEventRecord(s.ev_copy_done, s.s_copy));
       } else if (band == G && in->ld == G && s.ld_eff == G) {
         CU(cudaMemcpyAsync(s.assay.p, in->assay, (size_t)G * n * 8, cudaMemcpyHostToDevice, s.s_main));
       } else {
@@ -1923,6 +2057,7 @@ int mdeggs_create_rank(mdeggs_ctx** out, int device_id, int rank, int world, con
 int mdeggs_destroy(mdeggs_ctx* ctx) {
   if (!ctx) return MDEGGS_OK;
   if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
+  if (ctx->pack.h_buf) cudaFreeHost(ctx->pack.h_buf);
   for (cudaEvent_t e : ctx->trace_pool) cudaEventDestroy(e);
   for (Shard& s : ctx->shards) {
     cudaSetDevice(s.device);
@@ -2006,8 +2141,22 @@ int mdeggs_submit_omic(mdeggs_ctx* ctx, const mdeggs_problem* in, mdeggs_result*
     return MDEGGS_EINVAL;
   }
   const auto t_host0 = std::chrono::steady_clock::now();
+  int rc = plan_host_pack(ctx, in);
+  if (rc) return rc;
+  if (ctx->pack.active) {  // from here on the call runs on the packed problem (mdeggs_hostpack.h)
+    mdeggs_ctx::HostPack& K = ctx->pack;
+    K.user_median = out->median;
+    K.user_G = in->G;
+    in = &K.in2;
+    if (out->median) {  // the only output indexed by matrix row: produced for the packed rows, spread by mdeggs_wait
+      K.med_tmp.resize((size_t)in->K * (size_t)in->G);
+      K.out2 = *out;
+      K.out2.median = K.med_tmp.data();
+      out = &K.out2;
+    }
+  }
   HostLayout H;
-  int rc = build_layout(ctx, in, H);
+  rc = build_layout(ctx, in, H);
   if (rc) return rc;
   ctx->launches = 0;
   memset(&ctx->stats, 0, sizeof ctx->stats);
@@ -2116,9 +2265,22 @@ int mdeggs_submit_omic(mdeggs_ctx* ctx, const mdeggs_problem* in, mdeggs_result*
       replayed = true;
     }
   }
+  // Streamed host packing.  A replayed graph is ONE launch with nothing after it that could block this thread, so the
+  // packing runs behind it: the kernels wait on the gates and the front kernel works on the chunks as they land.
+  // Eager launches may block half-way (a growing scratch buffer is a cudaFree, which waits for the device - and the
+  // device would wait for the gates): there the chunks are packed and sent first, overlapping each other only.
   if (!replayed) {
+    if (ctx->pack.deferred) {
+      ctx->pack.deferred = false;
+      rc = run_host_pack(ctx, sh0, true);
+      if (rc) return rc;
+    }
     ctx->launches = 0;
     rc = enqueue_compute(&n_nodes);
+    if (rc) return rc;
+  }
+  if (ctx->pack.deferred) {
+    rc = run_host_pack(ctx, sh0, true);
     if (rc) return rc;
   }
   for (Shard& s : ctx->shards)  // a streamed input copy ends inside the compute phase: the call is not over before it
@@ -2212,7 +2374,17 @@ int mdeggs_wait(mdeggs_ctx* ctx) {
       prev[sid] = t;
     }
   }
+  if (ctx->pack.active && ctx->pack.user_median) {
+    const mdeggs_ctx::HostPack& K = ctx->pack;
+    const size_t Gu = (size_t)K.user_G, nn = K.rows.size();
+    for (int k = 0; k < in->K; ++k) {
+      double* dst = K.user_median + (size_t)k * Gu;
+      for (size_t g = 0; g < Gu; ++g) dst[g] = nan("");
+      for (size_t i = 0; i < nn; ++i) dst[(size_t)K.rows[i]] = K.med_tmp[(size_t)k * nn + i];
+    }
+  }
   ctx->last_valid = n_nodes > 0;
+  ctx->pack.last_packed = ctx->pack.active;
   ctx->last_L = ctx->pend.L;
   ctx->last_G = in->G;
   // ---- stats ----
@@ -2227,6 +2399,7 @@ int mdeggs_wait(mdeggs_ctx* ctx) {
   st.ms_total = ev_ms(s0.ev[EV_START], s0.ev[EV_END]);
   st.ms_h2d = ev_ms(s0.ev[EV_START], s0.ev[EV_H2D]);
   st.ms_d2h = ev_ms(s0.ev[EV_ADJ], s0.ev[EV_END]);
+  if (ctx->pack.active) st.fit_path |= 0x2000;  // bit 13: the call ran on host-packed node rows (mdeggs_hostpack.h)
   if (use_bucket_order(ctx, in, n_nodes)) st.fit_path |= 0x200;  // bit 9: K8 ordering by p-value buckets (no radix sort)
   if (replayed) {  // graph replay: no stage boundaries inside the graph; everything between H2D and D2H is compute
     st.fit_path |= 0x100;  // bit 8 flags "replayed from a CUDA graph"
@@ -2267,6 +2440,10 @@ int mdeggs_set_option(mdeggs_ctx* ctx, const char* name, int64_t value) {
   }
   if (!strcmp(name, "h2d_pipeline")) {  // 0 off, 1 on (12 MB chunks), > 1: chunk size in MB
     ctx->h2d_pipeline = (int)value;
+    return MDEGGS_OK;
+  }
+  if (!strcmp(name, "host_pack")) {
+    ctx->host_pack = (int)value;
     return MDEGGS_OK;
   }
   if (!strcmp(name, "copy_streams")) {
@@ -2401,6 +2578,37 @@ int mdeggs_pair_features(mdeggs_ctx* ctx, const double* x, int64_t ldx, int32_t 
   return rc;
 }
 
+int mdeggs_host_pack_rows(const double* src, int64_t ld, int32_t G, int32_t n, const int32_t* from, const int32_t* to,
+                          int64_t E, int32_t chunk_rows, double* dst, int64_t ld_dst, int32_t* rows_out, int32_t* n_nodes) {
+  if (!src || !from || !to || !n_nodes || G < 1 || n < 1 || E < 0 || ld < G) return MDEGGS_EINVAL;
+  std::vector<int32_t> rows, rank;
+  pack_node_rows(from, to, E, G, rows, rank);
+  *n_nodes = (int32_t)rows.size();
+  if (!dst) return MDEGGS_OK;  // (count only)
+  if (ld_dst < (int64_t)rows.size() || rows.empty()) return rows.empty() ? MDEGGS_OK : MDEGGS_EINVAL;
+  if (rows_out) memcpy(rows_out, rows.data(), rows.size() * 4);
+  PackJob J;
+  J.src = src;
+  J.ld_src = ld;
+  J.dst = dst;
+  J.ld_dst = ld_dst;
+  J.rows = rows.data();
+  J.nn = (int)rows.size();
+  J.n_cols = n;
+  J.contiguous = (int64_t)rows.back() - rows.front() + 1 == (int64_t)rows.size();
+  J.chunk_rows = chunk_rows > 0 ? chunk_rows : J.nn;
+  J.chunks = (int)((J.nn + J.chunk_rows - 1) / J.chunk_rows);
+  if (J.chunks > PACK_MAX_CHUNKS) return MDEGGS_EINVAL;
+  J.units_per_chunk = (n + PACK_COL_BLOCK - 1) / PACK_COL_BLOCK;
+  HostPool& pool = HostPool::get();
+  pool.start(J);
+  for (int c = 0; c < J.chunks; ++c)
+    while (!pool.chunk_done(c))
+      if (!pool.help()) _mm_pause();
+  pool.finish();
+  return MDEGGS_OK;
+}
+
 int mdeggs_pair_moments(mdeggs_ctx* ctx, const int32_t* a_rows, const int32_t* b_rows, int32_t n_pairs, double* out) {
   if (!ctx || !a_rows || !b_rows || !out || n_pairs < 0) return MDEGGS_EINVAL;
   if (ctx->pend.active) {
@@ -2422,6 +2630,19 @@ int mdeggs_pair_moments(mdeggs_ctx* ctx, const int32_t* a_rows, const int32_t* b
       dout.ensure(n_out * 8) != cudaSuccess) {
     rc = MDEGGS_ENOMEM;
   } else {
+    std::vector<int32_t> ta, tb;
+    if (ctx->pack.last_packed) {  // the last call ran on the packed problem: rows of the caller's matrix -> node ranks
+      const std::vector<int32_t>& rk = ctx->pack.rank;
+      ta.resize((size_t)n_pairs);
+      tb.resize((size_t)n_pairs);
+      for (int32_t j = 0; j < n_pairs; ++j) {
+        // (1-based on both sides; a row that was no node maps to 0 = invalid)
+        ta[(size_t)j] = (a_rows[j] >= 1 && (size_t)a_rows[j] <= rk.size()) ? rk[(size_t)a_rows[j] - 1] + 1 : 0;
+        tb[(size_t)j] = (b_rows[j] >= 1 && (size_t)b_rows[j] <= rk.size()) ? rk[(size_t)b_rows[j] - 1] + 1 : 0;
+      }
+      a_rows = ta.data();
+      b_rows = tb.data();
+    }
     cudaMemcpyAsync(da.p, a_rows, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, s.s_main);
     cudaMemcpyAsync(db.p, b_rows, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, s.s_main);
     LAUNCH(k_pair_moments, blocks_for((int64_t)n_pairs * 32, 256), 256, 0, s.s_main, s.D.as<double>(), L,

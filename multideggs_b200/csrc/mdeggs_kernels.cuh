@@ -47,7 +47,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 // while the compute phase already runs; behind every chunk the copy stream performs a stream-ordered 32-bit write
 // (cuStreamWriteValue32: fenced after the chunk's DMA) of gate[c] = 1.  A kernel that is about to read rows of chunk c
 // polls the word with a system-scope acquire load.  Everything a kernel waits for was enqueued BEFORE the kernel, so
-// the wait always ends; the time-out (2 s of the global timer) only guards against a failed copy: it raises the
+// the wait always ends; the time-out (10 s of the global timer) only guards against a failed copy: it raises the
 // device error flag (value 2) and lets the kernel run on.
 constexpr int GATE_MAX_CHUNKS = 32;
 constexpr int GATE_ERR = 2;
@@ -62,7 +62,7 @@ __device__ __forceinline__ void gate_wait(const unsigned int* __restrict__ gate,
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(gate + c) : "memory");
     if (v) return;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    if (t - t0 > 2000000000ull) {
+    if (t - t0 > 10000000000ull) {
       if (err) atomicMax(err, GATE_ERR);
       return;
     }

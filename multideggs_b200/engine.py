@@ -21,7 +21,7 @@ _LIB: C.CDLL | None = None
 # every symbol include/mdeggs.h declares (tests check the library exports all of them)
 ABI_SYMBOLS = (
     "mdeggs_create", "mdeggs_create_rank", "mdeggs_nccl_unique_id", "mdeggs_destroy", "mdeggs_run_omic",
-    "mdeggs_pair_features", "mdeggs_pair_moments", "mdeggs_measure_fp64_peak", "mdeggs_measure_l2_peak", "mdeggs_last_stats",
+    "mdeggs_pair_features", "mdeggs_pair_moments", "mdeggs_host_pack_rows", "mdeggs_measure_fp64_peak", "mdeggs_measure_l2_peak", "mdeggs_last_stats",
     "mdeggs_trace_count", "mdeggs_trace_get", "mdeggs_set_option", "mdeggs_last_error", "mdeggs_strerror", "mdeggs_abi_version",
     "mdeggs_dev_pt", "mdeggs_dev_pf_upper", "mdeggs_dev_p_two_sided_ref",
     "mdeggs_submit_omic", "mdeggs_wait", "mdeggs_run_omics",
@@ -30,6 +30,29 @@ ABI_SYMBOLS = (
 
 class EngineError(RuntimeError):
     pass
+
+
+def host_pack_rows(assay: np.ndarray, from_idx: np.ndarray, to_idx: np.ndarray, chunk_rows: int = 0):
+    """The packing step of option "host_pack" on its own (host threads only, no GPU): the network-node rows of a
+    column-major matrix gathered in ascending row order. Returns (packed [nodes x n, Fortran order], rows 0-based)."""
+    lib = load_library()
+    a = np.asfortranarray(assay, dtype=np.float64)
+    G, n = a.shape
+    f = np.ascontiguousarray(from_idx, dtype=np.int32)
+    t = np.ascontiguousarray(to_idx, dtype=np.int32)
+    nn = C.c_int32(0)
+    rc = lib.mdeggs_host_pack_rows(a.ctypes.data, G, G, n, f.ctypes.data, t.ctypes.data, f.shape[0], 0, None, 0, None,
+                                   C.byref(nn))
+    if rc != 0:
+        raise EngineError(f"mdeggs_host_pack_rows failed: {lib.mdeggs_strerror(rc).decode()}")
+    out = np.full((nn.value, n), np.nan, dtype=np.float64, order="F")
+    rows = np.zeros(nn.value, dtype=np.int32)
+    if nn.value:
+        rc = lib.mdeggs_host_pack_rows(a.ctypes.data, G, G, n, f.ctypes.data, t.ctypes.data, f.shape[0], int(chunk_rows),
+                                       out.ctypes.data, nn.value, rows.ctypes.data, C.byref(nn))
+        if rc != 0:
+            raise EngineError(f"mdeggs_host_pack_rows failed: {lib.mdeggs_strerror(rc).decode()}")
+    return out, rows
 
 
 class OmicError(EngineError):
@@ -63,6 +86,8 @@ def load_library() -> C.CDLL:
                                    C.POINTER(C.c_int)]
     L.mdeggs_pair_features.argtypes = [vp, vp, i64, C.c_int32, vp, vp, C.c_int32, C.c_int32, C.c_int32, vp]
     L.mdeggs_pair_moments.argtypes = [vp, vp, vp, C.c_int32, vp]
+    L.mdeggs_host_pack_rows.argtypes = [vp, C.c_int64, C.c_int32, C.c_int32, vp, vp, C.c_int64, C.c_int32, vp, C.c_int64,
+                                        vp, vp]
     L.mdeggs_last_stats.argtypes = [vp, C.POINTER(_abi.CStats)]
     L.mdeggs_set_option.argtypes = [vp, C.c_char_p, i64]
     L.mdeggs_measure_fp64_peak.argtypes = [vp, C.POINTER(C.c_double)]

@@ -32,6 +32,42 @@ def test_library_exports_every_header_symbol():
         assert f" T {nm}" in out
 
 
+@pytest.mark.parametrize("G,n,E,chunk_rows,contiguous", [
+    (500, 37, 300, 0, False),       # scattered node rows, one chunk, a last column block of 5
+    (3000, 64, 2500, 160, False),   # several row chunks (the unit order the streamed copy uses)
+    (400, 20, 4000, 48, True),      # every row is a node: contiguous runs are copied with memcpy
+    (64, 3, 1, 0, False),           # a single edge
+])
+def test_host_packing_of_node_rows(G, n, E, chunk_rows, contiguous):
+    """The host-side packing step of option "host_pack" (worker pool, no GPU): node rows of the edge list, ascending,
+    every value in place - against numpy (core_functions.R:333-336: assayData[rownames %in% nodes, ])."""
+    rng = np.random.default_rng(G + n)
+    a = np.asfortranarray(rng.normal(size=(G, n)))
+    a[rng.integers(0, G, 5), rng.integers(0, n, 5)] = np.nan
+    if contiguous:
+        f = np.arange(1, G + 1, dtype=np.int32).repeat(E // G + 1)[:E]
+        t = np.roll(f, 1)
+    else:
+        f = rng.integers(1, G + 1, E).astype(np.int32)
+        t = rng.integers(1, G + 1, E).astype(np.int32)
+    for rep in range(3):                                    # the pool is reused from job to job
+        packed, rows = eng_mod.host_pack_rows(a, f, t, chunk_rows)
+        want_rows = np.unique(np.concatenate([f, t])) - 1
+        assert np.array_equal(rows, want_rows)
+        assert packed.shape == (want_rows.size, n)
+        assert np.array_equal(packed, a[want_rows, :], equal_nan=True)
+    # indices outside 1..G are no nodes (the device check reports them)
+    f2 = f.copy()
+    f2[0] = G + 7
+    t2 = t.copy()
+    t2[-1] = 0
+    packed, rows = eng_mod.host_pack_rows(a, f2, t2, chunk_rows)
+    want_rows = np.unique(np.concatenate([f2[1:], t2[:-1], t2[:1] if E > 1 else t2[:0], f2[-1:] if E > 1 else f2[:0]])) - 1
+    want_rows = want_rows[(want_rows >= 0) & (want_rows < G)]
+    assert np.array_equal(rows, want_rows)
+    assert np.array_equal(packed, a[want_rows, :], equal_nan=True)
+
+
 def test_struct_layout_matches_header():
     """sizeof/offsetof cross-check of the ctypes mirrors against the C compiler."""
     src = r'''

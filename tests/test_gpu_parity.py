@@ -1161,7 +1161,7 @@ def test_onepass_adjustment_equals_three_pass(padj, K, E, seed):
     eng.close()
 
 
-@pytest.mark.parametrize("chunk_mb", [1, 2])
+@pytest.mark.parametrize("chunk_mb", [2, 5])        # 7 and 2 chunks of rows
 def test_streamed_input_copy_equals_plain_copy(oracle, chunk_mb):
     """Host matrices cross PCIe in row chunks while the compute phase already runs (option h2d_pipeline; the front
     kernel's TMA loader waits for the chunk of its tile, the quantile sample only draws from the first chunk): every
@@ -1182,4 +1182,63 @@ def test_streamed_input_copy_equals_plain_copy(oracle, chunk_mb):
             assert bits & 0x100, hex(bits)
         for k in ALL_FIELDS:
             assert np.array_equal(got[k], plain[k], equal_nan=True), (k, rep)
+    eng.close()
+
+
+@pytest.mark.parametrize("G,n,E,K,method,chunk_mb", [
+    (6000, 500, 5000, 3, _abi.METHOD_LM, 0),     # 24 MB, node rows scattered: packed + streamed in 4 MB chunks (auto)
+    (6000, 500, 5000, 2, _abi.METHOD_LM, 1),     # ... 1 MB chunks
+    (900, 60, 700, 2, _abi.METHOD_RLM, 0),       # small: packed, sent with one plain copy
+    (2500, 301, 40000, 3, _abi.METHOD_LM, 0),    # every row a node: contiguous runs, odd sample count
+])
+def test_host_packed_rows_equal_plain_copy(oracle, G, n, E, K, method, chunk_mb):
+    """Option host_pack: the host gathers the network-node rows into pinned staging with its worker threads and the call
+    runs on the packed problem (node-rank edge list), chunks streamed to the device behind the already enqueued compute
+    phase: every output equals the run on the caller's matrix bit for bit - eager, captured, replayed - and the oracle;
+    mdeggs_pair_moments keeps taking rows of the caller's matrix; an edge index outside 1..G is still reported."""
+    prob = synth.random_problem(G, n, E, K, 9100 + G + n, method)
+    ref = oracle.run_omic(prob, ALL_FIELDS)
+    eng = md.Engine([0])
+    eng.set_option("host_pack", 0)
+    plain = eng.run_omic(prob, ALL_FIELDS)
+    assert not int(eng.stats()["fit_path"]) & 0x2000
+    assert_parity(plain, ref, prob, what="plain copy: ")
+    a_rows = np.array([prob.from_idx[0], prob.to_idx[1], 1, G], dtype=np.int32)
+    b_rows = np.array([prob.to_idx[0], prob.from_idx[1], 2, G - 1], dtype=np.int32)
+    mom_plain = eng.pair_moments(a_rows, b_rows, K)
+    eng.set_option("host_pack", 2)
+    if chunk_mb:
+        eng.set_option("h2d_pipeline", chunk_mb)
+    for rep in range(4):
+        got = eng.run_omic(prob, ALL_FIELDS)
+        bits = int(eng.stats()["fit_path"])
+        assert bits & 0x2000, hex(bits)
+        if G * n * 8 > (16 << 20):
+            assert bits & 0x1000, hex(bits)              # streamed behind the compute phase
+        for k in ALL_FIELDS:
+            assert np.array_equal(got[k], plain[k], equal_nan=True), (k, rep)
+    assert np.array_equal(eng.pair_moments(a_rows, b_rows, K), mom_plain, equal_nan=True)
+    bad = synth.random_problem(G, n, E, K, 9100 + G + n, method)
+    bad.from_idx = bad.from_idx.copy()
+    bad.from_idx[3] = G + 1
+    with pytest.raises(md.EngineError, match="outside 1..G"):
+        eng.run_omic(bad, ALL_FIELDS)
+    got = eng.run_omic(prob, ALL_FIELDS)                    # the context is usable afterwards
+    for k in ALL_FIELDS:
+        assert np.array_equal(got[k], plain[k], equal_nan=True), k
+    eng.close()
+
+
+def test_pageable_matrices_are_packed_by_default(oracle):
+    """A pageable host matrix (numpy here, an R matrix in the drop-in) above 2 MB goes through the packing path without
+    any option; a small one keeps the plain copy."""
+    eng = md.Engine([0])
+    big = synth.random_problem(4000, 200, 3000, 2, 5150)
+    got = eng.run_omic(big, ALL_FIELDS)
+    assert int(eng.stats()["fit_path"]) & 0x2000
+    assert_parity(got, oracle.run_omic(big, ALL_FIELDS), big, what="packed by default: ")
+    small = synth.random_problem(300, 40, 200, 2, 5151)
+    got = eng.run_omic(small, ALL_FIELDS)
+    assert not int(eng.stats()["fit_path"]) & 0x2000
+    assert_parity(got, oracle.run_omic(small, ALL_FIELDS), small, what="small: ")
     eng.close()
