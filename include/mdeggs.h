@@ -229,6 +229,9 @@ int mdeggs_trace_get(const mdeggs_ctx* ctx, int i, char* name, int name_cap, int
  * "h2d_pipeline" (1 = the band of a column-major HOST matrix crosses PCIe in row chunks of 12 MB on two copy streams while
  * the compute phase already runs: the TMA loader of the front kernel waits for the chunk that holds its tile [default];
  * 0 = the whole band is copied before the compute phase starts; n > 1 = chunks of n MB);
+ * "tail_spline" (1 = two-category lm on edge lists of 16,384 edges or more per rank reads its t tails from ONE per-run
+ * interpolation table, built on the side stream from the same series / continued fractions [default]; 0 = every edge
+ * runs its own series / fraction; 2 = the table on every two-category lm call);
  * "host_pack" (1 = a column-major host matrix that is PAGEABLE, or whose network-node rows cover less than 3/4 of the
  * band they span, is not copied as it is: worker threads gather exactly the node rows into pinned staging, row chunk by
  * row chunk, and every finished chunk is sent while the next one is packed and while the front kernel already works
@@ -252,6 +255,9 @@ int mdeggs_abi_version(void);
 int mdeggs_dev_pt(mdeggs_ctx* ctx, const double* x, const double* df, int64_t n, double* out);
 int mdeggs_dev_pf_upper(mdeggs_ctx* ctx, const double* f, const double* df1, const double* df2, int64_t n, double* out);
 int mdeggs_dev_p_two_sided_ref(mdeggs_ctx* ctx, const double* t, const double* df, int64_t n, double* out);
+/* ... and the form the pipeline uses for a whole run (ONE df): the per-run series / continued-fraction tables and,
+ * with use_spline, the interpolation table of log P(|T| > t) in s = sqrt(log1p(t^2 / df)) (option "tail_spline"). */
+int mdeggs_dev_p_two_sided_tab(mdeggs_ctx* ctx, const double* t, double df, int32_t use_spline, int64_t n, double* out);
 
 #ifdef __cplusplus
 }

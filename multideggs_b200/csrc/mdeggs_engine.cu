@@ -37,6 +37,8 @@
 
 using namespace mdeggs;
 
+constexpr int64_t TAIL_SPLINE_MIN_EDGES = 16384;  // below, building the table costs more than it saves
+
 namespace {
 
 struct DevBuf {
@@ -77,6 +79,7 @@ struct Shard {
   cudaEvent_t ev_copy_go = nullptr, ev_copy_done = nullptr, ev_copy2_done = nullptr;
   // streamed input copy (stage_inputs): the band of a host matrix crosses PCIe in row chunks on s_copy while the
   // compute phase already runs; chunk c is complete once gate[c] != 0 (a stream-ordered 32-bit write behind its copy)
+  bool tail_sp_on = false;  // this call's t tails come from the interpolation table (k_tail_spline)
   bool gated = false;
   int gate_chunks = 0;
   int64_t gate_rows = 0;  // rows per chunk (a multiple of 16)
@@ -118,11 +121,11 @@ struct Shard {
     if (e == cudaSuccess) h_stage_cap = bytes + 256;
     return e;
   }
-  DevBuf gate, st8, act_t, Dc, tile_need, na_q, bh1_state, assay, from, to, ea, eb, stage_dev, bs_count, bs_slot, seg_done, seg_rank, fin_q, hm_p, hm_q1, hm_c, hm_sc, hm_idx, hm_off, seg_pi0, B16, stamps, excl, node_of_row, rowlist, scal, src_of_pos, pct, cutoff, D, cub_tmp, mean, sxx, med, bad, stat, status, p_edge, coef, iters, act, counters, sortk, sortk2, idx,
+  DevBuf tail_sp, gate, st8, act_t, Dc, tile_need, na_q, bh1_state, assay, from, to, ea, eb, stage_dev, bs_count, bs_slot, seg_done, seg_rank, fin_q, hm_p, hm_q1, hm_c, hm_sc, hm_idx, hm_off, seg_pi0, B16, stamps, excl, node_of_row, rowlist, scal, src_of_pos, pct, cutoff, D, cub_tmp, mean, sxx, med, bad, stat, status, p_edge, coef, iters, act, counters, sortk, sortk2, idx,
       idx2, ps, sa, sb, tile_cnt, tile_base, seg_n, tile_min, tile_carry, padj_best, cat_best, cat, padj, med_out,
       small_out, rsel_hist, rsel_state, rsel_cand, dense_S, cf_tab, sxy;
   void release_all() {
-    DevBuf* all[] = {&gate, &st8, &act_t, &Dc, &tile_need, &na_q, &bh1_state, &assay, &from, &to, &ea, &eb, &stage_dev, &bs_count, &bs_slot, &seg_done, &seg_rank, &fin_q, &hm_p, &hm_q1, &hm_c, &hm_sc, &hm_idx, &hm_off, &seg_pi0, &B16, &stamps, &excl, &node_of_row, &rowlist, &scal, &src_of_pos, &pct, &cutoff,
+    DevBuf* all[] = {&tail_sp, &gate, &st8, &act_t, &Dc, &tile_need, &na_q, &bh1_state, &assay, &from, &to, &ea, &eb, &stage_dev, &bs_count, &bs_slot, &seg_done, &seg_rank, &fin_q, &hm_p, &hm_q1, &hm_c, &hm_sc, &hm_idx, &hm_off, &seg_pi0, &B16, &stamps, &excl, &node_of_row, &rowlist, &scal, &src_of_pos, &pct, &cutoff,
                      &D, &cub_tmp, &mean, &sxx, &med, &bad, &stat, &status, &p_edge,
                      &coef, &iters, &act, &counters, &sortk, &sortk2, &idx, &idx2, &ps, &sa, &sb, &tile_cnt,
                      &tile_base, &seg_n, &tile_min, &tile_carry, &padj_best, &cat_best, &cat, &padj, &med_out,
@@ -170,6 +173,7 @@ struct mdeggs_ctx {
   int front_path = -1;         // -1 auto, 0 separate K1 + K2 kernels, 1 fused (TMA when possible), 2 fused with the plain loader
   bool last_zc = false;        // the last call read its assay through zero copy
   // host-side packing of the node rows into pinned staging (mdeggs_hostpack.h)
+  int tail_spline = 1;         // option "tail_spline": 0 off, 1 = table of the t tail on edge lists >= 16,384 per rank, 2 always
   int host_pack = 1;           // option "host_pack": 0 off, 1 auto (pageable or scattered node rows), 2 whenever possible
   struct HostPack {
     bool active = false;       // this call runs on the packed problem `in2`
@@ -1221,6 +1225,23 @@ int run_shard_main(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
     LAUNCH(k_cf_tables, 1, 256, 0, s.s_sort, ta, tdf2 / 2.0, s.cf_tab.as<double>(), s.cf_tab.as<double>() + CF_TABLE_LEN,
            s.cf_tab.as<double>() + 2 * CF_TABLE_LEN, s.cf_tab.as<double>() + 2 * CF_TABLE_LEN + 2,
            s.cf_tab.as<double>() + 3 * CF_TABLE_LEN + 2);
+    // two-category lm on a long edge list: the t tail of the run as one interpolation table (mdeggs_math.cuh)
+    const int64_t e_rank = (E + s.world - 1) / s.world;
+    s.tail_sp_on = K == 2 && !rlm2 && tdf2 >= 1.0 && ctx->tail_spline &&
+                   (ctx->tail_spline >= 2 || e_rank >= TAIL_SPLINE_MIN_EDGES);
+    if (s.tail_sp_on) {
+      CU(s.tail_sp.ensure((size_t)TS_M * TS_C * 8));
+      TailConsts tc;
+      memset(&tc, 0, sizeof tc);
+      tc.a = 0.5;
+      tc.b = tdf2 / 2.0;
+      tc.e_ab = s.cf_tab.as<double>();
+      tc.e_ba = s.cf_tab.as<double>() + CF_TABLE_LEN;
+      tc.c_ab = s.cf_tab.as<double>() + 2 * CF_TABLE_LEN + 2;
+      tc.c_ba = s.cf_tab.as<double>() + 3 * CF_TABLE_LEN + 2;
+      LAUNCH(k_tail_spline, TS_M * TS_C / 256, 256, 0, s.s_sort, tc, s.cf_tab.as<double>() + 2 * CF_TABLE_LEN, tdf2,
+             tail_spline_smax(tdf2) / (double)TS_M, s.tail_sp.as<double>());
+    }
     CU(cudaEventRecord(s.ev_cf, s.s_sort));
   }
   // ---- K2 gene stats (+ K3 S3: the values of the quantile slots are appended to their lists here) ----
@@ -1454,6 +1475,9 @@ int run_shard_main(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
     tc.e_ba = s.cf_tab.as<double>() + CF_TABLE_LEN;
     tc.c_ab = s.cf_tab.as<double>() + 2 * CF_TABLE_LEN + 2;
     tc.c_ba = s.cf_tab.as<double>() + 3 * CF_TABLE_LEN + 2;
+    tc.sp = (s.tail_sp_on && tail_mode == 0) ? s.tail_sp.as<double>() : nullptr;
+    tc.sp_inv_h = (double)TS_M / tail_spline_smax(df2);
+    tc.sp_inv_n = 1.0 / df2;
     const double* d_lbeta = s.cf_tab.as<double>() + 2 * CF_TABLE_LEN;
     const int src = is_rlm ? 2 : (use_dense ? 1 : 0);
     CU(cudaStreamWaitEvent(s.s_main, s.ev_cf, 0));  // continued-fraction tables (side stream)
@@ -2442,6 +2466,10 @@ int mdeggs_set_option(mdeggs_ctx* ctx, const char* name, int64_t value) {
     ctx->h2d_pipeline = (int)value;
     return MDEGGS_OK;
   }
+  if (!strcmp(name, "tail_spline")) {
+    ctx->tail_spline = (int)value;
+    return MDEGGS_OK;
+  }
   if (!strcmp(name, "host_pack")) {
     ctx->host_pack = (int)value;
     return MDEGGS_OK;
@@ -2742,6 +2770,47 @@ int mdeggs_dev_pf_upper(mdeggs_ctx* ctx, const double* f, const double* df1, con
 }
 int mdeggs_dev_p_two_sided_ref(mdeggs_ctx* ctx, const double* t, const double* df, int64_t n, double* out) {
   return dev_math(ctx, 2, t, df, nullptr, n, out);
+}
+
+int mdeggs_dev_p_two_sided_tab(mdeggs_ctx* ctx, const double* t, double df, int32_t use_spline, int64_t n, double* out) {
+  if (!ctx || !t || !out || n < 0 || !(df >= 1.0)) return MDEGGS_EINVAL;
+  if (n == 0) return MDEGGS_OK;
+  Shard& s = ctx->shards[0];
+  CU(cudaSetDevice(s.device));
+  CU(s.cf_tab.ensure((size_t)CF_TABLE_DOUBLES * 8));
+  CU(s.tail_sp.ensure((size_t)TS_M * TS_C * 8));
+  DevBuf dx, dout;
+  int rc = MDEGGS_OK;
+  if (dx.ensure((size_t)n * 8) != cudaSuccess || dout.ensure((size_t)n * 8) != cudaSuccess) {
+    rc = MDEGGS_ENOMEM;
+  } else {
+    double* cf = s.cf_tab.as<double>();
+    TailConsts tc;
+    memset(&tc, 0, sizeof tc);
+    tc.a = 0.5;
+    tc.b = df / 2.0;
+    tc.e_ab = cf;
+    tc.e_ba = cf + CF_TABLE_LEN;
+    tc.c_ab = cf + 2 * CF_TABLE_LEN + 2;
+    tc.c_ba = cf + 3 * CF_TABLE_LEN + 2;
+    LAUNCH(k_cf_tables, 1, 256, 0, s.s_main, 0.5, df / 2.0, cf, cf + CF_TABLE_LEN, cf + 2 * CF_TABLE_LEN,
+           cf + 2 * CF_TABLE_LEN + 2, cf + 3 * CF_TABLE_LEN + 2);
+    if (use_spline) {
+      LAUNCH(k_tail_spline, TS_M * TS_C / 256, 256, 0, s.s_main, tc, cf + 2 * CF_TABLE_LEN, df,
+             tail_spline_smax(df) / (double)TS_M, s.tail_sp.as<double>());
+      tc.sp = s.tail_sp.as<double>();
+      tc.sp_inv_h = (double)TS_M / tail_spline_smax(df);
+      tc.sp_inv_n = 1.0 / df;
+    }
+    cudaMemcpyAsync(dx.p, t, (size_t)n * 8, cudaMemcpyHostToDevice, s.s_main);
+    LAUNCH(k_dev_tail_tab, blocks_for(n, 128), 128, 0, s.s_main, tc, cf + 2 * CF_TABLE_LEN, df, dx.as<double>(), n,
+           dout.as<double>());
+    cudaMemcpyAsync(out, dout.p, (size_t)n * 8, cudaMemcpyDeviceToHost, s.s_main);
+    if (cudaStreamSynchronize(s.s_main) != cudaSuccess) rc = MDEGGS_ECUDA;
+  }
+  dx.release();
+  dout.release();
+  return rc;
 }
 
 }  // extern "C"

@@ -1971,4 +1971,14 @@ __global__ void k_dev_math(int which, const double* __restrict__ x, const double
   else out[i] = p_two_sided_ref_dev(x[i], a[i]);
 }
 
+// the run-table form of the two-sided t tail (series / continued fractions from k_cf_tables, and - tc.sp set - the
+// interpolation table of k_tail_spline), for tests
+__global__ void k_dev_tail_tab(TailConsts tc, const double* __restrict__ lbeta_p, double df, const double* __restrict__ x,
+                               int64_t n, double* __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  tc.lbeta_ab = *lbeta_p;
+  out[i] = p_two_sided_ref_tab(tc, x[i], df);
+}
+
 }  // namespace mdeggs

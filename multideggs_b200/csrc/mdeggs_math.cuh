@@ -141,6 +141,10 @@ struct TailConsts {
   const double* e_ba;  // e_j for I_x(b, a)
   const double* c_ab;  // c_k = (a + b + k - 1) / (a + k), k = 1..CF_TABLE_LEN: term ratios of the power series of I_x(a, b)
   const double* c_ba;  // ... of I_x(b, a)
+  // piecewise Chebyshev table of the log of the two-sided t tail for the run's degrees of freedom (k_tail_spline);
+  // null: not built for this run
+  const double* sp;
+  double sp_inv_h, sp_inv_n;
 };
 constexpr int CF_TABLE_DOUBLES = 4 * CF_TABLE_LEN + 2;  // e_ab, e_ba, lbeta (+ pad), c_ab, c_ba
 
@@ -221,8 +225,10 @@ __device__ inline double beta_cf_tab(const double* __restrict__ e, double a, dou
 // Where x (a + b) <= 14 the power series replaces the continued fractions: below the mode switch of pbeta
 // (x < (a + 1) / (a + b + 2)) and on the stretch beyond it where the complementary fraction needs O(sqrt(max(a, b)))
 // terms (|t| up to ~5 at 2,000 degrees of freedom), as long as the wanted tail 1 - w keeps its relative accuracy.
+// `strict`: the series is only taken where it yields the wanted tail directly (k_tail_spline: the nodes of the table
+// are worth the long fraction; 1 - w from the series carries ~1e-16 / (1 - w) of relative noise).
 __device__ inline double pbeta_xy_tab(const TailConsts& tc, bool swapped, double x, double y, bool lower,
-                                      int budget = CF_TABLE_LEN, bool* ok = nullptr) {
+                                      int budget = CF_TABLE_LEN, bool* ok = nullptr, bool strict = false) {
   const double a = swapped ? tc.b : tc.a, b = swapped ? tc.a : tc.b;
   if (isnan(x) || isnan(y)) return nan("");
   if (x <= 0.0) return lower ? 0.0 : 1.0;
@@ -231,7 +237,7 @@ __device__ inline double pbeta_xy_tab(const TailConsts& tc, bool swapped, double
   double ly = (y < 0.5) ? log(y) : log1p(-x);
   double front = exp(a * lx + b * ly - tc.lbeta_ab);
   const bool below = x < (a + 1.0) / (a + b + 2.0);
-  if (x * (a + b) <= BETA_SERIES_MAX_XAB) {  // (beyond that the series needs more terms than the fractions)
+  if (x * (a + b) <= BETA_SERIES_MAX_XAB && (!strict || below || lower)) {  // (beyond: more terms than the fractions)
     bool conv = true;
     const double sum = beta_series_tab(swapped ? tc.c_ba : tc.c_ab, x, budget, &conv);
     if (conv) {
@@ -250,22 +256,92 @@ __device__ inline double pbeta_xy_tab(const TailConsts& tc, bool swapped, double
   return lower ? 1.0 - w1 : w1;
 }
 
+// `val` of nmath/pt.c for the run's degrees of freedom (tc = {0.5, n/2}): P(|T| > x), x >= 0 finite
+__device__ inline double pt_val_tab(const TailConsts& tc, double x, double n, int budget = CF_TABLE_LEN,
+                                    bool* ok = nullptr, bool strict = false) {
+  if (n > x * x) {
+    double den = n + x * x;
+    return pbeta_xy_tab(tc, false, x * x / den, n / den, false, budget, ok, strict);
+  }
+  double nx = 1.0 + (x / n) * x;
+  return pbeta_xy_tab(tc, true, 1.0 / nx, (x / n) * x / nx, true, budget, ok, strict);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// One table per run instead of one series / continued fraction per edge.  Every edge of a run has the same degrees of
+// freedom n, so the two-sided tail val(t) = P(|T| > t) = I_x(n/2, 1/2), x = n / (n + t^2), is ONE smooth function of t.
+// In the variable s = sqrt(log1p(t^2 / n)) (x = exp(-s^2)) its logarithm g(s) = log val is analytic at s = 0
+// (val = 1 - c t + ..., t = sqrt(n expm1(s^2))) and close to the parabola -(n/2) s^2 in the far tail, so a piecewise
+// Chebyshev interpolant of degree 7 on TS_M uniform intervals of [0, s_max], (n/2) s_max^2 = 680 (val ~ 1e-295),
+// reproduces g to ~1e-13 for every n (the interval is ~1/50 of the scale 1/sqrt(n) on which g bends).  k_tail_spline
+// evaluates the 8 Chebyshev nodes of every interval with the run's series / continued fractions (16,384 evaluations,
+// once per run, on the side stream) and stores the Chebyshev coefficients; per edge the tail is then log1p, sqrt, a
+// Clenshaw recurrence of 8 terms and exp - no loop, no division, no divergent lanes.  Arguments beyond s_max (val
+// below ~1e-295) keep the fraction.  The result feeds the same  2 * (1 - (0.5 - val / 2 + 0.5))  composition.
+// ---------------------------------------------------------------------------------------------------
+constexpr int TS_M = 2048;
+constexpr int TS_C = 8;  // coefficients per interval
+inline double tail_spline_smax(double n) {
+  const double s2 = 1360.0 / n;
+  return sqrt(s2 < 680.0 ? s2 : 680.0);  // (t^2 = n expm1(s^2) stays finite)
+}
+__global__ void __launch_bounds__(256) k_tail_spline(TailConsts tc, const double* __restrict__ lbeta_p, double n,
+                                                     double h, double* __restrict__ sp) {
+  tc.lbeta_ab = *lbeta_p;
+  tc.sp = nullptr;
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;  // (TS_M * TS_C threads: whole groups of 8 lanes)
+  const int i = gid / TS_C, k = gid % TS_C;
+  const double theta = cospi(((double)k + 0.5) / (double)TS_C);
+  const double sv = ((double)i + 0.5 * (theta + 1.0)) * h;
+  const double t = sqrt(n * expm1(sv * sv));
+  const double f = log(pt_val_tab(tc, t, n, CF_TABLE_LEN, nullptr, true));
+  // c_j = (2 / 8) sum_k f_k cos(j pi (k + 1/2) / 8), c_0 halved: lane j of the group gathers the 8 node values
+  double c = 0.0;
+  const int lane = threadIdx.x & 31, base = lane & ~(TS_C - 1);
+#pragma unroll
+  for (int kk = 0; kk < TS_C; ++kk) {
+    const double fk = __shfl_sync(0xffffffffu, f, base + kk);
+    c += fk * cospi((double)k * ((double)kk + 0.5) / (double)TS_C);
+  }
+  c *= (k == 0 ? 1.0 : 2.0) / (double)TS_C;
+  if (i < TS_M) sp[(size_t)i * TS_C + k] = c;
+}
+// val from the table; *in_range = false (and nothing else) when |t| lies beyond it
+__device__ __forceinline__ double pt_val_spline(const TailConsts& tc, double x, bool* in_range) {
+  const double s = sqrt(log1p(x * x * tc.sp_inv_n));
+  const double u = s * tc.sp_inv_h;
+  if (!(u < (double)TS_M)) {  // (also inf / NaN)
+    *in_range = false;
+    return 0.0;
+  }
+  const int i = (int)u;
+  const double th = 2.0 * (u - (double)i) - 1.0, th2 = th + th;
+  const double2* __restrict__ c2 = reinterpret_cast<const double2*>(tc.sp + (size_t)i * TS_C);
+  const double2 c01 = __ldg(c2), c23 = __ldg(c2 + 1), c45 = __ldg(c2 + 2), c67 = __ldg(c2 + 3);
+  double b1 = c67.y, b0 = fma(th2, b1, c67.x), t2;  // Clenshaw: b_k = c_k + 2 th b_{k+1} - b_{k+2}
+  t2 = fma(th2, b0, c45.y - b1); b1 = b0; b0 = t2;
+  t2 = fma(th2, b0, c45.x - b1); b1 = b0; b0 = t2;
+  t2 = fma(th2, b0, c23.y - b1); b1 = b0; b0 = t2;
+  t2 = fma(th2, b0, c23.x - b1); b1 = b0; b0 = t2;
+  t2 = fma(th2, b0, c01.y - b1); b1 = b0; b0 = t2;
+  const double g = fma(th, b0, c01.x - b1);
+  *in_range = true;
+  return exp(g);
+}
+
 // 2 * (1 - pt(|t|, n)) with tc = {0.5, n/2}: same composition as p_two_sided_ref_dev
 __device__ inline double p_two_sided_ref_tab(const TailConsts& tc, double t, double n, int budget = CF_TABLE_LEN,
                                              bool* ok = nullptr) {
   if (isnan(t)) return nan("");
   double x = fabs(t), u;
-  if (isinf(x)) {
+  if (isinf(x) || x > 1e150) {  // (t^2 overflows; the tail is far below the 1.1e-16 grid of u for every n >= 1)
     u = 1.0;
   } else {
-    double val;
-    if (n > x * x) {
-      double den = n + x * x;
-      val = pbeta_xy_tab(tc, false, x * x / den, n / den, false, budget, ok);
-    } else {
-      double nx = 1.0 + (x / n) * x;
-      val = pbeta_xy_tab(tc, true, 1.0 / nx, (x / n) * x / nx, true, budget, ok);
-    }
+    double val = 0.0;
+    bool tabled = false;
+    if (tc.sp) val = pt_val_spline(tc, x, &tabled);
+    if (!tabled) val = pt_val_tab(tc, x, n, budget, ok);
+    if (tabled && val > 1.0) val = 1.0;  // (the interpolant may exceed 1 by an ulp at t -> 0)
     val *= 0.5;
     u = (x <= 0.0) ? val : __dadd_rn(__dsub_rn(0.5, val), 0.5);
   }

@@ -23,7 +23,7 @@ ABI_SYMBOLS = (
     "mdeggs_create", "mdeggs_create_rank", "mdeggs_nccl_unique_id", "mdeggs_destroy", "mdeggs_run_omic",
     "mdeggs_pair_features", "mdeggs_pair_moments", "mdeggs_host_pack_rows", "mdeggs_measure_fp64_peak", "mdeggs_measure_l2_peak", "mdeggs_last_stats",
     "mdeggs_trace_count", "mdeggs_trace_get", "mdeggs_set_option", "mdeggs_last_error", "mdeggs_strerror", "mdeggs_abi_version",
-    "mdeggs_dev_pt", "mdeggs_dev_pf_upper", "mdeggs_dev_p_two_sided_ref",
+    "mdeggs_dev_pt", "mdeggs_dev_pf_upper", "mdeggs_dev_p_two_sided_ref", "mdeggs_dev_p_two_sided_tab",
     "mdeggs_submit_omic", "mdeggs_wait", "mdeggs_run_omics",
 )
 
@@ -102,6 +102,7 @@ def load_library() -> C.CDLL:
     L.mdeggs_dev_pt.argtypes = [vp, vp, vp, i64, vp]
     L.mdeggs_dev_pf_upper.argtypes = [vp, vp, vp, vp, i64, vp]
     L.mdeggs_dev_p_two_sided_ref.argtypes = [vp, vp, vp, i64, vp]
+    L.mdeggs_dev_p_two_sided_tab.argtypes = [vp, vp, C.c_double, C.c_int32, i64, vp]
     for nm in ABI_SYMBOLS:
         if getattr(L, nm).restype is C.c_int or getattr(L, nm).restype is None:
             getattr(L, nm).restype = i
@@ -254,6 +255,14 @@ class Engine:
 
     def dev_p_two_sided_ref(self, t, df) -> np.ndarray:
         return self._vec(self._lib.mdeggs_dev_p_two_sided_ref, t, df)
+
+    def dev_p_two_sided_tab(self, t, df: float, use_spline: bool = True) -> np.ndarray:
+        """2 * (1 - pt(|t|, df)) the way a whole run evaluates it (one df): per-run tables, optionally the spline."""
+        x = np.ascontiguousarray(t, dtype=np.float64)
+        out = np.empty_like(x)
+        self._check(self._lib.mdeggs_dev_p_two_sided_tab(self._ctx, x.ctypes.data, float(df), int(bool(use_spline)),
+                                                         x.size, out.ctypes.data), "mdeggs_dev_p_two_sided_tab")
+        return out
 
 
 class EnginePool:

@@ -1242,3 +1242,47 @@ def test_pageable_matrices_are_packed_by_default(oracle):
     assert not int(eng.stats()["fit_path"]) & 0x2000
     assert_parity(got, oracle.run_omic(small, ALL_FIELDS), small, what="small: ")
     eng.close()
+
+
+@pytest.mark.parametrize("df", [1.0, 2.0, 6.0, 20.0, 96.0, 996.0, 1996.0, 19996.0, 4e5])
+def test_tail_table_against_series_and_mpmath(engine, df):
+    """Option tail_spline: the per-run interpolation table of log P(|T| > t) in s = sqrt(log1p(t^2 / df)) against the
+    per-edge series / continued fractions it is built from (dense grid of t, incl. interval boundaries and the far tail,
+    where the table ends and the fraction takes over) and against 50-digit mpmath (core_functions.R:1072)."""
+    import oracle_np
+    rng = np.random.default_rng(int(df))
+    t = np.concatenate([np.linspace(0.0, 6.0, 6001), np.geomspace(1e-9, 1e3, 4000), rng.uniform(0, 60, 4000),
+                        np.sqrt(df) * np.sqrt(np.expm1((np.arange(1, 2049) * (np.sqrt(min(1360.0 / df, 680.0)) / 2048)) ** 2)),
+                        [0.0, 1e-300, 1e140, 1e160, np.inf, -3.3]])
+    t = t[np.isfinite(t) | np.isinf(t)]
+    tab = engine.dev_p_two_sided_tab(t, df, True)
+    ser = engine.dev_p_two_sided_tab(t, df, False)
+    # (the per-edge series gives 1 - w for |t| ~ 3.5-4.5 with up to ~1e-10 relative noise from the cancellation; the
+    # nodes of the table take the fraction there; both are inside the 1e-9 parity bar) + one step of the 2.2e-16 grid
+    ok = np.abs(tab - ser) <= 5e-10 * ser + 2.3e-16
+    assert ok.all(), (df, t[~ok][:5], tab[~ok][:5], ser[~ok][:5])
+    assert np.all((tab / 2.220446049250313e-16) == np.round(tab / 2.220446049250313e-16)), "2.2e-16 grid"
+    ts = np.concatenate([[1e-6, 0.3, 1.0, 1.8, 2.5, 5.5, 9.9, 12.2, 28.8, 40.0], np.linspace(3.3, 4.7, 29)])
+    true2 = np.array([oracle_np.t_two_sided_mp(float(x), df) for x in ts])
+    got = engine.dev_p_two_sided_tab(ts, df, True)
+    rtol = 5e-12 if df <= 2000 else 2e-10     # (long fractions at df ~ 1e5 accumulate ~1e-11)
+    assert np.all(np.abs(got - true2) <= rtol * true2 + 2.3e-16), (df, np.max(np.abs(got - true2) / true2))
+
+
+@pytest.mark.parametrize("E", [40_000, 300])
+def test_tail_table_inside_the_pipeline(oracle, E):
+    """Two-category lm with the tail table on (forced for the small job) and off: p-values within one grid step of each
+    other, statuses / selections identical, both within the parity bar of the oracle."""
+    prob = synth.random_problem(500, 64, E, 2, 6060 + E, _abi.METHOD_LM, _abi.PADJ_BH)
+    ref = oracle.run_omic(prob, ALL_FIELDS)
+    eng = md.Engine([0])
+    outs = {}
+    for mode in (0, 2):
+        eng.set_option("tail_spline", mode)
+        outs[mode] = eng.run_omic(prob, ALL_FIELDS)
+        assert_parity(outs[mode], ref, prob, what=f"tail_spline {mode}: ")
+    a, b = outs[0]["p_edge"], outs[2]["p_edge"]
+    assert np.all((np.isnan(a) & np.isnan(b)) | (np.abs(a - b) <= 5e-10 * np.abs(a) + 2.3e-16))
+    for k in ("status", "cat", "best", "sig_count", "tot_edges", "cat_best"):
+        assert np.array_equal(outs[0][k], outs[2][k]), k
+    eng.close()
