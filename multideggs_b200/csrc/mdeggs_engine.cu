@@ -189,6 +189,7 @@ struct mdeggs_ctx {
     size_t h_cap = 0;
     PackJob job;
   } pack;
+  int launch_async = -1;       // -1 not probed yet, 1 kernel launches return before the kernel ends, 0 they do not
   int copy_streams = 2;        // option "copy_streams": streams the chunks of a streamed input copy alternate between
   int h2d_pipeline = 1;        // option "h2d_pipeline": 0 = the whole band is copied before the compute phase starts
   int zero_copy = 0;           // option "zero_copy": pinned host assays are read by the gather straight over PCIe
@@ -740,6 +741,30 @@ int plan_host_pack(mdeggs_ctx* ctx, const mdeggs_problem* in) {
   K.job.contiguous = band == nn;
   K.active = true;
   return MDEGGS_OK;
+}
+
+// True when a kernel launch returns to the host before the kernel has run (probed once per context): only then may a
+// launched kernel wait for copies the host enqueues AFTER the launch (streamed host packing under graph replay).
+bool launches_are_async(mdeggs_ctx* ctx, Shard& s) {
+  if (ctx->launch_async >= 0) return ctx->launch_async == 1;
+  ctx->launch_async = 0;
+  unsigned int* h = nullptr;
+  if (cudaHostAlloc(reinterpret_cast<void**>(&h), 64, cudaHostAllocMapped) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  volatile unsigned int* flag = h;
+  flag[0] = 0u;
+  h[8] = 0u;
+  unsigned int *d_flag = nullptr;
+  if (cudaHostGetDevicePointer(reinterpret_cast<void**>(&d_flag), h, 0) == cudaSuccess) {
+    k_async_probe<<<1, 1, 0, s.s_main>>>(d_flag, d_flag + 8);
+    flag[0] = 1u;
+    if (cudaStreamSynchronize(s.s_main) == cudaSuccess) ctx->launch_async = h[8] == 1u ? 1 : 0;
+  }
+  cudaGetLastError();
+  cudaFreeHost(h);
+  return ctx->launch_async == 1;
 }
 
 // Packs the node rows into the pinned staging with the pool.  streamed: chunk by chunk with the shard's gate geometry,
@@ -2282,6 +2307,11 @@ int mdeggs_submit_omic(mdeggs_ctx* ctx, const mdeggs_problem* in, mdeggs_result*
       }
     }
     if (graph_ok && ctx->graph_exec) {
+      if (ctx->pack.deferred && !launches_are_async(ctx, sh0)) {  // (a serialising profiler, CUDA_LAUNCH_BLOCKING)
+        ctx->pack.deferred = false;
+        rc = run_host_pack(ctx, sh0, true);
+        if (rc) return rc;
+      }
       CU(cudaGraphLaunch(ctx->graph_exec, sh0.s_main));
       CU(cudaEventRecord(sh0.ev[EV_ADJ], sh0.s_main));
       ctx->launches = ctx->graph_launches;

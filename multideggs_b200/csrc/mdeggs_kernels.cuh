@@ -69,6 +69,25 @@ __device__ __forceinline__ void gate_wait(const unsigned int* __restrict__ gate,
   }
 }
 
+// Are kernel launches asynchronous in this process?  The host raises `flag` (mapped pinned memory) right after the
+// launch call returns; a kernel that still sees it down after 2 ms was launched synchronously (a profiler that
+// serialises launches, CUDA_LAUNCH_BLOCKING=1): work that a running kernel waits for must then be enqueued BEFORE it.
+__global__ void k_async_probe(const volatile unsigned int* flag, unsigned int* result) {
+  unsigned long long t0, t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (;;) {
+    if (*flag) {
+      *result = 1u;
+      return;
+    }
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    if (t - t0 > 2000000ull) {
+      *result = 0u;
+      return;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // K0: node filter   (core_functions.R:333-336: nodes <- unique(c(from,to)); assayData[rownames %in% nodes,])
 //   k_mark_nodes : every CTA marks the end points of its edges in a shared-memory bitmap of the G rows (G/8 bytes;

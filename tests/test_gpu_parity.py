@@ -1286,3 +1286,32 @@ def test_tail_table_inside_the_pipeline(oracle, E):
     for k in ("status", "cat", "best", "sig_count", "tot_edges", "cat_best"):
         assert np.array_equal(outs[0][k], outs[2][k]), k
     eng.close()
+
+
+def test_streamed_packing_survives_blocking_launches():
+    """With CUDA_LAUNCH_BLOCKING=1 (or under a profiler that serialises launches) a launch only returns when the kernel
+    has run, so the engine must not launch the compute phase before the chunks it waits for are enqueued: it probes the
+    launch behaviour once per context (k_async_probe) and packs first.  Same results, no time-out."""
+    import os, subprocess, sys, textwrap
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = textwrap.dedent("""
+        import sys, numpy as np
+        sys.path.insert(0, %r); sys.path.insert(0, %r)
+        import multideggs_b200 as md
+        from multideggs_b200 import synth
+        prob = synth.random_problem(6000, 500, 5000, 2, 424242)
+        want = ("p_edge", "status", "cutoff", "median", "best", "sig_count", "padj_best")
+        eng = md.Engine([0])
+        eng.set_option("host_pack", 0); eng.set_option("h2d_pipeline", 0)
+        plain = eng.run_omic(prob, want)
+        eng.set_option("host_pack", 2); eng.set_option("h2d_pipeline", 1)
+        for rep in range(4):
+            got = eng.run_omic(prob, want)
+            assert int(eng.stats()["fit_path"]) & 0x3000 == 0x3000
+            for k in want:
+                assert np.array_equal(got[k], plain[k], equal_nan=True), (k, rep)
+        print("ok")
+    """) % (ROOT, os.path.join(ROOT, "tests"))
+    env = dict(os.environ, CUDA_LAUNCH_BLOCKING="1")
+    res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0 and "ok" in res.stdout, res.stdout + res.stderr
