@@ -65,6 +65,9 @@ struct BsArgs {
   const uint4* act_t;
   int nch;
   const int32_t *ea, *eb;
+  // run_first[r] = first bucket whose offset is >= r BS_CAP, for every window start r BS_CAP <= n_order (written by
+  // k_bsort_scatter, read by k_bsort_sort instead of a 19-step binary search over the offsets per CTA)
+  int* run_first;
 };
 
 // One call per thread of a kernel that covers edges; `live` threads contribute p, `tested` = the edge is tested at some
@@ -289,15 +292,15 @@ __global__ void __launch_bounds__(256) k_bsort_scatter(BsArgs B, int scan_in_cta
   __shared__ int s_warp_tot[32];
   if (*err) return;
   const int* base = B.base;
+  const int NB = BS_NLOG + B.nlin + 1;
+  int total = 0;
   if (!scan_in_cta && blockIdx.x == 0 && threadIdx.x == 0) {  // offsets came from a device-wide scan of count[0..NB]
-    const int NB = BS_NLOG + B.nlin + 1;
     *B.n_valid = (unsigned long long)(B.base[NB] - __ldcg(B.count + NB - 1));
     *B.n_order = (unsigned long long)B.base[NB];
     *B.n_low = (unsigned long long)B.base[bs_bucket(0.05, B.nlin, B.scale) + 1];
   }
   if (scan_in_cta) {
-    const int NB = BS_NLOG + B.nlin + 1;
-    const int total = bs_scan_counts(B.count, NB, s_base, s_warp_tot);
+    total = bs_scan_counts(B.count, NB, s_base, s_warp_tot);
     if (blockIdx.x == 0) {
       for (int i = threadIdx.x; i < NB; i += blockDim.x) B.base[i] = s_base[i];
       if (threadIdx.x == 0) {
@@ -310,6 +313,19 @@ __global__ void __launch_bounds__(256) k_bsort_scatter(BsArgs B, int scan_in_cta
     }
     base = s_base;
   }
+  // window starts: bucket b (b == NB: the end of the order) is the first one at or beyond r BS_CAP for every r with
+  // base[b - 1] < r BS_CAP <= base[b]
+  {
+    auto base_at = [&](int b) { return (scan_in_cta && b == NB) ? total : base[b]; };
+    // (every CTA holds the offsets - its own scan in shared memory, or the global array -: the buckets are spread over
+    // all threads of the grid)
+    const long long nthr = (long long)gridDim.x * blockDim.x;
+    for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x; b <= NB; b += nthr) {
+      const int hi = base_at((int)b), lo_excl = b == 0 ? -1 : base_at((int)b - 1);
+      if (hi == lo_excl) continue;
+      for (int r = lo_excl < 0 ? 0 : lo_excl / BS_CAP + 1; r <= hi / BS_CAP; ++r) B.run_first[r] = (int)b;
+    }
+  }
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= B.E) return;
   const int sl = B.slot[e];
@@ -317,7 +333,8 @@ __global__ void __launch_bounds__(256) k_bsort_scatter(BsArgs B, int scan_in_cta
   const double p = p_edge[e];
   const int pos = base[bs_bucket(p, B.nlin, B.scale)] + sl;
   bkey[pos] = dkey(p);
-  bidx[pos] = (int32_t)e;
+  bidx[pos] = (int32_t)e;  // (measured: carrying the end points along as a 16-byte payload costs the scatter 50 us on
+                           // 8 M edges and saves the sort 6)
 }
 
 __device__ __forceinline__ bool bs_less(unsigned long long ka, int ia, unsigned long long kb, int ib) {
@@ -420,29 +437,19 @@ __device__ void bs_sort_global(unsigned long long* __restrict__ bkey, int32_t* _
 // one CTA per run r: the whole buckets whose first element lies in [r BS_CAP, (r+1) BS_CAP)
 __global__ void __launch_bounds__(BS_SORT_THREADS) k_bsort_sort(BsArgs B, unsigned long long* __restrict__ bkey,
                                                                int32_t* __restrict__ bidx,
-                                                               const int32_t* __restrict__ ea,
-                                                               const int32_t* __restrict__ eb,
                                                                double* __restrict__ ps, int32_t* __restrict__ sa,
                                                                int32_t* __restrict__ sb, int32_t* __restrict__ sidx,
                                                                const int32_t* __restrict__ err) {
   __shared__ unsigned long long sk[2 * BS_CAP];
   __shared__ int si[2 * BS_CAP];
-  __shared__ int s_b[2];
   if (*err) return;
   const int NB = BS_NLOG + B.nlin + 1;
   const int r = blockIdx.x;
-  if (threadIdx.x < 2) {  // first bucket whose offset is >= (r + t) * BS_CAP
-    const long long target = (long long)(r + threadIdx.x) * BS_CAP;
-    int lo = 0, hi = NB;
-    while (lo < hi) {
-      const int mid = (lo + hi) >> 1;
-      if ((long long)B.base[mid] >= target) hi = mid;
-      else lo = mid + 1;
-    }
-    s_b[threadIdx.x] = lo;
-  }
-  __syncthreads();
-  const int bf = s_b[0], bl = s_b[1];
+  const int total = B.base[NB];
+  if ((long long)r * BS_CAP > (long long)total) return;  // beyond the order (the grid is sized for E edges)
+  // first bucket whose offset is >= r BS_CAP, and the same for the next window (k_bsort_scatter: run_first)
+  const int bf = B.run_first[r];
+  const int bl = (long long)(r + 1) * BS_CAP > (long long)total ? NB : B.run_first[r + 1];
   if (bf >= bl) return;  // no bucket starts in this window (an oversize bucket of an earlier run covers it)
   const int lo = B.base[bf], hi = B.base[bl];
   const int n = hi - lo;
@@ -452,7 +459,7 @@ __global__ void __launch_bounds__(BS_SORT_THREADS) k_bsort_sort(BsArgs B, unsign
     // p-values), so the work is spread per ELEMENT, not per bucket: a thread per bucket marks its elements with the
     // bucket's range, then a thread per element ranks its (key, edge id) inside that range with a short loop of
     // shared-memory reads.  No barrier-separated sorting network, no serial walk over buckets.  The rare bucket of
-    // more than BS_WARP_MAX elements is sorted in place by one warp (warp-synchronous network).
+    // more than BS_WARP_MAX elements is sorted in place by the CTA (below).
     __shared__ unsigned short s_st[2 * BS_CAP], s_cn[2 * BS_CAP];
     __shared__ int s_big[2 * BS_CAP / BS_WARP_MAX];
     __shared__ int s_nbig;
@@ -479,8 +486,8 @@ __global__ void __launch_bounds__(BS_SORT_THREADS) k_bsort_sort(BsArgs B, unsign
     __syncthreads();
     auto emit = [&](int pos, unsigned long long k, int e) {
       ps[pos] = k != ~0ull ? dkey_inv(k) : nan("");
-      sa[pos] = ea[e];
-      sb[pos] = eb[e];
+      sa[pos] = B.ea[e];
+      sb[pos] = B.eb[e];
       sidx[pos] = e;
     };
     for (int q = threadIdx.x; q < n; q += blockDim.x) {
@@ -493,15 +500,18 @@ __global__ void __launch_bounds__(BS_SORT_THREADS) k_bsort_sort(BsArgs B, unsign
       for (int t = 0; t < bn; ++t) rk += bs_less(sk[blo + t], si[blo + t], mk, me);
       emit(lo + blo + rk, mk, me);
     }
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    // Larger buckets (the binade buckets just below 2^-10 hold hundreds of null p-values on a multi-million edge list):
+    // the whole CTA runs the network on one bucket at a time; a single warp would keep its CTA - and, at the end of
+    // the grid, the whole GPU - waiting for tens of microseconds.
     const int nbig = s_nbig;
-    for (int i = warp; i < nbig; i += nwarp) {
+    __syncthreads();  // (every thread has read its neighbours' keys: the network may now move them)
+    for (int i = 0; i < nbig; ++i) {
       const int b = s_big[i];
       const int blo = B.base[b] - lo, bn = B.base[b + 1] - B.base[b];
       int n2 = 1;
       while (n2 < bn) n2 <<= 1;
-      bs_bitonic(BsSmemWarp{sk + blo, si + blo}, bn, n2, lane, 32);
-      for (int t = lane; t < bn; t += 32) emit(lo + blo + t, sk[blo + t], si[blo + t]);
+      bs_bitonic(BsSmem{sk + blo, si + blo}, bn, n2);  // (ends with a CTA barrier)
+      for (int t = threadIdx.x; t < bn; t += blockDim.x) emit(lo + blo + t, sk[blo + t], si[blo + t]);
     }
     return;
   }
@@ -535,8 +545,8 @@ __global__ void __launch_bounds__(BS_SORT_THREADS) k_bsort_sort(BsArgs B, unsign
     const unsigned long long k = bkey[i];
     const int e = bidx[i];
     ps[i] = k != ~0ull ? dkey_inv(k) : nan("");
-    sa[i] = ea[e];
-    sb[i] = eb[e];
+    sa[i] = B.ea[e];
+    sb[i] = B.eb[e];
     sidx[i] = e;
   }
 }

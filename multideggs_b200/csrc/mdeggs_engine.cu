@@ -121,11 +121,11 @@ struct Shard {
     if (e == cudaSuccess) h_stage_cap = bytes + 256;
     return e;
   }
-  DevBuf tail_sp, gate, st8, act_t, Dc, tile_need, na_q, bh1_state, assay, from, to, ea, eb, stage_dev, bs_count, bs_slot, seg_done, seg_rank, fin_q, hm_p, hm_q1, hm_c, hm_sc, hm_idx, hm_off, seg_pi0, B16, stamps, excl, node_of_row, rowlist, scal, src_of_pos, pct, cutoff, D, cub_tmp, mean, sxx, med, bad, stat, status, p_edge, coef, iters, act, counters, sortk, sortk2, idx,
+  DevBuf run_first, tail_sp, gate, st8, act_t, Dc, tile_need, na_q, bh1_state, assay, from, to, ea, eb, stage_dev, bs_count, bs_slot, seg_done, seg_rank, fin_q, hm_p, hm_q1, hm_c, hm_sc, hm_idx, hm_off, seg_pi0, B16, stamps, excl, node_of_row, rowlist, scal, src_of_pos, pct, cutoff, D, cub_tmp, mean, sxx, med, bad, stat, status, p_edge, coef, iters, act, counters, sortk, sortk2, idx,
       idx2, ps, sa, sb, tile_cnt, tile_base, seg_n, tile_min, tile_carry, padj_best, cat_best, cat, padj, med_out,
       small_out, rsel_hist, rsel_state, rsel_cand, dense_S, cf_tab, sxy;
   void release_all() {
-    DevBuf* all[] = {&tail_sp, &gate, &st8, &act_t, &Dc, &tile_need, &na_q, &bh1_state, &assay, &from, &to, &ea, &eb, &stage_dev, &bs_count, &bs_slot, &seg_done, &seg_rank, &fin_q, &hm_p, &hm_q1, &hm_c, &hm_sc, &hm_idx, &hm_off, &seg_pi0, &B16, &stamps, &excl, &node_of_row, &rowlist, &scal, &src_of_pos, &pct, &cutoff,
+    DevBuf* all[] = {&run_first, &tail_sp, &gate, &st8, &act_t, &Dc, &tile_need, &na_q, &bh1_state, &assay, &from, &to, &ea, &eb, &stage_dev, &bs_count, &bs_slot, &seg_done, &seg_rank, &fin_q, &hm_p, &hm_q1, &hm_c, &hm_sc, &hm_idx, &hm_off, &seg_pi0, &B16, &stamps, &excl, &node_of_row, &rowlist, &scal, &src_of_pos, &pct, &cutoff,
                      &D, &cub_tmp, &mean, &sxx, &med, &bad, &stat, &status, &p_edge,
                      &coef, &iters, &act, &counters, &sortk, &sortk2, &idx, &idx2, &ps, &sa, &sb, &tile_cnt,
                      &tile_base, &seg_n, &tile_min, &tile_carry, &padj_best, &cat_best, &cat, &padj, &med_out,
@@ -471,6 +471,7 @@ BsArgs make_bs_args(Shard& s, int64_t E) {
   B.E = E;
   B.act_t = s.order_tested_only ? s.act_t.as<uint4>() : nullptr;
   B.nch = s.act_nch;
+  B.run_first = nullptr;  // (set where the order is built)
   B.ea = s.ea.as<int32_t>();
   B.eb = s.eb.as<int32_t>();
   return B;
@@ -1728,11 +1729,13 @@ int run_shard_back(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
         ctx->launches += 2;
         trace_mark(ctx, "cub::ExclusiveSum", s.s_main);
       }
+      CU(s.run_first.ensure((size_t)(E / BS_CAP + 4) * 4));
+      B.run_first = s.run_first.as<int>();
       LAUNCH(k_bsort_scatter, blocks_for(E, 256), 256, scan_in_cta ? (size_t)bs_padded(NB) * 4 : 0, s.s_main, B, scan_in_cta,
              s.p_edge.as<double>(), s.sortk.as<unsigned long long>(), s.idx.as<int32_t>(),
              s.scal.as<int32_t>() + 2 * SC_ERR);
       LAUNCH(k_bsort_sort, blocks_for(E, BS_CAP), BS_SORT_THREADS, 0, s.s_main, B, s.sortk.as<unsigned long long>(),
-             s.idx.as<int32_t>(), s.ea.as<int32_t>(), s.eb.as<int32_t>(), s.ps.as<double>(), s.sa.as<int32_t>(),
+             s.idx.as<int32_t>(), s.ps.as<double>(), s.sa.as<int32_t>(),
              s.sb.as<int32_t>(), s.idx2.as<int32_t>(), s.scal.as<int32_t>() + 2 * SC_ERR);
     } else {
       LAUNCH(k_sort_keys, blocks_for(E, 256), 256, 0, s.s_main, s.p_edge.as<double>(), E,
