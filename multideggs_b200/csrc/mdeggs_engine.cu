@@ -1680,13 +1680,21 @@ int run_shard_back(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
   if (n_nodes > 0 && P > 0 && E > 0) {
     // (also writes NaN into the p.adj rows of the edges that are not tested at a percentile)
     const size_t pc_smem = (size_t)(3 * P + (want_seg_cnt ? P * K : 0)) * sizeof(unsigned);
+    // long edge lists: a capped grid (half of every SM's thread slots) walks the list with a grid stride, so that the
+    // ordering kernels of the main stream run beside this compute-bound kernel instead of queueing behind it
+    unsigned pc_grid = blocks_for(E, 256);
+    {
+      static const int cap_env = getenv("MDEGGS_PERC_CAP") ? atoi(getenv("MDEGGS_PERC_CAP")) : 4;
+      const unsigned cap = (unsigned)(s.sm_count * cap_env);
+      if (do_adjust && !count_in_percolate && cap_env > 0 && pc_grid > 4 * cap) pc_grid = cap;
+    }
     if (count_in_percolate) {  // several ranks: the gathered p-values are dropped into their buckets in the same pass
       PercolateBucketTail tail{make_bs_args(s, E)};
-      LAUNCH(k_percolate<PercolateBucketTail>, blocks_for(E, 256), 256, pc_smem, s.s_sort, tail, s.ea.as<int32_t>(),
+      LAUNCH(k_percolate<PercolateBucketTail>, pc_grid, 256, pc_smem, s.s_sort, tail, s.ea.as<int32_t>(),
              s.eb.as<int32_t>(), s.status.as<int32_t>(), s.p_edge.as<double>(), s.act_t.as<uint4>(), s.act_nch, E, P, c_tot,
              c_fail, c_raw, d_cat, d_padj, s.scal.as<int32_t>() + 2 * SC_ERR, K, want_seg_cnt ? d_seg_cnt : nullptr);
     } else {
-      LAUNCH(k_percolate<PercolateNoTail>, blocks_for(E, 256), 256, pc_smem, s.s_sort, PercolateNoTail{}, s.ea.as<int32_t>(),
+      LAUNCH(k_percolate<PercolateNoTail>, pc_grid, 256, pc_smem, s.s_sort, PercolateNoTail{}, s.ea.as<int32_t>(),
              s.eb.as<int32_t>(), s.status.as<int32_t>(), s.p_edge.as<double>(), s.act_t.as<uint4>(), s.act_nch, E, P, c_tot,
              c_fail, c_raw, d_cat, d_padj, s.scal.as<int32_t>() + 2 * SC_ERR, K, want_seg_cnt ? d_seg_cnt : nullptr);
     }

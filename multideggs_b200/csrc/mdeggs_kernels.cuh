@@ -809,7 +809,11 @@ __global__ void __launch_bounds__(256) k_percolate(Tail tail, const int32_t* __r
   const int n_cnt = 3 * P + (seg_cnt ? P * K : 0);
   for (int i = threadIdx.x; i < n_cnt; i += blockDim.x) s_cnt[i] = 0;
   __syncthreads();
-  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  // (a capped grid walks the edge list with a grid stride: on long lists the kernel then leaves room on every SM for the
+  // memory-bound ordering kernels of the main stream instead of running ahead of them)
+  const int lane = threadIdx.x & 31;
+  for (int64_t e0 = (int64_t)blockIdx.x * blockDim.x; e0 < E; e0 += (int64_t)gridDim.x * blockDim.x) {
+  const int64_t e = e0 + threadIdx.x;
   const bool live = e < E;
   int a = 0, b = 0, st = 0;
   double pv = 1.0;
@@ -820,7 +824,6 @@ __global__ void __launch_bounds__(256) k_percolate(Tail tail, const int32_t* __r
     pv = p_edge[e];
   }
   const bool hard = (st == MDEGGS_EDGE_SINGULAR || st == MDEGGS_EDGE_NONFINITE);
-  const int lane = threadIdx.x & 31;
   const unsigned w_hard = __ballot_sync(0xffffffffu, hard);
   const unsigned w_sig = __ballot_sync(0xffffffffu, pv < 0.05);
   const unsigned w_val = __ballot_sync(0xffffffffu, !isnan(pv));
@@ -867,6 +870,7 @@ __global__ void __launch_bounds__(256) k_percolate(Tail tail, const int32_t* __r
     }
   }
   tail(live, tested_bits != 0u, e, pv);  // (reached by whole warps)
+  }
   __syncthreads();
   for (int i = threadIdx.x; i < P; i += blockDim.x) {
     if (s_cnt[i]) atomicAdd(&tot[i], (unsigned long long)s_cnt[i]);
