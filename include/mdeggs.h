@@ -229,6 +229,9 @@ int mdeggs_trace_get(const mdeggs_ctx* ctx, int i, char* name, int name_cap, int
  * "h2d_pipeline" (1 = the band of a column-major HOST matrix crosses PCIe in row chunks of 12 MB on two copy streams while
  * the compute phase already runs: the TMA loader of the front kernel waits for the chunk that holds its tile [default];
  * 0 = the whole band is copied before the compute phase starts; n > 1 = chunks of n MB);
+ * "p2p" (one process per GPU, world > 1: 1 = the all-gather of the p-value / status blocks is a push over peer memory -
+ * every rank writes its block straight into the IPC-mapped buffers of its peers over NVLink and raises a flag word
+ * there [default; falls back to NCCL when the mappings cannot be made], 0 = ncclAllGather);
  * "tail_spline" (1 = two-category lm on edge lists of 16,384 edges or more per rank reads its t tails from ONE per-run
  * interpolation table, built on the side stream from the same series / continued fractions [default]; 0 = every edge
  * runs its own series / fraction; 2 = the table on every two-category lm call);

@@ -33,6 +33,7 @@
 #include "mdeggs_qsel.cuh"
 #include "mdeggs_front.cuh"
 #include "mdeggs_hostpack.h"
+#include "mdeggs_p2p.cuh"
 #include "nccl_dl.h"
 
 using namespace mdeggs;
@@ -44,8 +45,10 @@ namespace {
 struct DevBuf {
   void* p = nullptr;
   size_t cap = 0;
+  int gen = 0;  // (re)allocations so far: the same on every rank of a multi-rank job (same sizes, same history)
   cudaError_t ensure(size_t bytes) {
     if (bytes <= cap) return cudaSuccess;
+    ++gen;
     if (p && cap) cudaFree(p);  // cap == 0 marks a borrowed caller pointer
     p = nullptr;
     cap = 0;
@@ -79,6 +82,16 @@ struct Shard {
   cudaEvent_t ev_copy_go = nullptr, ev_copy_done = nullptr, ev_copy2_done = nullptr;
   // streamed input copy (stage_inputs): the band of a host matrix crosses PCIe in row chunks on s_copy while the
   // compute phase already runs; chunk c is complete once gate[c] != 0 (a stream-ordered 32-bit write behind its copy)
+  // peer-memory all-gather (mdeggs_p2p.cuh), one process per GPU: mappings of every rank's p_edge / status bytes / flags
+  struct P2P {
+    bool flags_ok = false, ok = false, failed = false;
+    int gen_p = -1, gen_st = -1;
+    void* peer_p[P2P_MAX] = {};
+    void* peer_st[P2P_MAX] = {};
+    void* peer_flags[P2P_MAX] = {};
+    bool used = false;  // this call pushed its block (k_signal_done closes it)
+    PushArgs args;
+  } p2p;
   bool tail_sp_on = false;  // this call's t tails come from the interpolation table (k_tail_spline)
   bool gated = false;
   int gate_chunks = 0;
@@ -121,11 +134,11 @@ struct Shard {
     if (e == cudaSuccess) h_stage_cap = bytes + 256;
     return e;
   }
-  DevBuf run_first, tail_sp, gate, st8, act_t, Dc, tile_need, na_q, bh1_state, assay, from, to, ea, eb, stage_dev, bs_count, bs_slot, seg_done, seg_rank, fin_q, hm_p, hm_q1, hm_c, hm_sc, hm_idx, hm_off, seg_pi0, B16, stamps, excl, node_of_row, rowlist, scal, src_of_pos, pct, cutoff, D, cub_tmp, mean, sxx, med, bad, stat, status, p_edge, coef, iters, act, counters, sortk, sortk2, idx,
+  DevBuf p2p_flags, p2p_x, run_first, tail_sp, gate, st8, act_t, Dc, tile_need, na_q, bh1_state, assay, from, to, ea, eb, stage_dev, bs_count, bs_slot, seg_done, seg_rank, fin_q, hm_p, hm_q1, hm_c, hm_sc, hm_idx, hm_off, seg_pi0, B16, stamps, excl, node_of_row, rowlist, scal, src_of_pos, pct, cutoff, D, cub_tmp, mean, sxx, med, bad, stat, status, p_edge, coef, iters, act, counters, sortk, sortk2, idx,
       idx2, ps, sa, sb, tile_cnt, tile_base, seg_n, tile_min, tile_carry, padj_best, cat_best, cat, padj, med_out,
       small_out, rsel_hist, rsel_state, rsel_cand, dense_S, cf_tab, sxy;
   void release_all() {
-    DevBuf* all[] = {&run_first, &tail_sp, &gate, &st8, &act_t, &Dc, &tile_need, &na_q, &bh1_state, &assay, &from, &to, &ea, &eb, &stage_dev, &bs_count, &bs_slot, &seg_done, &seg_rank, &fin_q, &hm_p, &hm_q1, &hm_c, &hm_sc, &hm_idx, &hm_off, &seg_pi0, &B16, &stamps, &excl, &node_of_row, &rowlist, &scal, &src_of_pos, &pct, &cutoff,
+    DevBuf* all[] = {&p2p_flags, &p2p_x, &run_first, &tail_sp, &gate, &st8, &act_t, &Dc, &tile_need, &na_q, &bh1_state, &assay, &from, &to, &ea, &eb, &stage_dev, &bs_count, &bs_slot, &seg_done, &seg_rank, &fin_q, &hm_p, &hm_q1, &hm_c, &hm_sc, &hm_idx, &hm_off, &seg_pi0, &B16, &stamps, &excl, &node_of_row, &rowlist, &scal, &src_of_pos, &pct, &cutoff,
                      &D, &cub_tmp, &mean, &sxx, &med, &bad, &stat, &status, &p_edge,
                      &coef, &iters, &act, &counters, &sortk, &sortk2, &idx, &idx2, &ps, &sa, &sb, &tile_cnt,
                      &tile_base, &seg_n, &tile_min, &tile_carry, &padj_best, &cat_best, &cat, &padj, &med_out,
@@ -165,6 +178,7 @@ struct mdeggs_ctx {
   cudaGraphExec_t graph_exec = nullptr;
   int64_t graph_launches = 0;
   int graph_fit_path = 0;    // stats.fit_path of the captured call (run_shard_main does not run on replay)
+  bool graph_p2p = false;    // ... and whether it pushed its block over peer memory (k_signal_done follows every call)
   int64_t rsel_cap_override = 0;  // option "rsel_cap": shrink the candidate list to exercise the overflow path (tests)
   int fit_path_override = -1;  // -1 auto, 0 force streaming, 1 force dense (MDEGGS_FIT_PATH, tests)
   int bh_onepass = 1;          // option "bh_onepass": 0 keeps the three-launch K8 for small edge lists too (tests)
@@ -189,6 +203,7 @@ struct mdeggs_ctx {
     size_t h_cap = 0;
     PackJob job;
   } pack;
+  int p2p = 1;                 // option "p2p": 1 = peer-memory push all-gather with one process per GPU, 0 = NCCL
   int launch_async = -1;       // -1 not probed yet, 1 kernel launches return before the kernel ends, 0 they do not
   int copy_streams = 2;        // option "copy_streams": streams the chunks of a streamed input copy alternate between
   int h2d_pipeline = 1;        // option "h2d_pipeline": 0 = the whole band is copied before the compute phase starts
@@ -1553,7 +1568,88 @@ int run_shard_main(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
   return MDEGGS_OK;
 }
 
-// NCCL all-gather of the per-rank edge blocks (p-values, status and whatever per-edge output was requested)
+
+// ---- peer-memory all-gather set-up (one process per GPU) ------------------------------------------------------------
+// All ranks call this at the same point of the same call (buffer generations are identical everywhere).  Handles travel
+// through the NCCL communicator; the outcome is agreed on with an all-reduce, so either every rank pushes or none does.
+int p2p_prepare(mdeggs_ctx* ctx, Shard& s) {
+  Shard::P2P& X = s.p2p;
+  X.used = false;
+  if (!ctx->p2p || X.failed || s.world < 2 || s.world > P2P_MAX || ctx->shards.size() != 1) return MDEGGS_OK;
+  if (X.ok && X.gen_p == s.p_edge.gen && X.gen_st == s.st8.gen) return MDEGGS_OK;
+  if (ctx->capturing) {  // (cannot happen: captured calls find every buffer in place) - NCCL for this graph
+    X.ok = false;
+    return MDEGGS_OK;
+  }
+  NcclApi& api = nccl_api();
+  const int W = s.world;
+  struct Rec {
+    cudaIpcMemHandle_t p, st, fl;
+  };
+  static_assert(sizeof(Rec) == 192, "three 64-byte handles");
+  bool good = true;
+  if (!X.flags_ok) {
+    if (s.p2p_flags.ensure(64 * 4) != cudaSuccess || cudaMemsetAsync(s.p2p_flags.p, 0, 64 * 4, s.s_main) != cudaSuccess)
+      good = false;
+  }
+  Rec mine;
+  memset(&mine, 0, sizeof mine);
+  if (good && (cudaIpcGetMemHandle(&mine.p, s.p_edge.p) != cudaSuccess ||
+               cudaIpcGetMemHandle(&mine.st, s.st8.p) != cudaSuccess ||
+               cudaIpcGetMemHandle(&mine.fl, s.p2p_flags.p) != cudaSuccess))
+    good = false;
+  cudaGetLastError();
+  CU(s.p2p_x.ensure((size_t)W * sizeof(Rec) + 64));
+  std::vector<Rec> all((size_t)W);
+  char* dx = s.p2p_x.as<char>();
+  CU(cudaMemcpyAsync(dx + (size_t)s.rank * sizeof(Rec), &mine, sizeof(Rec), cudaMemcpyHostToDevice, s.s_main));
+  NC(api.AllGather(dx + (size_t)s.rank * sizeof(Rec), dx, sizeof(Rec), NCCL_INT8, s.comm, s.s_main));
+  CU(cudaMemcpyAsync(all.data(), dx, (size_t)W * sizeof(Rec), cudaMemcpyDeviceToHost, s.s_main));
+  CU(cudaStreamSynchronize(s.s_main));
+  // (old mappings of the data buffers go first: the owners have reallocated them)
+  for (int r = 0; r < W; ++r) {
+    if (r == s.rank) continue;
+    if (X.peer_p[r]) cudaIpcCloseMemHandle(X.peer_p[r]);
+    if (X.peer_st[r]) cudaIpcCloseMemHandle(X.peer_st[r]);
+    X.peer_p[r] = X.peer_st[r] = nullptr;
+  }
+  cudaGetLastError();
+  for (int r = 0; r < W && good; ++r) {
+    if (r == s.rank) {
+      X.peer_p[r] = s.p_edge.p;
+      X.peer_st[r] = s.st8.p;
+      X.peer_flags[r] = s.p2p_flags.p;
+      continue;
+    }
+    if (cudaIpcOpenMemHandle(&X.peer_p[r], all[(size_t)r].p, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+        cudaIpcOpenMemHandle(&X.peer_st[r], all[(size_t)r].st, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess)
+      good = false;
+    if (good && !X.flags_ok &&
+        cudaIpcOpenMemHandle(&X.peer_flags[r], all[(size_t)r].fl, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess)
+      good = false;
+  }
+  cudaGetLastError();
+  // agreement: the minimum over ranks of "all my mappings are in place"
+  int32_t flag = good ? 1 : 0;
+  int32_t* dflag = reinterpret_cast<int32_t*>(dx + (size_t)W * sizeof(Rec));
+  CU(cudaMemcpyAsync(dflag, &flag, 4, cudaMemcpyHostToDevice, s.s_main));
+  NC(api.AllReduce(dflag, dflag, 1, NCCL_INT32, NCCL_MIN, s.comm, s.s_main));
+  CU(cudaMemcpyAsync(&flag, dflag, 4, cudaMemcpyDeviceToHost, s.s_main));
+  CU(cudaStreamSynchronize(s.s_main));
+  if (flag != 1) {
+    X.ok = false;
+    X.failed = true;  // stay on NCCL (every rank takes the same decision)
+    return MDEGGS_OK;
+  }
+  X.flags_ok = true;
+  X.ok = true;
+  X.gen_p = s.p_edge.gen;
+  X.gen_st = s.st8.gen;
+  return MDEGGS_OK;
+}
+
+// all-gather of the per-rank edge blocks (p-values, status and whatever per-edge output was requested): peer-memory
+// push with one process per GPU (mdeggs_p2p.cuh), NCCL otherwise
 int run_collective(mdeggs_ctx* ctx, const mdeggs_problem* in, const mdeggs_result* out) {
   const int64_t E = in->E;
   Shard& s0 = ctx->shards[0];
@@ -1561,22 +1657,54 @@ int run_collective(mdeggs_ctx* ctx, const mdeggs_problem* in, const mdeggs_resul
     NcclApi& api = nccl_api();
     const int64_t chunk = (E + s0.world - 1) / s0.world;
     const bool is_rlm = (in->K == 2 && in->method == MDEGGS_METHOD_RLM);
-    for (Shard& s : ctx->shards) {  // status codes as bytes
+    for (Shard& s : ctx->shards) {
       CU(cudaSetDevice(s.device));
       CU(s.st8.ensure((size_t)chunk * s0.world));
-      const int64_t lo = (int64_t)s.rank * chunk < E ? (int64_t)s.rank * chunk : E;
-      const int64_t n_own = lo + chunk < E ? chunk : E - lo;
-      if (n_own > 0)
-        LAUNCH(k_pack_status, blocks_for(n_own, 256), 256, 0, s.s_main, s.status.as<int32_t>() + lo, n_own,
-               s.st8.as<int8_t>() + lo);
     }
+    bool pushed = false;
+    if (ctx->shards.size() == 1) {
+      int rc = p2p_prepare(ctx, s0);
+      if (rc) return rc;
+      if (s0.p2p.ok) {
+        Shard& s = s0;
+        PushArgs& A = s.p2p.args;
+        memset(&A, 0, sizeof A);
+        for (int r = 0; r < s.world; ++r) {
+          A.p_dst[r] = static_cast<double*>(s.p2p.peer_p[r]);
+          A.st_dst[r] = static_cast<int8_t*>(s.p2p.peer_st[r]);
+          A.flag_dst[r] = static_cast<unsigned int*>(s.p2p.peer_flags[r]);
+        }
+        A.status = s.status.as<int32_t>();
+        A.world = s.world;
+        A.rank = s.rank;
+        A.lo = (long long)((int64_t)s.rank * chunk < E ? (int64_t)s.rank * chunk : E);
+        A.n_own = (long long)(A.lo + chunk < E ? chunk : E - A.lo);
+        A.ctl = s.p2p_flags.as<unsigned int>() + 2 * P2P_MAX;
+        A.err = s.scal.as<int32_t>() + 2 * SC_ERR;
+        LAUNCH(k_push_gather, (unsigned)(s.sm_count * 4), 256, 0, s.s_main, A);
+        LAUNCH(k_wait_gather, 1, 32, 0, s.s_main, A);
+        s.p2p.used = true;
+        pushed = true;
+      }
+    }
+    if (!pushed)
+      for (Shard& s : ctx->shards) {  // status codes as bytes
+        CU(cudaSetDevice(s.device));
+        const int64_t lo = (int64_t)s.rank * chunk < E ? (int64_t)s.rank * chunk : E;
+        const int64_t n_own = lo + chunk < E ? chunk : E - lo;
+        if (n_own > 0)
+          LAUNCH(k_pack_status, blocks_for(n_own, 256), 256, 0, s.s_main, s.status.as<int32_t>() + lo, n_own,
+                 s.st8.as<int8_t>() + lo);
+      }
     NC(api.GroupStart());
     for (Shard& s : ctx->shards) {
       CU(cudaSetDevice(s.device));
       char* pe = (char*)s.p_edge.p;
       char* st = (char*)s.st8.p;
-      NC(api.AllGather(pe + (size_t)s.rank * chunk * 8, pe, (size_t)chunk, NCCL_FLOAT64, s.comm, s.s_main));
-      NC(api.AllGather(st + (size_t)s.rank * chunk, st, (size_t)chunk, NCCL_INT8, s.comm, s.s_main));
+      if (!pushed) {
+        NC(api.AllGather(pe + (size_t)s.rank * chunk * 8, pe, (size_t)chunk, NCCL_FLOAT64, s.comm, s.s_main));
+        NC(api.AllGather(st + (size_t)s.rank * chunk, st, (size_t)chunk, NCCL_INT8, s.comm, s.s_main));
+      }
       if (out->stat) {
         char* x = (char*)s.stat.p;
         NC(api.AllGather(x + (size_t)s.rank * chunk * 8, x, (size_t)chunk, NCCL_FLOAT64, s.comm, s.s_main));
@@ -1600,7 +1728,7 @@ int run_collective(mdeggs_ctx* ctx, const mdeggs_problem* in, const mdeggs_resul
   for (Shard& s : ctx->shards) {
     CU(cudaSetDevice(s.device));
     EVREC(s.ev[EV_COLL], s.s_main);
-    if (s0.world > 1 && E > 0) trace_mark(ctx, "(ncclAllGather p, status)", s.s_main);
+    if (s0.world > 1 && E > 0) trace_mark(ctx, s0.p2p.used ? "(peer push p, status)" : "(ncclAllGather p, status)", s.s_main);
   }
   return MDEGGS_OK;
 }
@@ -1621,7 +1749,11 @@ int run_shard_back(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
   // stream, after the activity masks, while the main stream orders the edges; both join before K8
   // several ranks: the p-values arrived through the all-gather, so the bucket counting could not ride in k_finish; it
   // rides in k_percolate instead (its buffers are cleared before the side stream forks off)
-  const bool count_in_percolate = do_adjust && s.world > 1 && use_bucket_order(ctx, in, n_nodes) && s.order_tested_only;
+  // several ranks: the gathered p-values still have to be dropped into their buckets: by k_bsort_count on the main stream,
+  // beside the (capped) k_percolate of the side stream [default: config 5 on 2 GPUs 1.91 -> 1.87 ms], or -
+  // MDEGGS_COUNT_IN_PERC=1 - inside k_percolate (one pass over the edges instead of two, but then the ordering waits for it)
+  static const int count_in_perc_env = getenv("MDEGGS_COUNT_IN_PERC") ? atoi(getenv("MDEGGS_COUNT_IN_PERC")) : 0;
+  const bool count_in_percolate = count_in_perc_env && do_adjust && s.world > 1 && use_bucket_order(ctx, in, n_nodes) && s.order_tested_only;
   if (count_in_percolate) {
     CU(s.bs_count.ensure((size_t)2 * bs_padded(bs_nbuckets(E)) * 4));
     CU(s.bs_slot.ensure((size_t)E * 4));
@@ -2123,6 +2255,13 @@ int mdeggs_destroy(mdeggs_ctx* ctx) {
     cudaSetDevice(s.device);
     cudaDeviceSynchronize();
     if (s.h_stage) cudaFreeHost(s.h_stage);
+    for (int r = 0; r < P2P_MAX; ++r)
+      if (r != s.rank) {
+        if (s.p2p.peer_p[r]) cudaIpcCloseMemHandle(s.p2p.peer_p[r]);
+        if (s.p2p.peer_st[r]) cudaIpcCloseMemHandle(s.p2p.peer_st[r]);
+        if (s.p2p.peer_flags[r]) cudaIpcCloseMemHandle(s.p2p.peer_flags[r]);
+      }
+    cudaGetLastError();
     if (s.comm) nccl_api().CommDestroy(s.comm);
     s.release_all();
     for (int i = 0; i < EV_COUNT; ++i)
@@ -2224,6 +2363,7 @@ int mdeggs_submit_omic(mdeggs_ctx* ctx, const mdeggs_problem* in, mdeggs_result*
   ctx->trace_used = 0;
   const int src_device = ctx->shards[0].device;
   Shard& sh0 = ctx->shards[0];
+  sh0.p2p.used = false;
   // ---- phase A: inputs (eager) ----
   for (Shard& s : ctx->shards) {
     rc = stage_inputs(ctx, s, in, H, src_device);
@@ -2314,6 +2454,7 @@ int mdeggs_submit_omic(mdeggs_ctx* ctx, const mdeggs_problem* in, mdeggs_result*
         } else {
           ctx->graph_launches = ctx->launches;
           ctx->graph_fit_path = ctx->stats.fit_path;
+          ctx->graph_p2p = sh0.p2p.used;
         }
       }
     }
@@ -2327,6 +2468,7 @@ int mdeggs_submit_omic(mdeggs_ctx* ctx, const mdeggs_problem* in, mdeggs_result*
       CU(cudaEventRecord(sh0.ev[EV_ADJ], sh0.s_main));
       ctx->launches = ctx->graph_launches;
       ctx->stats.fit_path = ctx->graph_fit_path;
+      sh0.p2p.used = ctx->graph_p2p;
       replayed = true;
     }
   }
@@ -2362,6 +2504,9 @@ int mdeggs_submit_omic(mdeggs_ctx* ctx, const mdeggs_problem* in, mdeggs_result*
     rc = emit_outputs(ctx, sh0, in, out, H, n_nodes);
     if (rc) return rc;
   }
+  // peer-memory all-gather: this rank no longer reads the gathered values (its outputs are out): the peers' next push
+  // may overwrite them
+  if (sh0.p2p.used) LAUNCH(k_signal_done, 1, 32, 0, sh0.s_main, sh0.p2p.args);
   if (getenv("MDEGGS_HOSTTIME") && sh0.stamps.p) LAUNCH(k_stamp, 1, 1, 0, sh0.s_main, sh0.stamps.as<unsigned long long>() + 3);
   const auto t_host2 = std::chrono::steady_clock::now();
   for (size_t i = 1; i < ctx->shards.size(); ++i) {
@@ -2407,6 +2552,10 @@ int mdeggs_wait(mdeggs_ctx* ctx) {
   {
     int32_t err_flag = 0;
     finish_small_outputs(s0, in, out, &n_nodes, &err_flag);
+    if (err_flag == P2P_ERR) {
+      set_err(ctx, "a peer's p-value block did not arrive (peer-memory all-gather; option p2p = 0 selects NCCL)");
+      return MDEGGS_ECUDA;
+    }
     if (err_flag == GATE_ERR) {
       set_err(ctx, "the streamed input copy did not arrive (option h2d_pipeline = 0 disables it)");
       return MDEGGS_ECUDA;
@@ -2505,6 +2654,10 @@ int mdeggs_set_option(mdeggs_ctx* ctx, const char* name, int64_t value) {
   }
   if (!strcmp(name, "h2d_pipeline")) {  // 0 off, 1 on (12 MB chunks), > 1: chunk size in MB
     ctx->h2d_pipeline = (int)value;
+    return MDEGGS_OK;
+  }
+  if (!strcmp(name, "p2p")) {
+    ctx->p2p = (int)value;
     return MDEGGS_OK;
   }
   if (!strcmp(name, "tail_spline")) {

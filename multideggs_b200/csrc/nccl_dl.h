@@ -15,7 +15,7 @@ typedef struct {
   char internal[128];
 } nccl_unique_id;
 enum { NCCL_INT8 = 0, NCCL_INT32 = 2, NCCL_UINT64 = 5, NCCL_FLOAT64 = 8 };
-enum { NCCL_SUM = 0 };
+enum { NCCL_SUM = 0, NCCL_MIN = 3 };
 
 struct NcclApi {
   void* handle = nullptr;
