@@ -413,6 +413,21 @@ def test_single_process_multi_gpu_matches_one_gpu(engine):
     eng2.close()
 
 
+def test_one_process_per_gpu_peer_push_matches_one_gpu():
+    """One process per GPU (torchrun, 2 ranks): the peer-memory all-gather (k_push_gather over IPC-mapped buffers) and the
+    ncclAllGather path both reproduce the single-GPU results bit for bit, eagerly and under graph replay, across buffer
+    re-allocations (tools/p2p_check.py)."""
+    import os, subprocess, sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "tools", "p2p_check.py")],
+                         capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0 and "p2p_check ok" in res.stdout, res.stdout[-2000:] + res.stderr[-4000:]
+
+
 def test_node_band_copy_and_leading_dimension(engine, oracle):
     """Only the band of node rows crosses PCIe; ld > G (a sub-matrix of a bigger R matrix) is honoured."""
     import ctypes as C
