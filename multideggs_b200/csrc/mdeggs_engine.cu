@@ -1759,6 +1759,20 @@ int run_shard_back(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
     CU(s.bs_slot.ensure((size_t)E * 4));
     CU(cudaMemsetAsync(s.bs_count.p, 0, (size_t)(bs_nbuckets(E) + 1) * 4, s.s_main));
   }
+  // single GPU, many buckets: the device-wide scan of the bucket counts (they are final: k_finish wrote them) runs BEFORE
+  // the side stream forks off - beside the compute-bound k_percolate its look-back CTAs crawl (137 us instead of 8)
+  bool scan_done_early = false;
+  if (do_adjust && s.world == 1 && use_bucket_order(ctx, in, n_nodes) && bs_nbuckets(E) > BS_SCAN_SMEM) {
+    BsArgs B0 = make_bs_args(s, E);
+    const int NB0 = bs_nbuckets(E);
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, B0.count, B0.base, NB0 + 1, s.s_main);
+    CU(s.cub_tmp.ensure(tb));
+    CU(cub::DeviceScan::ExclusiveSum(s.cub_tmp.p, tb, B0.count, B0.base, NB0 + 1, s.s_main));
+    ctx->launches += 2;
+    trace_mark(ctx, "cub::ExclusiveSum", s.s_main);
+    scan_done_early = true;
+  }
   CU(cudaEventRecord(s.ev_fork, s.s_main));  // p-values and status of every edge are final
   CU(cudaStreamWaitEvent(s.s_sort, s.ev_fork, 0));
   // counters: tot[P] fail[P] sig[P] sig_raw[P] (u64), then out: tot_out[P] sig_out[P] fail_out[P] (i64)
@@ -1861,7 +1875,7 @@ int run_shard_back(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const md
       }
       const int NB = bs_nbuckets(E);
       const int scan_in_cta = NB <= BS_SCAN_SMEM;
-      if (!scan_in_cta) {  // many buckets: device-wide scan of count[0..NB] (count[NB] == 0, so base[NB] = total)
+      if (!scan_in_cta && !scan_done_early) {  // many buckets: device-wide scan of count[0..NB] (count[NB] == 0, so base[NB] = total)
         size_t tb = 0;
         cub::DeviceScan::ExclusiveSum(nullptr, tb, B.count, B.base, NB + 1, s.s_main);
         CU(s.cub_tmp.ensure(tb));
