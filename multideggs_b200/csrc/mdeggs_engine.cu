@@ -194,6 +194,12 @@ struct mdeggs_ctx {
     bool deferred = false;     // ... and its chunks still have to be packed + sent (submit decides when, see there)
     bool last_packed = false;  // the last completed call was packed: mdeggs_pair_moments translates row numbers
     std::vector<int32_t> rows, rank;
+    // the edge list the node rows above were derived from: repeated calls with the same network (nestedcv folds,
+    // benchmarks) compare (exactly, memcmp) instead of analysing again - 30 instead of 100 us in front of the first DMA
+    std::vector<int32_t> seen_from, seen_to;
+    int32_t seen_G = -1;
+    bool rows_valid = false;   // rows / rank describe the edge list of THIS call (stage_inputs reads the band from them)
+    bool idx_ok = false;       // ... and every index was inside 1..G
     std::vector<double> med_tmp;   // medians of the packed problem [K x nodes]; mdeggs_wait spreads them over [K x G]
     double* user_median = nullptr;
     int32_t user_G = 0;
@@ -705,12 +711,21 @@ int plan_host_pack(mdeggs_ctx* ctx, const mdeggs_problem* in) {
   mdeggs_ctx::HostPack& K = ctx->pack;
   K.active = false;
   K.deferred = false;
+  K.rows_valid = false;
   if (!ctx->host_pack || in->mem != MDEGGS_MEM_HOST || in->layout != MDEGGS_LAYOUT_COLMAJOR || in->E <= 0 ||
       in->E > ((int64_t)1 << 20) || ctx->shards.size() != 1 || ctx->zero_copy)
     return MDEGGS_OK;
   const size_t min_bytes = ctx->host_pack >= 2 ? 0 : ((size_t)2 << 20);
   if ((size_t)in->G * (size_t)in->n * 8 < min_bytes) return MDEGGS_OK;  // small matrices: the plain copy is as good
-  pack_node_rows(in->from, in->to, in->E, in->G, K.rows, K.rank);
+  const size_t eb = (size_t)in->E * 4;
+  if (!(K.seen_G == in->G && K.seen_from.size() == (size_t)in->E && memcmp(K.seen_from.data(), in->from, eb) == 0 &&
+        memcmp(K.seen_to.data(), in->to, eb) == 0)) {
+    K.idx_ok = pack_node_rows(in->from, in->to, in->E, in->G, K.rows, K.rank);
+    K.seen_from.assign(in->from, in->from + in->E);
+    K.seen_to.assign(in->to, in->to + in->E);
+    K.seen_G = in->G;
+  }
+  K.rows_valid = true;
   const int64_t nn = (int64_t)K.rows.size();
   if (nn == 0 || (size_t)nn * (size_t)in->n * 8 < min_bytes) return MDEGGS_OK;
   const int64_t band = (int64_t)K.rows.back() - K.rows.front() + 1;
@@ -853,7 +868,13 @@ int stage_inputs(mdeggs_ctx* ctx, Shard& s, const mdeggs_problem* in, const Host
     // the node-row RANGE [r_lo, r_hi] in one pass over from/to and only that band crosses PCIe (config 3: the
     // 8,405 node genes are the first rows of 20,000 -> 67 MB instead of 160 MB).
     int64_t r_lo = 0, r_hi = G - 1;
-    if (E > 0 && E <= (int64_t)1 << 20) {
+    if (E > 0 && E <= (int64_t)1 << 20 && ctx->pack.rows_valid && !ctx->pack.active) {
+      // (plan_host_pack has just analysed this very edge list: the band is its first and last node row)
+      if (ctx->pack.idx_ok && !ctx->pack.rows.empty()) {
+        r_lo = (int64_t)ctx->pack.rows.front() & ~(int64_t)15;
+        r_hi = ctx->pack.rows.back();
+      }
+    } else if (E > 0 && E <= (int64_t)1 << 20) {
       int32_t lo = INT32_MAX, hi = 0;
       for (const int32_t* v : {in->from, in->to}) {  // two plain min/max reductions: the host compiler vectorises them
         int32_t l = INT32_MAX, h = 0;
