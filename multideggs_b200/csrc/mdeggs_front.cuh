@@ -181,10 +181,18 @@ __device__ __forceinline__ double warp_select_dbl(const double (&v)[ITEMS], int 
   } else {
     if (lane == 0) *scratch_n = 0u;
     __syncwarp();
+    if (!lo_open && !hi_open) {  // the usual case: both sides of the bracket are values (two compares per item)
 #pragma unroll
-    for (int j = 0; j < ITEMS; ++j) {
-      const double x = v[j];
-      if ((lo_open ? x == x : x >= lo_d) && (hi_open || x < hi_d)) scratch32[atomicAdd(scratch_n, 1u)] = x;
+      for (int j = 0; j < ITEMS; ++j) {
+        const double x = v[j];
+        if (x >= lo_d && x < hi_d) scratch32[atomicAdd(scratch_n, 1u)] = x;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < ITEMS; ++j) {
+        const double x = v[j];
+        if ((lo_open ? x == x : x >= lo_d) && (hi_open || x < hi_d)) scratch32[atomicAdd(scratch_n, 1u)] = x;
+      }
     }
     __syncwarp();
     const int ncand = cnt_hi - cnt_lo;

@@ -24,6 +24,7 @@
 // Versus a full 64-bit radix sort of the matrix: one read of a 2-byte side array instead of ~16 read+write sweeps of D.
 #pragma once
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdint.h>
 
 #include "mdeggs_kernels.cuh"
@@ -92,16 +93,29 @@ __device__ __forceinline__ int qs_bin(const QsKnots* __restrict__ kn, double x) 
   const float xf = (float)(x - kn->base);  // monotone; +-inf and overflow stay ordered
   const unsigned e = kn->tab[qs_tab_index(xf, kn->inv_w, QS_TAB)];
   int c = (int)(e & 63u);
+  // (an entry without the 0x40 flag has every value of its uniform cell below knot[c + 1], so the comparison is simply
+  // made for all of them: no second test; the shared-memory copy carries knot[QS_CELLS] = NaN, see qs_load_knots)
   if (e & 0x80u) c = qs_cell_search(kn, xf);
-  else if (e & 0x40u) c += (xf >= kn->knot[c + 1]);
+  else c += (xf >= kn->knot[c + 1]);
   int sub = (int)((xf - kn->knot[c]) * kn->scale[c]);  // NaN products (inf * 0) convert to 0
   sub = sub < 0 ? 0 : (sub > QS_SUB - 1 ? QS_SUB - 1 : sub);
   return c * QS_SUB + sub;
 }
 
 __device__ __forceinline__ void qs_load_knots(QsKnots* __restrict__ dst, const QsState* __restrict__ st) {
-  for (int i = threadIdx.x; i < (int)(sizeof(QsKnots) / 8); i += blockDim.x)
-    reinterpret_cast<double*>(dst)[i] = reinterpret_cast<const double*>(&st->knots)[i];
+  // (knot[QS_CELLS], the sample maximum, is not needed by qs_bin: the copy holds NaN there so that the unconditional
+  // "next cell?" comparison of qs_bin can never leave the last cell; written by the thread that copies its word)
+  constexpr int last_word = (int)(offsetof(QsKnots, knot) / 8) + QS_CELLS / 2;  // knot[QS_CELLS] is the low float of it
+  static_assert(offsetof(QsKnots, knot) % 8 == 0 && QS_CELLS % 2 == 0, "knot[QS_CELLS] sits in the low half of a word");
+  for (int i = threadIdx.x; i < (int)(sizeof(QsKnots) / 8); i += blockDim.x) {
+    double w = reinterpret_cast<const double*>(&st->knots)[i];
+    if (i == last_word) {
+      unsigned long long b = (unsigned long long)__double_as_longlong(w);
+      b = (b & 0xffffffff00000000ull) | 0x7fc00000ull;  // low float := NaN (">=" is false for every value, +inf included)
+      w = __longlong_as_double((long long)b);
+    }
+    reinterpret_cast<double*>(dst)[i] = w;
+  }
 }
 __device__ __forceinline__ void qs_flush_hist(const unsigned int* __restrict__ s_hist, unsigned int* __restrict__ hist) {
   for (int i = threadIdx.x; i < QS_BINS; i += blockDim.x) {
