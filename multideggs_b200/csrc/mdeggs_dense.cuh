@@ -10,6 +10,8 @@
 // DENSE_USE_MMA = 0), so each row is read nn/128 times instead of ~nn times.  (tcgen05 has no FP64 type.)
 // Only tile pairs with ti <= tj are computed (Sxy is symmetric); k_finish (src 1) then finishes each edge
 // from Sxy[min(a,b)][max(a,b)] with the same closed forms as the streaming path (finish_pair).
+// The kernel the engine launches is the TMA-fed form at the end of this file (k_center_rows + k_dense_tma: 16-sample
+// stages of a centred copy, mbarrier ring, no CTA barrier in the sample loop); k_dense_moments below is its fallback.
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
