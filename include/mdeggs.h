@@ -146,7 +146,8 @@ typedef struct mdeggs_stats {
                              bit 9: K8 ordered the edges through p-value buckets (no radix sort);
                              bit 10 / 11: fused front kernel fed by TMA / by its plain loader;
                              bit 12: ... while the host matrix was still streaming in (option "h2d_pipeline");
-                             bit 13: the call ran on host-packed node rows (option "host_pack")                  */
+                             bit 13: the call ran on host-packed node rows (option "host_pack");
+                             bit 14: several ranks exchanged their p-value blocks by a peer-memory push (option "p2p") */
   int32_t n_ranks;
   float ms_total;         /* device time of the whole pipeline (CUDA events on the engine stream)       */
   float ms_h2d, ms_gather, ms_stats, ms_quantile, ms_fit, ms_tail, ms_collective, ms_percolate, ms_adjust, ms_d2h;
@@ -229,9 +230,10 @@ int mdeggs_trace_get(const mdeggs_ctx* ctx, int i, char* name, int name_cap, int
  * "h2d_pipeline" (1 = the band of a column-major HOST matrix crosses PCIe in row chunks of 12 MB on two copy streams while
  * the compute phase already runs: the TMA loader of the front kernel waits for the chunk that holds its tile [default];
  * 0 = the whole band is copied before the compute phase starts; n > 1 = chunks of n MB);
- * "p2p" (one process per GPU, world > 1: 1 = the all-gather of the p-value / status blocks is a push over peer memory -
- * every rank writes its block straight into the IPC-mapped buffers of its peers over NVLink and raises a flag word
- * there [default; falls back to NCCL when the mappings cannot be made], 0 = ncclAllGather);
+ * "p2p" (several GPUs: 1 = the all-gather of the p-value / status blocks is a push over peer memory -
+ * every rank writes its block straight into the buffers of its peers over NVLink (IPC-mapped with one process per GPU,
+ * addressed directly with one process for all GPUs) and raises a flag word there [default; falls back to NCCL when the
+ * mappings cannot be made], 0 = ncclAllGather);
  * "tail_spline" (1 = two-category lm on edge lists of 16,384 edges or more per rank reads its t tails from ONE per-run
  * interpolation table, built on the side stream from the same series / continued fractions [default]; 0 = every edge
  * runs its own series / fraction; 2 = the table on every two-category lm call);

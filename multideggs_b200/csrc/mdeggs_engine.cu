@@ -1669,8 +1669,57 @@ int p2p_prepare(mdeggs_ctx* ctx, Shard& s) {
   return MDEGGS_OK;
 }
 
+
+// one process, several GPUs: the same push, with the peers' buffers addressed directly (peer access enabled once)
+int p2p_prepare_local(mdeggs_ctx* ctx) {
+  const int W = (int)ctx->shards.size();
+  Shard& s0 = ctx->shards[0];
+  for (Shard& s : ctx->shards) s.p2p.used = false;
+  if (!ctx->p2p || s0.p2p.failed || W < 2 || W > P2P_MAX) return MDEGGS_OK;
+  bool same = s0.p2p.ok;
+  for (Shard& s : ctx->shards) same = same && s.p2p.gen_p == s.p_edge.gen && s.p2p.gen_st == s.st8.gen;
+  if (same) return MDEGGS_OK;
+  auto fail = [&]() {
+    for (Shard& s : ctx->shards) s.p2p.ok = false;
+    s0.p2p.failed = true;
+    cudaGetLastError();
+    return MDEGGS_OK;
+  };
+  if (!s0.p2p.flags_ok) {
+    // (a wait kernel of one GPU is enqueued before the push kernels of the next ones: launches must not block)
+    if (cudaSetDevice(s0.device) != cudaSuccess || !launches_are_async(ctx, s0)) return fail();
+    for (int i = 0; i < W; ++i)
+      for (int j = 0; j < W; ++j) {
+        if (i == j) continue;
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, ctx->shards[i].device, ctx->shards[j].device) != cudaSuccess || !can) return fail();
+        if (cudaSetDevice(ctx->shards[i].device) != cudaSuccess) return fail();
+        const cudaError_t e = cudaDeviceEnablePeerAccess(ctx->shards[j].device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail();
+        cudaGetLastError();
+      }
+    for (Shard& s : ctx->shards) {
+      if (cudaSetDevice(s.device) != cudaSuccess || s.p2p_flags.ensure(64 * 4) != cudaSuccess ||
+          cudaMemset(s.p2p_flags.p, 0, 64 * 4) != cudaSuccess)
+        return fail();
+    }
+    for (Shard& s : ctx->shards) s.p2p.flags_ok = true;
+  }
+  for (Shard& s : ctx->shards) {
+    for (int r = 0; r < W; ++r) {
+      s.p2p.peer_p[r] = ctx->shards[r].p_edge.p;
+      s.p2p.peer_st[r] = ctx->shards[r].st8.p;
+      s.p2p.peer_flags[r] = ctx->shards[r].p2p_flags.p;
+    }
+    s.p2p.gen_p = s.p_edge.gen;
+    s.p2p.gen_st = s.st8.gen;
+    s.p2p.ok = true;
+  }
+  return MDEGGS_OK;
+}
+
 // all-gather of the per-rank edge blocks (p-values, status and whatever per-edge output was requested): peer-memory
-// push with one process per GPU (mdeggs_p2p.cuh), NCCL otherwise
+// push (mdeggs_p2p.cuh), NCCL as the fallback and for the optional per-edge outputs
 int run_collective(mdeggs_ctx* ctx, const mdeggs_problem* in, const mdeggs_result* out) {
   const int64_t E = in->E;
   Shard& s0 = ctx->shards[0];
@@ -1683,28 +1732,33 @@ int run_collective(mdeggs_ctx* ctx, const mdeggs_problem* in, const mdeggs_resul
       CU(s.st8.ensure((size_t)chunk * s0.world));
     }
     bool pushed = false;
-    if (ctx->shards.size() == 1) {
-      int rc = p2p_prepare(ctx, s0);
+    {
+      int rc = ctx->shards.size() == 1 ? p2p_prepare(ctx, s0) : p2p_prepare_local(ctx);
       if (rc) return rc;
-      if (s0.p2p.ok) {
-        Shard& s = s0;
-        PushArgs& A = s.p2p.args;
-        memset(&A, 0, sizeof A);
-        for (int r = 0; r < s.world; ++r) {
-          A.p_dst[r] = static_cast<double*>(s.p2p.peer_p[r]);
-          A.st_dst[r] = static_cast<int8_t*>(s.p2p.peer_st[r]);
-          A.flag_dst[r] = static_cast<unsigned int*>(s.p2p.peer_flags[r]);
+      if (ctx->p2p && s0.p2p.ok) {  // (option p2p = 0 keeps valid mappings but sends through NCCL)
+        for (Shard& s : ctx->shards) {  // every rank pushes its block ...
+          CU(cudaSetDevice(s.device));
+          PushArgs& A = s.p2p.args;
+          memset(&A, 0, sizeof A);
+          for (int r = 0; r < s.world; ++r) {
+            A.p_dst[r] = static_cast<double*>(s.p2p.peer_p[r]);
+            A.st_dst[r] = static_cast<int8_t*>(s.p2p.peer_st[r]);
+            A.flag_dst[r] = static_cast<unsigned int*>(s.p2p.peer_flags[r]);
+          }
+          A.status = s.status.as<int32_t>();
+          A.world = s.world;
+          A.rank = s.rank;
+          A.lo = (long long)((int64_t)s.rank * chunk < E ? (int64_t)s.rank * chunk : E);
+          A.n_own = (long long)(A.lo + chunk < E ? chunk : E - A.lo);
+          A.ctl = s.p2p_flags.as<unsigned int>() + 2 * P2P_MAX;
+          A.err = s.scal.as<int32_t>() + 2 * SC_ERR;
+          LAUNCH(k_push_gather, (unsigned)(s.sm_count * 4), 256, 0, s.s_main, A);
+          s.p2p.used = true;
         }
-        A.status = s.status.as<int32_t>();
-        A.world = s.world;
-        A.rank = s.rank;
-        A.lo = (long long)((int64_t)s.rank * chunk < E ? (int64_t)s.rank * chunk : E);
-        A.n_own = (long long)(A.lo + chunk < E ? chunk : E - A.lo);
-        A.ctl = s.p2p_flags.as<unsigned int>() + 2 * P2P_MAX;
-        A.err = s.scal.as<int32_t>() + 2 * SC_ERR;
-        LAUNCH(k_push_gather, (unsigned)(s.sm_count * 4), 256, 0, s.s_main, A);
-        LAUNCH(k_wait_gather, 1, 32, 0, s.s_main, A);
-        s.p2p.used = true;
+        for (Shard& s : ctx->shards) {  // ... and waits for everybody else's
+          CU(cudaSetDevice(s.device));
+          LAUNCH(k_wait_gather, 1, 32, 0, s.s_main, s.p2p.args);
+        }
         pushed = true;
       }
     }
@@ -2290,7 +2344,7 @@ int mdeggs_destroy(mdeggs_ctx* ctx) {
     cudaSetDevice(s.device);
     cudaDeviceSynchronize();
     if (s.h_stage) cudaFreeHost(s.h_stage);
-    for (int r = 0; r < P2P_MAX; ++r)
+    for (int r = 0; r < P2P_MAX && ctx->shards.size() == 1; ++r)  // (IPC mappings exist with one process per GPU only)
       if (r != s.rank) {
         if (s.p2p.peer_p[r]) cudaIpcCloseMemHandle(s.p2p.peer_p[r]);
         if (s.p2p.peer_st[r]) cudaIpcCloseMemHandle(s.p2p.peer_st[r]);
@@ -2398,7 +2452,7 @@ int mdeggs_submit_omic(mdeggs_ctx* ctx, const mdeggs_problem* in, mdeggs_result*
   ctx->trace_used = 0;
   const int src_device = ctx->shards[0].device;
   Shard& sh0 = ctx->shards[0];
-  sh0.p2p.used = false;
+  for (Shard& s : ctx->shards) s.p2p.used = false;
   // ---- phase A: inputs (eager) ----
   for (Shard& s : ctx->shards) {
     rc = stage_inputs(ctx, s, in, H, src_device);
@@ -2541,7 +2595,12 @@ int mdeggs_submit_omic(mdeggs_ctx* ctx, const mdeggs_problem* in, mdeggs_result*
   }
   // peer-memory all-gather: this rank no longer reads the gathered values (its outputs are out): the peers' next push
   // may overwrite them
-  if (sh0.p2p.used) LAUNCH(k_signal_done, 1, 32, 0, sh0.s_main, sh0.p2p.args);
+  for (Shard& s : ctx->shards)
+    if (s.p2p.used) {
+      CU(cudaSetDevice(s.device));
+      LAUNCH(k_signal_done, 1, 32, 0, s.s_main, s.p2p.args);
+    }
+  CU(cudaSetDevice(sh0.device));
   if (getenv("MDEGGS_HOSTTIME") && sh0.stamps.p) LAUNCH(k_stamp, 1, 1, 0, sh0.s_main, sh0.stamps.as<unsigned long long>() + 3);
   const auto t_host2 = std::chrono::steady_clock::now();
   for (size_t i = 1; i < ctx->shards.size(); ++i) {
@@ -2649,6 +2708,7 @@ int mdeggs_wait(mdeggs_ctx* ctx) {
   st.ms_h2d = ev_ms(s0.ev[EV_START], s0.ev[EV_H2D]);
   st.ms_d2h = ev_ms(s0.ev[EV_ADJ], s0.ev[EV_END]);
   if (ctx->pack.active) st.fit_path |= 0x2000;  // bit 13: the call ran on host-packed node rows (mdeggs_hostpack.h)
+  if (s0.p2p.used) st.fit_path |= 0x4000;       // bit 14: the p-value blocks were pushed over peer memory (mdeggs_p2p.cuh)
   if (use_bucket_order(ctx, in, n_nodes)) st.fit_path |= 0x200;  // bit 9: K8 ordering by p-value buckets (no radix sort)
   if (replayed) {  // graph replay: no stage boundaries inside the graph; everything between H2D and D2H is compute
     st.fit_path |= 0x100;  // bit 8 flags "replayed from a CUDA graph"
@@ -2689,18 +2749,22 @@ int mdeggs_set_option(mdeggs_ctx* ctx, const char* name, int64_t value) {
   }
   if (!strcmp(name, "h2d_pipeline")) {  // 0 off, 1 on (12 MB chunks), > 1: chunk size in MB
     ctx->h2d_pipeline = (int)value;
+    ctx->key_valid = false;  // (a captured compute graph has the choice baked in)
     return MDEGGS_OK;
   }
   if (!strcmp(name, "p2p")) {
     ctx->p2p = (int)value;
+    ctx->key_valid = false;
     return MDEGGS_OK;
   }
   if (!strcmp(name, "tail_spline")) {
     ctx->tail_spline = (int)value;
+    ctx->key_valid = false;
     return MDEGGS_OK;
   }
   if (!strcmp(name, "host_pack")) {
     ctx->host_pack = (int)value;
+    ctx->key_valid = false;
     return MDEGGS_OK;
   }
   if (!strcmp(name, "copy_streams")) {

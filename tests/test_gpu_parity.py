@@ -397,6 +397,14 @@ def test_single_process_multi_gpu_matches_one_gpu(engine):
         for k in a:
             assert np.array_equal(a[k], b[k], equal_nan=True), (K, method, k)
     assert eng2.stats()["n_ranks"] >= 2
+    assert int(eng2.stats()["fit_path"]) & 0x4000          # p-value blocks pushed over peer memory (mdeggs_p2p.cuh)
+    eng2.set_option("p2p", 0)                               # ... and the ncclAllGather path
+    prob = synth.random_problem(80, 60, 333, 2, 502, _abi.METHOD_LM, _abi.PADJ_BH)
+    a, b = engine.run_omic(prob, ALL_FIELDS), eng2.run_omic(prob, ALL_FIELDS)
+    assert not int(eng2.stats()["fit_path"]) & 0x4000
+    for k in a:
+        assert np.array_equal(a[k], b[k], equal_nan=True), k
+    eng2.set_option("p2p", 1)
     # best-percentile outputs only: the BH segments are sharded over the ranks and the counts all-reduced;
     # dense-tile path: every rank computes only the tile rows of its edge block
     want = _abi.DEFAULT_WANT

@@ -33,6 +33,9 @@ for G, n, E, K, method, padj in cases:                       # (growing and shri
         eng.set_option("p2p", p2p)
         for rep in range(4):                                 # eager, eager, capture + replay, replay
             got = eng.run_omic(prob, want)
+            if bool(int(eng.stats()["fit_path"]) & 0x4000) != bool(p2p):
+                ok = False
+                sys.stderr.write(f"[rank {rank}] case E={E} p2p={p2p} rep={rep}: fit_path {hex(int(eng.stats()['fit_path']))}\n")
             for k in want:
                 if not np.array_equal(got[k], ref[k], equal_nan=True):
                     ok = False
