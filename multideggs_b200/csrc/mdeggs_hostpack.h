@@ -46,8 +46,22 @@ inline void pack_unit(const PackJob& J, int u) {
   for (int col = col0; col < col1; ++col) {
     const double* __restrict__ sc = J.src + (size_t)col * J.ld_src;
     double* __restrict__ dc = J.dst + (size_t)col * J.ld_dst;
-    if (J.contiguous) {
-      memcpy(dc + r0, sc + rows[r0], (size_t)(r1 - r0) * 8);
+    if (J.contiguous) {  // a plain copy - with streaming stores as well: a cached memcpy reads the destination lines first
+      const double* __restrict__ s0 = sc + rows[r0];
+      int64_t i = r0;
+      if ((reinterpret_cast<uintptr_t>(dc + i) & 15) && i < r1) {
+        dc[i] = s0[i - r0];
+        ++i;
+      }
+      for (; i + 8 <= r1; i += 8) {
+        const __m128d a = _mm_loadu_pd(s0 + (i - r0)), b = _mm_loadu_pd(s0 + (i - r0) + 2);
+        const __m128d c = _mm_loadu_pd(s0 + (i - r0) + 4), d = _mm_loadu_pd(s0 + (i - r0) + 6);
+        _mm_stream_pd(dc + i, a);
+        _mm_stream_pd(dc + i + 2, b);
+        _mm_stream_pd(dc + i + 4, c);
+        _mm_stream_pd(dc + i + 6, d);
+      }
+      for (; i < r1; ++i) dc[i] = s0[i - r0];
       continue;
     }
     int64_t i = r0;
