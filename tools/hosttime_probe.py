@@ -1,5 +1,6 @@
+"""Host-side timing of the e2e call (MDEGGS_HOSTTIME=1): prep + enqueue, emit, sync; python tools/hosttime_probe.py"""
 import os, sys
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 os.environ["MDEGGS_HOSTTIME"] = "1"
 import torch, bench
 import multideggs_b200 as md
