@@ -16,6 +16,7 @@
 
 #include "mdeggs.h"
 #include "mdeggs_kernels.cuh"
+#include "mdeggs_front.cuh"  // warp_select_dbl: exact selection on doubles held in registers
 
 namespace mdeggs {
 
@@ -324,6 +325,7 @@ __global__ void __launch_bounds__(RlmRegWarps<ITEMS>::value * 32) k_fit_rlm_reg(
                                                      int32_t* __restrict__ iters, const int32_t* __restrict__ err) {
   extern __shared__ double smem[];  // per warp: A row, B row (npad doubles each)
   __shared__ unsigned long long s_cand[RlmRegWarps<ITEMS>::value][32];
+  __shared__ unsigned int s_ncand[RlmRegWarps<ITEMS>::value];
   if (*err) return;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   double* sa = smem + (size_t)wib * 2 * L.npad;
@@ -407,48 +409,29 @@ __global__ void __launch_bounds__(RlmRegWarps<ITEMS>::value * 32) k_fit_rlm_reg(
       slope[k] = sxy[k] / sxa[k];
       icpt[k] = mb[k] - slope[k] * ma[k];
     }
-    unsigned long long keys[ITEMS];
-    // every valid |r| key lies in [0, bits(+inf)]: the selection needs no min / max pass, it starts from its guess bracket
-    const unsigned long long kmin = 0ull, kmax = 0x7ff0000000000000ull;
-    auto residual_keys = [&]() {  // |b - icpt_c - slope_c a| as order-preserving bit patterns; padding -> ~0
+    // |residuals| of this lane's positions (NaN on padding: it compares false everywhere and sorts above everything)
+    double ares[ITEMS];
+    auto residual_keys = [&]() {  // |b - icpt_c - slope_c a|
 #pragma unroll
       for (int j = 0; j < ITEMS; ++j) {
-        unsigned long long k = ~0ull;
+        double r = nan("");
         if (vmask >> j & 1) {
           const int pos = lane + 32 * j;
           const int c = cmask >> j & 1;
-          const double r = sb[pos] - icpt[c] - slope[c] * sa[pos];
-          k = (unsigned long long)__double_as_longlong(fabs(r));
+          r = fabs(sb[pos] - icpt[c] - slope[c] * sa[pos]);
         }
-        keys[j] = k;
+        ares[j] = r;
       }
     };
-    // `guess` > 0: expected median of |r| (previous iteration's, or 0.6745 sd of the residuals at the start); the
-    // selection starts from the bracket guess * (1 -+ rel)
+    // `guess` > 0: expected median of |r| (previous iteration's, or 0.6745 sd of the residuals at the start); the exact
+    // selection (warp_select_dbl, mdeggs_front.cuh: FP64 compares, ballot quick-select among the last <= 32 candidates)
+    // starts from the bracket guess * (1 -+ rel)
     auto median_abs = [&](double guess, double rel) -> double {
-      unsigned long long g_lo = 0ull, g_hi = 0ull;
-      if (guess > 0.0 && isfinite(guess)) {
-        g_lo = (unsigned long long)__double_as_longlong(guess * (1.0 - rel));
-        g_hi = (unsigned long long)__double_as_longlong(guess * (1.0 + rel));
-      }
-      if (n & 1)
-        return __longlong_as_double((long long)warp_select_reg<ITEMS>(keys, n / 2, kmin, kmax, n, s_cand[wib], lane, g_lo, g_hi));
-      unsigned long long k1 = warp_select_reg<ITEMS>(keys, n / 2 - 1, kmin, kmax, n, s_cand[wib], lane, g_lo, g_hi);
-      int c_le = 0;
-      unsigned long long nxt = ~0ull;
-#pragma unroll
-      for (int j = 0; j < ITEMS; ++j) {
-        c_le += (keys[j] <= k1);
-        if (keys[j] > k1 && keys[j] < nxt) nxt = keys[j];
-      }
-      c_le = __reduce_add_sync(0xffffffffu, c_le);
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        unsigned long long other = __shfl_xor_sync(0xffffffffu, nxt, o);
-        nxt = other < nxt ? other : nxt;
-      }
-      unsigned long long k2 = (c_le > n / 2) ? k1 : nxt;
-      return __ddiv_rn(__dadd_rn(__longlong_as_double((long long)k1), __longlong_as_double((long long)k2)), 2.0);
+      const bool have = guess > 0.0 && isfinite(guess);
+      double k2 = 0.0;
+      const double k1 = warp_select_dbl<ITEMS>(ares, (n - 1) / 2, n, reinterpret_cast<double*>(s_cand[wib]), s_ncand + wib,
+                                               lane, have, guess * (1.0 - rel), guess * (1.0 + rel), !(n & 1), &k2);
+      return (n & 1) ? k1 : __ddiv_rn(__dadd_rn(k1, k2), 2.0);
     };
     double med_prev = 0.0;
     double scale = 0.0;
@@ -490,7 +473,7 @@ __global__ void __launch_bounds__(RlmRegWarps<ITEMS>::value * 32) k_fit_rlm_reg(
         const int pos = lane + 32 * j;
         const int c = cmask >> j & 1;
         // psi.huber weight pmin(1, k / |r / s|) with ONE division per sample: k s / |r|
-        const double ar = __longlong_as_double((long long)keys[j]);
+        const double ar = ares[j];
         const double w = (ar <= ks) ? 1.0 : ks * rcp_newton(ar);
         const double da = sa[pos] - ma[c], db = sb[pos] - mb[c];
         const double wda = w * da;
@@ -543,7 +526,7 @@ __global__ void __launch_bounds__(RlmRegWarps<ITEMS>::value * 32) k_fit_rlm_reg(
       if (!(vmask >> j & 1)) continue;
       const int pos = lane + 32 * j;
       const int c = cmask >> j & 1;
-      const double ar = __longlong_as_double((long long)keys[j]);
+      const double ar = ares[j];
       const double u = ar / scale;
       const double w = (u <= kh) ? 1.0 : (kh * scale) * rcp_newton(ar);
       const double rw = ar * w;
