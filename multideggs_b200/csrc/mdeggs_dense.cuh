@@ -294,12 +294,22 @@ __global__ void __launch_bounds__(DENSE_TMA_THREADS, 1)
     k_dense_tma(const __grid_constant__ CUtensorMap tmap, DenseLayout Lc, SegLayout L, int nn, int ntiles,
                 const unsigned int* __restrict__ tile_bits, double* __restrict__ S) {
   extern __shared__ unsigned char dn_raw[];
-  int ti = 0, rem = blockIdx.x;
-  while (rem >= ntiles - ti) {
-    rem -= ntiles - ti;
-    ++ti;
+  // blockIdx.x -> (ti, tj), ti <= tj: the off-diagonal pairs row by row, then the diagonal tiles.  A diagonal tile only
+  // needs its upper triangle (k_finish reads S[min][max]), so the two warps that own rows 64.. x columns ..63 idle
+  // there; with the diagonal units at the END of the grid the last, partial wave consists of these cheaper units.
+  const int n_off = ntiles * (ntiles - 1) / 2;
+  int ti, tj;
+  if ((int)blockIdx.x >= n_off) {
+    ti = tj = (int)blockIdx.x - n_off;
+  } else {
+    ti = 0;
+    int rem = blockIdx.x;
+    while (rem >= ntiles - 1 - ti) {
+      rem -= ntiles - 1 - ti;
+      ++ti;
+    }
+    tj = ti + 1 + rem;
   }
-  const int tj = ti + rem;
   if (tile_bits && !((tile_bits[(ti * ntiles + tj) >> 5] >> ((ti * ntiles + tj) & 31)) & 1u)) return;
   const int k = blockIdx.y;
   if (L.cnt[k] == 0) return;
@@ -355,12 +365,13 @@ __global__ void __launch_bounds__(DENSE_TMA_THREADS, 1)
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+  const bool idle = diag && wrow >= 64 && wcol == 0;  // (lower-left quadrant of a diagonal tile: never read)
   for (int st = 0; st < nst; ++st) {
     const int slot = st % DSTAGES, use = st / DSTAGES;
     dn_mbar_wait(bar0 + 8 * slot, (uint32_t)use & 1u);
     const uint32_t stg = sb + (uint32_t)slot * 2 * DTILE_BYTES;
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < 2 && !idle; ++h) {
       const uint32_t sw = h ? swz1 : swz0;
       double2 a[4], b[8];
 #pragma unroll
@@ -387,6 +398,7 @@ __global__ void __launch_bounds__(DENSE_TMA_THREADS, 1)
     __syncwarp();
     if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar0 + 8 * (DSTAGES + slot)) : "memory");
   }
+  if (idle) return;
   double* Sk = S + (size_t)k * nn * nn;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
